@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Headline benchmark: agent-steps/sec of the batched env rollout hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+One "step" = one pass of the rollout hot path over one batch: T lockstep env steps of n_envs
+Checkers-v0 instances written straight into the rollout buffer (`mm_checkers_rollout`, one launch)
+followed by the GAE/return reverse scan over that buffer (`mm_gae_returns`, one launch).  Actions are
+synthetic (uniform in [0,5), seed 42) and resident in HBM before the timed region.  Every rank owns
+its own env shard (no data-path collective): scaling is weak.
+
+Workloads (per GPU):
+  mappo_rollout_16384x128  BASELINE.json configs[2]: 16 384 envs x T=128, A=2, D=47 (default; the
+                           configuration the agent-steps/sec metric and its roofline are quoted on)
+  qmix_rollout_4096x100    BASELINE.json configs[1]: 4 096 envs x T=100 (episode written to replay slots)
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference env
+(oracle/, pure Python like ma-gym itself) on all host cores instead.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "mappo_rollout_16384x128": dict(n_envs=16384, T=128, full_observable=False, max_steps=100),
+    "qmix_rollout_4096x100": dict(n_envs=4096, T=100, full_observable=False, max_steps=100),
+}
+AGENTS = 2
+# algorithmic bytes per env-step (D=47): actions 8 + state 40 r + 40 w + obs 376 + rew 8 + done 2
+ENV_STEP_BYTES = 474
+GAE_BYTES_PER_ELEM = 16
+METRIC = "agent-steps/sec batched env rollout"
+UNIT = "agent-steps/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.gpu = gpu_index
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def _py_env_worker(args):
+    n_envs, steps, seed, max_steps = args
+    import random
+    from oracle.ma_gym_ref import CheckersRef
+    rnd = random.Random(seed)
+    envs = [CheckersRef(full_observable=False, max_steps=max_steps) for _ in range(n_envs)]
+    for e in envs:
+        e.reset()
+    t0 = time.perf_counter()
+    for s in range(steps):
+        if s % max_steps == 0 and s:
+            for e in envs:
+                e.reset()
+        for e in envs:
+            e.step([rnd.randrange(5), rnd.randrange(5)])
+    return n_envs * steps, time.perf_counter() - t0
+
+
+def cpu_python_port(cores, budget_s, max_steps=100):
+    """Reference-style CPU rollout: the pure-Python env restatement, one process per core."""
+    import multiprocessing as mp
+    n, s = 8, 200
+    cnt, dt = _py_env_worker((n, s, 0, max_steps))           # calibrate on one core
+    rate1 = cnt / dt
+    steps = max(100, int(rate1 * budget_s / n))
+    if cores == 1:
+        cnt, dt = _py_env_worker((n, steps, 1, max_steps))
+        return cnt * AGENTS / dt, f"{n} envs x {steps} steps, random actions, 1 process"
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_py_env_worker, [(n, steps, 100 + i, max_steps) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    return total * AGENTS / wall, f"{cores} processes x {n} envs x {steps} steps, random actions"
+
+
+def cpu_c_port(budget_s, n_envs=4096, max_steps=100):
+    """The C restatement (oracle/magym_ref.c) on one core -- a much faster CPU than the reference has."""
+    import numpy as np
+    from oracle.magym_c import CheckersBatchRef
+    ref = CheckersBatchRef(n_envs, False, max_steps, -0.01, auto_reset=True)
+    ref.reset()
+    rng = np.random.default_rng(0)
+    acts = rng.integers(0, 5, size=(16, n_envs, 2), dtype=np.int32)
+    steps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        ref.step(acts[steps % 16])
+        steps += 1
+    return n_envs * steps * AGENTS / (time.perf_counter() - t0)
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    for _ in range(args.warmup):
+        cpu_python_port(cores, 0.5)
+    sample = ""
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, sample = cpu_python_port(cores, 2.0)
+        vals.append(v)
+    value = statistics.mean(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": (time.perf_counter() - t0) * 1e3 / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32",
+        "data": "synthetic", "config": {"workload": args.workload, **wl, "agents": AGENTS,
+                                          "note": "pure-Python env restatement (ma-gym is pure Python), "
+                                                  "each step a bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import minimarl_b200
+    from minimarl_b200.ops import gae_returns
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: minimarl_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, T, A = wl["n_envs"], wl["T"], AGENTS
+    D = 47 * (2 if wl["full_observable"] else 1)
+    env = minimarl_b200.BatchedCheckers(n, full_observable=wl["full_observable"], max_steps=wl["max_steps"],
+                                        step_cost=-0.01, device=dev)
+    # rollout buffer laid out like SharedReplayBuffer (mappo/runner/shared/shared_buffer.py:48-77)
+    obs = torch.zeros((T + 1, n, A, D), device=dev)
+    rewards = torch.zeros((T, n, A, 1), device=dev)
+    dones = torch.zeros((T, n, A), dtype=torch.uint8, device=dev)
+    value_preds = torch.randn((T + 1, n, A, 1), device=dev, generator=torch.Generator(dev).manual_seed(42 + rank))
+    masks = torch.ones((T + 1, n, A, 1), device=dev)
+    returns = torch.zeros((T + 1, n, A, 1), device=dev)
+    advantages = torch.zeros((T, n, A, 1), device=dev)
+    actions = torch.randint(0, 5, (T, n, A), dtype=torch.int32, device=dev,
+                            generator=torch.Generator(dev).manual_seed(42 + rank))
+
+    def step():
+        env.reset(out=obs[0])
+        env.rollout(T, actions=actions, out=(obs[1:], rewards.view(T, n, A), dones))
+        gae_returns(rewards, value_preds, masks, returns, 0.99, 0.95, use_gae=True,
+                    denorm=(1.1401754, 0.1), advantages=advantages)
+    launches_per_step = 3
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    start.record()
+    for k in range(args.steps):
+        env.reset(out=obs[0])
+        ev[3 * k].record()
+        env.rollout(T, actions=actions, out=(obs[1:], rewards.view(T, n, A), dones))
+        ev[3 * k + 1].record()
+        gae_returns(rewards, value_preds, masks, returns, 0.99, 0.95, use_gae=True,
+                    denorm=(1.1401754, 0.1), advantages=advantages)
+        ev[3 * k + 2].record()
+    end.record()
+    sync_all()
+    ms_total = start.elapsed_time(end)
+    rollout_ms = statistics.mean(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps))
+    gae_ms = statistics.mean(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(args.steps))
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+
+    agent_steps_per_step = n * T * A * world
+    value = agent_steps_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: the list/numpy-facing env API with HOST buffers, copies inside the timed region ----
+    e2e_steps = min(T, 32)
+    host_acts = actions[:e2e_steps].cpu().numpy()
+    env.reset()
+    for t in range(3):
+        env.step_host(host_acts[t])
+    sync_all()
+    t0 = time.perf_counter()
+    for t in range(e2e_steps):
+        o_h, r_h, d_h = env.step_host(host_acts[t])      # H2D actions, kernel, D2H obs/rew/done, sync
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = n * A * e2e_steps * world / e2e_s
+
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        achieved = n * T * ENV_STEP_BYTES / (rollout_ms * 1e-3) / 1e9
+        gae_achieved = n * T * A * (GAE_BYTES_PER_ELEM + 4) / (gae_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(args.workload, {}).get("checkers_rollout_kernel")
+        cores = os.cpu_count() or 1
+        cpu_v, cpu_sample = cpu_python_port(1, args.cpu_seconds)
+        cpu_c = cpu_c_port(min(2.0, args.cpu_seconds))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32", "data": "synthetic",
+            "config": {"workload": args.workload, "n_envs_per_gpu": n, "T": T, "agents": A, "obs_dim": D,
+                       "env": "Checkers-v0", "actions": "uniform int32 [0,5) seed 42, resident in HBM",
+                       "step": "reset + T-step rollout into the rollout buffer + GAE/advantages",
+                       "l2": f"outputs {n * T * ENV_STEP_BYTES / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"
+                       if n * T * ENV_STEP_BYTES > 126e6 else "working set below L2; buffer rewritten every step",
+                       "parallelism": f"env-shard x{world}, no data-path collective"},
+            "roofline": {"bound": "hbm", "kernel": "checkers_rollout_kernel", "achieved": achieved, "peak": peak,
+                         "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": n * T * ENV_STEP_BYTES, "kernel_ms": rollout_ms},
+            "roofline_gae": {"bound": "hbm", "kernel": "gae_kernel", "achieved": gae_achieved, "peak": peak,
+                             "unit": "GB/s", "frac": gae_achieved / peak, "kernel_ms": gae_ms,
+                             "algorithmic_bytes_per_launch": n * T * A * (GAE_BYTES_PER_ELEM + 4)},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample,
+                             "host_cores": cores, "c_port_1core": cpu_c},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step,
+                    "d2h_bytes_per_step": env.d2h_bytes_per_step,
+                    "api": "BatchedCheckers.step_host(numpy actions) -> numpy obs/rewards/dones, one env step per call"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mappo_rollout_16384x128", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU time spent on the cpu_baseline sample")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

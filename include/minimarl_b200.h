@@ -1,0 +1,136 @@
+/*
+ * minimarl_b200 -- C ABI of libminimarl_b200.so (sm_100a kernels behind mini-marl's Python surface).
+ *
+ * mini-marl has no plugin/FFI interface of its own: the boundary is its Python call
+ * surface.  Each entry point below names the reference callable (file:line under
+ * singforai/mini-marl) whose arithmetic it replaces.  The Python package `minimarl_b200` binds
+ * these symbols with ctypes (INTEGRATION.md shows the stub) and mirrors the reference's classes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`;
+ *     the library never allocates or frees tensor memory and keeps no global mutable state;
+ *   - every call is asynchronous and ordered on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 (MM_OK) on success, a negative mm_status on a bad argument or a failed
+ *     launch; `mm_status_string` / `mm_last_cuda_error` give the message the wrapper raises;
+ *   - row-major tensors; N = lockstep env instances, A = agents, D = per-agent obs length,
+ *     T = rollout length, R = N*A rows.
+ */
+#ifndef MINIMARL_B200_H_
+#define MINIMARL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum mm_status {
+    MM_OK = 0,
+    MM_ERR_BAD_ARG = -1,     /* null pointer, non-positive size, unsupported shape */
+    MM_ERR_LAUNCH = -2,      /* cudaGetLastError() != cudaSuccess after the launch */
+    MM_ERR_UNSUPPORTED = -3  /* shape outside what the kernel was built for */
+} mm_status;
+
+const char* mm_status_string(int status);
+const char* mm_last_cuda_error(void);   /* cudaGetErrorString of the last failed launch (thread-local) */
+int mm_version(void);                   /* ABI version, bumped on any signature change */
+
+/* ------------------------------------------------------------------------------------------------
+ * Checkers-v0 (ma-gym 0.0.14 `Checkers`, un-vendored; call sites vdn/main.py:61-64,83,93,
+ * mappo/runner/shared/magym_runner.py:52-57,98,108, offpolicy/runner/shared/magym_runner.py:55,97).
+ *
+ * Env state is structure-of-arrays: `state` points at MM_CHECKERS_STATE_WORDS planes of n_envs
+ * uint32 each (plane p of env e at state[p * n_envs + e]):
+ *   plane 0  food bitmap, bit (row*8+col) set while the cell still holds its apple/lemon
+ *            (apple iff (row+col) even); bit 31 = "episode finished" latch (ma-gym's
+ *            steps_beyond_done is not None)
+ *   plane 1  agent cells, 8 bits per agent (row*8+col), agent 0 in the low byte
+ *   plane 2  step_count
+ * ---------------------------------------------------------------------------------------------- */
+#define MM_CHECKERS_STATE_WORDS 3
+#define MM_CHECKERS_AGENTS 2
+#define MM_CHECKERS_OBS_DIM 47   /* 2 + 3*3*5; full_observable doubles it */
+
+typedef struct mm_checkers_cfg {
+    int32_t n_envs;
+    int32_t max_steps;
+    int32_t full_observable;  /* 0: obs [N,2,47]; 1: every agent gets concat(obs_0, obs_1): [N,2,94] */
+    int32_t auto_reset;       /* 1: an env that finishes is reset inside the same step and the obs
+                                 written is the reset obs (reference never auto-resets: default 0) */
+    float reward[2][3];       /* [agent][0 none, 1 lemon, 2 apple] = float32(step_cost (+/- food)) */
+    float pos_row[3];         /* float32(round(r / 3, 2)) */
+    float pos_col[8];         /* float32(round(c / 7, 2)) */
+} mm_checkers_cfg;
+
+/* env.reset() for every env (reset_mask == NULL) or for the envs whose mask byte is non-zero.
+ * obs may be NULL (state only). */
+int mm_checkers_reset(uint32_t* state, const uint8_t* reset_mask, float* obs,
+                      const mm_checkers_cfg* cfg_host, void* stream);
+
+/* One lockstep env.step(actions) over all envs.
+ *   actions [N,2] int32 in [0,5)  (0 down, 1 left, 2 up, 3 right, 4 no-op)
+ *   obs     [N,2,D] float32, rewards [N,2] float32, dones [N,2] uint8
+ *   bad_action_flag: optional int32[1]; set to 1 if any action was outside [0,5) (the reference
+ *   raises Exception('Action Not found!'); such an action is executed as a no-op here).
+ * obs/rewards/dones may point straight into a rollout or replay buffer slot (zero-copy insert). */
+int mm_checkers_step(uint32_t* state, const int32_t* actions, float* obs, float* rewards,
+                     uint8_t* dones, int32_t* bad_action_flag,
+                     const mm_checkers_cfg* cfg_host, void* stream);
+
+/* T lockstep steps in one launch, state held in registers between steps.
+ *   actions [T,N,2] int32, or NULL to draw them uniformly on the device (Philox4x32-10 keyed by
+ *   (seed, env, agent), counter = step_offset + t); drawn actions are written to actions_out
+ *   [T,N,2] when it is not NULL.
+ *   obs [T,N,2,D] (obs after step t), rewards [T,N,2], dones [T,N,2]; any of the three may be
+ *   NULL to skip that output.  Strides between consecutive t are the natural ones. */
+int mm_checkers_rollout(uint32_t* state, const int32_t* actions, int32_t* actions_out,
+                        float* obs, float* rewards, uint8_t* dones, int32_t* bad_action_flag,
+                        int32_t T, uint64_t seed, uint64_t step_offset,
+                        const mm_checkers_cfg* cfg_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Switch{2,4}-v0 (ma-gym 0.0.14 `Switch`, un-vendored; qmix default env, qmix/_config.py:13-18,
+ * qmix/main.py:66-71).  State planes: 0 = agent cells (8 bits per agent), 1 = per-agent done bits,
+ * 2 = step_count.
+ * ---------------------------------------------------------------------------------------------- */
+#define MM_SWITCH_STATE_WORDS 3
+
+typedef struct mm_switch_cfg {
+    int32_t n_envs;
+    int32_t n_agents;         /* 2..4 */
+    int32_t max_steps;
+    int32_t full_observable;
+    int32_t clock;            /* 1: obs carries step_count/max_steps (ma-gym default) */
+    float step_cost;          /* float32(step_cost) */
+    float goal_reward;        /* float32(5) */
+    float pos_row[3];         /* float32(round(r / 2, 2)) */
+    float pos_col[7];         /* float32(round(c / 6, 2)) */
+} mm_switch_cfg;
+
+int mm_switch_reset(uint32_t* state, const uint8_t* reset_mask, float* obs,
+                    const mm_switch_cfg* cfg_host, void* stream);
+int mm_switch_step(uint32_t* state, const int32_t* actions, float* obs, float* rewards,
+                   uint8_t* dones, int32_t* bad_action_flag,
+                   const mm_switch_cfg* cfg_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GAE / returns reverse scan: SharedReplayBuffer.compute_returns
+ * (mappo/runner/shared/shared_buffer.py:131-157) with ValueNorm.denormalize folded in
+ * (mappo/utils/valuenorm.py:67-78).
+ *   rewards [T,R], value_preds [T+1,R] (value_preds[T] must already hold next_value),
+ *   masks [T+1,R], returns [T+1,R] (rows 0..T-1 written; use_gae==0 also reads returns[T]).
+ *   denorm_scale/denorm_shift: sqrt(var) and mean of the value normaliser, or 1/0 when neither
+ *   PopArt nor ValueNorm is on.  advantages (optional, [T,R]) = returns - denorm(value_preds).
+ *   gamma / gae_lambda are the reference's Python floats (doubles).  The arithmetic follows the
+ *   reference's mixed precision operation by operation: delta in float32, the gae accumulator in
+ *   float64, the stored return rounded to float32.
+ * ---------------------------------------------------------------------------------------------- */
+int mm_gae_returns(const float* rewards, const float* value_preds, const float* masks,
+                   float* returns, float* advantages, int32_t T, int64_t R,
+                   double gamma, double gae_lambda, int32_t use_gae, int32_t use_denorm,
+                   float denorm_scale, float denorm_shift, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* MINIMARL_B200_H_ */

@@ -1,0 +1,90 @@
+"""ctypes binding of libminimarl_b200.so -- the only way Python reaches the CUDA kernels.
+
+The argument lists below restate ``include/minimarl_b200.h``; ``tests/test_abi.py`` checks that
+every symbol the header declares is exported and bound.  Nothing here touches the GPU at import
+time, so the binding also loads on a CPU-only box; compute calls need CUDA tensors.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libminimarl_b200.so")
+
+MM_OK = 0
+
+
+class CheckersCfg(C.Structure):
+    """struct mm_checkers_cfg"""
+    _fields_ = [
+        ("n_envs", C.c_int32), ("max_steps", C.c_int32), ("full_observable", C.c_int32),
+        ("auto_reset", C.c_int32), ("reward", (C.c_float * 3) * 2), ("pos_row", C.c_float * 3),
+        ("pos_col", C.c_float * 8),
+    ]
+
+
+class SwitchCfg(C.Structure):
+    """struct mm_switch_cfg"""
+    _fields_ = [
+        ("n_envs", C.c_int32), ("n_agents", C.c_int32), ("max_steps", C.c_int32),
+        ("full_observable", C.c_int32), ("clock", C.c_int32), ("step_cost", C.c_float),
+        ("goal_reward", C.c_float), ("pos_row", C.c_float * 3), ("pos_col", C.c_float * 7),
+    ]
+
+
+_P = C.c_void_p
+SIGNATURES = {
+    "mm_status_string": (C.c_char_p, [C.c_int]),
+    "mm_last_cuda_error": (C.c_char_p, []),
+    "mm_version": (C.c_int, []),
+    "mm_checkers_reset": (C.c_int, [_P, _P, _P, C.POINTER(CheckersCfg), _P]),
+    "mm_checkers_step": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(CheckersCfg), _P]),
+    "mm_checkers_rollout": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_uint64, C.c_uint64,
+                                      C.POINTER(CheckersCfg), _P]),
+    "mm_switch_reset": (C.c_int, [_P, _P, _P, C.POINTER(SwitchCfg), _P]),
+    "mm_switch_step": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(SwitchCfg), _P]),
+    "mm_gae_returns": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_double, C.c_double,
+                                 C.c_int32, C.c_int32, C.c_float, C.c_float, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m minimarl_b200.build` "
+                "(minimarl_b200 has no CPU fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(status):
+    if status != MM_OK:
+        l = lib()
+        msg = l.mm_status_string(status).decode()
+        if status == -2:
+            msg += ": " + l.mm_last_cuda_error().decode()
+        raise RuntimeError(f"minimarl_b200: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (or NULL for None); refuses host tensors."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("minimarl_b200 kernels take CUDA tensors; got a CPU tensor (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("minimarl_b200 kernels take contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
