@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference modules from /root/reference.
+
+Run in the build container only (the reference tree does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference imports `gym` (not installed here) for space classes only; a ~20-line stub stands in.
+Every fixture stores the seeded inputs, the network weights (state_dict) and the reference outputs, so
+the tests can rebuild the same computation through the oracle and through the CUDA path.
+"""
+import argparse
+import importlib
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+# ---------------------------------------------------------------------------------------------------
+def install_gym_stub():
+    gym = types.ModuleType("gym")
+    spaces = types.ModuleType("gym.spaces")
+    space_mod = types.ModuleType("gym.spaces.space")
+
+    class Space:
+        pass
+
+    class Box(Space):
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.low, self.high = np.asarray(low, dtype=dtype), np.asarray(high, dtype=dtype)
+            self.shape = self.low.shape if shape is None else shape
+            self.dtype = dtype
+
+    class Discrete(Space):
+        def __init__(self, n):
+            self.n, self.shape = n, ()
+
+    class MultiDiscrete(Space):
+        pass
+
+    class Tuple(Space):
+        pass
+
+    space_mod.Space = Space
+    spaces.Box, spaces.Discrete, spaces.Tuple, spaces.MultiDiscrete, spaces.Space = Box, Discrete, Tuple, MultiDiscrete, Space
+    spaces.space = space_mod
+    gym.spaces, gym.Space = spaces, Space
+    sys.modules.update({"gym": gym, "gym.spaces": spaces, "gym.spaces.space": space_mod})
+    return Box, Discrete
+
+
+class ref_package:
+    """Puts one reference package dir first on sys.path (its imports are CWD-relative) and drops the
+    modules it loaded on exit so the next package's `utils`, `algorithms`... do not collide."""
+
+    def __init__(self, name):
+        self.dir = os.path.join(REF, name)
+
+    def __enter__(self):
+        self.before = set(sys.modules)
+        sys.path.insert(0, self.dir)
+        return self
+
+    def __exit__(self, *exc):
+        sys.path.remove(self.dir)
+        for m in set(sys.modules) - self.before:
+            f = getattr(sys.modules[m], "__file__", None) or ""
+            if f.startswith(REF):
+                del sys.modules[m]
+
+
+def sd_numpy(module, prefix=""):
+    return {prefix + k: v.detach().cpu().numpy() for k, v in module.state_dict().items()}
+
+
+# ---------------------------------------------------------------------------------------------------
+def golden_gae():
+    """SharedReplayBuffer.compute_returns (mappo/runner/shared/shared_buffer.py:131-157)."""
+    Box, Discrete = install_gym_stub()
+    with ref_package("mappo"):
+        from runner.shared.shared_buffer import SharedReplayBuffer
+        from utils.valuenorm import ValueNorm
+        out = {}
+        for tag, (T, B, A, use_gae, use_vn) in {
+            "vn": (16, 8, 2, True, True), "plain": (16, 8, 2, True, False), "nogae": (16, 8, 2, False, False),
+            "long": (100, 32, 2, True, True),
+        }.items():
+            rng = np.random.default_rng(hash(tag) % 1000)
+            args = argparse.Namespace(use_gae=use_gae, use_popart=False, use_valuenorm=use_vn, hidden_size=32,
+                                      recurrent_N=1, max_step=T, batch_size=B, gamma=0.99, gae_lambda=0.95)
+            space = Box(np.zeros(47), np.ones(47))
+            buf = SharedReplayBuffer(args, A, space, space, Discrete(5))
+            buf.rewards[:] = rng.standard_normal(buf.rewards.shape).astype(np.float32)
+            buf.value_preds[:] = rng.standard_normal(buf.value_preds.shape).astype(np.float32)
+            buf.masks[:] = (rng.random(buf.masks.shape) < 0.9).astype(np.float32)
+            next_value = rng.standard_normal((B, A, 1)).astype(np.float32)
+            vn = None
+            scale = shift = np.float32(0)
+            if use_vn:
+                vn = ValueNorm(1)
+                for _ in range(3):
+                    vn.update(torch.from_numpy(rng.standard_normal((64, 1)).astype(np.float32) * 3 + 0.7))
+                mean, var = vn.running_mean_var()
+                scale, shift = torch.sqrt(var).numpy()[0], mean.numpy()[0]
+            out[f"{tag}_rewards"] = buf.rewards.copy()
+            out[f"{tag}_masks"] = buf.masks.copy()
+            out[f"{tag}_next_value"] = next_value
+            out[f"{tag}_value_preds_in"] = buf.value_preds.copy()
+            buf.compute_returns(next_value, vn)
+            out[f"{tag}_returns"] = buf.returns.copy()
+            out[f"{tag}_denorm"] = np.array([scale, shift], dtype=np.float32)
+            out[f"{tag}_flags"] = np.array([use_gae, use_vn], dtype=np.int32)
+            if use_gae:
+                adv = buf.returns[:-1] - (vn.denormalize(buf.value_preds[:-1]) if vn else buf.value_preds[:-1])
+                out[f"{tag}_advantages"] = adv.astype(np.float32)
+        np.savez_compressed(os.path.join(OUT, "gae.npz"), **out)
+        print("gae.npz", len(out), "arrays")
+
+
+def offpolicy_args(**over):
+    from config import get_config
+    args = get_config().parse_known_args([])[0]
+    for k, v in over.items():
+        setattr(args, k, v)
+    return args
+
+
+def golden_segment_tree_and_per():
+    """SumSegmentTree / MinSegmentTree / PrioritizedRecReplayBuffer (offpolicy/utils/segment_tree.py,
+    rec_buffer.py:243-324)."""
+    Box, Discrete = install_gym_stub()
+    with ref_package("offpolicy"):
+        from utils.segment_tree import SumSegmentTree, MinSegmentTree
+        from utils.rec_buffer import PrioritizedRecReplayBuffer
+        rng = np.random.default_rng(7)
+        out = {}
+        cap = 64
+        st, mt = SumSegmentTree(cap), MinSegmentTree(cap)
+        pri = rng.random(50) + 0.01
+        st[np.arange(50)] = pri
+        mt[np.arange(50)] = pri
+        # scattered update with duplicates of parents
+        idx = np.array([3, 4, 17, 18, 19, 49])
+        newp = rng.random(6) * 2 + 0.01
+        st[idx] = newp
+        mt[idx] = newp
+        out["tree_values"] = st._value.copy()
+        out["min_values"] = mt._value.copy()
+        mass = rng.random(200) * st.sum(0, 49)
+        out["tree_mass"] = mass
+        out["tree_idx"] = st.find_prefixsum_idx(mass)
+        out["tree_sum_0_49"] = np.array(st.sum(0, 49))
+        out["tree_min"] = np.array(mt.min())
+
+        # full PER buffer: insert episodes, update priorities, sample with recorded uniforms
+        T, A, D, nA, size = 6, 2, 47, 5, 24
+        obs_space, act_space = Box(np.zeros(D), np.ones(D)), Discrete(nA)
+        share_space = Box(np.zeros(A * D), np.ones(A * D))
+        info = {"policy_0": {"obs_space": obs_space, "share_obs_space": share_space, "act_space": act_space}}
+        buf = PrioritizedRecReplayBuffer(0.6, info, {"policy_0": [0, 1]}, size, T, True, False)
+        eps = []
+        for it in range(5):
+            n = 7
+            ep = dict(
+                obs=rng.random((T + 1, n, A, D)).astype(np.float32),
+                share_obs=rng.random((T + 1, n, A, A * D)).astype(np.float32),
+                acts=np.eye(nA, dtype=np.float32)[rng.integers(0, nA, (T, n, A))],
+                rewards=rng.standard_normal((T, n, A, 1)).astype(np.float32),
+                dones=(rng.random((T, n, A, 1)) < 0.1).astype(np.float32),
+                dones_env=(rng.random((T, n, 1)) < 0.1).astype(np.float32))
+            eps.append(ep)
+            idx_range = buf.insert(n, {"policy_0": ep["obs"]}, {"policy_0": ep["share_obs"]}, {"policy_0": ep["acts"]},
+                                   {"policy_0": ep["rewards"]}, {"policy_0": ep["dones"]}, {"policy_0": ep["dones_env"]})
+            out[f"per_insert{it}_idx"] = idx_range
+            for k, v in ep.items():
+                out[f"per_insert{it}_{k}"] = v
+            if it >= 1:
+                upd_idx = rng.choice(len(buf), 5, replace=False)
+                upd_p = rng.random(5) * 3 + 0.05
+                buf.update_priorities(upd_idx, upd_p, "policy_0")
+                out[f"per_update{it}_idx"], out[f"per_update{it}_p"] = upd_idx, upd_p
+        out["per_sum_tree"] = buf._it_sums["policy_0"]._value.copy()
+        out["per_min_tree"] = buf._it_mins["policy_0"]._value.copy()
+        out["per_max_priority"] = np.array(buf.max_priorities["policy_0"])
+        out["per_len"] = np.array(len(buf))
+        u = rng.random(8)
+        state = np.random.get_state()
+        np.random.seed(0)
+        orig = np.random.random
+        np.random.random = lambda size=None: u      # record the uniforms the sampler consumes
+        try:
+            s = buf.sample(8, beta=0.4, p_id="policy_0")
+        finally:
+            np.random.random = orig
+            np.random.set_state(state)
+        out["per_sample_u"] = u
+        names = ["obs", "share_obs", "acts", "rewards", "dones", "dones_env"]
+        for k, v in zip(names, s[:6]):
+            out[f"per_sample_{k}"] = v["policy_0"]
+        out["per_sample_weights"], out["per_sample_idx"] = s[7], s[8]
+        np.savez_compressed(os.path.join(OUT, "per.npz"), **out)
+        print("per.npz", len(out), "arrays")
+
+
+def golden_offpolicy_nets():
+    """AgentQFunction / QMixer / VDNMixer forward and one QMix.train_policy_on_batch
+    (offpolicy/algorithms/qmix/*)."""
+    Box, Discrete = install_gym_stub()
+    with ref_package("offpolicy"):
+        torch.manual_seed(3)
+        np.random.seed(3)
+        from algorithms.qmix.algorithm.QMixPolicy import QMixPolicy
+        from algorithms.qmix.qmix import QMix
+        from algorithms.vdn.algorithm.vdn_mixer import VDNMixer
+        T, B, A, D, nA = 12, 6, 2, 47, 5
+        args = offpolicy_args(episode_length=T, batch_size=B, use_per=True, algorithm_name="qmix")
+        dev = torch.device("cpu")
+        obs_space, act_space = Box(np.zeros(D), np.ones(D)), Discrete(nA)
+        pconf = {"cent_obs_dim": A * D, "cent_act_dim": A * nA, "obs_space": obs_space,
+                 "share_obs_space": Box(np.zeros(A * D), np.ones(A * D)), "act_space": act_space}
+        config = {"args": args, "device": dev, "num_agents": A}
+        policy = QMixPolicy(args, config, pconf)
+        policies = {"policy_0": policy}
+        trainer = QMix(args, A, B, policies, lambda a: "policy_0", device=dev, episode_length=T)
+        # perturb LayerNorm affine / biases so that they are exercised (they initialise to 1 / 0)
+        with torch.no_grad():
+            for m in [policy.q_network, trainer.mixer]:
+                for name, p in m.named_parameters():
+                    if p.dim() == 1:
+                        p.add_(0.1 * torch.randn_like(p))
+            trainer.target_policies["policy_0"].q_network.load_state_dict(policy.q_network.state_dict())
+            for p in trainer.target_policies["policy_0"].q_network.parameters():
+                p.add_(0.01 * torch.randn_like(p))
+            trainer.target_mixer.load_state_dict(trainer.mixer.state_dict())
+            for p in trainer.target_mixer.parameters():
+                p.add_(0.01 * torch.randn_like(p))
+        rng = np.random.default_rng(11)
+        obs = rng.random((A, T + 1, B, D)).astype(np.float32)
+        share_obs = rng.random((T + 1, B, A * D)).astype(np.float32)
+        act_idx = rng.integers(0, nA, (A, T, B))
+        acts = np.eye(nA, dtype=np.float32)[act_idx]
+        rewards = rng.standard_normal((A, T, B, 1)).astype(np.float32)
+        dones = np.zeros((A, T, B, 1), dtype=np.float32)
+        dones_env = np.zeros((T, B, 1), dtype=np.float32)
+        for b in range(B):
+            end = rng.integers(T // 2, T + 1)
+            dones_env[end - 1:, b] = 1.0
+        weights = (rng.random(B) * 0.8 + 0.2).astype(np.float64)
+        idxes = np.arange(B)
+        out = dict(obs=obs, share_obs=share_obs, acts=acts, rewards=rewards, dones=dones, dones_env=dones_env,
+                   weights=weights, gamma=np.array(args.gamma), per_nu=np.array(args.per_nu),
+                   per_eps=np.array(args.per_eps), max_grad_norm=np.array(args.max_grad_norm))
+        out.update(sd_numpy(policy.q_network, "q."))
+        out.update(sd_numpy(trainer.target_policies["policy_0"].q_network, "tq."))
+        out.update(sd_numpy(trainer.mixer, "mix."))
+        out.update(sd_numpy(trainer.target_mixer, "tmix."))
+
+        # forward pieces
+        stacked_obs = torch.cat(list(torch.from_numpy(obs)), dim=-2)            # [T+1, A*B, D]
+        with torch.no_grad():
+            q_all, h_final = policy.q_network(stacked_obs, policy.init_hidden(-1, A * B))
+            out["q_all"], out["h_final"] = q_all.numpy(), h_final.numpy()
+            q1, h1 = policy.q_network(stacked_obs[0], torch.zeros(A * B, args.hidden_size))
+            out["q_step0"], out["h_step0"] = q1.numpy(), h1.numpy()
+            agent_q = torch.from_numpy(rng.standard_normal((T, B, A)).astype(np.float32))
+            out["mixer_in_q"] = agent_q.numpy()
+            out["mixer_out"] = trainer.mixer(agent_q, torch.from_numpy(share_obs[:-1])).numpy()
+            vdn = VDNMixer(args, A, A * D, dev)
+            out["vdn_out"] = vdn(agent_q).numpy()
+
+        batch = ({"policy_0": obs}, {"policy_0": share_obs}, {"policy_0": acts}, {"policy_0": rewards},
+                 {"policy_0": dones}, {"policy_0": dones_env}, {"policy_0": None}, weights, idxes)
+        # capture the gradients before the optimiser step
+        grads = {}
+        orig_clip = torch.nn.utils.clip_grad_norm_
+
+        def spy(params, max_norm, *a, **k):
+            params = list(params)
+            for i, p in enumerate(params):
+                grads[i] = None if p.grad is None else p.grad.detach().clone().numpy()
+            return orig_clip(params, max_norm, *a, **k)
+        torch.nn.utils.clip_grad_norm_ = spy
+        try:
+            info, new_prio, _ = trainer.train_policy_on_batch(batch)
+        finally:
+            torch.nn.utils.clip_grad_norm_ = orig_clip
+        out["train_loss"] = info["loss"].detach().numpy()
+        out["train_grad_norm"] = np.array(float(info["grad_norm"]))
+        out["train_Q_tot"] = info["Q_tot"].detach().numpy()
+        out["train_new_priorities"] = new_prio
+        names = [n for n, _ in policy.q_network.named_parameters()] + ["mix." + n for n, _ in trainer.mixer.named_parameters()]
+        for i, n in enumerate(names):
+            if grads[i] is not None:
+                out["grad." + n] = grads[i]
+        np.savez_compressed(os.path.join(OUT, "offpolicy_qmix.npz"), **out)
+        print("offpolicy_qmix.npz", len(out), "arrays; loss", float(out["train_loss"]))
+
+
+def golden_log_scores():
+    """Episode scores logged by the author's VDN runs: the only numeric evidence about the env."""
+    out = {}
+    for name in ["vdn-1710766189.log", "vdn-1710733227.log", "double_dqn-1710514686.log"]:
+        sc = []
+        for line in open(os.path.join(REF, "vdn", "logs", name)):
+            m = re.search(r"episodes \| train score: (-?[\d.]+)", line)
+            if m:
+                sc.append(float(m.group(1)))
+        out[name.split(".")[0].replace("-", "_")] = np.round(np.array(sc) * 100).astype(np.int32)   # centi-points
+    np.savez_compressed(os.path.join(OUT, "vdn_log_scores.npz"), **out)
+    print("vdn_log_scores.npz", {k: len(v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gae", "per", "nets", "logs"]
+    if "gae" in which:
+        golden_gae()
+    if "per" in which:
+        golden_segment_tree_and_per()
+    if "nets" in which:
+        golden_offpolicy_nets()
+    if "logs" in which:
+        golden_log_scores()
