@@ -49,47 +49,82 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    A background thread polls NVML (the library nvidia-smi itself uses) every ~2 ms, because the timed
+    region of a short run is shorter than nvidia-smi's fastest loop period; if NVML is not importable it
+    falls back to one `nvidia-smi --query-gpu=...` call per sample.
+    """
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
-        self.proc = None
-        self.gpu = gpu_index
+        import threading
+        self.samples, self.stamps, self.reasons, self.max_mhz = [], [], set(), None
+        self.t_begin = self.t_end = None
+        self._stop = threading.Event()
+        self._nvml = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+        self._gpu = gpu_index
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _sample_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self._gpu)],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        self.samples.append(float(f[0]))
+        self.stamps.append(time.perf_counter())
+        self.max_mhz = float(f[1])
+        for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                if self._nvml is not None:
+                    n = self._nvml
+                    self.samples.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+                    self.stamps.append(time.perf_counter())
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                else:
+                    self._sample_smi()
+            except Exception as e:       # keep the benchmark alive, report the failure
+                self.reasons.add(f"sampler_error:{type(e).__name__}")
+                break
+            time.sleep(0.0005)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        self._thread.join(timeout=10)
+        timed = [c for c, t in zip(self.samples, self.stamps)
+                 if self.t_begin is not None and self.t_end is not None and self.t_begin <= t <= self.t_end]
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "samples_in_timed_region": len(timed),
+                "sm_mhz_timed_region": statistics.median(timed) if timed else None,
+                "window": "warm-up + timed region (GPU under load throughout)",
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -224,14 +259,15 @@ def run_ours(args, wl):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
-
-    sampler = ClockSampler(local) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    if sampler:
+        sampler.mark_begin()
     start.record()
     for k in range(args.steps):
         env.reset(out=obs[0])
@@ -243,6 +279,8 @@ def run_ours(args, wl):
         ev[3 * k + 2].record()
     end.record()
     sync_all()
+    if sampler:
+        sampler.mark_end()
     ms_total = start.elapsed_time(end)
     rollout_ms = statistics.mean(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps))
     gae_ms = statistics.mean(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(args.steps))

@@ -18,9 +18,10 @@ namespace {
 constexpr int kAgents = MM_CHECKERS_AGENTS;
 constexpr int kObs = MM_CHECKERS_OBS_DIM;          // 47
 constexpr int kEnvsPerWarp = 32 / kAgents;         // 16
-constexpr int kWarpsPerBlock = 4;
-constexpr int kThreads = 32 * kWarpsPerBlock;
 constexpr int kTileFloats = 32 * kObs;             // 1504 floats = one obs row per lane
+// Few envs: 1-warp blocks spread the warps evenly over the 148 SMs (16 384 envs = 1024 warps = 6.9 per
+// SM); many envs: 4-warp blocks.
+constexpr int kSmallGridWarps = 148 * 16;
 
 constexpr uint32_t kFoodCells = 0x3f3f3fu;                            // cols 0..5 of rows 0..2
 constexpr uint32_t kAppleCells = 0x15u | (0x2au << 8) | (0x15u << 16);  // (row + col) even
@@ -171,6 +172,9 @@ __device__ __forceinline__ void write_tile(const float* tile, float* out, int la
     }
 }
 
+// The caller alternates between two tiles, so the only barrier needed per step is the one between
+// fill and read-out: a lane can start filling tile B while slower lanes still read tile A, and by the
+// time anyone refills tile A every lane has passed the barrier of the step in between.
 template <bool FULL, bool VEC4>
 __device__ __forceinline__ void emit_obs(float* tile, float* obs, int warp_env0, int lane, int agent,
                                          const EnvRegs& s, const mm_checkers_cfg& cfg) {
@@ -179,7 +183,6 @@ __device__ __forceinline__ void emit_obs(float* tile, float* obs, int warp_env0,
     const int n_valid = min(kEnvsPerWarp, cfg.n_envs - warp_env0);
     const size_t env_floats = (size_t)kAgents * kObs * (FULL ? 2 : 1);
     write_tile<FULL, VEC4>(tile, obs + (size_t)warp_env0 * env_floats, lane, n_valid);
-    __syncwarp();
 }
 
 __device__ __forceinline__ EnvRegs load_state(const uint32_t* state, int env, int n) {
@@ -195,13 +198,13 @@ __device__ __forceinline__ void store_state(uint32_t* state, int env, int n, con
     state[2 * n + env] = s.step;
 }
 
-template <bool FULL, bool VEC4>
-__global__ void __launch_bounds__(kThreads)
+template <bool FULL, bool VEC4, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
 checkers_reset_kernel(uint32_t* __restrict__ state, const uint8_t* __restrict__ reset_mask,
                       float* __restrict__ obs, const __grid_constant__ mm_checkers_cfg cfg) {
-    __shared__ __align__(16) float tiles[kWarpsPerBlock][kTileFloats];
+    __shared__ __align__(16) float tiles[WARPS][kTileFloats];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int warp_env0 = (blockIdx.x * kWarpsPerBlock + warp) * kEnvsPerWarp;
+    const int warp_env0 = (blockIdx.x * WARPS + warp) * kEnvsPerWarp;
     if (warp_env0 >= cfg.n_envs) return;
     const int agent = lane & 1;
     const int env = warp_env0 + (lane >> 1);
@@ -219,16 +222,16 @@ checkers_reset_kernel(uint32_t* __restrict__ state, const uint8_t* __restrict__ 
 }
 
 // T == 1 with actions given is env.step; T > 1 keeps the state in registers across steps.
-template <bool FULL, bool VEC4>
-__global__ void __launch_bounds__(kThreads)
+template <bool FULL, bool VEC4, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
 checkers_rollout_kernel(uint32_t* __restrict__ state, const int32_t* __restrict__ actions,
                         int32_t* __restrict__ actions_out, float* __restrict__ obs,
                         float* __restrict__ rewards, uint8_t* __restrict__ dones,
                         int32_t* __restrict__ bad_action_flag, int T, uint2 seed, uint64_t step_offset,
                         const __grid_constant__ mm_checkers_cfg cfg) {
-    __shared__ __align__(16) float tiles[kWarpsPerBlock][kTileFloats];
+    __shared__ __align__(16) float tiles[WARPS][2][kTileFloats];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int warp_env0 = (blockIdx.x * kWarpsPerBlock + warp) * kEnvsPerWarp;
+    const int warp_env0 = (blockIdx.x * WARPS + warp) * kEnvsPerWarp;
     if (warp_env0 >= cfg.n_envs) return;
     const int agent = lane & 1;
     const int env = warp_env0 + (lane >> 1);
@@ -240,10 +243,13 @@ checkers_rollout_kernel(uint32_t* __restrict__ state, const int32_t* __restrict_
 
     EnvRegs s = load_state(state, env_c, cfg.n_envs);
     bool any_bad = false;
+    // the action of step t+1 is fetched while step t is computed: the load never sits on the critical path
+    int act_next = (actions != nullptr) ? actions[row] : 0;
     for (int t = 0; t < T; ++t) {
         int act;
         if (actions != nullptr) {
-            act = actions[(size_t)t * rows + row];
+            act = act_next;
+            if (t + 1 < T) act_next = actions[(size_t)(t + 1) * rows + row];
         } else {
             const uint64_t ctr = step_offset + (uint64_t)t;
             const uint4 rnd = mm::philox4x32_10(
@@ -262,7 +268,8 @@ checkers_rollout_kernel(uint32_t* __restrict__ state, const int32_t* __restrict_
         }
         if (cfg.auto_reset && done) reset_regs(s);
         if (obs != nullptr)
-            emit_obs<FULL, VEC4>(tiles[warp], obs + (size_t)t * obs_step_floats, warp_env0, lane, agent, s, cfg);
+            emit_obs<FULL, VEC4>(tiles[warp][t & 1], obs + (size_t)t * obs_step_floats, warp_env0, lane, agent, s,
+                                 cfg);
     }
     if (valid && agent == 0) store_state(state, env, cfg.n_envs, s);
     if (bad_action_flag != nullptr && any_bad && valid) *bad_action_flag = 1;
@@ -274,10 +281,7 @@ int validate(const uint32_t* state, const mm_checkers_cfg* cfg) {
     return MM_OK;
 }
 
-inline dim3 grid_for(int n_envs) {
-    const int envs_per_block = kEnvsPerWarp * kWarpsPerBlock;
-    return dim3((n_envs + envs_per_block - 1) / envs_per_block);
-}
+inline int warps_for(int n_envs) { return (n_envs + kEnvsPerWarp - 1) / kEnvsPerWarp; }
 
 }  // namespace
 
@@ -286,8 +290,14 @@ extern "C" int mm_checkers_reset(uint32_t* state, const uint8_t* reset_mask, flo
     if (int rc = validate(state, cfg)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool v4 = obs == nullptr || mm::aligned(obs, 16);
-    const dim3 grid = grid_for(cfg->n_envs);
-#define MM_LAUNCH(F, V) checkers_reset_kernel<F, V><<<grid, kThreads, 0, st>>>(state, reset_mask, obs, *cfg)
+    const int warps = warps_for(cfg->n_envs);
+#define MM_LAUNCH(F, V)                                                                                   \
+    do {                                                                                                  \
+        if (warps <= kSmallGridWarps)                                                                     \
+            checkers_reset_kernel<F, V, 1><<<warps, 32, 0, st>>>(state, reset_mask, obs, *cfg);           \
+        else                                                                                              \
+            checkers_reset_kernel<F, V, 4><<<(warps + 3) / 4, 128, 0, st>>>(state, reset_mask, obs, *cfg); \
+    } while (0)
     if (cfg->full_observable) { if (v4) MM_LAUNCH(true, true); else MM_LAUNCH(true, false); }
     else                      { if (v4) MM_LAUNCH(false, true); else MM_LAUNCH(false, false); }
 #undef MM_LAUNCH
@@ -305,11 +315,17 @@ extern "C" int mm_checkers_rollout(uint32_t* state, const int32_t* actions, int3
     // every per-step obs slice must keep the alignment of the vector path
     const size_t step_bytes = (size_t)cfg->n_envs * kAgents * kObs * (cfg->full_observable ? 2 : 1) * 4;
     const bool v4 = obs == nullptr || (mm::aligned(obs, 16) && (T == 1 || step_bytes % 16 == 0));
-    const dim3 grid = grid_for(cfg->n_envs);
+    const int warps = warps_for(cfg->n_envs);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-#define MM_LAUNCH(F, V)                                                                              \
-    checkers_rollout_kernel<F, V><<<grid, kThreads, 0, st>>>(state, actions, actions_out, obs, rewards, \
-                                                             dones, bad_action_flag, T, key, step_offset, *cfg)
+#define MM_LAUNCH(F, V)                                                                                       \
+    do {                                                                                                      \
+        if (warps <= kSmallGridWarps)                                                                         \
+            checkers_rollout_kernel<F, V, 1><<<warps, 32, 0, st>>>(state, actions, actions_out, obs, rewards,  \
+                                                                   dones, bad_action_flag, T, key, step_offset, *cfg); \
+        else                                                                                                  \
+            checkers_rollout_kernel<F, V, 4><<<(warps + 3) / 4, 128, 0, st>>>(                                 \
+                state, actions, actions_out, obs, rewards, dones, bad_action_flag, T, key, step_offset, *cfg); \
+    } while (0)
     if (cfg->full_observable) { if (v4) MM_LAUNCH(true, true); else MM_LAUNCH(true, false); }
     else                      { if (v4) MM_LAUNCH(false, true); else MM_LAUNCH(false, false); }
 #undef MM_LAUNCH

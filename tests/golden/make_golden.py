@@ -273,7 +273,7 @@ def golden_offpolicy_nets():
             out["mixer_in_q"] = agent_q.numpy()
             out["mixer_out"] = trainer.mixer(agent_q, torch.from_numpy(share_obs[:-1])).numpy()
             vdn = VDNMixer(args, A, A * D, dev)
-            out["vdn_out"] = vdn(agent_q).numpy()
+            out["vdn_out"] = vdn(agent_q, torch.from_numpy(share_obs[:-1])).numpy()
 
         batch = ({"policy_0": obs}, {"policy_0": share_obs}, {"policy_0": acts}, {"policy_0": rewards},
                  {"policy_0": dones}, {"policy_0": dones_env}, {"policy_0": None}, weights, idxes)
