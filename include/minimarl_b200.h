@@ -130,6 +130,42 @@ int mm_gae_returns(const float* rewards, const float* value_preds, const float* 
                    double gamma, double gae_lambda, int32_t use_gae, int32_t use_denorm,
                    float denorm_scale, float denorm_shift, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Episode replay on the device (offpolicy/utils/segment_tree.py, offpolicy/utils/rec_buffer.py).
+ * Trees: float64[2 * capacity], node 1 = root, leaf i at capacity + i (the reference's layout).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* SegmentTree.__setitem__ (segment_tree.py:74-89) on the sum and/or the min tree (either may be NULL):
+ * leaves idx[i] (or idx_base + i when idx == NULL) <- values[i] (or scalar_value when values == NULL),
+ * then every ancestor is recomputed level by level. */
+int mm_segtree_set(double* sum_tree, double* min_tree, int32_t capacity, const int64_t* idx,
+                   const double* values, double scalar_value, int64_t idx_base, int32_t n, void* stream);
+
+/* SegmentTree.reduce(start, end) (segment_tree.py:40-72): op over leaves [start, end), same association
+ * order as the reference's recursion.  out: device double[1]. */
+int mm_segtree_reduce(const double* tree, int32_t capacity, int32_t start, int32_t end, int32_t is_min,
+                      double* out, void* stream);
+
+/* SumSegmentTree.find_prefixsum_idx (segment_tree.py:115-146). */
+int mm_segtree_find_prefixsum(const double* sum_tree, int32_t capacity, const double* mass,
+                              int64_t* idx_out, int32_t n, void* stream);
+
+/* PrioritizedRecReplayBuffer.sample (rec_buffer.py:272-296) minus the gather: mass = uniforms *
+ * sum(0, len - 1), tree descent -> idx_out[n]; importance weights (p * len)^-beta / max_weight -> weights_out[n]. */
+int mm_per_sample(const double* sum_tree, const double* min_tree, int32_t capacity, int32_t len,
+                  const double* uniforms, int32_t n, double beta, int64_t* idx_out, double* weights_out,
+                  void* stream);
+
+/* RecPolicyBuffer.sample_inds (rec_buffer.py:192-240): gather B episodes idx[b] out of the time-major
+ * storage obs [T+1,S,A,D], share_obs [T+1,S,SD], acts [T,S,A,NA], rewards/dones [T,S,A,1],
+ * dones_env [T,S,1] into out_obs [A,T+1,B,D], out_share_obs [T+1,B,SD], out_acts [A,T,B,NA],
+ * out_rewards/out_dones [A,T,B,1], out_dones_env [T,B,1]. */
+int mm_replay_gather(const float* obs, const float* share_obs, const float* acts, const float* rewards,
+                     const float* dones, const float* dones_env, const int64_t* idx, float* out_obs,
+                     float* out_share_obs, float* out_acts, float* out_rewards, float* out_dones,
+                     float* out_dones_env, int32_t T, int32_t S, int32_t B, int32_t A, int32_t D, int32_t SD,
+                     int32_t NA, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

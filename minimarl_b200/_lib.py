@@ -44,6 +44,11 @@ SIGNATURES = {
     "mm_switch_step": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(SwitchCfg), _P]),
     "mm_gae_returns": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_double, C.c_double,
                                  C.c_int32, C.c_int32, C.c_float, C.c_float, _P]),
+    "mm_segtree_set": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_double, C.c_int64, C.c_int32, _P]),
+    "mm_segtree_reduce": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "mm_segtree_find_prefixsum": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P]),
+    "mm_per_sample": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_double, _P, _P, _P]),
+    "mm_replay_gather": (C.c_int, [_P] * 13 + [C.c_int32] * 7 + [_P]),
 }
 
 _lib = None

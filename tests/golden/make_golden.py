@@ -92,7 +92,7 @@ def golden_gae():
             "vn": (16, 8, 2, True, True), "plain": (16, 8, 2, True, False), "nogae": (16, 8, 2, False, False),
             "long": (100, 32, 2, True, True),
         }.items():
-            rng = np.random.default_rng(hash(tag) % 1000)
+            rng = np.random.default_rng(sum(map(ord, tag)))
             args = argparse.Namespace(use_gae=use_gae, use_popart=False, use_valuenorm=use_vn, hidden_size=32,
                                       recurrent_N=1, max_step=T, batch_size=B, gamma=0.99, gae_lambda=0.95)
             space = Box(np.zeros(47), np.ones(47))
@@ -317,8 +317,62 @@ def golden_log_scores():
     print("vdn_log_scores.npz", {k: len(v) for k, v in out.items()})
 
 
+def golden_mappo_generators():
+    """SharedReplayBuffer.insert / after_update / recurrent_generator / feed_forward_generator
+    (mappo/runner/shared/shared_buffer.py:82-129,159-219,318-427) with a recorded permutation."""
+    Box, Discrete = install_gym_stub()
+    with ref_package("mappo"):
+        from runner.shared.shared_buffer import SharedReplayBuffer
+        T, B, A, D, H = 10, 6, 2, 47, 32
+        rng = np.random.default_rng(21)
+        args = argparse.Namespace(use_gae=True, use_popart=False, use_valuenorm=False, hidden_size=H,
+                                  recurrent_N=1, max_step=T, batch_size=B, gamma=0.99, gae_lambda=0.95)
+        space = Box(np.zeros(D), np.ones(D))
+        buf = SharedReplayBuffer(args, A, space, space, Discrete(5))
+        out = {}
+        f = lambda *shape: rng.standard_normal(shape).astype(np.float32)
+        buf.obs[0] = f(B, A, D); buf.share_obs[0] = buf.obs[0]
+        out["obs0"] = buf.obs[0].copy()
+        for t in range(T):
+            step = dict(share_obs=f(B, A, D), obs=f(B, A, D), rnn_states_actor=f(B, A, 1, H),
+                        rnn_states_critic=f(B, A, 1, H), actions=rng.integers(0, 5, (B, A, 1)).astype(np.float32),
+                        action_log_probs=f(B, A, 1), value_preds=f(B, A, 1), rewards=f(B, A, 1),
+                        masks=(rng.random((B, A, 1)) < 0.9).astype(np.float32))
+            buf.insert(**step)
+            for k, v in step.items():
+                out[f"step{t}_{k}"] = v
+        next_value = f(B, A, 1)
+        out["next_value"] = next_value
+        buf.compute_returns(next_value, None)
+        out["returns"] = buf.returns.copy()
+        adv = f(T, B, A, 1)
+        out["advantages"] = adv
+        names = ["share_obs", "obs", "rnn_states", "rnn_states_critic", "actions", "value_preds", "returns",
+                 "masks", "active_masks", "old_action_log_probs", "adv_targ"]
+        orig = torch.randperm
+        for gen_name, kw, n_items in [("recurrent", dict(num_mini_batch=2, data_chunk_length=5), (T * B * A) // 5),
+                                      ("feed_forward", dict(num_mini_batch=3), T * B * A),
+                                      ("naive", dict(num_mini_batch=2), B * A)]:
+            perm = torch.from_numpy(rng.permutation(n_items))
+            out[f"{gen_name}_perm"] = perm.numpy()
+            torch.randperm = lambda n, *a, **k: perm
+            try:
+                gen = {"recurrent": buf.recurrent_generator, "feed_forward": buf.feed_forward_generator,
+                       "naive": buf.naive_recurrent_generator}[gen_name]
+                for mb, sample in enumerate(gen(advantages=adv, **kw)):
+                    for name, x in zip(names, sample[:11]):
+                        out[f"{gen_name}_mb{mb}_{name}"] = np.asarray(x)
+            finally:
+                torch.randperm = orig
+        buf.after_update()
+        out["after_update_obs0"] = buf.obs[0].copy()
+        out["after_update_masks0"] = buf.masks[0].copy()
+        np.savez_compressed(os.path.join(OUT, "mappo_buffer.npz"), **out)
+        print("mappo_buffer.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gae", "per", "nets", "logs"]
+    which = sys.argv[1:] or ["gae", "per", "nets", "logs", "mappo_buffer"]
     if "gae" in which:
         golden_gae()
     if "per" in which:
@@ -327,3 +381,5 @@ if __name__ == "__main__":
         golden_offpolicy_nets()
     if "logs" in which:
         golden_log_scores()
+    if "mappo_buffer" in which:
+        golden_mappo_generators()
