@@ -166,6 +166,54 @@ int mm_replay_gather(const float* obs, const float* share_obs, const float* acts
                      float* out_dones_env, int32_t T, int32_t S, int32_t B, int32_t A, int32_t D, int32_t SD,
                      int32_t NA, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Recurrent agent network forward, fused over the whole sequence:
+ * AgentQFunction.forward (offpolicy/algorithms/qmix/algorithm/agent_q_function.py:34-66) =
+ * LayerNorm(D) -> [Linear(D,H) ReLU LayerNorm] -> [Linear(H,H) ReLU LayerNorm] -> GRU(H,H) ->
+ * LayerNorm(H) -> Linear(H,NA); H in {32, 64} (MAPPO actor/critic trunk: mappo/algorithms/r_actor_critic.py).
+ *   params  packed fp32 parameters, 16-byte aligned (layout: mm_agentq_param_offsets; Linear / GRU
+ *           matrices stored TRANSPOSED [in][out], the D->H matrix zero-padded to a multiple of 4 rows,
+ *           the head zero-padded to a multiple of 4 columns)
+ *   obs [T1,R,D]; h0 [R,H] or NULL (zeros); q [T1,R,NA] or NULL; h_final [R,H] or NULL;
+ *   rnn_out [T1,R,H] or NULL (the LayerNorm'ed GRU outputs that feed the head).
+ * ---------------------------------------------------------------------------------------------- */
+int mm_agentq_param_count(int32_t D, int32_t H, int32_t NA);
+int mm_agentq_param_offsets(int32_t D, int32_t H, int32_t NA, int32_t* offsets_host /* int32[18] */);
+int mm_agentq_forward(const float* params, const float* obs, const float* h0, float* q, float* h_final,
+                      float* rnn_out, int32_t T1, int64_t R, int32_t D, int32_t H, int32_t NA, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * QMIX hypernetwork mixer forward (offpolicy/algorithms/qmix/algorithm/q_mixer.py:68-94,
+ * hypernet_layers == 2, hypernet_hidden_dim == 64, mixer_hidden_dim == 32) and the VDN sum
+ * (offpolicy/algorithms/vdn/algorithm/vdn_mixer.py:28-39).
+ *   params packed fp32 (layout: mm_qmixer_param_offsets; matrices transposed [in][out]; the four
+ *   first layers concatenated column-wise as hyper_w1.0 | hyper_w2.0 | hyper_b2.0 | hyper_b1 | 32 zero cols)
+ *   agent_q [M,A], states [M,SD], q_tot [M]  (M = T*B rows);  A in {2, 4}.
+ * ---------------------------------------------------------------------------------------------- */
+int mm_qmixer_param_count(int32_t SD, int32_t A);
+int mm_qmixer_param_offsets(int32_t SD, int32_t A, int32_t* offsets_host /* int32[8] */);
+int mm_qmixer_forward(const float* params, const float* agent_q, const float* states, float* q_tot,
+                      int64_t M, int32_t SD, int32_t A, void* stream);
+int mm_vdn_mix(const float* agent_q, float* q_tot, int64_t M, int32_t A, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tail of QMix.train_policy_on_batch (offpolicy/algorithms/qmix/qmix.py:134-191).
+ * mm_q_select: rows r = a*B + b.  q_all / target_q_all [T+1,R,NA], acts [T,R,NA] (one-hot rows; arg-max
+ *   with first-maximum tie-break like torch.max) -> q_taken [T,B,A] (q_values_from_actions,
+ *   QMixPolicy.py:92-111), act_idx [T,R], greedy [T+1,R] (live arg-max), next_q [T,B,A] = target Q at
+ *   step t+1 of the live greedy action (double_q) or its max over actions.  Outputs may be NULL.
+ * mm_qmix_td: q_tot / next_q_tot / rewards / dones_env [T,B], weights [B] or NULL ->
+ *   err [T,B] = (q_tot - (r + (1-d) gamma next)) * (1 - bad), bad[t] = dones_env[t-1];
+ *   ep_loss [B] = w_b * sum_t err^2; ep_valid [B] = sum_t (1 - bad); ep_qsum [B] = sum_t q_tot (1 - bad);
+ *   priorities [B] = (1-nu) mean_t|err| + nu max_t|err| + eps  (may be NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int mm_q_select(const float* q_all, const float* target_q_all, const float* acts, float* q_taken,
+                float* next_q, int64_t* act_idx, int64_t* greedy, int32_t T, int32_t B, int32_t A,
+                int32_t NA, int32_t double_q, void* stream);
+int mm_qmix_td(const float* q_tot, const float* next_q_tot, const float* rewards, const float* dones_env,
+               const float* weights, float gamma, float per_nu, float per_eps, int32_t T, int32_t B,
+               float* err, float* ep_loss, float* ep_valid, float* ep_qsum, float* priorities, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,16 @@ SIGNATURES = {
     "mm_segtree_find_prefixsum": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P]),
     "mm_per_sample": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_double, _P, _P, _P]),
     "mm_replay_gather": (C.c_int, [_P] * 13 + [C.c_int32] * 7 + [_P]),
+    "mm_agentq_param_count": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "mm_agentq_param_offsets": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "mm_agentq_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                    C.c_int32, _P]),
+    "mm_qmixer_param_count": (C.c_int, [C.c_int32, C.c_int32]),
+    "mm_qmixer_param_offsets": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "mm_qmixer_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "mm_vdn_mix": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P]),
+    "mm_q_select": (C.c_int, [_P] * 7 + [C.c_int32] * 5 + [_P]),
+    "mm_qmix_td": (C.c_int, [_P] * 5 + [C.c_float] * 3 + [C.c_int32] * 2 + [_P] * 6),
 }
 
 _lib = None

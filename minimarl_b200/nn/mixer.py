@@ -1,0 +1,127 @@
+"""QMIX / VDN mixers with the reference's module tree, fused on the GPU when no gradient is needed.
+
+``QMixer`` mirrors offpolicy/algorithms/qmix/algorithm/q_mixer.py:8-94 (state_dict keys ``hyper_w1.0.weight``,
+``hyper_w1.2.weight``, ``hyper_w2.*``, ``hyper_b1.*``, ``hyper_b2.*``); ``VDNMixer`` mirrors
+offpolicy/algorithms/vdn/algorithm/vdn_mixer.py:6-39.  The target mixer of a QMIX update always runs
+under ``torch.no_grad()`` and therefore always takes the one-kernel path (``mm_qmixer_forward``).
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+
+_NAMES = ["wcat", "bcat", "w1b", "b1b", "w2b", "b2b", "wb2", "bb2"]
+
+
+def pack_qmixer(sd, SD, A, device, prefix=""):
+    lib = _lib.lib()
+    total = lib.mm_qmixer_param_count(SD, A)
+    if total < 0:
+        raise RuntimeError(f"fused mixer supports 2 or 4 agents; got A={A}")
+    offs = (C.c_int32 * 8)()
+    _lib.check(lib.mm_qmixer_param_offsets(SD, A, offs))
+    o = dict(zip(_NAMES, list(offs)))
+    g = lambda k: sd[prefix + k].detach().to(device=device, dtype=torch.float32)
+    buf = torch.zeros(total, dtype=torch.float32, device=device)
+    K1 = (SD + 3) // 4 * 4
+    wcat = torch.zeros((K1, 256), dtype=torch.float32, device=device)
+    bcat = torch.zeros(256, dtype=torch.float32, device=device)
+    for col, key, width in [(0, "hyper_w1.0", 64), (64, "hyper_w2.0", 64), (128, "hyper_b2.0", 64), (192, "hyper_b1", 32)]:
+        wcat[:SD, col:col + width] = g(key + ".weight").t()
+        bcat[col:col + width] = g(key + ".bias")
+
+    def put(name, t):
+        t = t.reshape(-1)
+        buf[o[name]:o[name] + t.numel()] = t
+
+    put("wcat", wcat); put("bcat", bcat)
+    put("w1b", g("hyper_w1.2.weight").t().contiguous()); put("b1b", g("hyper_w1.2.bias"))
+    w2b = torch.zeros((64, 64), dtype=torch.float32, device=device)
+    w2b[:, :32] = g("hyper_w2.2.weight").t()
+    b2b = torch.zeros(64, dtype=torch.float32, device=device)
+    b2b[:32] = g("hyper_w2.2.bias")
+    put("w2b", w2b); put("b2b", b2b)
+    put("wb2", g("hyper_b2.2.weight")); put("bb2", g("hyper_b2.2.bias"))
+    return buf
+
+
+def _init(m, use_orthogonal):
+    (nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_)(m.weight.data, gain=1)
+    nn.init.constant_(m.bias.data, 0)
+    return m
+
+
+class QMixer(nn.Module):
+    def __init__(self, args, num_agents, cent_obs_dim, device, multidiscrete_list=None):
+        super().__init__()
+        if multidiscrete_list:
+            raise NotImplementedError("multi-discrete mixing is outside the hot path")
+        self.device = torch.device(device)
+        self.tpdv = dict(dtype=torch.float32, device=self.device)
+        self.num_agents = num_agents
+        self.cent_obs_dim = cent_obs_dim
+        self.hidden_layer_dim = args.mixer_hidden_dim
+        self.hypernet_hidden_dim = args.hypernet_hidden_dim
+        self.num_mixer_q_inps = num_agents
+        uo = args.use_orthogonal
+        lin = lambda i, o: _init(nn.Linear(i, o), uo)
+        S, HH, E, A = cent_obs_dim, self.hypernet_hidden_dim, self.hidden_layer_dim, num_agents
+        if args.hypernet_layers == 1:
+            self.hyper_w1, self.hyper_w2 = lin(S, A * E), lin(S, E)
+        elif args.hypernet_layers == 2:
+            self.hyper_w1 = nn.Sequential(lin(S, HH), nn.ReLU(), lin(HH, A * E))
+            self.hyper_w2 = nn.Sequential(lin(S, HH), nn.ReLU(), lin(HH, E))
+        self.hyper_b1 = lin(S, E)
+        self.hyper_b2 = nn.Sequential(lin(S, HH), nn.ReLU(), lin(HH, 1))
+        self.to(self.device)
+        self.fusable = args.hypernet_layers == 2 and HH == 64 and E == 32 and A in (2, 4)
+        self._packed, self._packed_key = None, None
+
+    def packed(self):
+        key = tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        if self._packed is None or key != self._packed_key:
+            self._packed = pack_qmixer(self.state_dict(), self.cent_obs_dim, self.num_agents, self.device)
+            self._packed_key = key
+        return self._packed
+
+    def forward(self, agent_q_inps, states):
+        agent_q_inps = torch.as_tensor(agent_q_inps).to(**self.tpdv)
+        states = torch.as_tensor(states).to(**self.tpdv)
+        batch_size = agent_q_inps.size(1)
+        needs_graph = torch.is_grad_enabled() and (agent_q_inps.requires_grad or
+                                                   any(p.requires_grad for p in self.parameters()))
+        if self.fusable and not needs_graph:
+            s = states.reshape(-1, self.cent_obs_dim).contiguous()
+            q = agent_q_inps.reshape(-1, self.num_agents).contiguous()
+            out = torch.empty(s.shape[0], **self.tpdv)
+            _lib.check(_lib.lib().mm_qmixer_forward(_lib.ptr(self.packed()), _lib.ptr(q), _lib.ptr(s), _lib.ptr(out),
+                                                    s.shape[0], self.cent_obs_dim, self.num_agents, _lib.stream()))
+            return out.view(-1, batch_size, 1, 1)
+        states = states.view(-1, batch_size, self.cent_obs_dim).float()
+        agent_q_inps = agent_q_inps.view(-1, batch_size, 1, self.num_mixer_q_inps)
+        w1 = torch.abs(self.hyper_w1(states)).view(-1, batch_size, self.num_mixer_q_inps, self.hidden_layer_dim)
+        b1 = self.hyper_b1(states).view(-1, batch_size, 1, self.hidden_layer_dim)
+        hidden_layer = F.elu(torch.matmul(agent_q_inps, w1) + b1)
+        w2 = torch.abs(self.hyper_w2(states)).view(-1, batch_size, self.hidden_layer_dim, 1)
+        b2 = self.hyper_b2(states).view(-1, batch_size, 1, 1)
+        return (torch.matmul(hidden_layer, w2) + b2).view(-1, batch_size, 1, 1)
+
+
+class VDNMixer(nn.Module):
+    def __init__(self, args, num_agents, cent_obs_dim, device, multidiscrete_list=None):
+        super().__init__()
+        self.device = torch.device(device)
+        self.num_agents = num_agents
+        self.num_mixer_q_inps = num_agents
+
+    def forward(self, agent_q_inps, states=None):
+        agent_q_inps = torch.as_tensor(agent_q_inps).to(device=self.device, dtype=torch.float32)
+        if torch.is_grad_enabled() and agent_q_inps.requires_grad:
+            return agent_q_inps.sum(dim=-1).view(-1, 1, 1)
+        q = agent_q_inps.reshape(-1, self.num_agents).contiguous()
+        out = torch.empty(q.shape[0], dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().mm_vdn_mix(_lib.ptr(q), _lib.ptr(out), q.shape[0], self.num_agents, _lib.stream()))
+        return out.view(-1, 1, 1)

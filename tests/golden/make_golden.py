@@ -77,7 +77,8 @@ class ref_package:
 
 
 def sd_numpy(module, prefix=""):
-    return {prefix + k: v.detach().cpu().numpy() for k, v in module.state_dict().items()}
+    # .copy(): a CPU tensor and its numpy view share memory, and the optimiser later updates in place
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in module.state_dict().items()}
 
 
 # ---------------------------------------------------------------------------------------------------

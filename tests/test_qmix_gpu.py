@@ -1,0 +1,152 @@
+"""GPU parity: mixer / selection / TD kernels and one full QMIX update vs values recorded from the
+reference's QMixer, VDNMixer and QMix.train_policy_on_batch (tests/golden/offpolicy_qmix.npz).
+Tolerances (fp32): mixer outputs 2e-5 abs; loss 1e-5 rel; gradients 2e-5 abs + 1e-3 rel; priorities 1e-5."""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from minimarl_b200.envs.spaces import Box, Discrete
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(**over):
+    a = argparse.Namespace(
+        hidden_size=64, use_rnn_layer=True, use_orthogonal=True, gain=0.01, layer_N=1, recurrent_N=1,
+        use_feature_normalization=True, use_ReLU=True, use_conv1d=False, prev_act_inp=False, batch_size=6,
+        mixer_hidden_dim=32, hypernet_hidden_dim=64, hypernet_layers=2, use_per=True, per_eps=1e-6, per_nu=0.9,
+        use_huber_loss=False, use_popart=False, lr=5e-4, tau=0.005, opti_eps=1e-5, episode_length=12,
+        use_same_share_obs=True, use_double_q=True, gamma=0.99, max_grad_norm=10.0, epsilon_start=1.0,
+        epsilon_finish=0.05, epsilon_anneal_time=50000, seed=1, weight_decay=0)
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+def _g():
+    return np.load(os.path.join(GOLDEN, "offpolicy_qmix.npz"))
+
+
+def _load(module, g, prefix):
+    module.load_state_dict({k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)})
+
+
+def test_qmixer_and_vdn_forward_match_reference(cuda):
+    from minimarl_b200.nn import QMixer, VDNMixer
+    g = _g()
+    mixer = QMixer(_args(), 2, 94, cuda)
+    _load(mixer, g, "mix.")
+    assert sum(p.numel() for p in mixer.parameters()) == 27585
+    q = torch.from_numpy(g["mixer_in_q"]).to(cuda)
+    s = torch.from_numpy(g["share_obs"][:-1]).to(cuda)
+    with torch.no_grad():
+        out = mixer(q, s)                                               # fused kernel
+    assert out.shape == g["mixer_out"].shape
+    assert np.abs(out.cpu().numpy() - g["mixer_out"]).max() < 2e-5
+    out_eager = mixer(q.clone().requires_grad_(True), s)                # autograd path, same maths
+    assert np.abs(out_eager.detach().cpu().numpy() - g["mixer_out"]).max() < 2e-5
+    with torch.no_grad():
+        v = VDNMixer(_args(), 2, 94, cuda)(q, s)
+    assert np.array_equal(v.cpu().numpy(), g["vdn_out"])
+
+
+def test_mixer_ragged_rows(cuda):
+    """Row counts that are not a multiple of the 64-row tile, more tiles than SMs."""
+    from minimarl_b200.nn import QMixer
+    torch.manual_seed(0)
+    mixer = QMixer(_args(), 2, 94, cuda)
+    with torch.no_grad():
+        for p in mixer.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    for T, B in [(1, 1), (3, 50), (100, 133)]:
+        q = torch.randn((T, B, 2), device=cuda)
+        s = torch.rand((T, B, 94), device=cuda)
+        with torch.no_grad():
+            fused = mixer(q, s)
+        eager = mixer(q.clone().requires_grad_(True), s).detach()
+        assert (fused - eager).abs().max().item() < 5e-5 * max(1.0, eager.abs().max().item())
+
+
+def test_full_qmix_update_matches_reference(cuda):
+    from minimarl_b200.algorithms import QMix, QMixPolicy
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = _g()
+    args = _args()
+    T, B, A, D, nA = 12, 6, 2, 47, 5
+    pconf = {"cent_obs_dim": A * D, "cent_act_dim": A * nA, "obs_space": Box(np.zeros(D), np.ones(D)),
+             "share_obs_space": Box(np.zeros(A * D), np.ones(A * D)), "act_space": Discrete(nA)}
+    policy = QMixPolicy(args, {"args": args, "device": cuda, "num_agents": A}, pconf)
+    trainer = QMix(args, A, B, {"policy_0": policy}, lambda a: "policy_0", device=cuda, episode_length=T)
+    _load(policy.q_network, g, "q.")
+    _load(trainer.target_policies["policy_0"].q_network, g, "tq.")
+    _load(trainer.mixer, g, "mix.")
+    _load(trainer.target_mixer, g, "tmix.")
+    batch = tuple({"policy_0": g[k]} for k in ["obs", "share_obs", "acts", "rewards", "dones", "dones_env"]) + \
+        ({"policy_0": None}, g["weights"], np.arange(B))
+    before = [p.detach().clone() for p in trainer.parameters]
+    info, new_prio, idxes = trainer.train_policy_on_batch(batch)
+    assert abs(info["loss"].item() - float(g["train_loss"])) < 1e-5 * max(1.0, abs(float(g["train_loss"])))
+    assert abs(float(info["grad_norm"]) - float(g["train_grad_norm"])) < 1e-4 * float(g["train_grad_norm"])
+    assert abs(info["Q_tot"].item() - float(g["train_Q_tot"])) < 1e-5
+    assert np.allclose(new_prio.cpu().numpy(), g["train_new_priorities"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(idxes, np.arange(B))
+    names = [n for n, _ in policy.q_network.named_parameters()] + ["mix." + n for n, _ in trainer.mixer.named_parameters()]
+    checked = 0
+    for n, p in zip(names, trainer.parameters):
+        key = "grad." + n
+        if key in g.files:
+            assert np.allclose(p.grad.cpu().numpy(), g[key], rtol=1e-3, atol=2e-5), n
+            checked += 1
+        else:
+            assert p.grad is None, n                                   # the unused fc_h duplicate
+    assert checked >= 30
+    assert any((a - b).abs().max().item() > 0 for a, b in zip(before, trainer.parameters))
+    trainer.soft_target_updates()
+    trainer.hard_target_updates()
+    trainer.prep_rollout(); trainer.prep_training()
+
+
+def test_q_select_and_td_kernels_against_torch(cuda):
+    from minimarl_b200.ops import q_select, qmix_td_loss
+    T, B, A, NA = 20, 37, 2, 5
+    gen = torch.Generator(device=cuda).manual_seed(0)
+    q_all = torch.randn((T + 1, A * B, NA), device=cuda, generator=gen)
+    tq_all = torch.randn((T + 1, A * B, NA), device=cuda, generator=gen)
+    idx = torch.randint(0, NA, (T, A * B), device=cuda, generator=gen)
+    acts = torch.nn.functional.one_hot(idx, NA).float()
+    q_taken, next_q, act_idx, greedy = q_select(q_all, tq_all, acts, T, B, A, double_q=True, want_greedy=True)
+    assert torch.equal(act_idx, idx) and torch.equal(greedy, q_all.argmax(-1))
+    want = torch.gather(q_all[:-1], 2, idx.unsqueeze(-1)).squeeze(-1).view(T, A, B).permute(0, 2, 1)
+    assert torch.equal(q_taken, want)
+    want_next = torch.gather(tq_all, 2, greedy.unsqueeze(-1)).squeeze(-1)[1:].view(T, A, B).permute(0, 2, 1)
+    assert torch.equal(next_q, want_next)
+    _, next_max, _, _ = q_select(q_all, tq_all, acts, T, B, A, double_q=False)
+    assert torch.equal(next_max, tq_all.max(-1)[0][1:].view(T, A, B).permute(0, 2, 1))
+    # Q11: the reference stores the action INDEX broadcast over the one-hot dim -> all ties -> index 0
+    tied = idx.unsqueeze(-1).expand(T, A * B, NA).float().contiguous()
+    _, _, tied_idx, _ = q_select(q_all, None, tied, T, B, A)
+    assert int(tied_idx.abs().max()) == 0
+
+    q_tot = torch.randn((T, B, 1), device=cuda, generator=gen, requires_grad=True)
+    nq = torch.randn((T, B, 1), device=cuda, generator=gen)
+    rew = torch.randn((T, B, 1), device=cuda, generator=gen)
+    done = (torch.rand((T, B, 1), device=cuda, generator=gen) < 0.1).float()
+    w = torch.rand(B, device=cuda, generator=gen)
+    loss, prio, qmean, denom = qmix_td_loss(q_tot, nq, rew, done, w, 0.99, 0.9, 1e-6)
+    loss.backward()
+    q2 = q_tot.detach().clone().requires_grad_(True)
+    bad = torch.cat((torch.zeros(1, B, 1, device=cuda), done[:-1]))
+    err = (q2 - (rew + (1 - done) * 0.99 * nq)) * (1 - bad)
+    ref = ((err ** 2).sum(0).flatten() * w).sum() / (1 - bad).sum()
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert torch.allclose(q_tot.grad, q2.grad, rtol=1e-4, atol=1e-7)
+    td = err.abs().detach()
+    assert torch.allclose(prio, (0.1 * td.mean(0) + 0.9 * td.max(0)[0]).flatten() + 1e-6, rtol=1e-5)
+    assert abs(qmean.item() - (q2.detach() * (1 - bad)).mean().item()) < 1e-6
