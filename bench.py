@@ -211,6 +211,84 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def learner_section(dev, steps):
+    """Second half of the BASELINE metric: QMIX train samples/sec (configs[3]: 1M-transition device replay =
+    10 000 episodes x T=100, batch 4 096 episodes, GRU agents, hidden 64, PER, double-Q).  One sample = one
+    transition of one env (all agents) consumed by an optimiser step, so one update = 409 600 samples."""
+    import argparse as ap
+    import numpy as np
+    import torch
+    from minimarl_b200.algorithms import QMix, QMixPolicy
+    from minimarl_b200.buffers import PrioritizedRecReplayBuffer
+    from minimarl_b200.envs.spaces import Box, Discrete
+    T, A, D, NA, S, B = 100, 2, 47, 5, 10000, 4096
+    args = ap.Namespace(
+        hidden_size=64, use_rnn_layer=True, use_orthogonal=True, gain=0.01, layer_N=1, recurrent_N=1,
+        use_feature_normalization=True, use_ReLU=True, use_conv1d=False, prev_act_inp=False, batch_size=B,
+        mixer_hidden_dim=32, hypernet_hidden_dim=64, hypernet_layers=2, use_per=True, per_eps=1e-6, per_nu=0.9,
+        use_huber_loss=False, use_popart=False, lr=5e-4, tau=0.005, opti_eps=1e-5, episode_length=T,
+        use_same_share_obs=True, use_double_q=True, gamma=0.99, max_grad_norm=10.0, epsilon_start=1.0,
+        epsilon_finish=0.05, epsilon_anneal_time=50000, seed=1)
+    info = {"policy_0": {"obs_space": Box(np.zeros(D), np.ones(D)), "share_obs_space": Box(np.zeros(A * D), np.ones(A * D)),
+                         "act_space": Discrete(NA)}}
+    buf = PrioritizedRecReplayBuffer(0.6, info, {"policy_0": [0, 1]}, S, T, True, False, device=dev)
+    pb = buf.policy_buffers["policy_0"]
+    g = torch.Generator(device=dev).manual_seed(42)
+    pb.obs.copy_((torch.rand(pb.obs.shape, device=dev, generator=g) * 100).round() / 100)
+    pb.share_obs.copy_(pb.obs.reshape(T + 1, S, A * D))
+    pb.acts.copy_(torch.nn.functional.one_hot(torch.randint(0, NA, (T, S, A), device=dev, generator=g), NA).float())
+    pb.rewards.copy_(torch.randn(pb.rewards.shape, device=dev, generator=g))
+    pb.dones.zero_(); pb.dones_env.zero_(); pb.dones_env[-1] = 1
+    pb.filled_i, pb.current_i = S, 0
+    buf.update_priorities(torch.arange(S, device=dev), torch.rand(S, device=dev, generator=g) * 0.99 + 0.01, "policy_0")
+    pconf = {"cent_obs_dim": A * D, "cent_act_dim": A * NA, "obs_space": info["policy_0"]["obs_space"],
+             "share_obs_space": info["policy_0"]["share_obs_space"], "act_space": info["policy_0"]["act_space"]}
+    policy = QMixPolicy(args, {"args": args, "device": dev, "num_agents": A}, pconf)
+    trainer = QMix(args, A, B, {"policy_0": policy}, lambda a: "policy_0", device=dev, episode_length=T)
+
+    def update():
+        sample = buf.sample(B, beta=0.4, p_id="policy_0")
+        info_, prio, idx = trainer.train_policy_on_batch(sample)
+        buf.update_priorities(idx, prio, "policy_0")
+        trainer.soft_target_updates()
+        return info_
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, out
+
+    for _ in range(3):
+        update()
+    ms_update, info_ = timed(update, steps)
+    # component timings (each in isolation, after the full updates)
+    ms_sample, sample = timed(lambda: buf.sample(B, beta=0.4, p_id="policy_0"), 5)
+    stacked = torch.cat(list(sample[0]["policy_0"]), dim=-2)
+    with torch.no_grad():
+        ms_agent, _ = timed(lambda: policy.q_network(stacked, torch.zeros(A * B, 64, device=dev)), 5)
+        qs = torch.randn((T, B, A), device=dev)
+        ms_mixer, _ = timed(lambda: trainer.target_mixer(qs, sample[1]["policy_0"][:-1]), 5)
+    rows = (T + 1) * A * B
+    peak, _ = measured_peaks()
+    gather_bytes = 2 * 81952 * B
+    return {
+        "metric": "QMIX train samples/sec", "value": B * T / (ms_update * 1e-3), "unit": "samples/s",
+        "config": {"buffer_episodes": S, "episode_length": T, "batch_episodes": B, "agents": A, "hidden": 64,
+                   "per": True, "double_q": True, "precision": "fp32"},
+        "ms_per_update": ms_update, "loss": float(info_["loss"]),
+        "sample_gather": {"ms": ms_sample, "algorithmic_GBps": gather_bytes / (ms_sample * 1e-3) / 1e9,
+                          "frac_of_measured_hbm": gather_bytes / (ms_sample * 1e-3) / 1e9 / peak},
+        "agentq_forward": {"ms": ms_agent, "rows_x_steps": rows, "TFLOPs": rows * 64000 / (ms_agent * 1e-3) / 1e12,
+                           "note": "fused fp32 FFMA kernel (target / greedy passes); 64 kFLOP per (row, step)"},
+        "mixer_forward": {"ms": ms_mixer, "rows": T * B, "TFLOPs": T * B * 54528 / (ms_mixer * 1e-3) / 1e12},
+    }
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -347,6 +425,11 @@ def run_ours(args, wl):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
+        if not args.no_learner:
+            try:
+                line["learner"] = learner_section(dev, args.learner_steps)
+            except Exception as e:          # the headline line must survive a learner failure; report it
+                line["learner"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -360,6 +443,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mappo_rollout_16384x128", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU time spent on the cpu_baseline sample")
+    ap.add_argument("--no-learner", action="store_true", help="skip the QMIX learner section")
+    ap.add_argument("--learner-steps", type=int, default=5)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

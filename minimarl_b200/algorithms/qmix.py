@@ -20,10 +20,10 @@ import copy
 
 import numpy as np
 import torch
-import torch.distributed as dist
 
 from ..nn import AgentQFunction, QMixer, VDNMixer
 from ..ops.td import q_select, qmix_td_loss
+from ..parallel import allreduce_mean_grads
 
 
 def _space_dim(space):
@@ -174,16 +174,7 @@ class QMix:
 
     # -- gradient exchange (the only collective on this path) -------------------------------------
     def _allreduce_grads(self):
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return
-        grads = [p.grad for p in self.parameters if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])            # one bucket, one call (260 KB for QMIX)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat /= dist.get_world_size()
-        off = 0
-        for g in grads:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
+        allreduce_mean_grads(self.parameters)
 
     def train_policy_on_batch(self, batch, update_policy_id=None):
         obs_batch, cent_obs_batch, act_batch, rew_batch, dones_batch, dones_env_batch, avail_act_batch, \

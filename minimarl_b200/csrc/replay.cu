@@ -108,15 +108,34 @@ struct GatherParams {
     int T, S, B, A, D, SD, NA;
 };
 
+// Loads are issued in batches of 4 per lane BEFORE the dependent stores (read-only path, so the compiler
+// may hoist them): a warp keeps 4 x 128 B per field in flight instead of one load-store round trip at a time.
+template <typename DstIndex>
+__device__ __forceinline__ void copy_run(const float* __restrict__ from, int n, float* __restrict__ dst,
+                                         DstIndex dst_index, int lane) {
+    for (int base = 0; base < n; base += 128) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = base + lane + 32 * u;
+            if (k < n) v[u] = __ldg(from + k);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = base + lane + 32 * u;
+            if (k < n) dst[dst_index(k)] = v[u];
+        }
+    }
+}
+
+// src [TT, S, A, d] at (t, s, :, :) -> dst [A, TT, B, d] at (:, t, b, :)
 __device__ __forceinline__ void copy_agent_major(const float* __restrict__ src, float* __restrict__ dst,
                                                  int t, int b, int64_t s, int S, int B, int A, int d, int TT,
                                                  int lane) {
-    // src [TT, S, A, d] at (t, s, :, :) -> dst [A, TT, B, d] at (:, t, b, :)
     const float* from = src + ((int64_t)t * S + s) * A * d;
-    for (int k = lane; k < A * d; k += 32) {
-        const int a = k / d, j = k - a * d;
-        dst[(((int64_t)a * TT + t) * B + b) * d + j] = mm::ld_stream(from + k);
-    }
+    const int64_t agent_stride = (int64_t)TT * B * d;
+    float* to = dst + ((int64_t)t * B + b) * d;
+    copy_run(from, A * d, to, [=](int k) { const int a = k / d; return (int64_t)a * agent_stride + (k - a * d); }, lane);
 }
 
 __global__ void __launch_bounds__(256) replay_gather_kernel(const GatherParams p) {
@@ -126,16 +145,13 @@ __global__ void __launch_bounds__(256) replay_gather_kernel(const GatherParams p
     const int t = (int)(w / p.B), b = (int)(w - (int64_t)t * p.B);
     const int64_t s = p.idx[b];
     copy_agent_major(p.obs, p.o_obs, t, b, s, p.S, p.B, p.A, p.D, p.T + 1, lane);
-    {   // share_obs [T+1, S, SD] -> [T+1, B, SD]
-        const float* from = p.share_obs + ((int64_t)t * p.S + s) * p.SD;
-        float* to = p.o_share_obs + ((int64_t)t * p.B + b) * p.SD;
-        for (int k = lane; k < p.SD; k += 32) to[k] = mm::ld_stream(from + k);
-    }
+    copy_run(p.share_obs + ((int64_t)t * p.S + s) * p.SD, p.SD, p.o_share_obs + ((int64_t)t * p.B + b) * p.SD,
+             [](int k) { return (int64_t)k; }, lane);
     if (t < p.T) {
         copy_agent_major(p.acts, p.o_acts, t, b, s, p.S, p.B, p.A, p.NA, p.T, lane);
         copy_agent_major(p.rewards, p.o_rewards, t, b, s, p.S, p.B, p.A, 1, p.T, lane);
         copy_agent_major(p.dones, p.o_dones, t, b, s, p.S, p.B, p.A, 1, p.T, lane);
-        if (lane == 0) p.o_dones_env[(int64_t)t * p.B + b] = p.dones_env[(int64_t)t * p.S + s];
+        if (lane == 0) p.o_dones_env[(int64_t)t * p.B + b] = __ldg(p.dones_env + (int64_t)t * p.S + s);
     }
 }
 
