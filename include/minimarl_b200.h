@@ -214,6 +214,20 @@ int mm_qmix_td(const float* q_tot, const float* next_q_tot, const float* rewards
                const float* weights, float gamma, float per_nu, float per_eps, int32_t T, int32_t B,
                float* err, float* ep_loss, float* ep_valid, float* ep_qsum, float* priorities, void* stream);
 
+/* Self-test of the tcgen05 / TMEM building blocks: D[128,N] = A[128,K] * B[N,K]^T in TF32 with fp32
+ * accumulation (one CTA).  N % 16 == 0, 16 <= N <= 256; K % 8 == 0, K <= 128. */
+int mm_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, void* stream);
+
+/* Tensor-core version of mm_agentq_forward: every dense contraction on tcgen05 (kind::tf32, fp32
+ * accumulators in TMEM), same arguments.  params: plain fp32 buffer of the PyTorch-layout tensors
+ * (offsets from mm_agentq_tc_param_offsets, same order of names as mm_agentq_param_offsets; the
+ * Linear(D,H) weight is [H][K1] with K1 = D rounded up to 8 and zero padding).  Returns
+ * MM_ERR_UNSUPPORTED when the tile does not fit shared memory (e.g. D = 94): use mm_agentq_forward. */
+int mm_agentq_tc_param_count(int32_t D, int32_t H, int32_t NA);
+int mm_agentq_tc_param_offsets(int32_t D, int32_t H, int32_t NA, int32_t* offsets_host /* int32[18] */);
+int mm_agentq_tc_forward(const float* params, const float* obs, const float* h0, float* q, float* h_final,
+                         float* rnn_out, int32_t T1, int64_t R, int32_t D, int32_t H, int32_t NA, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

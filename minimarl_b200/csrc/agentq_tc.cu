@@ -1,0 +1,354 @@
+// Tensor-core (tcgen05, TF32 in / fp32 accumulate in TMEM) fused recurrent agent network forward.
+//
+// Same computation as agentq.cu (AgentQFunction.forward,
+// offpolicy/algorithms/qmix/algorithm/agent_q_function.py:34-66) with every dense contraction on the
+// 5th-generation tensor cores:
+//     fc1   [128 x K1] x [K1 x H]      -> TMEM cols [0, H)
+//     fc2   [128 x H ] x [H  x H]      -> TMEM cols [0, H)            (fc1's accumulator is consumed by then)
+//     gates [128 x H ] x [H x 2H] (x)  + [128 x H] x [H x 2H] (h)  -> TMEM cols [H, 3H)   r | z, accumulated
+//           [128 x H ] x [H x H ] (x)  -> TMEM cols [0, H)            i_n
+//           [128 x H ] x [H x H ] (h)  -> TMEM cols [3H, 4H)          h_n
+// One CTA = 128 rows = 128 threads; thread r owns row r end to end (TMEM lane r), so bias, ReLU,
+// LayerNorm, the GRU gate math and the 5-wide head are thread-local on the accumulators read back with
+// tcgen05.ld, and the activations go back to shared memory directly in the K-major operand layout of the
+// next MMA.  Weights (W1, W2, W_ih, W_hh = 124 KB as tf32 at H = 64) stay in shared memory for the whole
+// sequence, the hidden state lives in shared memory in operand layout, and the obs tile of step t+1 is
+// prefetched with cp.async while step t computes.  MMAs are issued by one thread and tracked with one
+// mbarrier (tcgen05.commit); waits are bounded (trap instead of hang).
+// Precision: TF32 operands (round-to-nearest on every activation store and on the weights), fp32
+// accumulation and fp32 epilogues -> ~1e-3 relative on the Q-values; tests state the tolerance.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kRows = 128;
+constexpr float kEps = 1e-5f;
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// plain parameter buffer (fp32, PyTorch layouts): offsets in floats
+struct TcLayout {
+    int D, K1, H, NA;
+    int ln0_w, ln0_b, w1, b1, ln1_w, ln1_b, w2, b2, ln2_w, ln2_b, wih, whh, bih, bhh, ln3_w, ln3_b, wq, bq, total;
+    int small;   // everything from here on (vectors + the head) is copied to shared memory as is
+};
+__host__ __device__ inline TcLayout make_tc_layout(int D, int H, int NA) {
+    TcLayout L;
+    L.D = D; L.H = H; L.NA = NA; L.K1 = (D + 7) & ~7;
+    int o = 0;
+    auto take = [&](int n) { int at = o; o += (n + 3) & ~3; return at; };
+    // the four operand matrices first (PyTorch [out][in] layouts; w1 zero-padded to K1 columns) ...
+    L.w1 = take(H * L.K1); L.w2 = take(H * H); L.wih = take(3 * H * H); L.whh = take(3 * H * H);
+    // ... then the small vectors and the head
+    L.small = o;
+    L.ln0_w = take(D); L.ln0_b = take(D);
+    L.b1 = take(H); L.ln1_w = take(H); L.ln1_b = take(H);
+    L.b2 = take(H); L.ln2_w = take(H); L.ln2_b = take(H);
+    L.bih = take(3 * H); L.bhh = take(3 * H);
+    L.ln3_w = take(H); L.ln3_b = take(H);
+    L.wq = take(NA * H); L.bq = take(NA);
+    L.total = o;
+    return L;
+}
+
+// write one row of n (multiple of 4) fp32 values into a K-major no-swizzle tile (tf32-rounded)
+template <int N>
+__device__ __forceinline__ void store_row_kmajor(uint8_t* tile, int r, int K, const float (&v)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; k += 4)
+        *reinterpret_cast<float4*>(tile + tc::kmajor_offset(r, k, K)) =
+            make_float4(to_tf32(v[k]), to_tf32(v[k + 1]), to_tf32(v[k + 2]), to_tf32(v[k + 3]));
+}
+
+template <int N>
+__device__ __forceinline__ void layer_norm_inplace(float (&v)[N], const float* __restrict__ w, const float* __restrict__ b) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s += v[j];
+    const float mean = s * (1.0f / N);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) { v[j] -= mean; q = fmaf(v[j], v[j], q); }
+    const float rstd = rsqrtf(q * (1.0f / N) + kEps);
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = fmaf(v[j] * rstd, w[j], b[j]);
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_load_row(uint32_t taddr, float (&v)[N]) {
+#pragma unroll
+    for (int c = 0; c < N; c += 16) {
+        float t[16];
+        tc::tmem_ld16(taddr + c, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[c + j] = t[j];
+    }
+}
+
+__device__ __forceinline__ float sigmoid_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int H>
+__global__ void __launch_bounds__(kRows, 1)
+agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs, const float* __restrict__ h0,
+                 float* __restrict__ q_out, float* __restrict__ h_final, float* __restrict__ rnn_out, int T1,
+                 long long R, int D, int NA) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const TcLayout L = make_tc_layout(D, H, NA);
+    const int K1 = L.K1;
+    // ---- shared memory carve-up ------------------------------------------------------------------
+    uint8_t* sW1 = smem;                                  // [H  x K1] tf32, K-major
+    uint8_t* sW2 = sW1 + H * K1 * 4;                      // [H  x H ]
+    uint8_t* sWih = sW2 + H * H * 4;                      // [3H x H ]
+    uint8_t* sWhh = sWih + 3 * H * H * 4;                 // [3H x H ]
+    const int act_k = K1 > H ? K1 : H;
+    uint8_t* sA = sWhh + 3 * H * H * 4;                   // activation operand tile [128 x max(K1, H)]
+    uint8_t* sH = sA + kRows * act_k * 4;                 // hidden state [128 x H], operand layout, fp32 (tf32-rounded)
+    float* sObs = reinterpret_cast<float*>(sH + kRows * H * 4);   // staged obs tile [128][D]
+    // small params: sP is biased so that sP[L.x] addresses the copy of params[L.x] for every vector / head offset
+    float* sP = sObs + ((kRows * D + 3) & ~3) - L.small;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long row0 = (long long)blockIdx.x * kRows;
+    const int n_valid = (int)min((long long)kRows, R - row0);
+    const bool valid = tid < n_valid;
+    constexpr uint32_t kCols = 4 * H <= 32 ? 32 : (4 * H <= 64 ? 64 : (4 * H <= 128 ? 128 : 256));
+
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, kCols);
+    if (tid == 0) tc::mbar_init(&bar, 1);
+
+    // weights -> operand layout (tf32-rounded once), small vectors -> sP (same offsets as `params`)
+    auto stage_matrix = [&](uint8_t* dst, int off, int rows, int K) {
+        for (int i = tid; i < rows * K; i += kRows) {
+            const int r = i / K, k = i - r * K;
+            *reinterpret_cast<float*>(dst + tc::kmajor_offset(r, k, K)) = to_tf32(params[off + i]);
+        }
+    };
+    stage_matrix(sW1, L.w1, H, K1);
+    stage_matrix(sW2, L.w2, H, H);
+    stage_matrix(sWih, L.wih, 3 * H, H);
+    stage_matrix(sWhh, L.whh, 3 * H, H);
+    for (int i = L.small + tid; i < L.total; i += kRows) sP[i] = params[i];
+    // hidden state: kept unrounded (the tensor core only truncates it as an operand; the z*h term sees fp32)
+#pragma unroll
+    for (int k = 0; k < H; k += 4) {
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h0 != nullptr && valid) h = *reinterpret_cast<const float4*>(h0 + (row0 + tid) * H + k);
+        *reinterpret_cast<float4*>(sH + tc::kmajor_offset(tid, k, H)) = h;
+    }
+    // obs tile of step 0
+    auto prefetch_obs = [&](int t) {
+        const float* src = obs + ((long long)t * R + row0) * D;
+        const int n = n_valid * D;
+        for (int i = tid; i < n; i += kRows)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(sObs + i)), "l"(src + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch_obs(0);
+
+    tc::fence_smem_to_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+
+    const uint32_t idesc_h = tc::make_idesc_tf32(128, H);
+    const uint32_t idesc_2h = tc::make_idesc_tf32(128, 2 * H);
+    auto desc = [&](const uint8_t* base, int row_off, int K, int kk) {
+        // tile with K columns; operand starts at row `row_off` (multiple of 8), k-step kk (8 tf32 each)
+        return tc::make_desc(tc::smem_u32(base) + (uint32_t)(row_off >> 3) * (uint32_t)(K >> 2) * 128u + kk * 256u, 128u,
+                             (uint32_t)(K >> 2) * 128u);
+    };
+    // after the activation tile was written: make it visible to the tensor core, then one thread issues
+    auto publish = [&]() {
+        tc::fence_smem_to_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    };
+    auto wait_mma = [&]() {
+        tc::mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc::fence_after_sync();
+    };
+
+    for (int t = 0; t < T1; ++t) {
+        // ---- A. LayerNorm(D) of this thread's obs row -> sA [128 x K1] ------------------------------------
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // obs tile landed and is visible to every thread
+        {
+            const float* o = sObs + tid * D;
+            float s = 0.f;
+            for (int k = 0; k < D; ++k) s += valid ? o[k] : 0.f;
+            const float mean = s / (float)D;
+            float qv = 0.f;
+            for (int k = 0; k < D; ++k) { const float d = (valid ? o[k] : 0.f) - mean; qv = fmaf(d, d, qv); }
+            const float rstd = rsqrtf(qv / (float)D + kEps);
+            for (int k = 0; k < K1; k += 4) {
+                float x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kk = k + u;
+                    x[u] = kk < D ? to_tf32(fmaf(((valid ? o[kk] : 0.f) - mean) * rstd, sP[L.ln0_w + kk], sP[L.ln0_b + kk])) : 0.f;
+                }
+                *reinterpret_cast<float4*>(sA + tc::kmajor_offset(tid, k, K1)) = make_float4(x[0], x[1], x[2], x[3]);
+            }
+        }
+        publish();                                         // also: every thread is done reading sObs
+        if (t + 1 < T1) prefetch_obs(t + 1);
+        if (tid == 0) {
+            for (int kk = 0; kk < K1 / 8; ++kk)
+                tc::mma_tf32(tmem, desc(sA, 0, K1, kk), desc(sW1, 0, K1, kk), idesc_h, kk > 0);
+            tc::mma_commit(&bar);
+        }
+        wait_mma();
+
+        // ---- B. fc1 epilogue: bias, ReLU, LayerNorm -> sA [128 x H] -----------------------------------------
+        float v[H];
+        tmem_load_row<H>(lane_addr, v);
+#pragma unroll
+        for (int j = 0; j < H; ++j) v[j] = fmaxf(v[j] + sP[L.b1 + j], 0.f);
+        layer_norm_inplace<H>(v, sP + L.ln1_w, sP + L.ln1_b);
+        store_row_kmajor<H>(sA, tid, H, v);
+        publish();
+        if (tid == 0) {
+            for (int kk = 0; kk < H / 8; ++kk)
+                tc::mma_tf32(tmem, desc(sA, 0, H, kk), desc(sW2, 0, H, kk), idesc_h, kk > 0);
+            tc::mma_commit(&bar);
+        }
+        wait_mma();
+
+        // ---- C. fc2 epilogue -> sA; then all gate GEMMs ------------------------------------------------------
+        tmem_load_row<H>(lane_addr, v);
+#pragma unroll
+        for (int j = 0; j < H; ++j) v[j] = fmaxf(v[j] + sP[L.b2 + j], 0.f);
+        layer_norm_inplace<H>(v, sP + L.ln2_w, sP + L.ln2_b);
+        store_row_kmajor<H>(sA, tid, H, v);
+        publish();
+        if (tid == 0) {
+            for (int kk = 0; kk < H / 8; ++kk)         // r | z : x part, then h part accumulated on top
+                tc::mma_tf32(tmem + H, desc(sA, 0, H, kk), desc(sWih, 0, H, kk), idesc_2h, kk > 0);
+            for (int kk = 0; kk < H / 8; ++kk)
+                tc::mma_tf32(tmem + H, desc(sH, 0, H, kk), desc(sWhh, 0, H, kk), idesc_2h, true);
+            for (int kk = 0; kk < H / 8; ++kk)         // i_n
+                tc::mma_tf32(tmem, desc(sA, 0, H, kk), desc(sWih, 2 * H, H, kk), idesc_h, kk > 0);
+            for (int kk = 0; kk < H / 8; ++kk)         // h_n
+                tc::mma_tf32(tmem + 3 * H, desc(sH, 0, H, kk), desc(sWhh, 2 * H, H, kk), idesc_h, kk > 0);
+            tc::mma_commit(&bar);
+        }
+        wait_mma();
+
+        // ---- D. GRU gates (PyTorch order r, z, n), new hidden -> sH, LayerNorm, head -------------------------
+#pragma unroll
+        for (int c = 0; c < H; c += 16) {
+            float gr[16], gz[16], gin[16], ghn[16];
+            tc::tmem_ld16(lane_addr + H + c, gr);
+            tc::tmem_ld16(lane_addr + 2 * H + c, gz);
+            tc::tmem_ld16(lane_addr + c, gin);
+            tc::tmem_ld16(lane_addr + 3 * H + c, ghn);
+#pragma unroll
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+                const float4 hp = *reinterpret_cast<const float4*>(sH + tc::kmajor_offset(tid, c + j4, H));
+                const float hprev[4] = {hp.x, hp.y, hp.z, hp.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = c + j4 + u;
+                    const float rr = sigmoid_(gr[j4 + u] + sP[L.bih + j] + sP[L.bhh + j]);
+                    const float zz = sigmoid_(gz[j4 + u] + sP[L.bih + H + j] + sP[L.bhh + H + j]);
+                    const float nn = tanhf(gin[j4 + u] + sP[L.bih + 2 * H + j] + rr * (ghn[j4 + u] + sP[L.bhh + 2 * H + j]));
+                    v[j] = (1.0f - zz) * nn + zz * hprev[u];
+                }
+            }
+        }
+        // the MMAs that read sH have completed (we waited on their commit), so it can be overwritten in place;
+        // the hidden state is carried in fp32 registers-to-smem precision (tf32 rounding only affects operands)
+#pragma unroll
+        for (int k = 0; k < H; k += 4)
+            *reinterpret_cast<float4*>(sH + tc::kmajor_offset(tid, k, H)) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+        if (t == T1 - 1 && h_final != nullptr && valid) {
+#pragma unroll
+            for (int k = 0; k < H; k += 4)
+                *reinterpret_cast<float4*>(h_final + (row0 + tid) * H + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+        }
+        layer_norm_inplace<H>(v, sP + L.ln3_w, sP + L.ln3_b);
+        if (valid) {
+            if (rnn_out != nullptr) {
+                float* dst = rnn_out + ((long long)t * R + row0 + tid) * H;
+#pragma unroll
+                for (int k = 0; k < H; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+            }
+            if (q_out != nullptr) {
+                float* qd = q_out + ((long long)t * R + row0 + tid) * NA;
+                for (int a = 0; a < NA; ++a) {
+                    float acc = sP[L.bq + a];
+#pragma unroll
+                    for (int j = 0; j < H; ++j) acc = fmaf(v[j], sP[L.wq + a * H + j], acc);
+                    qd[a] = acc;
+                }
+            }
+        }
+        // next step's stage A overwrites sA only after its own __syncthreads; sH is published by stage A's publish()
+    }
+
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, kCols);
+}
+
+template <int H>
+size_t tc_smem_bytes(int D, int NA) {
+    const TcLayout L = make_tc_layout(D, H, NA);
+    const int act_k = L.K1 > H ? L.K1 : H;
+    return (size_t)4 * (H * L.K1 + H * H + 6 * H * H + kRows * act_k + kRows * H + ((kRows * D + 3) & ~3) +
+                        (L.total - L.small)) + 128;
+}
+
+template <int H>
+int launch_tc(const float* params, const float* obs, const float* h0, float* q, float* h_final, float* rnn_out,
+              int T1, long long R, int D, int NA, cudaStream_t st) {
+    const size_t smem = tc_smem_bytes<H>(D, NA);
+    if (smem > 227 * 1024) return MM_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(agentq_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
+    const long long tiles = (R + kRows - 1) / kRows;
+    agentq_tc_kernel<H><<<(unsigned)tiles, kRows, smem, st>>>(params, obs, h0, q, h_final, rnn_out, T1, R, D, NA);
+    return mm::check_launch();
+}
+
+}  // namespace
+
+extern "C" int mm_agentq_tc_param_count(int32_t D, int32_t H, int32_t NA) {
+    if (D <= 0 || D > 96 || (H != 32 && H != 64) || NA <= 0 || NA > 16) return MM_ERR_UNSUPPORTED;
+    return make_tc_layout(D, H, NA).total;
+}
+
+// offsets[18]: ln0_w, ln0_b, w1, b1, ln1_w, ln1_b, w2, b2, ln2_w, ln2_b, wih, whh, bih, bhh, ln3_w, ln3_b, wq, bq
+extern "C" int mm_agentq_tc_param_offsets(int32_t D, int32_t H, int32_t NA, int32_t* offsets_host) {
+    if (!offsets_host || mm_agentq_tc_param_count(D, H, NA) < 0) return MM_ERR_UNSUPPORTED;
+    const TcLayout L = make_tc_layout(D, H, NA);
+    const int o[18] = {L.ln0_w, L.ln0_b, L.w1, L.b1, L.ln1_w, L.ln1_b, L.w2, L.b2, L.ln2_w, L.ln2_b,
+                       L.wih, L.whh, L.bih, L.bhh, L.ln3_w, L.ln3_b, L.wq, L.bq};
+    for (int i = 0; i < 18; ++i) offsets_host[i] = o[i];
+    return MM_OK;
+}
+
+extern "C" int mm_agentq_tc_forward(const float* params, const float* obs, const float* h0, float* q,
+                                    float* h_final, float* rnn_out, int32_t T1, int64_t R, int32_t D, int32_t H,
+                                    int32_t NA, void* stream) {
+    if (!params || !obs || T1 <= 0 || R <= 0) return MM_ERR_BAD_ARG;
+    if (mm_agentq_tc_param_count(D, H, NA) < 0) return MM_ERR_UNSUPPORTED;
+    if (rnn_out && !mm::aligned(rnn_out, 16)) return MM_ERR_BAD_ARG;
+    if (h0 && !mm::aligned(h0, 16)) return MM_ERR_BAD_ARG;
+    if (h_final && !mm::aligned(h_final, 16)) return MM_ERR_BAD_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (H == 64) return launch_tc<64>(params, obs, h0, q, h_final, rnn_out, T1, R, D, NA, st);
+    return launch_tc<32>(params, obs, h0, q, h_final, rnn_out, T1, R, D, NA, st);
+}

@@ -1,0 +1,101 @@
+// tcgen05 / TMEM / mbarrier building blocks (inline PTX) for the sm_100a tensor-core kernels.
+//
+// Operand layout used everywhere here: K-major, no swizzle ("interleave").  In units of 16 bytes the
+// canonical layout is ((8, n), 2) : ((1, SBO), LBO): a core matrix is 8 rows x 16 B stored contiguously
+// (128 B); LBO is the byte distance between the two core matrices one MMA consumes along K, SBO the
+// distance between consecutive 8-row groups.  For a tile of ROWS x K fp32 (tf32) elements stored as
+// [ROWS/8][K/4][8][4]:  LBO = 128 B, SBO = (K/4) * 128 B, and the descriptor of k-step kk (UMMA_K = 8
+// tf32 = 32 B = two core matrices) starts at base + kk * 256 B.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of element (r, k) of a K-major no-swizzle tf32 tile with K columns (K % 8 == 0)
+__device__ __forceinline__ uint32_t kmajor_offset(int r, int k, int K) {
+    return (uint32_t)((((r >> 3) * (K >> 2) + (k >> 2)) << 7) + ((r & 7) << 4) + ((k & 3) << 2));
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version = 1 [46,48), layout_type = 0 (SWIZZLE_NONE) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, A and B K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4)            // c_format = F32
+         | (2u << 7)            // a_format = TF32
+         | (2u << 10)           // b_format = TF32
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {        // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (the tensor core's operand reads)
+__device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// Bounded wait: a wrong descriptor must end in a trap, never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+// 32 lanes x 16 consecutive 32-bit columns: thread `lane` of warp w gets TMEM lane 32*(w%4)+lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+}  // namespace tc

@@ -1,0 +1,71 @@
+// Self-test of the tcgen05 building blocks: D[128 x N] = A[128 x K] * B[N x K]^T with kind::tf32, one CTA,
+// operands staged by plain loads into the K-major no-swizzle layout, accumulator in TMEM, read back with
+// tcgen05.ld.  Exists so that descriptor / layout mistakes show up in a 2-second GPU test
+// (tests/test_tc_gpu.py) and not inside the fused network kernels that reuse tc_common.cuh.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(128, 1)
+tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* sA = smem;                         // 128 x K tf32
+    uint8_t* sB = smem + 128 * K * 4;           // N x K tf32
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t ncols = 32;
+    while ((int)ncols < N) ncols <<= 1;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) tc::mbar_init(&bar, 1);
+    for (int i = tid; i < 128 * K; i += 128) {
+        const int r = i / K, k = i - r * K;
+        *reinterpret_cast<float*>(sA + tc::kmajor_offset(r, k, K)) = A[i];
+    }
+    for (int i = tid; i < N * K; i += 128) {
+        const int r = i / K, k = i - r * K;
+        *reinterpret_cast<float*>(sB + tc::kmajor_offset(r, k, K)) = B[i];
+    }
+    tc::fence_smem_to_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_tf32(128, N);
+        const uint32_t sbo = (uint32_t)(K >> 2) * 128u;
+        for (int kk = 0; kk < K / 8; ++kk) {
+            const uint64_t da = tc::make_desc(tc::smem_u32(sA) + kk * 256, 128, sbo);
+            const uint64_t db = tc::make_desc(tc::smem_u32(sB) + kk * 256, 128, sbo);
+            tc::mma_tf32(tmem, da, db, idesc, kk > 0);
+        }
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    const int row = warp * 32 + lane;
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (c + j < N) D[row * N + c + j] = v[j];
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, ncols);
+}
+
+}  // namespace
+
+extern "C" int mm_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, void* stream) {
+    if (!A || !B || !D || N < 16 || N > 256 || N % 16 || K < 8 || K % 8 || K > 128) return MM_ERR_BAD_ARG;
+    const size_t smem = (size_t)(128 + N) * K * 4;
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
+    tc_gemm_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, B, D, N, K);
+    return mm::check_launch();
+}

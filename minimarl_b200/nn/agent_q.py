@@ -66,8 +66,44 @@ def pack_agentq(sd, D, H, NA, device, prefix=""):
     return buf
 
 
-def agentq_forward(packed, obs, h0, D, H, NA, want_q=True, want_rnn_out=False):
-    """obs [T1, R, D] (or [R, D]); h0 [R, H] or None.  Returns (q [T1,R,NA], h_final [R,H], rnn_out|None)."""
+def agentq_tc_layout(D, H, NA):
+    lib = _lib.lib()
+    total = lib.mm_agentq_tc_param_count(D, H, NA)
+    if total < 0:
+        return None, None
+    offs = (C.c_int32 * 18)()
+    _lib.check(lib.mm_agentq_tc_param_offsets(D, H, NA, offs))
+    return total, dict(zip(_OFFSET_NAMES, list(offs)))
+
+
+def pack_agentq_tc(sd, D, H, NA, device, prefix=""):
+    """Parameter buffer of the tensor-core kernel: the PyTorch tensors as they are ([out][in] matrices), only
+    the Linear(D,H) weight zero-padded to a multiple of 8 input columns."""
+    total, o = agentq_tc_layout(D, H, NA)
+    buf = torch.zeros(total, dtype=torch.float32, device=device)
+    g = lambda k: sd[prefix + k].detach().to(device=device, dtype=torch.float32)
+
+    def put(name, t):
+        t = t.reshape(-1)
+        buf[o[name]:o[name] + t.numel()] = t
+
+    K1 = (D + 7) // 8 * 8
+    w1 = torch.zeros((H, K1), dtype=torch.float32, device=device)
+    w1[:, :D] = g("rnn.mlp.fc1.0.weight")
+    put("w1", w1); put("w2", g("rnn.mlp.fc2.0.0.weight"))
+    put("wih", g("rnn.rnn.rnn.weight_ih_l0")); put("whh", g("rnn.rnn.rnn.weight_hh_l0"))
+    put("ln0_w", g("rnn.feature_norm.weight")); put("ln0_b", g("rnn.feature_norm.bias"))
+    put("b1", g("rnn.mlp.fc1.0.bias")); put("ln1_w", g("rnn.mlp.fc1.2.weight")); put("ln1_b", g("rnn.mlp.fc1.2.bias"))
+    put("b2", g("rnn.mlp.fc2.0.0.bias")); put("ln2_w", g("rnn.mlp.fc2.0.2.weight")); put("ln2_b", g("rnn.mlp.fc2.0.2.bias"))
+    put("bih", g("rnn.rnn.rnn.bias_ih_l0")); put("bhh", g("rnn.rnn.rnn.bias_hh_l0"))
+    put("ln3_w", g("rnn.rnn.norm.weight")); put("ln3_b", g("rnn.rnn.norm.bias"))
+    put("wq", g("q.action_out.weight")); put("bq", g("q.action_out.bias"))
+    return buf
+
+
+def agentq_forward(packed, obs, h0, D, H, NA, want_q=True, want_rnn_out=False, tensor_cores=False):
+    """obs [T1, R, D] (or [R, D]); h0 [R, H] or None.  Returns (q [T1,R,NA], h_final [R,H], rnn_out|None).
+    ``tensor_cores`` selects mm_agentq_tc_forward (tcgen05, TF32) and needs a buffer from pack_agentq_tc."""
     seq = obs.dim() == 3
     if not seq:
         obs = obs.unsqueeze(0)
@@ -79,11 +115,23 @@ def agentq_forward(packed, obs, h0, D, H, NA, want_q=True, want_rnn_out=False):
     rnn_out = torch.empty((T1, R, H), **z) if want_rnn_out else None
     if h0 is not None:
         h0 = h0.reshape(R, H).contiguous()
-    _lib.check(_lib.lib().mm_agentq_forward(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(h0), _lib.ptr(q),
-                                            _lib.ptr(h_final), _lib.ptr(rnn_out), T1, R, D, H, NA, _lib.stream()))
+    fn = _lib.lib().mm_agentq_tc_forward if tensor_cores else _lib.lib().mm_agentq_forward
+    _lib.check(fn(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(h0), _lib.ptr(q), _lib.ptr(h_final), _lib.ptr(rnn_out),
+                  T1, R, D, H, NA, _lib.stream()))
     if not seq and q is not None:
         q = q[0]
     return q, h_final, rnn_out
+
+
+def _tc_fits(D, H, NA):
+    """Shared-memory budget of agentq_tc.cu (weights + activation tile + hidden tile + obs stage + vectors)."""
+    total, o = agentq_tc_layout(D, H, NA)
+    if total is None:
+        return False
+    K1 = (D + 7) // 8 * 8
+    small = total - o["ln0_w"]
+    nbytes = 4 * (H * K1 + 7 * H * H + 128 * max(K1, H) + 128 * H + (128 * D + 3) // 4 * 4 + small) + 128
+    return nbytes <= 227 * 1024
 
 
 # ---- module tree (reference names) ---------------------------------------------------------------
@@ -189,8 +237,13 @@ class AgentQFunction(nn.Module):
         self.q = ACTLayer(act_dim, self.hidden_size, args.use_orthogonal, gain=args.gain)
         self.to(self.device)
         self._packed, self._packed_key = None, None
+        self._packed_tc, self._packed_tc_key = None, None
         self.fusable = (args.layer_N == 1 and args.recurrent_N == 1 and args.use_feature_normalization and
                         args.use_ReLU and self.hidden_size in (32, 64) and self.input_dim <= 96)
+        # "tf32": no-grad passes run on the tensor cores (tcgen05, TF32 operands, ~1e-3 relative on Q);
+        # "fp32": FFMA kernel, ~1e-5 of the reference.  The tensor-core tile needs D <= ~56 at H = 64.
+        self.precision = getattr(args, "fused_precision", "tf32")
+        self.tc_ok = self.fusable and _tc_fits(self.input_dim, self.hidden_size, self.act_dim)
 
     def packed(self):
         """Packed parameter buffer for the kernel, rebuilt only when a parameter changed."""
@@ -200,6 +253,13 @@ class AgentQFunction(nn.Module):
             self._packed_key = key
         return self._packed
 
+    def packed_tc(self):
+        key = tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        if self._packed_tc is None or key != self._packed_tc_key:
+            self._packed_tc = pack_agentq_tc(self.state_dict(), self.input_dim, self.hidden_size, self.act_dim, self.device)
+            self._packed_tc_key = key
+        return self._packed_tc
+
     def forward(self, obs, rnn_states):
         obs = torch.as_tensor(obs).to(**self.tpdv) if not torch.is_tensor(obs) else obs.to(**self.tpdv)
         rnn_states = (torch.as_tensor(rnn_states) if not torch.is_tensor(rnn_states) else rnn_states).to(**self.tpdv)
@@ -207,7 +267,11 @@ class AgentQFunction(nn.Module):
         needs_graph = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if self.fusable and not needs_graph:
             h0 = rnn_states[0] if rnn_states.dim() == 3 else rnn_states
-            q, h_final, _ = agentq_forward(self.packed(), obs, h0, self.input_dim, self.hidden_size, self.act_dim)
+            if self.precision == "tf32" and self.tc_ok:
+                q, h_final, _ = agentq_forward(self.packed_tc(), obs, h0, self.input_dim, self.hidden_size,
+                                               self.act_dim, tensor_cores=True)
+            else:
+                q, h_final, _ = agentq_forward(self.packed(), obs, h0, self.input_dim, self.hidden_size, self.act_dim)
             return q, h_final
         if no_sequence:
             obs = obs[None]

@@ -21,7 +21,7 @@ def _args(**over):
         mixer_hidden_dim=32, hypernet_hidden_dim=64, hypernet_layers=2, use_per=True, per_eps=1e-6, per_nu=0.9,
         use_huber_loss=False, use_popart=False, lr=5e-4, tau=0.005, opti_eps=1e-5, episode_length=12,
         use_same_share_obs=True, use_double_q=True, gamma=0.99, max_grad_norm=10.0, epsilon_start=1.0,
-        epsilon_finish=0.05, epsilon_anneal_time=50000, seed=1, weight_decay=0)
+        epsilon_finish=0.05, epsilon_anneal_time=50000, seed=1, weight_decay=0, fused_precision="fp32")
     for k, v in over.items():
         setattr(a, k, v)
     return a
