@@ -228,7 +228,7 @@ def learner_section(dev, steps):
         mixer_hidden_dim=32, hypernet_hidden_dim=64, hypernet_layers=2, use_per=True, per_eps=1e-6, per_nu=0.9,
         use_huber_loss=False, use_popart=False, lr=5e-4, tau=0.005, opti_eps=1e-5, episode_length=T,
         use_same_share_obs=True, use_double_q=True, gamma=0.99, max_grad_norm=10.0, epsilon_start=1.0,
-        epsilon_finish=0.05, epsilon_anneal_time=50000, seed=1)
+        epsilon_finish=0.05, epsilon_anneal_time=50000, seed=1, fused_precision="tf32")
     info = {"policy_0": {"obs_space": Box(np.zeros(D), np.ones(D)), "share_obs_space": Box(np.zeros(A * D), np.ones(A * D)),
                          "act_space": Discrete(NA)}}
     buf = PrioritizedRecReplayBuffer(0.6, info, {"policy_0": [0, 1]}, S, T, True, False, device=dev)
@@ -269,8 +269,12 @@ def learner_section(dev, steps):
     # component timings (each in isolation, after the full updates)
     ms_sample, sample = timed(lambda: buf.sample(B, beta=0.4, p_id="policy_0"), 5)
     stacked = torch.cat(list(sample[0]["policy_0"]), dim=-2)
+    from minimarl_b200.nn.agent_q import agentq_forward
+    net = policy.q_network
+    h0 = torch.zeros(A * B, 64, device=dev)
     with torch.no_grad():
-        ms_agent, _ = timed(lambda: policy.q_network(stacked, torch.zeros(A * B, 64, device=dev)), 5)
+        ms_agent_tc, _ = timed(lambda: agentq_forward(net.packed_tc(), stacked, h0, D, 64, NA, tensor_cores=True), 5)
+        ms_agent, _ = timed(lambda: agentq_forward(net.packed(), stacked, h0, D, 64, NA), 5)
         qs = torch.randn((T, B, A), device=dev)
         ms_mixer, _ = timed(lambda: trainer.target_mixer(qs, sample[1]["policy_0"][:-1]), 5)
     rows = (T + 1) * A * B
@@ -283,8 +287,12 @@ def learner_section(dev, steps):
         "ms_per_update": ms_update, "loss": float(info_["loss"]),
         "sample_gather": {"ms": ms_sample, "algorithmic_GBps": gather_bytes / (ms_sample * 1e-3) / 1e9,
                           "frac_of_measured_hbm": gather_bytes / (ms_sample * 1e-3) / 1e9 / peak},
-        "agentq_forward": {"ms": ms_agent, "rows_x_steps": rows, "TFLOPs": rows * 64000 / (ms_agent * 1e-3) / 1e12,
-                           "note": "fused fp32 FFMA kernel (target / greedy passes); 64 kFLOP per (row, step)"},
+        "agentq_forward_tcgen05": {"ms": ms_agent_tc, "rows_x_steps": rows,
+                                   "TFLOPs": rows * 64000 / (ms_agent_tc * 1e-3) / 1e12,
+                                   "note": "fused tcgen05 kernel (TF32 in, fp32 TMEM accumulators): target / greedy / "
+                                           "rollout passes; 64 kFLOP per (row, step); 64 CTAs of 128 rows"},
+        "agentq_forward_fp32": {"ms": ms_agent, "TFLOPs": rows * 64000 / (ms_agent * 1e-3) / 1e12,
+                                "note": "fused FFMA kernel, the 1e-5 parity path"},
         "mixer_forward": {"ms": ms_mixer, "rows": T * B, "TFLOPs": T * B * 54528 / (ms_mixer * 1e-3) / 1e12},
     }
 

@@ -8,10 +8,11 @@
 //     gates [128 x H ] x [H x 2H] (x)  + [128 x H] x [H x 2H] (h)  -> TMEM cols [H, 3H)   r | z, accumulated
 //           [128 x H ] x [H x H ] (x)  -> TMEM cols [0, H)            i_n
 //           [128 x H ] x [H x H ] (h)  -> TMEM cols [3H, 4H)          h_n
-// One CTA = 128 rows = 128 threads; thread r owns row r end to end (TMEM lane r), so bias, ReLU,
-// LayerNorm, the GRU gate math and the 5-wide head are thread-local on the accumulators read back with
-// tcgen05.ld, and the activations go back to shared memory directly in the K-major operand layout of the
-// next MMA.  Weights (W1, W2, W_ih, W_hh = 124 KB as tf32 at H = 64) stay in shared memory for the whole
+// One CTA = 128 rows, 512 threads: the four warps that may address the same 32 TMEM lanes split the
+// H columns of those rows (H/4 each), so bias, ReLU and the GRU gate math are thread-local on the
+// accumulators read back with tcgen05.ld, LayerNorm needs one 4-way exchange through shared memory, and the
+// activations go back to shared memory directly in the K-major operand layout of the next MMA.  Gates use
+// MUFU tanh (sigmoid(x) = 0.5 tanh(x/2) + 0.5): 3 MUFU per hidden unit instead of ~75 FP32 instructions.  Weights (W1, W2, W_ih, W_hh = 124 KB as tf32 at H = 64) stay in shared memory for the whole
 // sequence, the hidden state lives in shared memory in operand layout, and the obs tile of step t+1 is
 // prefetched with cp.async while step t computes.  MMAs are issued by one thread and tracked with one
 // mbarrier (tcgen05.commit); waits are bounded (trap instead of hang).
@@ -56,47 +57,58 @@ __host__ __device__ inline TcLayout make_tc_layout(int D, int H, int NA) {
     return L;
 }
 
-// write one row of n (multiple of 4) fp32 values into a K-major no-swizzle tile (tf32-rounded)
+// MUFU-based activations: tanh.approx has ~2^-11 relative error, the same order as the TF32 operands
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+// 512 threads: thread (row = 32*(warp%4) + lane, part = warp/4) owns CPT = H/4 consecutive columns of its row.
+// (A warp may only touch TMEM lanes 32*(warp%4)..+31, so the four warps that share `warp%4` split the columns.)
+template <int H>
+struct Geo {
+    static constexpr int CPT = H / 4;
+};
+
+// LayerNorm over a row whose H values are spread over 4 threads: partial (sum, sum of squares) through
+// shared memory, one barrier.  var = E[x^2] - mean^2 in fp32 (inputs are O(1) post-ReLU / gate outputs).
+template <int H>
+__device__ __forceinline__ void layer_norm_split(float (&v)[H / 4], float2* red, int row, int part,
+                                                 const float* __restrict__ w, const float* __restrict__ b) {
+    constexpr int CPT = H / 4;
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) { s += v[j]; q = fmaf(v[j], v[j], q); }
+    red[row * 4 + part] = make_float2(s, q);
+    __syncthreads();
+    const float4 a = *reinterpret_cast<const float4*>(red + row * 4);
+    const float4 c = *reinterpret_cast<const float4*>(red + row * 4 + 2);
+    const float mean = (a.x + a.z + c.x + c.z) * (1.0f / H);
+    const float var = fmaxf((a.y + a.w + c.y + c.w) * (1.0f / H) - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + kEps);
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) v[j] = fmaf((v[j] - mean) * rstd, w[part * CPT + j], b[part * CPT + j]);
+}
+
 template <int N>
-__device__ __forceinline__ void store_row_kmajor(uint8_t* tile, int r, int K, const float (&v)[N]) {
+__device__ __forceinline__ void store_cols_kmajor(uint8_t* tile, int r, int k0, int K, const float (&v)[N], bool round) {
 #pragma unroll
     for (int k = 0; k < N; k += 4)
-        *reinterpret_cast<float4*>(tile + tc::kmajor_offset(r, k, K)) =
-            make_float4(to_tf32(v[k]), to_tf32(v[k + 1]), to_tf32(v[k + 2]), to_tf32(v[k + 3]));
+        *reinterpret_cast<float4*>(tile + tc::kmajor_offset(r, k0 + k, K)) =
+            round ? make_float4(to_tf32(v[k]), to_tf32(v[k + 1]), to_tf32(v[k + 2]), to_tf32(v[k + 3]))
+                  : make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
 }
 
-template <int N>
-__device__ __forceinline__ void layer_norm_inplace(float (&v)[N], const float* __restrict__ w, const float* __restrict__ b) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < N; ++j) s += v[j];
-    const float mean = s * (1.0f / N);
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < N; ++j) { v[j] -= mean; q = fmaf(v[j], v[j], q); }
-    const float rstd = rsqrtf(q * (1.0f / N) + kEps);
-#pragma unroll
-    for (int j = 0; j < N; ++j) v[j] = fmaf(v[j] * rstd, w[j], b[j]);
-}
-
-template <int N>
-__device__ __forceinline__ void tmem_load_row(uint32_t taddr, float (&v)[N]) {
-#pragma unroll
-    for (int c = 0; c < N; c += 16) {
-        float t[16];
-        tc::tmem_ld16(taddr + c, t);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[c + j] = t[j];
-    }
-}
-
-__device__ __forceinline__ float sigmoid_(float x) { return 1.0f / (1.0f + expf(-x)); }
+constexpr int kThreadsTc = 512;
 
 template <int H>
-__global__ void __launch_bounds__(kRows, 1)
+__global__ void __launch_bounds__(kThreadsTc, 1)
 agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs, const float* __restrict__ h0,
                  float* __restrict__ q_out, float* __restrict__ h_final, float* __restrict__ rnn_out, int T1,
                  long long R, int D, int NA) {
+    constexpr int CPT = Geo<H>::CPT;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -108,16 +120,20 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
     uint8_t* sWih = sW2 + H * H * 4;                      // [3H x H ]
     uint8_t* sWhh = sWih + 3 * H * H * 4;                 // [3H x H ]
     const int act_k = K1 > H ? K1 : H;
-    uint8_t* sA = sWhh + 3 * H * H * 4;                   // activation operand tile [128 x max(K1, H)]
-    uint8_t* sH = sA + kRows * act_k * 4;                 // hidden state [128 x H], operand layout, fp32 (tf32-rounded)
+    uint8_t* sA = sWhh + 3 * H * H * 4;                   // activation operand tile [128 x max(K1, H)]; also sYt
+    uint8_t* sH = sA + kRows * act_k * 4;                 // hidden state [128 x H], operand layout, fp32
     float* sObs = reinterpret_cast<float*>(sH + kRows * H * 4);   // staged obs tile [128][D]
+    float2* red = reinterpret_cast<float2*>(sObs + ((kRows * D + 3) & ~3));   // [128][4] LayerNorm partials
     // small params: sP is biased so that sP[L.x] addresses the copy of params[L.x] for every vector / head offset
-    float* sP = sObs + ((kRows * D + 3) & ~3) - L.small;
+    float* sP = reinterpret_cast<float*>(red + kRows * 4) - L.small;
+    float* sYt = reinterpret_cast<float*>(sA);            // [H][128] LayerNorm'ed GRU output, transposed, for the head
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = (warp & 3) * 32 + lane, part = warp >> 2;
+    const int c0 = part * CPT;
     const long long row0 = (long long)blockIdx.x * kRows;
     const int n_valid = (int)min((long long)kRows, R - row0);
-    const bool valid = tid < n_valid;
+    const bool valid = row < n_valid;
     constexpr uint32_t kCols = 4 * H <= 32 ? 32 : (4 * H <= 64 ? 64 : (4 * H <= 128 ? 128 : 256));
 
     if (warp == 0) tc::tmem_alloc(&tmem_slot, kCols);
@@ -125,7 +141,7 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
 
     // weights -> operand layout (tf32-rounded once), small vectors -> sP (same offsets as `params`)
     auto stage_matrix = [&](uint8_t* dst, int off, int rows, int K) {
-        for (int i = tid; i < rows * K; i += kRows) {
+        for (int i = tid; i < rows * K; i += kThreadsTc) {
             const int r = i / K, k = i - r * K;
             *reinterpret_cast<float*>(dst + tc::kmajor_offset(r, k, K)) = to_tf32(params[off + i]);
         }
@@ -134,19 +150,18 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
     stage_matrix(sW2, L.w2, H, H);
     stage_matrix(sWih, L.wih, 3 * H, H);
     stage_matrix(sWhh, L.whh, 3 * H, H);
-    for (int i = L.small + tid; i < L.total; i += kRows) sP[i] = params[i];
+    for (int i = L.small + tid; i < L.total; i += kThreadsTc) sP[i] = params[i];
     // hidden state: kept unrounded (the tensor core only truncates it as an operand; the z*h term sees fp32)
 #pragma unroll
-    for (int k = 0; k < H; k += 4) {
+    for (int k = 0; k < CPT; k += 4) {
         float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (h0 != nullptr && valid) h = *reinterpret_cast<const float4*>(h0 + (row0 + tid) * H + k);
-        *reinterpret_cast<float4*>(sH + tc::kmajor_offset(tid, k, H)) = h;
+        if (h0 != nullptr && valid) h = *reinterpret_cast<const float4*>(h0 + (row0 + row) * H + c0 + k);
+        *reinterpret_cast<float4*>(sH + tc::kmajor_offset(row, c0 + k, H)) = h;
     }
-    // obs tile of step 0
     auto prefetch_obs = [&](int t) {
         const float* src = obs + ((long long)t * R + row0) * D;
         const int n = n_valid * D;
-        for (int i = tid; i < n; i += kRows)
+        for (int i = tid; i < n; i += kThreadsTc)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(sObs + i)), "l"(src + i) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -157,7 +172,7 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t phase = 0;
 
     const uint32_t idesc_h = tc::make_idesc_tf32(128, H);
@@ -167,8 +182,7 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
         return tc::make_desc(tc::smem_u32(base) + (uint32_t)(row_off >> 3) * (uint32_t)(K >> 2) * 128u + kk * 256u, 128u,
                              (uint32_t)(K >> 2) * 128u);
     };
-    // after the activation tile was written: make it visible to the tensor core, then one thread issues
-    auto publish = [&]() {
+    auto publish = [&]() {            // activation tile written -> visible to the tensor core, all threads done
         tc::fence_smem_to_async();
         tc::fence_before_sync();
         __syncthreads();
@@ -179,30 +193,41 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
         phase ^= 1;
         tc::fence_after_sync();
     };
+    // K1 columns of the obs row are split over the 4 parts in chunks of 4 (k = 4*(part + 4*i) ...)
+    const int kq = K1 >> 2;           // float4 groups per row
 
     for (int t = 0; t < T1; ++t) {
-        // ---- A. LayerNorm(D) of this thread's obs row -> sA [128 x K1] ------------------------------------
+        // ---- A. LayerNorm(D) of the obs rows -> sA [128 x K1] ----------------------------------------------
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                                   // obs tile landed and is visible to every thread
+        __syncthreads();                                   // obs tile landed; previous step's head is done with sYt
         {
-            const float* o = sObs + tid * D;
-            float s = 0.f;
-            for (int k = 0; k < D; ++k) s += valid ? o[k] : 0.f;
-            const float mean = s / (float)D;
-            float qv = 0.f;
-            for (int k = 0; k < D; ++k) { const float d = (valid ? o[k] : 0.f) - mean; qv = fmaf(d, d, qv); }
-            const float rstd = rsqrtf(qv / (float)D + kEps);
-            for (int k = 0; k < K1; k += 4) {
+            const float* o = sObs + row * D;
+            float s = 0.f, qv = 0.f;
+            for (int g = part; g < kq; g += 4)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = 4 * g + u;
+                    const float x = (valid && k < D) ? o[k] : 0.f;
+                    s += x; qv = fmaf(x, x, qv);
+                }
+            red[row * 4 + part] = make_float2(s, qv);
+            __syncthreads();
+            const float4 a = *reinterpret_cast<const float4*>(red + row * 4);
+            const float4 c = *reinterpret_cast<const float4*>(red + row * 4 + 2);
+            const float mean = (a.x + a.z + c.x + c.z) / (float)D;
+            const float var = fmaxf((a.y + a.w + c.y + c.w) / (float)D - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + kEps);
+            for (int g = part; g < kq; g += 4) {
                 float x[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int kk = k + u;
-                    x[u] = kk < D ? to_tf32(fmaf(((valid ? o[kk] : 0.f) - mean) * rstd, sP[L.ln0_w + kk], sP[L.ln0_b + kk])) : 0.f;
+                    const int k = 4 * g + u;
+                    x[u] = k < D ? to_tf32(fmaf(((valid ? o[k] : 0.f) - mean) * rstd, sP[L.ln0_w + k], sP[L.ln0_b + k])) : 0.f;
                 }
-                *reinterpret_cast<float4*>(sA + tc::kmajor_offset(tid, k, K1)) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(sA + tc::kmajor_offset(row, 4 * g, K1)) = make_float4(x[0], x[1], x[2], x[3]);
             }
         }
-        publish();                                         // also: every thread is done reading sObs
+        publish();                                         // also: every thread is done reading sObs and `red`
         if (t + 1 < T1) prefetch_obs(t + 1);
         if (tid == 0) {
             for (int kk = 0; kk < K1 / 8; ++kk)
@@ -212,12 +237,12 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
         wait_mma();
 
         // ---- B. fc1 epilogue: bias, ReLU, LayerNorm -> sA [128 x H] -----------------------------------------
-        float v[H];
-        tmem_load_row<H>(lane_addr, v);
+        float v[CPT];
+        tc::tmem_ld<CPT>(lane_addr + c0, v);
 #pragma unroll
-        for (int j = 0; j < H; ++j) v[j] = fmaxf(v[j] + sP[L.b1 + j], 0.f);
-        layer_norm_inplace<H>(v, sP + L.ln1_w, sP + L.ln1_b);
-        store_row_kmajor<H>(sA, tid, H, v);
+        for (int j = 0; j < CPT; ++j) v[j] = fmaxf(v[j] + sP[L.b1 + c0 + j], 0.f);
+        layer_norm_split<H>(v, red, row, part, sP + L.ln1_w, sP + L.ln1_b);
+        store_cols_kmajor<CPT>(sA, row, c0, H, v, true);
         publish();
         if (tid == 0) {
             for (int kk = 0; kk < H / 8; ++kk)
@@ -227,11 +252,11 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
         wait_mma();
 
         // ---- C. fc2 epilogue -> sA; then all gate GEMMs ------------------------------------------------------
-        tmem_load_row<H>(lane_addr, v);
+        tc::tmem_ld<CPT>(lane_addr + c0, v);
 #pragma unroll
-        for (int j = 0; j < H; ++j) v[j] = fmaxf(v[j] + sP[L.b2 + j], 0.f);
-        layer_norm_inplace<H>(v, sP + L.ln2_w, sP + L.ln2_b);
-        store_row_kmajor<H>(sA, tid, H, v);
+        for (int j = 0; j < CPT; ++j) v[j] = fmaxf(v[j] + sP[L.b2 + c0 + j], 0.f);
+        layer_norm_split<H>(v, red, row, part, sP + L.ln2_w, sP + L.ln2_b);
+        store_cols_kmajor<CPT>(sA, row, c0, H, v, true);
         publish();
         if (tid == 0) {
             for (int kk = 0; kk < H / 8; ++kk)         // r | z : x part, then h part accumulated on top
@@ -247,55 +272,55 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
         wait_mma();
 
         // ---- D. GRU gates (PyTorch order r, z, n), new hidden -> sH, LayerNorm, head -------------------------
+        {
+            float gr[CPT], gz[CPT], gin[CPT], ghn[CPT];
+            tc::tmem_ld<CPT>(lane_addr + H + c0, gr);
+            tc::tmem_ld<CPT>(lane_addr + 2 * H + c0, gz);
+            tc::tmem_ld<CPT>(lane_addr + c0, gin);
+            tc::tmem_ld<CPT>(lane_addr + 3 * H + c0, ghn);
 #pragma unroll
-        for (int c = 0; c < H; c += 16) {
-            float gr[16], gz[16], gin[16], ghn[16];
-            tc::tmem_ld16(lane_addr + H + c, gr);
-            tc::tmem_ld16(lane_addr + 2 * H + c, gz);
-            tc::tmem_ld16(lane_addr + c, gin);
-            tc::tmem_ld16(lane_addr + 3 * H + c, ghn);
-#pragma unroll
-            for (int j4 = 0; j4 < 16; j4 += 4) {
-                const float4 hp = *reinterpret_cast<const float4*>(sH + tc::kmajor_offset(tid, c + j4, H));
+            for (int j4 = 0; j4 < CPT; j4 += 4) {
+                const float4 hp = *reinterpret_cast<const float4*>(sH + tc::kmajor_offset(row, c0 + j4, H));
                 const float hprev[4] = {hp.x, hp.y, hp.z, hp.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int j = c + j4 + u;
-                    const float rr = sigmoid_(gr[j4 + u] + sP[L.bih + j] + sP[L.bhh + j]);
-                    const float zz = sigmoid_(gz[j4 + u] + sP[L.bih + H + j] + sP[L.bhh + H + j]);
-                    const float nn = tanhf(gin[j4 + u] + sP[L.bih + 2 * H + j] + rr * (ghn[j4 + u] + sP[L.bhh + 2 * H + j]));
-                    v[j] = (1.0f - zz) * nn + zz * hprev[u];
+                    const int j = c0 + j4 + u;
+                    const float rr = sigmoid_fast(gr[j4 + u] + sP[L.bih + j] + sP[L.bhh + j]);
+                    const float zz = sigmoid_fast(gz[j4 + u] + sP[L.bih + H + j] + sP[L.bhh + H + j]);
+                    const float nn = tanh_fast(gin[j4 + u] + sP[L.bih + 2 * H + j] + rr * (ghn[j4 + u] + sP[L.bhh + 2 * H + j]));
+                    v[j4 + u] = (1.0f - zz) * nn + zz * hprev[u];
                 }
             }
         }
-        // the MMAs that read sH have completed (we waited on their commit), so it can be overwritten in place;
-        // the hidden state is carried in fp32 registers-to-smem precision (tf32 rounding only affects operands)
-#pragma unroll
-        for (int k = 0; k < H; k += 4)
-            *reinterpret_cast<float4*>(sH + tc::kmajor_offset(tid, k, H)) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+        // the MMAs that read sH have completed (we waited on their commit), so it is overwritten in place
+        store_cols_kmajor<CPT>(sH, row, c0, H, v, false);
         if (t == T1 - 1 && h_final != nullptr && valid) {
 #pragma unroll
-            for (int k = 0; k < H; k += 4)
-                *reinterpret_cast<float4*>(h_final + (row0 + tid) * H + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+            for (int k = 0; k < CPT; k += 4)
+                *reinterpret_cast<float4*>(h_final + (row0 + row) * H + c0 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
         }
-        layer_norm_inplace<H>(v, sP + L.ln3_w, sP + L.ln3_b);
-        if (valid) {
-            if (rnn_out != nullptr) {
-                float* dst = rnn_out + ((long long)t * R + row0 + tid) * H;
+        layer_norm_split<H>(v, red, row, part, sP + L.ln3_w, sP + L.ln3_b);
+        if (rnn_out != nullptr && valid) {
+            float* dst = rnn_out + ((long long)t * R + row0 + row) * H + c0;
 #pragma unroll
-                for (int k = 0; k < H; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-            }
-            if (q_out != nullptr) {
-                float* qd = q_out + ((long long)t * R + row0 + tid) * NA;
-                for (int a = 0; a < NA; ++a) {
+            for (int k = 0; k < CPT; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+        }
+        if (q_out != nullptr) {
+            // head: y transposed into the (now free) activation tile, then thread (row, part) takes actions part, part+4, ...
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) sYt[(c0 + j) * kRows + row] = v[j];
+            __syncthreads();
+            if (valid) {
+                float* qd = q_out + ((long long)t * R + row0 + row) * NA;
+                for (int a = part; a < NA; a += 4) {
                     float acc = sP[L.bq + a];
-#pragma unroll
-                    for (int j = 0; j < H; ++j) acc = fmaf(v[j], sP[L.wq + a * H + j], acc);
+#pragma unroll 16
+                    for (int j = 0; j < H; ++j) acc = fmaf(sYt[j * kRows + row], sP[L.wq + a * H + j], acc);
                     qd[a] = acc;
                 }
             }
         }
-        // next step's stage A overwrites sA only after its own __syncthreads; sH is published by stage A's publish()
+        // stage A of the next step starts with a barrier before it overwrites sA / sYt
     }
 
     tc::fence_before_sync();
@@ -308,7 +333,7 @@ size_t tc_smem_bytes(int D, int NA) {
     const TcLayout L = make_tc_layout(D, H, NA);
     const int act_k = L.K1 > H ? L.K1 : H;
     return (size_t)4 * (H * L.K1 + H * H + 6 * H * H + kRows * act_k + kRows * H + ((kRows * D + 3) & ~3) +
-                        (L.total - L.small)) + 128;
+                        kRows * 8 + (L.total - L.small)) + 128;
 }
 
 template <int H>
@@ -319,7 +344,7 @@ int launch_tc(const float* params, const float* obs, const float* h0, float* q, 
     cudaError_t e = cudaFuncSetAttribute(agentq_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
     const long long tiles = (R + kRows - 1) / kRows;
-    agentq_tc_kernel<H><<<(unsigned)tiles, kRows, smem, st>>>(params, obs, h0, q, h_final, rnn_out, T1, R, D, NA);
+    agentq_tc_kernel<H><<<(unsigned)tiles, kThreadsTc, smem, st>>>(params, obs, h0, q, h_final, rnn_out, T1, R, D, NA);
     return mm::check_launch();
 }
 

@@ -130,7 +130,7 @@ def _tc_fits(D, H, NA):
         return False
     K1 = (D + 7) // 8 * 8
     small = total - o["ln0_w"]
-    nbytes = 4 * (H * K1 + 7 * H * H + 128 * max(K1, H) + 128 * H + (128 * D + 3) // 4 * 4 + small) + 128
+    nbytes = 4 * (H * K1 + 7 * H * H + 128 * max(K1, H) + 128 * H + (128 * D + 3) // 4 * 4 + 128 * 8 + small) + 128
     return nbytes <= 227 * 1024
 
 
