@@ -228,6 +228,45 @@ int mm_agentq_tc_param_offsets(int32_t D, int32_t H, int32_t NA, int32_t* offset
 int mm_agentq_tc_forward(const float* params, const float* obs, const float* h0, float* q, float* h_final,
                          float* rnn_out, int32_t T1, int64_t R, int32_t D, int32_t H, int32_t NA, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused policy + env rollout (the per-step body of MAGYM_Runner.collect_rollout,
+ * offpolicy/runner/shared/magym_runner.py:75-127, and of the vdn/qmix main loops, vdn/main.py:139-177):
+ * T steps of  agent network forward (tcgen05) -> eps-greedy action -> Checkers step -> next obs,
+ * for n_envs lockstep boards in ONE launch; nothing returns to the host between steps.
+ * Rows are (env, agent) pairs, row = 2*env + agent.  Every "t stride" is in elements between consecutive t
+ * so that outputs can land directly in replay-buffer slots ([T, S, ...] storage with S != n_envs).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mm_rollout_io {
+    uint32_t* env_state;        /* Checkers state planes [3][n_envs] (read unless do_reset, always written back) */
+    float* obs;                 /* slab t at obs + t*obs_t_stride, each [n_envs,2,47]; slabs 0..T are written
+                                   (slab 0 only when do_reset, otherwise it must hold the current observations) */
+    int64_t obs_t_stride;
+    int32_t* act_idx;           /* [T] slabs of [n_envs*2] chosen action indices, or NULL */
+    int64_t act_t_stride;
+    float* act_onehot;          /* [T] slabs of [n_envs*2, NA] one-hot actions, or NULL */
+    int64_t onehot_t_stride;
+    float* rewards;             /* [T] slabs of [n_envs*2], or NULL */
+    int64_t rew_t_stride;
+    float* dones;               /* [T] slabs of [n_envs*2] float32 0/1, or NULL */
+    int64_t done_t_stride;
+    float* dones_env;           /* [T] slabs of [n_envs] float32 0/1 (all agents done), or NULL */
+    int64_t denv_t_stride;
+    uint64_t step_offset;       /* Philox counter of step 0 (so consecutive rollouts draw fresh numbers) */
+    float eps;                  /* exploration rate: P(random action) per draw */
+    int32_t eps_per_env;        /* 0: one uniform per agent row (QMixPolicy.py:177-187); 1: one per env, all agents
+                                   of the env explore together (vdn/_network.py:52-58) */
+    int32_t do_reset;           /* 1: env.reset() first and write obs slab 0 */
+    int32_t freeze_after_done;  /* 1: a finished episode is no longer stepped (rewards 0, obs frozen), like
+                                   collect_rollout's `if not np.all(dones)` */
+    int32_t common_reward;      /* 1: every agent receives the team reward (use_common_reward, base_runner.py:346-348);
+                                   common_reward_lut[k0][k1] = float32(double(r0) + double(r1)) by food kind */
+} mm_rollout_io;
+
+int mm_qmix_rollout_tc(const float* params /* mm_agentq_tc layout, D = 47 */, const float* h0, float* h_final,
+                       float* q_out /* [T, n_envs*2, NA] or NULL */, const mm_rollout_io* io_host,
+                       const mm_checkers_cfg* cfg_host, const float* common_reward_lut_host /* float[9] or NULL */,
+                       int32_t T, int64_t n_envs, int32_t H, int32_t NA, uint64_t seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,17 @@ class SwitchCfg(C.Structure):
     ]
 
 
+class RolloutIO(C.Structure):
+    """struct mm_rollout_io"""
+    _fields_ = [
+        ("env_state", C.c_void_p), ("obs", C.c_void_p), ("obs_t_stride", C.c_int64),
+        ("act_idx", C.c_void_p), ("act_t_stride", C.c_int64), ("act_onehot", C.c_void_p), ("onehot_t_stride", C.c_int64),
+        ("rewards", C.c_void_p), ("rew_t_stride", C.c_int64), ("dones", C.c_void_p), ("done_t_stride", C.c_int64),
+        ("dones_env", C.c_void_p), ("denv_t_stride", C.c_int64), ("step_offset", C.c_uint64), ("eps", C.c_float),
+        ("eps_per_env", C.c_int32), ("do_reset", C.c_int32), ("freeze_after_done", C.c_int32), ("common_reward", C.c_int32),
+    ]
+
+
 _P = C.c_void_p
 SIGNATURES = {
     "mm_status_string": (C.c_char_p, [C.c_int]),
@@ -64,6 +75,8 @@ SIGNATURES = {
     "mm_agentq_tc_param_offsets": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "mm_agentq_tc_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                        C.c_int32, _P]),
+    "mm_qmix_rollout_tc": (C.c_int, [_P, _P, _P, _P, C.POINTER(RolloutIO), C.POINTER(CheckersCfg), C.POINTER(C.c_float),
+                                     C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _P]),
 }
 
 _lib = None

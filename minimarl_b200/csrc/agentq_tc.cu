@@ -18,7 +18,7 @@
 // mbarrier (tcgen05.commit); waits are bounded (trap instead of hang).
 // Precision: TF32 operands (round-to-nearest on every activation store and on the weights), fp32
 // accumulation and fp32 epilogues -> ~1e-3 relative on the Q-values; tests state the tolerance.
-#include "common.cuh"
+#include "checkers_core.cuh"
 #include "tc_common.cuh"
 
 namespace {
@@ -102,12 +102,26 @@ __device__ __forceinline__ void store_cols_kmajor(uint8_t* tile, int r, int k0, 
 }
 
 constexpr int kThreadsTc = 512;
+constexpr int kMaxNaEnv = 8;
 
-template <int H>
+// Device-side copy of mm_rollout_io plus the env configuration (only read by the ENV instantiation).
+struct RolloutDev {
+    mm_rollout_io io;
+    mm_checkers_cfg cfg;
+    float common[3][3];     // float32(python_double(reward_0 + reward_1)) by (food kind of agent 0, of agent 1)
+    uint2 seed;
+};
+
+// ENV == false: the sequence of observations is given (obs [T1, R, D]), pure network forward.
+// ENV == true : fused policy + env rollout.  Rows are (env, agent) pairs, row = 2*env + agent, so a CTA owns 64
+//   Checkers boards; after the head of step t the first four warps pick eps-greedy actions (Philox), step their
+//   boards with the shuffle-based transition of checkers_core.cuh and expand the next observations straight into
+//   the shared obs tile, which is both streamed to obs[t+1] in HBM and consumed by step t+1's LayerNorm.
+template <int H, bool ENV>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs, const float* __restrict__ h0,
                  float* __restrict__ q_out, float* __restrict__ h_final, float* __restrict__ rnn_out, int T1,
-                 long long R, int D, int NA) {
+                 long long R, int D, int NA, const __grid_constant__ RolloutDev ro) {
     constexpr int CPT = Geo<H>::CPT;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -126,7 +140,7 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
     float2* red = reinterpret_cast<float2*>(sObs + ((kRows * D + 3) & ~3));   // [128][4] LayerNorm partials
     // small params: sP is biased so that sP[L.x] addresses the copy of params[L.x] for every vector / head offset
     float* sP = reinterpret_cast<float*>(red + kRows * 4) - L.small;
-    float* sYt = reinterpret_cast<float*>(sA);            // [H][128] LayerNorm'ed GRU output, transposed, for the head
+    float* sYt = reinterpret_cast<float*>(sA);            // [NA][4][128] partial head sums (aliases the activation tile)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = (warp & 3) * 32 + lane, part = warp >> 2;
@@ -165,7 +179,31 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(sObs + i)), "l"(src + i) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    prefetch_obs(0);
+    ck::EnvRegs env_regs;
+    env_regs.food = env_regs.cells = env_regs.step = 0;
+    const long long env_id = (row0 + row) >> 1;
+    const long long n_envs = R >> 1;
+    if (ENV) {
+        if (part == 0) {
+            const long long e = valid ? env_id : n_envs - 1;
+            if (ro.io.do_reset) ck::reset_regs(env_regs);
+            else {
+                env_regs.food = ro.io.env_state[e];
+                env_regs.cells = ro.io.env_state[n_envs + e];
+                env_regs.step = ro.io.env_state[2 * n_envs + e];
+            }
+        }
+        if (ro.io.do_reset) {
+            if (part == 0) ck::fill_tile(sObs, row, row & 1, env_regs, ro.cfg);
+            __syncthreads();
+            float* dst = ro.io.obs + row0 * D;           // slab 0
+            for (int i = tid; i < n_valid * D; i += kThreadsTc) dst[i] = sObs[i];
+        } else {
+            prefetch_obs(0);
+        }
+    } else {
+        prefetch_obs(0);
+    }
 
     tc::fence_smem_to_async();
     tc::fence_before_sync();
@@ -177,20 +215,27 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
 
     const uint32_t idesc_h = tc::make_idesc_tf32(128, H);
     const uint32_t idesc_2h = tc::make_idesc_tf32(128, 2 * H);
-    auto desc = [&](const uint8_t* base, int row_off, int K, int kk) {
-        // tile with K columns; operand starts at row `row_off` (multiple of 8), k-step kk (8 tf32 each)
-        return tc::make_desc(tc::smem_u32(base) + (uint32_t)(row_off >> 3) * (uint32_t)(K >> 2) * 128u + kk * 256u, 128u,
+    auto desc = [&](const uint8_t* base, int row_off, int K) {
+        // tile with K columns; operand starts at row `row_off` (multiple of 8); k-step kk adds kk * 256 B, i.e.
+        // kk * 16 to the (address >> 4) field in the low bits of the descriptor
+        return tc::make_desc(tc::smem_u32(base) + (uint32_t)(row_off >> 3) * (uint32_t)(K >> 2) * 128u, 128u,
                              (uint32_t)(K >> 2) * 128u);
     };
+    // loop-invariant operand descriptors (only thread 0 uses them)
+    const uint64_t dA1 = desc(sA, 0, K1), dW1 = desc(sW1, 0, K1);
+    const uint64_t dA = desc(sA, 0, H), dHid = desc(sH, 0, H), dW2 = desc(sW2, 0, H);
+    const uint64_t dWih_rz = desc(sWih, 0, H), dWih_n = desc(sWih, 2 * H, H);
+    const uint64_t dWhh_rz = desc(sWhh, 0, H), dWhh_n = desc(sWhh, 2 * H, H);
     auto publish = [&]() {            // activation tile written -> visible to the tensor core, all threads done
         tc::fence_smem_to_async();
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
     };
-    auto wait_mma = [&]() {
-        tc::mbar_wait(&bar, phase);
+    auto wait_mma = [&]() {           // warp 0 polls the mbarrier, the other 15 warps sleep in the block barrier
+        if (warp == 0) tc::mbar_wait(&bar, phase);
         phase ^= 1;
+        __syncthreads();
         tc::fence_after_sync();
     };
     // K1 columns of the obs row are split over the 4 parts in chunks of 4 (k = 4*(part + 4*i) ...)
@@ -228,10 +273,10 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
             }
         }
         publish();                                         // also: every thread is done reading sObs and `red`
-        if (t + 1 < T1) prefetch_obs(t + 1);
+        if (!ENV && t + 1 < T1) prefetch_obs(t + 1);
         if (tid == 0) {
             for (int kk = 0; kk < K1 / 8; ++kk)
-                tc::mma_tf32(tmem, desc(sA, 0, K1, kk), desc(sW1, 0, K1, kk), idesc_h, kk > 0);
+                tc::mma_tf32(tmem, dA1 + 16 * kk, dW1 + 16 * kk, idesc_h, kk > 0);
             tc::mma_commit(&bar);
         }
         wait_mma();
@@ -245,8 +290,9 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
         store_cols_kmajor<CPT>(sA, row, c0, H, v, true);
         publish();
         if (tid == 0) {
+#pragma unroll
             for (int kk = 0; kk < H / 8; ++kk)
-                tc::mma_tf32(tmem, desc(sA, 0, H, kk), desc(sW2, 0, H, kk), idesc_h, kk > 0);
+                tc::mma_tf32(tmem, dA + 16 * kk, dW2 + 16 * kk, idesc_h, kk > 0);
             tc::mma_commit(&bar);
         }
         wait_mma();
@@ -259,14 +305,18 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
         store_cols_kmajor<CPT>(sA, row, c0, H, v, true);
         publish();
         if (tid == 0) {
+#pragma unroll
             for (int kk = 0; kk < H / 8; ++kk)         // r | z : x part, then h part accumulated on top
-                tc::mma_tf32(tmem + H, desc(sA, 0, H, kk), desc(sWih, 0, H, kk), idesc_2h, kk > 0);
+                tc::mma_tf32(tmem + H, dA + 16 * kk, dWih_rz + 16 * kk, idesc_2h, kk > 0);
+#pragma unroll
             for (int kk = 0; kk < H / 8; ++kk)
-                tc::mma_tf32(tmem + H, desc(sH, 0, H, kk), desc(sWhh, 0, H, kk), idesc_2h, true);
+                tc::mma_tf32(tmem + H, dHid + 16 * kk, dWhh_rz + 16 * kk, idesc_2h, true);
+#pragma unroll
             for (int kk = 0; kk < H / 8; ++kk)         // i_n
-                tc::mma_tf32(tmem, desc(sA, 0, H, kk), desc(sWih, 2 * H, H, kk), idesc_h, kk > 0);
+                tc::mma_tf32(tmem, dA + 16 * kk, dWih_n + 16 * kk, idesc_h, kk > 0);
+#pragma unroll
             for (int kk = 0; kk < H / 8; ++kk)         // h_n
-                tc::mma_tf32(tmem + 3 * H, desc(sH, 0, H, kk), desc(sWhh, 2 * H, H, kk), idesc_h, kk > 0);
+                tc::mma_tf32(tmem + 3 * H, dHid + 16 * kk, dWhh_n + 16 * kk, idesc_h, kk > 0);
             tc::mma_commit(&bar);
         }
         wait_mma();
@@ -282,13 +332,19 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
             for (int j4 = 0; j4 < CPT; j4 += 4) {
                 const float4 hp = *reinterpret_cast<const float4*>(sH + tc::kmajor_offset(row, c0 + j4, H));
                 const float hprev[4] = {hp.x, hp.y, hp.z, hp.w};
+                const int j = c0 + j4;
+                const float4 bir = *reinterpret_cast<const float4*>(sP + L.bih + j), bhr = *reinterpret_cast<const float4*>(sP + L.bhh + j);
+                const float4 biz = *reinterpret_cast<const float4*>(sP + L.bih + H + j), bhz = *reinterpret_cast<const float4*>(sP + L.bhh + H + j);
+                const float4 bin = *reinterpret_cast<const float4*>(sP + L.bih + 2 * H + j), bhn = *reinterpret_cast<const float4*>(sP + L.bhh + 2 * H + j);
+                const float br[4] = {bir.x + bhr.x, bir.y + bhr.y, bir.z + bhr.z, bir.w + bhr.w};
+                const float bz[4] = {biz.x + bhz.x, biz.y + bhz.y, biz.z + bhz.z, biz.w + bhz.w};
+                const float bi[4] = {bin.x, bin.y, bin.z, bin.w}, bh[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int j = c0 + j4 + u;
-                    const float rr = sigmoid_fast(gr[j4 + u] + sP[L.bih + j] + sP[L.bhh + j]);
-                    const float zz = sigmoid_fast(gz[j4 + u] + sP[L.bih + H + j] + sP[L.bhh + H + j]);
-                    const float nn = tanh_fast(gin[j4 + u] + sP[L.bih + 2 * H + j] + rr * (ghn[j4 + u] + sP[L.bhh + 2 * H + j]));
-                    v[j4 + u] = (1.0f - zz) * nn + zz * hprev[u];
+                    const float rr = sigmoid_fast(gr[j4 + u] + br[u]);
+                    const float zz = sigmoid_fast(gz[j4 + u] + bz[u]);
+                    const float nn = tanh_fast(gin[j4 + u] + bi[u] + rr * (ghn[j4 + u] + bh[u]));
+                    v[j4 + u] = fmaf(zz, hprev[u] - nn, nn);          // (1 - z) n + z h
                 }
             }
         }
@@ -305,24 +361,98 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
 #pragma unroll
             for (int k = 0; k < CPT; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
         }
-        if (q_out != nullptr) {
-            // head: y transposed into the (now free) activation tile, then thread (row, part) takes actions part, part+4, ...
+        if (ENV || q_out != nullptr) {
+            // head: every thread dots its CPT columns with all NA rows of W_q; the 4 partials of a row meet in
+            // the (now free) activation tile and part 0 adds them up
+            for (int a = 0; a < NA; ++a) {
+                float acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) sYt[(c0 + j) * kRows + row] = v[j];
+                for (int j = 0; j < CPT; j += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(sP + L.wq + a * H + c0 + j);
+                    acc = fmaf(v[j], w.x, fmaf(v[j + 1], w.y, fmaf(v[j + 2], w.z, fmaf(v[j + 3], w.w, acc))));
+                }
+                sYt[(a * 4 + part) * kRows + row] = acc;
+            }
             __syncthreads();
-            if (valid) {
-                float* qd = q_out + ((long long)t * R + row0 + row) * NA;
-                for (int a = part; a < NA; a += 4) {
-                    float acc = sP[L.bq + a];
-#pragma unroll 16
-                    for (int j = 0; j < H; ++j) acc = fmaf(sYt[j * kRows + row], sP[L.wq + a * H + j], acc);
-                    qd[a] = acc;
+            if (part == 0) {
+                float qv[ENV ? kMaxNaEnv : 1];
+                int greedy = 0;
+                float best = 0.f;
+                for (int a = 0; a < NA; ++a) {
+                    const float qa = sP[L.bq + a] + ((sYt[(a * 4 + 0) * kRows + row] + sYt[(a * 4 + 1) * kRows + row]) +
+                                                     (sYt[(a * 4 + 2) * kRows + row] + sYt[(a * 4 + 3) * kRows + row]));
+                    if (valid && q_out != nullptr) q_out[((long long)t * R + row0 + row) * NA + a] = qa;
+                    if (ENV) {
+                        if (a < kMaxNaEnv) qv[a] = qa;
+                        if (a == 0 || qa > best) { best = qa; greedy = a; }      // first maximum, like torch.max
+                    }
+                }
+                if (ENV) {
+                    // ---- eps-greedy action (QMixPolicy.actions_from_q: one uniform per agent row) ----------------
+                    const long long grow = row0 + row;
+                    const unsigned long long ctr = ro.io.step_offset + (unsigned long long)t;
+                    const long long key_row = ro.io.eps_per_env ? (grow >> 1) : grow;     // vdn/_network.py: one draw per env
+                    const uint4 rnd = mm::philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)key_row,
+                                                                   (uint32_t)(key_row >> 32)), ro.seed);
+                    const uint4 rnd2 = mm::philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)grow,
+                                                                    0x80000000u | (uint32_t)(grow >> 32)), ro.seed);
+                    const bool take_random = (float)(rnd.x >> 8) * (1.0f / 16777216.0f) < ro.io.eps;
+                    const int act = take_random ? (int)__umulhi(rnd2.x, (uint32_t)NA) : greedy;
+                    // ---- env step (frozen once the episode has finished, like collect_rollout's `if not all(dones)`) ----
+                    const bool frozen = ro.io.freeze_after_done && (env_regs.food & ck::kDoneLatch);
+                    ck::EnvRegs next = env_regs;
+                    float reward;
+                    uint32_t done;
+                    bool bad;
+                    const int agent = row & 1;
+                    // food kind eaten, recovered from the reward LUT index: recompute via before/after food bits
+                    const uint32_t food_before = env_regs.food & ck::kFoodCells;
+                    const bool latched = (env_regs.food & ck::kDoneLatch) != 0;   // steps_beyond_done: rewards are [0, 0]
+                    ck::transition(next, act, agent, lane, ro.cfg, reward, done, bad);
+                    if (frozen) { reward = 0.f; done = 1u; } else { env_regs = next; }
+                    if (ro.io.common_reward) {
+                        // kinds: which cell this agent ate (0 none, 1 lemon, 2 apple) -> LUT of exactly rounded sums
+                        const uint32_t mine_cell = (env_regs.cells >> (8 * agent)) & 0xffu;
+                        const uint32_t ate = frozen ? 0u : (food_before & ~env_regs.food & (1u << mine_cell));
+                        const int kind = ate ? ((ate & ck::kAppleCells) ? 2 : 1) : 0;
+                        const int other = __shfl_xor_sync(MM_FULL_MASK, kind, 1);
+                        reward = (latched || frozen) ? 0.f : (agent == 0 ? ro.common[kind][other] : ro.common[other][kind]);
+                    }
+                    if (valid) {
+                        const long long ti = (long long)t;
+                        if (ro.io.act_idx) ro.io.act_idx[ti * ro.io.act_t_stride + grow] = act;
+                        if (ro.io.act_onehot) {
+                            float* oh = ro.io.act_onehot + ti * ro.io.onehot_t_stride + grow * NA;
+                            for (int a = 0; a < NA; ++a) oh[a] = (a == act) ? 1.0f : 0.0f;
+                        }
+                        if (ro.io.rewards) ro.io.rewards[ti * ro.io.rew_t_stride + grow] = reward;
+                        if (ro.io.dones) ro.io.dones[ti * ro.io.done_t_stride + grow] = done ? 1.0f : 0.0f;
+                        if (ro.io.dones_env && agent == 0) ro.io.dones_env[ti * ro.io.denv_t_stride + (grow >> 1)] = done ? 1.0f : 0.0f;
+                    }
+                    // next observation straight into the shared obs tile (nobody reads it until the next barrier)
+                    ck::fill_tile(sObs, row, agent, env_regs, ro.cfg);
+                }
+            }
+            if (ENV) {
+                __syncthreads();
+                float* dst = ro.io.obs + (long long)(t + 1) * ro.io.obs_t_stride + row0 * D;
+                const int n = n_valid * D;
+                if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    for (int i = tid; i < (n >> 2); i += kThreadsTc)
+                        mm::st_stream(reinterpret_cast<float4*>(dst) + i, reinterpret_cast<const float4*>(sObs)[i]);
+                } else {
+                    for (int i = tid; i < n; i += kThreadsTc) dst[i] = sObs[i];
                 }
             }
         }
         // stage A of the next step starts with a barrier before it overwrites sA / sYt
     }
 
+    if (ENV && part == 0 && valid && (row & 1) == 0) {
+        ro.io.env_state[env_id] = env_regs.food;
+        ro.io.env_state[n_envs + env_id] = env_regs.cells;
+        ro.io.env_state[2 * n_envs + env_id] = env_regs.step;
+    }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, kCols);
@@ -341,10 +471,24 @@ int launch_tc(const float* params, const float* obs, const float* h0, float* q, 
               int T1, long long R, int D, int NA, cudaStream_t st) {
     const size_t smem = tc_smem_bytes<H>(D, NA);
     if (smem > 227 * 1024) return MM_ERR_UNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(agentq_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(agentq_tc_kernel<H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
     const long long tiles = (R + kRows - 1) / kRows;
-    agentq_tc_kernel<H><<<(unsigned)tiles, kThreadsTc, smem, st>>>(params, obs, h0, q, h_final, rnn_out, T1, R, D, NA);
+    RolloutDev none{};
+    agentq_tc_kernel<H, false><<<(unsigned)tiles, kThreadsTc, smem, st>>>(params, obs, h0, q, h_final, rnn_out, T1, R, D, NA, none);
+    return mm::check_launch();
+}
+
+template <int H>
+int launch_rollout(const float* params, const float* h0, float* h_final, float* q, int T, long long R, int NA,
+                   const RolloutDev& ro, cudaStream_t st) {
+    const int D = ck::kObs;
+    const size_t smem = tc_smem_bytes<H>(D, NA);
+    if (smem > 227 * 1024) return MM_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(agentq_tc_kernel<H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
+    const long long tiles = (R + kRows - 1) / kRows;
+    agentq_tc_kernel<H, true><<<(unsigned)tiles, kThreadsTc, smem, st>>>(params, ro.io.obs, h0, q, h_final, nullptr, T, R, D, NA, ro);
     return mm::check_launch();
 }
 
@@ -376,4 +520,26 @@ extern "C" int mm_agentq_tc_forward(const float* params, const float* obs, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (H == 64) return launch_tc<64>(params, obs, h0, q, h_final, rnn_out, T1, R, D, NA, st);
     return launch_tc<32>(params, obs, h0, q, h_final, rnn_out, T1, R, D, NA, st);
+}
+
+extern "C" int mm_qmix_rollout_tc(const float* params, const float* h0, float* h_final, float* q_out,
+                                  const mm_rollout_io* io, const mm_checkers_cfg* cfg,
+                                  const float* common_reward_lut_host, int32_t T, int64_t n_envs, int32_t H,
+                                  int32_t NA, uint64_t seed, void* stream) {
+    if (!params || !io || !cfg || !io->env_state || !io->obs || T <= 0 || n_envs <= 0) return MM_ERR_BAD_ARG;
+    if (cfg->full_observable || NA > kMaxNaEnv) return MM_ERR_UNSUPPORTED;
+    if (io->common_reward && !common_reward_lut_host) return MM_ERR_BAD_ARG;
+    if (mm_agentq_tc_param_count(ck::kObs, H, NA) < 0) return MM_ERR_UNSUPPORTED;
+    if (h0 && !mm::aligned(h0, 16)) return MM_ERR_BAD_ARG;
+    if (h_final && !mm::aligned(h_final, 16)) return MM_ERR_BAD_ARG;
+    RolloutDev ro;
+    ro.io = *io;
+    ro.cfg = *cfg;
+    ro.cfg.n_envs = (int32_t)n_envs;
+    for (int i = 0; i < 9; ++i) (&ro.common[0][0])[i] = common_reward_lut_host ? common_reward_lut_host[i] : 0.f;
+    ro.seed = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long R = 2 * (long long)n_envs;
+    if (H == 64) return launch_rollout<64>(params, h0, h_final, q_out, T, R, NA, ro, st);
+    return launch_rollout<32>(params, h0, h_final, q_out, T, R, NA, ro, st);
 }
