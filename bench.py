@@ -211,6 +211,45 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def policy_rollout_section(dev, steps):
+    """Rollout WITH the policy in the loop: QMIX agent network (GRU, hidden 64, tcgen05) -> eps-greedy -> Checkers
+    step, T = 100 steps of n_envs lockstep envs in ONE launch (mm_qmix_rollout_tc), episodes written to replay
+    layout.  This is what collect_rollout (offpolicy/runner/shared/magym_runner.py:39-141) does one env-step at a time."""
+    import argparse as ap
+    import torch
+    from minimarl_b200 import BatchedCheckers
+    from minimarl_b200.nn import AgentQFunction
+    from minimarl_b200.rollout import qmix_rollout
+    args = ap.Namespace(hidden_size=64, use_rnn_layer=True, use_orthogonal=True, gain=0.01, layer_N=1, recurrent_N=1,
+                        use_feature_normalization=True, use_ReLU=True, use_conv1d=False, fused_precision="tf32")
+    net = AgentQFunction(args, 47, 5, dev)
+    out = {}
+    for n_envs in (4096, 9472, 16384):
+        T = 100
+        env = BatchedCheckers(n_envs, max_steps=T, device=dev)
+        z = dict(dtype=torch.float32, device=dev)
+        bufs = dict(obs=torch.zeros((T + 1, n_envs, 2, 47), **z), act_idx=torch.empty((T, n_envs, 2), dtype=torch.int32, device=dev),
+                    act_onehot=torch.empty((T, n_envs, 2, 5), **z), rewards=torch.empty((T, n_envs, 2), **z),
+                    dones=torch.empty((T, n_envs, 2), **z), dones_env=torch.empty((T, n_envs), **z))
+        run = lambda k: qmix_rollout(net, env, T, eps=0.3, seed=42, step_offset=k * T, **bufs)
+        for k in range(3):
+            run(k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            run(3 + k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[f"n_envs_{n_envs}"] = {"ms_per_rollout": ms, "agent_steps_per_s": n_envs * T * 2 / (ms * 1e-3),
+                                   "us_per_env_step_all_envs": ms * 1e3 / T,
+                                   "net_TFLOPs": n_envs * 2 * T * 64000 / (ms * 1e-3) / 1e12}
+    out["note"] = ("policy in the loop: agent net forward (64 kFLOP per agent-step, TF32 tcgen05) + eps-greedy + env step "
+                   "+ obs/act/reward/done writes, one launch per 100-step rollout; 128 rows (64 envs) per CTA")
+    return out
+
+
 def learner_section(dev, steps):
     """Second half of the BASELINE metric: QMIX train samples/sec (configs[3]: 1M-transition device replay =
     10 000 episodes x T=100, batch 4 096 episodes, GRU agents, hidden 64, PER, double-Q).  One sample = one
@@ -434,6 +473,10 @@ def run_ours(args, wl):
             "clocks": clocks,
         }
         if not args.no_learner:
+            try:
+                line["policy_rollout"] = policy_rollout_section(dev, args.learner_steps)
+            except Exception as e:
+                line["policy_rollout"] = {"error": f"{type(e).__name__}: {e}"}
             try:
                 line["learner"] = learner_section(dev, args.learner_steps)
             except Exception as e:          # the headline line must survive a learner failure; report it
