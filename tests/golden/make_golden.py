@@ -372,8 +372,92 @@ def golden_mappo_generators():
         print("mappo_buffer.npz", len(out), "arrays")
 
 
+def golden_mappo_train():
+    """R_MAPPOPolicy forward pieces and one R_MAPPO.train (mappo/algorithms/*), recorded perms."""
+    Box, Discrete = install_gym_stub()
+    with ref_package("mappo"):
+        from _config import get_config
+        from algorithms.rmappo_policy import R_MAPPOPolicy
+        from algorithms.ramppo_network import R_MAPPO
+        from runner.shared.shared_buffer import SharedReplayBuffer
+        torch.manual_seed(5)
+        np.random.seed(5)
+        args = get_config().parse_known_args([])[0]
+        T, B, A, D, H = 10, 6, 2, 47, 32
+        args.max_step, args.batch_size, args.ppo_epoch, args.train_batch_size, args.data_chunk_length = T, B, 2, 2, 5
+        args.use_cuda = False
+        dev = torch.device("cpu")
+        space = Box(np.zeros(D), np.ones(D))
+        policy = R_MAPPOPolicy(args, space, space, Discrete(5), device=dev)
+        trainer = R_MAPPO(args, policy, device=dev)
+        with torch.no_grad():
+            for m in (policy.actor, policy.critic):
+                for p_ in m.parameters():
+                    if p_.dim() == 1:
+                        p_.add_(0.1 * torch.randn_like(p_))
+        out = {k: np.array(getattr(args, k)) for k in ["hidden_size", "ppo_epoch", "train_batch_size", "data_chunk_length",
+               "clip_param", "entropy_coef", "value_loss_coef", "max_grad_norm", "huber_delta", "actor_lr", "critic_lr",
+               "opti_eps", "gamma", "gae_lambda"]}
+        out.update(sd_numpy(policy.actor, "actor."))
+        out.update(sd_numpy(policy.critic, "critic."))
+        rng = np.random.default_rng(31)
+        f = lambda *shape: rng.standard_normal(shape).astype(np.float32)
+        buf = SharedReplayBuffer(args, A, space, space, Discrete(5))
+        buf.obs[:] = rng.random(buf.obs.shape).astype(np.float32)
+        buf.share_obs[:] = buf.obs
+        buf.rnn_states[:] = 0.3 * f(*buf.rnn_states.shape)
+        buf.rnn_states_critic[:] = 0.3 * f(*buf.rnn_states_critic.shape)
+        buf.actions[:] = rng.integers(0, 5, buf.actions.shape).astype(np.float32)
+        buf.masks[:] = (rng.random(buf.masks.shape) < 0.85).astype(np.float32)
+        buf.rewards[:] = f(*buf.rewards.shape)
+        # one-step forward pieces (rollout path): values, log-probs of given actions, new rnn states
+        with torch.no_grad():
+            obs0 = np.concatenate(buf.obs[0]); h_a = np.concatenate(buf.rnn_states[0]); h_c = np.concatenate(buf.rnn_states_critic[0])
+            m0 = np.concatenate(buf.masks[0])
+            values, h_c1 = policy.critic(obs0, h_c, m0)
+            a_feat = policy.actor.base(torch.from_numpy(obs0))
+            a_feat, h_a1 = policy.actor.rnn(a_feat, torch.from_numpy(h_a), torch.from_numpy(m0))
+            logits = policy.actor.act.action_out.linear(a_feat)
+            det_actions, h_a2 = policy.act(obs0, h_a, m0, deterministic=True)
+            out["step_obs"], out["step_h_actor"], out["step_h_critic"], out["step_masks"] = obs0, h_a, h_c, m0
+            out["step_values"], out["step_h_critic_out"] = values.numpy(), h_c1.numpy()
+            out["step_logits"], out["step_h_actor_out"] = logits.numpy(), h_a1.numpy()
+            out["step_det_actions"] = det_actions.numpy()
+            # fill value_preds / log-probs the way a rollout would
+            for t in range(T):
+                o = np.concatenate(buf.obs[t]); m = np.concatenate(buf.masks[t])
+                v, _ = policy.critic(o, np.concatenate(buf.rnn_states_critic[t]), m)
+                lp, _ = policy.actor.evaluate_actions(o, np.concatenate(buf.rnn_states[t]), np.concatenate(buf.actions[t]), m)
+                buf.value_preds[t] = v.numpy().reshape(B, A, 1)
+                buf.action_log_probs[t] = lp.numpy().reshape(B, A, 1) + 0.05 * f(B, A, 1)
+            next_value = policy.get_values(np.concatenate(buf.obs[-1]), np.concatenate(buf.rnn_states_critic[-1]),
+                                           np.concatenate(buf.masks[-1])).numpy().reshape(B, A, 1)
+        buf.compute_returns(next_value, trainer.value_normalizer)
+        for k in ["obs", "share_obs", "rnn_states", "rnn_states_critic", "actions", "masks", "rewards", "value_preds",
+                  "action_log_probs", "returns", "active_masks"]:
+            out["buf_" + k] = getattr(buf, k).copy()
+        out["next_value"] = next_value
+        n_chunks = (T * B * A) // args.data_chunk_length
+        perms = [torch.from_numpy(rng.permutation(n_chunks)) for _ in range(args.ppo_epoch)]
+        out["perms"] = np.stack([p_.numpy() for p_ in perms])
+        it = iter(perms)
+        orig = torch.randperm
+        torch.randperm = lambda n, *a, **k: next(it)
+        try:
+            info = trainer.train(buf)
+        finally:
+            torch.randperm = orig
+        for k, v in info.items():
+            out["info_" + k] = np.array(float(v))
+        out.update(sd_numpy(policy.actor, "actor_after."))
+        out.update(sd_numpy(policy.critic, "critic_after."))
+        out.update(sd_numpy(trainer.value_normalizer, "vn_after."))
+        np.savez_compressed(os.path.join(OUT, "mappo_train.npz"), **out)
+        print("mappo_train.npz", len(out), "arrays;", {k: float(v) for k, v in info.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gae", "per", "nets", "logs", "mappo_buffer"]
+    which = sys.argv[1:] or ["gae", "per", "nets", "logs", "mappo_buffer", "mappo_train"]
     if "gae" in which:
         golden_gae()
     if "per" in which:
@@ -384,3 +468,5 @@ if __name__ == "__main__":
         golden_log_scores()
     if "mappo_buffer" in which:
         golden_mappo_generators()
+    if "mappo_train" in which:
+        golden_mappo_train()
