@@ -267,6 +267,20 @@ int mm_qmix_rollout_tc(const float* params /* mm_agentq_tc layout, D = 47 */, co
                        const mm_checkers_cfg* cfg_host, const float* common_reward_lut_host /* float[9] or NULL */,
                        int32_t T, int64_t n_envs, int32_t H, int32_t NA, uint64_t seed, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Chunk-PER sum tree of the top-level vdn/ and qmix/ packages (vdn/replay_buffer/sumtree.py:8-66):
+ * float64[2*capacity-1], heap order, root 0, leaf i at node capacity-1+i.
+ *   update:      for each (node_idx[i], priority[i]) IN ORDER: propagate the change to the ancestors.
+ *   sample:      stratified draw (buffer.py:42-66): s_i = seg*i + (seg*(i+1) - seg*i) * u_i, seg = total/n,
+ *                `_retrieve_max` walk -> node index and its priority.
+ *   argmin_leaf: first leaf with the minimum priority (the eviction rule of `add` on a full buffer).
+ * ---------------------------------------------------------------------------------------------- */
+int mm_heaptree_update(double* tree, int32_t capacity, const int64_t* node_idx, const double* priority,
+                       int32_t n, void* stream);
+int mm_heaptree_sample(const double* tree, int32_t capacity, const double* uniforms, int32_t n,
+                       int64_t* node_idx_out, double* priority_out, void* stream);
+int mm_heaptree_argmin_leaf(const double* tree, int32_t capacity, int64_t* leaf_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,316 @@
+"""Device mirror of the top-level ``vdn/`` and ``qmix/`` packages.
+
+* ``Q_Net`` -- per-agent ``Linear(D,64) ReLU Linear(64,32) ReLU -> GRUCell(32,32) -> Linear(32,5)`` with the
+  reference's ParameterList names (vdn/_network.py:5-91; qmix/_network.py:5-77), ``sample_action`` with ONE
+  epsilon draw per batch row (vdn/_network.py:52-58, quirk Q8) and float actions.
+* ``Mix_Net`` -- recurrent hypernetwork mixer of qmix/_network.py:172-220.
+* ``Prioritized_Experience_Replay`` -- chunk PER (vdn/replay_buffer/buffer.py:9-90, qmix/replay_buffer/per.py:9-81):
+  payload as device tensors, priorities in the reference's heap-ordered float64 sum tree maintained by
+  ``mm_heaptree_*`` kernels; stratified sampling, whole-tree decay (``step_weight``, vdn only), arg-min eviction.
+* ``Target_Dqn`` / ``Train_dqn`` -- the DQN-target learners (vdn/_train.py:56-101, qmix/_train.py:19-121)
+  including quirk Q7 (the bootstrap term summed over the agent axis) and the last-step-only priority (Q9).
+* ``cal_td_error`` (vdn/_utils.py:44-52).
+
+The networks are small per-agent MLP / GRUCell stacks evaluated with PyTorch (cuBLAS) on the device; what is
+custom here is the replay path (tree kernels, device-resident chunks instead of Python lists of lists) and the
+lockstep env.  Both top-level packages hard-wire the CPU in places (``.to("cpu")``, qmix/_network.py:64); the
+mirror runs wherever its parameters live.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+
+
+class Network(nn.Module):
+    def __init__(self, observation_space, action_space, args):
+        super().__init__()
+        self.use_recurrent = args.use_recurrent
+        self.num_agents = len(observation_space)
+        self.observation_space, self.action_space = observation_space, action_space
+        self.feature_hidden, self.gru_input, self.gru_hidden = 64, 32, 32
+        self.feature_net = nn.ParameterList()
+        self.gru_net = nn.ParameterList()
+        self.action_net = nn.ParameterList()
+        self.value_net = nn.ParameterList()
+        self.advantage_net = nn.ParameterList()
+        self._gen = None
+
+    def _feature(self, i):
+        n_obs = self.observation_space[i].shape[0]
+        self.feature_net.append(nn.Sequential(nn.Linear(n_obs, self.feature_hidden), nn.ReLU(),
+                                              nn.Linear(self.feature_hidden, self.gru_input), nn.ReLU()))
+
+    def epsilon_greedy(self, q_tensor, epsilon):
+        """One uniform per batch row; a row that explores draws random actions for ALL its agents."""
+        dev = q_tensor.device
+        B, A, NA = q_tensor.shape
+        mask = torch.rand(B, device=dev, generator=self._gen) <= epsilon
+        rand = torch.randint(0, NA, (B, A), device=dev, generator=self._gen).float()
+        action = torch.where(mask.unsqueeze(1), rand, q_tensor.argmax(dim=2).float())
+        return action, q_tensor
+
+
+class Q_Net(Network):
+    def __init__(self, observation_space, action_space, args):
+        super().__init__(observation_space, action_space, args)
+        for i in range(self.num_agents):
+            self._feature(i)
+            if self.use_recurrent:
+                self.gru_net.append(nn.GRUCell(self.gru_input, self.gru_hidden))
+            self.action_net.append(nn.Sequential(nn.Linear(self.gru_hidden, self.action_space[i].n)))
+
+    def forward(self, obs, hidden):
+        q_values, next_hidden = [], []
+        for i in range(self.num_agents):
+            feature = self.feature_net[i](obs[:, i, :])
+            if self.use_recurrent:
+                feature = self.gru_net[i](feature, hidden[:, i, :])
+                next_hidden.append(feature.unsqueeze(1))
+            q_values.append(self.action_net[i](feature).unsqueeze(1))
+        return torch.cat(q_values, dim=1), (torch.cat(next_hidden, dim=1) if next_hidden else hidden)
+
+    def sample_action(self, obs, hidden, epsilon):
+        q_tensor, next_hidden = self.forward(obs, hidden)
+        action, q_tensor = self.epsilon_greedy(q_tensor, epsilon)
+        return action, next_hidden, q_tensor
+
+    def init_hidden(self, batch_size=1):
+        p = next(self.parameters())
+        return torch.zeros((batch_size, self.num_agents, self.gru_hidden), device=p.device)
+
+
+class Mix_Net(nn.Module):
+    def __init__(self, observation_space, args):
+        super().__init__()
+        hidden_dim, hx_size = 32, 32
+        state_size = sum(s.shape[0] for s in observation_space)
+        self.hidden_dim, self.hx_size, self.n_agents = hidden_dim, hx_size, len(observation_space)
+        self.recurrent = args.use_recurrent
+        inp = state_size
+        if self.recurrent:
+            self.gru = nn.GRUCell(state_size, hx_size)
+            inp = hx_size
+        self.hyper_net_weight_1 = nn.Linear(inp, self.n_agents * hidden_dim)
+        self.hyper_net_weight_2 = nn.Linear(inp, hidden_dim)
+        self.hyper_net_bias_1 = nn.Linear(inp, hidden_dim)
+        self.hyper_net_bias_2 = nn.Sequential(nn.Linear(inp, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, 1))
+
+    def forward(self, q_values, observations, hidden):
+        batch_size, n_agents, obs_size = observations.shape
+        x = observations.reshape(batch_size, n_agents * obs_size)
+        if self.recurrent:
+            hidden = self.gru(x, hidden)
+            x = hidden
+        weight_1 = torch.abs(self.hyper_net_weight_1(x)).view(batch_size, self.hidden_dim, n_agents)
+        bias_1 = self.hyper_net_bias_1(x).unsqueeze(-1)
+        weight_2 = torch.abs(self.hyper_net_weight_2(x))
+        bias_2 = self.hyper_net_bias_2(x)
+        x = torch.relu(torch.bmm(weight_1, q_values.unsqueeze(-1)) + bias_1)
+        return (weight_2.unsqueeze(-1) * x).sum(dim=1) + bias_2, hidden
+
+    def init_hidden(self, batch_size=1):
+        p = next(self.parameters())
+        return torch.zeros((batch_size, self.hx_size), device=p.device)
+
+
+def cal_td_error(action, reward, done, behavior_q, target_q, gamma):
+    """|sum r + (1 - done) gamma sum_a max Q_tgt - sum_a Q_beh[a]| for every env of the batch ([B] tensor)."""
+    idx = action.long().unsqueeze(-1)
+    behavior_value = torch.gather(behavior_q, 2, idx).squeeze(-1).sum(dim=1)
+    target_max_q = target_q.max(dim=2)[0].sum(dim=1)
+    reward = torch.as_tensor(reward, device=behavior_q.device, dtype=behavior_q.dtype)
+    done = torch.as_tensor(done, device=behavior_q.device, dtype=behavior_q.dtype)
+    return (reward.sum(dim=-1) + (1 - done) * gamma * target_max_q - behavior_value).abs()
+
+
+class SumTree:
+    """Heap-ordered float64 sum tree on the device (same node numbering as the reference)."""
+
+    def __init__(self, capacity, device):
+        self.capacity = capacity
+        self.device = torch.device(device)
+        self.priority_tree = torch.zeros(2 * capacity - 1, dtype=torch.float64, device=self.device)
+        self.n_data = 0
+
+    def total(self):
+        return self.priority_tree[0]
+
+    def update(self, node_idx, priority):
+        idx = torch.as_tensor(node_idx, device=self.device, dtype=torch.int64).reshape(-1).contiguous()
+        pr = torch.as_tensor(priority, device=self.device).to(torch.float64).reshape(-1).contiguous()
+        _lib.check(_lib.lib().mm_heaptree_update(_lib.ptr(self.priority_tree), self.capacity, _lib.ptr(idx), _lib.ptr(pr),
+                                                 idx.numel(), _lib.stream()))
+
+    def argmin_leaf(self):
+        out = torch.empty(1, dtype=torch.int64, device=self.device)
+        _lib.check(_lib.lib().mm_heaptree_argmin_leaf(_lib.ptr(self.priority_tree), self.capacity, _lib.ptr(out), _lib.stream()))
+        return out
+
+    def sample(self, uniforms):
+        n = uniforms.numel()
+        node = torch.empty(n, dtype=torch.int64, device=self.device)
+        prio = torch.empty(n, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib().mm_heaptree_sample(_lib.ptr(self.priority_tree), self.capacity, _lib.ptr(uniforms), n,
+                                                 _lib.ptr(node), _lib.ptr(prio), _lib.stream()))
+        return node, prio
+
+
+class Prioritized_Experience_Replay:
+    def __init__(self, args, n_agents=2, obs_dim=94, device="cuda"):
+        self.use_step_weight = getattr(args, "use_step_weight", False)
+        self.capacity = args.buffer_limit
+        self.step_weight = getattr(args, "step_weight", 1.0)
+        self.eps, self.alpha, self.beta = args.eps, args.alpha, args.beta
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("minimarl_b200 replay buffers live on a CUDA device (no CPU fallback)")
+        self.sum_tree = SumTree(self.capacity, self.device)
+        L = args.chunk_size
+        z = dict(dtype=torch.float32, device=self.device)
+        self.states = torch.zeros((self.capacity, L, n_agents, obs_dim), **z)
+        self.actions = torch.zeros((self.capacity, L, n_agents), **z)
+        self.rewards = torch.zeros((self.capacity, L, n_agents), **z)
+        self.next_states = torch.zeros((self.capacity, L, n_agents, obs_dim), **z)
+        self.dones = torch.zeros((self.capacity, L, 1), **z)
+        if args.update_alpha_beta:
+            self.alpha_increment_per_sampling = (1 - self.alpha) / (args.max_episodes * args.update_iter)
+            self.beta_increment_per_sampling = (1 - self.beta) / (args.max_episodes * args.update_iter)
+        else:
+            self.alpha_increment_per_sampling = self.beta_increment_per_sampling = 0
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(int(getattr(args, "seed", 0)))
+
+    def _get_priority(self, td_error):
+        """(td + eps) ** alpha in the arithmetic of the argument, like the reference: Python floats stay Python
+        doubles (collect_sample), float32 tensors are raised in float32 and only then widened (update)."""
+        if isinstance(td_error, (float, int, np.floating)):
+            return (float(td_error) + self.eps) ** self.alpha
+        td = torch.as_tensor(td_error, device=self.device)
+        return ((td + self.eps) ** self.alpha).to(torch.float64)
+
+    def collect_sample(self, sample, td_error, warm_up):
+        """sample = [states [L,A,D], actions [L,A] or [L,1,A], rewards [L,A], next_states [L,A,D], dones [L]]."""
+        t = lambda x: torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, device=self.device, dtype=torch.float32)
+        tree = self.sum_tree
+        if tree.n_data < self.capacity:
+            slot = torch.tensor([tree.n_data], device=self.device)
+        else:
+            slot = tree.argmin_leaf()
+        s, a, r, s2, d = (t(x) for x in sample)
+        self.states[slot] = s.reshape(1, *self.states.shape[1:])
+        self.actions[slot] = a.reshape(1, *self.actions.shape[1:])
+        self.rewards[slot] = r.reshape(1, *self.rewards.shape[1:])
+        self.next_states[slot] = s2.reshape(1, *self.next_states.shape[1:])
+        self.dones[slot] = d.reshape(1, *self.dones.shape[1:])
+        tree.update(slot + self.capacity - 1,
+                    torch.as_tensor(self._get_priority(td_error), dtype=torch.float64, device=self.device).reshape(1))
+        if tree.n_data < self.capacity:
+            tree.n_data += 1
+        return tree.n_data if warm_up else None
+
+    def sample(self, batch_size, _chunk_size, uniforms=None):
+        """7-tuple of the reference (buffer.py:81-86), all CUDA tensors; priority_idxs is an int64 tensor of NODE ids."""
+        tree = self.sum_tree
+        self.alpha = float(np.min([1., self.alpha + self.alpha_increment_per_sampling]))
+        self.beta = float(np.min([1., self.beta + self.beta_increment_per_sampling]))
+        if uniforms is None:
+            uniforms = torch.rand(batch_size, dtype=torch.float64, device=self.device, generator=self._gen)
+        else:
+            uniforms = torch.as_tensor(np.asarray(uniforms) if not torch.is_tensor(uniforms) else uniforms,
+                                       dtype=torch.float64, device=self.device).contiguous()
+        node, prio = tree.sample(uniforms)
+        data = node - (self.capacity - 1)
+        if self.use_step_weight:
+            tree.priority_tree.mul_(self.step_weight)
+        probs = prio / tree.total()
+        w = torch.pow(self.capacity * probs, -self.beta)
+        w = (w / w.max()).to(torch.float32).view(batch_size, 1)
+        return (self.states[data], self.actions[data], self.rewards[data], self.next_states[data], self.dones[data],
+                node, w)
+
+    def update(self, priority_idx, new_td_error):
+        self.sum_tree.update(priority_idx, self._get_priority(new_td_error))
+
+
+class Target_Dqn:
+    """vdn/_train.py:56-101."""
+
+    def __init__(self, Replay_buffer, behavior_network, target_network, args, device):
+        self.replay_buffer, self.behavior_network, self.target_network = Replay_buffer, behavior_network, target_network
+        self.batch_size, self.update_iter = args.batch_size, args.update_iter
+        self.chunk_size = args.chunk_size if args.use_recurrent else 1
+        self.gamma, self.grad_clip_norm, self.device = args.gamma, args.grad_clip_norm, device
+
+    def train(self, target_network, optimizer, epsilon, uniforms=None):
+        iter_loss = 0
+        for it in range(self.update_iter):
+            u = None if uniforms is None else uniforms[it]
+            states, actions, rewards, next_states, dones, priority_idx, is_weight = \
+                self.replay_buffer.sample(self.batch_size, self.chunk_size, uniforms=u)
+            hidden = self.behavior_network.init_hidden(self.batch_size)
+            target_hidden = target_network.init_hidden(self.batch_size)
+            loss = 0.0
+            for step in range(self.chunk_size):
+                state, action = states[:, step], actions[:, step].unsqueeze(-1).long()
+                reward, next_state, done = rewards[:, step], next_states[:, step], dones[:, step]
+                behavior_q, next_hidden = self.behavior_network(obs=state, hidden=hidden)
+                sum_q = behavior_q.gather(dim=2, index=action).squeeze(-1).sum(dim=1, keepdims=True)
+                with torch.no_grad():
+                    target_q, next_target_hidden = target_network(obs=next_state, hidden=target_hidden.detach())
+                sum_max_target_q = target_q.max(dim=2)[0].sum(dim=1, keepdims=True)
+                target_values = is_weight * (reward + self.gamma * (1 - done) * sum_max_target_q).sum(dim=1, keepdims=True)
+                loss = loss + F.mse_loss(target_values.detach(), sum_q)
+                keep = (1 - done).view(-1, 1, 1)                       # hidden rows of finished envs restart at zero
+                hidden, target_hidden = next_hidden * keep, next_target_hidden * keep
+            optimizer.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(parameters=self.behavior_network.parameters(), max_norm=self.grad_clip_norm, norm_type=2)
+            optimizer.step()
+            iter_loss += loss.detach()
+            new_td_error = (target_values - sum_q).abs().detach().reshape(-1)   # last chunk step only (Q9)
+            self.replay_buffer.update(priority_idx, new_td_error)
+        return iter_loss / self.update_iter
+
+
+class Train_dqn:
+    """qmix/_train.py:19-121: the same loop with the recurrent mixer on both sides; only q-net grads are clipped."""
+
+    def __init__(self, args, device):
+        self.batch_size, self.update_iter = args.batch_size, args.update_iter
+        self.chunk_size = args.chunk_size if args.use_recurrent else 1
+        self.gamma, self.grad_clip_norm, self.device = args.gamma, args.grad_clip_norm, device
+
+    def train(self, Replay_buffer, behavior_q_net, behavior_mix_net, target_q_net, target_mix_net, optimizer, epsilon,
+              uniforms=None):
+        iter_loss = 0
+        for it in range(self.update_iter):
+            u = None if uniforms is None else uniforms[it]
+            states, actions, rewards, next_states, dones, priority_idx, w = Replay_buffer.sample(self.batch_size, self.chunk_size, uniforms=u)
+            hidden, target_hidden = behavior_q_net.init_hidden(self.batch_size), target_q_net.init_hidden(self.batch_size)
+            mix_hidden, target_mix_hidden = behavior_mix_net.init_hidden(self.batch_size), target_mix_net.init_hidden(self.batch_size)
+            loss = 0.0
+            for step in range(self.chunk_size):
+                state, action = states[:, step], actions[:, step].unsqueeze(-1).long()
+                reward, next_state, done = rewards[:, step], next_states[:, step], dones[:, step]
+                behavior_q, next_hidden = behavior_q_net(state, hidden)
+                max_behavior_q = behavior_q.gather(dim=2, index=action).squeeze(-1)
+                sum_mix_q, next_mix_hidden = behavior_mix_net(max_behavior_q, state, mix_hidden)
+                with torch.no_grad():
+                    target_q, next_target_hidden = target_q_net(next_state, target_hidden.detach())
+                    max_target_q = target_q.max(dim=2)[0]
+                    sum_target_mix_q, next_target_mix_hidden = target_mix_net(max_target_q, next_state, target_mix_hidden.detach())
+                target_values = w * (reward + self.gamma * (1 - done) * sum_target_mix_q).sum(dim=1, keepdims=True)
+                loss = loss + F.mse_loss(target_values.detach(), sum_mix_q)
+                keep = (1 - done)
+                hidden, target_hidden = next_hidden * keep.view(-1, 1, 1), next_target_hidden * keep.view(-1, 1, 1)
+                mix_hidden, target_mix_hidden = next_mix_hidden * keep, next_target_mix_hidden * keep
+            optimizer.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(parameters=behavior_q_net.parameters(), max_norm=self.grad_clip_norm, norm_type=2)
+            optimizer.step()
+            iter_loss += loss.detach()
+            Replay_buffer.update(priority_idx, (target_values - sum_mix_q).abs().detach().reshape(-1))
+        return iter_loss / self.update_iter

@@ -456,8 +456,92 @@ def golden_mappo_train():
         print("mappo_train.npz", len(out), "arrays;", {k: float(v) for k, v in info.items()})
 
 
+def golden_vdn_toplevel():
+    """vdn/ top level: Q_Net forward, chunk PER (SumTree add / evict / sample / decay / update), Target_Dqn.train,
+    and qmix/ Mix_Net forward.  random.uniform is patched to consume recorded uniforms."""
+    import random as pyrandom
+    Box, Discrete = install_gym_stub()
+    out = {}
+    with ref_package("vdn"):
+        from _config import get_config
+        from _network import Q_Net
+        from _train import Target_Dqn
+        from _utils import cal_td_error
+        from replay_buffer.buffer import Prioritized_Experience_Replay
+        torch.manual_seed(9)
+        args = get_config().parse_known_args([])[0]
+        args.buffer_limit, args.batch_size, args.update_iter, args.chunk_size, args.use_cuda = 50, 8, 2, 10, False
+        A, D, L = 2, 94, args.chunk_size
+        obs_space = [Box(np.zeros(D), np.ones(D)) for _ in range(A)]
+        act_space = [Discrete(5) for _ in range(A)]
+        beh, tgt = Q_Net(obs_space, act_space, args), Q_Net(obs_space, act_space, args)
+        out.update(sd_numpy(beh, "beh."))
+        out.update(sd_numpy(tgt, "tgt."))
+        for k in ["gamma", "eps", "alpha", "beta", "step_weight", "grad_clip_norm", "lr", "max_episodes", "update_iter"]:
+            out["arg_" + k] = np.array(getattr(args, k))
+        rng = np.random.default_rng(17)
+        obs = rng.random((3, A, D)).astype(np.float32)
+        hid = (0.3 * rng.standard_normal((3, A, 32))).astype(np.float32)
+        with torch.no_grad():
+            q, h = beh(torch.from_numpy(obs), torch.from_numpy(hid))
+            tq, _ = tgt(torch.from_numpy(obs), torch.from_numpy(hid))
+        out["fwd_obs"], out["fwd_hidden"], out["fwd_q"], out["fwd_h"] = obs, hid, q.numpy(), h.numpy()
+        act = torch.tensor([1.0, 3.0])
+        out["td_error"] = np.array(cal_td_error(action=act, reward=[-0.01, 9.99], done=0, behavior_q=q[:1], target_q=tq[:1], gamma=args.gamma))
+        out["td_action"], out["td_target_q"] = act.numpy(), tq[:1].numpy()
+
+        per = Prioritized_Experience_Replay(args)
+        n_add = 70                                           # > capacity: exercises the arg-min eviction
+        chunks = dict(states=rng.random((n_add, L, A, D)).astype(np.float32), actions=rng.integers(0, 5, (n_add, L, 1, A)).astype(np.float32),
+                      rewards=rng.standard_normal((n_add, L, A)).astype(np.float32), next_states=rng.random((n_add, L, A, D)).astype(np.float32),
+                      dones=(rng.random((n_add, L)) < 0.05).astype(np.float32), td=(rng.random(n_add) * 5).astype(np.float64))
+        for k, v in chunks.items():
+            out["chunk_" + k] = v
+        for i in range(n_add):
+            sample = [chunks["states"][i].tolist(), chunks["actions"][i].tolist(), chunks["rewards"][i].tolist(),
+                      chunks["next_states"][i].tolist(), chunks["dones"][i].tolist()]
+            per.collect_sample(sample=sample, td_error=float(chunks["td"][i]), warm_up=True)
+        out["tree_after_add"] = per.sum_tree.priority_tree.copy()
+        u = rng.random((args.update_iter + 1, args.batch_size))
+        out["uniforms"] = u
+        seq = iter(u.reshape(-1))
+        orig = pyrandom.uniform
+        pyrandom.uniform = lambda a, b: a + (b - a) * next(seq)
+        try:
+            s = per.sample(args.batch_size, L)
+            out["sample_states"], out["sample_actions"], out["sample_rewards"] = s[0].numpy(), s[1].numpy(), s[2].numpy()
+            out["sample_next_states"], out["sample_dones"] = s[3].numpy(), s[4].numpy()
+            out["sample_idx"], out["sample_w"] = np.array(s[5]), s[6].numpy()
+            out["tree_after_sample"] = per.sum_tree.priority_tree.copy()
+            out["alpha_after_sample"], out["beta_after_sample"] = np.array(per.alpha), np.array(per.beta)
+            trainer = Target_Dqn(per, beh, tgt, args, torch.device("cpu"))
+            opt = torch.optim.Adam(beh.parameters(), lr=args.lr)
+            loss = trainer.train(target_network=tgt, optimizer=opt, epsilon=0.5)
+        finally:
+            pyrandom.uniform = orig
+        out["train_loss"] = np.array(float(loss))
+        out["tree_after_train"] = per.sum_tree.priority_tree.copy()
+        out.update(sd_numpy(beh, "beh_after."))
+    with ref_package("qmix"):
+        from _config import get_config as qcfg
+        from _network import Mix_Net
+        qargs = qcfg().parse_known_args([])[0]
+        torch.manual_seed(10)
+        mix = Mix_Net([Box(np.zeros(3), np.ones(3)) for _ in range(2)], qargs)
+        out.update(sd_numpy(mix, "mix."))
+        rng = np.random.default_rng(4)
+        qv = rng.standard_normal((5, 2)).astype(np.float32)
+        ob = rng.random((5, 2, 3)).astype(np.float32)
+        hd = (0.2 * rng.standard_normal((5, 32))).astype(np.float32)
+        with torch.no_grad():
+            y, h = mix(torch.from_numpy(qv), torch.from_numpy(ob), torch.from_numpy(hd))
+        out["mix_q"], out["mix_obs"], out["mix_hidden"], out["mix_out"], out["mix_h"] = qv, ob, hd, y.numpy(), h.numpy()
+    np.savez_compressed(os.path.join(OUT, "toplevel.npz"), **out)
+    print("toplevel.npz", len(out), "arrays; vdn train loss", float(out["train_loss"]))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gae", "per", "nets", "logs", "mappo_buffer", "mappo_train"]
+    which = sys.argv[1:] or ["gae", "per", "nets", "logs", "mappo_buffer", "mappo_train", "toplevel"]
     if "gae" in which:
         golden_gae()
     if "per" in which:
@@ -470,3 +554,5 @@ if __name__ == "__main__":
         golden_mappo_generators()
     if "mappo_train" in which:
         golden_mappo_train()
+    if "toplevel" in which:
+        golden_vdn_toplevel()
