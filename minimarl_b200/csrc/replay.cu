@@ -155,6 +155,70 @@ __global__ void __launch_bounds__(256) replay_gather_kernel(const GatherParams p
     }
 }
 
+// Fast path for the shapes of the hot path (2 agents, D <= 64, SD <= 96, NA <= 16): no integer divisions, every
+// load of the (t, b) chunk is issued before the first store, addresses are hoisted.  The generic kernel above
+// was issue-bound (75 % issue-active, 311 us for 4 096 x 101 chunks); this one moves the same bytes with
+// ~4x fewer instructions.
+__global__ void __launch_bounds__(256) replay_gather_fast_kernel(const GatherParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int T1 = p.T + 1;
+    if (w >= (int64_t)T1 * p.B) return;
+    const int t = (int)(w / p.B), b = (int)(w - (int64_t)t * p.B);
+    const int64_t s = __ldg(p.idx + b);
+    const int D = p.D, SD = p.SD, NA = p.NA;
+    const int64_t src_tb = (int64_t)t * p.S + s;           // (t, episode) in the storage
+    const int64_t dst_tb = (int64_t)t * p.B + b;           // (t, batch slot) in the output
+    const float* so = p.obs + src_tb * 2 * D;
+    const float* ss = p.share_obs + src_tb * SD;
+    float o[2][2], sh[3], ac = 0.f, rw = 0.f, dn = 0.f, de = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = lane + 32 * u;
+            o[a][u] = k < D ? __ldg(so + a * D + k) : 0.f;
+        }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const int k = lane + 32 * u;
+        sh[u] = k < SD ? __ldg(ss + k) : 0.f;
+    }
+    const bool step = t < p.T;
+    if (step) {
+        if (lane < 2 * NA) ac = __ldg(p.acts + src_tb * 2 * NA + lane);
+        if (lane < 2) { rw = __ldg(p.rewards + src_tb * 2 + lane); dn = __ldg(p.dones + src_tb * 2 + lane); }
+        if (lane == 0) de = __ldg(p.dones_env + src_tb);
+    }
+    const int64_t agent_stride_obs = (int64_t)T1 * p.B * D;
+    float* dobs = p.o_obs + dst_tb * D;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = lane + 32 * u;
+            if (k < D) dobs[a * agent_stride_obs + k] = o[a][u];
+        }
+    float* dsh = p.o_share_obs + dst_tb * SD;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        const int k = lane + 32 * u;
+        if (k < SD) dsh[k] = sh[u];
+    }
+    if (step) {
+        const int64_t agent_stride = (int64_t)p.T * p.B;
+        if (lane < 2 * NA) {
+            const int a = lane >= NA ? 1 : 0;
+            p.o_acts[(a * agent_stride + dst_tb) * NA + (lane - a * NA)] = ac;
+        }
+        if (lane < 2) {
+            p.o_rewards[lane * agent_stride + dst_tb] = rw;
+            p.o_dones[lane * agent_stride + dst_tb] = dn;
+        }
+        if (lane == 0) p.o_dones_env[dst_tb] = de;
+    }
+}
+
 }  // namespace
 
 extern "C" int mm_segtree_set(double* sum_tree, double* min_tree, int32_t capacity, const int64_t* idx,
@@ -205,6 +269,9 @@ extern "C" int mm_replay_gather(const float* obs, const float* share_obs, const 
                    out_rewards, out_dones, out_dones_env, idx, T, S, B, A, D, SD, NA};
     const int64_t warps = (int64_t)(T + 1) * B;
     const int64_t blocks = (warps * 32 + 255) / 256;
-    replay_gather_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    if (A == 2 && D <= 64 && SD <= 96 && NA <= 16)
+        replay_gather_fast_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    else
+        replay_gather_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     return mm::check_launch();
 }
