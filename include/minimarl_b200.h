@@ -281,6 +281,18 @@ int mm_heaptree_sample(const double* tree, int32_t capacity, const double* unifo
                        int64_t* node_idx_out, double* priority_out, void* stream);
 int mm_heaptree_argmin_leaf(const double* tree, int32_t capacity, int64_t* leaf_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over short rows (N <= 128, eps 1e-5) for the differentiated network pass: the nn.LayerNorm
+ * calls of MLPLayer / RNNLayer (offpolicy/utils/algorithm_utils/mlp.py:17-29, rnn.py:18,28;
+ * mappo/utils/algorithm_utils/mlp.py:17-30, rnn.py:22,78).
+ *   fwd: y = (x - mean) * rstd * weight + bias; mean / rstd [M] are saved for the backward.
+ *   bwd: dx [M,N]; dweight_accum / dbias_accum [N] are ADDED to (zero them first).
+ * ---------------------------------------------------------------------------------------------- */
+int mm_layernorm_fwd(const float* x, const float* weight, const float* bias, float* y, float* mean, float* rstd,
+                     int64_t M, int32_t N, void* stream);
+int mm_layernorm_bwd(const float* dy, const float* x, const float* weight, const float* mean, const float* rstd,
+                     float* dx, float* dweight_accum, float* dbias_accum, int64_t M, int32_t N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,8 @@ SIGNATURES = {
     "mm_agentq_tc_param_offsets": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "mm_agentq_tc_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                        C.c_int32, _P]),
+    "mm_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "mm_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "mm_heaptree_update": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P]),
     "mm_heaptree_sample": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "mm_heaptree_argmin_leaf": (C.c_int, [_P, C.c_int32, _P, _P]),

@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from ..nn.agent_q import MLPBase, _init_linear, _tc_fits, agentq_forward, pack_agentq, pack_agentq_tc
+from ..nn.layernorm import LayerNorm
 from ..parallel import allreduce_mean_grads, allreduce_stats
 
 
@@ -105,7 +106,7 @@ class RNNLayer(nn.Module):
                 nn.init.constant_(param, 0)
             elif "weight" in name:
                 (nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_)(param)
-        self.norm = nn.LayerNorm(outputs_dim)
+        self.norm = LayerNorm(outputs_dim)
 
     def forward(self, x, hxs, masks):
         if x.size(0) == hxs.size(0):

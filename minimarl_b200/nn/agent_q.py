@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
+from .layernorm import LayerNorm
 
 _OFFSET_NAMES = ["ln0_w", "ln0_b", "w1", "b1", "ln1_w", "ln1_b", "w2", "b2", "ln2_w", "ln2_b", "wih", "whh",
                  "bih", "bhh", "ln3_w", "ln3_b", "wq", "bq"]
@@ -147,7 +148,7 @@ class MLPLayer(nn.Module):
         self._layer_N = layer_N
         act = nn.ReLU if use_ReLU else nn.Tanh
         gain = nn.init.calculate_gain("relu" if use_ReLU else "tanh")
-        mk = lambda i, o: nn.Sequential(_init_linear(nn.Linear(i, o), use_orthogonal, gain), act(), nn.LayerNorm(o))
+        mk = lambda i, o: nn.Sequential(_init_linear(nn.Linear(i, o), use_orthogonal, gain), act(), LayerNorm(o))
         self.fc1 = mk(input_dim, hidden_size)
         self.fc_h = mk(hidden_size, hidden_size)        # registered but unused, exactly like the reference (Q6)
         self.fc2 = nn.ModuleList([copy.deepcopy(self.fc_h) for _ in range(layer_N)])
@@ -170,7 +171,7 @@ class MLPBase(nn.Module):
         if getattr(args, "use_conv1d", False):
             raise NotImplementedError("use_conv1d is outside the hot path (SURVEY.md section 2)")
         if self._use_feature_normalization:
-            self.feature_norm = nn.LayerNorm(inputs_dim)
+            self.feature_norm = LayerNorm(inputs_dim)
         self.mlp = MLPLayer(inputs_dim, self.hidden_size, self._layer_N, self._use_orthogonal, self._use_ReLU)
 
     def forward(self, x):
@@ -188,7 +189,7 @@ class RNNLayer(nn.Module):
                 nn.init.constant_(param, 0)
             elif "weight" in name:
                 (nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_)(param)
-        self.norm = nn.LayerNorm(outputs_dim)
+        self.norm = LayerNorm(outputs_dim)
 
     def forward(self, x, hxs):
         x, hxs = self.rnn(x, hxs)
