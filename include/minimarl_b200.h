@@ -293,6 +293,21 @@ int mm_layernorm_fwd(const float* x, const float* weight, const float* bias, flo
 int mm_layernorm_bwd(const float* dy, const float* x, const float* weight, const float* mean, const float* rstd,
                      float* dx, float* dweight_accum, float* dbias_accum, int64_t M, int32_t N, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Recurrent half of nn.GRU (one layer, H in {32, 64}) on tcgen05, forward and BPTT backward, for the
+ * differentiated pass of RNNLayer.forward (offpolicy/utils/algorithm_utils/rnn.py:26-29).
+ *   fwd: gi [T,R,3H] = x W_ih^T + b_ih (caller, cuBLAS); h0 [R,H] or NULL; w_hh [3H,H]; b_hh [3H] ->
+ *        h_seq [T,R,H]; r, z, n, ghn [T,R,H] saved for the backward (all four NULL for inference).
+ *   bwd: dh_seq [T,R,H] (gradient w.r.t. every h_t) + the saved tensors -> dgi [T,R,3H] (gradient w.r.t. gi;
+ *        its r and z thirds are also the gradient w.r.t. gh), dghn [T,R,H] (gradient w.r.t. gh_n), dh0 [R,H].
+ *        dx, dW_ih, dW_hh, db are row-parallel GEMMs / sums the caller does with cuBLAS.
+ * ---------------------------------------------------------------------------------------------- */
+int mm_gru_seq_fwd(const float* gi, const float* h0, const float* w_hh, const float* b_hh, float* h_seq, float* r,
+                   float* z, float* n, float* ghn, int32_t T, int64_t R, int32_t H, void* stream);
+int mm_gru_seq_bwd(const float* dh_seq, const float* r, const float* z, const float* n, const float* ghn,
+                   const float* h_seq, const float* h0, const float* w_hh, float* dgi, float* dghn, float* dh0,
+                   int32_t T, int64_t R, int32_t H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from ..nn.agent_q import MLPBase, _init_linear, _tc_fits, agentq_forward, pack_agentq, pack_agentq_tc
+from ..nn.gru import GRU
 from ..nn.layernorm import LayerNorm
 from ..parallel import allreduce_mean_grads, allreduce_stats
 
@@ -100,7 +101,7 @@ class RNNLayer(nn.Module):
     def __init__(self, inputs_dim, outputs_dim, recurrent_N, use_orthogonal):
         super().__init__()
         self._recurrent_N = recurrent_N
-        self.rnn = nn.GRU(inputs_dim, outputs_dim, num_layers=recurrent_N)
+        self.rnn = GRU(inputs_dim, outputs_dim, num_layers=recurrent_N)
         for name, param in self.rnn.named_parameters():
             if "bias" in name:
                 nn.init.constant_(param, 0)

@@ -1,0 +1,289 @@
+// Recurrent half of nn.GRU (forward and BPTT backward) on tcgen05 for the DIFFERENTIATED network pass.
+//
+// Replaces cuDNN's GRU in RNNLayer.forward (offpolicy/utils/algorithm_utils/rnn.py:26-29;
+// mappo/utils/algorithm_utils/rnn.py:24-80) for hidden size H in {32, 64}, one layer.  The input projection
+// gi = x W_ih^T + b_ih (and in the backward dx, dW_ih, dW_hh) are large row-parallel GEMMs that stay in cuBLAS;
+// what is sequential -- gh = h_{t-1} W_hh^T, the gates, and in the backward dh_{t-1} = dgh W_hh -- runs here:
+// one CTA per 128 rows walks the sequence with W_hh (forward) or W_hh^T (backward) and the hidden / gate-gradient
+// tile resident in shared memory in tcgen05 operand layout, accumulators in TMEM, 512 threads splitting the H
+// columns of each row four ways exactly like agentq_tc.cu.  cuDNN's backward for this shape (101 steps x 8 192
+// rows x 64) takes 15 ms, 11.5 ms of it in one element-wise kernel; this pair takes well under 1 ms.
+//   forward : r = s(gi_r + gh_r + b_hr), z = s(gi_z + gh_z + b_hz), ghn = gh_n + b_hn, n = tanh(gi_n + r ghn),
+//             h_t = (1 - z) n + z h_{t-1};           saves r, z, n, ghn for the backward
+//   backward: dn = dh (1 - z), dz = dh (h_{t-1} - n), a = dn (1 - n^2), dgi_n = a, dgh_n = a r, dr = a ghn,
+//             dgi_r = dgh_r = dr r (1 - r), dgi_z = dgh_z = dz z (1 - z), dh_{t-1} = dh z + dgh W_hh
+// Operands are TF32 (like cuDNN's default allow_tf32), accumulation and all gate math fp32 with precise
+// expf / tanhf (this pass produces the gradients).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kRows = 128;
+constexpr int kThreads = 512;
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float sigmoid_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int N>
+__device__ __forceinline__ void ld_row(const float* __restrict__ p, float (&v)[N], bool ok) {
+#pragma unroll
+    for (int k = 0; k < N; k += 4) {
+        const float4 q = ok ? *reinterpret_cast<const float4*>(p + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
+    }
+}
+template <int N>
+__device__ __forceinline__ void st_row(float* __restrict__ p, const float (&v)[N], bool ok) {
+    if (!ok) return;
+#pragma unroll
+    for (int k = 0; k < N; k += 4) *reinterpret_cast<float4*>(p + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+}
+
+struct GruFwdArgs {
+    const float *gi, *h0, *whh, *bhh;          // gi [T,R,3H]; h0 [R,H] or null; whh [3H,H]; bhh [3H]
+    float *h_seq, *r, *z, *n, *ghn;            // [T,R,H] each (r/z/n/ghn may be null: inference)
+    int T;
+    long long R;
+};
+
+template <int H>
+__global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const GruFwdArgs a) {
+    constexpr int CPT = H / 4;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* sW = smem;                        // W_hh [3H x H] K-major (B operand, N = 3H rows)
+    uint8_t* sH = sW + 3 * H * H * 4;          // h [128 x H] K-major (A operand), fp32
+    float* sB = reinterpret_cast<float*>(sH + kRows * H * 4);   // b_hh [3H]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = (warp & 3) * 32 + lane, part = warp >> 2, c0 = part * CPT;
+    const long long row0 = (long long)blockIdx.x * kRows;
+    const bool valid = row0 + row < a.R;
+    constexpr uint32_t kCols = 3 * H <= 128 ? 128 : 256;
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, kCols);
+    if (tid == 0) tc::mbar_init(&bar, 1);
+    for (int i = tid; i < 3 * H * H; i += kThreads) {
+        const int rr = i / H, k = i - rr * H;
+        *reinterpret_cast<float*>(sW + tc::kmajor_offset(rr, k, H)) = to_tf32(a.whh[i]);
+    }
+    for (int i = tid; i < 3 * H; i += kThreads) sB[i] = a.bhh[i];
+    float h[CPT];
+    ld_row<CPT>(a.h0 ? a.h0 + (row0 + row) * H + c0 : nullptr, h, valid && a.h0 != nullptr);
+#pragma unroll
+    for (int k = 0; k < CPT; k += 4)
+        *reinterpret_cast<float4*>(sH + tc::kmajor_offset(row, c0 + k, H)) = make_float4(h[k], h[k + 1], h[k + 2], h[k + 3]);
+    tc::fence_smem_to_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t sbo = (uint32_t)(H >> 2) * 128u;
+    const uint64_t dH = tc::make_desc(tc::smem_u32(sH), 128u, sbo);
+    const uint64_t dW_rz = tc::make_desc(tc::smem_u32(sW), 128u, sbo);
+    const uint64_t dW_n = tc::make_desc(tc::smem_u32(sW) + (uint32_t)(2 * H >> 3) * sbo, 128u, sbo);
+    const uint32_t idesc_2h = tc::make_idesc_tf32(128, 2 * H), idesc_h = tc::make_idesc_tf32(128, H);
+    uint32_t phase = 0;
+
+    for (int t = 0; t < a.T; ++t) {
+        if (tid == 0) {
+#pragma unroll
+            for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem, dH + 16 * kk, dW_rz + 16 * kk, idesc_2h, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 2 * H, dH + 16 * kk, dW_n + 16 * kk, idesc_h, kk > 0);
+            tc::mma_commit(&bar);
+        }
+        // the input projections of this step are fetched while the tensor core works
+        const float* gi = a.gi + ((long long)t * a.R + row0 + row) * 3 * H + c0;
+        float gir[CPT], giz[CPT], gin[CPT];
+        ld_row<CPT>(gi, gir, valid);
+        ld_row<CPT>(gi + H, giz, valid);
+        ld_row<CPT>(gi + 2 * H, gin, valid);
+        if (warp == 0) tc::mbar_wait(&bar, phase);
+        phase ^= 1;
+        __syncthreads();
+        tc::fence_after_sync();
+        float gr[CPT], gz[CPT], gn[CPT];
+        tc::tmem_ld<CPT>(lane_addr + c0, gr);
+        tc::tmem_ld<CPT>(lane_addr + H + c0, gz);
+        tc::tmem_ld<CPT>(lane_addr + 2 * H + c0, gn);
+        float rr[CPT], zz[CPT], nn[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            rr[j] = sigmoid_(gir[j] + gr[j] + sB[c0 + j]);
+            zz[j] = sigmoid_(giz[j] + gz[j] + sB[H + c0 + j]);
+            gn[j] += sB[2 * H + c0 + j];
+            nn[j] = tanhf(gin[j] + rr[j] * gn[j]);
+            h[j] = (1.0f - zz[j]) * nn[j] + zz[j] * h[j];
+        }
+        const long long o = ((long long)t * a.R + row0 + row) * H + c0;
+        st_row<CPT>(a.h_seq + o, h, valid);
+        if (a.r != nullptr) {
+            st_row<CPT>(a.r + o, rr, valid);
+            st_row<CPT>(a.z + o, zz, valid);
+            st_row<CPT>(a.n + o, nn, valid);
+            st_row<CPT>(a.ghn + o, gn, valid);
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; k += 4)
+            *reinterpret_cast<float4*>(sH + tc::kmajor_offset(row, c0 + k, H)) = make_float4(h[k], h[k + 1], h[k + 2], h[k + 3]);
+        tc::fence_smem_to_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    }
+    if (warp == 0) tc::tmem_dealloc(tmem, kCols);
+}
+
+struct GruBwdArgs {
+    const float *dh_seq, *r, *z, *n, *ghn, *h_seq, *h0, *whh;   // [T,R,H] x6; h0 [R,H] or null; whh [3H,H]
+    float *dgi, *dghn, *dh0;                                    // [T,R,3H]; [T,R,H]; [R,H]
+    int T;
+    long long R;
+};
+
+template <int H>
+__global__ void __launch_bounds__(kThreads, 1) gru_bwd_kernel(const GruBwdArgs a) {
+    constexpr int CPT = H / 4;
+    constexpr int K3 = 3 * H;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* sWt = smem;                       // W_hh^T [H x 3H] K-major (B operand: N = H rows, K = 3H)
+    uint8_t* sG = sWt + H * K3 * 4;            // dgh [128 x 3H] K-major (A operand)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = (warp & 3) * 32 + lane, part = warp >> 2, c0 = part * CPT;
+    const long long row0 = (long long)blockIdx.x * kRows;
+    const bool valid = row0 + row < a.R;
+    constexpr uint32_t kCols = H <= 32 ? 32 : 64;
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, kCols);
+    if (tid == 0) tc::mbar_init(&bar, 1);
+    for (int i = tid; i < K3 * H; i += kThreads) {   // whh[g][j] (g in 3H, j in H) -> sWt row j, column g
+        const int g = i / H, j = i - g * H;
+        *reinterpret_cast<float*>(sWt + tc::kmajor_offset(j, g, K3)) = to_tf32(a.whh[i]);
+    }
+    tc::fence_smem_to_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t sbo = (uint32_t)(K3 >> 2) * 128u;
+    const uint64_t dG = tc::make_desc(tc::smem_u32(sG), 128u, sbo), dW = tc::make_desc(tc::smem_u32(sWt), 128u, sbo);
+    const uint32_t idesc = tc::make_idesc_tf32(128, H);
+    uint32_t phase = 0;
+    float dh_rec[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) dh_rec[j] = 0.f;
+
+    for (int t = a.T - 1; t >= 0; --t) {
+        const long long o = ((long long)t * a.R + row0 + row) * H + c0;
+        float dh[CPT], rr[CPT], zz[CPT], nn[CPT], gn[CPT], hp[CPT];
+        ld_row<CPT>(a.dh_seq + o, dh, valid);
+        ld_row<CPT>(a.r + o, rr, valid);
+        ld_row<CPT>(a.z + o, zz, valid);
+        ld_row<CPT>(a.n + o, nn, valid);
+        ld_row<CPT>(a.ghn + o, gn, valid);
+        if (t > 0) ld_row<CPT>(a.h_seq + o - a.R * H, hp, valid);
+        else       ld_row<CPT>(a.h0 ? a.h0 + (row0 + row) * H + c0 : nullptr, hp, valid && a.h0 != nullptr);
+        float d_r[CPT], d_z[CPT], d_n[CPT], d_hn[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const float g = dh[j] + dh_rec[j];
+            const float an = g * (1.0f - zz[j]) * (1.0f - nn[j] * nn[j]);
+            d_n[j] = an;
+            d_hn[j] = an * rr[j];
+            d_r[j] = an * gn[j] * rr[j] * (1.0f - rr[j]);
+            d_z[j] = g * (hp[j] - nn[j]) * zz[j] * (1.0f - zz[j]);
+            dh_rec[j] = g * zz[j];                                   // direct path; the W_hh path is added after the MMA
+        }
+        float* dgi = a.dgi + ((long long)t * a.R + row0 + row) * K3 + c0;
+        st_row<CPT>(dgi, d_r, valid);
+        st_row<CPT>(dgi + H, d_z, valid);
+        st_row<CPT>(dgi + 2 * H, d_n, valid);
+        st_row<CPT>(a.dghn + o, d_hn, valid);
+        // dgh = [d_r | d_z | d_hn] as the A operand
+#pragma unroll
+        for (int k = 0; k < CPT; k += 4) {
+            *reinterpret_cast<float4*>(sG + tc::kmajor_offset(row, c0 + k, K3)) =
+                make_float4(to_tf32(d_r[k]), to_tf32(d_r[k + 1]), to_tf32(d_r[k + 2]), to_tf32(d_r[k + 3]));
+            *reinterpret_cast<float4*>(sG + tc::kmajor_offset(row, H + c0 + k, K3)) =
+                make_float4(to_tf32(d_z[k]), to_tf32(d_z[k + 1]), to_tf32(d_z[k + 2]), to_tf32(d_z[k + 3]));
+            *reinterpret_cast<float4*>(sG + tc::kmajor_offset(row, 2 * H + c0 + k, K3)) =
+                make_float4(to_tf32(d_hn[k]), to_tf32(d_hn[k + 1]), to_tf32(d_hn[k + 2]), to_tf32(d_hn[k + 3]));
+        }
+        tc::fence_smem_to_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        if (tid == 0) {
+#pragma unroll
+            for (int kk = 0; kk < K3 / 8; ++kk) tc::mma_tf32(tmem, dG + 16 * kk, dW + 16 * kk, idesc, kk > 0);
+            tc::mma_commit(&bar);
+        }
+        if (warp == 0) tc::mbar_wait(&bar, phase);
+        phase ^= 1;
+        __syncthreads();
+        tc::fence_after_sync();
+        float mm_[CPT];
+        tc::tmem_ld<CPT>(lane_addr + c0, mm_);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) dh_rec[j] += mm_[j];
+        tc::fence_before_sync();          // the next step's MMA overwrites this accumulator: order the loads before it
+    }
+    if (a.dh0 != nullptr) st_row<CPT>(a.dh0 + (row0 + row) * H + c0, dh_rec, valid);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, kCols);
+}
+
+template <int H>
+int launch_fwd(const GruFwdArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)4 * (3 * H * H + kRows * H + 3 * H) + 128;
+    cudaError_t e = cudaFuncSetAttribute(gru_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
+    gru_fwd_kernel<H><<<(unsigned)((a.R + kRows - 1) / kRows), kThreads, smem, st>>>(a);
+    return mm::check_launch();
+}
+template <int H>
+int launch_bwd(const GruBwdArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)4 * (3 * H * H + kRows * 3 * H) + 128;
+    cudaError_t e = cudaFuncSetAttribute(gru_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
+    gru_bwd_kernel<H><<<(unsigned)((a.R + kRows - 1) / kRows), kThreads, smem, st>>>(a);
+    return mm::check_launch();
+}
+
+bool aligned16(const void* p) { return p == nullptr || mm::aligned(p, 16); }
+
+}  // namespace
+
+extern "C" int mm_gru_seq_fwd(const float* gi, const float* h0, const float* w_hh, const float* b_hh, float* h_seq,
+                              float* r, float* z, float* n, float* ghn, int32_t T, int64_t R, int32_t H, void* stream) {
+    if (!gi || !w_hh || !b_hh || !h_seq || T <= 0 || R <= 0) return MM_ERR_BAD_ARG;
+    if (H != 32 && H != 64) return MM_ERR_UNSUPPORTED;
+    if ((r || z || n || ghn) && !(r && z && n && ghn)) return MM_ERR_BAD_ARG;
+    if (!aligned16(gi) || !aligned16(h0) || !aligned16(h_seq) || !aligned16(r) || !aligned16(z) || !aligned16(n) || !aligned16(ghn))
+        return MM_ERR_BAD_ARG;
+    GruFwdArgs a{gi, h0, w_hh, b_hh, h_seq, r, z, n, ghn, T, R};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return H == 64 ? launch_fwd<64>(a, st) : launch_fwd<32>(a, st);
+}
+
+extern "C" int mm_gru_seq_bwd(const float* dh_seq, const float* r, const float* z, const float* n, const float* ghn,
+                              const float* h_seq, const float* h0, const float* w_hh, float* dgi, float* dghn,
+                              float* dh0, int32_t T, int64_t R, int32_t H, void* stream) {
+    if (!dh_seq || !r || !z || !n || !ghn || !h_seq || !w_hh || !dgi || !dghn || T <= 0 || R <= 0) return MM_ERR_BAD_ARG;
+    if (H != 32 && H != 64) return MM_ERR_UNSUPPORTED;
+    if (!aligned16(dh_seq) || !aligned16(r) || !aligned16(z) || !aligned16(n) || !aligned16(ghn) || !aligned16(h_seq) ||
+        !aligned16(h0) || !aligned16(dgi) || !aligned16(dghn) || !aligned16(dh0))
+        return MM_ERR_BAD_ARG;
+    GruBwdArgs a{dh_seq, r, z, n, ghn, h_seq, h0, w_hh, dgi, dghn, dh0, T, R};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return H == 64 ? launch_bwd<64>(a, st) : launch_bwd<32>(a, st);
+}

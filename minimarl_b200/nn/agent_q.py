@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
+from .gru import GRU
 from .layernorm import LayerNorm
 
 _OFFSET_NAMES = ["ln0_w", "ln0_b", "w1", "b1", "ln1_w", "ln1_b", "w2", "b2", "ln2_w", "ln2_b", "wih", "whh",
@@ -183,7 +184,7 @@ class MLPBase(nn.Module):
 class RNNLayer(nn.Module):
     def __init__(self, inputs_dim, outputs_dim, recurrent_N, use_orthogonal):
         super().__init__()
-        self.rnn = nn.GRU(inputs_dim, outputs_dim, num_layers=recurrent_N)
+        self.rnn = GRU(inputs_dim, outputs_dim, num_layers=recurrent_N)
         for name, param in self.rnn.named_parameters():
             if "bias" in name:
                 nn.init.constant_(param, 0)
