@@ -261,6 +261,10 @@ def learner_section(dev, steps):
     from minimarl_b200.buffers import PrioritizedRecReplayBuffer
     from minimarl_b200.envs.spaces import Box, Discrete
     T, A, D, NA, S, B = 100, 2, 47, 5, 10000, 4096
+    # TF32 operands / fp32 accumulation throughout the learner: the custom kernels (tcgen05 kind::tf32) and, with this
+    # flag, the remaining cuBLAS GEMMs (hypernetworks, input projections, weight gradients)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
     args = ap.Namespace(
         hidden_size=64, use_rnn_layer=True, use_orthogonal=True, gain=0.01, layer_N=1, recurrent_N=1,
         use_feature_normalization=True, use_ReLU=True, use_conv1d=False, prev_act_inp=False, batch_size=B,
@@ -322,7 +326,7 @@ def learner_section(dev, steps):
     return {
         "metric": "QMIX train samples/sec", "value": B * T / (ms_update * 1e-3), "unit": "samples/s",
         "config": {"buffer_episodes": S, "episode_length": T, "batch_episodes": B, "agents": A, "hidden": 64,
-                   "per": True, "double_q": True, "precision": "fp32"},
+                   "per": True, "double_q": True, "precision": "tf32 operands, fp32 accumulate (custom kernels and cuBLAS)"},
         "ms_per_update": ms_update, "loss": float(info_["loss"]),
         "sample_gather": {"ms": ms_sample, "algorithmic_GBps": gather_bytes / (ms_sample * 1e-3) / 1e9,
                           "frac_of_measured_hbm": gather_bytes / (ms_sample * 1e-3) / 1e9 / peak},

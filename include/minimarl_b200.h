@@ -308,6 +308,14 @@ int mm_gru_seq_bwd(const float* dh_seq, const float* r, const float* z, const fl
                    const float* h_seq, const float* h0, const float* w_hh, float* dgi, float* dghn, float* dh0,
                    int32_t T, int64_t R, int32_t H, void* stream);
 
+/* The mixing step of QMixer.forward after the hypernetworks (q_mixer.py:80-93), forward and backward, for the
+ * differentiated pass:  out[m] = elu(q[m,:] @ w1[m,:,:] + b1[m,:]) . w2[m,:] + b2[m]
+ *   q [M,A]; w1 [M,A,32] (already |.|); b1 [M,32]; w2 [M,32] (already |.|); b2 [M]; A in {2, 4}. */
+int mm_qmix_mixing_fwd(const float* q, const float* w1, const float* b1, const float* w2, const float* b2, float* out,
+                       int64_t M, int32_t A, void* stream);
+int mm_qmix_mixing_bwd(const float* dout, const float* q, const float* w1, const float* b1, const float* w2, float* dq,
+                       float* dw1, float* db1, float* dw2, float* db2, int64_t M, int32_t A, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,8 @@ SIGNATURES = {
     "mm_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "mm_gru_seq_fwd": (C.c_int, [_P] * 9 + [C.c_int32, C.c_int64, C.c_int32, _P]),
     "mm_gru_seq_bwd": (C.c_int, [_P] * 11 + [C.c_int32, C.c_int64, C.c_int32, _P]),
+    "mm_qmix_mixing_fwd": (C.c_int, [_P] * 6 + [C.c_int64, C.c_int32, _P]),
+    "mm_qmix_mixing_bwd": (C.c_int, [_P] * 10 + [C.c_int64, C.c_int32, _P]),
     "mm_heaptree_update": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P]),
     "mm_heaptree_sample": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "mm_heaptree_argmin_leaf": (C.c_int, [_P, C.c_int32, _P, _P]),

@@ -48,6 +48,31 @@ def pack_qmixer(sd, SD, A, device, prefix=""):
     return buf
 
 
+class _MixingFn(torch.autograd.Function):
+    """hidden = elu(q @ w1 + b1); out = hidden . w2 + b2 per row, one warp per row (mm_qmix_mixing_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, q, w1, b1, w2, b2):
+        M, A = q.shape
+        q, w1, b1, w2, b2 = (t.contiguous() for t in (q, w1, b1, w2, b2))
+        out = torch.empty(M, dtype=torch.float32, device=q.device)
+        _lib.check(_lib.lib().mm_qmix_mixing_fwd(_lib.ptr(q), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2),
+                                                 _lib.ptr(out), M, A, _lib.stream()))
+        ctx.save_for_backward(q, w1, b1, w2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, w1, b1, w2 = ctx.saved_tensors
+        M, A = q.shape
+        dq, dw1, db1, dw2 = torch.empty_like(q), torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2)
+        db2 = torch.empty(M, dtype=torch.float32, device=q.device)
+        _lib.check(_lib.lib().mm_qmix_mixing_bwd(_lib.ptr(dout.contiguous()), _lib.ptr(q), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2),
+                                                 _lib.ptr(dq), _lib.ptr(dw1), _lib.ptr(db1), _lib.ptr(dw2), _lib.ptr(db2),
+                                                 M, A, _lib.stream()))
+        return dq, dw1, db1, dw2, db2
+
+
 def _init(m, use_orthogonal):
     (nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_)(m.weight.data, gain=1)
     nn.init.constant_(m.bias.data, 0)
@@ -101,6 +126,14 @@ class QMixer(nn.Module):
                                                     s.shape[0], self.cent_obs_dim, self.num_agents, _lib.stream()))
             return out.view(-1, batch_size, 1, 1)
         states = states.view(-1, batch_size, self.cent_obs_dim).float()
+        if states.is_cuda and self.hidden_layer_dim == 32 and self.num_mixer_q_inps in (2, 4):
+            # differentiated pass: hypernetworks through cuBLAS, the per-row mixing through one custom kernel
+            s2 = states.reshape(-1, self.cent_obs_dim)
+            w1 = torch.abs(self.hyper_w1(s2)).view(-1, self.num_mixer_q_inps, self.hidden_layer_dim)
+            w2 = torch.abs(self.hyper_w2(s2))
+            out = _MixingFn.apply(agent_q_inps.reshape(-1, self.num_mixer_q_inps), w1, self.hyper_b1(s2), w2,
+                                  self.hyper_b2(s2).reshape(-1))
+            return out.view(-1, batch_size, 1, 1)
         agent_q_inps = agent_q_inps.view(-1, batch_size, 1, self.num_mixer_q_inps)
         w1 = torch.abs(self.hyper_w1(states)).view(-1, batch_size, self.num_mixer_q_inps, self.hidden_layer_dim)
         b1 = self.hyper_b1(states).view(-1, batch_size, 1, self.hidden_layer_dim)
