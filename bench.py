@@ -306,9 +306,17 @@ def learner_section(dev, steps):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n, out
 
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
     for _ in range(3):
         update()
+    if world > 1:
+        dist.barrier()
     ms_update, info_ = timed(update, steps)
+    if world > 1:                       # weak scaling: every rank trains on its own batch, gradients all-reduced (NCCL)
+        t_ = torch.tensor([ms_update], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        ms_update = float(t_.item())
     # component timings (each in isolation, after the full updates)
     ms_sample, sample = timed(lambda: buf.sample(B, beta=0.4, p_id="policy_0"), 5)
     stacked = torch.cat(list(sample[0]["policy_0"]), dim=-2)
@@ -324,8 +332,9 @@ def learner_section(dev, steps):
     peak, _ = measured_peaks()
     gather_bytes = 2 * 81952 * B
     return {
-        "metric": "QMIX train samples/sec", "value": B * T / (ms_update * 1e-3), "unit": "samples/s",
-        "config": {"buffer_episodes": S, "episode_length": T, "batch_episodes": B, "agents": A, "hidden": 64,
+        "metric": "QMIX train samples/sec", "value": world * B * T / (ms_update * 1e-3), "unit": "samples/s",
+        "n_gpus": world, "grad_allreduce": "NCCL all-reduce of one flattened fp32 bucket per update" if world > 1 else None,
+        "config": {"buffer_episodes": S, "episode_length": T, "batch_episodes_per_gpu": B, "agents": A, "hidden": 64,
                    "per": True, "double_q": True, "precision": "tf32 operands, fp32 accumulate (custom kernels and cuBLAS)"},
         "ms_per_update": ms_update, "loss": float(info_["loss"]),
         "sample_gather": {"ms": ms_sample, "algorithmic_GBps": gather_bytes / (ms_sample * 1e-3) / 1e9,
@@ -440,6 +449,13 @@ def run_ours(args, wl):
         e2e_s = float(t.item())
     e2e_value = n * A * e2e_steps * world / e2e_s
 
+    learner = None
+    if not args.no_learner:             # on every rank: the update all-reduces its gradients when world > 1
+        try:
+            learner = learner_section(dev, args.learner_steps)
+        except Exception as e:          # the headline line must survive a learner failure; report it
+            learner = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         peak, peak_kind = measured_peaks()
         achieved = n * T * ENV_STEP_BYTES / (rollout_ms * 1e-3) / 1e9
@@ -481,10 +497,7 @@ def run_ours(args, wl):
                 line["policy_rollout"] = policy_rollout_section(dev, args.learner_steps)
             except Exception as e:
                 line["policy_rollout"] = {"error": f"{type(e).__name__}: {e}"}
-            try:
-                line["learner"] = learner_section(dev, args.learner_steps)
-            except Exception as e:          # the headline line must survive a learner failure; report it
-                line["learner"] = {"error": f"{type(e).__name__}: {e}"}
+            line["learner"] = learner
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
