@@ -316,6 +316,24 @@ int mm_qmix_mixing_fwd(const float* q, const float* w1, const float* b1, const f
 int mm_qmix_mixing_bwd(const float* dout, const float* q, const float* w1, const float* b1, const float* w2, float* dq,
                        float* dw1, float* db1, float* dw2, float* db2, int64_t M, int32_t A, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused MAPPO rollout (mappo/runner/shared/magym_runner.py:41-98 run/collect/insert, rmappo_policy.py:57-95
+ * get_actions, r_actor_critic.py:60-93,189-208): T lockstep steps of actor + critic (hidden 32, local-obs critic)
+ * + categorical sampling + Checkers step (auto-reset) in ONE launch, writing every SharedReplayBuffer field of
+ * shared_buffer.py:82-117 in place.  Buffers are the contiguous SharedReplayBuffer tensors:
+ *   obs, share_obs [T+1, N, 2, 47]; rnn_states, rnn_states_critic [T+1, N, 2, 1, 32]; masks [T+1, N, 2, 1];
+ *   actions, action_log_probs, value_preds (first T slabs), rewards [T, N, 2, 1].
+ * Slab 0 of obs / rnn_states / masks is the input (obs[0] is written when do_reset != 0).
+ * params: mm_mappo_rollout_param_offsets layout; LayerNorm(47)'s affine is folded into the first Linear on the host.
+ * Sampling: inverse CDF on softmax(logits) with one Philox4x32-10 uniform per (step_offset + t, row).
+ * ---------------------------------------------------------------------------------------------- */
+int mm_mappo_rollout_param_count(void);
+int mm_mappo_rollout_param_offsets(int32_t* offsets19);
+int mm_mappo_rollout_tc(const float* params, uint32_t* env_state, float* obs, float* share_obs, float* rnn_states,
+                        float* rnn_states_critic, float* actions, float* action_log_probs, float* value_preds,
+                        float* rewards, float* masks, int32_t T, int64_t n_envs, int32_t do_reset, uint64_t seed,
+                        uint64_t step_offset, const mm_checkers_cfg* cfg_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

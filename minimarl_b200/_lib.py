@@ -84,6 +84,10 @@ SIGNATURES = {
     "mm_heaptree_update": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P]),
     "mm_heaptree_sample": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "mm_heaptree_argmin_leaf": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "mm_mappo_rollout_param_count": (C.c_int, []),
+    "mm_mappo_rollout_param_offsets": (C.c_int, [_P]),
+    "mm_mappo_rollout_tc": (C.c_int, [_P] * 11 + [C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64,
+                                                  C.POINTER(CheckersCfg), _P]),
     "mm_qmix_rollout_tc": (C.c_int, [_P, _P, _P, _P, C.POINTER(RolloutIO), C.POINTER(CheckersCfg), C.POINTER(C.c_float),
                                      C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _P]),
 }

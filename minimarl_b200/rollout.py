@@ -65,6 +65,79 @@ def qmix_rollout(net, env, T, eps, seed=0, step_offset=0, obs=None, act_idx=None
                 h_final=h_final, q=q_out)
 
 
+_MAPPO_OFFSETS = None
+
+
+def _mappo_offsets():
+    global _MAPPO_OFFSETS
+    if _MAPPO_OFFSETS is None:
+        o = (C.c_int32 * 19)()
+        _lib.check(_lib.lib().mm_mappo_rollout_param_offsets(o))
+        names = ("w1 w2 wih whh b1 ln1_w ln1_b b2 ln2_w ln2_b bih bhh ln3_w ln3_b wa wv ba bv total").split()
+        _MAPPO_OFFSETS = dict(zip(names, list(o)))
+    return _MAPPO_OFFSETS
+
+
+def mappo_rollout_fusable(policy, env):
+    """True when ``mm_mappo_rollout_tc`` covers this policy / env pair: hidden 32, one MLP layer + one GRU layer with
+    feature normalisation and ReLU (the defaults of mappo/_config.py:176-249), local-observation critic, Checkers with
+    partial observations."""
+    a, c = policy.actor, policy.critic
+    return (getattr(a, "_fusable", False) and getattr(c, "_fusable", False) and a.hidden_size == 32 and
+            a._in == 47 and c._in == 47 and a._n_out == 5 and a._precision == "tf32" and
+            env.__class__.__name__ == "BatchedCheckers" and not env.full_observable and env.n_agents == 2)
+
+
+def pack_mappo_rollout(actor, critic, out=None):
+    """Flatten actor + critic into the ``mm_mappo_rollout_tc`` parameter buffer.  LayerNorm(47)'s affine is folded
+    into the first Linear: W1' = W1 diag(gamma), b1' = b1 + W1 beta (r_actor_critic.py / mlp.py feature_norm -> fc1)."""
+    o = _mappo_offsets()
+    dev = next(actor.parameters()).device
+    buf = torch.zeros(o["total"], dtype=torch.float32, device=dev) if out is None else out
+    H, K1 = 32, 48
+    with torch.no_grad():
+        for k, net in enumerate((actor, critic)):
+            sd = dict(net.named_parameters())
+            g, b = sd["base.feature_norm.weight"], sd["base.feature_norm.bias"]
+            W1, b1 = sd["base.mlp.fc1.0.weight"], sd["base.mlp.fc1.0.bias"]
+            w1 = buf[o["w1"] + k * H * K1: o["w1"] + (k + 1) * H * K1].view(H, K1)
+            w1.zero_()
+            w1[:, :47] = W1 * g
+            def put(name, val, n):
+                buf[o[name] + k * n: o[name] + (k + 1) * n] = val.reshape(-1)
+            put("b1", b1 + W1 @ b, H)
+            put("ln1_w", sd["base.mlp.fc1.2.weight"], H); put("ln1_b", sd["base.mlp.fc1.2.bias"], H)
+            put("w2", sd["base.mlp.fc2.0.0.weight"], H * H); put("b2", sd["base.mlp.fc2.0.0.bias"], H)
+            put("ln2_w", sd["base.mlp.fc2.0.2.weight"], H); put("ln2_b", sd["base.mlp.fc2.0.2.bias"], H)
+            put("wih", sd["rnn.rnn.weight_ih_l0"], 3 * H * H); put("whh", sd["rnn.rnn.weight_hh_l0"], 3 * H * H)
+            put("bih", sd["rnn.rnn.bias_ih_l0"], 3 * H); put("bhh", sd["rnn.rnn.bias_hh_l0"], 3 * H)
+            put("ln3_w", sd["rnn.norm.weight"], H); put("ln3_b", sd["rnn.norm.bias"], H)
+        sa, sc = dict(actor.named_parameters()), dict(critic.named_parameters())
+        buf[o["wa"]: o["wa"] + 5 * H] = sa["act.action_out.linear.weight"].reshape(-1)
+        buf[o["ba"]: o["ba"] + 5] = sa["act.action_out.linear.bias"]
+        buf[o["wv"]: o["wv"] + H] = sc["v_out.weight"].reshape(-1)
+        buf[o["bv"]: o["bv"] + 1] = sc["v_out.bias"]
+    return buf
+
+
+def mappo_rollout(params, env, buffer, T=None, seed=0, step_offset=0, reset=False):
+    """T lockstep steps of policy + env written straight into ``buffer`` (a device SharedReplayBuffer whose
+    n_rollout_threads == env.n_envs): obs/share_obs/rnn_states/rnn_states_critic/masks [1..T], actions,
+    action_log_probs, value_preds, rewards [0..T-1].  Slab 0 is the input (``reset=True`` resets the envs first)."""
+    T = buffer.episode_length if T is None else T
+    N = env.n_envs
+    b = buffer
+    assert b.obs.shape[1] == N and b.obs.shape[0] >= T + 1 and b.obs.shape[-1] == 47 and b.share_obs.shape[-1] == 47
+    for x in (b.obs, b.share_obs, b.rnn_states, b.rnn_states_critic, b.actions, b.action_log_probs, b.value_preds,
+              b.rewards, b.masks):
+        assert x.is_contiguous() and x.dtype == torch.float32
+    _lib.check(_lib.lib().mm_mappo_rollout_tc(
+        _lib.ptr(params), _lib.ptr(env.state), _lib.ptr(b.obs), _lib.ptr(b.share_obs), _lib.ptr(b.rnn_states),
+        _lib.ptr(b.rnn_states_critic), _lib.ptr(b.actions), _lib.ptr(b.action_log_probs), _lib.ptr(b.value_preds),
+        _lib.ptr(b.rewards), _lib.ptr(b.masks), int(T), int(N), int(bool(reset)), int(seed), int(step_offset),
+        C.byref(env.cfg), _lib.stream()))
+
+
 class EpisodeCollector:
     """N lockstep envs -> N episodes per call, written straight into a PrioritizedRecReplayBuffer / RecReplayBuffer."""
 

@@ -5,11 +5,16 @@ The reference steps ONE env object ``batch_size`` times per time step (quirk Q1 
 ``train_env`` is a ``BatchedCheckers`` with ``n_envs == args.batch_size`` boards (auto-reset on done), the actor
 and critic run as one fused kernel each per step, the env kernel writes ``obs[t+1]`` / ``rewards[t]`` of the
 device ``SharedReplayBuffer`` in place, returns come from the GAE kernel, and ``R_MAPPO.train`` does the update.
+
+With the default network (hidden 32, local-observation critic, partial observations) the whole T-step rollout --
+collect + env.step + insert of every step -- is ONE launch of ``mm_mappo_rollout_tc`` (``args.fused_rollout``,
+default on; ``collect`` / ``insert`` stay available and are what the per-step path runs).
 """
 import torch
 
 from ..algorithms.mappo import R_MAPPO, R_MAPPOPolicy
 from ..buffers import SharedReplayBuffer
+from ..rollout import mappo_rollout, mappo_rollout_fusable, pack_mappo_rollout
 
 
 class MAGYM_Runner:
@@ -30,6 +35,32 @@ class MAGYM_Runner:
                                          device=self.device)
         self._dones = torch.zeros((self.batch_size, self.num_agents), dtype=torch.uint8, device=self.device)
         self.train_infos = []
+        self.fused_rollout = bool(getattr(args, "fused_rollout", True)) and mappo_rollout_fusable(self.policy, self.train_env)
+        self._packed, self._packed_key = None, None
+        self._seed, self._steps_done = int(getattr(args, "seed", 0)), 0
+
+    def _rollout_params(self):
+        ps = list(self.policy.actor.parameters()) + list(self.policy.critic.parameters())
+        key = tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps)
+        if key != self._packed_key:
+            self._packed, self._packed_key = pack_mappo_rollout(self.policy.actor, self.policy.critic, out=self._packed), key
+        return self._packed
+
+    @torch.no_grad()
+    def rollout(self):
+        """All ``episode_length`` lockstep steps of collect / env.step / insert."""
+        b, N, A = self.buffer, self.batch_size, self.num_agents
+        if self.fused_rollout:
+            mappo_rollout(self._rollout_params(), self.train_env, b, self.episode_length, seed=self._seed,
+                          step_offset=self._steps_done)
+        else:
+            for step in range(self.episode_length):
+                values, actions, log_probs, rnn_a, rnn_c = self.collect(step)
+                self.train_env.step_into(actions.reshape(N, A).to(torch.int32).contiguous(), b.obs[step + 1],
+                                         b.rewards[step].view(N, A), self._dones)
+                self.insert((b.obs[step + 1], b.obs[step + 1], b.rewards[step], self._dones, values, actions, log_probs,
+                             rnn_a, rnn_c))
+        self._steps_done += self.episode_length
 
     def warmup(self):
         self.train_env.reset(out=self.buffer.obs[0])
@@ -75,13 +106,7 @@ class MAGYM_Runner:
         """One rollout of T lockstep steps + one PPO update (the body of the reference's ``run`` loop)."""
         if self.use_linear_lr_decay:
             self.policy.lr_decay(episode=episode, episodes=self.max_episodes)
-        b, N, A = self.buffer, self.batch_size, self.num_agents
-        for step in range(self.episode_length):
-            values, actions, log_probs, rnn_a, rnn_c = self.collect(step)
-            self.train_env.step_into(actions.reshape(N, A).to(torch.int32).contiguous(), b.obs[step + 1],
-                                     b.rewards[step].view(N, A), self._dones)
-            self.insert((b.obs[step + 1], b.obs[step + 1], b.rewards[step], self._dones, values, actions, log_probs,
-                         rnn_a, rnn_c))
+        self.rollout()
         self.compute()
         infos = self.train()
         self.train_infos.append(infos)
