@@ -217,6 +217,14 @@ int mm_qmix_td(const float* q_tot, const float* next_q_tot, const float* rewards
 /* Self-test of the tcgen05 / TMEM building blocks: D[128,N] = A[128,K] * B[N,K]^T in TF32 with fp32
  * accumulation (one CTA).  N % 16 == 0, 16 <= N <= 256; K % 8 == 0, K <= 128. */
 int mm_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, void* stream);
+/* Same with transposed ("MN-major") operand tiles: trans_a -> A is [K][FA] (D rows >= FA undefined), trans_b -> B is
+ * [K][N]; N <= 128.  Proves the descriptors the backward kernels use to contract over tile rows. */
+/* Raw probe: 64 KB shared-memory images (float[16384] each) and descriptor fields (bytes) supplied by the caller. */
+int mm_tc_raw_selftest(const float* imgA, const float* imgB, float* D, int32_t N, int32_t steps, int32_t a_step,
+                       int32_t a_lbo, int32_t a_sbo, int32_t b_step, int32_t b_lbo, int32_t b_sbo, int32_t trans_a,
+                       int32_t trans_b, void* stream);
+int mm_tc_gemm_t_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t FA, int32_t trans_a,
+                          int32_t trans_b, void* stream);
 
 /* Tensor-core version of mm_agentq_forward: every dense contraction on tcgen05 (kind::tf32, fp32
  * accumulators in TMEM), same arguments.  params: plain fp32 buffer of the PyTorch-layout tensors
@@ -333,6 +341,31 @@ int mm_mappo_rollout_tc(const float* params, uint32_t* env_state, float* obs, fl
                         float* rnn_states_critic, float* actions, float* action_log_probs, float* value_preds,
                         float* rewards, float* masks, int32_t T, int64_t n_envs, int32_t do_reset, uint64_t seed,
                         uint64_t step_offset, const mm_checkers_cfg* cfg_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused recurrent trunk of the PPO update (R_Actor.evaluate_actions / R_Critic.forward inside R_MAPPO.ppo_update:
+ * mappo/algorithms/r_actor_critic.py:95-146,189-208, utils/algorithm_utils/mlp.py, rnn.py:24-80), hidden size 32:
+ *   LayerNorm(D) -> [Linear ReLU LayerNorm] x2 -> GRU (state * masks[t] before every step) -> LayerNorm -> Linear(NO)
+ * over L-step data chunks, rows = chunks.  obs [L,R,D] (D <= 48), h0 [R,32], masks [L,R] or NULL, out [L,R,NO] (NO <= 8).
+ * params: mm_ppo_trunk_param_offsets layout, LayerNorm(D)'s affine folded into the first Linear by the caller.
+ * fwd, training mode (x0 != NULL): also stores x0 [L,R,48], x1, x2, hp [L,R,32] -- the operands of the weight gradients.
+ * bwd: recomputes the forward per step, needs hp from fwd and dout [L,R,NO]; writes the pre-activation gradients
+ *   gA1, gA2 [L,R,32], gGi [L,R,96] (r,z,n), gGhn [L,R,32] and, per CTA, the column-sum gradients of every small
+ *   parameter (layout = params[small:total]) into gsmall_partials [n_partials >= mm_ppo_trunk_max_ctas()][total-small].
+ *   Weight gradients (caller, four large-K GEMMs): dW1' = gA1^T x0, dW2 = gA2^T x1, dWih = gGi^T x2,
+ *   dWhh = [gGi[:, :64] | gGhn]^T hp;  dbhh = [dbih[:64] | partial bhh[64:]].
+ * ---------------------------------------------------------------------------------------------- */
+int mm_ppo_trunk_param_count(void);
+int mm_ppo_trunk_param_offsets(int32_t* offsets18);
+int mm_ppo_trunk_max_ctas(void);
+/* Debug: CTA 0 of later launches accumulates clock64() deltas per kernel phase into dev_buf16 (int64[16]); NULL = off. */
+int mm_ppo_trunk_set_prof(long long* dev_buf16);
+int mm_ppo_trunk_fwd(const float* params, const float* obs, const float* h0, const float* masks, float* out,
+                     float* h_final, float* x0, float* x1, float* x2, float* hp, int32_t L, int64_t R, int32_t D,
+                     int32_t NO, void* stream);
+int mm_ppo_trunk_bwd(const float* params, const float* obs, const float* masks, const float* hp, const float* dout,
+                     float* gA1, float* gA2, float* gGi, float* gGhn, float* gsmall_partials, int32_t n_partials,
+                     int32_t L, int64_t R, int32_t D, int32_t NO, void* stream);
 
 #ifdef __cplusplus
 }

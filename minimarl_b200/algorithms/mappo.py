@@ -21,6 +21,7 @@ import torch.nn as nn
 from ..nn.agent_q import MLPBase, _init_linear, _tc_fits, agentq_forward, pack_agentq, pack_agentq_tc
 from ..nn.gru import GRU
 from ..nn.layernorm import LayerNorm
+from ..nn.ppo_trunk import ppo_trunk, trunk_fits
 from ..parallel import allreduce_mean_grads, allreduce_stats
 
 
@@ -186,6 +187,31 @@ class _FusedTrunk(nn.Module):
                          args.use_feature_normalization and args.use_ReLU and args.hidden_size in (32, 64) and
                          self._in <= 96 and (args.use_recurrent_policy or args.use_naive_recurrent_policy))
         self._precision = getattr(args, "fused_precision", "tf32")
+        self._fused_update = bool(getattr(args, "fused_update", True))
+
+    def _chunk_fusable(self, obs, rnn_states):
+        """The differentiated chunk pass runs as the fused trunk op: default network shape, tf32, CUDA, TF32 matmuls on."""
+        return (self._fusable and self._precision == "tf32" and trunk_fits(self._in, self.hidden_size, self._n_out)
+                and getattr(self, "_fused_update", True) and torch.backends.cuda.matmul.allow_tf32
+                and obs.size(0) > rnn_states.size(0) and obs.size(0) % rnn_states.size(0) == 0)
+
+    def _trunk_params(self):
+        sd = dict(self.named_parameters())
+        return dict(ln0_w=sd["base.feature_norm.weight"], ln0_b=sd["base.feature_norm.bias"],
+                    w1=sd["base.mlp.fc1.0.weight"], b1=sd["base.mlp.fc1.0.bias"],
+                    ln1_w=sd["base.mlp.fc1.2.weight"], ln1_b=sd["base.mlp.fc1.2.bias"],
+                    w2=sd["base.mlp.fc2.0.0.weight"], b2=sd["base.mlp.fc2.0.0.bias"],
+                    ln2_w=sd["base.mlp.fc2.0.2.weight"], ln2_b=sd["base.mlp.fc2.0.2.bias"],
+                    wih=sd["rnn.rnn.weight_ih_l0"], whh=sd["rnn.rnn.weight_hh_l0"], bih=sd["rnn.rnn.bias_ih_l0"],
+                    bhh=sd["rnn.rnn.bias_hh_l0"], ln3_w=sd["rnn.norm.weight"], ln3_b=sd["rnn.norm.bias"],
+                    wo=sd[self._head_key + ".weight"], bo=sd[self._head_key + ".bias"])
+
+    def _fused_chunks(self, obs, rnn_states, masks):
+        """obs [L*N, D] (step-major), rnn_states [N, 1, H], masks [L*N, 1] -> head output [L*N, n_out]."""
+        N = rnn_states.size(0)
+        Lc = obs.size(0) // N
+        out = ppo_trunk(obs.view(Lc, N, -1), rnn_states[:, 0, :], masks.view(Lc, N), self._trunk_params())
+        return out.view(Lc * N, -1)
 
     def _agentq_state(self):
         sd = self.state_dict()
@@ -249,6 +275,14 @@ class R_Actor(_FusedTrunk):
         masks = check(masks).to(**self.tpdv)
         if active_masks is not None:
             active_masks = check(active_masks).to(**self.tpdv)
+        if available_actions is None and self._chunk_fusable(obs, rnn_states):
+            dist = torch.distributions.Categorical(logits=self._fused_chunks(obs, rnn_states, masks))
+            action_log_probs = dist.log_prob(action.squeeze(-1)).view(action.size(0), -1).sum(-1).unsqueeze(-1)
+            if active_masks is not None and self._use_policy_active_masks:
+                dist_entropy = (dist.entropy() * active_masks.squeeze(-1)).sum() / active_masks.sum()
+            else:
+                dist_entropy = dist.entropy().mean()
+            return action_log_probs, dist_entropy
         actor_features = self.base(obs)
         if self._use_rnn:
             actor_features, rnn_states = self.rnn(actor_features, rnn_states, masks)
@@ -276,6 +310,8 @@ class R_Critic(_FusedTrunk):
         masks = check(masks).to(**self.tpdv)
         if self._fusable and not torch.is_grad_enabled() and cent_obs.size(0) == rnn_states.size(0):
             return self._fused_step(cent_obs, rnn_states, masks)
+        if torch.is_grad_enabled() and self._chunk_fusable(cent_obs, rnn_states):
+            return self._fused_chunks(cent_obs, rnn_states, masks), None
         critic_features = self.base(cent_obs)
         if self._use_rnn:
             critic_features, rnn_states = self.rnn(critic_features, rnn_states, masks)

@@ -1,0 +1,670 @@
+// Fused recurrent trunk for the PPO update: forward AND backward of
+//     LayerNorm(D) -> [Linear ReLU LayerNorm] x2 -> GRU(32) (mask-reset) -> LayerNorm -> Linear head
+// over data chunks, every contraction of the data path on tcgen05 (kind::tf32, fp32 accumulators in TMEM).
+//
+// This is what R_Actor.evaluate_actions / R_Critic.forward run inside R_MAPPO.ppo_update
+// (mappo/algorithms/r_actor_critic.py:95-146,189-208; mlp.py; rnn.py:24-80 -- the reference runs the GRU over the
+// maximal mask-free runs of steps, which is the same function as multiplying the carried state by masks[t] at
+// every step, because every step at which some row has mask 0 starts a new run).  One row = one data chunk
+// (shared_buffer.py:318-427 recurrent_generator), one tile = 128 rows, 512 threads: thread (row, part) owns 8 of the
+// 32 hidden columns of its row, the four parts of a row meet through shared memory for the LayerNorm statistics.
+//
+// Forward (training mode) also stores, per (step, row), the operands the weight gradients need: the normalised
+// observation x0 [48], the two MLP activations x1, x2 [32] and the masked input state hp [32].
+// Backward walks the steps in reverse; for each step it RE-COMPUTES the forward from obs[t] and hp[t] (three MMA
+// phases; cheaper than storing and re-reading every intermediate), then propagates
+//     d head -> LayerNorm -> GRU cell -> (dx2 = dGi Wih, dhp = dGh Whh on tcgen05) -> LayerNorm/ReLU -> (dx1 = dA2 W2)
+//     -> LayerNorm/ReLU
+// and emits the pre-activation gradients dA1, dA2 [32], dGi [96], dGh_n [32] per (step, row).  The weight gradients
+// are then four large-K GEMMs of those against x0 / x1 / x2 / hp (host side, TF32 cuBLAS); everything that is a
+// column sum -- bias and LayerNorm gains/offsets, the head weight -- is reduced here (warp transpose-reduction,
+// shared-memory accumulators, one partial vector per CTA).
+//
+// LayerNorm(D)'s affine is folded into the first Linear on the host (W1' = W1 diag(g0), b1' = b1 + W1 b0); the host
+// unfolds the gradients (dW1 = dW1' diag(g0), dg0 = sum_n dW1'[n,:] * W1[n,:], db0 = W1^T db1').
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kRows = 128;
+constexpr int kThreads = 512;
+constexpr int H = 32;
+constexpr int K1 = 48;
+constexpr int CPT = 8;
+constexpr int NOMAX = 8;
+constexpr float kEps = 1e-5f;
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float sigmoid_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_(float x) {
+    const float e = __expf(-2.0f * fabsf(x));
+    return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+}
+
+// Parameter buffer (floats).  Matrices: w1 [H][K1] (LayerNorm(D) folded, zero padded), w2 [H][H], wih [3H][H],
+// whh [3H][H].  Small: b1 (folded), ln1_w, ln1_b, b2, ln2_w, ln2_b [H], bih, bhh [3H], ln3_w, ln3_b [H], wo [8][H], bo [8].
+struct Layout {
+    int w1, w2, wih, whh, small, b1, ln1_w, ln1_b, b2, ln2_w, ln2_b, bih, bhh, ln3_w, ln3_b, wo, bo, total;
+};
+__host__ __device__ inline Layout make_layout() {
+    Layout L;
+    int o = 0;
+    auto take = [&](int n) { int at = o; o += n; return at; };
+    L.w1 = take(H * K1); L.w2 = take(H * H); L.wih = take(3 * H * H); L.whh = take(3 * H * H);
+    L.small = o;
+    L.b1 = take(H); L.ln1_w = take(H); L.ln1_b = take(H);
+    L.b2 = take(H); L.ln2_w = take(H); L.ln2_b = take(H);
+    L.bih = take(3 * H); L.bhh = take(3 * H);
+    L.ln3_w = take(H); L.ln3_b = take(H);
+    L.wo = take(NOMAX * H); L.bo = take(NOMAX);
+    L.total = o;
+    return L;
+}
+
+struct Args {
+    const float* params;
+    const float* obs;      // [L][R][D]
+    const float* h0;       // [R][H]                      (forward)
+    const float* masks;    // [L][R] or null
+    float* out;            // [L][R][NO]                  (forward)
+    float* h_final;        // [R][H] or null              (forward)
+    float* x0;             // [L][R][K1]   saves (forward, may be null = inference); backward does not read them
+    float* x1;             // [L][R][H]
+    float* x2;             // [L][R][H]
+    float* hp;             // [L][R][H]    forward writes, backward reads
+    const float* dout;     // [L][R][NO]                  (backward)
+    float* gA1;            // [L][R][H]
+    float* gA2;            // [L][R][H]
+    float* gGi;            // [L][R][3H]
+    float* gGhn;           // [L][R][H]
+    float* gsmall;         // [grid][total - small]
+    int L, D, NO;
+    long long R, n_tiles;
+    long long* prof;       // optional: CTA 0 accumulates clock64() deltas per phase (debug / profiles)
+};
+
+// column sums of v[0..7] over the 32 lanes of the warp (= 32 rows), added to acc[0..7] in shared memory
+__device__ __forceinline__ void colsum8(const float (&v)[CPT], float* acc, int lane) {
+    float a[4], b[2], c;
+    const bool hi4 = lane & 16, hi3 = lane & 8, hi2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = hi4 ? v[4 + i] : v[i], send = hi4 ? v[i] : v[4 + i];
+        a[i] = keep + __shfl_xor_sync(MM_FULL_MASK, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = hi3 ? a[2 + i] : a[i], send = hi3 ? a[i] : a[2 + i];
+        b[i] = keep + __shfl_xor_sync(MM_FULL_MASK, send, 8);
+    }
+    {
+        const float keep = hi2 ? b[1] : b[0], send = hi2 ? b[0] : b[1];
+        c = keep + __shfl_xor_sync(MM_FULL_MASK, send, 4);
+    }
+    c += __shfl_xor_sync(MM_FULL_MASK, c, 2);
+    c += __shfl_xor_sync(MM_FULL_MASK, c, 1);
+    if ((lane & 3) == 0) atomicAdd(acc + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1), c);
+}
+
+__device__ __forceinline__ void store8_kmajor(uint8_t* tile, int r, int k0, int K, const float (&v)[CPT]) {
+    *reinterpret_cast<float4*>(tile + tc::kmajor_offset(r, k0, K)) =
+        make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+    *reinterpret_cast<float4*>(tile + tc::kmajor_offset(r, k0 + 4, K)) =
+        make_float4(to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7]));
+}
+__device__ __forceinline__ void store8_global(float* dst, const float (&v)[CPT]) {
+    mm::st_stream(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+    mm::st_stream(reinterpret_cast<float4*>(dst) + 1, make_float4(v[4], v[5], v[6], v[7]));
+}
+
+#define PROF(i)                                                      \
+    do {                                                             \
+        if (a.prof && blockIdx.x == 0 && tid == 0) {                 \
+            const long long now_ = clock64();                        \
+            a.prof[i] += now_ - prof_t;                              \
+            prof_t = now_;                                           \
+        }                                                            \
+    } while (0)
+
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_constant__ Args a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const Layout L = make_layout();
+    // ---- shared memory ---------------------------------------------------------------------------------------------
+    uint8_t* sW1 = smem;                                  // [H x K1]
+    uint8_t* sW2 = sW1 + H * K1 * 4;                      // [H x H]
+    uint8_t* sWih = sW2 + H * H * 4;                      // [3H x H]
+    uint8_t* sWhh = sWih + 3 * H * H * 4;                 // [3H x H]
+    uint8_t* sX0 = sWhh + 3 * H * H * 4;                  // [128 x K1]
+    uint8_t* sX1 = sX0 + kRows * K1 * 4;                  // [128 x H]
+    uint8_t* sX2 = sX1 + kRows * H * 4;
+    uint8_t* sHp = sX2 + kRows * H * 4;
+    float2* red = reinterpret_cast<float2*>(sHp + kRows * H * 4);          // [128][4]
+    float* sHead = reinterpret_cast<float*>(red + kRows * 4);              // [NOMAX][4][128] partial head sums
+    float* sP = sHead + NOMAX * 4 * kRows - L.small;                       // small params, biased by L.small
+    uint8_t* tail = reinterpret_cast<uint8_t*>(sP + L.total);
+    tail = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tail) + 127) & ~uintptr_t(127));
+    // backward only
+    uint8_t* sW2T = tail;                                 // [H(in) x H(out)]
+    uint8_t* sWihT = sW2T + H * H * 4;                    // [H(in) x 3H(out)]
+    uint8_t* sWhhT = sWihT + 3 * H * H * 4;               // [H(in) x 3H(out)]
+    uint8_t* sdG = sWhhT + 3 * H * H * 4;                 // [128 x 4H]: dr | dz | dn | dn*r ; dA2 re-uses its first 16 KB
+    float* sAcc = reinterpret_cast<float*>(sdG + kRows * 4 * H * 4) - L.small;   // gradient accumulators of the small params
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = (warp & 3) * 32 + lane, part = warp >> 2, j0 = part * CPT;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
+    if (tid == 0) tc::mbar_init(&bar, 1);
+    auto stage = [&](uint8_t* dst, int off, int rows, int K) {
+        for (int i = tid; i < rows * K; i += kThreads) {
+            const int r = i / K, k = i - r * K;
+            *reinterpret_cast<float*>(dst + tc::kmajor_offset(r, k, K)) = to_tf32(a.params[off + i]);
+        }
+    };
+    auto stage_t = [&](uint8_t* dst, int off, int rows, int K) {       // dst[k][r] = src[r][k]: tile [K x rows]
+        for (int i = tid; i < rows * K; i += kThreads) {
+            const int r = i / K, k = i - r * K;
+            *reinterpret_cast<float*>(dst + tc::kmajor_offset(k, r, rows)) = to_tf32(a.params[off + i]);
+        }
+    };
+    stage(sW1, L.w1, H, K1);
+    stage(sW2, L.w2, H, H);
+    stage(sWih, L.wih, 3 * H, H);
+    stage(sWhh, L.whh, 3 * H, H);
+    for (int i = L.small + tid; i < L.total; i += kThreads) sP[i] = a.params[i];
+    if (BWD) {
+        stage_t(sW2T, L.w2, H, H);
+        stage_t(sWihT, L.wih, 3 * H, H);
+        stage_t(sWhhT, L.whh, 3 * H, H);
+        for (int i = L.small + tid; i < L.total; i += kThreads) sAcc[i] = 0.f;
+    }
+    tc::fence_smem_to_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t phase = 0;
+    long long prof_t = clock64();
+
+    auto desc = [&](const uint8_t* base, int row_off, int K) {
+        return tc::make_desc(tc::smem_u32(base) + (uint32_t)(row_off >> 3) * (uint32_t)(K >> 2) * 128u, 128u,
+                             (uint32_t)(K >> 2) * 128u);
+    };
+    const uint64_t dX0 = desc(sX0, 0, K1), dW1 = desc(sW1, 0, K1), dX1 = desc(sX1, 0, H), dW2 = desc(sW2, 0, H);
+    const uint64_t dX2 = desc(sX2, 0, H), dHp = desc(sHp, 0, H);
+    const uint64_t dWih_rz = desc(sWih, 0, H), dWih_n = desc(sWih, 2 * H, H);
+    const uint64_t dWhh_rz = desc(sWhh, 0, H), dWhh_n = desc(sWhh, 2 * H, H);
+    const uint64_t dG = desc(sdG, 0, 4 * H), dA2 = desc(sdG, 0, H);
+    const uint64_t dW2T = desc(sW2T, 0, H), dWihT = desc(sWihT, 0, 3 * H), dWhhT = desc(sWhhT, 0, 3 * H);
+    const uint32_t id64 = tc::make_idesc_tf32(128, 64), id32 = tc::make_idesc_tf32(128, 32);
+    // TMEM columns: fc1 [0,32) fc2 [32,64) rz [64,128) i_n [128,160) h_n [160,192); backward: dx2 [192,224) dhp [224,256),
+    // dx1 re-uses [0,32)
+    auto publish = [&]() {
+        tc::fence_smem_to_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    };
+    auto wait_mma = [&]() {
+        if (warp == 0) tc::mbar_wait(&bar, phase);
+        phase ^= 1;
+        __syncthreads();
+        tc::fence_after_sync();
+    };
+    // LayerNorm statistics of a 32-wide row held as 4 x 8 columns
+    auto row_stats = [&](float s, float q, float& mean, float& rstd, int n) {
+        red[row * 4 + part] = make_float2(s, q);
+        __syncthreads();
+        const float4 p01 = *reinterpret_cast<const float4*>(red + row * 4);
+        const float4 p23 = *reinterpret_cast<const float4*>(red + row * 4 + 2);
+        mean = (p01.x + p01.z + p23.x + p23.z) / n;
+        const float var = fmaxf((p01.y + p01.w + p23.y + p23.w) / n - mean * mean, 0.f);
+        rstd = rsqrtf(var + kEps);
+        __syncthreads();
+    };
+    auto row_sums = [&](float s, float q, float& S, float& Q) {
+        red[row * 4 + part] = make_float2(s, q);
+        __syncthreads();
+        const float4 p01 = *reinterpret_cast<const float4*>(red + row * 4);
+        const float4 p23 = *reinterpret_cast<const float4*>(red + row * 4 + 2);
+        S = p01.x + p01.z + p23.x + p23.z;
+        Q = p01.y + p01.w + p23.y + p23.w;
+        __syncthreads();
+    };
+
+    for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const long long row0 = tile * kRows;
+        const int n_valid = (int)min((long long)kRows, a.R - row0);
+        const bool valid = row < n_valid;
+        const long long grow = valid ? row0 + row : a.R - 1;        // out-of-range rows shadow the last row, stores guarded
+
+        float h[CPT];          // forward: carried hidden state; backward: gradient carried to the previous step
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) h[j] = 0.f;
+        if (!BWD) {
+            const float4 q0 = *reinterpret_cast<const float4*>(a.h0 + grow * H + j0);
+            const float4 q1 = *reinterpret_cast<const float4*>(a.h0 + grow * H + j0 + 4);
+            h[0] = q0.x; h[1] = q0.y; h[2] = q0.z; h[3] = q0.w; h[4] = q1.x; h[5] = q1.y; h[6] = q1.z; h[7] = q1.w;
+        }
+
+        for (int step = 0; step < a.L; ++step) {
+            const int t = BWD ? a.L - 1 - step : step;
+            const long long tr = (long long)t * a.R + grow;
+            const float mask = a.masks ? a.masks[tr] : 1.0f;
+            // ---- F1. plain LayerNorm of the observation row -> X0 tile; masked input state -> Hp tile ----------------
+            float x0[12];
+            {
+                const float* o = a.obs + tr * a.D;
+                float s = 0.f, q = 0.f;
+#pragma unroll
+                for (int gi = 0; gi < 3; ++gi)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = 4 * (part + 4 * gi) + u;
+                        const float x = k < a.D ? o[k] : 0.f;
+                        x0[4 * gi + u] = x;
+                        s += x; q = fmaf(x, x, q);
+                    }
+                float mean, rstd;
+                row_stats(s, q, mean, rstd, a.D);
+#pragma unroll
+                for (int gi = 0; gi < 3; ++gi) {
+                    const int g = part + 4 * gi;
+                    float4 v;
+                    v.x = 4 * g + 0 < a.D ? (x0[4 * gi + 0] - mean) * rstd : 0.f;
+                    v.y = 4 * g + 1 < a.D ? (x0[4 * gi + 1] - mean) * rstd : 0.f;
+                    v.z = 4 * g + 2 < a.D ? (x0[4 * gi + 2] - mean) * rstd : 0.f;
+                    v.w = 4 * g + 3 < a.D ? (x0[4 * gi + 3] - mean) * rstd : 0.f;
+                    *reinterpret_cast<float4*>(sX0 + tc::kmajor_offset(row, 4 * g, K1)) =
+                        make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+                    if (!BWD && a.x0 && valid) mm::st_stream(reinterpret_cast<float4*>(a.x0 + tr * K1 + 4 * g), v);
+                }
+            }
+            float hp[CPT];
+            if (BWD) {
+                const float4 q0 = *reinterpret_cast<const float4*>(a.hp + tr * H + j0);
+                const float4 q1 = *reinterpret_cast<const float4*>(a.hp + tr * H + j0 + 4);
+                hp[0] = q0.x; hp[1] = q0.y; hp[2] = q0.z; hp[3] = q0.w; hp[4] = q1.x; hp[5] = q1.y; hp[6] = q1.z; hp[7] = q1.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) hp[j] = h[j] * mask;
+                if (a.hp && valid) store8_global(a.hp + tr * H + j0, hp);
+            }
+            store8_kmajor(sHp, row, j0, H, hp);
+            PROF(0);
+            publish();
+            PROF(1);
+            if (tid == 0) {
+#pragma unroll
+                for (int kk = 0; kk < K1 / 8; ++kk) tc::mma_tf32(tmem, dX0 + 16 * kk, dW1 + 16 * kk, id32, kk > 0);
+                tc::mma_commit(&bar);
+            }
+            wait_mma();
+            PROF(2);
+            // ---- F2. fc1 epilogue ------------------------------------------------------------------------------------
+            float xh1[CPT], rstd1;
+            uint32_t relu1 = 0;
+            {
+                float v[CPT];
+                tc::tmem_ld8(lane_addr + j0, v);
+                float s = 0.f, q = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    v[j] += sP[L.b1 + j0 + j];
+                    if (v[j] > 0.f) relu1 |= 1u << j; else v[j] = 0.f;
+                    s += v[j]; q = fmaf(v[j], v[j], q);
+                }
+                float mean;
+                row_stats(s, q, mean, rstd1, H);
+                float y[CPT];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    xh1[j] = (v[j] - mean) * rstd1;
+                    y[j] = fmaf(xh1[j], sP[L.ln1_w + j0 + j], sP[L.ln1_b + j0 + j]);
+                }
+                store8_kmajor(sX1, row, j0, H, y);
+                if (!BWD && a.x1 && valid) store8_global(a.x1 + tr * H + j0, y);
+            }
+            publish();
+            if (tid == 0) {
+#pragma unroll
+                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 32, dX1 + 16 * kk, dW2 + 16 * kk, id32, kk > 0);
+                tc::mma_commit(&bar);
+            }
+            PROF(3);
+            wait_mma();
+            PROF(4);
+            // ---- F3. fc2 epilogue ------------------------------------------------------------------------------------
+            float xh2[CPT], rstd2;
+            uint32_t relu2 = 0;
+            {
+                float v[CPT];
+                tc::tmem_ld8(lane_addr + 32 + j0, v);
+                float s = 0.f, q = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    v[j] += sP[L.b2 + j0 + j];
+                    if (v[j] > 0.f) relu2 |= 1u << j; else v[j] = 0.f;
+                    s += v[j]; q = fmaf(v[j], v[j], q);
+                }
+                float mean;
+                row_stats(s, q, mean, rstd2, H);
+                float y[CPT];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    xh2[j] = (v[j] - mean) * rstd2;
+                    y[j] = fmaf(xh2[j], sP[L.ln2_w + j0 + j], sP[L.ln2_b + j0 + j]);
+                }
+                store8_kmajor(sX2, row, j0, H, y);
+                if (!BWD && a.x2 && valid) store8_global(a.x2 + tr * H + j0, y);
+            }
+            publish();
+            if (tid == 0) {
+#pragma unroll
+                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 64, dX2 + 16 * kk, dWih_rz + 16 * kk, id64, kk > 0);
+#pragma unroll
+                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 64, dHp + 16 * kk, dWhh_rz + 16 * kk, id64, true);
+#pragma unroll
+                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 128, dX2 + 16 * kk, dWih_n + 16 * kk, id32, kk > 0);
+#pragma unroll
+                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 160, dHp + 16 * kk, dWhh_n + 16 * kk, id32, kk > 0);
+                tc::mma_commit(&bar);
+            }
+            PROF(5);
+            wait_mma();
+            PROF(6);
+            // ---- F4. GRU cell, LayerNorm, head -----------------------------------------------------------------------
+            float r[CPT], z[CPT], n[CPT], hnb[CPT], xh3[CPT], rstd3, y3[CPT];
+            {
+                float gr[CPT], gz[CPT], gin[CPT], ghn[CPT];
+                tc::tmem_ld8(lane_addr + 64 + j0, gr);
+                tc::tmem_ld8(lane_addr + 96 + j0, gz);
+                tc::tmem_ld8(lane_addr + 128 + j0, gin);
+                tc::tmem_ld8(lane_addr + 160 + j0, ghn);
+                const float* bi = sP + L.bih + j0;
+                const float* bh = sP + L.bhh + j0;
+                float hn[CPT], s = 0.f, q = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    r[j] = sigmoid_(gr[j] + bi[j] + bh[j]);
+                    z[j] = sigmoid_(gz[j] + bi[H + j] + bh[H + j]);
+                    hnb[j] = ghn[j] + bh[2 * H + j];
+                    n[j] = tanh_(gin[j] + bi[2 * H + j] + r[j] * hnb[j]);
+                    hn[j] = fmaf(z[j], hp[j] - n[j], n[j]);
+                    s += hn[j]; q = fmaf(hn[j], hn[j], q);
+                }
+                float mean;
+                row_stats(s, q, mean, rstd3, H);
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    xh3[j] = (hn[j] - mean) * rstd3;
+                    y3[j] = fmaf(xh3[j], sP[L.ln3_w + j0 + j], sP[L.ln3_b + j0 + j]);
+                    if (!BWD) h[j] = hn[j];
+                }
+            }
+            if (!BWD) {
+                for (int o = 0; o < a.NO; ++o) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) acc = fmaf(y3[j], sP[L.wo + o * H + j0 + j], acc);
+                    sHead[(o * 4 + part) * kRows + row] = acc;
+                }
+                __syncthreads();
+                if (part == 0 && valid)
+                    for (int o = 0; o < a.NO; ++o)
+                        a.out[tr * a.NO + o] = sP[L.bo + o] + ((sHead[(o * 4) * kRows + row] + sHead[(o * 4 + 1) * kRows + row]) +
+                                                               (sHead[(o * 4 + 2) * kRows + row] + sHead[(o * 4 + 3) * kRows + row]));
+                PROF(7);
+                continue;           // the next step's first barrier orders the sHead reads before its writes
+            }
+            PROF(7);
+            // ================================================ backward ================================================
+            const float live = valid ? 1.f : 0.f;                     // shadow rows contribute nothing to the parameter sums
+            float dy[CPT];
+            {
+                float dO[NOMAX];
+#pragma unroll
+                for (int o = 0; o < NOMAX; ++o) dO[o] = (o < a.NO) ? a.dout[tr * a.NO + o] * live : 0.f;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) dy[j] = 0.f;
+#pragma unroll
+                for (int o = 0; o < NOMAX; ++o) {
+                    if (o < a.NO) {
+                        float p[CPT];
+#pragma unroll
+                        for (int j = 0; j < CPT; ++j) {
+                            dy[j] = fmaf(dO[o], sP[L.wo + o * H + j0 + j], dy[j]);
+                            p[j] = dO[o] * y3[j];
+                        }
+                        colsum8(p, sAcc + L.wo + o * H + j0, lane);
+                    }
+                }
+                if (part == 0) colsum8(dO, sAcc + L.bo, lane);
+            }
+            // LayerNorm(h) backward
+            float dh[CPT];
+            {
+                float g[CPT], p[CPT], s = 0.f, q = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    g[j] = dy[j] * sP[L.ln3_w + j0 + j];
+                    p[j] = dy[j] * xh3[j];
+                    s += g[j]; q = fmaf(g[j], xh3[j], q);
+                }
+                colsum8(p, sAcc + L.ln3_w + j0, lane);
+                colsum8(dy, sAcc + L.ln3_b + j0, lane);
+                float S, Q;
+                row_sums(s, q, S, Q);
+#pragma unroll
+                for (int j = 0; j < CPT; ++j)
+                    dh[j] = rstd3 * (g[j] - S * (1.0f / H) - xh3[j] * Q * (1.0f / H)) + h[j];
+            }
+            // GRU cell backward: h = n + z (hp - n)
+            {
+                float dr[CPT], dz[CPT], dn[CPT], dnr[CPT];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const float dn_ = dh[j] * (1.f - z[j]);
+                    dn[j] = dn_ * (1.f - n[j] * n[j]);
+                    dz[j] = dh[j] * (hp[j] - n[j]) * z[j] * (1.f - z[j]);
+                    dr[j] = dn[j] * hnb[j] * r[j] * (1.f - r[j]);
+                    dnr[j] = dn[j] * r[j];
+                    h[j] = dh[j] * z[j];                              // direct path to hp; the matrix path is added below
+                }
+                store8_kmajor(sdG, row, j0, 4 * H, dr);
+                store8_kmajor(sdG, row, H + j0, 4 * H, dz);
+                store8_kmajor(sdG, row, 2 * H + j0, 4 * H, dn);
+                store8_kmajor(sdG, row, 3 * H + j0, 4 * H, dnr);
+                if (valid) {
+                    store8_global(a.gGi + tr * 3 * H + j0, dr);
+                    store8_global(a.gGi + tr * 3 * H + H + j0, dz);
+                    store8_global(a.gGi + tr * 3 * H + 2 * H + j0, dn);
+                    store8_global(a.gGhn + tr * H + j0, dnr);
+                }
+                colsum8(dr, sAcc + L.bih + j0, lane);
+                colsum8(dz, sAcc + L.bih + H + j0, lane);
+                colsum8(dn, sAcc + L.bih + 2 * H + j0, lane);
+                colsum8(dnr, sAcc + L.bhh + 2 * H + j0, lane);
+            }
+            publish();
+            if (tid == 0) {
+                // dx2 = [dr dz dn] Wih  (K = 96);  dhp = [dr dz dn*r] Whh  (K = 96, the last 32 from tile columns 96..127)
+#pragma unroll
+                for (int kk = 0; kk < 12; ++kk) tc::mma_tf32(tmem + 192, dG + 16 * kk, dWihT + 16 * kk, id32, kk > 0);
+#pragma unroll
+                for (int kk = 0; kk < 12; ++kk)
+                    tc::mma_tf32(tmem + 224, dG + 16 * (kk < 8 ? kk : kk + 4), dWhhT + 16 * kk, id32, kk > 0);
+                tc::mma_commit(&bar);
+            }
+            PROF(8);
+            wait_mma();
+            PROF(9);
+            // ---- dx2 -> LayerNorm / ReLU backward -> dA2 ---------------------------------------------------------------
+            {
+                float dhp[CPT], dx[CPT];
+                tc::tmem_ld8(lane_addr + 224 + j0, dhp);
+                tc::tmem_ld8(lane_addr + 192 + j0, dx);
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) h[j] = (h[j] + dhp[j]) * mask;
+                float g[CPT], p[CPT], s = 0.f, q = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    g[j] = dx[j] * sP[L.ln2_w + j0 + j];
+                    p[j] = dx[j] * xh2[j];
+                    s += g[j]; q = fmaf(g[j], xh2[j], q);
+                }
+                colsum8(p, sAcc + L.ln2_w + j0, lane);
+                colsum8(dx, sAcc + L.ln2_b + j0, lane);
+                float S, Q;
+                row_sums(s, q, S, Q);
+                float da[CPT];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const float v = rstd2 * (g[j] - S * (1.0f / H) - xh2[j] * Q * (1.0f / H));
+                    da[j] = (relu2 >> j & 1u) ? v : 0.f;
+                }
+                store8_kmajor(sdG, row, j0, H, da);                  // dA2 tile over the (consumed) head of the dG tile
+                if (valid) store8_global(a.gA2 + tr * H + j0, da);
+                colsum8(da, sAcc + L.b2 + j0, lane);
+            }
+            publish();
+            if (tid == 0) {
+#pragma unroll
+                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem, dA2 + 16 * kk, dW2T + 16 * kk, id32, kk > 0);
+                tc::mma_commit(&bar);
+            }
+            PROF(10);
+            wait_mma();
+            PROF(11);
+            // ---- dx1 -> LayerNorm / ReLU backward -> dA1 ---------------------------------------------------------------
+            {
+                float dx[CPT];
+                tc::tmem_ld8(lane_addr + j0, dx);
+                float g[CPT], p[CPT], s = 0.f, q = 0.f;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    g[j] = dx[j] * sP[L.ln1_w + j0 + j];
+                    p[j] = dx[j] * xh1[j];
+                    s += g[j]; q = fmaf(g[j], xh1[j], q);
+                }
+                colsum8(p, sAcc + L.ln1_w + j0, lane);
+                colsum8(dx, sAcc + L.ln1_b + j0, lane);
+                float S, Q;
+                row_sums(s, q, S, Q);
+                float da[CPT];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const float v = rstd1 * (g[j] - S * (1.0f / H) - xh1[j] * Q * (1.0f / H));
+                    da[j] = (relu1 >> j & 1u) ? v : 0.f;
+                }
+                if (valid) store8_global(a.gA1 + tr * H + j0, da);
+                colsum8(da, sAcc + L.b1 + j0, lane);
+            }
+            PROF(12);
+        }
+        if (!BWD && a.h_final && valid) store8_global(a.h_final + grow * H + j0, h);
+        __syncthreads();
+    }
+    if (BWD) {
+        __syncthreads();
+        float* dst = a.gsmall + (size_t)blockIdx.x * (L.total - L.small);
+        for (int i = L.small + tid; i < L.total; i += kThreads) dst[i - L.small] = sAcc[i];
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+size_t trunk_smem(bool bwd) {
+    const Layout L = make_layout();
+    size_t s = (size_t)4 * (H * K1 + H * H + 6 * H * H + kRows * K1 + 3 * kRows * H + kRows * 8 + NOMAX * 4 * kRows +
+                            (L.total - L.small)) + 256;
+    if (bwd) s += (size_t)4 * (H * H + 6 * H * H + kRows * 4 * H + (L.total - L.small));
+    return s;
+}
+
+int check_common(const float* params, const float* obs, int32_t L, int64_t R, int32_t D, int32_t NO) {
+    if (!params || !obs || L <= 0 || R <= 0) return MM_ERR_BAD_ARG;
+    if (D < 1 || D > K1 || NO < 1 || NO > NOMAX) return MM_ERR_UNSUPPORTED;
+    return MM_OK;
+}
+
+long long* g_prof = nullptr;
+
+int n_ctas(long long tiles) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)(tiles < sms ? tiles : sms);
+}
+
+}  // namespace
+
+extern "C" int mm_ppo_trunk_param_count(void) { return make_layout().total; }
+
+// offsets[18]: w1, w2, wih, whh, small, b1, ln1_w, ln1_b, b2, ln2_w, ln2_b, bih, bhh, ln3_w, ln3_b, wo, bo, total
+extern "C" int mm_ppo_trunk_param_offsets(int32_t* o) {
+    if (!o) return MM_ERR_BAD_ARG;
+    const Layout L = make_layout();
+    const int v[18] = {L.w1, L.w2, L.wih, L.whh, L.small, L.b1, L.ln1_w, L.ln1_b, L.b2, L.ln2_w, L.ln2_b, L.bih, L.bhh,
+                       L.ln3_w, L.ln3_b, L.wo, L.bo, L.total};
+    for (int i = 0; i < 18; ++i) o[i] = v[i];
+    return MM_OK;
+}
+
+// Debug: device buffer of 16 int64 into which CTA 0 of later launches accumulates per-phase clock64() deltas (NULL = off).
+extern "C" int mm_ppo_trunk_set_prof(long long* dev_buf16) { g_prof = dev_buf16; return MM_OK; }
+
+extern "C" int mm_ppo_trunk_max_ctas(void) { return n_ctas(1 << 30); }
+
+extern "C" int mm_ppo_trunk_fwd(const float* params, const float* obs, const float* h0, const float* masks, float* out,
+                                float* h_final, float* x0, float* x1, float* x2, float* hp, int32_t L, int64_t R, int32_t D,
+                                int32_t NO, void* stream) {
+    int rc = check_common(params, obs, L, R, D, NO);
+    if (rc != MM_OK) return rc;
+    if (!h0 || !out || !mm::aligned(h0, 16)) return MM_ERR_BAD_ARG;
+    if ((x0 || x1 || x2) && !(x0 && x1 && x2 && hp)) return MM_ERR_BAD_ARG;
+    for (const void* p : {(const void*)x0, (const void*)x1, (const void*)x2, (const void*)hp, (const void*)h_final})
+        if (p && !mm::aligned(p, 16)) return MM_ERR_BAD_ARG;
+    Args a{};
+    a.params = params; a.obs = obs; a.h0 = h0; a.masks = masks; a.out = out; a.h_final = h_final;
+    a.prof = g_prof;
+    a.x0 = x0; a.x1 = x1; a.x2 = x2; a.hp = hp; a.L = L; a.D = D; a.NO = NO; a.R = R; a.n_tiles = (R + kRows - 1) / kRows;
+    const size_t smem = trunk_smem(false);
+    cudaError_t e = cudaFuncSetAttribute(ppo_trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
+    ppo_trunk_kernel<false><<<n_ctas(a.n_tiles), kThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    return mm::check_launch();
+}
+
+extern "C" int mm_ppo_trunk_bwd(const float* params, const float* obs, const float* masks, const float* hp, const float* dout,
+                                float* gA1, float* gA2, float* gGi, float* gGhn, float* gsmall_partials, int32_t n_partials,
+                                int32_t L, int64_t R, int32_t D, int32_t NO, void* stream) {
+    int rc = check_common(params, obs, L, R, D, NO);
+    if (rc != MM_OK) return rc;
+    if (!hp || !dout || !gA1 || !gA2 || !gGi || !gGhn || !gsmall_partials) return MM_ERR_BAD_ARG;
+    for (const void* p : {(const void*)hp, (const void*)gA1, (const void*)gA2, (const void*)gGi, (const void*)gGhn})
+        if (!mm::aligned(p, 16)) return MM_ERR_BAD_ARG;
+    Args a{};
+    a.params = params; a.obs = obs; a.masks = masks; a.hp = const_cast<float*>(hp); a.dout = dout;
+    a.prof = g_prof;
+    a.gA1 = gA1; a.gA2 = gA2; a.gGi = gGi; a.gGhn = gGhn; a.gsmall = gsmall_partials;
+    a.L = L; a.D = D; a.NO = NO; a.R = R; a.n_tiles = (R + kRows - 1) / kRows;
+    const int ctas = n_ctas(a.n_tiles);
+    if (n_partials < ctas) return MM_ERR_BAD_ARG;
+    const size_t smem = trunk_smem(true);
+    if (smem > 227 * 1024) return MM_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(ppo_trunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
+    ppo_trunk_kernel<true><<<ctas, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    return mm::check_launch();
+}
