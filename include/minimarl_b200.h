@@ -217,14 +217,10 @@ int mm_qmix_td(const float* q_tot, const float* next_q_tot, const float* rewards
 /* Self-test of the tcgen05 / TMEM building blocks: D[128,N] = A[128,K] * B[N,K]^T in TF32 with fp32
  * accumulation (one CTA).  N % 16 == 0, 16 <= N <= 256; K % 8 == 0, K <= 128. */
 int mm_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, void* stream);
-/* Same with transposed ("MN-major") operand tiles: trans_a -> A is [K][FA] (D rows >= FA undefined), trans_b -> B is
- * [K][N]; N <= 128.  Proves the descriptors the backward kernels use to contract over tile rows. */
 /* Raw probe: 64 KB shared-memory images (float[16384] each) and descriptor fields (bytes) supplied by the caller. */
 int mm_tc_raw_selftest(const float* imgA, const float* imgB, float* D, int32_t N, int32_t steps, int32_t a_step,
                        int32_t a_lbo, int32_t a_sbo, int32_t b_step, int32_t b_lbo, int32_t b_sbo, int32_t trans_a,
                        int32_t trans_b, void* stream);
-int mm_tc_gemm_t_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t FA, int32_t trans_a,
-                          int32_t trans_b, void* stream);
 
 /* Tensor-core version of mm_agentq_forward: every dense contraction on tcgen05 (kind::tf32, fp32
  * accumulators in TMEM), same arguments.  params: plain fp32 buffer of the PyTorch-layout tensors
@@ -348,24 +344,49 @@ int mm_mappo_rollout_tc(const float* params, uint32_t* env_state, float* obs, fl
  *   LayerNorm(D) -> [Linear ReLU LayerNorm] x2 -> GRU (state * masks[t] before every step) -> LayerNorm -> Linear(NO)
  * over L-step data chunks, rows = chunks.  obs [L,R,D] (D <= 48), h0 [R,32], masks [L,R] or NULL, out [L,R,NO] (NO <= 8).
  * params: mm_ppo_trunk_param_offsets layout, LayerNorm(D)'s affine folded into the first Linear by the caller.
- * fwd, training mode (x0 != NULL): also stores x0 [L,R,48], x1, x2, hp [L,R,32] -- the operands of the weight gradients.
- * bwd: recomputes the forward per step, needs hp from fwd and dout [L,R,NO]; writes the pre-activation gradients
- *   gA1, gA2 [L,R,32], gGi [L,R,96] (r,z,n), gGhn [L,R,32] and, per CTA, the column-sum gradients of every small
- *   parameter (layout = params[small:total]) into gsmall_partials [n_partials >= mm_ppo_trunk_max_ctas()][total-small].
- *   Weight gradients (caller, four large-K GEMMs): dW1' = gA1^T x0, dW2 = gA2^T x1, dWih = gGi^T x2,
- *   dWhh = [gGi[:, :64] | gGhn]^T hp;  dbhh = [dbih[:64] | partial bhh[64:]].
+ * mm_ppo_trunk_dims -> {XS, GS, n_acc, off_S, off_dbo, off_dgamma2, off_dgamma1, NOMAX}.
+ * fwd, training mode (X != NULL): stores the operands of the weight gradients into X [L*R, XS]:
+ *   x0 (normalised obs) [0,48) | x1 [48,80) | x2 [80,112) | hp (masked input state) [112,144); the caller owns columns
+ *   [144,XS) and sets X[:,144] = 1 so that the bias gradients fall out of the same GEMM.
+ * bwd: recomputes the forward per step (reads hp from X), needs dout [L,R,NO]; writes the pre-activation gradients
+ *   G [L*R, GS] = dA1 [0,32) | dA2 [32,64) | dGi (r,z,n) [64,160) | dGh_n [160,192) and per CTA the column sums
+ *   S[o][j] = sum dout[.,o] xhat3[.,j], dbo, dgamma2, dgamma1 into acc_partials [n_partials >= mm_ppo_trunk_max_ctas()][n_acc].
+ *   All weight and bias gradients are blocks of the ONE large-K GEMM G^T X (caller, TF32 cuBLAS); the LayerNorm
+ *   offsets' gradients follow from the bias gradients (dbeta2 = dbih Wih, dbeta1 = db2 W2, dbeta3 = dbo Wo).
  * ---------------------------------------------------------------------------------------------- */
 int mm_ppo_trunk_param_count(void);
 int mm_ppo_trunk_param_offsets(int32_t* offsets18);
+int mm_ppo_trunk_dims(int32_t* dims8);
 int mm_ppo_trunk_max_ctas(void);
 /* Debug: CTA 0 of later launches accumulates clock64() deltas per kernel phase into dev_buf16 (int64[16]); NULL = off. */
 int mm_ppo_trunk_set_prof(long long* dev_buf16);
 int mm_ppo_trunk_fwd(const float* params, const float* obs, const float* h0, const float* masks, float* out,
-                     float* h_final, float* x0, float* x1, float* x2, float* hp, int32_t L, int64_t R, int32_t D,
-                     int32_t NO, void* stream);
-int mm_ppo_trunk_bwd(const float* params, const float* obs, const float* masks, const float* hp, const float* dout,
-                     float* gA1, float* gA2, float* gGi, float* gGhn, float* gsmall_partials, int32_t n_partials,
-                     int32_t L, int64_t R, int32_t D, int32_t NO, void* stream);
+                     float* h_final, float* X, int32_t L, int64_t R, int32_t D, int32_t NO, void* stream);
+int mm_ppo_trunk_bwd(const float* params, const float* obs, const float* masks, const float* X, const float* dout,
+                     float* G, float* acc_partials, int32_t n_partials, int32_t L, int64_t R, int32_t D, int32_t NO,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PPO losses of R_MAPPO.ppo_update / cal_value_loss (mappo/algorithms/ramppo_network.py:70-171), one pass each.
+ * Rows R = minibatch entries; every per-row input is a float32 vector of length R (logits [R, NA], NA <= 8);
+ * active == NULL means weight 1.
+ *   actor fwd:  sums4 (double, caller zeroes) += {sum min(imp adv, clamp(imp, 1-clip, 1+clip) adv) w, sum entropy w,
+ *               sum imp, sum w};  logp_out (optional) = log-prob of the taken action.
+ *   actor bwd:  dlogits = g2[0] * d(sum min w)/dlogits + g2[1] * d(sum entropy w)/dlogits   (g2 on the device).
+ *   value fwd:  sums2 += {sum max(loss(ret - v), loss(ret - clipped v)) w, sum w}; ret = (returns - norm2[0]) * norm2[1]
+ *               when norm2 != NULL (ValueNorm mean and 1/sqrt(var), device); Huber(delta) or e^2/2.
+ *   value bwd:  dvalues = g1[0] * d(sum loss w)/dvalues.
+ * ---------------------------------------------------------------------------------------------- */
+int mm_ppo_actor_loss_fwd(const float* logits, const float* actions, const float* old_logp, const float* adv,
+                          const float* active, float* logp_out, int64_t R, int32_t NA, float clip, double* sums4, void* stream);
+int mm_ppo_actor_loss_bwd(const float* logits, const float* actions, const float* old_logp, const float* adv,
+                          const float* active, const float* g2, float* dlogits, int64_t R, int32_t NA, float clip, void* stream);
+int mm_ppo_value_loss_fwd(const float* values, const float* value_preds, const float* returns, const float* active,
+                          const float* norm2, int64_t R, float clip, float huber_delta, int32_t use_huber, int32_t use_clipped,
+                          double* sums2, void* stream);
+int mm_ppo_value_loss_bwd(const float* values, const float* value_preds, const float* returns, const float* active,
+                          const float* norm2, const float* g1, float* dvalues, int64_t R, float clip, float huber_delta,
+                          int32_t use_huber, int32_t use_clipped, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,7 @@ from ..nn.agent_q import MLPBase, _init_linear, _tc_fits, agentq_forward, pack_a
 from ..nn.gru import GRU
 from ..nn.layernorm import LayerNorm
 from ..nn.ppo_trunk import ppo_trunk, trunk_fits
+from ..ops.ppo_loss import ppo_actor_loss, ppo_value_loss
 from ..parallel import allreduce_mean_grads, allreduce_stats
 
 
@@ -276,7 +277,10 @@ class R_Actor(_FusedTrunk):
         if active_masks is not None:
             active_masks = check(active_masks).to(**self.tpdv)
         if available_actions is None and self._chunk_fusable(obs, rnn_states):
-            dist = torch.distributions.Categorical(logits=self._fused_chunks(obs, rnn_states, masks))
+            logits = self._fused_chunks(obs, rnn_states, masks)
+            if getattr(self, "_want_logits", False):
+                return logits, None                  # R_MAPPO's fused loss kernel takes the logits themselves
+            dist = torch.distributions.Categorical(logits=logits)
             action_log_probs = dist.log_prob(action.squeeze(-1)).view(action.size(0), -1).sum(-1).unsqueeze(-1)
             if active_masks is not None and self._use_policy_active_masks:
                 dist_entropy = (dist.entropy() * active_masks.squeeze(-1)).sum() / active_masks.sum()
@@ -383,8 +387,18 @@ class R_MAPPO:
         if self._use_popart:
             raise NotImplementedError("PopArt is outside the hot path")
         self.value_normalizer = ValueNorm(input_shape=1).to(self.device) if self._use_valuenorm else None
+        self._fused_loss = bool(getattr(args, "fused_update", True)) and torch.device(device).type == "cuda"
 
     def cal_value_loss(self, values, value_preds_batch, return_batch, active_masks_batch):
+        if self._fused_loss and values.is_cuda:
+            norm = None
+            if self._use_valuenorm:
+                self.value_normalizer.update(return_batch)
+                mean, var = self.value_normalizer.running_mean_var()
+                norm = torch.cat([mean.reshape(1), torch.rsqrt(var).reshape(1)]).to(torch.float32)
+            return ppo_value_loss(values, value_preds_batch, return_batch,
+                                  active_masks_batch if self._use_value_active_masks else None, norm, self.clip_param,
+                                  self.huber_delta, self._use_huber_loss, self._use_clipped_value_loss)
         value_pred_clipped = value_preds_batch + (values - value_preds_batch).clamp(-self.clip_param, self.clip_param)
         if self._use_valuenorm:
             self.value_normalizer.update(return_batch)
@@ -406,6 +420,10 @@ class R_MAPPO:
         to = lambda x: check(x).to(**self.tpdv)
         old_action_log_probs_batch, adv_targ = to(old_action_log_probs_batch), to(adv_targ)
         value_preds_batch, return_batch, active_masks_batch = to(value_preds_batch), to(return_batch), to(active_masks_batch)
+        actor = self.policy.actor
+        if (self._fused_loss and available_actions_batch is None and hasattr(actor, "_chunk_fusable")
+                and actor._chunk_fusable(to(obs_batch), to(rnn_states_batch))):
+            return self._ppo_update_fused(sample, update_actor)
         values, action_log_probs, dist_entropy = self.policy.evaluate_actions(
             share_obs_batch, obs_batch, rnn_states_batch, rnn_states_critic_batch, actions_batch, masks_batch,
             available_actions_batch, active_masks_batch)
@@ -434,6 +452,34 @@ class R_MAPPO:
             if self._use_max_grad_norm else _grad_norm(self.policy.critic.parameters())
         self.policy.critic_optimizer.step()
         return value_loss, critic_grad_norm, policy_loss, dist_entropy, actor_grad_norm, imp_weights
+
+    def _ppo_update_fused(self, sample, update_actor=True):
+        """Same update with the fused trunk op and the loss kernels: logits -> (policy loss, entropy, ratio) in one pass."""
+        (share_obs_batch, obs_batch, rnn_states_batch, rnn_states_critic_batch, actions_batch, value_preds_batch,
+         return_batch, masks_batch, active_masks_batch, old_action_log_probs_batch, adv_targ, _) = sample
+        to = lambda x: check(x).to(**self.tpdv)
+        actor, critic = self.policy.actor, self.policy.critic
+        logits = actor._fused_chunks(to(obs_batch), to(rnn_states_batch), to(masks_batch))
+        policy_loss, dist_entropy, ratio = ppo_actor_loss(
+            logits, to(actions_batch), to(old_action_log_probs_batch), to(adv_targ),
+            to(active_masks_batch) if self._use_policy_active_masks else None, self.clip_param)
+        self.policy.actor_optimizer.zero_grad()
+        if update_actor:
+            (policy_loss - dist_entropy * self.entropy_coef).backward()
+        allreduce_mean_grads(list(actor.parameters()))
+        actor_grad_norm = nn.utils.clip_grad_norm_(actor.parameters(), self.max_grad_norm) \
+            if self._use_max_grad_norm else _grad_norm(actor.parameters())
+        self.policy.actor_optimizer.step()
+
+        values, _ = critic(to(share_obs_batch), to(rnn_states_critic_batch), to(masks_batch))
+        value_loss = self.cal_value_loss(values, to(value_preds_batch), to(return_batch), to(active_masks_batch))
+        self.policy.critic_optimizer.zero_grad()
+        (value_loss * self.value_loss_coef).backward()
+        allreduce_mean_grads(list(critic.parameters()))
+        critic_grad_norm = nn.utils.clip_grad_norm_(critic.parameters(), self.max_grad_norm) \
+            if self._use_max_grad_norm else _grad_norm(critic.parameters())
+        self.policy.critic_optimizer.step()
+        return value_loss, critic_grad_norm, policy_loss, dist_entropy, actor_grad_norm, ratio
 
     def train(self, buffer, update_actor=True, perms=None):
         """``perms`` (optional list, one permutation per PPO epoch) replaces the internal randperm (tests)."""

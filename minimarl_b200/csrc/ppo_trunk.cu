@@ -66,6 +66,11 @@ __host__ __device__ inline Layout make_layout() {
     return L;
 }
 
+constexpr int XS = 152;   // row stride of the saved-operand matrix X: x0 [0,48) x1 [48,80) x2 [80,112) hp [112,144) 1 [144] 0 [145,152)
+constexpr int GS = 192;   // row stride of the gradient matrix G: dA1 [0,32) dA2 [32,64) dGi [64,160) dGh_n [160,192)
+// per-CTA column-sum accumulators: S[o][j] = sum_r dout[r][o] * xhat3[r][j] (NOMAX x H), dbo (NOMAX), dgamma2 (H), dgamma1 (H)
+constexpr int ACC_S = 0, ACC_BO = NOMAX * H, ACC_G2 = ACC_BO + NOMAX, ACC_G1 = ACC_G2 + H, ACC_N = ACC_G1 + H;
+
 struct Args {
     const float* params;
     const float* obs;      // [L][R][D]
@@ -73,22 +78,26 @@ struct Args {
     const float* masks;    // [L][R] or null
     float* out;            // [L][R][NO]                  (forward)
     float* h_final;        // [R][H] or null              (forward)
-    float* x0;             // [L][R][K1]   saves (forward, may be null = inference); backward does not read them
-    float* x1;             // [L][R][H]
-    float* x2;             // [L][R][H]
-    float* hp;             // [L][R][H]    forward writes, backward reads
+    float* X;              // [L*R][XS]  forward writes columns [0,144) (may be null = inference); backward reads hp
     const float* dout;     // [L][R][NO]                  (backward)
-    float* gA1;            // [L][R][H]
-    float* gA2;            // [L][R][H]
-    float* gGi;            // [L][R][3H]
-    float* gGhn;           // [L][R][H]
-    float* gsmall;         // [grid][total - small]
+    float* G;              // [L*R][GS]                   (backward)
+    float* gacc;           // [grid][ACC_N]               (backward)
     int L, D, NO;
     long long R, n_tiles;
     long long* prof;       // optional: CTA 0 accumulates clock64() deltas per phase (debug / profiles)
 };
 
-// column sums of v[0..7] over the 32 lanes of the warp (= 32 rows), added to acc[0..7] in shared memory
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// column sums of v[0..7] over the 32 lanes of the warp (= 32 rows), added to acc[0..7] -- a shared-memory slot that only
+// this warp updates, so the read-modify-write needs no atomic
 __device__ __forceinline__ void colsum8(const float (&v)[CPT], float* acc, int lane) {
     float a[4], b[2], c;
     const bool hi4 = lane & 16, hi3 = lane & 8, hi2 = lane & 4;
@@ -108,7 +117,7 @@ __device__ __forceinline__ void colsum8(const float (&v)[CPT], float* acc, int l
     }
     c += __shfl_xor_sync(MM_FULL_MASK, c, 2);
     c += __shfl_xor_sync(MM_FULL_MASK, c, 1);
-    if ((lane & 3) == 0) atomicAdd(acc + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1), c);
+    if ((lane & 3) == 0) acc[((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] += c;
 }
 
 __device__ __forceinline__ void store8_kmajor(uint8_t* tile, int r, int k0, int K, const float (&v)[CPT]) {
@@ -120,6 +129,29 @@ __device__ __forceinline__ void store8_kmajor(uint8_t* tile, int r, int k0, int 
 __device__ __forceinline__ void store8_global(float* dst, const float (&v)[CPT]) {
     mm::st_stream(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
     mm::st_stream(reinterpret_cast<float4*>(dst) + 1, make_float4(v[4], v[5], v[6], v[7]));
+}
+__device__ __forceinline__ void load8_global(const float* src, float (&v)[CPT]) {
+    const float4 q0 = *reinterpret_cast<const float4*>(src), q1 = *reinterpret_cast<const float4*>(src + 4);
+    v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+}
+
+// Copies between a [128 x F] K-major tile and F consecutive columns of global rows (row stride gs floats).  A warp moves
+// 8 rows x 4 sixteen-byte chunks per instruction: conflict-free on the tile side, 64 contiguous bytes per row on the
+// global side.
+__device__ __forceinline__ void tile_to_global(const uint8_t* tile, int F, float* g, long long gs, int n_valid, int tid) {
+    const int lane = tid & 31, r_lo = lane & 7, c_lo = lane >> 3;
+    for (int b = tid >> 5; b < 16 * (F >> 4); b += kThreads / 32) {
+        const int r = (b & 15) * 8 + r_lo, c = (b >> 4) * 4 + c_lo;
+        const float4 v = *reinterpret_cast<const float4*>(tile + tc::kmajor_offset(r, 4 * c, F));
+        if (r < n_valid) mm::st_stream(reinterpret_cast<float4*>(g + r * gs + 4 * c), v);
+    }
+}
+__device__ __forceinline__ void global_to_tile_async(uint8_t* tile, int F, const float* g, long long gs, int n_valid, int tid) {
+    const int lane = tid & 31, r_lo = lane & 7, c_lo = lane >> 3;
+    for (int b = tid >> 5; b < 16 * (F >> 4); b += kThreads / 32) {
+        const int r = (b & 15) * 8 + r_lo, c = (b >> 4) * 4 + c_lo;
+        cp_async16(tile + tc::kmajor_offset(r, 4 * c, F), g + min(r, n_valid - 1) * gs + 4 * c);
+    }
 }
 
 #define PROF(i)                                                      \
@@ -146,9 +178,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
     uint8_t* sX1 = sX0 + kRows * K1 * 4;                  // [128 x H]
     uint8_t* sX2 = sX1 + kRows * H * 4;
     uint8_t* sHp = sX2 + kRows * H * 4;
-    float2* red = reinterpret_cast<float2*>(sHp + kRows * H * 4);          // [128][4]
-    float* sHead = reinterpret_cast<float*>(red + kRows * 4);              // [NOMAX][4][128] partial head sums
-    float* sP = sHead + NOMAX * 4 * kRows - L.small;                       // small params, biased by L.small
+    float2* red = reinterpret_cast<float2*>(sHp + kRows * H * 4);          // [2][128][4], alternating
+    float* sP = reinterpret_cast<float*>(red + 2 * kRows * 4) - L.small;   // small params, biased by L.small
     uint8_t* tail = reinterpret_cast<uint8_t*>(sP + L.total);
     tail = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tail) + 127) & ~uintptr_t(127));
     // backward only
@@ -156,7 +187,12 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
     uint8_t* sWihT = sW2T + H * H * 4;                    // [H(in) x 3H(out)]
     uint8_t* sWhhT = sWihT + 3 * H * H * 4;               // [H(in) x 3H(out)]
     uint8_t* sdG = sWhhT + 3 * H * H * 4;                 // [128 x 4H]: dr | dz | dn | dn*r ; dA2 re-uses its first 16 KB
-    float* sAcc = reinterpret_cast<float*>(sdG + kRows * 4 * H * 4) - L.small;   // gradient accumulators of the small params
+    float* sAcc = reinterpret_cast<float*>(sdG + kRows * 4 * H * 4);       // [4 row quarters][ACC_N]
+    float* sDout = sAcc + 4 * ACC_N;                                       // [128][NO] head gradients of the current step
+    // regions that are idle while a step starts double as the raw observation tile (filled by cp.async one step ahead)
+    // and, in the forward, as the head's partial sums
+    float* sObs = reinterpret_cast<float*>(sX1);                           // [128][D]  (<= 24 KB, forward only)
+    float* sHead = reinterpret_cast<float*>(sX0);                          // [NOMAX][4][128]  (forward only)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = (warp & 3) * 32 + lane, part = warp >> 2, j0 = part * CPT;
@@ -184,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
         stage_t(sW2T, L.w2, H, H);
         stage_t(sWihT, L.wih, 3 * H, H);
         stage_t(sWhhT, L.whh, 3 * H, H);
-        for (int i = L.small + tid; i < L.total; i += kThreads) sAcc[i] = 0.f;
+        for (int i = tid; i < 4 * ACC_N; i += kThreads) sAcc[i] = 0.f;
     }
     tc::fence_smem_to_async();
     tc::fence_before_sync();
@@ -192,8 +228,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t phase = 0;
+    uint32_t phase = 0, red_sel = 0;
     long long prof_t = clock64();
+    float* acc = sAcc + (warp & 3) * ACC_N;               // this warp's row quarter
 
     auto desc = [&](const uint8_t* base, int row_off, int K) {
         return tc::make_desc(tc::smem_u32(base) + (uint32_t)(row_off >> 3) * (uint32_t)(K >> 2) * 128u, 128u,
@@ -220,25 +257,48 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
         __syncthreads();
         tc::fence_after_sync();
     };
-    // LayerNorm statistics of a 32-wide row held as 4 x 8 columns
-    auto row_stats = [&](float s, float q, float& mean, float& rstd, int n) {
-        red[row * 4 + part] = make_float2(s, q);
-        __syncthreads();
-        const float4 p01 = *reinterpret_cast<const float4*>(red + row * 4);
-        const float4 p23 = *reinterpret_cast<const float4*>(red + row * 4 + 2);
-        mean = (p01.x + p01.z + p23.x + p23.z) / n;
-        const float var = fmaxf((p01.y + p01.w + p23.y + p23.w) / n - mean * mean, 0.f);
-        rstd = rsqrtf(var + kEps);
-        __syncthreads();
-    };
+    // sums of (s, q) over the four parts of a row; the exchange buffer alternates so that one barrier is enough
     auto row_sums = [&](float s, float q, float& S, float& Q) {
-        red[row * 4 + part] = make_float2(s, q);
-        __syncthreads();
-        const float4 p01 = *reinterpret_cast<const float4*>(red + row * 4);
-        const float4 p23 = *reinterpret_cast<const float4*>(red + row * 4 + 2);
-        S = p01.x + p01.z + p23.x + p23.z;
-        Q = p01.y + p01.w + p23.y + p23.w;
-        __syncthreads();
+        float2* r2 = red + red_sel * (kRows * 4);
+        red_sel ^= 1;
+        r2[row * 4 + part] = make_float2(s, q);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory");      // the four warps that share these 32 rows
+        const float4 p01 = *reinterpret_cast<const float4*>(r2 + row * 4);
+        const float4 p23 = *reinterpret_cast<const float4*>(r2 + row * 4 + 2);
+        S = (p01.x + p01.z) + (p23.x + p23.z);
+        Q = (p01.y + p01.w) + (p23.y + p23.w);
+    };
+    auto row_stats = [&](float s, float q, float& mean, float& rstd, int n) {
+        float S, Q;
+        row_sums(s, q, S, Q);
+        mean = S / n;
+        rstd = rsqrtf(fmaxf(Q / n - mean * mean, 0.f) + kEps);
+    };
+    // raw observation tile of (tile row0, step t) -> sObs, asynchronously; rows past the end of the batch are zero
+    auto fetch_obs = [&](long long row0, int n_valid, int t) {
+        const float* src = a.obs + ((long long)t * a.R + row0) * a.D;
+        const int n = n_valid * a.D;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            for (int i = tid; i < (n >> 2); i += kThreads) cp_async16(sObs + 4 * i, src + 4 * i);
+            for (int i = (n & ~3) + tid; i < n; i += kThreads) cp_async4(sObs + i, src + i);
+        } else {
+            for (int i = tid; i < n; i += kThreads) cp_async4(sObs + i, src + i);
+        }
+        for (int i = n + tid; i < kRows * a.D; i += kThreads) sObs[i] = 0.f;
+        cp_async_commit();
+    };
+
+    // head gradients of (tile row0, step t) -> sDout, asynchronously (contiguous n_valid * NO floats)
+    auto fetch_dout = [&](long long row0, int n_valid, int t) {
+        const float* src = a.dout + ((long long)t * a.R + row0) * a.NO;
+        const int n = n_valid * a.NO;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            for (int i = tid; i < (n >> 2); i += kThreads) cp_async16(sDout + 4 * i, src + 4 * i);
+            for (int i = (n & ~3) + tid; i < n; i += kThreads) cp_async4(sDout + i, src + i);
+        } else {
+            for (int i = tid; i < n; i += kThreads) cp_async4(sDout + i, src + i);
+        }
+        for (int i = n + tid; i < kRows * a.NO; i += kThreads) sDout[i] = 0.f;
     };
 
     for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -251,19 +311,28 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < CPT; ++j) h[j] = 0.f;
         if (!BWD) {
-            const float4 q0 = *reinterpret_cast<const float4*>(a.h0 + grow * H + j0);
-            const float4 q1 = *reinterpret_cast<const float4*>(a.h0 + grow * H + j0 + 4);
-            h[0] = q0.x; h[1] = q0.y; h[2] = q0.z; h[3] = q0.w; h[4] = q1.x; h[5] = q1.y; h[6] = q1.z; h[7] = q1.w;
+            load8_global(a.h0 + grow * H + j0, h);
+            fetch_obs(row0, n_valid, 0);
+        } else {
+            // backward: the normalised observations and the input state of a step come straight from X into the operand tiles
+            const float* xrow = a.X + ((long long)(a.L - 1) * a.R + row0) * XS;
+            global_to_tile_async(sX0, K1, xrow, XS, n_valid, tid);
+            global_to_tile_async(sHp, H, xrow + 112, XS, n_valid, tid);
+            fetch_dout(row0, n_valid, a.L - 1);
+            cp_async_commit();
         }
 
         for (int step = 0; step < a.L; ++step) {
             const int t = BWD ? a.L - 1 - step : step;
             const long long tr = (long long)t * a.R + grow;
             const float mask = a.masks ? a.masks[tr] : 1.0f;
+            float hp[CPT];
             // ---- F1. plain LayerNorm of the observation row -> X0 tile; masked input state -> Hp tile ----------------
-            float x0[12];
-            {
-                const float* o = a.obs + tr * a.D;
+            cp_async_wait_all();
+            __syncthreads();
+            if (!BWD) {
+                float x0[12];
+                const float* o = sObs + row * a.D;
                 float s = 0.f, q = 0.f;
 #pragma unroll
                 for (int gi = 0; gi < 3; ++gi)
@@ -280,26 +349,21 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 for (int gi = 0; gi < 3; ++gi) {
                     const int g = part + 4 * gi;
                     float4 v;
-                    v.x = 4 * g + 0 < a.D ? (x0[4 * gi + 0] - mean) * rstd : 0.f;
-                    v.y = 4 * g + 1 < a.D ? (x0[4 * gi + 1] - mean) * rstd : 0.f;
-                    v.z = 4 * g + 2 < a.D ? (x0[4 * gi + 2] - mean) * rstd : 0.f;
-                    v.w = 4 * g + 3 < a.D ? (x0[4 * gi + 3] - mean) * rstd : 0.f;
-                    *reinterpret_cast<float4*>(sX0 + tc::kmajor_offset(row, 4 * g, K1)) =
-                        make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-                    if (!BWD && a.x0 && valid) mm::st_stream(reinterpret_cast<float4*>(a.x0 + tr * K1 + 4 * g), v);
+                    v.x = 4 * g + 0 < a.D ? to_tf32((x0[4 * gi + 0] - mean) * rstd) : 0.f;
+                    v.y = 4 * g + 1 < a.D ? to_tf32((x0[4 * gi + 1] - mean) * rstd) : 0.f;
+                    v.z = 4 * g + 2 < a.D ? to_tf32((x0[4 * gi + 2] - mean) * rstd) : 0.f;
+                    v.w = 4 * g + 3 < a.D ? to_tf32((x0[4 * gi + 3] - mean) * rstd) : 0.f;
+                    *reinterpret_cast<float4*>(sX0 + tc::kmajor_offset(row, 4 * g, K1)) = v;
                 }
-            }
-            float hp[CPT];
-            if (BWD) {
-                const float4 q0 = *reinterpret_cast<const float4*>(a.hp + tr * H + j0);
-                const float4 q1 = *reinterpret_cast<const float4*>(a.hp + tr * H + j0 + 4);
-                hp[0] = q0.x; hp[1] = q0.y; hp[2] = q0.z; hp[3] = q0.w; hp[4] = q1.x; hp[5] = q1.y; hp[6] = q1.z; hp[7] = q1.w;
-            } else {
+                // the state enters the cell rounded to tf32 -- the same value the tensor core multiplies and the backward re-reads
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) hp[j] = h[j] * mask;
-                if (a.hp && valid) store8_global(a.hp + tr * H + j0, hp);
+                for (int j = 0; j < CPT; ++j) hp[j] = to_tf32(h[j] * mask);
+                store8_kmajor(sHp, row, j0, H, hp);
+            } else {
+                const float4 q0 = *reinterpret_cast<const float4*>(sHp + tc::kmajor_offset(row, j0, H));
+                const float4 q1 = *reinterpret_cast<const float4*>(sHp + tc::kmajor_offset(row, j0 + 4, H));
+                hp[0] = q0.x; hp[1] = q0.y; hp[2] = q0.z; hp[3] = q0.w; hp[4] = q1.x; hp[5] = q1.y; hp[6] = q1.z; hp[7] = q1.w;
             }
-            store8_kmajor(sHp, row, j0, H, hp);
             PROF(0);
             publish();
             PROF(1);
@@ -307,6 +371,11 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
 #pragma unroll
                 for (int kk = 0; kk < K1 / 8; ++kk) tc::mma_tf32(tmem, dX0 + 16 * kk, dW1 + 16 * kk, id32, kk > 0);
                 tc::mma_commit(&bar);
+            }
+            float* const xtile = a.X ? a.X + ((long long)t * a.R + row0) * XS : nullptr;      // this tile's rows of X at step t
+            if (!BWD && xtile) {
+                tile_to_global(sX0, K1, xtile, XS, n_valid, tid);
+                tile_to_global(sHp, H, xtile + 112, XS, n_valid, tid);
             }
             wait_mma();
             PROF(2);
@@ -332,7 +401,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                     y[j] = fmaf(xh1[j], sP[L.ln1_w + j0 + j], sP[L.ln1_b + j0 + j]);
                 }
                 store8_kmajor(sX1, row, j0, H, y);
-                if (!BWD && a.x1 && valid) store8_global(a.x1 + tr * H + j0, y);
             }
             publish();
             if (tid == 0) {
@@ -340,6 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 32, dX1 + 16 * kk, dW2 + 16 * kk, id32, kk > 0);
                 tc::mma_commit(&bar);
             }
+            if (!BWD && xtile) tile_to_global(sX1, H, xtile + 48, XS, n_valid, tid);
             PROF(3);
             wait_mma();
             PROF(4);
@@ -365,7 +434,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                     y[j] = fmaf(xh2[j], sP[L.ln2_w + j0 + j], sP[L.ln2_b + j0 + j]);
                 }
                 store8_kmajor(sX2, row, j0, H, y);
-                if (!BWD && a.x2 && valid) store8_global(a.x2 + tr * H + j0, y);
             }
             publish();
             if (tid == 0) {
@@ -379,11 +447,22 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 160, dHp + 16 * kk, dWhh_n + 16 * kk, id32, kk > 0);
                 tc::mma_commit(&bar);
             }
+            if (!BWD && xtile) tile_to_global(sX2, H, xtile + 80, XS, n_valid, tid);
             PROF(5);
             wait_mma();
             PROF(6);
+            if (step + 1 < a.L) {
+                if (!BWD) {
+                    fetch_obs(row0, n_valid, t + 1);     // the X1 / X2 tiles are consumed, the next observations land there
+                } else {
+                    const float* xrow = a.X + ((long long)(t - 1) * a.R + row0) * XS;   // X0 / Hp tiles are consumed as well
+                    global_to_tile_async(sX0, K1, xrow, XS, n_valid, tid);
+                    global_to_tile_async(sHp, H, xrow + 112, XS, n_valid, tid);
+                    cp_async_commit();
+                }
+            }
             // ---- F4. GRU cell, LayerNorm, head -----------------------------------------------------------------------
-            float r[CPT], z[CPT], n[CPT], hnb[CPT], xh3[CPT], rstd3, y3[CPT];
+            float r[CPT], z[CPT], n[CPT], hnb[CPT], xh3[CPT], rstd3;
             {
                 float gr[CPT], gz[CPT], gin[CPT], ghn[CPT];
                 tc::tmem_ld8(lane_addr + 64 + j0, gr);
@@ -407,16 +486,16 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) {
                     xh3[j] = (hn[j] - mean) * rstd3;
-                    y3[j] = fmaf(xh3[j], sP[L.ln3_w + j0 + j], sP[L.ln3_b + j0 + j]);
                     if (!BWD) h[j] = hn[j];
                 }
             }
             if (!BWD) {
                 for (int o = 0; o < a.NO; ++o) {
-                    float acc = 0.f;
+                    float sum = 0.f;
 #pragma unroll
-                    for (int j = 0; j < CPT; ++j) acc = fmaf(y3[j], sP[L.wo + o * H + j0 + j], acc);
-                    sHead[(o * 4 + part) * kRows + row] = acc;
+                    for (int j = 0; j < CPT; ++j)
+                        sum = fmaf(fmaf(xh3[j], sP[L.ln3_w + j0 + j], sP[L.ln3_b + j0 + j]), sP[L.wo + o * H + j0 + j], sum);
+                    sHead[(o * 4 + part) * kRows + row] = sum;
                 }
                 __syncthreads();
                 if (part == 0 && valid)
@@ -424,16 +503,15 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                         a.out[tr * a.NO + o] = sP[L.bo + o] + ((sHead[(o * 4) * kRows + row] + sHead[(o * 4 + 1) * kRows + row]) +
                                                                (sHead[(o * 4 + 2) * kRows + row] + sHead[(o * 4 + 3) * kRows + row]));
                 PROF(7);
-                continue;           // the next step's first barrier orders the sHead reads before its writes
+                continue;           // the next step's first barrier orders these sHead reads before the X0 tile is rewritten
             }
             PROF(7);
             // ================================================ backward ================================================
-            const float live = valid ? 1.f : 0.f;                     // shadow rows contribute nothing to the parameter sums
             float dy[CPT];
             {
                 float dO[NOMAX];
 #pragma unroll
-                for (int o = 0; o < NOMAX; ++o) dO[o] = (o < a.NO) ? a.dout[tr * a.NO + o] * live : 0.f;
+                for (int o = 0; o < NOMAX; ++o) dO[o] = (o < a.NO) ? sDout[row * a.NO + o] : 0.f;
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) dy[j] = 0.f;
 #pragma unroll
@@ -443,31 +521,30 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < CPT; ++j) {
                             dy[j] = fmaf(dO[o], sP[L.wo + o * H + j0 + j], dy[j]);
-                            p[j] = dO[o] * y3[j];
+                            p[j] = dO[o] * xh3[j];
                         }
-                        colsum8(p, sAcc + L.wo + o * H + j0, lane);
+                        colsum8(p, acc + ACC_S + o * H + j0, lane);
                     }
                 }
-                if (part == 0) colsum8(dO, sAcc + L.bo, lane);
+                if (part == 0) colsum8(dO, acc + ACC_BO, lane);
             }
+            PROF(13);
             // LayerNorm(h) backward
             float dh[CPT];
             {
-                float g[CPT], p[CPT], s = 0.f, q = 0.f;
+                float g[CPT], s = 0.f, q = 0.f;
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) {
                     g[j] = dy[j] * sP[L.ln3_w + j0 + j];
-                    p[j] = dy[j] * xh3[j];
                     s += g[j]; q = fmaf(g[j], xh3[j], q);
                 }
-                colsum8(p, sAcc + L.ln3_w + j0, lane);
-                colsum8(dy, sAcc + L.ln3_b + j0, lane);
                 float S, Q;
                 row_sums(s, q, S, Q);
 #pragma unroll
                 for (int j = 0; j < CPT; ++j)
                     dh[j] = rstd3 * (g[j] - S * (1.0f / H) - xh3[j] * Q * (1.0f / H)) + h[j];
             }
+            PROF(14);
             // GRU cell backward: h = n + z (hp - n)
             {
                 float dr[CPT], dz[CPT], dn[CPT], dnr[CPT];
@@ -484,17 +561,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 store8_kmajor(sdG, row, H + j0, 4 * H, dz);
                 store8_kmajor(sdG, row, 2 * H + j0, 4 * H, dn);
                 store8_kmajor(sdG, row, 3 * H + j0, 4 * H, dnr);
-                if (valid) {
-                    store8_global(a.gGi + tr * 3 * H + j0, dr);
-                    store8_global(a.gGi + tr * 3 * H + H + j0, dz);
-                    store8_global(a.gGi + tr * 3 * H + 2 * H + j0, dn);
-                    store8_global(a.gGhn + tr * H + j0, dnr);
-                }
-                colsum8(dr, sAcc + L.bih + j0, lane);
-                colsum8(dz, sAcc + L.bih + H + j0, lane);
-                colsum8(dn, sAcc + L.bih + 2 * H + j0, lane);
-                colsum8(dnr, sAcc + L.bhh + 2 * H + j0, lane);
             }
+            PROF(15);
             publish();
             if (tid == 0) {
                 // dx2 = [dr dz dn] Wih  (K = 96);  dhp = [dr dz dn*r] Whh  (K = 96, the last 32 from tile columns 96..127)
@@ -505,9 +573,15 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                     tc::mma_tf32(tmem + 224, dG + 16 * (kk < 8 ? kk : kk + 4), dWhhT + 16 * kk, id32, kk > 0);
                 tc::mma_commit(&bar);
             }
+            float* const gtile = a.G + ((long long)t * a.R + row0) * GS;
+            tile_to_global(sdG, 4 * H, gtile + 64, GS, n_valid, tid);
             PROF(8);
             wait_mma();
             PROF(9);
+            if (step + 1 < a.L) {                        // every thread is past its sDout reads: bring in the previous step's
+                fetch_dout(row0, n_valid, t - 1);
+                cp_async_commit();
+            }
             // ---- dx2 -> LayerNorm / ReLU backward -> dA2 ---------------------------------------------------------------
             {
                 float dhp[CPT], dx[CPT];
@@ -522,8 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                     p[j] = dx[j] * xh2[j];
                     s += g[j]; q = fmaf(g[j], xh2[j], q);
                 }
-                colsum8(p, sAcc + L.ln2_w + j0, lane);
-                colsum8(dx, sAcc + L.ln2_b + j0, lane);
+                colsum8(p, acc + ACC_G2 + j0, lane);
                 float S, Q;
                 row_sums(s, q, S, Q);
                 float da[CPT];
@@ -533,8 +606,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                     da[j] = (relu2 >> j & 1u) ? v : 0.f;
                 }
                 store8_kmajor(sdG, row, j0, H, da);                  // dA2 tile over the (consumed) head of the dG tile
-                if (valid) store8_global(a.gA2 + tr * H + j0, da);
-                colsum8(da, sAcc + L.b2 + j0, lane);
             }
             publish();
             if (tid == 0) {
@@ -542,6 +613,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem, dA2 + 16 * kk, dW2T + 16 * kk, id32, kk > 0);
                 tc::mma_commit(&bar);
             }
+            tile_to_global(sdG, H, gtile + 32, GS, n_valid, tid);
             PROF(10);
             wait_mma();
             PROF(11);
@@ -556,8 +628,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                     p[j] = dx[j] * xh1[j];
                     s += g[j]; q = fmaf(g[j], xh1[j], q);
                 }
-                colsum8(p, sAcc + L.ln1_w + j0, lane);
-                colsum8(dx, sAcc + L.ln1_b + j0, lane);
+                colsum8(p, acc + ACC_G1 + j0, lane);
                 float S, Q;
                 row_sums(s, q, S, Q);
                 float da[CPT];
@@ -566,18 +637,20 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                     const float v = rstd1 * (g[j] - S * (1.0f / H) - xh1[j] * Q * (1.0f / H));
                     da[j] = (relu1 >> j & 1u) ? v : 0.f;
                 }
-                if (valid) store8_global(a.gA1 + tr * H + j0, da);
-                colsum8(da, sAcc + L.b1 + j0, lane);
+                store8_kmajor(sX1, row, j0, H, da);                  // staged through the (idle) X1 tile for a coalesced store
             }
+            __syncthreads();
+            tile_to_global(sX1, H, gtile, GS, n_valid, tid);
             PROF(12);
         }
         if (!BWD && a.h_final && valid) store8_global(a.h_final + grow * H + j0, h);
-        __syncthreads();
+        __syncthreads();           // the next tile's first fetch overwrites the staging region
     }
     if (BWD) {
         __syncthreads();
-        float* dst = a.gsmall + (size_t)blockIdx.x * (L.total - L.small);
-        for (int i = L.small + tid; i < L.total; i += kThreads) dst[i - L.small] = sAcc[i];
+        float* dst = a.gacc + (size_t)blockIdx.x * ACC_N;
+        for (int i = tid; i < ACC_N; i += kThreads)
+            dst[i] = (sAcc[i] + sAcc[ACC_N + i]) + (sAcc[2 * ACC_N + i] + sAcc[3 * ACC_N + i]);
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -586,15 +659,15 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
 
 size_t trunk_smem(bool bwd) {
     const Layout L = make_layout();
-    size_t s = (size_t)4 * (H * K1 + H * H + 6 * H * H + kRows * K1 + 3 * kRows * H + kRows * 8 + NOMAX * 4 * kRows +
-                            (L.total - L.small)) + 256;
-    if (bwd) s += (size_t)4 * (H * H + 6 * H * H + kRows * 4 * H + (L.total - L.small));
+    size_t s = (size_t)4 * (H * K1 + H * H + 6 * H * H + kRows * K1 + 3 * kRows * H + 2 * kRows * 8 + (L.total - L.small)) + 256;
+    if (bwd) s += (size_t)4 * (H * H + 6 * H * H + kRows * 4 * H + 4 * ACC_N + kRows * NOMAX);
     return s;
 }
 
 int check_common(const float* params, const float* obs, int32_t L, int64_t R, int32_t D, int32_t NO) {
     if (!params || !obs || L <= 0 || R <= 0) return MM_ERR_BAD_ARG;
     if (D < 1 || D > K1 || NO < 1 || NO > NOMAX) return MM_ERR_UNSUPPORTED;
+    if (!mm::aligned(obs, 4)) return MM_ERR_BAD_ARG;
     return MM_OK;
 }
 
@@ -621,24 +694,29 @@ extern "C" int mm_ppo_trunk_param_offsets(int32_t* o) {
     return MM_OK;
 }
 
+// dims[8]: X row stride, G row stride, accumulator count, offsets of S, dbo, dgamma2, dgamma1 in the accumulator, NOMAX
+extern "C" int mm_ppo_trunk_dims(int32_t* d) {
+    if (!d) return MM_ERR_BAD_ARG;
+    const int v[8] = {XS, GS, ACC_N, ACC_S, ACC_BO, ACC_G2, ACC_G1, NOMAX};
+    for (int i = 0; i < 8; ++i) d[i] = v[i];
+    return MM_OK;
+}
+
 // Debug: device buffer of 16 int64 into which CTA 0 of later launches accumulates per-phase clock64() deltas (NULL = off).
 extern "C" int mm_ppo_trunk_set_prof(long long* dev_buf16) { g_prof = dev_buf16; return MM_OK; }
 
 extern "C" int mm_ppo_trunk_max_ctas(void) { return n_ctas(1 << 30); }
 
 extern "C" int mm_ppo_trunk_fwd(const float* params, const float* obs, const float* h0, const float* masks, float* out,
-                                float* h_final, float* x0, float* x1, float* x2, float* hp, int32_t L, int64_t R, int32_t D,
-                                int32_t NO, void* stream) {
+                                float* h_final, float* X, int32_t L, int64_t R, int32_t D, int32_t NO, void* stream) {
     int rc = check_common(params, obs, L, R, D, NO);
     if (rc != MM_OK) return rc;
     if (!h0 || !out || !mm::aligned(h0, 16)) return MM_ERR_BAD_ARG;
-    if ((x0 || x1 || x2) && !(x0 && x1 && x2 && hp)) return MM_ERR_BAD_ARG;
-    for (const void* p : {(const void*)x0, (const void*)x1, (const void*)x2, (const void*)hp, (const void*)h_final})
-        if (p && !mm::aligned(p, 16)) return MM_ERR_BAD_ARG;
+    if ((X && !mm::aligned(X, 16)) || (h_final && !mm::aligned(h_final, 16))) return MM_ERR_BAD_ARG;
     Args a{};
-    a.params = params; a.obs = obs; a.h0 = h0; a.masks = masks; a.out = out; a.h_final = h_final;
+    a.params = params; a.obs = obs; a.h0 = h0; a.masks = masks; a.out = out; a.h_final = h_final; a.X = X;
     a.prof = g_prof;
-    a.x0 = x0; a.x1 = x1; a.x2 = x2; a.hp = hp; a.L = L; a.D = D; a.NO = NO; a.R = R; a.n_tiles = (R + kRows - 1) / kRows;
+    a.L = L; a.D = D; a.NO = NO; a.R = R; a.n_tiles = (R + kRows - 1) / kRows;
     const size_t smem = trunk_smem(false);
     cudaError_t e = cudaFuncSetAttribute(ppo_trunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
@@ -646,18 +724,15 @@ extern "C" int mm_ppo_trunk_fwd(const float* params, const float* obs, const flo
     return mm::check_launch();
 }
 
-extern "C" int mm_ppo_trunk_bwd(const float* params, const float* obs, const float* masks, const float* hp, const float* dout,
-                                float* gA1, float* gA2, float* gGi, float* gGhn, float* gsmall_partials, int32_t n_partials,
-                                int32_t L, int64_t R, int32_t D, int32_t NO, void* stream) {
+extern "C" int mm_ppo_trunk_bwd(const float* params, const float* obs, const float* masks, const float* X, const float* dout,
+                                float* G, float* acc_partials, int32_t n_partials, int32_t L, int64_t R, int32_t D,
+                                int32_t NO, void* stream) {
     int rc = check_common(params, obs, L, R, D, NO);
     if (rc != MM_OK) return rc;
-    if (!hp || !dout || !gA1 || !gA2 || !gGi || !gGhn || !gsmall_partials) return MM_ERR_BAD_ARG;
-    for (const void* p : {(const void*)hp, (const void*)gA1, (const void*)gA2, (const void*)gGi, (const void*)gGhn})
-        if (!mm::aligned(p, 16)) return MM_ERR_BAD_ARG;
+    if (!X || !dout || !G || !acc_partials || !mm::aligned(X, 16) || !mm::aligned(G, 16)) return MM_ERR_BAD_ARG;
     Args a{};
-    a.params = params; a.obs = obs; a.masks = masks; a.hp = const_cast<float*>(hp); a.dout = dout;
-    a.prof = g_prof;
-    a.gA1 = gA1; a.gA2 = gA2; a.gGi = gGi; a.gGhn = gGhn; a.gsmall = gsmall_partials;
+    a.params = params; a.obs = obs; a.masks = masks; a.X = const_cast<float*>(X); a.dout = dout; a.G = G;
+    a.gacc = acc_partials; a.prof = g_prof;
     a.L = L; a.D = D; a.NO = NO; a.R = R; a.n_tiles = (R + kRows - 1) / kRows;
     const int ctas = n_ctas(a.n_tiles);
     if (n_partials < ctas) return MM_ERR_BAD_ARG;

@@ -59,83 +59,11 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B
     if (warp == 0) tc::tmem_dealloc(tmem, ncols);
 }
 
-// Transposed-operand variant: either operand may come from a tile whose ROWS are the contraction index
-// ("MN-major" in the instruction descriptor) -- the same [rows/8][feat/4][8][4] tile a K-major operand uses, read
-// through a descriptor with SBO = 128 B (next 4 features) and LBO = (feat/4) * 128 B (next 8 rows).  This is how the
-// backward kernels contract over the 128 rows of a tile (weight gradients) and over the output features of a weight
-// tile (input gradients) without a second, transposed copy in shared memory.
-//   ta == 0: A is [128][K] row-major;  ta == 1: A is [K][FA] row-major, D rows >= FA are garbage (FA % 4 == 0)
-//   tb == 0: B is [N][K] row-major;    tb == 1: B is [K][N] row-major
-__global__ void __launch_bounds__(128, 1)
-tc_gemm_t_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int N, int K,
-                          int FA, int ta, int tb) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t tmem_slot;
-    uint8_t* sA = smem;                         // 16 KB..64 KB region (zero-filled so that garbage rows stay finite)
-    uint8_t* sB = smem + 128 * 128 * 4;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint32_t ncols = 32;
-    while ((int)ncols < N) ncols <<= 1;
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, ncols);
-    if (tid == 0) tc::mbar_init(&bar, 1);
-    for (int i = tid; i < 2 * 128 * 128; i += 128) reinterpret_cast<float*>(smem)[i] = 0.f;
-    __syncthreads();
-    if (ta) {
-        for (int i = tid; i < K * FA; i += 128) {
-            const int r = i / FA, f = i - r * FA;
-            *reinterpret_cast<float*>(sA + tc::kmajor_offset(r, f, FA)) = A[i];
-        }
-    } else {
-        for (int i = tid; i < 128 * K; i += 128) {
-            const int r = i / K, k = i - r * K;
-            *reinterpret_cast<float*>(sA + tc::kmajor_offset(r, k, K)) = A[i];
-        }
-    }
-    if (tb) {
-        for (int i = tid; i < K * N; i += 128) {
-            const int r = i / N, f = i - r * N;
-            *reinterpret_cast<float*>(sB + tc::kmajor_offset(r, f, N)) = B[i];
-        }
-    } else {
-        for (int i = tid; i < N * K; i += 128) {
-            const int r = i / K, k = i - r * K;
-            *reinterpret_cast<float*>(sB + tc::kmajor_offset(r, k, K)) = B[i];
-        }
-    }
-    tc::fence_smem_to_async();
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem = tmem_slot;
-    if (tid == 0) {
-        const uint32_t idesc = tc::make_idesc_tf32(128, N) | ((uint32_t)ta << 15) | ((uint32_t)tb << 16);
-        for (int kk = 0; kk < K / 8; ++kk) {
-            const uint64_t da = ta ? tc::make_desc(tc::smem_u32(sA) + kk * (FA >> 2) * 128, (uint32_t)(FA >> 2) * 128u, 128u)
-                                   : tc::make_desc(tc::smem_u32(sA) + kk * 256, 128, (uint32_t)(K >> 2) * 128u);
-            const uint64_t db = tb ? tc::make_desc(tc::smem_u32(sB) + kk * (N >> 2) * 128, (uint32_t)(N >> 2) * 128u, 128u)
-                                   : tc::make_desc(tc::smem_u32(sB) + kk * 256, 128, (uint32_t)(K >> 2) * 128u);
-            tc::mma_tf32(tmem, da, db, idesc, kk > 0);
-        }
-        tc::mma_commit(&bar);
-    }
-    tc::mbar_wait(&bar, 0);
-    tc::fence_after_sync();
-    const int row = warp * 32 + lane;
-    for (int c = 0; c < N; c += 16) {
-        float v[16];
-        tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (c + j < N) D[row * N + c + j] = v[j];
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, ncols);
-}
-
 // Raw probe: shared-memory images and descriptor fields given by the caller (layout exploration / regression of the
-// descriptor conventions documented in tc_common.cuh).
+// descriptor conventions documented in tc_common.cuh).  Finding recorded in tests/test_tc_gpu.py: with kind::tf32 and the
+// no-swizzle layout the a_major / b_major ("MN-major") bits of the instruction descriptor make the MMA read zeros --
+// transposed tf32 operands need the 128B_BASE32B swizzled layout -- so the backward kernels stage explicit transposed
+// weight tiles instead.
 __global__ void __launch_bounds__(128, 1)
 tc_raw_selftest_kernel(const float* __restrict__ imgA, const float* __restrict__ imgB, float* __restrict__ D, int N, int steps,
                        int a_step, int a_lbo, int a_sbo, int b_step, int b_lbo, int b_sbo, int ta, int tb) {
@@ -185,17 +113,6 @@ extern "C" int mm_tc_gemm_selftest(const float* A, const float* B, float* D, int
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
     tc_gemm_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, B, D, N, K);
-    return mm::check_launch();
-}
-
-extern "C" int mm_tc_gemm_t_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t FA,
-                                     int32_t trans_a, int32_t trans_b, void* stream) {
-    if (!A || !B || !D || N < 16 || N > 128 || N % 16 || K < 8 || K % 8 || K > 128) return MM_ERR_BAD_ARG;
-    if (trans_a && (FA < 4 || FA > 128 || FA % 4)) return MM_ERR_BAD_ARG;
-    const size_t smem = (size_t)2 * 128 * 128 * 4;
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_t_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
-    tc_gemm_t_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, B, D, N, K, FA, trans_a, trans_b);
     return mm::check_launch();
 }
 

@@ -4,9 +4,9 @@ over data chunks as ONE differentiable op (``mm_ppo_trunk_fwd`` / ``mm_ppo_trunk
 It computes what ``R_Actor.evaluate_actions`` / ``R_Critic.forward`` compute in the chunked (recurrent-generator)
 mode (mappo/algorithms/r_actor_critic.py:95-146,189-208; rnn.py:24-80): rows are data chunks, the carried state is
 multiplied by ``masks[t]`` before every step.  The forward stores the operands of the weight gradients, the backward
-kernel re-computes the forward per step, walks the chunk in reverse and returns the pre-activation gradients; the
-weight gradients are four large-K TF32 GEMMs of those, every bias / LayerNorm / head-weight gradient is reduced
-inside the kernel.  ``LayerNorm(D)``'s affine is folded into the first Linear for the kernel and unfolded here.
+kernel re-computes the forward per step, walks the chunk in reverse and returns the pre-activation gradients G; all
+weight and bias gradients are blocks of ONE large-K TF32 GEMM ``G^T X`` (X carries a ones column), the LayerNorm gain
+and head gradients come from column sums reduced inside the kernel.  ``LayerNorm(D)``'s affine is folded into the first Linear for the kernel and unfolded here.
 """
 import ctypes as C
 
@@ -51,6 +51,28 @@ def _pack(p, D, NO):
     return buf
 
 
+_DIMS = None
+
+
+def dims():
+    global _DIMS
+    if _DIMS is None:
+        d = (C.c_int32 * 8)()
+        _lib.check(_lib.lib().mm_ppo_trunk_dims(d))
+        _DIMS = dict(zip("XS GS n_acc S dbo g2 g1 NOMAX".split(), list(d)))
+    return _DIMS
+
+
+def _gram(G, X):
+    """G^T X for tall operands [rows, g] and [rows, x]: split the contraction into S slabs (batched GEMM) and add them up.
+    A single GEMM call leaves the 5.8 GB of operands at 2.4 ms on a B200; S = 64..256 slabs read them at HBM speed (0.9 ms)."""
+    rows = G.shape[0]
+    for S in (256, 128, 64, 32, 16, 8, 4, 2):
+        if rows % S == 0 and rows // S >= 2048:
+            return torch.bmm(G.view(S, rows // S, -1).transpose(1, 2), X.view(S, rows // S, -1)).sum(0)
+    return G.t() @ X
+
+
 class _PPOTrunkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, obs, h0, masks, *params):
@@ -62,49 +84,49 @@ class _PPOTrunkFn(torch.autograd.Function):
         z = dict(dtype=torch.float32, device=obs.device)
         out = torch.empty((L, R, NO), **z)
         train = any(ctx.needs_input_grad[3:])
+        X = None
         if train:
-            x0, x1 = torch.empty((L, R, K1), **z), torch.empty((L, R, H), **z)
-            x2, hp = torch.empty((L, R, H), **z), torch.empty((L, R, H), **z)
-        else:
-            x0 = x1 = x2 = hp = None
+            XS = dims()["XS"]
+            X = torch.empty((L * R, XS), **z)
+            tail = torch.zeros(XS - 144, **z)
+            tail[0] = 1.0
+            X[:, 144:] = tail                      # the ones column: bias gradients come out of the weight-gradient GEMM
         _lib.check(_lib.lib().mm_ppo_trunk_fwd(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(h0), _lib.ptr(masks), _lib.ptr(out),
-                                               None, _lib.ptr(x0), _lib.ptr(x1), _lib.ptr(x2), _lib.ptr(hp), L, R, D, NO,
-                                               _lib.stream()))
+                                               None, _lib.ptr(X), L, R, D, NO, _lib.stream()))
         if train:
-            ctx.save_for_backward(packed, obs, masks, x0, x1, x2, hp, p["w1"], p["ln0_w"], p["ln0_b"])
+            ctx.save_for_backward(packed, obs, masks, X, *params)
             ctx.dims = (L, R, D, NO)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        packed, obs, masks, x0, x1, x2, hp, w1, ln0_w, ln0_b = ctx.saved_tensors
+        packed, obs, masks, X = ctx.saved_tensors[:4]
+        p = dict(zip(PARAM_ORDER, ctx.saved_tensors[4:]))
         L, R, D, NO = ctx.dims
-        o = offsets()
-        n_small = o["total"] - o["small"]
+        d = dims()
         z = dict(dtype=torch.float32, device=obs.device)
-        gA1, gA2 = torch.empty((L * R, H), **z), torch.empty((L * R, H), **z)
-        gGi, gGhn = torch.empty((L * R, 3 * H), **z), torch.empty((L * R, H), **z)
+        G = torch.empty((L * R, d["GS"]), **z)
         n_part = _lib.lib().mm_ppo_trunk_max_ctas()
-        partial = torch.zeros((n_part, n_small), **z)
-        _lib.check(_lib.lib().mm_ppo_trunk_bwd(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(masks), _lib.ptr(hp),
-                                               _lib.ptr(dout.contiguous()), _lib.ptr(gA1), _lib.ptr(gA2), _lib.ptr(gGi),
-                                               _lib.ptr(gGhn), _lib.ptr(partial), n_part, L, R, D, NO, _lib.stream()))
-        small = partial.sum(0)
-        s = lambda k, n: small[o[k] - o["small"]: o[k] - o["small"] + n]
-        gw1f = gA1.t() @ x0.view(L * R, K1)                       # gradient of the folded first Linear [H, K1]
-        gb1f = s("b1", H)
-        gw2 = gA2.t() @ x1.view(L * R, H)
-        gwih = gGi.t() @ x2.view(L * R, H)
-        hp2 = hp.view(L * R, H)
-        gwhh = torch.cat([gGi[:, :2 * H].t() @ hp2, gGhn.t() @ hp2], 0)
-        gbih = s("bih", 3 * H)
-        gbhh = torch.cat([gbih[:2 * H], s("bhh", 3 * H)[2 * H:]])
-        # unfold LayerNorm(D): w1f = w1 * g0, b1f = b1 + w1 @ b0  =>  dw1 = dw1f * g0 + outer(db1f, b0)
-        gw1f = gw1f[:, :D]
-        grads = dict(ln0_w=(gw1f * w1).sum(0), ln0_b=w1.t() @ gb1f, w1=gw1f * ln0_w + torch.outer(gb1f, ln0_b), b1=gb1f,
-                     ln1_w=s("ln1_w", H), ln1_b=s("ln1_b", H), w2=gw2, b2=s("b2", H), ln2_w=s("ln2_w", H),
-                     ln2_b=s("ln2_b", H), wih=gwih, whh=gwhh, bih=gbih, bhh=gbhh, ln3_w=s("ln3_w", H),
-                     ln3_b=s("ln3_b", H), wo=s("wo", NOMAX * H).view(NOMAX, H)[:NO], bo=s("bo", NOMAX)[:NO])
+        partial = torch.zeros((n_part, d["n_acc"]), **z)
+        _lib.check(_lib.lib().mm_ppo_trunk_bwd(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(masks), _lib.ptr(X),
+                                               _lib.ptr(dout.contiguous()), _lib.ptr(G), _lib.ptr(partial), n_part, L, R, D, NO,
+                                               _lib.stream()))
+        acc = partial.sum(0)
+        W = _gram(G, X)                                           # [GS, XS]: every weight / bias gradient is a block of it
+        S = acc[d["S"]: d["S"] + NOMAX * H].view(NOMAX, H)[:NO]   # sum_r dout[r, o] * xhat3[r, j]
+        dbo = acc[d["dbo"]: d["dbo"] + NO]
+        gw1f, gb1f = W[0:32, 0:D], W[0:32, 144]                   # folded first Linear
+        gw2, gb2 = W[32:64, 48:80], W[32:64, 144]
+        gwih, gbih = W[64:160, 80:112], W[64:160, 144]
+        gwhh = torch.cat([W[64:128, 112:144], W[160:192, 112:144]], 0)
+        gbhh = torch.cat([gbih[:2 * H], W[160:192, 144]])
+        w1, wo = p["w1"], p["wo"]
+        grads = dict(
+            # unfold LayerNorm(D): w1f = w1 * g0, b1f = b1 + w1 @ b0  =>  dw1 = dw1f * g0 + outer(db1f, b0)
+            ln0_w=(gw1f * w1).sum(0), ln0_b=w1.t() @ gb1f, w1=gw1f * p["ln0_w"] + torch.outer(gb1f, p["ln0_b"]), b1=gb1f,
+            ln1_w=acc[d["g1"]: d["g1"] + H], ln1_b=gb2 @ p["w2"], w2=gw2, b2=gb2,
+            ln2_w=acc[d["g2"]: d["g2"] + H], ln2_b=gbih @ p["wih"], wih=gwih, whh=gwhh, bih=gbih, bhh=gbhh,
+            ln3_w=(wo * S).sum(0), ln3_b=dbo @ wo, wo=S * p["ln3_w"] + torch.outer(dbo, p["ln3_b"]), bo=dbo)
         return (None, None, None) + tuple(grads[k] if ctx.needs_input_grad[3 + i] else None
                                           for i, k in enumerate(PARAM_ORDER))
 

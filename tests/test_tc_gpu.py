@@ -25,17 +25,24 @@ def test_tcgen05_tf32_gemm_selftest(cuda, N, K):
     assert torch.equal(D, Ai @ Bi.t())
 
 
-@pytest.mark.parametrize("ta,tb,N,K,FA", [(1, 1, 96, 128, 32), (1, 1, 32, 128, 128), (0, 1, 32, 96, 0), (0, 1, 48, 32, 0),
-                                          (1, 0, 64, 64, 48), (1, 1, 64, 128, 64)])
-def test_tcgen05_transposed_operand_descriptors(cuda, ta, tb, N, K, FA):
-    """MN-major descriptors on the K-major tiles: contraction over tile rows (exact on small integers)."""
+
+def test_tcgen05_descriptor_strides_probe(cuda):
+    """Raw probe of the K-major no-swizzle descriptor: a single 1.0 at byte offset (m & 7) * 16 + (m >> 3) * SBO +
+    (k >> 2) * LBO + (k & 3) * 4 of the A image lands in row m of D (B = ones), for non-default LBO / SBO as well."""
     from minimarl_b200 import _lib
-    g = torch.Generator(device=cuda).manual_seed(7 + N + K)
-    A = torch.randint(-4, 5, (K, FA) if ta else (128, K), device=cuda, generator=g).float()
-    B = torch.randint(-4, 5, (K, N) if tb else (N, K), device=cuda, generator=g).float()
-    D = torch.zeros((128, N), device=cuda)
-    _lib.check(_lib.lib().mm_tc_gemm_t_selftest(_lib.ptr(A), _lib.ptr(B), _lib.ptr(D), N, K, FA, ta, tb, _lib.stream()))
-    torch.cuda.synchronize()
-    ref = (A.t() if ta else A) @ (B if tb else B.t())
-    rows = FA if ta else 128
-    assert torch.equal(D[:rows], ref)
+    N = 16
+    ones = torch.ones(16384, device=cuda)
+    for lbo, sbo in ((128, 256), (256, 128), (1024, 128)):
+        for m, k in ((0, 0), (5, 3), (9, 6), (77, 1), (127, 7)):
+            off = (m & 7) * 16 + (m >> 3) * sbo + (k >> 2) * lbo + (k & 3) * 4
+            if off >= 65536:
+                continue
+            img = torch.zeros(16384, device=cuda)
+            img[off // 4] = 1.0
+            D = torch.full((128, N), -1.0, device=cuda)
+            _lib.check(_lib.lib().mm_tc_raw_selftest(_lib.ptr(img), _lib.ptr(ones), _lib.ptr(D), N, 1, 0, lbo, sbo, 0, 128, 256,
+                                                     0, 0, _lib.stream()))
+            torch.cuda.synchronize()
+            rows = (D[:, 0] != 0).nonzero().flatten().tolist()
+            # with SBO = 128 and LBO = 256 row m and row m + 16 (second k group of m) share a byte: both must light up
+            assert m in rows and all((r - m) % 8 == 0 for r in rows), (lbo, sbo, m, k, rows)
