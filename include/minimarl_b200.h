@@ -345,10 +345,13 @@ int mm_mappo_rollout_tc(const float* params, uint32_t* env_state, float* obs, fl
  * over L-step data chunks, rows = chunks.  obs [L,R,D] (D <= 48), h0 [R,32], masks [L,R] or NULL, out [L,R,NO] (NO <= 8).
  * params: mm_ppo_trunk_param_offsets layout, LayerNorm(D)'s affine folded into the first Linear by the caller.
  * mm_ppo_trunk_dims -> {XS, GS, n_acc, off_S, off_dbo, off_dgamma2, off_dgamma1, NOMAX}.
+ * obs_row != NULL: the chunks are gathered in place -- obs is then a row table [*, D] (the rollout buffer's
+ *   [T+1, N, A, D] storage) and step t of chunk r is table row obs_row[r] + t * obs_step_rows, which is how
+ *   recurrent_generator (shared_buffer.py:318-427) addresses its chunks; nothing is materialised.
  * fwd, training mode (X != NULL): stores the operands of the weight gradients into X [L*R, XS]:
  *   x0 (normalised obs) [0,48) | x1 [48,80) | x2 [80,112) | hp (masked input state) [112,144); the caller owns columns
  *   [144,XS) and sets X[:,144] = 1 so that the bias gradients fall out of the same GEMM.
- * bwd: recomputes the forward per step (reads hp from X), needs dout [L,R,NO]; writes the pre-activation gradients
+ * bwd: recomputes the forward per step (reads x0 and hp from X), needs dout [L,R,NO]; writes the pre-activation gradients
  *   G [L*R, GS] = dA1 [0,32) | dA2 [32,64) | dGi (r,z,n) [64,160) | dGh_n [160,192) and per CTA the column sums
  *   S[o][j] = sum dout[.,o] xhat3[.,j], dbo, dgamma2, dgamma1 into acc_partials [n_partials >= mm_ppo_trunk_max_ctas()][n_acc].
  *   All weight and bias gradients are blocks of the ONE large-K GEMM G^T X (caller, TF32 cuBLAS); the LayerNorm
@@ -360,11 +363,11 @@ int mm_ppo_trunk_dims(int32_t* dims8);
 int mm_ppo_trunk_max_ctas(void);
 /* Debug: CTA 0 of later launches accumulates clock64() deltas per kernel phase into dev_buf16 (int64[16]); NULL = off. */
 int mm_ppo_trunk_set_prof(long long* dev_buf16);
-int mm_ppo_trunk_fwd(const float* params, const float* obs, const float* h0, const float* masks, float* out,
-                     float* h_final, float* X, int32_t L, int64_t R, int32_t D, int32_t NO, void* stream);
-int mm_ppo_trunk_bwd(const float* params, const float* obs, const float* masks, const float* X, const float* dout,
-                     float* G, float* acc_partials, int32_t n_partials, int32_t L, int64_t R, int32_t D, int32_t NO,
+int mm_ppo_trunk_fwd(const float* params, const float* obs, const int64_t* obs_row, int64_t obs_step_rows, const float* h0,
+                     const float* masks, float* out, float* h_final, float* X, int32_t L, int64_t R, int32_t D, int32_t NO,
                      void* stream);
+int mm_ppo_trunk_bwd(const float* params, const float* masks, const float* X, const float* dout, float* G,
+                     float* acc_partials, int32_t n_partials, int32_t L, int64_t R, int32_t D, int32_t NO, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PPO losses of R_MAPPO.ppo_update / cal_value_loss (mappo/algorithms/ramppo_network.py:70-171), one pass each.

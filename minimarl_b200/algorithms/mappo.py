@@ -21,7 +21,7 @@ import torch.nn as nn
 from ..nn.agent_q import MLPBase, _init_linear, _tc_fits, agentq_forward, pack_agentq, pack_agentq_tc
 from ..nn.gru import GRU
 from ..nn.layernorm import LayerNorm
-from ..nn.ppo_trunk import ppo_trunk, trunk_fits
+from ..nn.ppo_trunk import ChunkRows, ppo_trunk, trunk_fits
 from ..ops.ppo_loss import ppo_actor_loss, ppo_value_loss
 from ..parallel import allreduce_mean_grads, allreduce_stats
 
@@ -211,7 +211,9 @@ class _FusedTrunk(nn.Module):
         """obs [L*N, D] (step-major), rnn_states [N, 1, H], masks [L*N, 1] -> head output [L*N, n_out]."""
         N = rnn_states.size(0)
         Lc = obs.size(0) // N
-        out = ppo_trunk(obs.view(Lc, N, -1), rnn_states[:, 0, :], masks.view(Lc, N), self._trunk_params())
+        if not isinstance(obs, ChunkRows):
+            obs = obs.view(Lc, N, -1)
+        out = ppo_trunk(obs, rnn_states[:, 0, :], masks.view(Lc, N), self._trunk_params())
         return out.view(Lc * N, -1)
 
     def _agentq_state(self):
@@ -417,13 +419,15 @@ class R_MAPPO:
     def ppo_update(self, sample, update_actor=True):
         (share_obs_batch, obs_batch, rnn_states_batch, rnn_states_critic_batch, actions_batch, value_preds_batch,
          return_batch, masks_batch, active_masks_batch, old_action_log_probs_batch, adv_targ, available_actions_batch) = sample
-        to = lambda x: check(x).to(**self.tpdv)
+        to = lambda x: x if isinstance(x, ChunkRows) else check(x).to(**self.tpdv)
         old_action_log_probs_batch, adv_targ = to(old_action_log_probs_batch), to(adv_targ)
         value_preds_batch, return_batch, active_masks_batch = to(value_preds_batch), to(return_batch), to(active_masks_batch)
         actor = self.policy.actor
         if (self._fused_loss and available_actions_batch is None and hasattr(actor, "_chunk_fusable")
                 and actor._chunk_fusable(to(obs_batch), to(rnn_states_batch))):
             return self._ppo_update_fused(sample, update_actor)
+        if isinstance(obs_batch, ChunkRows):
+            share_obs_batch, obs_batch = share_obs_batch.gather(), obs_batch.gather()
         values, action_log_probs, dist_entropy = self.policy.evaluate_actions(
             share_obs_batch, obs_batch, rnn_states_batch, rnn_states_critic_batch, actions_batch, masks_batch,
             available_actions_batch, active_masks_batch)
@@ -457,7 +461,7 @@ class R_MAPPO:
         """Same update with the fused trunk op and the loss kernels: logits -> (policy loss, entropy, ratio) in one pass."""
         (share_obs_batch, obs_batch, rnn_states_batch, rnn_states_critic_batch, actions_batch, value_preds_batch,
          return_batch, masks_batch, active_masks_batch, old_action_log_probs_batch, adv_targ, _) = sample
-        to = lambda x: check(x).to(**self.tpdv)
+        to = lambda x: x if isinstance(x, ChunkRows) else check(x).to(**self.tpdv)
         actor, critic = self.policy.actor, self.policy.critic
         logits = actor._fused_chunks(to(obs_batch), to(rnn_states_batch), to(masks_batch))
         policy_loss, dist_entropy, ratio = ppo_actor_loss(
@@ -471,7 +475,11 @@ class R_MAPPO:
             if self._use_max_grad_norm else _grad_norm(actor.parameters())
         self.policy.actor_optimizer.step()
 
-        values, _ = critic(to(share_obs_batch), to(rnn_states_critic_batch), to(masks_batch))
+        if critic._chunk_fusable(to(share_obs_batch), to(rnn_states_critic_batch)):
+            values = critic._fused_chunks(to(share_obs_batch), to(rnn_states_critic_batch), to(masks_batch))
+        else:
+            cent = share_obs_batch.gather() if isinstance(share_obs_batch, ChunkRows) else share_obs_batch
+            values, _ = critic(cent, rnn_states_critic_batch, masks_batch)
         value_loss = self.cal_value_loss(values, to(value_preds_batch), to(return_batch), to(active_masks_batch))
         self.policy.critic_optimizer.zero_grad()
         (value_loss * self.value_loss_coef).backward()
@@ -499,7 +507,8 @@ class R_MAPPO:
         for epoch in range(self.ppo_epoch):
             perm = None if perms is None else perms[epoch]
             if self._use_recurrent_policy:
-                gen = buffer.recurrent_generator(advantages, self.train_batch_size, self.data_chunk_length, perm=perm)
+                gen = buffer.recurrent_generator(advantages, self.train_batch_size, self.data_chunk_length, perm=perm,
+                                                 lazy_obs=self._fused_loss)
             elif self._use_naive_recurrent:
                 gen = buffer.naive_recurrent_generator(advantages, self.train_batch_size, perm=perm)
             else:

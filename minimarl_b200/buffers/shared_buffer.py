@@ -140,7 +140,7 @@ class SharedReplayBuffer(object):
             yield (share_obs[ind], obs[ind], rnn_states[ind], rnn_states_critic[ind], actions[ind],
                    value_preds[ind], returns[ind], masks[ind], active_masks[ind], log_probs[ind], adv[ind], None)
 
-    def recurrent_generator(self, advantages, num_mini_batch, data_chunk_length, perm=None):
+    def recurrent_generator(self, advantages, num_mini_batch, data_chunk_length, perm=None, lazy_obs=False):
         """Chunks of L consecutive rows of the (env, agent, time)-major flattening, shuffled
         (shared_buffer.py:318-427).  Row f of that flattening is storage element [t, env, agent] with
         env = f // (A*T), agent = (f // T) % A, t = f % T, so the chunks are gathered straight from the
@@ -160,7 +160,15 @@ class SharedReplayBuffer(object):
             take = lambda x: x[t, env, agent].reshape(L * mini_batch_size, *x.shape[3:])
             f0 = chunk * L
             env0, agent0, t0 = f0 // (A * T), (f0 // T) % A, f0 % T
-            yield (take(self.share_obs), take(self.obs), self.rnn_states[t0, env0, agent0],
+            if lazy_obs and T % L == 0:
+                # the fused update reads the chunks in place: first row of every chunk in the [(T+1)*N*A, D] storage
+                from ..nn.ppo_trunk import ChunkRows
+                first = (t0 * N + env0) * A + agent0
+                rows = lambda x: ChunkRows(x.view(-1, x.shape[-1]), first, N * A, L)
+                share_b, obs_b = rows(self.share_obs), rows(self.obs)
+            else:
+                share_b, obs_b = take(self.share_obs), take(self.obs)
+            yield (share_b, obs_b, self.rnn_states[t0, env0, agent0],
                    self.rnn_states_critic[t0, env0, agent0], take(self.actions), take(self.value_preds),
                    take(self.returns), take(self.masks), take(self.active_masks), take(self.action_log_probs),
                    take(adv), None)

@@ -73,7 +73,9 @@ constexpr int ACC_S = 0, ACC_BO = NOMAX * H, ACC_G2 = ACC_BO + NOMAX, ACC_G1 = A
 
 struct Args {
     const float* params;
-    const float* obs;      // [L][R][D]
+    const float* obs;      // [L][R][D], or (obs_row != null) a row table [*][D] addressed through obs_row
+    const long long* obs_row;   // [R] first-step row of every chunk in the table, or null          (forward)
+    long long obs_step;    // rows between consecutive steps of a chunk in the table                   (forward)
     const float* h0;       // [R][H]                      (forward)
     const float* masks;    // [L][R] or null
     float* out;            // [L][R][NO]                  (forward)
@@ -276,6 +278,16 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
     };
     // raw observation tile of (tile row0, step t) -> sObs, asynchronously; rows past the end of the batch are zero
     auto fetch_obs = [&](long long row0, int n_valid, int t) {
+        if (a.obs_row) {
+            // chunk rows gathered straight from the rollout buffer: row r of the tile is table row obs_row[row0 + r] + t * obs_step
+            for (int r = warp; r < n_valid; r += kThreads / 32) {
+                const float* src = a.obs + (a.obs_row[row0 + r] + (long long)t * a.obs_step) * a.D;
+                for (int k = lane; k < a.D; k += 32) cp_async4(sObs + r * a.D + k, src + k);
+            }
+            for (int i = n_valid * a.D + tid; i < kRows * a.D; i += kThreads) sObs[i] = 0.f;
+            cp_async_commit();
+            return;
+        }
         const float* src = a.obs + ((long long)t * a.R + row0) * a.D;
         const int n = n_valid * a.D;
         if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
@@ -287,7 +299,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
         for (int i = n + tid; i < kRows * a.D; i += kThreads) sObs[i] = 0.f;
         cp_async_commit();
     };
-
     // head gradients of (tile row0, step t) -> sDout, asynchronously (contiguous n_valid * NO floats)
     auto fetch_dout = [&](long long row0, int n_valid, int t) {
         const float* src = a.dout + ((long long)t * a.R + row0) * a.NO;
@@ -707,14 +718,16 @@ extern "C" int mm_ppo_trunk_set_prof(long long* dev_buf16) { g_prof = dev_buf16;
 
 extern "C" int mm_ppo_trunk_max_ctas(void) { return n_ctas(1 << 30); }
 
-extern "C" int mm_ppo_trunk_fwd(const float* params, const float* obs, const float* h0, const float* masks, float* out,
-                                float* h_final, float* X, int32_t L, int64_t R, int32_t D, int32_t NO, void* stream) {
+extern "C" int mm_ppo_trunk_fwd(const float* params, const float* obs, const int64_t* obs_row, int64_t obs_step_rows,
+                                const float* h0, const float* masks, float* out, float* h_final, float* X, int32_t L, int64_t R,
+                                int32_t D, int32_t NO, void* stream) {
     int rc = check_common(params, obs, L, R, D, NO);
     if (rc != MM_OK) return rc;
     if (!h0 || !out || !mm::aligned(h0, 16)) return MM_ERR_BAD_ARG;
     if ((X && !mm::aligned(X, 16)) || (h_final && !mm::aligned(h_final, 16))) return MM_ERR_BAD_ARG;
     Args a{};
     a.params = params; a.obs = obs; a.h0 = h0; a.masks = masks; a.out = out; a.h_final = h_final; a.X = X;
+    a.obs_row = reinterpret_cast<const long long*>(obs_row); a.obs_step = obs_step_rows;
     a.prof = g_prof;
     a.L = L; a.D = D; a.NO = NO; a.R = R; a.n_tiles = (R + kRows - 1) / kRows;
     const size_t smem = trunk_smem(false);
@@ -724,14 +737,14 @@ extern "C" int mm_ppo_trunk_fwd(const float* params, const float* obs, const flo
     return mm::check_launch();
 }
 
-extern "C" int mm_ppo_trunk_bwd(const float* params, const float* obs, const float* masks, const float* X, const float* dout,
+extern "C" int mm_ppo_trunk_bwd(const float* params, const float* masks, const float* X, const float* dout,
                                 float* G, float* acc_partials, int32_t n_partials, int32_t L, int64_t R, int32_t D,
                                 int32_t NO, void* stream) {
-    int rc = check_common(params, obs, L, R, D, NO);
+    int rc = check_common(params, X, L, R, D, NO);
     if (rc != MM_OK) return rc;
     if (!X || !dout || !G || !acc_partials || !mm::aligned(X, 16) || !mm::aligned(G, 16)) return MM_ERR_BAD_ARG;
     Args a{};
-    a.params = params; a.obs = obs; a.masks = masks; a.X = const_cast<float*>(X); a.dout = dout; a.G = G;
+    a.params = params; a.masks = masks; a.X = const_cast<float*>(X); a.dout = dout; a.G = G;
     a.gacc = acc_partials; a.prof = g_prof;
     a.L = L; a.D = D; a.NO = NO; a.R = R; a.n_tiles = (R + kRows - 1) / kRows;
     const int ctas = n_ctas(a.n_tiles);

@@ -75,15 +75,20 @@ def _gram(G, X):
 
 class _PPOTrunkFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, obs, h0, masks, *params):
+    def forward(ctx, obs, h0, masks, rows, *params):
         p = dict(zip(PARAM_ORDER, params))
-        L, R, D = obs.shape
+        if rows is None:
+            L, R, D = obs.shape
+            row_index, step_rows = None, 0
+        else:                                   # obs is a row table, rows = (first-step row of every chunk, rows per step, L)
+            row_index, step_rows, L = rows
+            R, D = row_index.numel(), obs.shape[-1]
         NO = p["wo"].shape[0]
         with torch.no_grad():
             packed = _pack(p, D, NO)
         z = dict(dtype=torch.float32, device=obs.device)
         out = torch.empty((L, R, NO), **z)
-        train = any(ctx.needs_input_grad[3:])
+        train = any(ctx.needs_input_grad[4:])
         X = None
         if train:
             XS = dims()["XS"]
@@ -91,24 +96,24 @@ class _PPOTrunkFn(torch.autograd.Function):
             tail = torch.zeros(XS - 144, **z)
             tail[0] = 1.0
             X[:, 144:] = tail                      # the ones column: bias gradients come out of the weight-gradient GEMM
-        _lib.check(_lib.lib().mm_ppo_trunk_fwd(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(h0), _lib.ptr(masks), _lib.ptr(out),
-                                               None, _lib.ptr(X), L, R, D, NO, _lib.stream()))
+        _lib.check(_lib.lib().mm_ppo_trunk_fwd(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(row_index), int(step_rows), _lib.ptr(h0),
+                                               _lib.ptr(masks), _lib.ptr(out), None, _lib.ptr(X), L, R, D, NO, _lib.stream()))
         if train:
-            ctx.save_for_backward(packed, obs, masks, X, *params)
+            ctx.save_for_backward(packed, masks, X, *params)
             ctx.dims = (L, R, D, NO)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        packed, obs, masks, X = ctx.saved_tensors[:4]
-        p = dict(zip(PARAM_ORDER, ctx.saved_tensors[4:]))
+        packed, masks, X = ctx.saved_tensors[:3]
+        p = dict(zip(PARAM_ORDER, ctx.saved_tensors[3:]))
         L, R, D, NO = ctx.dims
         d = dims()
-        z = dict(dtype=torch.float32, device=obs.device)
+        z = dict(dtype=torch.float32, device=X.device)
         G = torch.empty((L * R, d["GS"]), **z)
         n_part = _lib.lib().mm_ppo_trunk_max_ctas()
         partial = torch.zeros((n_part, d["n_acc"]), **z)
-        _lib.check(_lib.lib().mm_ppo_trunk_bwd(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(masks), _lib.ptr(X),
+        _lib.check(_lib.lib().mm_ppo_trunk_bwd(_lib.ptr(packed), _lib.ptr(masks), _lib.ptr(X),
                                                _lib.ptr(dout.contiguous()), _lib.ptr(G), _lib.ptr(partial), n_part, L, R, D, NO,
                                                _lib.stream()))
         acc = partial.sum(0)
@@ -127,12 +132,31 @@ class _PPOTrunkFn(torch.autograd.Function):
             ln1_w=acc[d["g1"]: d["g1"] + H], ln1_b=gb2 @ p["w2"], w2=gw2, b2=gb2,
             ln2_w=acc[d["g2"]: d["g2"] + H], ln2_b=gbih @ p["wih"], wih=gwih, whh=gwhh, bih=gbih, bhh=gbhh,
             ln3_w=(wo * S).sum(0), ln3_b=dbo @ wo, wo=S * p["ln3_w"] + torch.outer(dbo, p["ln3_b"]), bo=dbo)
-        return (None, None, None) + tuple(grads[k] if ctx.needs_input_grad[3 + i] else None
+        return (None, None, None, None) + tuple(grads[k] if ctx.needs_input_grad[4 + i] else None
                                           for i, k in enumerate(PARAM_ORDER))
 
 
+class ChunkRows:
+    """Data chunks addressed in place: ``table`` [rows, D] is the rollout buffer's storage seen as rows, step ``l`` of
+    chunk ``c`` is row ``first[c] + l * step_rows``.  What recurrent_generator would otherwise gather into [L * Nc, D]."""
+
+    def __init__(self, table, first, step_rows, L):
+        self.table, self.first, self.step_rows, self.L = table, first, int(step_rows), int(L)
+
+    def size(self, dim):
+        return (self.L * self.first.numel(), self.table.shape[-1])[dim]
+
+    def gather(self):
+        idx = self.first.unsqueeze(0) + torch.arange(self.L, device=self.first.device).unsqueeze(1) * self.step_rows
+        return self.table[idx.reshape(-1)]
+
+
 def ppo_trunk(obs, h0, masks, params):
-    """obs [L, R, D], h0 [R, 32], masks [L, R] or None, params: dict keyed by PARAM_ORDER -> head output [L, R, NO]."""
-    obs, h0 = obs.contiguous(), h0.contiguous()
+    """obs [L, R, D] (or ChunkRows), h0 [R, 32], masks [L, R] or None, params: dict keyed by PARAM_ORDER -> head output
+    [L, R, NO]."""
+    h0 = h0.contiguous()
     masks = masks.contiguous() if masks is not None else None
-    return _PPOTrunkFn.apply(obs, h0, masks, *[params[k] for k in PARAM_ORDER])
+    if isinstance(obs, ChunkRows):
+        return _PPOTrunkFn.apply(obs.table, h0, masks, (obs.first.contiguous(), obs.step_rows, obs.L),
+                                 *[params[k] for k in PARAM_ORDER])
+    return _PPOTrunkFn.apply(obs.contiguous(), h0, masks, None, *[params[k] for k in PARAM_ORDER])

@@ -104,3 +104,32 @@ def test_fused_update_matches_stepwise_update(cuda):
     for k in ("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio"):
         a, b = infos[True][k], infos[False][k]
         assert abs(a - b) <= 2e-2 * max(abs(b), 1e-3) + 1e-4, (k, a, b)
+
+
+def test_chunks_read_in_place_equal_gathered_chunks(cuda):
+    """recurrent_generator(lazy_obs=True) hands the trunk op row addresses instead of a gathered copy: same bits."""
+    from minimarl_b200.buffers import SharedReplayBuffer
+    from minimarl_b200.envs.spaces import Box, Discrete
+    from minimarl_b200.nn.ppo_trunk import ChunkRows
+    from test_mappo_gpu import _args, _g
+    policy = _nets(cuda, seed=2)
+    T, N, Lc = 24, 37, 8
+    args = _args(_g(), "tf32", hidden_size=32, max_step=T, batch_size=N)
+    space = Box(np.zeros(47), np.ones(47))
+    buf = SharedReplayBuffer(args, 2, space, space, Discrete(5), device=cuda)
+    buf.obs.uniform_(); buf.share_obs.copy_(buf.obs); buf.rnn_states.normal_(); buf.masks.bernoulli_(0.8)
+    adv = torch.randn_like(buf.rewards)
+    perm = torch.randperm(T * N * 2 // Lc, generator=torch.Generator().manual_seed(1)).to(cuda)
+    lazy = next(iter(buf.recurrent_generator(adv, 1, Lc, perm=perm, lazy_obs=True)))
+    full = next(iter(buf.recurrent_generator(adv, 1, Lc, perm=perm)))
+    assert isinstance(lazy[1], ChunkRows) and torch.equal(lazy[1].gather(), full[1]) and torch.equal(lazy[0].gather(), full[0])
+    for a, b in zip(lazy[2:11], full[2:11]):
+        assert torch.equal(a, b)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        with torch.no_grad():
+            out_lazy = policy.actor._fused_chunks(lazy[1], lazy[2], lazy[7])
+            out_full = policy.actor._fused_chunks(full[1], full[2], full[7])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+    assert torch.equal(out_lazy, out_full)
