@@ -250,6 +250,67 @@ def policy_rollout_section(dev, steps):
     return out
 
 
+def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
+    """BASELINE configs[2] / [4]: one full MAPPO iteration -- fused policy + env rollout of n_envs x T steps into the device
+    SharedReplayBuffer, bootstrap value + GAE, and R_MAPPO.train (ppo_epoch 15, one minibatch of all data chunks of
+    length 8, recurrent actor / critic of hidden size 32: the defaults of mappo/_config.py).  Runs on every rank (env
+    shard per GPU); the PPO update all-reduces its gradients over NCCL when world > 1."""
+    import argparse as ap
+    import torch
+    import torch.distributed as dist
+    from minimarl_b200 import BatchedCheckers
+    from minimarl_b200.runners import MappoRunner
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    args = ap.Namespace(
+        hidden_size=32, layer_N=1, recurrent_N=1, use_feature_normalization=True, use_ReLU=True, use_orthogonal=True,
+        gain=0.01, use_conv1d=False, use_recurrent_policy=True, use_naive_recurrent_policy=False,
+        use_policy_active_masks=True, use_value_active_masks=True, use_popart=False, use_valuenorm=True,
+        use_huber_loss=True, use_max_grad_norm=True, use_clipped_value_loss=True, use_gae=True, ppo_epoch=15,
+        train_batch_size=1, data_chunk_length=8, clip_param=0.2, entropy_coef=0.01, value_loss_coef=1.0,
+        max_grad_norm=10.0, huber_delta=10.0, actor_lr=5e-4, critic_lr=5e-4, opti_eps=1e-5, weight_decay=0, gamma=0.99,
+        gae_lambda=0.95, max_step=T, batch_size=n_envs, fused_precision="tf32", max_episodes=1000, use_eval=False,
+        eval_interval=10, use_linear_lr_decay=False, seed=1)
+    env = BatchedCheckers(n_envs, max_steps=100, auto_reset=True, device=dev)
+    r = MappoRunner({"args": args, "train_env": env, "eval_env": env, "num_agents": AGENTS, "device": dev})
+    r.warmup()
+    r.run_episode(0)                                        # warm-up iteration (allocations, cuBLAS heuristics)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    infos = None
+    for k in range(steps):
+        ev[k][0].record(); r.rollout()
+        ev[k][1].record(); r.compute()
+        ev[k][2].record(); infos = r.train()
+        ev[k][3].record()
+    torch.cuda.synchronize()
+    ms = [sum(e[i].elapsed_time(e[i + 1]) for e in ev) / steps for i in range(3)]
+    tot = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    total_ms = float(tot.item())
+    agent_steps = world * n_envs * T * AGENTS
+    out = {
+        "metric": "agent-steps/sec through the full MAPPO iteration (rollout + GAE + PPO update)",
+        "value": agent_steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "ms_per_iteration": total_ms,
+        "ms_rollout": ms[0], "ms_gae_and_bootstrap": ms[1], "ms_ppo_update": ms[2],
+        "rollout_agent_steps_per_s": n_envs * T * AGENTS / (ms[0] * 1e-3),
+        "ppo_update_samples_per_s": world * n_envs * T * AGENTS * args.ppo_epoch / (ms[2] * 1e-3),
+        "config": {"n_envs_per_gpu": n_envs, "T": T, "agents": AGENTS, "ppo_epoch": args.ppo_epoch, "num_mini_batch": 1,
+                   "data_chunk_length": 8, "hidden": 32, "fused_rollout": bool(r.fused_rollout),
+                   "fused_update": "tcgen05 trunk fwd/bwd + loss kernels", "precision": "tf32 operands, fp32 accumulate",
+                   "grad_allreduce": "NCCL, one flattened bucket per optimiser step" if world > 1 else None},
+        "train_info": {k: float(v) for k, v in infos.items()},
+        "peak_mem_GiB": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+    }
+    del r, env
+    torch.cuda.empty_cache()
+    return out
+
+
 def learner_section(dev, steps):
     """Second half of the BASELINE metric: QMIX train samples/sec (configs[3]: 1M-transition device replay =
     10 000 episodes x T=100, batch 4 096 episodes, GRU agents, hidden 64, PER, double-Q).  One sample = one
@@ -449,12 +510,17 @@ def run_ours(args, wl):
         e2e_s = float(t.item())
     e2e_value = n * A * e2e_steps * world / e2e_s
 
-    learner = None
+    learner = mappo_it = None
     if not args.no_learner:             # on every rank: the update all-reduces its gradients when world > 1
         try:
             learner = learner_section(dev, args.learner_steps)
         except Exception as e:          # the headline line must survive a learner failure; report it
             learner = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+        try:
+            mappo_it = mappo_iteration_section(dev, max(2, args.learner_steps // 2))
+        except Exception as e:
+            mappo_it = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
@@ -498,6 +564,7 @@ def run_ours(args, wl):
             except Exception as e:
                 line["policy_rollout"] = {"error": f"{type(e).__name__}: {e}"}
             line["learner"] = learner
+            line["mappo_iteration"] = mappo_it
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
