@@ -391,6 +391,10 @@ int mm_ppo_value_loss_bwd(const float* values, const float* value_preds, const f
                           const float* norm2, const float* g1, float* dvalues, int64_t R, float clip, float huber_delta,
                           int32_t use_huber, int32_t use_clipped, void* stream);
 
+/* Column sums of a row-major float32 matrix x [rows, C] (C <= 256) accumulated into out [C] (caller zeroes): the bias
+ * gradients of the learner's Linear / GRU layers (what autograd computes with dY.sum(0)). */
+int mm_colsum(const float* x, float* out, int64_t rows, int32_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

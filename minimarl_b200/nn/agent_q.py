@@ -19,6 +19,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .linear import Linear
+
 from .. import _lib
 from .gru import GRU
 from .layernorm import LayerNorm
@@ -149,7 +151,7 @@ class MLPLayer(nn.Module):
         self._layer_N = layer_N
         act = nn.ReLU if use_ReLU else nn.Tanh
         gain = nn.init.calculate_gain("relu" if use_ReLU else "tanh")
-        mk = lambda i, o: nn.Sequential(_init_linear(nn.Linear(i, o), use_orthogonal, gain), act(), LayerNorm(o))
+        mk = lambda i, o: nn.Sequential(_init_linear(Linear(i, o), use_orthogonal, gain), act(), LayerNorm(o))
         self.fc1 = mk(input_dim, hidden_size)
         self.fc_h = mk(hidden_size, hidden_size)        # registered but unused, exactly like the reference (Q6)
         self.fc2 = nn.ModuleList([copy.deepcopy(self.fc_h) for _ in range(layer_N)])
@@ -216,7 +218,7 @@ class ACTLayer(nn.Module):
         self.multi_discrete = False
         if isinstance(act_dim, np.ndarray):
             raise NotImplementedError("multi-discrete action heads are outside the hot path")
-        self.action_out = _init_linear(nn.Linear(hidden_size, act_dim), use_orthogonal, gain)
+        self.action_out = _init_linear(Linear(hidden_size, act_dim), use_orthogonal, gain)
 
     def forward(self, x, no_sequence=False):
         out = self.action_out(x)

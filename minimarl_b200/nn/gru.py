@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
+from ..ops.gram import colsum, gram
 
 
 class _FusedGRUFn(torch.autograd.Function):
@@ -43,8 +44,8 @@ class _FusedGRUFn(torch.autograd.Function):
                                              _lib.ptr(dgi), _lib.ptr(dghn), _lib.ptr(dh0), T, R, H, _lib.stream()))
         dgi2 = dgi.view(T * R, 3 * H)
         dx = (dgi2 @ w_ih).view(T, R, I) if ctx.needs_input_grad[0] else None
-        dw_ih = dgi2.t() @ x2
-        db_ih = dgi2.sum(0)
+        dw_ih = gram(dgi2, x2.reshape(T * R, I).contiguous())
+        db_ih = colsum(dgi2)
         # h_{t-1} for every step: h0 (or zeros) followed by h_seq[:-1]
         h_prev = torch.empty((T, R, H), **z_)
         if has_h0:
@@ -54,8 +55,9 @@ class _FusedGRUFn(torch.autograd.Function):
         h_prev[1:].copy_(h_seq[:-1])
         hp2 = h_prev.view(T * R, H)
         dghn2 = dghn.view(T * R, H)
-        dw_hh = torch.cat((dgi2[:, :2 * H].t() @ hp2, dghn2.t() @ hp2), dim=0)
-        db_hh = torch.cat((dgi2[:, :2 * H].sum(0), dghn2.sum(0)))
+        dw_hh_all = gram(dgi2, hp2)                      # the n rows of this product are discarded: one pass over hp2
+        dw_hh = torch.cat((dw_hh_all[:2 * H], gram(dghn2, hp2)), dim=0)
+        db_hh = torch.cat((db_ih[:2 * H], colsum(dghn2)))
         return dx, (dh0 if (has_h0 and ctx.needs_input_grad[1]) else None), dw_ih, dw_hh, db_ih, db_hh
 
 

@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
+from .linear import Linear
 
 _NAMES = ["wcat", "bcat", "w1b", "b1b", "w2b", "b2b", "wb2", "bb2"]
 
@@ -92,7 +93,7 @@ class QMixer(nn.Module):
         self.hypernet_hidden_dim = args.hypernet_hidden_dim
         self.num_mixer_q_inps = num_agents
         uo = args.use_orthogonal
-        lin = lambda i, o: _init(nn.Linear(i, o), uo)
+        lin = lambda i, o: _init(Linear(i, o), uo)
         S, HH, E, A = cent_obs_dim, self.hypernet_hidden_dim, self.hidden_layer_dim, num_agents
         if args.hypernet_layers == 1:
             self.hyper_w1, self.hyper_w2 = lin(S, A * E), lin(S, E)

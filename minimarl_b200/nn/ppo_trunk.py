@@ -13,6 +13,7 @@ import ctypes as C
 import torch
 
 from .. import _lib
+from ..ops.gram import gram
 
 _OFF = None
 _NAMES = "w1 w2 wih whh small b1 ln1_w ln1_b b2 ln2_w ln2_b bih bhh ln3_w ln3_b wo bo total".split()
@@ -63,16 +64,6 @@ def dims():
     return _DIMS
 
 
-def _gram(G, X):
-    """G^T X for tall operands [rows, g] and [rows, x]: split the contraction into S slabs (batched GEMM) and add them up.
-    A single GEMM call leaves the 5.8 GB of operands at 2.4 ms on a B200; S = 64..256 slabs read them at HBM speed (0.9 ms)."""
-    rows = G.shape[0]
-    for S in (256, 128, 64, 32, 16, 8, 4, 2):
-        if rows % S == 0 and rows // S >= 2048:
-            return torch.bmm(G.view(S, rows // S, -1).transpose(1, 2), X.view(S, rows // S, -1)).sum(0)
-    return G.t() @ X
-
-
 class _PPOTrunkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, obs, h0, masks, rows, *params):
@@ -117,7 +108,7 @@ class _PPOTrunkFn(torch.autograd.Function):
                                                _lib.ptr(dout.contiguous()), _lib.ptr(G), _lib.ptr(partial), n_part, L, R, D, NO,
                                                _lib.stream()))
         acc = partial.sum(0)
-        W = _gram(G, X)                                           # [GS, XS]: every weight / bias gradient is a block of it
+        W = gram(G, X)                                           # [GS, XS]: every weight / bias gradient is a block of it
         S = acc[d["S"]: d["S"] + NOMAX * H].view(NOMAX, H)[:NO]   # sum_r dout[r, o] * xhat3[r, j]
         dbo = acc[d["dbo"]: d["dbo"] + NO]
         gw1f, gb1f = W[0:32, 0:D], W[0:32, 144]                   # folded first Linear

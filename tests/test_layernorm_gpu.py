@@ -38,3 +38,16 @@ def test_layernorm_3d_input_and_state_dict_keys(cuda):
     assert torch.allclose(ln(x), F.layer_norm(x, (64,), ln.weight, ln.bias), atol=5e-6)
     cpu = LayerNorm(64)                                      # parameters on the CPU: plain nn.LayerNorm path (fixture tooling)
     assert cpu(torch.randn(4, 64)).shape == (4, 64)
+
+
+@pytest.mark.parametrize("rows,C", [(5000, 64), (100001, 5), (8192, 192), (4096, 1), (70000, 47)])
+def test_colsum_and_gram_match_torch(cuda, rows, C):
+    """Bias / weight gradient helpers of the learner: column-sum kernel and slab-split G^T X (fp32: 1e-5 relative)."""
+    from minimarl_b200.ops.gram import colsum, gram
+    g = torch.Generator(device=cuda).manual_seed(rows + C)
+    x = torch.randn((rows, C), device=cuda, generator=g)
+    ref = x.double().sum(0)
+    assert float((colsum(x).double() - ref).abs().max()) < 1e-5 * float(x.abs().sum(0).max())
+    y = torch.randn((rows, 32), device=cuda, generator=g)
+    got, want = gram(x, y), x.double().t() @ y.double()
+    assert float((got.double() - want).abs().max()) < 2e-5 * float(want.abs().max() + rows ** 0.5)
