@@ -139,21 +139,26 @@ __device__ __forceinline__ void load8_global(const float* src, float (&v)[CPT]) 
 
 // Copies between a [128 x F] K-major tile and F consecutive columns of global rows (row stride gs floats).  A warp moves
 // 8 rows x 4 sixteen-byte chunks per instruction: conflict-free on the tile side, 64 contiguous bytes per row on the
-// global side.
-__device__ __forceinline__ void tile_to_global(const uint8_t* tile, int F, float* g, long long gs, int n_valid, int tid) {
-    const int lane = tid & 31, r_lo = lane & 7, c_lo = lane >> 3;
-    for (int b = tid >> 5; b < 16 * (F >> 4); b += kThreads / 32) {
-        const int r = (b & 15) * 8 + r_lo, c = (b >> 4) * 4 + c_lo;
-        const float4 v = *reinterpret_cast<const float4*>(tile + tc::kmajor_offset(r, 4 * c, F));
-        if (r < n_valid) mm::st_stream(reinterpret_cast<float4*>(g + r * gs + 4 * c), v);
-    }
+// global side.  Thread (warp w, lane) always handles row 8 (w & 15) + (lane & 7) and chunks (lane >> 3) + 4 i, so every
+// address is a per-thread base plus a compile-time offset.
+template <int F>
+__device__ __forceinline__ void tile_to_global(const uint8_t* tile, float* g, long long gs, int n_valid, int tid) {
+    static_assert(kThreads == 512 && F % 16 == 0, "one pass of 16 warps covers all 128 rows");
+    const int r = ((tid >> 5) & 15) * 8 + (tid & 7), c = (tid & 31) >> 3;
+    if (r >= n_valid) return;
+    const uint8_t* src = tile + tc::kmajor_offset(r, 4 * c, F);
+    float4* dst = reinterpret_cast<float4*>(g + r * gs + 4 * c);
+#pragma unroll
+    for (int i = 0; i < F / 16; ++i) mm::st_stream(dst + 4 * i, *reinterpret_cast<const float4*>(src + 512 * i));
 }
-__device__ __forceinline__ void global_to_tile_async(uint8_t* tile, int F, const float* g, long long gs, int n_valid, int tid) {
-    const int lane = tid & 31, r_lo = lane & 7, c_lo = lane >> 3;
-    for (int b = tid >> 5; b < 16 * (F >> 4); b += kThreads / 32) {
-        const int r = (b & 15) * 8 + r_lo, c = (b >> 4) * 4 + c_lo;
-        cp_async16(tile + tc::kmajor_offset(r, 4 * c, F), g + min(r, n_valid - 1) * gs + 4 * c);
-    }
+template <int F>
+__device__ __forceinline__ void global_to_tile_async(uint8_t* tile, const float* g, long long gs, int n_valid, int tid) {
+    static_assert(kThreads == 512 && F % 16 == 0, "one pass of 16 warps covers all 128 rows");
+    const int r = ((tid >> 5) & 15) * 8 + (tid & 7), c = (tid & 31) >> 3;
+    uint8_t* dst = tile + tc::kmajor_offset(r, 4 * c, F);
+    const float* src = g + min(r, n_valid - 1) * gs + 4 * c;
+#pragma unroll
+    for (int i = 0; i < F / 16; ++i) cp_async16(dst + 512 * i, src + 16 * i);
 }
 
 #define PROF(i)                                                      \
@@ -184,6 +189,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
     float* sP = reinterpret_cast<float*>(red + 2 * kRows * 4) - L.small;   // small params, biased by L.small
     uint8_t* tail = reinterpret_cast<uint8_t*>(sP + L.total);
     tail = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tail) + 127) & ~uintptr_t(127));
+    long long* sRowBase = reinterpret_cast<long long*>(tail);              // [128] first-step table row of the tile's chunks
+    tail += kRows * 8;
     // backward only
     uint8_t* sW2T = tail;                                 // [H(in) x H(out)]
     uint8_t* sWihT = sW2T + H * H * 4;                    // [H(in) x 3H(out)]
@@ -263,12 +270,11 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
     auto row_sums = [&](float s, float q, float& S, float& Q) {
         float2* r2 = red + red_sel * (kRows * 4);
         red_sel ^= 1;
-        r2[row * 4 + part] = make_float2(s, q);
+        r2[part * kRows + row] = make_float2(s, q);                              // [part][row]: conflict-free both ways
         asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory");      // the four warps that share these 32 rows
-        const float4 p01 = *reinterpret_cast<const float4*>(r2 + row * 4);
-        const float4 p23 = *reinterpret_cast<const float4*>(r2 + row * 4 + 2);
-        S = (p01.x + p01.z) + (p23.x + p23.z);
-        Q = (p01.y + p01.w) + (p23.y + p23.w);
+        const float2 p0 = r2[row], p1 = r2[kRows + row], p2 = r2[2 * kRows + row], p3 = r2[3 * kRows + row];
+        S = (p0.x + p1.x) + (p2.x + p3.x);
+        Q = (p0.y + p1.y) + (p2.y + p3.y);
     };
     auto row_stats = [&](float s, float q, float& mean, float& rstd, int n) {
         float S, Q;
@@ -279,10 +285,17 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
     // raw observation tile of (tile row0, step t) -> sObs, asynchronously; rows past the end of the batch are zero
     auto fetch_obs = [&](long long row0, int n_valid, int t) {
         if (a.obs_row) {
-            // chunk rows gathered straight from the rollout buffer: row r of the tile is table row obs_row[row0 + r] + t * obs_step
-            for (int r = warp; r < n_valid; r += kThreads / 32) {
-                const float* src = a.obs + (a.obs_row[row0 + r] + (long long)t * a.obs_step) * a.D;
-                for (int k = lane; k < a.D; k += 32) cp_async4(sObs + r * a.D + k, src + k);
+            // chunk rows gathered straight from the rollout buffer: row r of the tile is table row sRowBase[r] + t * obs_step
+            const long long toff = (long long)t * a.obs_step;
+#pragma unroll
+            for (int j = 0; j < kRows / (kThreads / 32); ++j) {
+                const int r = warp + (kThreads / 32) * j;
+                if (r < n_valid) {
+                    const float* src = a.obs + (sRowBase[r] + toff) * a.D;
+                    float* dst = sObs + r * a.D;
+                    if (lane < a.D) cp_async4(dst + lane, src + lane);
+                    if (lane + 32 < a.D) cp_async4(dst + lane + 32, src + lane + 32);
+                }
             }
             for (int i = n_valid * a.D + tid; i < kRows * a.D; i += kThreads) sObs[i] = 0.f;
             cp_async_commit();
@@ -323,12 +336,16 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
         for (int j = 0; j < CPT; ++j) h[j] = 0.f;
         if (!BWD) {
             load8_global(a.h0 + grow * H + j0, h);
+            if (a.obs_row) {
+                if (tid < n_valid) sRowBase[tid] = a.obs_row[row0 + tid];
+                __syncthreads();
+            }
             fetch_obs(row0, n_valid, 0);
         } else {
             // backward: the normalised observations and the input state of a step come straight from X into the operand tiles
             const float* xrow = a.X + ((long long)(a.L - 1) * a.R + row0) * XS;
-            global_to_tile_async(sX0, K1, xrow, XS, n_valid, tid);
-            global_to_tile_async(sHp, H, xrow + 112, XS, n_valid, tid);
+            global_to_tile_async<K1>(sX0, xrow, XS, n_valid, tid);
+            global_to_tile_async<H>(sHp, xrow + 112, XS, n_valid, tid);
             fetch_dout(row0, n_valid, a.L - 1);
             cp_async_commit();
         }
@@ -385,8 +402,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
             }
             float* const xtile = a.X ? a.X + ((long long)t * a.R + row0) * XS : nullptr;      // this tile's rows of X at step t
             if (!BWD && xtile) {
-                tile_to_global(sX0, K1, xtile, XS, n_valid, tid);
-                tile_to_global(sHp, H, xtile + 112, XS, n_valid, tid);
+                tile_to_global<K1>(sX0, xtile, XS, n_valid, tid);
+                tile_to_global<H>(sHp, xtile + 112, XS, n_valid, tid);
             }
             wait_mma();
             PROF(2);
@@ -419,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 32, dX1 + 16 * kk, dW2 + 16 * kk, id32, kk > 0);
                 tc::mma_commit(&bar);
             }
-            if (!BWD && xtile) tile_to_global(sX1, H, xtile + 48, XS, n_valid, tid);
+            if (!BWD && xtile) tile_to_global<H>(sX1, xtile + 48, XS, n_valid, tid);
             PROF(3);
             wait_mma();
             PROF(4);
@@ -458,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 160, dHp + 16 * kk, dWhh_n + 16 * kk, id32, kk > 0);
                 tc::mma_commit(&bar);
             }
-            if (!BWD && xtile) tile_to_global(sX2, H, xtile + 80, XS, n_valid, tid);
+            if (!BWD && xtile) tile_to_global<H>(sX2, xtile + 80, XS, n_valid, tid);
             PROF(5);
             wait_mma();
             PROF(6);
@@ -467,8 +484,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                     fetch_obs(row0, n_valid, t + 1);     // the X1 / X2 tiles are consumed, the next observations land there
                 } else {
                     const float* xrow = a.X + ((long long)(t - 1) * a.R + row0) * XS;   // X0 / Hp tiles are consumed as well
-                    global_to_tile_async(sX0, K1, xrow, XS, n_valid, tid);
-                    global_to_tile_async(sHp, H, xrow + 112, XS, n_valid, tid);
+                    global_to_tile_async<K1>(sX0, xrow, XS, n_valid, tid);
+                    global_to_tile_async<H>(sHp, xrow + 112, XS, n_valid, tid);
                     cp_async_commit();
                 }
             }
@@ -585,7 +602,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 tc::mma_commit(&bar);
             }
             float* const gtile = a.G + ((long long)t * a.R + row0) * GS;
-            tile_to_global(sdG, 4 * H, gtile + 64, GS, n_valid, tid);
+            tile_to_global<4 * H>(sdG, gtile + 64, GS, n_valid, tid);
             PROF(8);
             wait_mma();
             PROF(9);
@@ -624,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem, dA2 + 16 * kk, dW2T + 16 * kk, id32, kk > 0);
                 tc::mma_commit(&bar);
             }
-            tile_to_global(sdG, H, gtile + 32, GS, n_valid, tid);
+            tile_to_global<H>(sdG, gtile + 32, GS, n_valid, tid);
             PROF(10);
             wait_mma();
             PROF(11);
@@ -651,7 +668,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 store8_kmajor(sX1, row, j0, H, da);                  // staged through the (idle) X1 tile for a coalesced store
             }
             __syncthreads();
-            tile_to_global(sX1, H, gtile, GS, n_valid, tid);
+            tile_to_global<H>(sX1, gtile, GS, n_valid, tid);
             PROF(12);
         }
         if (!BWD && a.h_final && valid) store8_global(a.h_final + grow * H + j0, h);
@@ -670,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
 
 size_t trunk_smem(bool bwd) {
     const Layout L = make_layout();
-    size_t s = (size_t)4 * (H * K1 + H * H + 6 * H * H + kRows * K1 + 3 * kRows * H + 2 * kRows * 8 + (L.total - L.small)) + 256;
+    size_t s = (size_t)4 * (H * K1 + H * H + 6 * H * H + kRows * K1 + 3 * kRows * H + 2 * kRows * 8 + (L.total - L.small)) + 256 + kRows * 8;
     if (bwd) s += (size_t)4 * (H * H + 6 * H * H + kRows * 4 * H + 4 * ACC_N + kRows * NOMAX);
     return s;
 }
