@@ -126,6 +126,44 @@ def cal_td_error(action, reward, done, behavior_q, target_q, gamma):
     return (reward.sum(dim=-1) + (1 - done) * gamma * target_max_q - behavior_value).abs()
 
 
+class Test:
+    """Greedy evaluation with the TD loss of the behaviour / target pair: ``vdn/_test.py:7-52`` (``qmix/_test.py`` is the
+    same loop).  ``test_env`` is a lockstep batch (``BatchedCheckers`` / ``BatchedSwitch``): its boards play
+    ``test_episodes`` episodes side by side (several passes if there are fewer boards than episodes); score and loss
+    accumulate on the device and are read once at the end."""
+
+    def __init__(self, test_env, args, device):
+        self.test_env = test_env
+        self.batch_size, self.chunk_size, self.update_iter = args.batch_size, args.chunk_size, args.update_iter
+        self.test_episodes, self.gamma, self.grad_clip_norm = args.test_episodes, args.gamma, args.grad_clip_norm
+        self.device = device
+
+    @torch.no_grad()
+    def execute(self, behavior_network, target_network):
+        env, dev = self.test_env, self.device
+        N = env.n_envs
+        score = torch.zeros((), dtype=torch.float64, device=dev)
+        iter_loss = torch.zeros((), dtype=torch.float64, device=dev)
+        left = self.test_episodes
+        while left > 0:
+            count = torch.arange(N, device=dev) < left             # boards that stand for an episode in this pass
+            state = env.reset()
+            hidden, target_hidden = behavior_network.init_hidden(N), target_network.init_hidden(N)
+            alive = count.clone()
+            for _ in range(env.max_steps):
+                action, next_hidden, behavior_q = behavior_network.sample_action(state, hidden, epsilon=0)
+                next_state, reward, done = env.step(action)
+                target_q, target_hidden = target_network(next_state, target_hidden)
+                done_env = done.all(1)
+                td = cal_td_error(action, reward, done_env.float(), behavior_q, target_q, self.gamma)
+                iter_loss += (td.double() ** 2 * alive).sum()
+                score += (reward.sum(1).double() * alive).sum()
+                alive = alive & ~done_env
+                state, hidden = next_state, next_hidden
+            left -= N
+        return float(score) / self.test_episodes, float(iter_loss) / self.test_episodes
+
+
 class SumTree:
     """Heap-ordered float64 sum tree on the device (same node numbering as the reference)."""
 

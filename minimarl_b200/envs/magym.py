@@ -41,8 +41,26 @@ class MaGymEnv:
         rewards = [table.get(r, r) for r in rew[0].cpu().tolist()]
         return obs[0].cpu().tolist(), rewards, done[0].cpu().tolist(), {}
 
-    def render(self, *args, **kwargs):
-        return None
+    def render(self, mode="human", *args, **kwargs):
+        """Text picture of the board decoded from the device state (the reference only calls ``env.render()`` on its
+        eval path, offpolicy/runner/shared/magym_runner.py:72-73): ``R`` apple, ``Y`` lemon, ``1``/``2``.. agents.
+        Printed for ``mode="human"``, returned as a string otherwise."""
+        env = self._env
+        rows, cols = env.grid_shape
+        grid = [["." for _ in range(cols)] for _ in range(rows)]
+        if hasattr(env, "food_bitmap"):
+            food = int(env.food_bitmap()[0].item())
+            for r in range(rows):
+                for c in range(cols):
+                    if food >> (r * 8 + c) & 1:
+                        grid[r][c] = "R" if (r + c) % 2 == 0 else "Y"
+        for i, (r, c) in enumerate(env.positions()[0].cpu().tolist()):
+            grid[r][c] = str(i + 1)
+        text = "\n".join(" ".join(row) for row in grid)
+        if mode == "human":
+            print(text)
+            return None
+        return text
 
     def close(self):
         return None

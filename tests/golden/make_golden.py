@@ -540,8 +540,39 @@ def golden_vdn_toplevel():
     print("toplevel.npz", len(out), "arrays; vdn train loss", float(out["train_loss"]))
 
 
+def golden_vdn_test():
+    """vdn/_test.py Test.execute (the eval adaptor) run by the reference itself on the oracle env:
+    greedy episodes of reference Q_Nets with recorded weights -> (score, TD loss)."""
+    Box, Discrete = install_gym_stub()
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle.ma_gym_ref import CheckersRef
+    out = {}
+    with ref_package("vdn"):
+        from _config import get_config
+        from _network import Q_Net
+        from _test import Test
+        args = get_config().parse_known_args([])[0]
+        args.use_cuda, args.test_episodes = False, 2
+        for seed, max_step in ((21, 40), (22, 100)):
+            torch.manual_seed(seed)
+            env = CheckersRef(full_observable=True, max_steps=max_step, step_cost=args.step_cost)
+            obs_space = [Box(np.zeros(94), np.ones(94)) for _ in range(2)]
+            act_space = [Discrete(5) for _ in range(2)]
+            beh, tgt = Q_Net(obs_space, act_space, args), Q_Net(obs_space, act_space, args)
+            beh.device = tgt.device = torch.device("cpu")
+            score, loss = Test(env, args, torch.device("cpu")).execute(behavior_network=beh, target_network=tgt)
+            tag = f"s{seed}_"
+            out.update(sd_numpy(beh, tag + "beh."))
+            out.update(sd_numpy(tgt, tag + "tgt."))
+            out[tag + "score"], out[tag + "loss"], out[tag + "max_step"] = np.array(float(score)), np.array(float(loss)), np.array(max_step)
+        out["gamma"], out["step_cost"], out["test_episodes"] = np.array(args.gamma), np.array(args.step_cost), np.array(2)
+        out["use_recurrent"] = np.array(bool(args.use_recurrent))
+    np.savez_compressed(os.path.join(OUT, "vdn_test.npz"), **out)
+    print("vdn_test.npz", {k: float(out[k]) for k in out if k.endswith(("score", "loss"))})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gae", "per", "nets", "logs", "mappo_buffer", "mappo_train", "toplevel"]
+    which = sys.argv[1:] or ["gae", "per", "nets", "logs", "mappo_buffer", "mappo_train", "toplevel", "vdn_test"]
     if "gae" in which:
         golden_gae()
     if "per" in which:
@@ -556,3 +587,5 @@ if __name__ == "__main__":
         golden_mappo_train()
     if "toplevel" in which:
         golden_vdn_toplevel()
+    if "vdn_test" in which:
+        golden_vdn_test()

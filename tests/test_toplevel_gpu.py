@@ -124,3 +124,45 @@ def test_qmix_toplevel_train_runs_with_lockstep_envs(cuda):
     opt = torch.optim.Adam(list(q.parameters()) + list(mix.parameters()), lr=1e-3)
     loss = Train_dqn(args, cuda).train(per, q, mix, tq, tmix, opt, 0.5)
     assert torch.isfinite(loss)
+
+
+def test_eval_adaptor_matches_reference_test_execute(cuda):
+    """``Test.execute`` (vdn/_test.py) recorded from the reference on the oracle env (tests/golden/vdn_test.npz):
+    greedy score exact (sums of the same float rewards), TD loss 1e-4 relative (fp32 network on GPU vs CPU)."""
+    import argparse
+    from minimarl_b200 import BatchedCheckers
+    from minimarl_b200.algorithms import Q_Net, Test
+    g = np.load(os.path.join(GOLDEN, "vdn_test.npz"))
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for tag in ("s21_", "s22_"):
+            args = argparse.Namespace(use_recurrent=bool(g["use_recurrent"]), batch_size=8, chunk_size=10, update_iter=2,
+                                      test_episodes=int(g["test_episodes"]), gamma=float(g["gamma"]), grad_clip_norm=5)
+            env = BatchedCheckers(int(g["test_episodes"]), full_observable=True, max_steps=int(g[tag + "max_step"]),
+                                  step_cost=float(g["step_cost"]), device=cuda)
+            nets = []
+            for name in ("beh.", "tgt."):
+                net = Q_Net(env.observation_space, env.action_space, args).to(cuda)
+                net.load_state_dict({k[len(tag + name):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(tag + name)})
+                nets.append(net)
+            score, loss = Test(env, args, cuda).execute(nets[0], nets[1])
+            assert abs(score - float(g[tag + "score"])) < 1e-5, (score, float(g[tag + "score"]))
+            assert abs(loss - float(g[tag + "loss"])) < 1e-4 * float(g[tag + "loss"]), (loss, float(g[tag + "loss"]))
+        # one board, two episodes: two passes give the same averages
+        env1 = BatchedCheckers(1, full_observable=True, max_steps=int(g["s22_max_step"]), step_cost=float(g["step_cost"]), device=cuda)
+        s1, l1 = Test(env1, args, cuda).execute(nets[0], nets[1])
+        assert abs(s1 - score) < 1e-6 and abs(l1 - loss) < 1e-5 * loss
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def test_render_shim(cuda):
+    import minimarl_b200
+    env = minimarl_b200.make("ma_gym:Checkers-v0", max_steps=10, step_cost=-0.01, full_observable=False)
+    env.reset()
+    text = env.render(mode="ansi")
+    rows = text.split("\n")
+    assert len(rows) == 3 and rows[0].split() == ["R", "Y", "R", "Y", "R", "Y", "1", "."] and rows[2].split()[6] == "2"
+    env.step([1, 4])                                    # agent 1 moves left onto the lemon at (0, 5)
+    assert env.render(mode="ansi").split("\n")[0].split() == ["R", "Y", "R", "Y", "R", "1", ".", "."]
