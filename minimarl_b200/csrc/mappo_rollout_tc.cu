@@ -36,11 +36,14 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-__device__ __forceinline__ float sigmoid_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// MUFU.TANH (one special-function op; abs error ~5e-4, below the tf32 operand rounding); sigmoid through the same unit --
+// the same activations as the PPO trunk kernels that re-evaluate these networks during the update
 __device__ __forceinline__ float tanh_(float x) {
-    const float e = __expf(-2.0f * fabsf(x));
-    return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
+__device__ __forceinline__ float sigmoid_(float x) { return fmaf(tanh_(0.5f * x), 0.5f, 0.5f); }
 
 // Parameter buffer (floats), per network k in {0 actor, 1 critic} unless noted:
 //   w1 [2][H][K1] (LayerNorm(47) affine folded in, zero-padded), w2 [2][H][H], wih [2][3H][H], whh [2][3H][H]   (matrices)
