@@ -71,6 +71,7 @@ __host__ __device__ inline Layout make_layout() {
 constexpr int XS = 152;   // row stride of the saved-operand matrix X: x0 [0,48) x1 [48,80) x2 [80,112) hp [112,144) 1 [144] 0 [145,152)
 constexpr int GS = 192;   // row stride of the gradient matrix G: dA1 [0,32) dA2 [32,64) dGi [64,160) dGh_n [160,192)
 // per-CTA column-sum accumulators: S[o][j] = sum_r dout[r][o] * xhat3[r][j] (NOMAX x H), dbo (NOMAX), dgamma2 (H), dgamma1 (H)
+constexpr int kTmemS = 5;   // head outputs whose S rows are accumulated in TMEM (the rest, if any, by warp shuffles per step)
 constexpr int ACC_S = 0, ACC_BO = NOMAX * H, ACC_G2 = ACC_BO + NOMAX, ACC_G1 = ACC_G2 + H, ACC_N = ACC_G1 + H;
 
 struct Args {
@@ -208,7 +209,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = (warp & 3) * 32 + lane, part = warp >> 2, j0 = part * CPT;
 
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
+    constexpr uint32_t kTmemCols = BWD ? 512 : 256;
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, kTmemCols);
     if (tid == 0) tc::mbar_init(&bar, 1);
     auto stage = [&](uint8_t* dst, int off, int rows, int K) {
         for (int i = tid; i < rows * K; i += kThreads) {
@@ -240,6 +242,22 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
     const uint32_t tmem = tmem_slot;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t phase = 0, red_sel = 0;
+    // backward: running per-thread column partials live in the upper half of TMEM (64 columns per part: S[0..4] | dgamma2 |
+    // dgamma1 | dbo) and are reduced across rows once, at the end of the kernel
+    const uint32_t acc_addr = lane_addr + 256 + part * 64;
+    auto tmem_accumulate = [&](uint32_t col, const float (&v)[CPT]) {
+        float t8[CPT];
+        tc::tmem_ld8(acc_addr + col, t8);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) t8[j] += v[j];
+        tc::tmem_st8(acc_addr + col, t8);
+    };
+    if (BWD) {
+        const float zero8[CPT] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) tc::tmem_st8(acc_addr + c, zero8);
+        tc::tmem_wait_st();
+    }
     long long prof_t = clock64();
     float* acc = sAcc + (warp & 3) * ACC_N;               // this warp's row quarter
 
@@ -553,10 +571,11 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                             dy[j] = fmaf(dO[o], sP[L.wo + o * H + j0 + j], dy[j]);
                             p[j] = dO[o] * xh3[j];
                         }
-                        colsum8(p, acc + ACC_S + o * H + j0, lane);
+                        if (o < kTmemS) tmem_accumulate(8 * o, p);
+                        else            colsum8(p, acc + ACC_S + o * H + j0, lane);
                     }
                 }
-                if (part == 0) colsum8(dO, acc + ACC_BO, lane);
+                if (part == 0) tmem_accumulate(56, dO);
             }
             PROF(13);
             // LayerNorm(h) backward
@@ -626,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                     p[j] = dx[j] * xh2[j];
                     s += g[j]; q = fmaf(g[j], xh2[j], q);
                 }
-                colsum8(p, acc + ACC_G2 + j0, lane);
+                tmem_accumulate(40, p);
                 float S, Q;
                 row_sums(s, q, S, Q);
                 float da[CPT];
@@ -658,7 +677,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                     p[j] = dx[j] * xh1[j];
                     s += g[j]; q = fmaf(g[j], xh1[j], q);
                 }
-                colsum8(p, acc + ACC_G1 + j0, lane);
+                tmem_accumulate(48, p);
                 float S, Q;
                 row_sums(s, q, S, Q);
                 float da[CPT];
@@ -669,6 +688,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 }
                 store8_kmajor(sX1, row, j0, H, da);                  // staged through the (idle) X1 tile for a coalesced store
             }
+            tc::tmem_wait_st();
             __syncthreads();
             tile_to_global<H>(sX1, gtile, GS, n_valid, tid);
             PROF(12);
@@ -677,6 +697,19 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
         __syncthreads();           // the next tile's first fetch overwrites the staging region
     }
     if (BWD) {
+        float t8[CPT];
+        for (int o = 0; o < kTmemS && o < a.NO; ++o) {
+            tc::tmem_ld8(acc_addr + 8 * o, t8);
+            colsum8(t8, acc + ACC_S + o * H + j0, lane);
+        }
+        tc::tmem_ld8(acc_addr + 40, t8);
+        colsum8(t8, acc + ACC_G2 + j0, lane);
+        tc::tmem_ld8(acc_addr + 48, t8);
+        colsum8(t8, acc + ACC_G1 + j0, lane);
+        if (part == 0) {
+            tc::tmem_ld8(acc_addr + 56, t8);
+            colsum8(t8, acc + ACC_BO, lane);
+        }
         __syncthreads();
         float* dst = a.gacc + (size_t)blockIdx.x * ACC_N;
         for (int i = tid; i < ACC_N; i += kThreads)
@@ -684,7 +717,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+    if (warp == 0) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
 size_t trunk_smem(bool bwd) {
