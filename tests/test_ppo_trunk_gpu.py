@@ -133,3 +133,54 @@ def test_chunks_read_in_place_equal_gathered_chunks(cuda):
     finally:
         torch.backends.cuda.matmul.allow_tf32 = False
     assert torch.equal(out_lazy, out_full)
+
+
+def _trunk_ref(obs, h0, masks, p):
+    """Plain PyTorch statement of the trunk (float64 on CPU): LayerNorm -> [Linear ReLU LayerNorm] x2 -> GRU with the state
+    multiplied by masks[t] before every step -> LayerNorm -> Linear."""
+    import torch.nn.functional as F
+    L, R, D = obs.shape
+    ln = lambda x, w, b: F.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
+    x = ln(obs, p["ln0_w"], p["ln0_b"])
+    x = ln(torch.relu(x @ p["w1"].t() + p["b1"]), p["ln1_w"], p["ln1_b"])
+    x = ln(torch.relu(x @ p["w2"].t() + p["b2"]), p["ln2_w"], p["ln2_b"])
+    h, outs = h0, []
+    for t in range(L):
+        hp = h * masks[t].unsqueeze(-1)
+        gi, gh = x[t] @ p["wih"].t() + p["bih"], hp @ p["whh"].t() + p["bhh"]
+        r = torch.sigmoid(gi[:, :32] + gh[:, :32])
+        z = torch.sigmoid(gi[:, 32:64] + gh[:, 32:64])
+        n = torch.tanh(gi[:, 64:] + r * gh[:, 64:])
+        h = n + z * (hp - n)
+        outs.append(ln(h, p["ln3_w"], p["ln3_b"]) @ p["wo"].t() + p["bo"])
+    return torch.stack(outs)
+
+
+@pytest.mark.parametrize("L,R,D,NO", [(3, 200, 30, 8), (8, 129, 47, 1), (5, 128, 48, 6), (2, 1, 9, 3)])
+def test_trunk_op_general_shapes_against_plain_pytorch(cuda, L, R, D, NO):
+    """Input widths below 47 (zero padding), every head width 1..8 (more than 5 outputs take the per-step shuffle
+    reduction instead of the TMEM accumulators), ragged and single-row tiles."""
+    from minimarl_b200.nn.ppo_trunk import PARAM_ORDER, ppo_trunk
+    g = torch.Generator().manual_seed(L * 1000 + R + D + NO)
+    rn = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    p = dict(ln0_w=1 + 0.2 * rn(D), ln0_b=0.2 * rn(D), w1=rn(32, D) / D ** 0.5, b1=0.2 * rn(32), ln1_w=1 + 0.2 * rn(32),
+             ln1_b=0.2 * rn(32), w2=rn(32, 32) / 32 ** 0.5, b2=0.2 * rn(32), ln2_w=1 + 0.2 * rn(32), ln2_b=0.2 * rn(32),
+             wih=rn(96, 32) / 32 ** 0.5, whh=rn(96, 32) / 32 ** 0.5, bih=0.2 * rn(96), bhh=0.2 * rn(96),
+             ln3_w=1 + 0.2 * rn(32), ln3_b=0.2 * rn(32), wo=rn(NO, 32) / 32 ** 0.5, bo=0.2 * rn(NO))
+    obs, h0 = torch.rand((L, R, D), generator=g, dtype=torch.float64), 0.5 * rn(R, 32)
+    masks = (torch.rand((L, R), generator=g) > 0.25).double()
+    w = rn(L, R, NO)
+    pr = {k: v.clone().requires_grad_() for k, v in p.items()}
+    ref = _trunk_ref(obs, h0, masks, pr)
+    (ref * w).sum().backward()
+    pc = {k: v.float().to(cuda).requires_grad_() for k, v in p.items()}
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        out = ppo_trunk(obs.float().to(cuda), h0.float().to(cuda), masks.float().to(cuda), pc)
+        (out * w.float().to(cuda)).sum().backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+    assert float((out.detach().cpu().double() - ref.detach()).abs().max()) < 2e-2
+    for k in PARAM_ORDER:
+        rel = _rel(pc[k].grad.cpu().double(), pr[k].grad)
+        assert rel < 5e-2, (k, rel)
