@@ -347,7 +347,8 @@ int mm_mappo_rollout_tc(const float* params, uint32_t* env_state, float* obs, fl
  * mm_ppo_trunk_dims -> {XS, GS, n_acc, off_S, off_dbo, off_dgamma2, off_dgamma1, NOMAX}.
  * obs_row != NULL: the chunks are gathered in place -- obs is then a row table [*, D] (the rollout buffer's
  *   [T+1, N, A, D] storage) and step t of chunk r is table row obs_row[r] + t * obs_step_rows, which is how
- *   recurrent_generator (shared_buffer.py:318-427) addresses its chunks; nothing is materialised.
+ *   recurrent_generator (shared_buffer.py:318-427) addresses its chunks; nothing is materialised.  In this mode h0 and
+ *   masks are tables as well: h0 row obs_row[r] of [*, 32] (rnn_states storage), masks entry obs_row[r] + t * obs_step_rows.
  * fwd, training mode (X != NULL): stores the operands of the weight gradients into X [L*R, XS]:
  *   x0 (normalised obs) [0,48) | x1 [48,80) | x2 [80,112) | hp (masked input state) [112,144); the caller owns columns
  *   [144,XS) and sets X[:,144] = 1 so that the bias gradients fall out of the same GEMM.
@@ -366,8 +367,9 @@ int mm_ppo_trunk_set_prof(long long* dev_buf16);
 int mm_ppo_trunk_fwd(const float* params, const float* obs, const int64_t* obs_row, int64_t obs_step_rows, const float* h0,
                      const float* masks, float* out, float* h_final, float* X, int32_t L, int64_t R, int32_t D, int32_t NO,
                      void* stream);
-int mm_ppo_trunk_bwd(const float* params, const float* masks, const float* X, const float* dout, float* G,
-                     float* acc_partials, int32_t n_partials, int32_t L, int64_t R, int32_t D, int32_t NO, void* stream);
+int mm_ppo_trunk_bwd(const float* params, const int64_t* obs_row, int64_t obs_step_rows, const float* masks, const float* X,
+                     const float* dout, float* G, float* acc_partials, int32_t n_partials, int32_t L, int64_t R, int32_t D,
+                     int32_t NO, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PPO losses of R_MAPPO.ppo_update / cal_value_loss (mappo/algorithms/ramppo_network.py:70-171), one pass each.
@@ -379,17 +381,23 @@ int mm_ppo_trunk_bwd(const float* params, const float* masks, const float* X, co
  *   value fwd:  sums2 += {sum max(loss(ret - v), loss(ret - clipped v)) w, sum w}; ret = (returns - norm2[0]) * norm2[1]
  *               when norm2 != NULL (ValueNorm mean and 1/sqrt(var), device); Huber(delta) or e^2/2.
  *   value bwd:  dvalues = g1[0] * d(sum loss w)/dvalues.
+ * first != NULL: every per-row input except logits / values is a TABLE addressed like recurrent_generator's chunks --
+ *   row r = l * n_chunks + c reads entry first[c] + l * step_rows (the rollout buffer's [T, N, A, 1] storage as rows), so
+ *   no minibatch tensor is gathered.
  * ---------------------------------------------------------------------------------------------- */
 int mm_ppo_actor_loss_fwd(const float* logits, const float* actions, const float* old_logp, const float* adv,
-                          const float* active, float* logp_out, int64_t R, int32_t NA, float clip, double* sums4, void* stream);
+                          const float* active, float* logp_out, int64_t R, int32_t NA, float clip, double* sums4,
+                          const int64_t* first, int64_t step_rows, int64_t n_chunks, void* stream);
 int mm_ppo_actor_loss_bwd(const float* logits, const float* actions, const float* old_logp, const float* adv,
-                          const float* active, const float* g2, float* dlogits, int64_t R, int32_t NA, float clip, void* stream);
+                          const float* active, const float* g2, float* dlogits, int64_t R, int32_t NA, float clip,
+                          const int64_t* first, int64_t step_rows, int64_t n_chunks, void* stream);
 int mm_ppo_value_loss_fwd(const float* values, const float* value_preds, const float* returns, const float* active,
                           const float* norm2, int64_t R, float clip, float huber_delta, int32_t use_huber, int32_t use_clipped,
-                          double* sums2, void* stream);
+                          double* sums2, const int64_t* first, int64_t step_rows, int64_t n_chunks, void* stream);
 int mm_ppo_value_loss_bwd(const float* values, const float* value_preds, const float* returns, const float* active,
                           const float* norm2, const float* g1, float* dvalues, int64_t R, float clip, float huber_delta,
-                          int32_t use_huber, int32_t use_clipped, void* stream);
+                          int32_t use_huber, int32_t use_clipped, const int64_t* first, int64_t step_rows, int64_t n_chunks,
+                          void* stream);
 
 /* Column sums of a row-major float32 matrix x [rows, C] (C <= 256) accumulated into out [C] (caller zeroes): the bias
  * gradients of the learner's Linear / GRU layers (what autograd computes with dY.sum(0)). */

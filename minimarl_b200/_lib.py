@@ -85,16 +85,18 @@ SIGNATURES = {
     "mm_heaptree_sample": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "mm_heaptree_argmin_leaf": (C.c_int, [_P, C.c_int32, _P, _P]),
     "mm_colsum": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P]),
-    "mm_ppo_actor_loss_fwd": (C.c_int, [_P] * 6 + [C.c_int64, C.c_int32, C.c_float, _P, _P]),
-    "mm_ppo_actor_loss_bwd": (C.c_int, [_P] * 7 + [C.c_int64, C.c_int32, C.c_float, _P]),
-    "mm_ppo_value_loss_fwd": (C.c_int, [_P] * 5 + [C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P]),
-    "mm_ppo_value_loss_bwd": (C.c_int, [_P] * 7 + [C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_int32, _P]),
+    "mm_ppo_actor_loss_fwd": (C.c_int, [_P] * 6 + [C.c_int64, C.c_int32, C.c_float, _P, _P, C.c_int64, C.c_int64, _P]),
+    "mm_ppo_actor_loss_bwd": (C.c_int, [_P] * 7 + [C.c_int64, C.c_int32, C.c_float, _P, C.c_int64, C.c_int64, _P]),
+    "mm_ppo_value_loss_fwd": (C.c_int, [_P] * 5 + [C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P, C.c_int64,
+                                         C.c_int64, _P]),
+    "mm_ppo_value_loss_bwd": (C.c_int, [_P] * 7 + [C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, C.c_int64,
+                                         C.c_int64, _P]),
     "mm_ppo_trunk_param_count": (C.c_int, []),
     "mm_ppo_trunk_param_offsets": (C.c_int, [_P]),
     "mm_ppo_trunk_max_ctas": (C.c_int, []),
     "mm_ppo_trunk_set_prof": (C.c_int, [_P]),
     "mm_ppo_trunk_fwd": (C.c_int, [_P, _P, _P, C.c_int64] + [_P] * 5 + [C.c_int32, C.c_int64, C.c_int32, C.c_int32, _P]),
-    "mm_ppo_trunk_bwd": (C.c_int, [_P] * 6 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "mm_ppo_trunk_bwd": (C.c_int, [_P, _P, C.c_int64] + [_P] * 5 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _P]),
     "mm_ppo_trunk_dims": (C.c_int, [_P]),
     "mm_tc_raw_selftest": (C.c_int, [_P, _P, _P] + [C.c_int32] * 10 + [_P]),
     "mm_mappo_rollout_param_count": (C.c_int, []),

@@ -211,9 +211,10 @@ class _FusedTrunk(nn.Module):
         """obs [L*N, D] (step-major), rnn_states [N, 1, H], masks [L*N, 1] -> head output [L*N, n_out]."""
         N = rnn_states.size(0)
         Lc = obs.size(0) // N
-        if not isinstance(obs, ChunkRows):
-            obs = obs.view(Lc, N, -1)
-        out = ppo_trunk(obs, rnn_states[:, 0, :], masks.view(Lc, N), self._trunk_params())
+        if isinstance(obs, ChunkRows):                 # chunks addressed in place in the rollout buffer (all three)
+            out = ppo_trunk(obs, rnn_states, masks, self._trunk_params())
+        else:
+            out = ppo_trunk(obs.view(Lc, N, -1), rnn_states[:, 0, :], masks.view(Lc, N), self._trunk_params())
         return out.view(Lc * N, -1)
 
     def _agentq_state(self):
@@ -395,7 +396,7 @@ class R_MAPPO:
         if self._fused_loss and values.is_cuda:
             norm = None
             if self._use_valuenorm:
-                self.value_normalizer.update(return_batch)
+                self.value_normalizer.update(return_batch.gather() if isinstance(return_batch, ChunkRows) else return_batch)
                 mean, var = self.value_normalizer.running_mean_var()
                 norm = torch.cat([mean.reshape(1), torch.rsqrt(var).reshape(1)]).to(torch.float32)
             return ppo_value_loss(values, value_preds_batch, return_batch,
@@ -426,8 +427,10 @@ class R_MAPPO:
         if (self._fused_loss and available_actions_batch is None and hasattr(actor, "_chunk_fusable")
                 and actor._chunk_fusable(to(obs_batch), to(rnn_states_batch))):
             return self._ppo_update_fused(sample, update_actor)
-        if isinstance(obs_batch, ChunkRows):
-            share_obs_batch, obs_batch = share_obs_batch.gather(), obs_batch.gather()
+        if isinstance(obs_batch, ChunkRows):             # eager path: materialise the minibatch the generator only addressed
+            (share_obs_batch, obs_batch, rnn_states_batch, rnn_states_critic_batch, actions_batch, value_preds_batch,
+             return_batch, masks_batch, active_masks_batch, old_action_log_probs_batch, adv_targ) = \
+                [x.gather() for x in sample[:11]]
         values, action_log_probs, dist_entropy = self.policy.evaluate_actions(
             share_obs_batch, obs_batch, rnn_states_batch, rnn_states_critic_batch, actions_batch, masks_batch,
             available_actions_batch, active_masks_batch)
@@ -478,8 +481,8 @@ class R_MAPPO:
         if critic._chunk_fusable(to(share_obs_batch), to(rnn_states_critic_batch)):
             values = critic._fused_chunks(to(share_obs_batch), to(rnn_states_critic_batch), to(masks_batch))
         else:
-            cent = share_obs_batch.gather() if isinstance(share_obs_batch, ChunkRows) else share_obs_batch
-            values, _ = critic(cent, rnn_states_critic_batch, masks_batch)
+            g = lambda x: x.gather() if isinstance(x, ChunkRows) else x
+            values, _ = critic(g(share_obs_batch), g(rnn_states_critic_batch), g(masks_batch))
         value_loss = self.cal_value_loss(values, to(value_preds_batch), to(return_batch), to(active_masks_batch))
         self.policy.critic_optimizer.zero_grad()
         (value_loss * self.value_loss_coef).backward()

@@ -155,20 +155,23 @@ class SharedReplayBuffer(object):
         steps = torch.arange(L, device=self.device)
         for i in range(num_mini_batch):
             chunk = rand[i * mini_batch_size:(i + 1) * mini_batch_size]
-            f = (chunk * L).unsqueeze(0) + steps.unsqueeze(1)               # [L, Nc] flat (env, agent, t) rows
-            env, agent, t = f // (A * T), (f // T) % A, f % T
-            take = lambda x: x[t, env, agent].reshape(L * mini_batch_size, *x.shape[3:])
             f0 = chunk * L
             env0, agent0, t0 = f0 // (A * T), (f0 // T) % A, f0 % T
             if lazy_obs and T % L == 0:
-                # the fused update reads the chunks in place: first row of every chunk in the [(T+1)*N*A, D] storage
+                # the fused update reads every chunk in place: one row map (first row of each chunk in the [rows, F] storage
+                # of a [T(+1), N, A, F] tensor, N * A rows per step) serves all eleven fields, nothing is gathered
                 from ..nn.ppo_trunk import ChunkRows
                 first = (t0 * N + env0) * A + agent0
-                rows = lambda x: ChunkRows(x.view(-1, x.shape[-1]), first, N * A, L)
-                share_b, obs_b = rows(self.share_obs), rows(self.obs)
-            else:
-                share_b, obs_b = take(self.share_obs), take(self.obs)
-            yield (share_b, obs_b, self.rnn_states[t0, env0, agent0],
+                rows = lambda x: ChunkRows(x.reshape(-1, x.shape[-1]), first, N * A, L)
+                state = lambda x: ChunkRows(x.reshape(-1, *x.shape[3:]), first, N * A, 1)
+                yield (rows(self.share_obs), rows(self.obs), state(self.rnn_states), state(self.rnn_states_critic),
+                       rows(self.actions), rows(self.value_preds), rows(self.returns), rows(self.masks),
+                       rows(self.active_masks), rows(self.action_log_probs), rows(adv), None)
+                continue
+            f = f0.unsqueeze(0) + steps.unsqueeze(1)                        # [L, Nc] flat (env, agent, t) rows
+            env, agent, t = f // (A * T), (f // T) % A, f % T
+            take = lambda x: x[t, env, agent].reshape(L * mini_batch_size, *x.shape[3:])
+            yield (take(self.share_obs), take(self.obs), self.rnn_states[t0, env0, agent0],
                    self.rnn_states_critic[t0, env0, agent0], take(self.actions), take(self.value_preds),
                    take(self.returns), take(self.masks), take(self.active_masks), take(self.action_log_probs),
                    take(adv), None)

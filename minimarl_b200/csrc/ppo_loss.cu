@@ -11,6 +11,18 @@
 namespace {
 
 constexpr int kBlock = 256;
+
+// Per-row inputs are either dense [R] vectors (first == null) or tables addressed like the data chunks of
+// recurrent_generator: row r = l * n_chunks + c lives at table entry first[c] + l * step.
+struct RowMap {
+    const long long* first;
+    long long step, n_chunks;
+    __device__ __forceinline__ long long operator()(long long r) const {
+        if (!first) return r;
+        const long long l = r / n_chunks;
+        return first[r - l * n_chunks] + l * step;
+    }
+};
 constexpr int kMaxNA = 8;
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -74,13 +86,14 @@ __device__ __forceinline__ ActorRow actor_row(const float* __restrict__ logits, 
 __global__ void __launch_bounds__(kBlock) actor_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ actions,
                                                           const float* __restrict__ old_logp, const float* __restrict__ adv,
                                                           const float* __restrict__ active, float* __restrict__ logp_out,
-                                                          long long R, int NA, float clip, double* __restrict__ sums) {
+                                                          long long R, int NA, float clip, double* __restrict__ sums, RowMap map) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (long long r = (long long)blockIdx.x * kBlock + threadIdx.x; r < R; r += (long long)gridDim.x * kBlock) {
-        const ActorRow o = actor_row(logits, r, NA, actions[r]);
-        const float w = active ? active[r] : 1.0f;
-        const float imp = expf(o.logp_act - old_logp[r]);
-        const float s1 = imp * adv[r], s2 = fminf(fmaxf(imp, 1.0f - clip), 1.0f + clip) * adv[r];
+        const long long i = map(r);
+        const ActorRow o = actor_row(logits, r, NA, actions[i]);
+        const float w = active ? active[i] : 1.0f;
+        const float imp = expf(o.logp_act - old_logp[i]);
+        const float s1 = imp * adv[i], s2 = fminf(fmaxf(imp, 1.0f - clip), 1.0f + clip) * adv[i];
         if (logp_out) logp_out[r] = o.logp_act;
         acc[0] += (double)(fminf(s1, s2) * w);
         acc[1] += (double)(o.ent * w);
@@ -94,12 +107,13 @@ __global__ void __launch_bounds__(kBlock) actor_fwd_kernel(const float* __restri
 __global__ void __launch_bounds__(kBlock) actor_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ actions,
                                                           const float* __restrict__ old_logp, const float* __restrict__ adv,
                                                           const float* __restrict__ active, const float* __restrict__ g,
-                                                          float* __restrict__ dlogits, long long R, int NA, float clip) {
+                                                          float* __restrict__ dlogits, long long R, int NA, float clip, RowMap map) {
     const float g_min = g[0], g_ent = g[1];
     for (long long r = (long long)blockIdx.x * kBlock + threadIdx.x; r < R; r += (long long)gridDim.x * kBlock) {
-        const ActorRow o = actor_row(logits, r, NA, actions[r]);
-        const float w = active ? active[r] : 1.0f;
-        const float imp = expf(o.logp_act - old_logp[r]), A = adv[r];
+        const long long i = map(r);
+        const ActorRow o = actor_row(logits, r, NA, actions[i]);
+        const float w = active ? active[i] : 1.0f;
+        const float imp = expf(o.logp_act - old_logp[i]), A = adv[i];
         const float lo = 1.0f - clip, hi = 1.0f + clip;
         const float s1 = imp * A, s2 = fminf(fmaxf(imp, lo), hi) * A;
         const bool inside = imp >= lo && imp <= hi;          // clamp passes the gradient on the closed interval
@@ -139,15 +153,16 @@ __device__ __forceinline__ float err_grad(float e, const ValueCfg& c) {
 __global__ void __launch_bounds__(kBlock) value_fwd_kernel(const float* __restrict__ values, const float* __restrict__ value_preds,
                                                           const float* __restrict__ returns, const float* __restrict__ active,
                                                           const float* __restrict__ norm, long long R, ValueCfg c,
-                                                          double* __restrict__ sums) {
+                                                          double* __restrict__ sums, RowMap map) {
     const float mean = norm ? norm[0] : 0.f, istd = norm ? norm[1] : 1.f;
     double acc[2] = {0.0, 0.0};
     for (long long r = (long long)blockIdx.x * kBlock + threadIdx.x; r < R; r += (long long)gridDim.x * kBlock) {
-        const float v = values[r], vp = value_preds[r];
-        const float ret = norm ? (returns[r] - mean) * istd : returns[r];
+        const long long i = map(r);
+        const float v = values[r], vp = value_preds[i];
+        const float ret = norm ? (returns[i] - mean) * istd : returns[i];
         const float vc = vp + fminf(fmaxf(v - vp, -c.clip), c.clip);
         const float lo = err_loss(ret - v, c), lc = err_loss(ret - vc, c);
-        const float w = active ? active[r] : 1.0f;
+        const float w = active ? active[i] : 1.0f;
         acc[0] += (double)((c.clipped ? fmaxf(lo, lc) : lo) * w);
         acc[1] += (double)w;
     }
@@ -157,11 +172,12 @@ __global__ void __launch_bounds__(kBlock) value_fwd_kernel(const float* __restri
 __global__ void __launch_bounds__(kBlock) value_bwd_kernel(const float* __restrict__ values, const float* __restrict__ value_preds,
                                                           const float* __restrict__ returns, const float* __restrict__ active,
                                                           const float* __restrict__ norm, const float* __restrict__ g,
-                                                          float* __restrict__ dvalues, long long R, ValueCfg c) {
+                                                          float* __restrict__ dvalues, long long R, ValueCfg c, RowMap map) {
     const float mean = norm ? norm[0] : 0.f, istd = norm ? norm[1] : 1.f, gs = g[0];
     for (long long r = (long long)blockIdx.x * kBlock + threadIdx.x; r < R; r += (long long)gridDim.x * kBlock) {
-        const float v = values[r], vp = value_preds[r];
-        const float ret = norm ? (returns[r] - mean) * istd : returns[r];
+        const long long i = map(r);
+        const float v = values[r], vp = value_preds[i];
+        const float ret = norm ? (returns[i] - mean) * istd : returns[i];
         const float d = v - vp;
         const float vc = vp + fminf(fmaxf(d, -c.clip), c.clip);
         const float eo = ret - v, ec = ret - vc;
@@ -170,7 +186,7 @@ __global__ void __launch_bounds__(kBlock) value_bwd_kernel(const float* __restri
         const float gc = (d >= -c.clip && d <= c.clip) ? -err_grad(ec, c) : 0.0f;
         float gv = go;
         if (c.clipped) gv = lo > lc ? go : (lo < lc ? gc : 0.5f * (go + gc));
-        dvalues[r] = gv * gs * (active ? active[r] : 1.0f);
+        dvalues[r] = gv * gs * (active ? active[i] : 1.0f);
     }
 }
 
@@ -183,40 +199,50 @@ int grid_for(long long R) {
 
 extern "C" int mm_ppo_actor_loss_fwd(const float* logits, const float* actions, const float* old_logp, const float* adv,
                                      const float* active, float* logp_out, int64_t R, int32_t NA, float clip, double* sums4,
-                                     void* stream) {
+                                     const int64_t* first, int64_t step_rows, int64_t n_chunks, void* stream) {
     if (!logits || !actions || !old_logp || !adv || !sums4 || R <= 0) return MM_ERR_BAD_ARG;
     if (NA < 1 || NA > kMaxNA) return MM_ERR_UNSUPPORTED;
+    if (first && (n_chunks <= 0 || R % n_chunks)) return MM_ERR_BAD_ARG;
+    const RowMap map{reinterpret_cast<const long long*>(first), step_rows, n_chunks};
     actor_fwd_kernel<<<grid_for(R), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(logits, actions, old_logp, adv, active,
-                                                                                  logp_out, R, NA, clip, sums4);
+                                                                                  logp_out, R, NA, clip, sums4, map);
     return mm::check_launch();
 }
 
 extern "C" int mm_ppo_actor_loss_bwd(const float* logits, const float* actions, const float* old_logp, const float* adv,
                                      const float* active, const float* g2, float* dlogits, int64_t R, int32_t NA, float clip,
-                                     void* stream) {
+                                     const int64_t* first, int64_t step_rows, int64_t n_chunks, void* stream) {
     if (!logits || !actions || !old_logp || !adv || !g2 || !dlogits || R <= 0) return MM_ERR_BAD_ARG;
     if (NA < 1 || NA > kMaxNA) return MM_ERR_UNSUPPORTED;
+    if (first && (n_chunks <= 0 || R % n_chunks)) return MM_ERR_BAD_ARG;
+    const RowMap map{reinterpret_cast<const long long*>(first), step_rows, n_chunks};
     actor_bwd_kernel<<<grid_for(R), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(logits, actions, old_logp, adv, active, g2,
-                                                                                  dlogits, R, NA, clip);
+                                                                                  dlogits, R, NA, clip, map);
     return mm::check_launch();
 }
 
 extern "C" int mm_ppo_value_loss_fwd(const float* values, const float* value_preds, const float* returns, const float* active,
                                      const float* norm2, int64_t R, float clip, float huber_delta, int32_t use_huber,
-                                     int32_t use_clipped, double* sums2, void* stream) {
+                                     int32_t use_clipped, double* sums2, const int64_t* first, int64_t step_rows,
+                                     int64_t n_chunks, void* stream) {
     if (!values || !value_preds || !returns || !sums2 || R <= 0) return MM_ERR_BAD_ARG;
+    if (first && (n_chunks <= 0 || R % n_chunks)) return MM_ERR_BAD_ARG;
     const ValueCfg c{clip, huber_delta, use_huber, use_clipped};
+    const RowMap map{reinterpret_cast<const long long*>(first), step_rows, n_chunks};
     value_fwd_kernel<<<grid_for(R), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(values, value_preds, returns, active, norm2, R,
-                                                                                  c, sums2);
+                                                                                  c, sums2, map);
     return mm::check_launch();
 }
 
 extern "C" int mm_ppo_value_loss_bwd(const float* values, const float* value_preds, const float* returns, const float* active,
                                      const float* norm2, const float* g1, float* dvalues, int64_t R, float clip,
-                                     float huber_delta, int32_t use_huber, int32_t use_clipped, void* stream) {
+                                     float huber_delta, int32_t use_huber, int32_t use_clipped, const int64_t* first,
+                                     int64_t step_rows, int64_t n_chunks, void* stream) {
     if (!values || !value_preds || !returns || !g1 || !dvalues || R <= 0) return MM_ERR_BAD_ARG;
+    if (first && (n_chunks <= 0 || R % n_chunks)) return MM_ERR_BAD_ARG;
     const ValueCfg c{clip, huber_delta, use_huber, use_clipped};
+    const RowMap map{reinterpret_cast<const long long*>(first), step_rows, n_chunks};
     value_bwd_kernel<<<grid_for(R), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(values, value_preds, returns, active, norm2, g1,
-                                                                                  dvalues, R, c);
+                                                                                  dvalues, R, c, map);
     return mm::check_launch();
 }

@@ -77,10 +77,10 @@ constexpr int ACC_S = 0, ACC_BO = NOMAX * H, ACC_G2 = ACC_BO + NOMAX, ACC_G1 = A
 struct Args {
     const float* params;
     const float* obs;      // [L][R][D], or (obs_row != null) a row table [*][D] addressed through obs_row
-    const long long* obs_row;   // [R] first-step row of every chunk in the table, or null          (forward)
-    long long obs_step;    // rows between consecutive steps of a chunk in the table                   (forward)
-    const float* h0;       // [R][H]                      (forward)
-    const float* masks;    // [L][R] or null
+    const long long* obs_row;   // [R] first-step row of every chunk in the tables, or null
+    long long obs_step;    // rows between consecutive steps of a chunk in the tables
+    const float* h0;       // [R][H]; with obs_row: table [*][H], row obs_row[r]             (forward)
+    const float* masks;    // [L][R] or null; with obs_row: table [*], entry obs_row[r] + t * obs_step
     float* out;            // [L][R][NO]                  (forward)
     float* h_final;        // [R][H] or null              (forward)
     float* X;              // [L*R][XS]  forward writes columns [0,144) (may be null = inference); backward reads hp
@@ -354,12 +354,12 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
         float h[CPT];          // forward: carried hidden state; backward: gradient carried to the previous step
 #pragma unroll
         for (int j = 0; j < CPT; ++j) h[j] = 0.f;
+        if (a.obs_row) {
+            if (tid < kRows) sRowBase[tid] = a.obs_row[row0 + min(tid, n_valid - 1)];
+            __syncthreads();
+        }
         if (!BWD) {
-            load8_global(a.h0 + grow * H + j0, h);
-            if (a.obs_row) {
-                if (tid < n_valid) sRowBase[tid] = a.obs_row[row0 + tid];
-                __syncthreads();
-            }
+            load8_global(a.obs_row ? a.h0 + sRowBase[row] * H + j0 : a.h0 + grow * H + j0, h);
             fetch_obs(row0, n_valid, 0);
         } else {
             // backward: the normalised observations and the input state of a step come straight from X into the operand tiles
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
         for (int step = 0; step < a.L; ++step) {
             const int t = BWD ? a.L - 1 - step : step;
             const long long tr = (long long)t * a.R + grow;
-            const float mask = a.masks ? a.masks[tr] : 1.0f;
+            const float mask = !a.masks ? 1.0f : a.obs_row ? a.masks[sRowBase[row] + (long long)t * a.obs_step] : a.masks[tr];
             float hp[CPT];
             // ---- F1. plain LayerNorm of the observation row -> X0 tile; masked input state -> Hp tile ----------------
             cp_async_wait_all();
@@ -789,7 +789,8 @@ extern "C" int mm_ppo_trunk_fwd(const float* params, const float* obs, const int
     return mm::check_launch();
 }
 
-extern "C" int mm_ppo_trunk_bwd(const float* params, const float* masks, const float* X, const float* dout,
+extern "C" int mm_ppo_trunk_bwd(const float* params, const int64_t* obs_row, int64_t obs_step_rows, const float* masks,
+                                const float* X, const float* dout,
                                 float* G, float* acc_partials, int32_t n_partials, int32_t L, int64_t R, int32_t D,
                                 int32_t NO, void* stream) {
     int rc = check_common(params, X, L, R, D, NO);
@@ -797,6 +798,7 @@ extern "C" int mm_ppo_trunk_bwd(const float* params, const float* masks, const f
     if (!X || !dout || !G || !acc_partials || !mm::aligned(X, 16) || !mm::aligned(G, 16)) return MM_ERR_BAD_ARG;
     Args a{};
     a.params = params; a.masks = masks; a.X = const_cast<float*>(X); a.dout = dout; a.G = G;
+    a.obs_row = reinterpret_cast<const long long*>(obs_row); a.obs_step = obs_step_rows;
     a.gacc = acc_partials; a.prof = g_prof;
     a.L = L; a.D = D; a.NO = NO; a.R = R; a.n_tiles = (R + kRows - 1) / kRows;
     const int ctas = n_ctas(a.n_tiles);

@@ -71,7 +71,7 @@ class _PPOTrunkFn(torch.autograd.Function):
         if rows is None:
             L, R, D = obs.shape
             row_index, step_rows = None, 0
-        else:                                   # obs is a row table, rows = (first-step row of every chunk, rows per step, L)
+        else:                                   # obs / h0 / masks are row tables, rows = (first row of every chunk, rows per step, L)
             row_index, step_rows, L = rows
             R, D = row_index.numel(), obs.shape[-1]
         NO = p["wo"].shape[0]
@@ -90,21 +90,22 @@ class _PPOTrunkFn(torch.autograd.Function):
         _lib.check(_lib.lib().mm_ppo_trunk_fwd(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(row_index), int(step_rows), _lib.ptr(h0),
                                                _lib.ptr(masks), _lib.ptr(out), None, _lib.ptr(X), L, R, D, NO, _lib.stream()))
         if train:
-            ctx.save_for_backward(packed, masks, X, *params)
-            ctx.dims = (L, R, D, NO)
+            ctx.save_for_backward(packed, masks, X, row_index if row_index is not None else packed.new_empty(0), *params)
+            ctx.dims = (L, R, D, NO, int(step_rows), row_index is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        packed, masks, X = ctx.saved_tensors[:3]
-        p = dict(zip(PARAM_ORDER, ctx.saved_tensors[3:]))
-        L, R, D, NO = ctx.dims
+        packed, masks, X, row_index = ctx.saved_tensors[:4]
+        p = dict(zip(PARAM_ORDER, ctx.saved_tensors[4:]))
+        L, R, D, NO, step_rows, lazy = ctx.dims
         d = dims()
         z = dict(dtype=torch.float32, device=X.device)
         G = torch.empty((L * R, d["GS"]), **z)
         n_part = _lib.lib().mm_ppo_trunk_max_ctas()
         partial = torch.zeros((n_part, d["n_acc"]), **z)
-        _lib.check(_lib.lib().mm_ppo_trunk_bwd(_lib.ptr(packed), _lib.ptr(masks), _lib.ptr(X),
+        _lib.check(_lib.lib().mm_ppo_trunk_bwd(_lib.ptr(packed), _lib.ptr(row_index if lazy else None), step_rows,
+                                               _lib.ptr(masks), _lib.ptr(X),
                                                _lib.ptr(dout.contiguous()), _lib.ptr(G), _lib.ptr(partial), n_part, L, R, D, NO,
                                                _lib.stream()))
         acc = partial.sum(0)
@@ -143,11 +144,14 @@ class ChunkRows:
 
 
 def ppo_trunk(obs, h0, masks, params):
-    """obs [L, R, D] (or ChunkRows), h0 [R, 32], masks [L, R] or None, params: dict keyed by PARAM_ORDER -> head output
-    [L, R, NO]."""
+    """obs [L, R, D], h0 [R, 32], masks [L, R] or None -- or all three as ChunkRows over the rollout buffer's storage (h0 with
+    L = 1) -- params: dict keyed by PARAM_ORDER -> head output [L, R, NO]."""
+    if isinstance(obs, ChunkRows):
+        if not isinstance(h0, ChunkRows):        # only the observations are addressed in place: gather would defeat it
+            raise TypeError("with ChunkRows observations, h0 and masks must be ChunkRows of the same row map")
+        assert h0.first is obs.first and masks.first is obs.first and masks.step_rows == obs.step_rows
+        return _PPOTrunkFn.apply(obs.table, h0.table, masks.table.reshape(-1), (obs.first.contiguous(), obs.step_rows, obs.L),
+                                 *[params[k] for k in PARAM_ORDER])
     h0 = h0.contiguous()
     masks = masks.contiguous() if masks is not None else None
-    if isinstance(obs, ChunkRows):
-        return _PPOTrunkFn.apply(obs.table, h0, masks, (obs.first.contiguous(), obs.step_rows, obs.L),
-                                 *[params[k] for k in PARAM_ORDER])
     return _PPOTrunkFn.apply(obs.contiguous(), h0, masks, None, *[params[k] for k in PARAM_ORDER])

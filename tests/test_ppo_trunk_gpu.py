@@ -122,9 +122,9 @@ def test_chunks_read_in_place_equal_gathered_chunks(cuda):
     perm = torch.randperm(T * N * 2 // Lc, generator=torch.Generator().manual_seed(1)).to(cuda)
     lazy = next(iter(buf.recurrent_generator(adv, 1, Lc, perm=perm, lazy_obs=True)))
     full = next(iter(buf.recurrent_generator(adv, 1, Lc, perm=perm)))
-    assert isinstance(lazy[1], ChunkRows) and torch.equal(lazy[1].gather(), full[1]) and torch.equal(lazy[0].gather(), full[0])
-    for a, b in zip(lazy[2:11], full[2:11]):
-        assert torch.equal(a, b)
+    assert all(isinstance(x, ChunkRows) for x in lazy[:11])
+    for a, b in zip(lazy[:11], full[:11]):                 # every field: the row map addresses exactly the gathered minibatch
+        assert torch.equal(a.gather(), b)
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
         with torch.no_grad():
@@ -133,6 +133,21 @@ def test_chunks_read_in_place_equal_gathered_chunks(cuda):
     finally:
         torch.backends.cuda.matmul.allow_tf32 = False
     assert torch.equal(out_lazy, out_full)
+    # the loss kernels through the same row map
+    from minimarl_b200.ops.ppo_loss import ppo_actor_loss, ppo_value_loss
+    logits = out_full.detach().clone().requires_grad_()
+    logits2 = out_full.detach().clone().requires_grad_()
+    a = ppo_actor_loss(logits, full[4], full[9], full[10], full[8], 0.2)
+    b = ppo_actor_loss(logits2, lazy[4], lazy[9], lazy[10], lazy[8], 0.2)
+    (a[0] - 0.01 * a[1]).backward(); (b[0] - 0.01 * b[1]).backward()
+    assert all(torch.equal(x, y) for x, y in zip(a, b)) and torch.equal(logits.grad, logits2.grad)
+    v = torch.randn(out_full.shape[0], 1, device=cuda)
+    v1, v2 = v.clone().requires_grad_(), v.clone().requires_grad_()
+    norm = torch.tensor([0.3, 1.7], device=cuda)
+    la = ppo_value_loss(v1, full[5], full[6], full[8], norm, 0.2, 10.0, True, True)
+    lb = ppo_value_loss(v2, lazy[5], lazy[6], lazy[8], norm, 0.2, 10.0, True, True)
+    la.backward(); lb.backward()
+    assert torch.equal(la, lb) and torch.equal(v1.grad, v2.grad)
 
 
 def _trunk_ref(obs, h0, masks, p):
