@@ -48,83 +48,103 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+_SAMPLER_CHILD = r"""
+import subprocess, sys, time
+idx = int(sys.argv[1])
+REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+try:
+    import pynvml as n
+    n.nvmlInit()
+    h = n.nvmlDeviceGetHandleByIndex(idx)
+    print("max", float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)), "nvml", flush=True)
+    while True:
+        mask = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        names = ",".join(v for b, v in REASONS.items() if mask & b) or "-"
+        print(time.monotonic(), float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), names, flush=True)
+        time.sleep(0.001)
+except ImportError:
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    first = True
+    while True:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", str(idx)],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        if first:
+            print("max", float(f[1]), "nvidia-smi", flush=True)
+            first = False
+        names = ",".join(nm for nm, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                              "sw_power_cap"], f[2:6]) if v.lower().startswith("active")) or "-"
+        print(time.monotonic(), float(f[0]), names, flush=True)
+"""
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region.
 
-    A background thread polls NVML (the library nvidia-smi itself uses) every ~2 ms, because the timed
-    region of a short run is shorter than nvidia-smi's fastest loop period; if NVML is not importable it
-    falls back to one `nvidia-smi --query-gpu=...` call per sample.
+    The timed region of a short run lasts milliseconds, and a sampling thread inside this process starves
+    behind the GIL while the main thread enqueues launches.  So the sampler is a separate PROCESS polling NVML
+    (the library nvidia-smi itself uses) at about 1 kHz and stamping every sample with CLOCK_MONOTONIC, which
+    is system-wide: the parent brackets the timed region with the same clock and keeps the samples inside it.
+    Without pynvml the child falls back to an `nvidia-smi --query-gpu=...` loop.
     """
-    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
-        import threading
-        self.samples, self.stamps, self.reasons, self.max_mhz = [], [], set(), None
+        import tempfile
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = gpu_index
+        if visible:
+            ids = visible.split(",")
+            if gpu_index < len(ids) and ids[gpu_index].strip().isdigit():
+                idx = int(ids[gpu_index])
         self.t_begin = self.t_end = None
-        self._stop = threading.Event()
-        self._nvml = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
-            self._nvml = pynvml
-        except Exception:
-            self._nvml = None
-        self._gpu = gpu_index
-        self._thread = threading.Thread(target=self._run, daemon=True)
-        self._thread.start()
-
-    def _sample_smi(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self._gpu)],
-                             capture_output=True, text=True, timeout=5).stdout
-        f = [x.strip() for x in out.strip().split(",")]
-        self.samples.append(float(f[0]))
-        self.stamps.append(time.perf_counter())
-        self.max_mhz = float(f[1])
-        for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
-            if v.lower().startswith("active"):
-                self.reasons.add(name)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                if self._nvml is not None:
-                    n = self._nvml
-                    self.samples.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
-                    self.stamps.append(time.perf_counter())
-                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
-                    for bit, name in self.REASONS.items():
-                        if mask & bit:
-                            self.reasons.add(name)
-                else:
-                    self._sample_smi()
-            except Exception as e:       # keep the benchmark alive, report the failure
-                self.reasons.add(f"sampler_error:{type(e).__name__}")
+        self._out = tempfile.NamedTemporaryFile("w+", suffix=".clocks", delete=False)
+        self._proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_CHILD, str(idx)], stdout=self._out,
+                                      stderr=subprocess.DEVNULL)
+        t0 = time.monotonic()
+        while time.monotonic() - t0 < 10.0 and self._proc.poll() is None:      # wait for the first sample
+            if os.path.getsize(self._out.name) > 40:
                 break
-            time.sleep(0.0005)
+            time.sleep(0.01)
 
     def mark_begin(self):
-        self.t_begin = time.perf_counter()
+        self.t_begin = time.monotonic()
 
     def mark_end(self):
-        self.t_end = time.perf_counter()
+        self.t_end = time.monotonic()
 
     def stop(self):
-        self._stop.set()
-        self._thread.join(timeout=10)
-        timed = [c for c, t in zip(self.samples, self.stamps)
-                 if self.t_begin is not None and self.t_end is not None and self.t_begin <= t <= self.t_end]
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
-                "samples_in_timed_region": len(timed),
-                "sm_mhz_timed_region": statistics.median(timed) if timed else None,
-                "window": "warm-up + timed region (GPU under load throughout)",
-                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
+        time.sleep(0.003)
+        self._proc.terminate()
+        try:
+            self._proc.wait(timeout=10)
+        except subprocess.TimeoutExpired:
+            self._proc.kill()
+        with open(self._out.name) as f:
+            lines = f.read().splitlines()
+        os.unlink(self._out.name)
+        max_mhz, source, samples, timed, reasons, timed_reasons = None, None, [], [], set(), set()
+        for ln in lines:
+            f = ln.split()
+            if len(f) != 3:
+                continue
+            if f[0] == "max":
+                max_mhz, source = float(f[1]), f[2]
+                continue
+            t, mhz = float(f[0]), float(f[1])
+            names = set() if f[2] == "-" else set(f[2].split(","))
+            samples.append(mhz)
+            reasons |= names
+            if self.t_begin is not None and self.t_end is not None and self.t_begin <= t <= self.t_end:
+                timed.append(mhz)
+                timed_reasons |= names
+        use = timed if timed else samples
+        return {"sm_mhz": statistics.median(use) if use else None, "sm_max_mhz": max_mhz,
+                "reasons": sorted(timed_reasons if timed else reasons), "samples": len(samples),
+                "samples_in_timed_region": len(timed), "sm_mhz_min_timed_region": min(timed) if timed else None,
+                "reasons_warmup_and_timed": sorted(reasons),
+                "window": "sm_mhz / reasons: samples inside the timed region (separate sampler process, ~1 kHz, "
+                          "CLOCK_MONOTONIC stamps)", "source": source}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -492,23 +512,41 @@ def run_ours(args, wl):
     agent_steps_per_step = n * T * A * world
     value = agent_steps_per_step * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: the list/numpy-facing env API with HOST buffers, copies inside the timed region ----
-    e2e_steps = min(T, 32)
-    host_acts = actions[:e2e_steps].cpu().numpy()
+    # ---- e2e: the numpy-facing env API with HOST buffers, every copy inside the timed region ----
+    # one e2e step = the same rollout as above for a caller holding host arrays: reset, then rollout_host (actions
+    # [T,N,A] from page-locked host memory -> obs / rewards / dones of all T steps back in host memory), H2D, kernels
+    # and D2H pipelined chunk by chunk inside mm_checkers_rollout_host
+    hb = env.host_buffers(T)
+    host_acts = hb["act"].numpy()
+    host_acts[...] = actions.cpu().numpy()
+    e2e_steps = max(1, min(args.steps, 20))
+    for _ in range(3):
+        env.reset()
+        env.rollout_host(host_acts)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        env.reset()
+        o_h, r_h, d_h = env.rollout_host(host_acts)      # returns after the last D2H landed (stream synchronised)
+    e2e_s = time.perf_counter() - t0
+    e2e_checksum = float(r_h.sum())                      # the host result is read
+    # the one-env-step-per-call variant (step_host: H2D, kernel, D2H, sync every env step), for comparison
+    sw_steps = min(T, 32)
     env.reset()
     for t in range(3):
         env.step_host(host_acts[t])
-    sync_all()
-    t0 = time.perf_counter()
-    for t in range(e2e_steps):
-        o_h, r_h, d_h = env.step_host(host_acts[t])      # H2D actions, kernel, D2H obs/rew/done, sync
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    for t in range(sw_steps):
+        env.step_host(host_acts[t])
+    sw_s = time.perf_counter() - t1
     if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([e2e_s, sw_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = n * A * e2e_steps * world / e2e_s
+        e2e_s, sw_s = float(t[0].item()), float(t[1].item())
+    e2e_value = n * A * T * e2e_steps * world / e2e_s
+    e2e_stepwise = n * A * sw_steps * world / sw_s
+    h2d_step, d2h_step = env.rollout_host_bytes(T)
 
     learner = mappo_it = None
     if not args.no_learner:             # on every rank: the update all-reduces its gradients when world > 1
@@ -552,9 +590,14 @@ def run_ours(args, wl):
                              "algorithmic_bytes_per_launch": n * T * A * (GAE_BYTES_PER_ELEM + 4)},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample,
                              "host_cores": cores, "c_port_1core": cpu_c},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step,
-                    "d2h_bytes_per_step": env.d2h_bytes_per_step,
-                    "api": "BatchedCheckers.step_host(numpy actions) -> numpy obs/rewards/dones, one env step per call"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                    "steps": e2e_steps, "ms_per_step": e2e_s * 1e3 / e2e_steps,
+                    "pcie_GBps": (h2d_step + d2h_step) * e2e_steps / e2e_s / 1e9, "result_checksum": e2e_checksum,
+                    "api": "BatchedCheckers.reset(); BatchedCheckers.rollout_host(numpy actions [T,N,A]) -> numpy obs / "
+                           "rewards / dones of all T steps (page-locked host arrays; mm_checkers_rollout_host pipelines "
+                           "H2D, kernel and D2H in chunks of 8 env steps); wall clock around the calls",
+                    "stepwise_value": e2e_stepwise,
+                    "stepwise_api": "BatchedCheckers.step_host: one env step per call, synchronised every step"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
@@ -573,7 +616,7 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mappo_rollout_16384x128", choices=sorted(WORKLOADS))

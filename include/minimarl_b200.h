@@ -88,6 +88,22 @@ int mm_checkers_rollout(uint32_t* state, const int32_t* actions, int32_t* action
                         int32_t T, uint64_t seed, uint64_t step_offset,
                         const mm_checkers_cfg* cfg_host, void* stream);
 
+/* The same rollout for a caller that holds HOST arrays, as the reference's runners do (they hand
+ * env.step host lists / numpy arrays: mappo/runner/shared/magym_runner.py:52-57,
+ * offpolicy/runner/shared/magym_runner.py:94-97).  `*_host` pointers are host memory (page-locked for
+ * the copies to overlap; pageable memory works but serialises), laid out like mm_checkers_rollout's
+ * tensors for all T steps.  `*_stage` are caller-owned DEVICE staging buffers for two chunks:
+ * actions_stage [2,chunk,N,2] int32, obs_stage [2,chunk,N,2,D], rewards_stage / dones_stage
+ * [2,chunk,N,2].  An output is skipped when both its host and stage pointers are NULL.  Steps are
+ * processed in chunks of `chunk`: H2D of the chunk's actions and its kernel on `stream`, D2H of its
+ * outputs on `copy_stream` (a different stream) while the next chunk computes.  On return `stream`
+ * has been made to wait for the last copy, so synchronising `stream` is enough. */
+int mm_checkers_rollout_host(uint32_t* state, const int32_t* actions_host, float* obs_host,
+                             float* rewards_host, uint8_t* dones_host, int32_t* actions_stage,
+                             float* obs_stage, float* rewards_stage, uint8_t* dones_stage,
+                             int32_t* bad_action_flag, int32_t T, int32_t chunk,
+                             const mm_checkers_cfg* cfg_host, void* stream, void* copy_stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Switch{2,4}-v0 (ma-gym 0.0.14 `Switch`, un-vendored; qmix default env, qmix/_config.py:13-18,
  * qmix/main.py:66-71).  State planes: 0 = agent cells (8 bits per agent), 1 = per-agent done bits,

@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
+    subprocess.check_call([NVCC, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB, *objs, "-lcudart"])
     return LIB
 
 

@@ -168,6 +168,50 @@ class BatchedCheckers(_BatchedBase):
             C.byref(self.cfg), _lib.stream()))
         return obs, rew, done.view(torch.bool)
 
+    # -- host-buffer rollout: numpy in / numpy out, copies pipelined against the kernel --------------
+    def host_buffers(self, T, chunk=8):
+        """Page-locked numpy arrays for ``rollout_host``: actions [T,N,A] int32 (fill it), obs [T,N,A,D] f32,
+        rewards [T,N,A] f32, dones [T,N,A] bool, plus the device staging for two chunks of ``chunk`` steps."""
+        key = (int(T), int(chunk))
+        if getattr(self, "_hostT", None) is None or self._hostT["key"] != key:
+            n, a, d = self.n_envs, self.n_agents, self.obs_dim
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+            dev = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.device)
+            self._hostT = dict(
+                key=key,
+                act=pin((T, n, a), torch.int32), obs=pin((T, n, a, d), torch.float32),
+                rew=pin((T, n, a), torch.float32), done=pin((T, n, a), torch.uint8),
+                s_act=dev((2, chunk, n, a), torch.int32), s_obs=dev((2, chunk, n, a, d), torch.float32),
+                s_rew=dev((2, chunk, n, a), torch.float32), s_done=dev((2, chunk, n, a), torch.uint8),
+                copy_stream=torch.cuda.Stream(device=self.device))
+        return self._hostT
+
+    def rollout_host(self, actions_np, chunk=8, want_obs=True):
+        """T lockstep steps for a caller holding HOST arrays (what the reference's runners hold):
+        ``actions_np`` [T,N,A] ints -> numpy (obs [T,N,A,D], rewards [T,N,A], dones [T,N,A] bool), views of
+        page-locked buffers that the next call overwrites.  H2D of the actions, the kernels and the D2H of the
+        outputs are pipelined chunk by chunk (``mm_checkers_rollout_host``); returns after the last copy landed.
+        Pass the ``host_buffers(T)["act"].numpy()`` array itself to skip the staging copy of the actions."""
+        T = int(np.shape(actions_np)[0])
+        h = self.host_buffers(T, chunk)
+        act = h["act"].numpy()
+        if not (isinstance(actions_np, np.ndarray) and np.shares_memory(actions_np, act)):
+            act[...] = np.asarray(actions_np).reshape(T, self.n_envs, self.n_agents)
+        cur = torch.cuda.current_stream(self.device)
+        h["copy_stream"].wait_stream(cur)
+        _lib.check(_lib.lib().mm_checkers_rollout_host(
+            _lib.ptr(self.state), h["act"].data_ptr(), h["obs"].data_ptr() if want_obs else None,
+            h["rew"].data_ptr(), h["done"].data_ptr(), _lib.ptr(h["s_act"]),
+            _lib.ptr(h["s_obs"]) if want_obs else None, _lib.ptr(h["s_rew"]), _lib.ptr(h["s_done"]),
+            _lib.ptr(self.bad_action), T, int(chunk), C.byref(self.cfg), cur.cuda_stream,
+            h["copy_stream"].cuda_stream))
+        cur.synchronize()
+        return (h["obs"].numpy() if want_obs else None), h["rew"].numpy(), h["done"].numpy().view(np.bool_)
+
+    def rollout_host_bytes(self, T):
+        """(H2D, D2H) bytes one ``rollout_host`` call of T steps moves over PCIe."""
+        return T * self.h2d_bytes_per_step, T * self.d2h_bytes_per_step
+
     # -- state decoding (tests, eval, render shims) -------------------------------------------------
     def positions(self):
         """[N, A, 2] (row, col) of every agent."""

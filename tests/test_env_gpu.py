@@ -254,3 +254,33 @@ def test_full_size_rollout_properties(cuda):
     obs_b, rew_b, done_b = env.rollout(T, actions=None, seed=42)
     assert torch.equal(obs, obs_b) and torch.equal(rew, rew_b) and torch.equal(done, done_b)
     assert torch.equal(env.reset(), obs0)
+
+
+@pytest.mark.parametrize("T,chunk,full", [(1, 8, False), (5, 8, False), (8, 8, True), (37, 8, False), (48, 5, True)])
+def test_checkers_rollout_host_matches_oracle(cuda, T, chunk, full):
+    """Host-buffer rollout (mm_checkers_rollout_host: chunked H2D / kernel / D2H pipeline) vs the oracle, incl.
+    ragged last chunks, a single chunk, and a second call that continues from the state the first one left."""
+    from minimarl_b200 import BatchedCheckers
+    n = 333
+    env = BatchedCheckers(n, full_observable=full, max_steps=30, device=cuda)
+    ref = CheckersBatchRef(n, full, 30, -0.01)
+    env.reset(); ref.reset()
+    rng = np.random.default_rng(T * 100 + chunk)
+    for call in range(2):
+        acts = rng.integers(0, 5, size=(T, n, 2), dtype=np.int32)
+        obs, rew, done = env.rollout_host(acts, chunk=chunk)
+        for t in range(T):
+            o, r, d = ref.step(acts[t])
+            assert np.array_equal(obs[t], o), f"call {call}: obs differ at step {t}"
+            assert np.array_equal(rew[t], r) and np.array_equal(done[t], d), f"call {call}: step {t}"
+    # actions written straight into the page-locked staging array, observations not requested
+    h = env.host_buffers(T, chunk)
+    h["act"].numpy()[...] = rng.integers(0, 5, size=(T, n, 2), dtype=np.int32)
+    acts = h["act"].numpy().copy()
+    obs, rew, done = env.rollout_host(h["act"].numpy(), chunk=chunk, want_obs=False)
+    assert obs is None
+    for t in range(T):
+        _, r, d = ref.step(acts[t])
+        assert np.array_equal(rew[t], r) and np.array_equal(done[t], d)
+    pos, steps, _ = ref.export()
+    assert np.array_equal(env.positions().cpu().numpy(), pos) and np.array_equal(env.step_count().cpu().numpy(), steps)
