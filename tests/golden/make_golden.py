@@ -540,6 +540,72 @@ def golden_vdn_toplevel():
     print("toplevel.npz", len(out), "arrays; vdn train loss", float(out["train_loss"]))
 
 
+def golden_qmix_toplevel():
+    """qmix/ top level: chunk PER with the whole-tree-argsort eviction of qmix/replay_buffer/sumtree.py,
+    then ONE Train_dqn.train call (update_iter 2: Q_Net + recurrent Mix_Net on both sides, done resets, q-net-only
+    clipping, last-step priorities) on the qmix default env shape (Switch2: A=2, D=3).  batch_size must be 32: the
+    reference's mix-hidden reset indexes a [32] row with the [B] done mask (qmix/_train.py:97-99).
+    random.uniform is patched to consume recorded uniforms; F.mse_loss is wrapped to record the per-step losses."""
+    import random as pyrandom
+    Box, Discrete = install_gym_stub()
+    out = {}
+    with ref_package("qmix"):
+        from _config import get_config
+        from _network import Mix_Net, Q_Net
+        from _train import Train_dqn
+        import _train as train_mod
+        from replay_buffer.per import Prioritized_Experience_Replay
+        torch.manual_seed(21)
+        args = get_config().parse_known_args([])[0]
+        args.buffer_limit, args.batch_size, args.update_iter, args.chunk_size, args.use_recurrent = 64, 32, 2, 10, True
+        A, D, L = 2, 3, args.chunk_size
+        obs_space = [Box(np.zeros(D), np.ones(D)) for _ in range(A)]
+        act_space = [Discrete(5) for _ in range(A)]
+        q, tq = Q_Net(obs_space, act_space, args), Q_Net(obs_space, act_space, args)
+        mix, tmix = Mix_Net(obs_space, args), Mix_Net(obs_space, args)
+        for name, m in [("q.", q), ("tq.", tq), ("mixnet.", mix), ("tmixnet.", tmix)]:
+            out.update(sd_numpy(m, name))
+        for k in ["gamma", "eps", "alpha", "beta", "grad_clip_norm", "lr", "max_episodes", "update_iter", "update_alpha_beta"]:
+            out["arg_" + k] = np.array(getattr(args, k))
+        rng = np.random.default_rng(23)
+        per = Prioritized_Experience_Replay(args)
+        n_add = 80
+        chunks = dict(states=rng.random((n_add, L, A, D)).astype(np.float32), actions=rng.integers(0, 5, (n_add, L, 1, A)).astype(np.float32),
+                      rewards=rng.standard_normal((n_add, L, A)).astype(np.float32), next_states=rng.random((n_add, L, A, D)).astype(np.float32),
+                      dones=(rng.random((n_add, L)) < 0.08).astype(np.float32), td=(rng.random(n_add) * 5 + 0.01).astype(np.float64))
+        for k, v in chunks.items():
+            out["chunk_" + k] = v
+        for i in range(n_add):
+            sample = [chunks["states"][i].tolist(), chunks["actions"][i].tolist(), chunks["rewards"][i].tolist(),
+                      chunks["next_states"][i].tolist(), chunks["dones"][i].tolist()]
+            per.collect_sample(sample=sample, td_error=float(chunks["td"][i]), warm_up=True)
+        out["tree_after_add"] = per.sum_tree.priority_tree.copy()
+        u = rng.random((args.update_iter, args.batch_size))
+        out["uniforms"] = u
+        seq = iter(u.reshape(-1))
+        orig_uniform, orig_mse = pyrandom.uniform, train_mod.F.mse_loss
+        step_losses = []
+
+        def mse(a, b):
+            v = orig_mse(a, b)
+            step_losses.append(float(v))
+            return v
+        pyrandom.uniform = lambda a, b: a + (b - a) * next(seq)
+        train_mod.F.mse_loss = mse
+        try:
+            opt = torch.optim.Adam(list(q.parameters()) + list(mix.parameters()), lr=args.lr)
+            Train_dqn(args, torch.device("cpu")).train(per, q, mix, tq, tmix, opt, 0.5)
+        finally:
+            pyrandom.uniform, train_mod.F.mse_loss = orig_uniform, orig_mse
+        out["step_losses"] = np.array(step_losses).reshape(args.update_iter, L)
+        out["tree_after_train"] = np.asarray(per.sum_tree.priority_tree, dtype=np.float64).copy()
+        out["alpha_after"], out["beta_after"] = np.array(per.alpha), np.array(per.beta)
+        out.update(sd_numpy(q, "q_after."))
+        out.update(sd_numpy(mix, "mixnet_after."))
+    np.savez_compressed(os.path.join(OUT, "qmix_toplevel.npz"), **out)
+    print("qmix_toplevel.npz", len(out), "arrays; iteration losses", out["step_losses"].sum(1))
+
+
 def golden_vdn_test():
     """vdn/_test.py Test.execute (the eval adaptor) run by the reference itself on the oracle env:
     greedy episodes of reference Q_Nets with recorded weights -> (score, TD loss)."""
@@ -572,7 +638,7 @@ def golden_vdn_test():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gae", "per", "nets", "logs", "mappo_buffer", "mappo_train", "toplevel", "vdn_test"]
+    which = sys.argv[1:] or ["gae", "per", "nets", "logs", "mappo_buffer", "mappo_train", "toplevel", "qmix_toplevel", "vdn_test"]
     if "gae" in which:
         golden_gae()
     if "per" in which:
@@ -587,5 +653,7 @@ if __name__ == "__main__":
         golden_mappo_train()
     if "toplevel" in which:
         golden_vdn_toplevel()
+    if "qmix_toplevel" in which:
+        golden_qmix_toplevel()
     if "vdn_test" in which:
         golden_vdn_test()

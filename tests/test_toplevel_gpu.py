@@ -166,3 +166,37 @@ def test_render_shim(cuda):
     assert len(rows) == 3 and rows[0].split() == ["R", "Y", "R", "Y", "R", "Y", "1", "."] and rows[2].split()[6] == "2"
     env.step([1, 4])                                    # agent 1 moves left onto the lemon at (0, 5)
     assert env.render(mode="ansi").split("\n")[0].split() == ["R", "Y", "R", "Y", "R", "1", ".", "."]
+
+
+def test_qmix_toplevel_train_matches_reference(cuda):
+    """qmix/_train.py Train_dqn.train recorded from the reference (tests/golden/qmix_toplevel.npz): 80 chunk adds into
+    64 slots (whole-tree-argsort eviction), two update iterations with Q_Net + recurrent Mix_Net on both sides."""
+    from minimarl_b200.algorithms import Mix_Net, Prioritized_Experience_Replay, Q_Net, Train_dqn
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = np.load(os.path.join(GOLDEN, "qmix_toplevel.npz"))
+    args = argparse.Namespace(use_recurrent=True, buffer_limit=64, batch_size=32, update_iter=2, chunk_size=10,
+                              gamma=float(g["arg_gamma"]), eps=float(g["arg_eps"]), alpha=float(g["arg_alpha"]),
+                              beta=float(g["arg_beta"]), use_step_weight=False, update_alpha_beta=bool(g["arg_update_alpha_beta"]),
+                              max_episodes=int(g["arg_max_episodes"]), grad_clip_norm=float(g["arg_grad_clip_norm"]),
+                              lr=float(g["arg_lr"]), seed=0)
+    spaces = [Box(np.zeros(3), np.ones(3)) for _ in range(2)]
+    acts = [Discrete(5) for _ in range(2)]
+    load = lambda m, pre: m.load_state_dict({k[len(pre):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre)})
+    q, tq = Q_Net(spaces, acts, args).to(cuda), Q_Net(spaces, acts, args).to(cuda)
+    mix, tmix = Mix_Net(spaces, args).to(cuda), Mix_Net(spaces, args).to(cuda)
+    load(q, "q."); load(tq, "tq."); load(mix, "mixnet."); load(tmix, "tmixnet.")
+    per = Prioritized_Experience_Replay(args, n_agents=2, obs_dim=3, device=cuda)
+    for i in range(g["chunk_td"].shape[0]):
+        per.collect_sample([g["chunk_states"][i], g["chunk_actions"][i], g["chunk_rewards"][i], g["chunk_next_states"][i],
+                            g["chunk_dones"][i]], float(g["chunk_td"][i]), warm_up=True)
+    assert np.array_equal(per.sum_tree.priority_tree.cpu().numpy(), g["tree_after_add"])
+    opt = torch.optim.Adam(list(q.parameters()) + list(mix.parameters()), lr=args.lr)
+    loss = Train_dqn(args, cuda).train(per, q, mix, tq, tmix, opt, 0.5, uniforms=g["uniforms"])
+    want = g["step_losses"].sum(1).mean()
+    assert abs(loss.item() - want) < 1e-4 * want, (loss.item(), want)
+    assert per.alpha == float(g["alpha_after"]) and per.beta == float(g["beta_after"])
+    assert np.allclose(per.sum_tree.priority_tree.cpu().numpy(), g["tree_after_train"], rtol=2e-4, atol=1e-7)
+    for name, p in q.state_dict().items():
+        assert np.allclose(p.cpu().numpy(), g["q_after." + name], atol=2e-3, rtol=1e-3), name
+    for name, p in mix.state_dict().items():
+        assert np.allclose(p.cpu().numpy(), g["mixnet_after." + name], atol=2e-3, rtol=1e-3), name
