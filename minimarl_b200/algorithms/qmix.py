@@ -171,6 +171,8 @@ class QMix:
         self.parameters += self.mixer.parameters()
         self.optimizer = torch.optim.Adam(params=self.parameters, lr=self.lr, eps=self.opti_eps)
         self.batch_size = batch_size
+        self.overlap_target = True
+        self._side_stream = torch.cuda.Stream(device=self.device)
 
     # -- gradient exchange (the only collective on this path) -------------------------------------
     def _allreduce_grads(self):
@@ -195,19 +197,35 @@ class QMix:
         if self.args.prev_act_inp:
             prev_acts = torch.cat((torch.zeros(1, total, policy.act_dim, **self.tpdv), stacked_acts))
 
+        # The target side (no gradient: fused kernels of 64 CTAs each, about half the SMs) runs on a second stream next to
+        # the live pass: target network ‖ live forward, then target mixer ‖ live mixer; the streams meet at q_select and at
+        # the TD loss.  Tensors crossing streams are pinned to their consumer with record_stream.
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream if self.overlap_target else main
+        if side is not main:
+            side.wait_stream(main)
+        with torch.no_grad(), torch.cuda.stream(side):
+            tq_all, _ = target_policy.get_q_values(stacked_obs, prev_acts, target_policy.init_hidden(-1, total))
         # live network: the differentiated pass
         q_all, _ = policy.get_q_values(stacked_obs, prev_acts, policy.init_hidden(-1, total))
+        if side is not main:
+            main.wait_stream(side)
+            tq_all.record_stream(main)
         with torch.no_grad():
-            tq_all, _ = target_policy.get_q_values(stacked_obs, prev_acts, target_policy.init_hidden(-1, total))
             _, next_q, act_idx, _ = q_select(q_all.detach(), tq_all, stacked_acts, T, B, A,
                                              double_q=self.args.use_double_q)
+        if side is not main:
+            side.wait_stream(main)
+        with torch.no_grad(), torch.cuda.stream(side):
+            next_Q_tot = torch.reshape(self.target_mixer(next_q, cent_obs[1:]), (-1, B, 1))
         # chosen-action Q of the live net, [T, A*B] -> [T, B, A]
         q_taken = torch.gather(q_all[:-1], 2, act_idx.unsqueeze(-1)).squeeze(-1)
         agent_q_seq = q_taken.view(T, A, B).permute(0, 2, 1)
 
         Q_tot_seq = torch.reshape(self.mixer(agent_q_seq, cent_obs[:-1]), (-1, B, 1))
-        with torch.no_grad():
-            next_Q_tot = torch.reshape(self.target_mixer(next_q, cent_obs[1:]), (-1, B, 1))
+        if side is not main:
+            main.wait_stream(side)
+            next_Q_tot.record_stream(main)
         rewards = _t(rew_batch[p_id], dev)[0]                        # agents share the reward: agent 0's copy
 
         w = _t(importance_weights, dev) if (self.use_per and importance_weights is not None) else None

@@ -37,6 +37,23 @@ class Network(nn.Module):
         self.value_net = nn.ParameterList()
         self.advantage_net = nn.ParameterList()
         self._gen = None
+        # qmix/_network.py registers the same per-agent modules with setattr names (feature_network_0, gru_network_0,
+        # action_network_0 ...) where vdn/_network.py uses ParameterLists: accept both spellings when loading
+        self._register_load_state_dict_pre_hook(self._accept_qmix_names)
+
+    @staticmethod
+    def _accept_qmix_names(state_dict, prefix, *unused):
+        import re
+        for key in list(state_dict.keys()):
+            m = re.match(re.escape(prefix) + r"(feature|gru|action|value|advantage)_network_(\d+)(\..*)$", key)
+            if m:
+                state_dict[f"{prefix}{m.group(1)}_net.{m.group(2)}{m.group(3)}"] = state_dict.pop(key)
+
+    def qmix_state_dict(self):
+        """state_dict with the key spelling of qmix/_network.py (``feature_network_0.0.weight`` ...)."""
+        import re
+        return {re.sub(r"^(feature|gru|action|value|advantage)_net\.(\d+)\.", r"\1_network_\2.", k): v
+                for k, v in self.state_dict().items()}
 
     def _feature(self, i):
         n_obs = self.observation_space[i].shape[0]

@@ -196,7 +196,7 @@ def test_qmix_toplevel_train_matches_reference(cuda):
     assert abs(loss.item() - want) < 1e-4 * want, (loss.item(), want)
     assert per.alpha == float(g["alpha_after"]) and per.beta == float(g["beta_after"])
     assert np.allclose(per.sum_tree.priority_tree.cpu().numpy(), g["tree_after_train"], rtol=2e-4, atol=1e-7)
-    for name, p in q.state_dict().items():
+    for name, p in q.qmix_state_dict().items():              # the key spelling of qmix/_network.py
         assert np.allclose(p.cpu().numpy(), g["q_after." + name], atol=2e-3, rtol=1e-3), name
     for name, p in mix.state_dict().items():
         assert np.allclose(p.cpu().numpy(), g["mixnet_after." + name], atol=2e-3, rtol=1e-3), name
