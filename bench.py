@@ -448,6 +448,7 @@ def run_ours(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the ONE JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     n, T, A = wl["n_envs"], wl["T"], AGENTS
