@@ -331,6 +331,35 @@ def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
     return out
 
 
+def qmix_toplevel_section(dev, episodes=3, n_envs=4096):
+    """BASELINE configs[1]: the qmix/main.py loop on 4 096 lockstep Switch2-v0 envs (the qmix/_config.py default env) with
+    the chunk replay on the GPU: Q_Net.sample_action -> lockstep env kernel -> target Q_Net -> cal_td_error per step,
+    4 096 chunk inserts per 10 steps in one mm_heaptree_add_batch launch, then Train_dqn.train (update_iter 10, recurrent
+    Mix_Net on both sides).  qmix/_config.py defaults except buffer_limit (1 000 -> 8 192 chunks) and batch_size
+    (32 -> 4 096 chunks), scaled with the env count.  The per-agent networks are PyTorch modules (cuBLAS)."""
+    import argparse as ap
+    import torch
+    from minimarl_b200.runners import run_qmix
+    torch.backends.cuda.matmul.allow_tf32 = True
+    batch = 4096
+    args = ap.Namespace(use_recurrent=True, buffer_limit=8192, batch_size=batch, update_iter=10, chunk_size=10, gamma=0.99,
+                        eps=1e-6, alpha=0.8, beta=0.2, use_step_weight=False, update_alpha_beta=True, max_episodes=100000,
+                        grad_clip_norm=5, lr=1e-3, seed=42, max_step=100, step_cost=-0.01, max_epsilon=0.9, min_epsilon=0.05,
+                        epsilon_anneal_episode=60000, update_target_interval=20)
+    run_qmix(args, n_envs, 1, device=dev)                     # warm-up (allocations, cuBLAS heuristics)
+    timing = {}
+    history, _ = run_qmix(args, n_envs, episodes, device=dev, timing=timing)
+    samples = episodes * args.update_iter * batch * args.chunk_size
+    return {"metric": "qmix/main.py loop, 4 096 lockstep Switch2-v0 envs, chunk replay on the GPU",
+            "rollout_agent_steps_per_s": timing["env_steps"] * 2 / timing["rollout_s"],
+            "rollout_ms_per_env_step_all_envs": timing["rollout_s"] * 1e3 / (timing["env_steps"] / n_envs),
+            "train_samples_per_s": samples / timing["train_s"], "train_ms_per_call": timing["train_s"] * 1e3 / episodes,
+            "episodes": episodes, "chunk_inserts_per_episode": n_envs * args.max_step // args.chunk_size,
+            "config": {"n_envs": n_envs, "env": "Switch2-v0", "buffer_limit_chunks": args.buffer_limit,
+                       "batch_chunks": batch, "chunk_size": args.chunk_size, "update_iter": args.update_iter},
+            "train_loss": history[-1]["train_loss"], "train_score": history[-1]["train_score"]}
+
+
 def learner_section(dev, steps):
     """Second half of the BASELINE metric: QMIX train samples/sec (configs[3]: 1M-transition device replay =
     10 000 episodes x T=100, batch 4 096 episodes, GRU agents, hidden 64, PER, double-Q).  One sample = one
@@ -609,6 +638,10 @@ def run_ours(args, wl):
                 line["policy_rollout"] = {"error": f"{type(e).__name__}: {e}"}
             line["learner"] = learner
             line["mappo_iteration"] = mappo_it
+            try:
+                line["qmix_toplevel"] = qmix_toplevel_section(dev)
+            except Exception as e:
+                line["qmix_toplevel"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

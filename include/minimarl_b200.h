@@ -300,6 +300,13 @@ int mm_heaptree_update(double* tree, int32_t capacity, const int64_t* node_idx, 
 int mm_heaptree_sample(const double* tree, int32_t capacity, const double* uniforms, int32_t n,
                        int64_t* node_idx_out, double* priority_out, void* stream);
 int mm_heaptree_argmin_leaf(const double* tree, int32_t capacity, int64_t* leaf_out, void* stream);
+/* k consecutive SumTree.add calls (vdn/replay_buffer/sumtree.py:38-58, qmix/replay_buffer/sumtree.py:38-64) in one
+ * launch -- what N lockstep envs hand the buffer at every chunk boundary.  Item i goes to data slot n_data while the
+ * buffer is filling (n_data = fill count before the call), afterwards to the arg-min-priority leaf as it is AFTER
+ * items 0..i-1 went in (a later item of the batch may evict an earlier one).  slot_out[i] = data slot of item i.
+ * MM_ERR_UNSUPPORTED when the arg-min tree (12 B per slot) does not fit in shared memory (capacity > ~14 500). */
+int mm_heaptree_add_batch(double* tree, int32_t capacity, int32_t n_data, const double* priority, int32_t k,
+                          int64_t* slot_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over short rows (N <= 128, eps 1e-5) for the differentiated network pass: the nn.LayerNorm

@@ -85,6 +85,7 @@ SIGNATURES = {
     "mm_heaptree_update": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P]),
     "mm_heaptree_sample": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "mm_heaptree_argmin_leaf": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "mm_heaptree_add_batch": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "mm_colsum": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P]),
     "mm_ppo_actor_loss_fwd": (C.c_int, [_P] * 6 + [C.c_int64, C.c_int32, C.c_float, _P, _P, C.c_int64, C.c_int64, _P]),
     "mm_ppo_actor_loss_bwd": (C.c_int, [_P] * 7 + [C.c_int64, C.c_int32, C.c_float, _P, C.c_int64, C.c_int64, _P]),

@@ -225,11 +225,13 @@ class Prioritized_Experience_Replay:
         self.sum_tree = SumTree(self.capacity, self.device)
         L = args.chunk_size
         z = dict(dtype=torch.float32, device=self.device)
-        self.states = torch.zeros((self.capacity, L, n_agents, obs_dim), **z)
-        self.actions = torch.zeros((self.capacity, L, n_agents), **z)
-        self.rewards = torch.zeros((self.capacity, L, n_agents), **z)
-        self.next_states = torch.zeros((self.capacity, L, n_agents, obs_dim), **z)
-        self.dones = torch.zeros((self.capacity, L, 1), **z)
+        # one spare row (index capacity) absorbs the payload of items that a later item of the same batch evicted
+        rows = self.capacity + 1
+        self.states = torch.zeros((rows, L, n_agents, obs_dim), **z)
+        self.actions = torch.zeros((rows, L, n_agents), **z)
+        self.rewards = torch.zeros((rows, L, n_agents), **z)
+        self.next_states = torch.zeros((rows, L, n_agents, obs_dim), **z)
+        self.dones = torch.zeros((rows, L, 1), **z)
         if args.update_alpha_beta:
             self.alpha_increment_per_sampling = (1 - self.alpha) / (args.max_episodes * args.update_iter)
             self.beta_increment_per_sampling = (1 - self.beta) / (args.max_episodes * args.update_iter)
@@ -264,6 +266,41 @@ class Prioritized_Experience_Replay:
                     torch.as_tensor(self._get_priority(td_error), dtype=torch.float64, device=self.device).reshape(1))
         if tree.n_data < self.capacity:
             tree.n_data += 1
+        return tree.n_data if warm_up else None
+
+    def collect_samples_batch(self, samples, td_errors, warm_up, host_pow=False):
+        """K consecutive ``collect_sample`` calls -- the chunks N lockstep envs finish at the same step, in env order
+        (the reference's add order) -- without a Python loop: ``mm_heaptree_add_batch`` replays the K ``SumTree.add``s
+        on the device (fill, then arg-min eviction where a later chunk may evict an earlier one of the same batch), the
+        payloads are scattered into the slots their final owners got.
+        samples = [states [K,L,A,D], actions [K,L,A] or [K,L,1,A], rewards [K,L,A], next_states [K,L,A,D], dones [K,L]];
+        td_errors [K].  ``host_pow``: raise (td + eps) ** alpha with Python doubles like the reference (one D2H sync)
+        instead of torch.pow on the device (<= 1 ulp from libm)."""
+        tree = self.sum_tree
+        s, a, r, s2, d = (torch.as_tensor(x, device=self.device, dtype=torch.float32) for x in samples)
+        K = s.shape[0]
+        td = torch.as_tensor(td_errors, device=self.device).reshape(K)
+        if host_pow:
+            prio = torch.tensor([(float(v) + self.eps) ** self.alpha for v in td.tolist()], dtype=torch.float64, device=self.device)
+        else:
+            prio = torch.pow(td.to(torch.float64) + self.eps, self.alpha)
+        slot = torch.empty(K, dtype=torch.int64, device=self.device)
+        rc = _lib.lib().mm_heaptree_add_batch(_lib.ptr(tree.priority_tree), self.capacity, tree.n_data, _lib.ptr(prio.contiguous()),
+                                              K, _lib.ptr(slot), _lib.stream())
+        if rc == -3:                                      # arg-min tree larger than shared memory: one by one
+            for i in range(K):
+                self.collect_sample([s[i], a[i], r[i], s2[i], d[i]], float(td[i]), warm_up)
+            return tree.n_data if warm_up else None
+        _lib.check(rc)
+        order = torch.arange(K, device=self.device)
+        last = torch.full((self.capacity,), -1, dtype=torch.int64, device=self.device).scatter_reduce_(0, slot, order, "amax")
+        dest = torch.where(last[slot] == order, slot, torch.full_like(slot, self.capacity))
+        self.states[dest] = s.reshape(K, *self.states.shape[1:])
+        self.actions[dest] = a.reshape(K, *self.actions.shape[1:])
+        self.rewards[dest] = r.reshape(K, *self.rewards.shape[1:])
+        self.next_states[dest] = s2.reshape(K, *self.next_states.shape[1:])
+        self.dones[dest] = d.reshape(K, *self.dones.shape[1:])
+        tree.n_data = min(self.capacity, tree.n_data + K)
         return tree.n_data if warm_up else None
 
     def sample(self, batch_size, _chunk_size, uniforms=None):

@@ -68,6 +68,62 @@ __global__ void heaptree_argmin_kernel(const double* __restrict__ tree, int capa
     if (threadIdx.x == 0) *out = s_idx[0];
 }
 
+// k SumTree.add calls in one launch.  An arg-min index tree with the shape of the sum tree (2*capacity-1 nodes) and a
+// copy of the leaf values live in shared memory; thread 0 then replays the adds strictly in order: slot = n_data while
+// the buffer fills, else the current arg-min leaf (lowest slot on ties, like heaptree_argmin_kernel); the leaf CHANGE is
+// propagated through the float64 sums in the reference's order; the arg-min path of the slot is repaired.
+__device__ __forceinline__ int argmin_pick(const double* vals, int a, int b) {
+    // a, b: slot indices; lower value wins, lower slot on ties
+    const double va = vals[a], vb = vals[b];
+    return (vb < va || (vb == va && b < a)) ? b : a;
+}
+
+__global__ void heaptree_add_batch_kernel(double* __restrict__ tree, int capacity, int n_data,
+                                          const double* __restrict__ priority, int k, int64_t* __restrict__ slot_out) {
+    extern __shared__ __align__(8) unsigned char smem_raw[];
+    double* vals = reinterpret_cast<double*>(smem_raw);                   // [capacity] leaf priorities
+    int* arg = reinterpret_cast<int*>(vals + capacity);                     // [2*capacity-1] arg-min slot per node
+    const bool evicts = n_data + k > capacity;
+    if (evicts) {
+        for (int i = threadIdx.x; i < capacity; i += blockDim.x) {
+            vals[i] = tree[capacity - 1 + i];
+            arg[capacity - 1 + i] = i;
+        }
+        __syncthreads();
+        // internal nodes bottom-up: node j has children 2j+1, 2j+2 > j, so levels are processed deepest first
+        int hi = capacity - 2;                                              // last internal node
+        while (hi >= 0) {
+            const int lo = (hi + 1) / 2;                                    // nodes [lo, hi] have all children > hi
+            for (int j = lo + threadIdx.x; j <= hi; j += blockDim.x) arg[j] = argmin_pick(vals, arg[2 * j + 1], arg[2 * j + 2]);
+            __syncthreads();
+            hi = lo - 1;
+        }
+    }
+    if (threadIdx.x != 0) return;
+    for (int i = 0; i < k; ++i) {
+        int slot;
+        if (n_data < capacity) slot = n_data++;
+        else slot = arg[0];
+        const double p = priority[i];
+        int idx = capacity - 1 + slot;
+        const double change = p - tree[idx];
+        tree[idx] = p;
+        while (idx != 0) {
+            idx = (idx - 1) / 2;
+            tree[idx] += change;
+        }
+        slot_out[i] = slot;
+        if (evicts) {
+            vals[slot] = p;
+            int j = capacity - 1 + slot;
+            while (j != 0) {
+                j = (j - 1) / 2;
+                arg[j] = argmin_pick(vals, arg[2 * j + 1], arg[2 * j + 2]);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int mm_heaptree_update(double* tree, int32_t capacity, const int64_t* node_idx, const double* priority,
@@ -88,5 +144,16 @@ extern "C" int mm_heaptree_sample(const double* tree, int32_t capacity, const do
 extern "C" int mm_heaptree_argmin_leaf(const double* tree, int32_t capacity, int64_t* leaf_out, void* stream) {
     if (!tree || !leaf_out || capacity <= 0) return MM_ERR_BAD_ARG;
     heaptree_argmin_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(tree, capacity, leaf_out);
+    return mm::check_launch();
+}
+
+extern "C" int mm_heaptree_add_batch(double* tree, int32_t capacity, int32_t n_data, const double* priority, int32_t k,
+                                     int64_t* slot_out, void* stream) {
+    if (!tree || !priority || !slot_out || capacity <= 0 || k <= 0 || n_data < 0 || n_data > capacity) return MM_ERR_BAD_ARG;
+    const size_t smem = (size_t)capacity * sizeof(double) + (size_t)(2 * capacity - 1) * sizeof(int);
+    if (smem > 227 * 1024) return MM_ERR_UNSUPPORTED;           // capacity > ~14 500: insert one by one
+    cudaError_t e = cudaFuncSetAttribute(heaptree_add_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
+    heaptree_add_batch_kernel<<<1, 1024, smem, static_cast<cudaStream_t>(stream)>>>(tree, capacity, n_data, priority, k, slot_out);
     return mm::check_launch();
 }

@@ -1,30 +1,50 @@
-"""The training loop of ``vdn/main.py`` (:80-198) for N lockstep Checkers boards (full observations, D = 94).
+"""The training loops of ``vdn/main.py`` (:80-198) and ``qmix/main.py`` (:96-260) for N lockstep envs.
 
 Per step: ``behavior_network.sample_action`` (one epsilon draw per env) -> lockstep env kernel ->
-``target_network`` forward -> ``cal_td_error`` for every env -> every ``chunk_size`` steps the chunks of all
-envs go into the device chunk-PER; after each batch of episodes ``Target_Dqn.train`` and the periodic hard
+``target_network`` forward -> ``cal_td_error`` for every env -> every ``chunk_size`` steps the chunks of ALL
+envs go into the device chunk-PER in one ``collect_samples_batch`` call (env order = the reference's add order;
+``mm_heaptree_add_batch`` replays the adds, evictions included, in one launch); after each batch of episodes
+``Target_Dqn.train`` (vdn) or ``Train_dqn.train`` with the recurrent ``Mix_Net`` (qmix) and the periodic hard
 target copy, with the reference's epsilon / alpha / beta schedules.
+
+``run_vdn``: Checkers-v0 with full observations (D = 94), the vdn/_config.py default.
+``run_qmix``: Switch2-v0 (D = 3), the qmix/_config.py default (qmix/_config.py:13-18).
 """
+import time
+
 import torch
 
-from ..algorithms.toplevel import Prioritized_Experience_Replay, Q_Net, Target_Dqn, cal_td_error
-from ..envs.batched import BatchedCheckers
+from ..algorithms.toplevel import Mix_Net, Prioritized_Experience_Replay, Q_Net, Target_Dqn, Train_dqn, cal_td_error
+from ..envs.batched import BatchedCheckers, BatchedSwitch
 
 
-def run_vdn(args, n_envs, episodes, device="cuda", log=None):
-    dev = torch.device(device)
-    env = BatchedCheckers(n_envs, full_observable=True, max_steps=args.max_step, step_cost=args.step_cost, device=dev)
+def _run(args, env, episodes, mixer, log, timing):
+    dev, n_envs = env.device, env.n_envs
     beh = Q_Net(env.observation_space, env.action_space, args).to(dev)
     tgt = Q_Net(env.observation_space, env.action_space, args).to(dev)
     tgt.load_state_dict(beh.state_dict())
-    per = Prioritized_Experience_Replay(args, n_agents=2, obs_dim=env.obs_dim, device=dev)
-    opt = torch.optim.Adam(beh.parameters(), lr=args.lr)
-    trainer = Target_Dqn(per, beh, tgt, args, dev)
+    per = Prioritized_Experience_Replay(args, n_agents=env.n_agents, obs_dim=env.obs_dim, device=dev)
+    if mixer:
+        mix, tmix = Mix_Net(env.observation_space, args).to(dev), Mix_Net(env.observation_space, args).to(dev)
+        tmix.load_state_dict(mix.state_dict())
+        opt = torch.optim.Adam([{"params": beh.parameters()}, {"params": mix.parameters()}], lr=args.lr)
+        trainer = Train_dqn(args, dev)
+        train = lambda eps: trainer.train(per, beh, mix, tgt, tmix, opt, eps)
+    else:
+        mix = tmix = None
+        opt = torch.optim.Adam(beh.parameters(), lr=args.lr)
+        trainer = Target_Dqn(per, beh, tgt, args, dev)
+        train = lambda eps: trainer.train(target_network=tgt, optimizer=opt, epsilon=eps)
     L = args.chunk_size
     history = []
+    t_roll = t_train = 0.0
+    env_steps = 0
     for episode in range(episodes):
         epsilon = max(args.min_epsilon, args.max_epsilon - (args.max_epsilon - args.min_epsilon) *
                       (episode / args.epsilon_anneal_episode))
+        if timing is not None:
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
         state = env.reset()
         hidden, target_hidden = beh.init_hidden(n_envs), tgt.init_hidden(n_envs)
         score = torch.zeros(n_envs, device=dev)
@@ -42,23 +62,47 @@ def run_vdn(args, n_envs, episodes, device="cuda", log=None):
                     chunk[k].append(v)
                 score += reward.sum(1) * alive
                 alive &= ~done.all(1)
+                env_steps += n_envs
                 if (step + 1) % L == 0:
-                    stack = {k: torch.stack(v, 1) for k, v in chunk.items()}
-                    for e in range(n_envs):              # one chunk per env, in env order (the reference's add order)
-                        per.collect_sample([stack["s"][e], stack["a"][e], stack["r"][e], stack["n"][e], stack["d"][e]],
-                                           td_sum[e].item(), warm_up=False)
+                    stack = [torch.stack(chunk[k], 1) for k in "sarnd"]
+                    per.collect_samples_batch(stack, td_sum, warm_up=False)    # one chunk per env, in env order
                     chunk = {k: [] for k in "sarnd"}
-                    td_sum.zero_()
+                    td_sum = torch.zeros(n_envs, device=dev)
+                    if not bool(alive.any()):                                # the reference stops at `all(done)`
+                        break
                 state, hidden = next_state, next_hidden
-                if not bool(alive.any()):
-                    break
-        loss = trainer.train(target_network=tgt, optimizer=opt, epsilon=epsilon) if per.sum_tree.n_data >= args.batch_size \
-            else torch.tensor(float("nan"))
+        if timing is not None:
+            torch.cuda.synchronize(dev)
+            t1 = time.perf_counter()
+            t_roll += t1 - t0
+        loss = train(epsilon) if per.sum_tree.n_data >= args.batch_size else torch.tensor(float("nan"))
         if episode % args.update_target_interval == 0:
             tgt.load_state_dict(beh.state_dict())
+            if mixer:
+                tmix.load_state_dict(mix.state_dict())
+        if timing is not None:
+            torch.cuda.synchronize(dev)
+            t_train += time.perf_counter() - t1
         rec = {"episode": episode, "train_score": score.mean().item(), "train_loss": float(loss), "eps": epsilon,
                "alpha": per.alpha, "beta": per.beta}
         history.append(rec)
         if log:
             log(rec)
+    if timing is not None:
+        timing.update(rollout_s=t_roll, train_s=t_train, env_steps=env_steps, chunks_in_buffer=per.sum_tree.n_data)
     return history, beh
+
+
+def run_vdn(args, n_envs, episodes, device="cuda", log=None, timing=None):
+    env = BatchedCheckers(n_envs, full_observable=True, max_steps=args.max_step, step_cost=args.step_cost,
+                          device=torch.device(device))
+    return _run(args, env, episodes, False, log, timing)
+
+
+def run_qmix(args, n_envs, episodes, device="cuda", log=None, timing=None, env_id="Switch2-v0"):
+    dev = torch.device(device)
+    if env_id.startswith("Switch"):
+        env = BatchedSwitch(n_envs, n_agents=int(env_id[6]), max_steps=args.max_step, step_cost=args.step_cost, device=dev)
+    else:
+        env = BatchedCheckers(n_envs, full_observable=False, max_steps=args.max_step, step_cost=args.step_cost, device=dev)
+    return _run(args, env, episodes, True, log, timing)

@@ -56,3 +56,17 @@ def test_vdn_main_loop(cuda):
                               max_epsilon=0.8, min_epsilon=0.05, epsilon_anneal_episode=50, update_target_interval=2)
     history, net = run_vdn(args, n_envs=16, episodes=3, device=cuda)
     assert len(history) == 3 and np.isfinite(history[-1]["train_loss"]) and history[-1]["alpha"] > 0.4
+
+
+def test_qmix_main_loop_on_lockstep_switch(cuda):
+    """qmix/main.py loop on lockstep Switch2 envs (the qmix default env): rollout -> batched chunk inserts (more chunks
+    than slots, so the in-batch eviction runs) -> Train_dqn with the recurrent mixer."""
+    from minimarl_b200.runners import run_qmix
+    args = argparse.Namespace(use_recurrent=True, buffer_limit=100, batch_size=32, update_iter=2, chunk_size=10, gamma=0.99,
+                              eps=1e-6, alpha=0.4, beta=0.4, use_step_weight=False, update_alpha_beta=True,
+                              max_episodes=100, grad_clip_norm=5, lr=1e-3, seed=42, max_step=20, step_cost=-0.1,
+                              max_epsilon=0.9, min_epsilon=0.05, epsilon_anneal_episode=50, update_target_interval=2)
+    timing = {}
+    history, net = run_qmix(args, n_envs=64, episodes=3, device=cuda, timing=timing)
+    assert len(history) == 3 and np.isfinite(history[-1]["train_loss"]) and history[-1]["beta"] > 0.4
+    assert timing["chunks_in_buffer"] == 100 and timing["env_steps"] == 3 * 20 * 64

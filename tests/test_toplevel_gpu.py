@@ -200,3 +200,37 @@ def test_qmix_toplevel_train_matches_reference(cuda):
         assert np.allclose(p.cpu().numpy(), g["q_after." + name], atol=2e-3, rtol=1e-3), name
     for name, p in mix.state_dict().items():
         assert np.allclose(p.cpu().numpy(), g["mixnet_after." + name], atol=2e-3, rtol=1e-3), name
+
+
+@pytest.mark.parametrize("fixture,cap,D,splits", [("toplevel.npz", 50, 94, [70]), ("toplevel.npz", 50, 94, [30, 25, 15]),
+                                                  ("qmix_toplevel.npz", 64, 3, [80]), ("qmix_toplevel.npz", 64, 3, [1, 63, 1, 15])])
+def test_batched_chunk_insert_equals_sequential_reference_adds(cuda, fixture, cap, D, splits):
+    """collect_samples_batch (mm_heaptree_add_batch: K SumTree.add calls in one launch, eviction inside the batch
+    included) leaves the tree bit-identical to the reference's one-by-one adds, and every slot holds the payload of
+    the chunk the reference put there (checked through the stratified sample recorded from the reference)."""
+    from minimarl_b200.algorithms import Prioritized_Experience_Replay
+    g = np.load(os.path.join(GOLDEN, fixture))
+    args = argparse.Namespace(use_recurrent=True, buffer_limit=cap, batch_size=8, update_iter=2, chunk_size=10,
+                              eps=float(g["arg_eps"]), alpha=float(g["arg_alpha"]), beta=float(g["arg_beta"]),
+                              step_weight=1.0, use_step_weight=False, update_alpha_beta=False, max_episodes=1, seed=0)
+    per = Prioritized_Experience_Replay(args, n_agents=2, obs_dim=D, device=cuda)
+    seq = Prioritized_Experience_Replay(args, n_agents=2, obs_dim=D, device=cuda)
+    lo = 0
+    for k in splits:
+        sl = slice(lo, lo + k)
+        n = per.collect_samples_batch([g["chunk_states"][sl], g["chunk_actions"][sl], g["chunk_rewards"][sl],
+                                       g["chunk_next_states"][sl], g["chunk_dones"][sl]], g["chunk_td"][sl], True, host_pow=True)
+        lo += k
+        assert n == min(cap, lo)
+    assert np.array_equal(per.sum_tree.priority_tree.cpu().numpy(), g["tree_after_add"])
+    for i in range(lo):
+        seq.collect_sample([g["chunk_states"][i], g["chunk_actions"][i], g["chunk_rewards"][i], g["chunk_next_states"][i],
+                            g["chunk_dones"][i]], float(g["chunk_td"][i]), True)
+    for name in ["states", "actions", "rewards", "next_states", "dones"]:
+        assert torch.equal(getattr(per, name)[:cap], getattr(seq, name)[:cap]), name
+    # device pow path: same slots, priorities within 1 ulp
+    dev = Prioritized_Experience_Replay(args, n_agents=2, obs_dim=D, device=cuda)
+    dev.collect_samples_batch([g["chunk_states"][:lo], g["chunk_actions"][:lo], g["chunk_rewards"][:lo],
+                               g["chunk_next_states"][:lo], g["chunk_dones"][:lo]], torch.from_numpy(g["chunk_td"][:lo]).to(cuda), True)
+    assert np.allclose(dev.sum_tree.priority_tree.cpu().numpy(), g["tree_after_add"], rtol=1e-14)
+    assert torch.equal(dev.states[:cap], seq.states[:cap])
