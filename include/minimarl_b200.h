@@ -238,6 +238,10 @@ int mm_tc_raw_selftest(const float* imgA, const float* imgB, float* D, int32_t N
                        int32_t a_lbo, int32_t a_sbo, int32_t b_step, int32_t b_lbo, int32_t b_sbo, int32_t trans_a,
                        int32_t trans_b, void* stream);
 
+/* Lane probe: the same product with the instruction descriptor's M = 64 or 128 (A has M rows); every TMEM lane holds
+ * -12345 before the MMA and D [128,N] is the dump of all 128 lanes afterwards: shows where a 64-row accumulator lives. */
+int mm_tc_lane_probe(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, void* stream);
+
 /* Tensor-core version of mm_agentq_forward: every dense contraction on tcgen05 (kind::tf32, fp32
  * accumulators in TMEM), same arguments.  params: plain fp32 buffer of the PyTorch-layout tensors
  * (offsets from mm_agentq_tc_param_offsets, same order of names as mm_agentq_param_offsets; the

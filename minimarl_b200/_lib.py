@@ -100,6 +100,7 @@ SIGNATURES = {
     "mm_ppo_trunk_fwd": (C.c_int, [_P, _P, _P, C.c_int64] + [_P] * 5 + [C.c_int32, C.c_int64, C.c_int32, C.c_int32, _P]),
     "mm_ppo_trunk_bwd": (C.c_int, [_P, _P, C.c_int64] + [_P] * 5 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _P]),
     "mm_ppo_trunk_dims": (C.c_int, [_P]),
+    "mm_tc_lane_probe": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "mm_tc_raw_selftest": (C.c_int, [_P, _P, _P] + [C.c_int32] * 10 + [_P]),
     "mm_mappo_rollout_param_count": (C.c_int, []),
     "mm_mappo_rollout_param_offsets": (C.c_int, [_P]),

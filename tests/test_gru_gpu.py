@@ -10,7 +10,8 @@ def _rel(a, b):
     return ((a - b).norm() / b.norm().clamp(min=1e-12)).item()
 
 
-@pytest.mark.parametrize("T,R,I,H,with_h0", [(1, 5, 64, 64, True), (12, 300, 64, 64, True), (7, 129, 32, 32, False), (40, 128, 64, 64, False)])
+@pytest.mark.parametrize("T,R,I,H,with_h0", [(1, 5, 64, 64, True), (12, 300, 64, 64, True), (7, 129, 32, 32, False), (40, 128, 64, 64, False),
+                                               (5, 9600, 64, 64, True), (6, 9500, 32, 32, True), (9, 8192, 64, 64, False)])   # > 148 x 64 rows: 128-row tiles
 def test_fused_gru_matches_nn_gru(cuda, T, R, I, H, with_h0):
     from minimarl_b200.nn.gru import GRU
     torch.backends.cudnn.allow_tf32 = True
