@@ -117,6 +117,35 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Several loads in flight, one wait: the *_issue calls return immediately, tmem_ld_fence makes every listed register
+// array depend on the single tcgen05.wait::ld (the "+r" operands keep the compiler from reading them earlier).
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, float (&v)[8]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, float (&v)[N]) {
+    static_assert(N == 8 || N == 16, "8 or 16 columns per load");
+    if constexpr (N == 16) tmem_ld16_issue(taddr, v);
+    else                   tmem_ld8_issue(taddr, v);
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_fence(float (&a)[N], float (&b)[N], float (&c)[N]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("" : "+f"(a[i]), "+f"(b[i]), "+f"(c[i]));
+}
+
 template <int N>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]) {
     static_assert(N == 8 || N == 16, "8 or 16 columns per load");
