@@ -429,6 +429,7 @@ def learner_section(dev, steps):
         ms_update = float(t_.item())
     # component timings (each in isolation, after the full updates)
     ms_sample, sample = timed(lambda: buf.sample(B, beta=0.4, p_id="policy_0"), 5)
+    ms_gather, _ = timed(lambda: buf._gather(sample[8]), 10)          # the gather launch alone (indices already drawn)
     stacked = torch.cat(list(sample[0]["policy_0"]), dim=-2)
     from minimarl_b200.nn.agent_q import agentq_forward
     net = policy.q_network
@@ -448,7 +449,11 @@ def learner_section(dev, steps):
                    "per": True, "double_q": True, "precision": "tf32 operands, fp32 accumulate (custom kernels and cuBLAS)"},
         "ms_per_update": ms_update, "loss": float(info_["loss"]),
         "sample_gather": {"ms": ms_sample, "algorithmic_GBps": gather_bytes / (ms_sample * 1e-3) / 1e9,
-                          "frac_of_measured_hbm": gather_bytes / (ms_sample * 1e-3) / 1e9 / peak},
+                          "frac_of_measured_hbm": gather_bytes / (ms_sample * 1e-3) / 1e9 / peak,
+                          "note": "PER draw (uniforms, mm_per_sample) + mm_replay_gather; 2 x 81 952 B per sampled episode"},
+        "gather_only": {"ms": ms_gather, "algorithmic_GBps": gather_bytes / (ms_gather * 1e-3) / 1e9,
+                        "frac_of_measured_hbm": gather_bytes / (ms_gather * 1e-3) / 1e9 / peak,
+                        "note": "mm_replay_gather for 4 096 already-drawn episode indices"},
         "agentq_forward_tcgen05": {"ms": ms_agent_tc, "rows_x_steps": rows,
                                    "TFLOPs": rows * 64000 / (ms_agent_tc * 1e-3) / 1e12,
                                    "note": "fused tcgen05 kernel (TF32 in, fp32 TMEM accumulators): target / greedy / "

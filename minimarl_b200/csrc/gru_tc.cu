@@ -4,10 +4,11 @@
 // mappo/utils/algorithm_utils/rnn.py:24-80) for hidden size H in {32, 64}, one layer.  The input projection
 // gi = x W_ih^T + b_ih (and in the backward dx, dW_ih, dW_hh) are large row-parallel GEMMs that stay in cuBLAS;
 // what is sequential -- gh = h_{t-1} W_hh^T, the gates, and in the backward dh_{t-1} = dgh W_hh -- runs here:
-// one CTA per 128 rows walks the sequence with W_hh (forward) or W_hh^T (backward) and the hidden / gate-gradient
-// tile resident in shared memory in tcgen05 operand layout, accumulators in TMEM, 512 threads splitting the H
-// columns of each row four ways exactly like agentq_tc.cu.  cuDNN's backward for this shape (101 steps x 8 192
-// rows x 64) takes 15 ms, 11.5 ms of it in one element-wise kernel; this pair takes well under 1 ms.
+// one CTA per 64 rows (tcgen05 M = 64: row r in TMEM lane 32 (r / 16) + r % 16, see mm_tc_lane_probe) walks the
+// sequence with W_hh (forward) or W_hh^T (backward) and the hidden / gate-gradient tile resident in shared memory
+// in tcgen05 operand layout, accumulators in TMEM; 512 threads = 4 quarters x 4 column parts x 2 half-warps, the
+// upper half-warp receiving its 8 accumulator columns by shuffle.  cuDNN's backward for this shape (101 steps x
+// 8 192 rows x 64) takes 15 ms, 11.5 ms of it in one element-wise kernel; this pair takes 0.44 + 0.61 ms.
 //   forward : r = s(gi_r + gh_r + b_hr), z = s(gi_z + gh_z + b_hz), ghn = gh_n + b_hn, n = tanh(gi_n + r ghn),
 //             h_t = (1 - z) n + z h_{t-1};           saves r, z, n, ghn for the backward
 //   backward: dn = dh (1 - z), dz = dh (h_{t-1} - n), a = dn (1 - n^2), dgi_n = a, dgh_n = a r, dr = a ghn,
@@ -49,9 +50,6 @@ __device__ __forceinline__ void st_row(float* __restrict__ p, const float (&v)[N
     for (int k = 0; k < N; k += 4) *reinterpret_cast<float4*>(p + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
 }
 
-// Per-thread staging in shared memory, filled with cp.async one step ahead: tensor s, 16-byte piece k4 of thread slot u
-// lives at ((s * CPT/4 + k4) * kSlots + u) * 16 B, so the 16-byte accesses of consecutive threads are contiguous.
-// Every thread reads back only what it copied itself: cp.async.wait_group is all the synchronisation needed.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool ok) {
     const uint32_t n = ok ? 16u : 0u;                                      // 0 source bytes: zero-fill
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
@@ -59,143 +57,12 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool o
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int CPT, int SLOTS>
-__device__ __forceinline__ void stage_row(uint8_t* stage, int s, int slot, const float* __restrict__ src, bool ok) {
-#pragma unroll
-    for (int k4 = 0; k4 < CPT / 4; ++k4)
-        cp_async16(tc::smem_u32(stage + ((size_t)(s * (CPT / 4) + k4) * SLOTS + slot) * 16), src + 4 * k4, ok);
-}
-template <int CPT, int SLOTS>
-__device__ __forceinline__ void unstage_row(const uint8_t* stage, int s, int slot, float (&v)[CPT]) {
-#pragma unroll
-    for (int k4 = 0; k4 < CPT / 4; ++k4) {
-        const float4 q = *reinterpret_cast<const float4*>(stage + ((size_t)(s * (CPT / 4) + k4) * SLOTS + slot) * 16);
-        v[4 * k4] = q.x; v[4 * k4 + 1] = q.y; v[4 * k4 + 2] = q.z; v[4 * k4 + 3] = q.w;
-    }
-}
-
 struct GruFwdArgs {
     const float *gi, *h0, *whh, *bhh;          // gi [T,R,3H]; h0 [R,H] or null; whh [3H,H]; bhh [3H]
     float *h_seq, *r, *z, *n, *ghn;            // [T,R,H] each (r/z/n/ghn may be null: inference)
     int T;
     long long R;
 };
-
-// ROWS = 128: one accumulator row per TMEM lane.  ROWS = 64 (tcgen05 M = 64): row r sits in lane 32 (r / 16) + r % 16, the
-// upper 16 lanes of every quarter are unused (mm_tc_lane_probe), so lanes 16..31 of every warp idle -- but a batch of
-// 8 192 rows then runs on 128 SMs instead of 64, and the per-step latency chain, not the lane count, is what bounds
-// this kernel.
-template <int H, int ROWS>
-__global__ void __launch_bounds__(kThreads, 1) gru_fwd_kernel(const GruFwdArgs a) {
-    constexpr int CPT = H / 4;
-    constexpr int SLOTS = ROWS * 4;                       // active threads
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t tmem_slot;
-    uint8_t* sW = smem;                        // W_hh [3H x H] K-major (B operand, N = 3H rows)
-    uint8_t* sH = sW + 3 * H * H * 4;          // h [ROWS x H] K-major (A operand), fp32
-    float* sB = reinterpret_cast<float*>(sH + ROWS * H * 4);   // b_hh [3H]
-    uint8_t* sS = reinterpret_cast<uint8_t*>(sB + 3 * H);      // staging: gi_r | gi_z | gi_n of the next step
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool active = ROWS == 128 || lane < 16;
-    const int row = ROWS == 128 ? (warp & 3) * 32 + lane : (warp & 3) * 16 + (lane & 15);
-    const int part = warp >> 2, c0 = part * CPT;
-    const int slot = part * ROWS + row;
-    const long long row0 = (long long)blockIdx.x * ROWS;
-    const bool valid = active && row0 + row < a.R;
-    constexpr uint32_t kCols = 3 * H <= 128 ? 128 : 256;
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, kCols);
-    if (tid == 0) tc::mbar_init(&bar, 1);
-    for (int i = tid; i < 3 * H * H; i += kThreads) {
-        const int rr = i / H, k = i - rr * H;
-        *reinterpret_cast<float*>(sW + tc::kmajor_offset(rr, k, H)) = to_tf32(a.whh[i]);
-    }
-    for (int i = tid; i < 3 * H; i += kThreads) sB[i] = a.bhh[i];
-    const float* gi_row = a.gi + (row0 + (valid ? row : 0)) * 3 * H + c0;       // step 0; + t * R * 3H per step
-    auto prefetch = [&](int t) {
-        if (active) {
-            const float* g = gi_row + (long long)t * a.R * 3 * H;
-            stage_row<CPT, SLOTS>(sS, 0, slot, g, valid);
-            stage_row<CPT, SLOTS>(sS, 1, slot, g + H, valid);
-            stage_row<CPT, SLOTS>(sS, 2, slot, g + 2 * H, valid);
-        }
-        cp_async_commit();
-    };
-    prefetch(0);
-    float h[CPT];
-    ld_row<CPT>(a.h0 ? a.h0 + (row0 + row) * H + c0 : nullptr, h, valid && a.h0 != nullptr);
-    if (active) {
-#pragma unroll
-        for (int k = 0; k < CPT; k += 4)
-            *reinterpret_cast<float4*>(sH + tc::kmajor_offset(row, c0 + k, H)) = make_float4(h[k], h[k + 1], h[k + 2], h[k + 3]);
-    }
-    tc::fence_smem_to_async();
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem = tmem_slot;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t sbo = (uint32_t)(H >> 2) * 128u;
-    const uint64_t dH = tc::make_desc(tc::smem_u32(sH), 128u, sbo);
-    const uint64_t dW_rz = tc::make_desc(tc::smem_u32(sW), 128u, sbo);
-    const uint64_t dW_n = tc::make_desc(tc::smem_u32(sW) + (uint32_t)(2 * H >> 3) * sbo, 128u, sbo);
-    const uint32_t idesc_2h = tc::make_idesc_tf32(ROWS, 2 * H), idesc_h = tc::make_idesc_tf32(ROWS, H);
-    uint32_t phase = 0;
-
-    for (int t = 0; t < a.T; ++t) {
-        if (tid == 0) {
-#pragma unroll
-            for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem, dH + 16 * kk, dW_rz + 16 * kk, idesc_2h, kk > 0);
-#pragma unroll
-            for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 2 * H, dH + 16 * kk, dW_n + 16 * kk, idesc_h, kk > 0);
-            tc::mma_commit(&bar);
-        }
-        // the input projections of this step were fetched during the previous one; the next step's go out now
-        float gir[CPT], giz[CPT], gin[CPT];
-        cp_async_wait_all();
-        if (active) {
-            unstage_row<CPT, SLOTS>(sS, 0, slot, gir);
-            unstage_row<CPT, SLOTS>(sS, 1, slot, giz);
-            unstage_row<CPT, SLOTS>(sS, 2, slot, gin);
-        }
-        if (t + 1 < a.T) prefetch(t + 1);
-        if (warp == 0) tc::mbar_wait(&bar, phase);
-        phase ^= 1;
-        __syncthreads();
-        tc::fence_after_sync();
-        float gr[CPT], gz[CPT], gn[CPT];
-        tc::tmem_ld<CPT>(lane_addr + c0, gr);
-        tc::tmem_ld<CPT>(lane_addr + H + c0, gz);
-        tc::tmem_ld<CPT>(lane_addr + 2 * H + c0, gn);
-        if (active) {
-            float rr[CPT], zz[CPT], nn[CPT];
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                rr[j] = sigmoid_(gir[j] + gr[j] + sB[c0 + j]);
-                zz[j] = sigmoid_(giz[j] + gz[j] + sB[H + c0 + j]);
-                gn[j] += sB[2 * H + c0 + j];
-                nn[j] = tanh_(gin[j] + rr[j] * gn[j]);
-                h[j] = (1.0f - zz[j]) * nn[j] + zz[j] * h[j];
-            }
-            const long long o = ((long long)t * a.R + row0 + row) * H + c0;
-            st_row<CPT>(a.h_seq + o, h, valid);
-            if (a.r != nullptr) {
-                st_row<CPT>(a.r + o, rr, valid);
-                st_row<CPT>(a.z + o, zz, valid);
-                st_row<CPT>(a.n + o, nn, valid);
-                st_row<CPT>(a.ghn + o, gn, valid);
-            }
-#pragma unroll
-            for (int k = 0; k < CPT; k += 4)
-                *reinterpret_cast<float4*>(sH + tc::kmajor_offset(row, c0 + k, H)) = make_float4(h[k], h[k + 1], h[k + 2], h[k + 3]);
-        }
-        tc::fence_smem_to_async();
-        tc::fence_before_sync();
-        __syncthreads();
-        tc::fence_after_sync();
-    }
-    if (warp == 0) tc::tmem_dealloc(tmem, kCols);
-}
 
 // ---- 64-row forward with coalesced tile I/O -----------------------------------------------------------------------------
 // The thread = row binding that TMEM forces makes every per-thread global access touch 16 different 128-byte lines per warp
@@ -361,136 +228,6 @@ struct GruBwdArgs {
     long long R;
 };
 
-template <int H, int ROWS, bool STAGE>
-__global__ void __launch_bounds__(kThreads, 1) gru_bwd_kernel(const GruBwdArgs a) {
-    constexpr int CPT = H / 4;
-    constexpr int K3 = 3 * H;
-    constexpr int SLOTS = ROWS * 4;
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t tmem_slot;
-    uint8_t* sWt = smem;                       // W_hh^T [H x 3H] K-major (B operand: N = H rows, K = 3H)
-    uint8_t* sG = sWt + H * K3 * 4;            // dgh [ROWS x 3H] K-major (A operand)
-    uint8_t* sS = sG + ROWS * K3 * 4;          // STAGE: dh | r | z | n | ghn | h_prev of the next (earlier) step
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool active = ROWS == 128 || lane < 16;
-    const int row = ROWS == 128 ? (warp & 3) * 32 + lane : (warp & 3) * 16 + (lane & 15);
-    const int part = warp >> 2, c0 = part * CPT;
-    const int slot = part * ROWS + row;
-    const long long row0 = (long long)blockIdx.x * ROWS;
-    const bool valid = active && row0 + row < a.R;
-    constexpr uint32_t kCols = H <= 32 ? 32 : 64;
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, kCols);
-    if (tid == 0) tc::mbar_init(&bar, 1);
-    for (int i = tid; i < K3 * H; i += kThreads) {   // whh[g][j] (g in 3H, j in H) -> sWt row j, column g
-        const int g = i / H, j = i - g * H;
-        *reinterpret_cast<float*>(sWt + tc::kmajor_offset(j, g, K3)) = to_tf32(a.whh[i]);
-    }
-    const long long orow = (row0 + (valid ? row : 0)) * H + c0;              // offset inside one [R, H] step slab
-    auto prefetch = [&](int t) {
-        if (active) {
-            const long long o = (long long)t * a.R * H + orow;
-            stage_row<CPT, SLOTS>(sS, 0, slot, a.dh_seq + o, valid);
-            stage_row<CPT, SLOTS>(sS, 1, slot, a.r + o, valid);
-            stage_row<CPT, SLOTS>(sS, 2, slot, a.z + o, valid);
-            stage_row<CPT, SLOTS>(sS, 3, slot, a.n + o, valid);
-            stage_row<CPT, SLOTS>(sS, 4, slot, a.ghn + o, valid);
-            if (t > 0) stage_row<CPT, SLOTS>(sS, 5, slot, a.h_seq + o - a.R * H, valid);
-            else       stage_row<CPT, SLOTS>(sS, 5, slot, a.h0 ? a.h0 + orow : a.dh_seq, valid && a.h0 != nullptr);
-        }
-        cp_async_commit();
-    };
-    if constexpr (STAGE) prefetch(a.T - 1);
-    tc::fence_smem_to_async();
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem = tmem_slot;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t sbo = (uint32_t)(K3 >> 2) * 128u;
-    const uint64_t dG = tc::make_desc(tc::smem_u32(sG), 128u, sbo), dW = tc::make_desc(tc::smem_u32(sWt), 128u, sbo);
-    const uint32_t idesc = tc::make_idesc_tf32(ROWS, H);
-    uint32_t phase = 0;
-    float dh_rec[CPT];
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) dh_rec[j] = 0.f;
-
-    for (int t = a.T - 1; t >= 0; --t) {
-        const long long o = ((long long)t * a.R + row0 + row) * H + c0;
-        float dh[CPT], rr[CPT], zz[CPT], nn[CPT], gn[CPT], hp[CPT];
-        if constexpr (STAGE) {
-            cp_async_wait_all();
-            if (active) {
-                unstage_row<CPT, SLOTS>(sS, 0, slot, dh);
-                unstage_row<CPT, SLOTS>(sS, 1, slot, rr);
-                unstage_row<CPT, SLOTS>(sS, 2, slot, zz);
-                unstage_row<CPT, SLOTS>(sS, 3, slot, nn);
-                unstage_row<CPT, SLOTS>(sS, 4, slot, gn);
-                unstage_row<CPT, SLOTS>(sS, 5, slot, hp);
-            }
-            if (t > 0) prefetch(t - 1);            // in flight during the whole of this step
-        } else {
-            ld_row<CPT>(a.dh_seq + o, dh, valid);
-            ld_row<CPT>(a.r + o, rr, valid);
-            ld_row<CPT>(a.z + o, zz, valid);
-            ld_row<CPT>(a.n + o, nn, valid);
-            ld_row<CPT>(a.ghn + o, gn, valid);
-            if (t > 0) ld_row<CPT>(a.h_seq + o - a.R * H, hp, valid);
-            else       ld_row<CPT>(a.h0 ? a.h0 + (row0 + row) * H + c0 : nullptr, hp, valid && a.h0 != nullptr);
-        }
-        if (active) {
-            float d_r[CPT], d_z[CPT], d_n[CPT], d_hn[CPT];
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                const float g = dh[j] + dh_rec[j];
-                const float an = g * (1.0f - zz[j]) * (1.0f - nn[j] * nn[j]);
-                d_n[j] = an;
-                d_hn[j] = an * rr[j];
-                d_r[j] = an * gn[j] * rr[j] * (1.0f - rr[j]);
-                d_z[j] = g * (hp[j] - nn[j]) * zz[j] * (1.0f - zz[j]);
-                dh_rec[j] = g * zz[j];                                   // direct path; the W_hh path is added after the MMA
-            }
-            float* dgi = a.dgi + ((long long)t * a.R + row0 + row) * K3 + c0;
-            st_row<CPT>(dgi, d_r, valid);
-            st_row<CPT>(dgi + H, d_z, valid);
-            st_row<CPT>(dgi + 2 * H, d_n, valid);
-            st_row<CPT>(a.dghn + o, d_hn, valid);
-            // dgh = [d_r | d_z | d_hn] as the A operand
-#pragma unroll
-            for (int k = 0; k < CPT; k += 4) {
-                *reinterpret_cast<float4*>(sG + tc::kmajor_offset(row, c0 + k, K3)) =
-                    make_float4(to_tf32(d_r[k]), to_tf32(d_r[k + 1]), to_tf32(d_r[k + 2]), to_tf32(d_r[k + 3]));
-                *reinterpret_cast<float4*>(sG + tc::kmajor_offset(row, H + c0 + k, K3)) =
-                    make_float4(to_tf32(d_z[k]), to_tf32(d_z[k + 1]), to_tf32(d_z[k + 2]), to_tf32(d_z[k + 3]));
-                *reinterpret_cast<float4*>(sG + tc::kmajor_offset(row, 2 * H + c0 + k, K3)) =
-                    make_float4(to_tf32(d_hn[k]), to_tf32(d_hn[k + 1]), to_tf32(d_hn[k + 2]), to_tf32(d_hn[k + 3]));
-            }
-        }
-        tc::fence_smem_to_async();
-        tc::fence_before_sync();
-        __syncthreads();
-        tc::fence_after_sync();
-        if (tid == 0) {
-#pragma unroll
-            for (int kk = 0; kk < K3 / 8; ++kk) tc::mma_tf32(tmem, dG + 16 * kk, dW + 16 * kk, idesc, kk > 0);
-            tc::mma_commit(&bar);
-        }
-        if (warp == 0) tc::mbar_wait(&bar, phase);
-        phase ^= 1;
-        __syncthreads();
-        tc::fence_after_sync();
-        float mm_[CPT];
-        tc::tmem_ld<CPT>(lane_addr + c0, mm_);
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) dh_rec[j] += mm_[j];
-        tc::fence_before_sync();          // the next step's MMA overwrites this accumulator: order the loads before it
-    }
-    if (a.dh0 != nullptr) st_row<CPT>(a.dh0 + (row0 + row) * H + c0, dh_rec, valid);
-    tc::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, kCols);
-}
-
 // ---- 64-row backward with coalesced tile loads --------------------------------------------------------------------------
 // Same idea as gru_fwd_tile_kernel: the six [64 x H] input tiles of the NEXT (earlier) step -- dh, r, z, n, ghn, h_prev, each
 // contiguous in global memory -- are fetched with 512-contiguous-byte cp.async instructions into padded shared rows while
@@ -625,29 +362,12 @@ __global__ void __launch_bounds__(kThreads, 1) gru_bwd_tile_kernel(const GruBwdA
     if (warp == 0) tc::tmem_dealloc(tmem, kCols);
 }
 
-// M = 64 tiles whenever they fit one wave better: R <= 64 rows x SM count (8 192 rows -> 128 CTAs instead of 64)
-inline bool use_rows64(long long R) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long ctas128 = (R + 127) / 128, ctas64 = (R + 63) / 64;
-    const long long waves128 = (ctas128 + sms - 1) / sms, waves64 = (ctas64 + sms - 1) / sms;
-    return waves64 <= waves128;           // same number of waves with half-size tiles: twice the SMs share the work
-}
-
 template <int H>
 int launch_fwd_tile(const GruFwdArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)4 * (3 * H * H + 64 * H + 3 * H) + (size_t)64 * (3 * H * 4 + 16) + (size_t)5 * 64 * (H * 4 + 16) + 128;
     cudaError_t e = cudaFuncSetAttribute(gru_fwd_tile_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
     gru_fwd_tile_kernel<H><<<(unsigned)((a.R + 63) / 64), kThreads, smem, st>>>(a);
-    return mm::check_launch();
-}
-template <int H, int ROWS>
-int launch_fwd(const GruFwdArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)4 * (3 * H * H + ROWS * H + 3 * H) + (size_t)12 * H * ROWS + 128;
-    cudaError_t e = cudaFuncSetAttribute(gru_fwd_kernel<H, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
-    gru_fwd_kernel<H, ROWS><<<(unsigned)((a.R + ROWS - 1) / ROWS), kThreads, smem, st>>>(a);
     return mm::check_launch();
 }
 template <int H>
@@ -658,17 +378,6 @@ int launch_bwd_tile(const GruBwdArgs& a, cudaStream_t st) {
     gru_bwd_tile_kernel<H><<<(unsigned)((a.R + 63) / 64), kThreads, smem, st>>>(a);
     return mm::check_launch();
 }
-template <int H, int ROWS>
-int launch_bwd(const GruBwdArgs& a, cudaStream_t st) {
-    // the six-tensor staging (24 H ROWS bytes) fits beside W_hh^T and the dgh tile except at H = 64 with 128-row tiles
-    constexpr bool STAGE = (size_t)4 * (3 * H * H + ROWS * 3 * H) + (size_t)24 * H * ROWS + 128 <= 227 * 1024;
-    const size_t smem = (size_t)4 * (3 * H * H + ROWS * 3 * H) + (STAGE ? (size_t)24 * H * ROWS : 0) + 128;
-    cudaError_t e = cudaFuncSetAttribute(gru_bwd_kernel<H, ROWS, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
-    gru_bwd_kernel<H, ROWS, STAGE><<<(unsigned)((a.R + ROWS - 1) / ROWS), kThreads, smem, st>>>(a);
-    return mm::check_launch();
-}
-
 bool aligned16(const void* p) { return p == nullptr || mm::aligned(p, 16); }
 
 }  // namespace
@@ -682,8 +391,7 @@ extern "C" int mm_gru_seq_fwd(const float* gi, const float* h0, const float* w_h
         return MM_ERR_BAD_ARG;
     GruFwdArgs a{gi, h0, w_hh, b_hh, h_seq, r, z, n, ghn, T, R};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (use_rows64(R)) return H == 64 ? launch_fwd_tile<64>(a, st) : launch_fwd_tile<32>(a, st);
-    return H == 64 ? launch_fwd<64, 128>(a, st) : launch_fwd<32, 128>(a, st);
+    return H == 64 ? launch_fwd_tile<64>(a, st) : launch_fwd_tile<32>(a, st);
 }
 
 extern "C" int mm_gru_seq_bwd(const float* dh_seq, const float* r, const float* z, const float* n, const float* ghn,
@@ -696,6 +404,5 @@ extern "C" int mm_gru_seq_bwd(const float* dh_seq, const float* r, const float* 
         return MM_ERR_BAD_ARG;
     GruBwdArgs a{dh_seq, r, z, n, ghn, h_seq, h0, w_hh, dgi, dghn, dh0, T, R};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (use_rows64(R)) return H == 64 ? launch_bwd_tile<64>(a, st) : launch_bwd_tile<32>(a, st);
-    return H == 64 ? launch_bwd<64, 128>(a, st) : launch_bwd<32, 128>(a, st);
+    return H == 64 ? launch_bwd_tile<64>(a, st) : launch_bwd_tile<32>(a, st);
 }
