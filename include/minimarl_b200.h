@@ -211,6 +211,15 @@ int mm_qmixer_param_offsets(int32_t SD, int32_t A, int32_t* offsets_host /* int3
 int mm_qmixer_forward(const float* params, const float* agent_q, const float* states, float* q_tot,
                       int64_t M, int32_t SD, int32_t A, void* stream);
 int mm_vdn_mix(const float* agent_q, float* q_tot, int64_t M, int32_t A, void* stream);
+/* Tensor-core version of mm_qmixer_forward for 2 agents: every hypernetwork contraction on tcgen05 (kind::tf32, fp32
+ * accumulators in TMEM), persistent CTAs with the weights resident in shared memory.  SD even, SD <= 96.
+ * params: wcat [224][96] (rows hyper_w1.0 | hyper_w2.0 | hyper_b2.0 | hyper_b1 weights, K zero-padded), w1b [64][64]
+ * (hyper_w1.2), w2b [32][64] (hyper_w2.2), bcat [224], b1b [64], b2b [32], wb2 [64] (hyper_b2.2), bb2 [4] -- the PyTorch
+ * [out][in] layouts; mm_qmixer_tc_param_offsets gives the 8 offsets in that order.  ~1e-3 relative on Q_tot. */
+int mm_qmixer_tc_param_count(int32_t SD, int32_t A);
+int mm_qmixer_tc_param_offsets(int32_t SD, int32_t A, int32_t* offsets_host);
+int mm_qmixer_tc_forward(const float* params, const float* agent_q, const float* states, float* q_tot,
+                         int64_t M, int32_t SD, int32_t A, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Tail of QMix.train_policy_on_batch (offpolicy/algorithms/qmix/qmix.py:134-191).

@@ -69,6 +69,9 @@ SIGNATURES = {
     "mm_qmixer_param_offsets": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "mm_qmixer_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "mm_vdn_mix": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P]),
+    "mm_qmixer_tc_param_count": (C.c_int, [C.c_int32, C.c_int32]),
+    "mm_qmixer_tc_param_offsets": (C.c_int, [C.c_int32, C.c_int32, _P]),
+    "mm_qmixer_tc_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P]),
     "mm_q_select": (C.c_int, [_P] * 7 + [C.c_int32] * 5 + [_P]),
     "mm_qmix_td": (C.c_int, [_P] * 5 + [C.c_float] * 3 + [C.c_int32] * 2 + [_P] * 6),
     "mm_tc_gemm_selftest": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),

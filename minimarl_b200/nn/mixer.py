@@ -49,6 +49,38 @@ def pack_qmixer(sd, SD, A, device, prefix=""):
     return buf
 
 
+_TC_NAMES = ["wcat", "w1b", "w2b", "bcat", "b1b", "b2b", "wb2", "bb2"]
+
+
+def pack_qmixer_tc(sd, SD, A, device, prefix=""):
+    """Parameter buffer of the tensor-core mixer (mm_qmixer_tc_forward): the PyTorch [out][in] matrices as they are, the four
+    first layers stacked row-wise with their input columns zero-padded to 96.  None when the shape is not supported."""
+    lib = _lib.lib()
+    total = lib.mm_qmixer_tc_param_count(SD, A)
+    if total < 0:
+        return None
+    offs = (C.c_int32 * 8)()
+    _lib.check(lib.mm_qmixer_tc_param_offsets(SD, A, offs))
+    o = dict(zip(_TC_NAMES, list(offs)))
+    g = lambda k: sd[prefix + k].detach().to(device=device, dtype=torch.float32)
+    buf = torch.zeros(total, dtype=torch.float32, device=device)
+    wcat = torch.zeros((224, 96), dtype=torch.float32, device=device)
+    bcat = torch.zeros(224, dtype=torch.float32, device=device)
+    for r0, key, width in [(0, "hyper_w1.0", 64), (64, "hyper_w2.0", 64), (128, "hyper_b2.0", 64), (192, "hyper_b1", 32)]:
+        wcat[r0:r0 + width, :SD] = g(key + ".weight")
+        bcat[r0:r0 + width] = g(key + ".bias")
+
+    def put(name, t):
+        t = t.reshape(-1)
+        buf[o[name]:o[name] + t.numel()] = t
+
+    put("wcat", wcat); put("bcat", bcat)
+    put("w1b", g("hyper_w1.2.weight")); put("b1b", g("hyper_w1.2.bias"))
+    put("w2b", g("hyper_w2.2.weight")); put("b2b", g("hyper_w2.2.bias"))
+    put("wb2", g("hyper_b2.2.weight")); put("bb2", g("hyper_b2.2.bias"))
+    return buf
+
+
 class _MixingFn(torch.autograd.Function):
     """hidden = elu(q @ w1 + b1); out = hidden . w2 + b2 per row, one warp per row (mm_qmix_mixing_fwd / _bwd)."""
 
@@ -105,6 +137,10 @@ class QMixer(nn.Module):
         self.to(self.device)
         self.fusable = args.hypernet_layers == 2 and HH == 64 and E == 32 and A in (2, 4)
         self._packed, self._packed_key = None, None
+        # "tf32": the no-grad pass runs on the tensor cores (mm_qmixer_tc_forward, ~1e-3 relative on Q_tot); "fp32": FFMA kernel
+        self.precision = getattr(args, "fused_precision", "tf32")
+        self.tc_ok = self.fusable and _lib.lib().mm_qmixer_tc_param_count(S, A) > 0
+        self._packed_tc, self._packed_tc_key = None, None
 
     def packed(self):
         key = tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
@@ -112,6 +148,13 @@ class QMixer(nn.Module):
             self._packed = pack_qmixer(self.state_dict(), self.cent_obs_dim, self.num_agents, self.device)
             self._packed_key = key
         return self._packed
+
+    def packed_tc(self):
+        key = tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+        if self._packed_tc is None or key != self._packed_tc_key:
+            self._packed_tc = pack_qmixer_tc(self.state_dict(), self.cent_obs_dim, self.num_agents, self.device)
+            self._packed_tc_key = key
+        return self._packed_tc
 
     def forward(self, agent_q_inps, states):
         agent_q_inps = torch.as_tensor(agent_q_inps).to(**self.tpdv)
@@ -123,8 +166,12 @@ class QMixer(nn.Module):
             s = states.reshape(-1, self.cent_obs_dim).contiguous()
             q = agent_q_inps.reshape(-1, self.num_agents).contiguous()
             out = torch.empty(s.shape[0], **self.tpdv)
-            _lib.check(_lib.lib().mm_qmixer_forward(_lib.ptr(self.packed()), _lib.ptr(q), _lib.ptr(s), _lib.ptr(out),
-                                                    s.shape[0], self.cent_obs_dim, self.num_agents, _lib.stream()))
+            if self.precision == "tf32" and self.tc_ok:
+                _lib.check(_lib.lib().mm_qmixer_tc_forward(_lib.ptr(self.packed_tc()), _lib.ptr(q), _lib.ptr(s), _lib.ptr(out),
+                                                           s.shape[0], self.cent_obs_dim, self.num_agents, _lib.stream()))
+            else:
+                _lib.check(_lib.lib().mm_qmixer_forward(_lib.ptr(self.packed()), _lib.ptr(q), _lib.ptr(s), _lib.ptr(out),
+                                                        s.shape[0], self.cent_obs_dim, self.num_agents, _lib.stream()))
             return out.view(-1, batch_size, 1, 1)
         states = states.view(-1, batch_size, self.cent_obs_dim).float()
         if states.is_cuda and self.hidden_layer_dim == 32 and self.num_mixer_q_inps in (2, 4):

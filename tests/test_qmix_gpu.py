@@ -72,6 +72,36 @@ def test_mixer_ragged_rows(cuda):
         assert (fused - eager).abs().max().item() < 5e-5 * max(1.0, eager.abs().max().item())
 
 
+def test_tensor_core_mixer_matches_fp32_and_reference(cuda):
+    """mm_qmixer_tc_forward (tcgen05, TF32 operands): the reference-recorded mixer output within 2e-3 of its scale, and the
+    fp32 kernel on ragged row counts (1 row, partial tiles, more tiles than SMs)."""
+    from minimarl_b200.nn import QMixer
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = _g()
+    mixer = QMixer(_args(fused_precision="tf32"), 2, 94, cuda)
+    assert mixer.tc_ok
+    _load(mixer, g, "mix.")
+    q, s = torch.from_numpy(g["mixer_in_q"]).to(cuda), torch.from_numpy(g["share_obs"][:-1]).to(cuda)
+    with torch.no_grad():
+        out = mixer(q, s)
+    scale = np.abs(g["mixer_out"]).max()
+    assert np.abs(out.cpu().numpy() - g["mixer_out"]).max() < 2e-3 * scale
+    torch.manual_seed(1)
+    ref = QMixer(_args(fused_precision="fp32"), 2, 94, cuda)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    mixer.load_state_dict(ref.state_dict())
+    for T, B in [(1, 1), (3, 50), (7, 128), (100, 333), (40, 4096)]:
+        q = torch.randn((T, B, 2), device=cuda)
+        s = torch.rand((T, B, 94), device=cuda)
+        with torch.no_grad():
+            a, b = mixer(q, s), ref(q, s)
+        assert a.shape == b.shape
+        # Q_tot is a sum of 32 products of O(1) magnitude plus b2: the TF32 error scales with those terms, not with the sum
+        assert (a - b).abs().max().item() < 5e-3 * max(1.0, b.abs().max().item()), (T, B)
+
+
 def test_full_qmix_update_matches_reference(cuda):
     from minimarl_b200.algorithms import QMix, QMixPolicy
     torch.backends.cudnn.allow_tf32 = False
