@@ -177,6 +177,8 @@ class QMixer(nn.Module):
         if states.is_cuda and self.hidden_layer_dim == 32 and self.num_mixer_q_inps in (2, 4):
             # differentiated pass: hypernetworks through cuBLAS, the per-row mixing through one custom kernel
             s2 = states.reshape(-1, self.cent_obs_dim)
+            if self.cent_obs_dim % 4:                                    # pad once for the four first layers (nn/linear.py)
+                s2 = F.pad(s2, (0, (-self.cent_obs_dim) % 4))
             w1 = torch.abs(self.hyper_w1(s2)).view(-1, self.num_mixer_q_inps, self.hidden_layer_dim)
             w2 = torch.abs(self.hyper_w2(s2))
             out = _MixingFn.apply(agent_q_inps.reshape(-1, self.num_mixer_q_inps), w1, self.hyper_b1(s2), w2,
