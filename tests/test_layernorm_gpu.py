@@ -8,7 +8,8 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("M,N", [(1, 47), (1000, 47), (4097, 64), (333, 32), (50000, 94), (77, 128), (5, 3)])
+@pytest.mark.parametrize("M,N", [(1, 47), (1000, 47), (4097, 64), (333, 32), (50000, 94), (77, 128), (5, 3), (100003, 64), (1, 64),
+                                 (20001, 32), (9, 128)])
 def test_layernorm_forward_backward(cuda, M, N):
     from minimarl_b200.nn import LayerNorm
     torch.manual_seed(M + N)
