@@ -467,6 +467,32 @@ def learner_section(dev, steps):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa_node(gpu_index):
+    """Restricts this rank to the CPU cores NVML reports as local to its GPU (intersected with the cores the process may use),
+    so that the page-locked host buffers of the e2e leg are first-touched on the GPU's NUMA node.  Returns the core count, or
+    None when NVML is unavailable / the intersection is empty (then nothing changes)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = gpu_index
+        if visible:
+            ids = visible.split(",")
+            if gpu_index < len(ids) and ids[gpu_index].strip().isdigit():
+                idx = int(ids[gpu_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        local = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0) & local
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return len(allowed)
+    except Exception:
+        return None
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -481,9 +507,21 @@ def run_ours(args, wl):
         raise RuntimeError("bench.py needs a CUDA device: minimarl_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the ONE JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the ONE JSON line only: NCCL prints its version banner to fd 1 when NCCL_DEBUG is set, so fd 1 points
+        # at stderr while the communicator is created (init + one warm-up all-reduce)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     n, T, A = wl["n_envs"], wl["T"], AGENTS
     D = 47 * (2 if wl["full_observable"] else 1)
@@ -616,7 +654,8 @@ def run_ours(args, wl):
                        "step": "reset + T-step rollout into the rollout buffer + GAE/advantages",
                        "l2": f"outputs {n * T * ENV_STEP_BYTES / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)"
                        if n * T * ENV_STEP_BYTES > 126e6 else "working set below L2; buffer rewritten every step",
-                       "parallelism": f"env-shard x{world}, no data-path collective"},
+                       "parallelism": f"env-shard x{world}, no data-path collective",
+                       "host_cores_local_to_gpu": numa},
             "roofline": {"bound": "hbm", "kernel": "checkers_rollout_kernel", "achieved": achieved, "peak": peak,
                          "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_launch": n * T * ENV_STEP_BYTES, "kernel_ms": rollout_ms},
