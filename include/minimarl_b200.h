@@ -317,7 +317,7 @@ int mm_heaptree_argmin_leaf(const double* tree, int32_t capacity, int64_t* leaf_
  * launch -- what N lockstep envs hand the buffer at every chunk boundary.  Item i goes to data slot n_data while the
  * buffer is filling (n_data = fill count before the call), afterwards to the arg-min-priority leaf as it is AFTER
  * items 0..i-1 went in (a later item of the batch may evict an earlier one).  slot_out[i] = data slot of item i.
- * MM_ERR_UNSUPPORTED when the arg-min tree (12 B per slot) does not fit in shared memory (capacity > ~14 500). */
+ * MM_ERR_UNSUPPORTED when the sum tree (16 B per slot) does not fit in shared memory (capacity > ~14 000). */
 int mm_heaptree_add_batch(double* tree, int32_t capacity, int32_t n_data, const double* priority, int32_t k,
                           int64_t* slot_out, void* stream);
 

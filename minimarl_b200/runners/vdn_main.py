@@ -18,6 +18,76 @@ from ..algorithms.toplevel import Mix_Net, Prioritized_Experience_Replay, Q_Net,
 from ..envs.batched import BatchedCheckers, BatchedSwitch
 
 
+class _ChunkGraph:
+    """One chunk (``chunk_size`` env steps of all lockstep envs) of the rollout body as ONE CUDA graph.
+
+    The body -- ``sample_action``, the env kernel, the target forward, ``cal_td_error``, the chunk / score bookkeeping -- is
+    ~60 small launches per step on a few thousand rows: launch-bound from Python (1.5 ms per step at 4 096 envs).  Captured
+    once into static tensors and replayed per chunk it runs at GPU speed.  epsilon is a device scalar so that one graph
+    serves every episode; the random draws come from the default generator, which torch registers with the capture."""
+
+    def __init__(self, beh, tgt, env, args):
+        dev, n, L = env.device, env.n_envs, args.chunk_size
+        self.beh, self.tgt, self.env, self.gamma, self.L = beh, tgt, env, args.gamma, L
+        z = dict(dtype=torch.float32, device=dev)
+        A, D = env.n_agents, env.obs_dim
+        self.state = torch.zeros((n, A, D), **z)
+        self.hidden, self.target_hidden = beh.init_hidden(n), tgt.init_hidden(n)
+        self.eps = torch.zeros((), **z)
+        self.score = torch.zeros(n, **z)
+        self.alive = torch.ones(n, dtype=torch.bool, device=dev)
+        self.td_sum = torch.zeros(n, **z)
+        self.chunk = [torch.zeros((n, L, A, D), **z), torch.zeros((n, L, A), **z), torch.zeros((n, L, A), **z),
+                      torch.zeros((n, L, A, D), **z), torch.zeros((n, L), **z)]
+        self.graph = None
+
+    def _body(self):
+        s, a_, r_, n_, d_ = self.chunk
+        self.td_sum.zero_()
+        state, hidden, target_hidden = self.state, self.hidden, self.target_hidden
+        for l in range(self.L):
+            action, next_hidden, behavior_q = self.beh.sample_action(state, hidden, self.eps)
+            next_state, reward, done = self.env.step(action)
+            target_q, target_hidden = self.tgt(next_state, target_hidden)
+            done_all = done.all(1)
+            done_env = done_all.float()
+            self.td_sum += cal_td_error(action, reward, done_env, behavior_q, target_q, self.gamma)
+            s[:, l], a_[:, l], r_[:, l], n_[:, l], d_[:, l] = state, action, reward, next_state, done_env
+            self.score += reward.sum(1) * self.alive
+            self.alive &= ~done_all
+            state, hidden = next_state, next_hidden
+        self.state.copy_(state)
+        self.hidden.copy_(hidden)
+        self.target_hidden.copy_(target_hidden)
+
+    def begin_episode(self, obs, epsilon):
+        self.state.copy_(obs)
+        self.hidden.zero_(); self.target_hidden.zero_(); self.score.zero_(); self.alive.fill_(True)
+        self.eps.fill_(float(epsilon))
+
+    def capture(self):
+        if self.graph is None:
+            snap = [t.clone() for t in (self.state, self.hidden, self.target_hidden, self.score, self.alive, self.env.state)]
+            side = torch.cuda.Stream(device=self.state.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():                 # warm-up outside the capture (allocator, cuBLAS)
+                self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            for t, v in zip((self.state, self.hidden, self.target_hidden, self.score, self.alive, self.env.state), snap):
+                t.copy_(v)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(self.graph):
+                self._body()
+            for t, v in zip((self.state, self.hidden, self.target_hidden, self.score, self.alive, self.env.state), snap):
+                t.copy_(v)                                                 # capture does not execute, but keep it explicit
+        return self
+
+    def run_chunk(self):
+        self.capture()
+        self.graph.replay()
+        return self.chunk, self.td_sum
+
+
 def _run(args, env, episodes, mixer, log, timing):
     dev, n_envs = env.device, env.n_envs
     beh = Q_Net(env.observation_space, env.action_space, args).to(dev)
@@ -36,6 +106,7 @@ def _run(args, env, episodes, mixer, log, timing):
         trainer = Target_Dqn(per, beh, tgt, args, dev)
         train = lambda eps: trainer.train(target_network=tgt, optimizer=opt, epsilon=eps)
     L = args.chunk_size
+    graph = _ChunkGraph(beh, tgt, env, args).capture() if getattr(args, "rollout_graph", True) else None   # one-time capture
     history = []
     t_roll = t_train = 0.0
     env_steps = 0
@@ -45,32 +116,42 @@ def _run(args, env, episodes, mixer, log, timing):
         if timing is not None:
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-        state = env.reset()
-        hidden, target_hidden = beh.init_hidden(n_envs), tgt.init_hidden(n_envs)
-        score = torch.zeros(n_envs, device=dev)
-        alive = torch.ones(n_envs, dtype=torch.bool, device=dev)
-        chunk = {k: [] for k in "sarnd"}
-        td_sum = torch.zeros(n_envs, device=dev)
-        with torch.no_grad():
-            for step in range(args.max_step):
-                action, next_hidden, behavior_q = beh.sample_action(state, hidden, epsilon)
-                next_state, reward, done = env.step(action)
-                target_q, target_hidden = tgt(next_state, target_hidden)
-                done_env = done.all(1).float()
-                td_sum += cal_td_error(action, reward, done_env, behavior_q, target_q, args.gamma)
-                for k, v in zip("sarnd", (state, action, reward, next_state, done_env)):
-                    chunk[k].append(v)
-                score += reward.sum(1) * alive
-                alive &= ~done.all(1)
-                env_steps += n_envs
-                if (step + 1) % L == 0:
-                    stack = [torch.stack(chunk[k], 1) for k in "sarnd"]
-                    per.collect_samples_batch(stack, td_sum, warm_up=False)    # one chunk per env, in env order
-                    chunk = {k: [] for k in "sarnd"}
-                    td_sum = torch.zeros(n_envs, device=dev)
-                    if not bool(alive.any()):                                # the reference stops at `all(done)`
-                        break
-                state, hidden = next_state, next_hidden
+        if graph is not None:
+            graph.begin_episode(env.reset(), epsilon)
+            for _ in range(args.max_step // L):
+                chunk_tensors, td_sum = graph.run_chunk()
+                per.collect_samples_batch(chunk_tensors, td_sum, warm_up=False)    # one chunk per env, in env order
+                env_steps += n_envs * L
+                if not bool(graph.alive.any()):                              # the reference stops at `all(done)`
+                    break
+            score = graph.score
+        else:
+            state = env.reset()
+            hidden, target_hidden = beh.init_hidden(n_envs), tgt.init_hidden(n_envs)
+            score = torch.zeros(n_envs, device=dev)
+            alive = torch.ones(n_envs, dtype=torch.bool, device=dev)
+            chunk = {k: [] for k in "sarnd"}
+            td_sum = torch.zeros(n_envs, device=dev)
+            with torch.no_grad():
+                for step in range(args.max_step):
+                    action, next_hidden, behavior_q = beh.sample_action(state, hidden, epsilon)
+                    next_state, reward, done = env.step(action)
+                    target_q, target_hidden = tgt(next_state, target_hidden)
+                    done_env = done.all(1).float()
+                    td_sum += cal_td_error(action, reward, done_env, behavior_q, target_q, args.gamma)
+                    for k, v in zip("sarnd", (state, action, reward, next_state, done_env)):
+                        chunk[k].append(v)
+                    score += reward.sum(1) * alive
+                    alive &= ~done.all(1)
+                    env_steps += n_envs
+                    if (step + 1) % L == 0:
+                        stack = [torch.stack(chunk[k], 1) for k in "sarnd"]
+                        per.collect_samples_batch(stack, td_sum, warm_up=False)    # one chunk per env, in env order
+                        chunk = {k: [] for k in "sarnd"}
+                        td_sum = torch.zeros(n_envs, device=dev)
+                        if not bool(alive.any()):                                # the reference stops at `all(done)`
+                            break
+                    state, hidden = next_state, next_hidden
         if timing is not None:
             torch.cuda.synchronize(dev)
             t1 = time.perf_counter()
