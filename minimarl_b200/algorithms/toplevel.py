@@ -239,6 +239,22 @@ class Prioritized_Experience_Replay:
             self.alpha_increment_per_sampling = self.beta_increment_per_sampling = 0
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(getattr(args, "seed", 0)))
+        self._sched = None            # graph mode: [alpha, beta] as a device float64 pair, advanced inside the captured graph
+
+    # -- CUDA-graph support: the annealed exponents must be device values, or a captured sample() would replay stale ones ----
+    def enable_graph_mode(self):
+        """``sample`` / ``update`` read alpha and beta from a device tensor that ``sample`` itself advances (so one captured
+        training iteration can be replayed), and draw their uniforms from the default generator (which torch registers with
+        a capture).  The host copies ``self.alpha`` / ``self.beta`` are advanced by ``advance_host_schedule`` once per
+        iteration, with the same float64 arithmetic."""
+        if self._sched is None:
+            self._sched = torch.tensor([self.alpha, self.beta], dtype=torch.float64, device=self.device)
+            self._sched_inc = torch.tensor([self.alpha_increment_per_sampling, self.beta_increment_per_sampling],
+                                           dtype=torch.float64, device=self.device)
+
+    def advance_host_schedule(self):
+        self.alpha = float(np.min([1., self.alpha + self.alpha_increment_per_sampling]))
+        self.beta = float(np.min([1., self.beta + self.beta_increment_per_sampling]))
 
     def _get_priority(self, td_error):
         """(td + eps) ** alpha in the arithmetic of the argument, like the reference: Python floats stay Python
@@ -246,6 +262,8 @@ class Prioritized_Experience_Replay:
         if isinstance(td_error, (float, int, np.floating)):
             return (float(td_error) + self.eps) ** self.alpha
         td = torch.as_tensor(td_error, device=self.device)
+        if self._sched is not None:
+            return torch.pow(td + self.eps, self._sched[0].to(td.dtype)).to(torch.float64)
         return ((td + self.eps) ** self.alpha).to(torch.float64)
 
     def collect_sample(self, sample, td_error, warm_up):
@@ -306,10 +324,15 @@ class Prioritized_Experience_Replay:
     def sample(self, batch_size, _chunk_size, uniforms=None):
         """7-tuple of the reference (buffer.py:81-86), all CUDA tensors; priority_idxs is an int64 tensor of NODE ids."""
         tree = self.sum_tree
-        self.alpha = float(np.min([1., self.alpha + self.alpha_increment_per_sampling]))
-        self.beta = float(np.min([1., self.beta + self.beta_increment_per_sampling]))
+        if self._sched is not None:
+            self._sched.add_(self._sched_inc).clamp_(max=1.0)
+            beta = self._sched[1]
+        else:
+            self.advance_host_schedule()
+            beta = self.beta
         if uniforms is None:
-            uniforms = torch.rand(batch_size, dtype=torch.float64, device=self.device, generator=self._gen)
+            uniforms = torch.rand(batch_size, dtype=torch.float64, device=self.device,
+                                  generator=None if self._sched is not None else self._gen)
         else:
             uniforms = torch.as_tensor(np.asarray(uniforms) if not torch.is_tensor(uniforms) else uniforms,
                                        dtype=torch.float64, device=self.device).contiguous()
@@ -318,7 +341,7 @@ class Prioritized_Experience_Replay:
         if self.use_step_weight:
             tree.priority_tree.mul_(self.step_weight)
         probs = prio / tree.total()
-        w = torch.pow(self.capacity * probs, -self.beta)
+        w = torch.pow(self.capacity * probs, -beta)
         w = (w / w.max()).to(torch.float32).view(batch_size, 1)
         return (self.states[data], self.actions[data], self.rewards[data], self.next_states[data], self.dones[data],
                 node, w)
@@ -327,7 +350,46 @@ class Prioritized_Experience_Replay:
         self.sum_tree.update(priority_idx, self._get_priority(new_td_error))
 
 
-class Target_Dqn:
+class _GraphedIterations:
+    """Runs ``update_iter`` training iterations; with ``use_graph`` the iteration (PER draw, chunk forward of both networks,
+    loss, backward, clipping, Adam step, priority write-back: ~700 small launches) is captured ONCE as a CUDA graph and
+    replayed -- the loop is launch-bound from Python, not GPU-bound.  The first iteration of the first call runs eagerly on a
+    side stream (it is a real update and doubles as the warm-up a capture needs); the optimiser must be ``capturable``."""
+
+    use_graph = False
+    _graph = None
+
+    def _run_iterations(self, per, optimizer, iteration):
+        if not self.use_graph:
+            total = 0
+            for _ in range(self.update_iter):
+                total = total + iteration(None)
+                if per._sched is not None:                       # device-side schedule: the host copy follows
+                    per.advance_host_schedule()
+            return total / self.update_iter
+        done, total = 0, 0
+        if self._graph is None:
+            per.enable_graph_mode()
+            main = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=per.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                total = total + iteration(None).clone()
+            main.wait_stream(side)
+            per.advance_host_schedule()
+            done = 1
+            optimizer.zero_grad(set_to_none=True)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._static_loss = iteration(None)
+        for _ in range(self.update_iter - done):
+            self._graph.replay()
+            per.advance_host_schedule()
+            total = total + self._static_loss
+        return total / self.update_iter
+
+
+class Target_Dqn(_GraphedIterations):
     """vdn/_train.py:56-101."""
 
     def __init__(self, Replay_buffer, behavior_network, target_network, args, device):
@@ -335,74 +397,85 @@ class Target_Dqn:
         self.batch_size, self.update_iter = args.batch_size, args.update_iter
         self.chunk_size = args.chunk_size if args.use_recurrent else 1
         self.gamma, self.grad_clip_norm, self.device = args.gamma, args.grad_clip_norm, device
+        self.use_graph = bool(getattr(args, "train_graph", False))
+
+    def _iteration(self, target_network, optimizer, u):
+        states, actions, rewards, next_states, dones, priority_idx, is_weight = \
+            self.replay_buffer.sample(self.batch_size, self.chunk_size, uniforms=u)
+        hidden = self.behavior_network.init_hidden(self.batch_size)
+        target_hidden = target_network.init_hidden(self.batch_size)
+        loss = 0.0
+        for step in range(self.chunk_size):
+            state, action = states[:, step], actions[:, step].unsqueeze(-1).long()
+            reward, next_state, done = rewards[:, step], next_states[:, step], dones[:, step]
+            behavior_q, next_hidden = self.behavior_network(obs=state, hidden=hidden)
+            sum_q = behavior_q.gather(dim=2, index=action).squeeze(-1).sum(dim=1, keepdims=True)
+            with torch.no_grad():
+                target_q, next_target_hidden = target_network(obs=next_state, hidden=target_hidden.detach())
+            sum_max_target_q = target_q.max(dim=2)[0].sum(dim=1, keepdims=True)
+            target_values = is_weight * (reward + self.gamma * (1 - done) * sum_max_target_q).sum(dim=1, keepdims=True)
+            loss = loss + F.mse_loss(target_values.detach(), sum_q)
+            keep = (1 - done).view(-1, 1, 1)                       # hidden rows of finished envs restart at zero
+            hidden, target_hidden = next_hidden * keep, next_target_hidden * keep
+        optimizer.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(parameters=self.behavior_network.parameters(), max_norm=self.grad_clip_norm, norm_type=2)
+        optimizer.step()
+        new_td_error = (target_values - sum_q).abs().detach().reshape(-1)   # last chunk step only (Q9)
+        self.replay_buffer.update(priority_idx, new_td_error)
+        return loss.detach()
 
     def train(self, target_network, optimizer, epsilon, uniforms=None):
-        iter_loss = 0
-        for it in range(self.update_iter):
-            u = None if uniforms is None else uniforms[it]
-            states, actions, rewards, next_states, dones, priority_idx, is_weight = \
-                self.replay_buffer.sample(self.batch_size, self.chunk_size, uniforms=u)
-            hidden = self.behavior_network.init_hidden(self.batch_size)
-            target_hidden = target_network.init_hidden(self.batch_size)
-            loss = 0.0
-            for step in range(self.chunk_size):
-                state, action = states[:, step], actions[:, step].unsqueeze(-1).long()
-                reward, next_state, done = rewards[:, step], next_states[:, step], dones[:, step]
-                behavior_q, next_hidden = self.behavior_network(obs=state, hidden=hidden)
-                sum_q = behavior_q.gather(dim=2, index=action).squeeze(-1).sum(dim=1, keepdims=True)
-                with torch.no_grad():
-                    target_q, next_target_hidden = target_network(obs=next_state, hidden=target_hidden.detach())
-                sum_max_target_q = target_q.max(dim=2)[0].sum(dim=1, keepdims=True)
-                target_values = is_weight * (reward + self.gamma * (1 - done) * sum_max_target_q).sum(dim=1, keepdims=True)
-                loss = loss + F.mse_loss(target_values.detach(), sum_q)
-                keep = (1 - done).view(-1, 1, 1)                       # hidden rows of finished envs restart at zero
-                hidden, target_hidden = next_hidden * keep, next_target_hidden * keep
-            optimizer.zero_grad()
-            loss.backward()
-            torch.nn.utils.clip_grad_norm_(parameters=self.behavior_network.parameters(), max_norm=self.grad_clip_norm, norm_type=2)
-            optimizer.step()
-            iter_loss += loss.detach()
-            new_td_error = (target_values - sum_q).abs().detach().reshape(-1)   # last chunk step only (Q9)
-            self.replay_buffer.update(priority_idx, new_td_error)
-        return iter_loss / self.update_iter
+        if uniforms is not None:                                   # recorded uniforms (tests): always the eager loop
+            total = 0
+            for it in range(self.update_iter):
+                total = total + self._iteration(target_network, optimizer, uniforms[it])
+            return total / self.update_iter
+        return self._run_iterations(self.replay_buffer, optimizer, lambda u: self._iteration(target_network, optimizer, u))
 
 
-class Train_dqn:
+class Train_dqn(_GraphedIterations):
     """qmix/_train.py:19-121: the same loop with the recurrent mixer on both sides; only q-net grads are clipped."""
 
     def __init__(self, args, device):
         self.batch_size, self.update_iter = args.batch_size, args.update_iter
         self.chunk_size = args.chunk_size if args.use_recurrent else 1
         self.gamma, self.grad_clip_norm, self.device = args.gamma, args.grad_clip_norm, device
+        self.use_graph = bool(getattr(args, "train_graph", False))
+
+    def _iteration(self, Replay_buffer, behavior_q_net, behavior_mix_net, target_q_net, target_mix_net, optimizer, u):
+        states, actions, rewards, next_states, dones, priority_idx, w = Replay_buffer.sample(self.batch_size, self.chunk_size, uniforms=u)
+        hidden, target_hidden = behavior_q_net.init_hidden(self.batch_size), target_q_net.init_hidden(self.batch_size)
+        mix_hidden, target_mix_hidden = behavior_mix_net.init_hidden(self.batch_size), target_mix_net.init_hidden(self.batch_size)
+        loss = 0.0
+        for step in range(self.chunk_size):
+            state, action = states[:, step], actions[:, step].unsqueeze(-1).long()
+            reward, next_state, done = rewards[:, step], next_states[:, step], dones[:, step]
+            behavior_q, next_hidden = behavior_q_net(state, hidden)
+            max_behavior_q = behavior_q.gather(dim=2, index=action).squeeze(-1)
+            sum_mix_q, next_mix_hidden = behavior_mix_net(max_behavior_q, state, mix_hidden)
+            with torch.no_grad():
+                target_q, next_target_hidden = target_q_net(next_state, target_hidden.detach())
+                max_target_q = target_q.max(dim=2)[0]
+                sum_target_mix_q, next_target_mix_hidden = target_mix_net(max_target_q, next_state, target_mix_hidden.detach())
+            target_values = w * (reward + self.gamma * (1 - done) * sum_target_mix_q).sum(dim=1, keepdims=True)
+            loss = loss + F.mse_loss(target_values.detach(), sum_mix_q)
+            keep = (1 - done)
+            hidden, target_hidden = next_hidden * keep.view(-1, 1, 1), next_target_hidden * keep.view(-1, 1, 1)
+            mix_hidden, target_mix_hidden = next_mix_hidden * keep, next_target_mix_hidden * keep
+        optimizer.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(parameters=behavior_q_net.parameters(), max_norm=self.grad_clip_norm, norm_type=2)
+        optimizer.step()
+        Replay_buffer.update(priority_idx, (target_values - sum_mix_q).abs().detach().reshape(-1))
+        return loss.detach()
 
     def train(self, Replay_buffer, behavior_q_net, behavior_mix_net, target_q_net, target_mix_net, optimizer, epsilon,
               uniforms=None):
-        iter_loss = 0
-        for it in range(self.update_iter):
-            u = None if uniforms is None else uniforms[it]
-            states, actions, rewards, next_states, dones, priority_idx, w = Replay_buffer.sample(self.batch_size, self.chunk_size, uniforms=u)
-            hidden, target_hidden = behavior_q_net.init_hidden(self.batch_size), target_q_net.init_hidden(self.batch_size)
-            mix_hidden, target_mix_hidden = behavior_mix_net.init_hidden(self.batch_size), target_mix_net.init_hidden(self.batch_size)
-            loss = 0.0
-            for step in range(self.chunk_size):
-                state, action = states[:, step], actions[:, step].unsqueeze(-1).long()
-                reward, next_state, done = rewards[:, step], next_states[:, step], dones[:, step]
-                behavior_q, next_hidden = behavior_q_net(state, hidden)
-                max_behavior_q = behavior_q.gather(dim=2, index=action).squeeze(-1)
-                sum_mix_q, next_mix_hidden = behavior_mix_net(max_behavior_q, state, mix_hidden)
-                with torch.no_grad():
-                    target_q, next_target_hidden = target_q_net(next_state, target_hidden.detach())
-                    max_target_q = target_q.max(dim=2)[0]
-                    sum_target_mix_q, next_target_mix_hidden = target_mix_net(max_target_q, next_state, target_mix_hidden.detach())
-                target_values = w * (reward + self.gamma * (1 - done) * sum_target_mix_q).sum(dim=1, keepdims=True)
-                loss = loss + F.mse_loss(target_values.detach(), sum_mix_q)
-                keep = (1 - done)
-                hidden, target_hidden = next_hidden * keep.view(-1, 1, 1), next_target_hidden * keep.view(-1, 1, 1)
-                mix_hidden, target_mix_hidden = next_mix_hidden * keep, next_target_mix_hidden * keep
-            optimizer.zero_grad()
-            loss.backward()
-            torch.nn.utils.clip_grad_norm_(parameters=behavior_q_net.parameters(), max_norm=self.grad_clip_norm, norm_type=2)
-            optimizer.step()
-            iter_loss += loss.detach()
-            Replay_buffer.update(priority_idx, (target_values - sum_mix_q).abs().detach().reshape(-1))
-        return iter_loss / self.update_iter
+        nets = (Replay_buffer, behavior_q_net, behavior_mix_net, target_q_net, target_mix_net, optimizer)
+        if uniforms is not None:                                   # recorded uniforms (tests): always the eager loop
+            total = 0
+            for it in range(self.update_iter):
+                total = total + self._iteration(*nets, uniforms[it])
+            return total / self.update_iter
+        return self._run_iterations(Replay_buffer, optimizer, lambda u: self._iteration(*nets, u))

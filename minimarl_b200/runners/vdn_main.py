@@ -94,21 +94,22 @@ def _run(args, env, episodes, mixer, log, timing):
     tgt = Q_Net(env.observation_space, env.action_space, args).to(dev)
     tgt.load_state_dict(beh.state_dict())
     per = Prioritized_Experience_Replay(args, n_agents=env.n_agents, obs_dim=env.obs_dim, device=dev)
+    use_graph = bool(getattr(args, "train_graph", False))            # capture one training iteration as a CUDA graph
     if mixer:
         mix, tmix = Mix_Net(env.observation_space, args).to(dev), Mix_Net(env.observation_space, args).to(dev)
         tmix.load_state_dict(mix.state_dict())
-        opt = torch.optim.Adam([{"params": beh.parameters()}, {"params": mix.parameters()}], lr=args.lr)
+        opt = torch.optim.Adam([{"params": beh.parameters()}, {"params": mix.parameters()}], lr=args.lr, capturable=use_graph)
         trainer = Train_dqn(args, dev)
         train = lambda eps: trainer.train(per, beh, mix, tgt, tmix, opt, eps)
     else:
         mix = tmix = None
-        opt = torch.optim.Adam(beh.parameters(), lr=args.lr)
+        opt = torch.optim.Adam(beh.parameters(), lr=args.lr, capturable=use_graph)
         trainer = Target_Dqn(per, beh, tgt, args, dev)
         train = lambda eps: trainer.train(target_network=tgt, optimizer=opt, epsilon=eps)
     L = args.chunk_size
     graph = _ChunkGraph(beh, tgt, env, args).capture() if getattr(args, "rollout_graph", True) else None   # one-time capture
     history = []
-    t_roll = t_train = 0.0
+    t_roll, t_train = [], []
     env_steps = 0
     for episode in range(episodes):
         epsilon = max(args.min_epsilon, args.max_epsilon - (args.max_epsilon - args.min_epsilon) *
@@ -155,7 +156,7 @@ def _run(args, env, episodes, mixer, log, timing):
         if timing is not None:
             torch.cuda.synchronize(dev)
             t1 = time.perf_counter()
-            t_roll += t1 - t0
+            t_roll.append(t1 - t0)
         loss = train(epsilon) if per.sum_tree.n_data >= args.batch_size else torch.tensor(float("nan"))
         if episode % args.update_target_interval == 0:
             tgt.load_state_dict(beh.state_dict())
@@ -163,14 +164,15 @@ def _run(args, env, episodes, mixer, log, timing):
                 tmix.load_state_dict(mix.state_dict())
         if timing is not None:
             torch.cuda.synchronize(dev)
-            t_train += time.perf_counter() - t1
+            t_train.append(time.perf_counter() - t1)
         rec = {"episode": episode, "train_score": score.mean().item(), "train_loss": float(loss), "eps": epsilon,
                "alpha": per.alpha, "beta": per.beta}
         history.append(rec)
         if log:
             log(rec)
     if timing is not None:
-        timing.update(rollout_s=t_roll, train_s=t_train, env_steps=env_steps, chunks_in_buffer=per.sum_tree.n_data)
+        timing.update(rollout_s=sum(t_roll), train_s=sum(t_train), rollout_s_per_episode=t_roll, train_s_per_episode=t_train,
+                      env_steps=env_steps, chunks_in_buffer=per.sum_tree.n_data)
     return history, beh
 
 
