@@ -331,6 +331,36 @@ def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
     return out
 
 
+def switch_rollout_section(dev, steps=10):
+    """Switch2-v0 (the qmix/_config.py default env, BASELINE configs[1]) stepped by mm_switch_rollout: T lockstep steps per launch.
+    Algorithmic bytes per env-step (A = 2, D = 3): actions 8 + state 12 r + 12 w + obs 24 + rewards 8 + dones 2 = 66 B."""
+    import torch
+    from minimarl_b200 import BatchedSwitch
+    peak, _ = measured_peaks()
+    out = {}
+    for n, T in ((4096, 100), (262144, 128)):
+        env = BatchedSwitch(n, max_steps=100, step_cost=-0.01, device=dev)
+        acts = torch.randint(0, 5, (T, n, 2), dtype=torch.int32, device=dev, generator=torch.Generator(dev).manual_seed(42))
+        bufs = env.new_outputs(T)
+        for _ in range(3):
+            env.reset()
+            env.rollout(T, actions=acts, out=bufs)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            env.rollout(T, actions=acts, out=bufs)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        gbs = n * T * 66 / (ms * 1e-3) / 1e9
+        out[f"n_envs_{n}_T_{T}"] = {"ms_per_rollout": ms, "agent_steps_per_s": n * T * 2 / (ms * 1e-3),
+                                    "algorithmic_GBps": gbs, "frac_of_measured_hbm": gbs / peak}
+    out["note"] = ("4 096 envs are 64 warps: the launch is bound by the latency of 100 dependent steps (0.35 us each), not by "
+                   "HBM; the roofline fraction is meaningful at the large size")
+    return out
+
+
 def qmix_toplevel_section(dev, episodes=3, n_envs=4096):
     """BASELINE configs[1]: the qmix/main.py loop on 4 096 lockstep Switch2-v0 envs (the qmix/_config.py default env) with
     the chunk replay on the GPU: Q_Net.sample_action -> lockstep env kernel -> target Q_Net -> cal_td_error per step,
@@ -689,6 +719,10 @@ def run_ours(args, wl):
                 line["policy_rollout"] = {"error": f"{type(e).__name__}: {e}"}
             line["learner"] = learner
             line["mappo_iteration"] = mappo_it
+            try:
+                line["env_switch2"] = switch_rollout_section(dev)
+            except Exception as e:
+                line["env_switch2"] = {"error": f"{type(e).__name__}: {e}"}
             try:
                 line["qmix_toplevel"] = qmix_toplevel_section(dev)
             except Exception as e:

@@ -128,6 +128,11 @@ int mm_switch_reset(uint32_t* state, const uint8_t* reset_mask, float* obs,
 int mm_switch_step(uint32_t* state, const int32_t* actions, float* obs, float* rewards,
                    uint8_t* dones, int32_t* bad_action_flag,
                    const mm_switch_cfg* cfg_host, void* stream);
+/* T lockstep steps in one launch, state in registers between steps; arguments as mm_checkers_rollout (actions [T,N,A] or
+ * NULL for device-drawn uniform actions, obs [T,N,A,D] / rewards [T,N,A] / dones [T,N,A], any of them NULL to skip). */
+int mm_switch_rollout(uint32_t* state, const int32_t* actions, int32_t* actions_out, float* obs, float* rewards,
+                      uint8_t* dones, int32_t* bad_action_flag, int32_t T, uint64_t seed, uint64_t step_offset,
+                      const mm_switch_cfg* cfg_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GAE / returns reverse scan: SharedReplayBuffer.compute_returns

@@ -54,6 +54,8 @@ SIGNATURES = {
     "mm_checkers_rollout_host": (C.c_int, [_P] * 10 + [C.c_int32, C.c_int32, C.POINTER(CheckersCfg), _P, _P]),
     "mm_switch_reset": (C.c_int, [_P, _P, _P, C.POINTER(SwitchCfg), _P]),
     "mm_switch_step": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(SwitchCfg), _P]),
+    "mm_switch_rollout": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_uint64, C.c_uint64,
+                                    C.POINTER(SwitchCfg), _P]),
     "mm_gae_returns": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_double, C.c_double,
                                  C.c_int32, C.c_int32, C.c_float, C.c_float, _P]),
     "mm_segtree_set": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_double, C.c_int64, C.c_int32, _P]),

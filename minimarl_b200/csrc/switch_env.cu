@@ -72,56 +72,79 @@ switch_reset_kernel(uint32_t* __restrict__ state, const uint8_t* __restrict__ re
     if (obs != nullptr) write_obs<A>(obs, env, agent, cells, step, cfg);
 }
 
+// T lockstep steps in one launch (T = 1 is env.step): env state stays in registers between steps, the action of step
+// t + 1 is fetched while step t is computed.  actions == nullptr: uniform actions from Philox4x32-10 keyed by (seed), counter
+// (step_offset + t, row), like checkers_rollout_kernel.
 template <int A>
 __global__ void __launch_bounds__(kThreads)
-switch_step_kernel(uint32_t* __restrict__ state, const int32_t* __restrict__ actions,
-                   float* __restrict__ obs, float* __restrict__ rewards, uint8_t* __restrict__ dones,
-                   int32_t* __restrict__ bad_action_flag, const __grid_constant__ mm_switch_cfg cfg) {
+switch_rollout_kernel(uint32_t* __restrict__ state, const int32_t* __restrict__ actions, int32_t* __restrict__ actions_out,
+                      float* __restrict__ obs, float* __restrict__ rewards, uint8_t* __restrict__ dones,
+                      int32_t* __restrict__ bad_action_flag, int T, uint2 seed, unsigned long long step_offset,
+                      const __grid_constant__ mm_switch_cfg cfg) {
     const int gid = blockIdx.x * kThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int env = gid / A, agent = gid % A;
     const bool valid = env < cfg.n_envs;
     const int n = cfg.n_envs;
     const int env_c = valid ? env : n - 1;
+    const size_t rows = (size_t)n * A, row = (size_t)env_c * A + agent;
+    const size_t obs_step = rows * (size_t)((2 + (cfg.clock ? 1 : 0)) * (cfg.full_observable ? A : 1));
     uint32_t cells = state[env_c];
     uint32_t done = state[n + env_c];
-    uint32_t step = state[2 * n + env_c] + 1;
-    const int my_act = actions[(size_t)env_c * A + agent];
-    const bool bad = (unsigned)my_act > 4u;
-    float reward = cfg.step_cost;
+    uint32_t step = state[2 * n + env_c];
     const int group = lane & ~(A - 1);
+    bool any_bad = false;
+    int act_next = actions != nullptr ? actions[row] : 0;
+    for (int t = 0; t < T; ++t) {
+        int my_act;
+        if (actions != nullptr) {
+            my_act = act_next;
+            if (t + 1 < T) act_next = actions[(size_t)(t + 1) * rows + row];
+        } else {
+            const unsigned long long ctr = step_offset + (unsigned long long)t;
+            const uint4 rnd = mm::philox4x32_10(
+                make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)row, (uint32_t)((unsigned long long)row >> 32)), seed);
+            my_act = (int)__umulhi(rnd.x, 5u);
+            if (actions_out != nullptr && valid) actions_out[(size_t)t * rows + row] = my_act;
+        }
+        any_bad |= (unsigned)my_act > 4u;
+        step += 1;
+        float reward = cfg.step_cost;
 #pragma unroll
-    for (int a = 0; a < A; ++a) {
-        const int act = __shfl_sync(MM_FULL_MASK, my_act, group + a);
-        if ((done >> a) & 1u) continue;                      // finished agents no longer move
-        const uint32_t cell = (cells >> (8 * a)) & 0xffu;
-        const int r = cell >> 3, c = cell & 7;
-        const int nr = r + (act == 0) - (act == 2);
-        const int nc = c + (act == 3) - (act == 1);
-        uint32_t occupied = 0;
+        for (int a = 0; a < A; ++a) {
+            const int act = __shfl_sync(MM_FULL_MASK, my_act, group + a);
+            if ((done >> a) & 1u) continue;                      // finished agents no longer move
+            const uint32_t cell = (cells >> (8 * a)) & 0xffu;
+            const int r = cell >> 3, c = cell & 7;
+            const int nr = r + (act == 0) - (act == 2);
+            const int nc = c + (act == 3) - (act == 1);
+            uint32_t occupied = 0;
 #pragma unroll
-        for (int b = 0; b < A; ++b) occupied |= 1u << ((cells >> (8 * b)) & 0xffu);
-        const uint32_t target = (uint32_t)(nr * 8 + nc);
-        const bool vacant = ((unsigned)act < 4u) && ((unsigned)nr < 3u) && ((unsigned)nc < 7u) &&
-                            (((kFreeCells & ~occupied) >> target) & 1u);
-        const uint32_t now = vacant ? target : cell;
-        cells = (cells & ~(0xffu << (8 * a))) | (now << (8 * a));
-        if (now == goal_cell(a)) {
-            done |= 1u << a;
-            if (a == agent) reward = cfg.goal_reward;        // assignment, not +=, as in ma-gym
+            for (int b = 0; b < A; ++b) occupied |= 1u << ((cells >> (8 * b)) & 0xffu);
+            const uint32_t target = (uint32_t)(nr * 8 + nc);
+            const bool vacant = ((unsigned)act < 4u) && ((unsigned)nr < 3u) && ((unsigned)nc < 7u) &&
+                                (((kFreeCells & ~occupied) >> target) & 1u);
+            const uint32_t now = vacant ? target : cell;
+            cells = (cells & ~(0xffu << (8 * a))) | (now << (8 * a));
+            if (now == goal_cell(a)) {
+                done |= 1u << a;
+                if (a == agent) reward = cfg.goal_reward;        // assignment, not +=, as in ma-gym
+            }
+        }
+        if ((int)step >= cfg.max_steps) done = (1u << A) - 1u;
+        if (valid) {
+            if (rewards != nullptr) rewards[(size_t)t * rows + row] = reward;
+            if (dones != nullptr) dones[(size_t)t * rows + row] = (uint8_t)((done >> agent) & 1u);
+            if (obs != nullptr) write_obs<A>(obs + (size_t)t * obs_step, env, agent, cells, step, cfg);
         }
     }
-    if ((int)step >= cfg.max_steps) done = (1u << A) - 1u;
     if (!valid) return;
     if (agent == 0) {
         state[env] = cells;
         state[n + env] = done;
         state[2 * n + env] = step;
     }
-    rewards[(size_t)env * A + agent] = reward;
-    dones[(size_t)env * A + agent] = (uint8_t)((done >> agent) & 1u);
-    if (bad && bad_action_flag != nullptr) *bad_action_flag = 1;
-    write_obs<A>(obs, env, agent, cells, step, cfg);
+    if (any_bad && bad_action_flag != nullptr) *bad_action_flag = 1;
 }
 
 int validate(const uint32_t* state, const mm_switch_cfg* cfg) {
@@ -144,17 +167,27 @@ extern "C" int mm_switch_reset(uint32_t* state, const uint8_t* reset_mask, float
     return mm::check_launch();
 }
 
-extern "C" int mm_switch_step(uint32_t* state, const int32_t* actions, float* obs, float* rewards,
-                              uint8_t* dones, int32_t* bad_action_flag, const mm_switch_cfg* cfg,
-                              void* stream) {
+extern "C" int mm_switch_rollout(uint32_t* state, const int32_t* actions, int32_t* actions_out, float* obs, float* rewards,
+                                 uint8_t* dones, int32_t* bad_action_flag, int32_t T, uint64_t seed, uint64_t step_offset,
+                                 const mm_switch_cfg* cfg, void* stream) {
     if (int rc = validate(state, cfg)) return rc;
-    if (actions == nullptr || obs == nullptr || rewards == nullptr || dones == nullptr) return MM_ERR_BAD_ARG;
+    if (T <= 0) return MM_ERR_BAD_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long threads = (long long)cfg->n_envs * cfg->n_agents;
     const dim3 grid((unsigned)((threads + kThreads - 1) / kThreads));
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     if (cfg->n_agents == 2)
-        switch_step_kernel<2><<<grid, kThreads, 0, st>>>(state, actions, obs, rewards, dones, bad_action_flag, *cfg);
+        switch_rollout_kernel<2><<<grid, kThreads, 0, st>>>(state, actions, actions_out, obs, rewards, dones, bad_action_flag, T,
+                                                            key, step_offset, *cfg);
     else
-        switch_step_kernel<4><<<grid, kThreads, 0, st>>>(state, actions, obs, rewards, dones, bad_action_flag, *cfg);
+        switch_rollout_kernel<4><<<grid, kThreads, 0, st>>>(state, actions, actions_out, obs, rewards, dones, bad_action_flag, T,
+                                                            key, step_offset, *cfg);
     return mm::check_launch();
+}
+
+extern "C" int mm_switch_step(uint32_t* state, const int32_t* actions, float* obs, float* rewards,
+                              uint8_t* dones, int32_t* bad_action_flag, const mm_switch_cfg* cfg,
+                              void* stream) {
+    if (actions == nullptr || obs == nullptr || rewards == nullptr || dones == nullptr) return MM_ERR_BAD_ARG;
+    return mm_switch_rollout(state, actions, nullptr, obs, rewards, dones, bad_action_flag, 1, 0, 0, cfg, stream);
 }

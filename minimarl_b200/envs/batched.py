@@ -268,6 +268,18 @@ class BatchedSwitch(_BatchedBase):
             _lib.ptr(self.state), _lib.ptr(actions), _lib.ptr(obs), _lib.ptr(rewards), _lib.ptr(dones),
             _lib.ptr(self.bad_action), C.byref(self.cfg), _lib.stream()))
 
+    def rollout(self, T, actions=None, seed=0, step_offset=0, out=None, actions_out=None, want_obs=True):
+        """T lockstep steps in ONE launch (``mm_switch_rollout``); arguments and results as ``BatchedCheckers.rollout``."""
+        if actions is not None:
+            actions = actions.to(device=self.device, dtype=torch.int32).reshape(T, self.n_envs, self.n_agents).contiguous()
+        obs, rew, done = out if out is not None else self.new_outputs(T)
+        if not want_obs:
+            obs = None
+        _lib.check(_lib.lib().mm_switch_rollout(
+            _lib.ptr(self.state), _lib.ptr(actions), _lib.ptr(actions_out), _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(done),
+            _lib.ptr(self.bad_action), int(T), int(seed), int(step_offset), C.byref(self.cfg), _lib.stream()))
+        return obs, rew, done.view(torch.bool)
+
     def positions(self):
         cells = self.state[0].to(torch.int64)
         per = torch.stack([(cells >> (8 * a)) & 0xFF for a in range(self.n_agents)], dim=1)

@@ -227,6 +227,40 @@ def test_switch_step_matches_oracle(cuda, n_agents, full):
     assert (rew.cpu().numpy() == 5).sum() == 0 or True
 
 
+@pytest.mark.parametrize("n_agents,full", [(2, False), (4, True)])
+def test_switch_rollout_kernel_matches_oracle(cuda, n_agents, full):
+    """mm_switch_rollout (T steps in one launch): given actions vs the oracle step by step; device-drawn actions are
+    written out and replay through the oracle to the same observations, rewards, dones and final positions."""
+    from minimarl_b200 import BatchedSwitch
+    n, T, max_steps = 777, 45, 40                                # runs past max_steps
+    env = BatchedSwitch(n, n_agents=n_agents, full_observable=full, max_steps=max_steps, step_cost=-0.1, device=cuda)
+    ref = SwitchBatchRef(n, n_agents, full, max_steps, -0.1)
+    env.reset(); ref.reset()
+    rng = np.random.default_rng(5)
+    acts = rng.integers(0, 5, size=(T, n, n_agents), dtype=np.int32)
+    toward = np.where(np.arange(n_agents) % 2 == 0, 3, 1)[None, None, :]
+    acts = np.where(rng.random(acts.shape) < 0.5, toward, acts).astype(np.int32)
+    obs, rew, done = env.rollout(T, actions=torch.from_numpy(acts).to(cuda))
+    for t in range(T):
+        o, r, d = ref.step(acts[t])
+        assert np.array_equal(obs[t].cpu().numpy(), o), t
+        assert np.array_equal(rew[t].cpu().numpy(), r) and np.array_equal(done[t].cpu().numpy(), d), t
+    assert np.array_equal(env.positions().cpu().numpy(), ref.export())
+    # device-drawn actions, two launches that continue each other (step_offset)
+    env.reset(); ref.reset()
+    drawn = torch.empty((T, n, n_agents), dtype=torch.int32, device=cuda)
+    o1, r1, d1 = env.rollout(20, seed=9, step_offset=0, actions_out=drawn[:20])
+    o2, r2, d2 = env.rollout(T - 20, seed=9, step_offset=20, actions_out=drawn[20:])
+    a = drawn.cpu().numpy()
+    assert a.min() >= 0 and a.max() <= 4 and len(np.unique(a)) == 5
+    obs, rew, done = torch.cat([o1, o2]), torch.cat([r1, r2]), torch.cat([d1, d2])
+    for t in range(T):
+        o, r, d = ref.step(a[t])
+        assert np.array_equal(obs[t].cpu().numpy(), o), t
+        assert np.array_equal(rew[t].cpu().numpy(), r) and np.array_equal(done[t].cpu().numpy(), d), t
+    assert np.array_equal(env.positions().cpu().numpy(), ref.export())
+
+
 def test_full_size_rollout_properties(cuda):
     """BASELINE sizes (16 384 envs x T=128): size-independent properties instead of the slow oracle."""
     from minimarl_b200 import BatchedCheckers
