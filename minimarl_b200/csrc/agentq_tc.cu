@@ -324,10 +324,11 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
         // ---- D. GRU gates (PyTorch order r, z, n), new hidden -> sH, LayerNorm, head -------------------------
         {
             float gr[CPT], gz[CPT], gin[CPT], ghn[CPT];
-            tc::tmem_ld<CPT>(lane_addr + H + c0, gr);
-            tc::tmem_ld<CPT>(lane_addr + 2 * H + c0, gz);
-            tc::tmem_ld<CPT>(lane_addr + c0, gin);
-            tc::tmem_ld<CPT>(lane_addr + 3 * H + c0, ghn);
+            tc::tmem_ld_issue<CPT>(lane_addr + H + c0, gr);          // four loads in flight, one wait
+            tc::tmem_ld_issue<CPT>(lane_addr + 2 * H + c0, gz);
+            tc::tmem_ld_issue<CPT>(lane_addr + c0, gin);
+            tc::tmem_ld_issue<CPT>(lane_addr + 3 * H + c0, ghn);
+            tc::tmem_ld_fence<CPT>(gr, gz, gin, ghn);
 #pragma unroll
             for (int j4 = 0; j4 < CPT; j4 += 4) {
                 const float4 hp = *reinterpret_cast<const float4*>(sH + tc::kmajor_offset(row, c0 + j4, H));

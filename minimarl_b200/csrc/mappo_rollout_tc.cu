@@ -307,10 +307,11 @@ __global__ void __launch_bounds__(kThreads, 1) mappo_rollout_kernel(const __grid
         // ---- D. GRU gates -> new hidden (registers), LayerNorm, heads ---------------------------------------------
         {
             float gr[CPT], gz[CPT], gin[CPT], ghn[CPT];
-            tc::tmem_ld16(lane_addr + 64 + 64 * net + j0, gr);
-            tc::tmem_ld16(lane_addr + 64 + 64 * net + 32 + j0, gz);
-            tc::tmem_ld16(lane_addr + 192 + 32 * net + j0, gin);
-            tc::tmem_ld16(lane_addr + 256 + 32 * net + j0, ghn);
+            tc::tmem_ld16_issue(lane_addr + 64 + 64 * net + j0, gr);       // four loads in flight, one wait
+            tc::tmem_ld16_issue(lane_addr + 64 + 64 * net + 32 + j0, gz);
+            tc::tmem_ld16_issue(lane_addr + 192 + 32 * net + j0, gin);
+            tc::tmem_ld16_issue(lane_addr + 256 + 32 * net + j0, ghn);
+            tc::tmem_ld_fence<16>(gr, gz, gin, ghn);
             const float* bi = sP + L.bih + net * 3 * H + j0;
             const float* bh = sP + L.bhh + net * 3 * H + j0;
 #pragma unroll

@@ -513,10 +513,11 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
             float r[CPT], z[CPT], n[CPT], hnb[CPT], xh3[CPT], rstd3;
             {
                 float gr[CPT], gz[CPT], gin[CPT], ghn[CPT];
-                tc::tmem_ld8(lane_addr + 64 + j0, gr);
-                tc::tmem_ld8(lane_addr + 96 + j0, gz);
-                tc::tmem_ld8(lane_addr + 128 + j0, gin);
-                tc::tmem_ld8(lane_addr + 160 + j0, ghn);
+                tc::tmem_ld8_issue(lane_addr + 64 + j0, gr);       // four loads in flight, one wait
+                tc::tmem_ld8_issue(lane_addr + 96 + j0, gz);
+                tc::tmem_ld8_issue(lane_addr + 128 + j0, gin);
+                tc::tmem_ld8_issue(lane_addr + 160 + j0, ghn);
+                tc::tmem_ld_fence<CPT>(gr, gz, gin, ghn);
                 const float* bi = sP + L.bih + j0;
                 const float* bh = sP + L.bhh + j0;
                 float hn[CPT], s = 0.f, q = 0.f;
@@ -634,8 +635,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
             // ---- dx2 -> LayerNorm / ReLU backward -> dA2 ---------------------------------------------------------------
             {
                 float dhp[CPT], dx[CPT];
-                tc::tmem_ld8(lane_addr + 224 + j0, dhp);
-                tc::tmem_ld8(lane_addr + 192 + j0, dx);
+                tc::tmem_ld8_issue(lane_addr + 224 + j0, dhp);
+                tc::tmem_ld8_issue(lane_addr + 192 + j0, dx);
+                tc::tmem_ld_fence<CPT>(dhp, dx);
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) h[j] = (h[j] + dhp[j]) * mask;
                 float g[CPT], p[CPT], s = 0.f, q = 0.f;

@@ -147,6 +147,19 @@ __device__ __forceinline__ void tmem_ld_fence(float (&a)[N], float (&b)[N], floa
 }
 
 template <int N>
+__device__ __forceinline__ void tmem_ld_fence(float (&a)[N], float (&b)[N]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("" : "+f"(a[i]), "+f"(b[i]));
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_fence(float (&a)[N], float (&b)[N], float (&c)[N], float (&d)[N]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("" : "+f"(a[i]), "+f"(b[i]), "+f"(c[i]), "+f"(d[i]));
+}
+
+template <int N>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]) {
     static_assert(N == 8 || N == 16, "8 or 16 columns per load");
     if constexpr (N == 16) tmem_ld16(taddr, v);
