@@ -14,8 +14,12 @@ Workloads (per GPU):
                            configuration the agent-steps/sec metric and its roofline are quoted on)
   qmix_rollout_4096x100    BASELINE.json configs[1]: 4 096 envs x T=100 (episode written to replay slots)
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference env
-(oracle/, pure Python like ma-gym itself) on all host cores instead.
+Prints ONE JSON line (rank 0).  Besides the contract keys it carries: `roofline` / `roofline_gae` (CUDA-event kernel times
+inside the timed region against MEASURED_PEAKS.json), `e2e` (the same rollout for a caller holding HOST arrays:
+BatchedCheckers.rollout_host, H2D / kernels / D2H pipelined in mm_checkers_rollout_host, wall clock), `cpu_baseline`,
+`clocks` (a separate NVML sampling process), and the sections `policy_rollout`, `learner` (QMIX train samples/sec),
+`mappo_iteration`, `env_switch2`, `qmix_toplevel` (skipped with --no-learner).  `--impl reference` times the CPU restatement
+of the reference env (oracle/, pure Python like ma-gym itself) on all host cores instead.
 """
 import argparse
 import json
@@ -208,12 +212,13 @@ def run_reference(args, wl):
         return
     cores = os.cpu_count() or 1
     vals = []
+    per_step_s = min(2.0, 60.0 / max(1, args.steps))         # the whole run stays near a minute whatever K is
     for _ in range(args.warmup):
-        cpu_python_port(cores, 0.5)
+        cpu_python_port(cores, min(0.5, per_step_s))
     sample = ""
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, sample = cpu_python_port(cores, 2.0)
+        v, sample = cpu_python_port(cores, per_step_s)
         vals.append(v)
     value = statistics.mean(vals)
     line = {
