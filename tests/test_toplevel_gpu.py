@@ -234,3 +234,35 @@ def test_batched_chunk_insert_equals_sequential_reference_adds(cuda, fixture, ca
                                g["chunk_next_states"][:lo], g["chunk_dones"][:lo]], torch.from_numpy(g["chunk_td"][:lo]).to(cuda), True)
     assert np.allclose(dev.sum_tree.priority_tree.cpu().numpy(), g["tree_after_add"], rtol=1e-14)
     assert torch.equal(dev.states[:cap], seq.states[:cap])
+
+
+def test_batched_tree_kernels_equal_one_by_one_at_scale(cuda):
+    """mm_heaptree_add_batch and the batched mm_heaptree_update beyond one staging pass (k, n > 1 024), non-power-of-two
+    capacity, duplicate update targets: trees and slots bit-identical to the same operations issued one at a time (the
+    single-update / arg-min kernels, already pinned against the reference fixtures)."""
+    from minimarl_b200.algorithms.toplevel import SumTree
+    from minimarl_b200 import _lib
+    cap = 3001
+    g = torch.Generator(device=cuda).manual_seed(7)
+    a, b = SumTree(cap, cuda), SumTree(cap, cuda)
+    n_data = 0
+    for k in (2500, 1700, 1300):                       # fill, then evict (also inside the batch)
+        prio = (torch.rand(k, dtype=torch.float64, device=cuda, generator=g) * 4 + 1e-3)
+        slots = torch.empty(k, dtype=torch.int64, device=cuda)
+        _lib.check(_lib.lib().mm_heaptree_add_batch(_lib.ptr(a.priority_tree), cap, n_data, _lib.ptr(prio), k, _lib.ptr(slots),
+                                                    _lib.stream()))
+        want, nd = [], n_data
+        for i in range(k):
+            s = nd if nd < cap else int(b.argmin_leaf().item())
+            nd = min(cap, nd + 1)
+            b.update(torch.tensor([s + cap - 1], device=cuda), prio[i:i + 1])
+            want.append(s)
+        n_data = min(cap, n_data + k)
+        assert slots.cpu().tolist() == want
+        assert torch.equal(a.priority_tree, b.priority_tree)
+    idx = torch.randint(0, cap, (4096,), device=cuda, generator=g) + cap - 1          # many duplicates
+    pr = torch.rand(4096, dtype=torch.float64, device=cuda, generator=g) + 0.01
+    a.update(idx, pr)                                   # one launch, four staging passes
+    for i in range(4096):
+        b.update(idx[i:i + 1], pr[i:i + 1])             # n = 1: the sequential kernel
+    assert torch.equal(a.priority_tree, b.priority_tree)
