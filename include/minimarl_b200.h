@@ -326,6 +326,84 @@ int mm_heaptree_argmin_leaf(const double* tree, int32_t capacity, int64_t* leaf_
 int mm_heaptree_add_batch(double* tree, int32_t capacity, int32_t n_data, const double* priority, int32_t k,
                           int64_t* slot_out, void* stream);
 
+/* Batch formulations for N lockstep envs (heaptree_batch.cu); the sequential calls above stay the reference-exact path.
+ *   add_set:    the valid items (valid == NULL: all) first fill the free slots in order, the rest replace the lowest-priority
+ *               slots occupied before the batch (ties: lowest slot; r-th lowest -> r-th remaining item); items of one batch
+ *               never evict each other, items beyond capacity are dropped.  slot_out[i] = data slot or -1.
+ *               n_data_dev: device int32 fill count, updated.  Inner nodes are recomputed from the leaves.
+ *               workspace: int32[k + capacity + 4].
+ *   set_leaves: tree[node_idx[i]] = priority[i], the last i naming a leaf wins (the order of Replay_buffer.update calls in
+ *               vdn/_train.py:96-99); node indices outside the leaf range are ignored; inner nodes recomputed.
+ *               workspace: int32[capacity].
+ *   rows_scatter: dst[t][slot[i]] = src[t][i] for n <= 8 row-major float tensors (row_floats[t] floats per row); slot -1 skips. */
+int mm_heaptree_add_set(double* tree, int32_t capacity, int32_t* n_data_dev, const double* priority, const uint8_t* valid,
+                        int32_t k, int64_t* slot_out, int32_t* workspace, void* stream);
+int mm_heaptree_set_leaves(double* tree, int32_t capacity, const int64_t* node_idx, const double* priority, int32_t n,
+                           int32_t* workspace, void* stream);
+int mm_rows_scatter(const float* const* src_host, float* const* dst_host, const int32_t* row_floats_host, int32_t n,
+                    const int64_t* slot, int32_t k, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Top-level vdn/ and qmix/ packages: fused per-agent Q_Net and recurrent Mix_Net.
+ * Networks are passed as HOST arrays of device pointers to the reference-layout tensors (nn.Linear / nn.GRUCell
+ * weight [out][in]); the kernels stage them into shared memory themselves, so optimiser steps need no re-packing.
+ *   Q_Net  (vdn/_network.py:61-91): per agent w1 [64,D] b1 w2 [32,64] b2 wih [96,32] whh [96,32] bih bhh wo [NA,32] bo;
+ *          params_host = 20 pointers (agent 0 then agent 1).  A = 2 agents, D <= 96, NA <= 8.
+ *   Mix_Net (qmix/_network.py:172-220, recurrent): gru.weight_ih [96,S] weight_hh [96,32] bias_ih bias_hh,
+ *          hyper_net_weight_1 {w [64,32], b}, hyper_net_weight_2 {w [32,32], b}, hyper_net_bias_1 {w, b},
+ *          hyper_net_bias_2.0 {w, b}, hyper_net_bias_2.2 {w [1,32], b [1]}: 14 pointers.  S = A * D <= 96.
+ *
+ * mm_toplevel_rollout: the rollout body of vdn/main.py:139-177 / qmix/main.py:183-240 for N lockstep envs, T = C * L steps
+ *   in ONE launch (env reset at the start): behaviour Q_Net -> epsilon_greedy with one uniform per env
+ *   (vdn/_network.py:52-58; Philox4x32-10 keyed by seed, counter (step_offset + t, env)) -> env.step
+ *   (env_kind 1 = Checkers-v0 with mm_checkers_cfg, 2 = Switch2-v0 with mm_switch_cfg) -> next observation.
+ *   Outputs in chunk layout: states / next_states [C,N,L,2,D], actions / rewards [C,N,L,2], dones [C,N,L] (all agents
+ *   done), behv [T,N] = sum_a Q_beh[a][action_a], alive [T,N] (env not finished before step t), score [N] = sum of the
+ *   rewards over the alive steps.  forced_actions [T,N,2] (optional) replaces the epsilon-greedy choice.
+ * mm_toplevel_qnet_seq: Q_Net over recorded observations.  obs element (c, b, l, agent, d) at
+ *   c * chunk_stride + ((row_index[b] * L + l) * 2 + agent) * D + d (row_index NULL = identity); the GRU state starts at
+ *   zero, runs over all C * L steps and, with reset_on_done, is zeroed after steps whose dones entry
+ *   (c * done_chunk_stride + row_index[b] * L + l) is non-zero.  q_out [C,B,L,2,NA]; save (optional) receives the
+ *   activations the backward needs: [2, C*L, B, mm_toplevel_qnet_save_stride()].
+ * mm_toplevel_qnet_bwd: BPTT through one chunk (C = 1) given dq [B,L,2,NA]; writes (accumulate = 0) or adds the weight
+ *   gradients into grads_host (20 pointers, same order and layout as the parameters).  partials: workspace of
+ *   2 * ceil(B / 32) * mm_toplevel_qnet_param_count(D, NA) floats.  Deterministic (fixed reduction order).
+ * mm_toplevel_td: cal_td_error (vdn/_utils.py:44-52) summed per chunk over the steps at which the env was alive.
+ * mm_vdn_chunk_loss: Target_Dqn.train's per-step targets and squared errors (vdn/_train.py:66-86, quirk Q7), dq and the
+ *   last-step |TD| (quirk Q9); actions / rewards / dones are read through row_index from the PER payload.
+ * mm_toplevel_mix_seq / _bwd, mm_qmix_chunk_loss: the same for Train_dqn.train (qmix/_train.py:19-121): q fed to the
+ *   mixer is the taken action's value (actions != NULL) or max_o (target side); the mixer state is zeroed after terminal
+ *   steps; _bwd also writes dq [B,L,2,NA] for mm_toplevel_qnet_bwd.
+ * ---------------------------------------------------------------------------------------------- */
+int mm_toplevel_qnet_param_count(int32_t D, int32_t NA);
+int mm_toplevel_qnet_save_stride(void);
+int mm_toplevel_rollout(const float* const* params_host, int32_t env_kind, const void* env_cfg_host, float* states,
+                        float* next_states, float* actions, float* rewards, float* dones, float* behv, uint8_t* alive,
+                        float* score, uint32_t* env_state, const int32_t* forced_actions, int32_t N, int32_t T, int32_t L,
+                        int32_t D, int32_t NA, float eps, uint64_t seed, uint64_t step_offset, void* stream);
+int mm_toplevel_qnet_seq(const float* const* params_host, const float* obs, const int64_t* row_index, int64_t chunk_stride,
+                         const float* dones, int64_t done_chunk_stride, int32_t reset_on_done, float* q_out, float* save,
+                         int32_t B, int32_t L, int32_t C, int32_t D, int32_t NA, void* stream);
+int mm_toplevel_qnet_bwd(const float* const* params_host, float* const* grads_host, const float* obs, const int64_t* row_index,
+                         const float* dones, int32_t reset_on_done, const float* save, const float* dq, float* partials,
+                         int32_t accumulate, int32_t B, int32_t L, int32_t D, int32_t NA, void* stream);
+int mm_toplevel_td(const float* q_tgt, const float* rewards, const float* dones, const float* behv, const uint8_t* alive,
+                   float* td_sum, uint8_t* chunk_valid, int32_t N, int32_t L, int32_t C, int32_t NA, float gamma, void* stream);
+int mm_vdn_chunk_loss(const float* q_beh, const float* q_tgt, const float* actions, const float* rewards, const float* dones,
+                      const int64_t* row_index, const float* is_weight, float* se, float* dq, float* td_last, int32_t B,
+                      int32_t L, int32_t NA, float gamma, void* stream);
+int mm_toplevel_mix_param_count(int32_t S);
+int mm_toplevel_mix_save_stride(void);
+int mm_toplevel_mix_seq(const float* const* params_host, const float* obs, const int64_t* row_index, const float* dones,
+                        const float* q_all, const float* actions, float* qtot, float* save, int32_t B, int32_t L, int32_t S,
+                        int32_t NA, void* stream);
+int mm_toplevel_mix_bwd(const float* const* params_host, float* const* grads_host, const float* obs, const int64_t* row_index,
+                        const float* dones, const float* q_all, const float* actions, const float* save, const float* dqtot,
+                        float* dq, float* partials, int32_t accumulate, int32_t B, int32_t L, int32_t S, int32_t NA, void* stream);
+int mm_qmix_chunk_loss(const float* qtot, const float* qtot_tgt, const float* rewards, const float* dones,
+                       const int64_t* row_index, const float* is_weight, float* se, float* dqtot, float* td_last, int32_t B,
+                       int32_t L, float gamma, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over short rows (N <= 128, eps 1e-5) for the differentiated network pass: the nn.LayerNorm
  * calls of MLPLayer / RNNLayer (offpolicy/utils/algorithm_utils/mlp.py:17-29, rnn.py:18,28;

@@ -113,6 +113,21 @@ SIGNATURES = {
                                                   C.POINTER(CheckersCfg), _P]),
     "mm_qmix_rollout_tc": (C.c_int, [_P, _P, _P, _P, C.POINTER(RolloutIO), C.POINTER(CheckersCfg), C.POINTER(C.c_float),
                                      C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _P]),
+    "mm_heaptree_add_set": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P]),
+    "mm_heaptree_set_leaves": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P, _P]),
+    "mm_rows_scatter": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P]),
+    "mm_toplevel_qnet_param_count": (C.c_int, [C.c_int32, C.c_int32]),
+    "mm_toplevel_qnet_save_stride": (C.c_int, []),
+    "mm_toplevel_rollout": (C.c_int, [_P, C.c_int32] + [_P] * 11 + [C.c_int32] * 5 + [C.c_float, C.c_uint64, C.c_uint64, _P]),
+    "mm_toplevel_qnet_seq": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P] + [C.c_int32] * 5 + [_P]),
+    "mm_toplevel_qnet_bwd": (C.c_int, [_P] * 5 + [C.c_int32, _P, _P, _P] + [C.c_int32] * 5 + [_P]),
+    "mm_toplevel_td": (C.c_int, [_P] * 7 + [C.c_int32] * 4 + [C.c_float, _P]),
+    "mm_vdn_chunk_loss": (C.c_int, [_P] * 10 + [C.c_int32] * 3 + [C.c_float, _P]),
+    "mm_toplevel_mix_param_count": (C.c_int, [C.c_int32]),
+    "mm_toplevel_mix_save_stride": (C.c_int, []),
+    "mm_toplevel_mix_seq": (C.c_int, [_P] * 8 + [C.c_int32] * 4 + [_P]),
+    "mm_toplevel_mix_bwd": (C.c_int, [_P] * 11 + [C.c_int32] * 5 + [_P]),
+    "mm_qmix_chunk_loss": (C.c_int, [_P] * 9 + [C.c_int32, C.c_int32, C.c_float, _P]),
 }
 
 _lib = None

@@ -11,17 +11,23 @@
   including quirk Q7 (the bootstrap term summed over the agent axis) and the last-step-only priority (Q9).
 * ``cal_td_error`` (vdn/_utils.py:44-52).
 
-The networks are small per-agent MLP / GRUCell stacks evaluated with PyTorch (cuBLAS) on the device; what is
-custom here is the replay path (tree kernels, device-resident chunks instead of Python lists of lists) and the
-lockstep env.  Both top-level packages hard-wire the CPU in places (``.to("cpu")``, qmix/_network.py:64); the
-mirror runs wherever its parameters live.
+``Q_Net`` / ``Mix_Net`` are ordinary modules with the reference's parameter names (so ``state_dict`` / optimisers / target
+copies work), and their ``forward`` is the module path used for single steps and as the parity statement.  The hot loops --
+the rollout body, ``Target_Dqn.train`` and ``Train_dqn.train`` -- run on the fused kernels of ``toplevel_fused.py``
+(``csrc/toplevel_qnet.cu``, ``csrc/toplevel_mix.cu``): one launch per chunk pass, BPTT with in-register weight gradients,
+payload read through the PER slots without a gather.  ``fused=False`` (or an unsupported shape) keeps the module path.
+Both top-level packages hard-wire the CPU in places (``.to("cpu")``, qmix/_network.py:64); the mirror runs wherever its
+parameters live.
 """
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
+from . import toplevel_fused as tf
 
 
 class Network(nn.Module):
@@ -189,6 +195,8 @@ class SumTree:
         self.device = torch.device(device)
         self.priority_tree = torch.zeros(2 * capacity - 1, dtype=torch.float64, device=self.device)
         self.n_data = 0
+        self._n_data_dev = None       # device copy of the fill count, owned by the batch ("set") insert
+        self._ws = None
 
     def total(self):
         return self.priority_tree[0]
@@ -198,6 +206,33 @@ class SumTree:
         pr = torch.as_tensor(priority, device=self.device).to(torch.float64).reshape(-1).contiguous()
         _lib.check(_lib.lib().mm_heaptree_update(_lib.ptr(self.priority_tree), self.capacity, _lib.ptr(idx), _lib.ptr(pr),
                                                  idx.numel(), _lib.stream()))
+
+    def set_leaves(self, node_idx, priority):
+        """Batch write-back (``mm_heaptree_set_leaves``): last write to a leaf wins, inner nodes recomputed from the leaves."""
+        idx = torch.as_tensor(node_idx, device=self.device, dtype=torch.int64).reshape(-1).contiguous()
+        pr = torch.as_tensor(priority, device=self.device).to(torch.float64).reshape(-1).contiguous()
+        if self._ws is None or self._ws.numel() < self.capacity:
+            self._ws = torch.empty(self.capacity, dtype=torch.int32, device=self.device)
+        _lib.check(_lib.lib().mm_heaptree_set_leaves(_lib.ptr(self.priority_tree), self.capacity, _lib.ptr(idx), _lib.ptr(pr),
+                                                     idx.numel(), _lib.ptr(self._ws), _lib.stream()))
+
+    def add_set(self, priority, valid=None):
+        """Batch insert with set semantics (``mm_heaptree_add_set``); returns the slot of every item (-1 = not stored).  The
+        fill count lives on the device; ``sync_n_data`` refreshes the host copy."""
+        k = priority.numel()
+        if self._n_data_dev is None:
+            self._n_data_dev = torch.tensor([self.n_data], dtype=torch.int32, device=self.device)
+        ws = torch.empty(k + self.capacity + 4, dtype=torch.int32, device=self.device)
+        slot = torch.empty(k, dtype=torch.int64, device=self.device)
+        _lib.check(_lib.lib().mm_heaptree_add_set(_lib.ptr(self.priority_tree), self.capacity, _lib.ptr(self._n_data_dev),
+                                                  _lib.ptr(priority), _lib.ptr(valid), k, _lib.ptr(slot), _lib.ptr(ws),
+                                                  _lib.stream()))
+        return slot
+
+    def sync_n_data(self):
+        if self._n_data_dev is not None:
+            self.n_data = int(self._n_data_dev.item())
+        return self.n_data
 
     def argmin_leaf(self):
         out = torch.empty(1, dtype=torch.int64, device=self.device)
@@ -240,6 +275,9 @@ class Prioritized_Experience_Replay:
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(int(getattr(args, "seed", 0)))
         self._sched = None            # graph mode: [alpha, beta] as a device float64 pair, advanced inside the captured graph
+        # batch formulations for lockstep envs (heaptree_batch.cu): set-semantics insert, write-back with tree rebuild.  Off by
+        # default: the sequential kernels reproduce the reference's trees bit for bit.
+        self.fast_tree = bool(getattr(args, "fast_tree", False))
 
     # -- CUDA-graph support: the annealed exponents must be device values, or a captured sample() would replay stale ones ----
     def enable_graph_mode(self):
@@ -286,18 +324,22 @@ class Prioritized_Experience_Replay:
             tree.n_data += 1
         return tree.n_data if warm_up else None
 
-    def collect_samples_batch(self, samples, td_errors, warm_up, host_pow=False):
+    def collect_samples_batch(self, samples, td_errors, warm_up, host_pow=False, valid=None):
         """K consecutive ``collect_sample`` calls -- the chunks N lockstep envs finish at the same step, in env order
         (the reference's add order) -- without a Python loop: ``mm_heaptree_add_batch`` replays the K ``SumTree.add``s
         on the device (fill, then arg-min eviction where a later chunk may evict an earlier one of the same batch), the
         payloads are scattered into the slots their final owners got.
         samples = [states [K,L,A,D], actions [K,L,A] or [K,L,1,A], rewards [K,L,A], next_states [K,L,A,D], dones [K,L]];
         td_errors [K].  ``host_pow``: raise (td + eps) ** alpha with Python doubles like the reference (one D2H sync)
-        instead of torch.pow on the device (<= 1 ulp from libm)."""
+        instead of torch.pow on the device (<= 1 ulp from libm).
+        ``fast_tree`` or ``valid`` (uint8 [K]: chunks of envs that had already finished are not stored): the batch goes in as a
+        SET (``mm_heaptree_add_set`` + one ``mm_rows_scatter``), see heaptree_batch.cu."""
         tree = self.sum_tree
         s, a, r, s2, d = (torch.as_tensor(x, device=self.device, dtype=torch.float32) for x in samples)
         K = s.shape[0]
         td = torch.as_tensor(td_errors, device=self.device).reshape(K)
+        if self.fast_tree or valid is not None:
+            return self._collect_set(s, a, r, s2, d, td, valid, warm_up)
         if host_pow:
             prio = torch.tensor([(float(v) + self.eps) ** self.alpha for v in td.tolist()], dtype=torch.float64, device=self.device)
         else:
@@ -321,8 +363,37 @@ class Prioritized_Experience_Replay:
         tree.n_data = min(self.capacity, tree.n_data + K)
         return tree.n_data if warm_up else None
 
+    def _collect_set(self, s, a, r, s2, d, td, valid, warm_up):
+        tree = self.sum_tree
+        K = s.shape[0]
+        alpha = self._sched[0] if self._sched is not None else self.alpha
+        prio = torch.pow(td.to(torch.float64) + self.eps, alpha).contiguous()
+        if valid is not None:
+            valid = valid.to(device=self.device, dtype=torch.uint8).contiguous()
+        slot = tree.add_set(prio, valid)
+        src = [s.reshape(K, -1), a.reshape(K, -1), r.reshape(K, -1), s2.reshape(K, -1), d.reshape(K, -1)]
+        dst = [self.states, self.actions, self.rewards, self.next_states, self.dones]
+        src = [x if x.is_contiguous() else x.contiguous() for x in src]
+        sp = (C.c_void_p * 5)(*[x.data_ptr() for x in src])
+        dp = (C.c_void_p * 5)(*[x.data_ptr() for x in dst])
+        rf = (C.c_int32 * 5)(*[x.shape[1] for x in src])
+        _lib.check(_lib.lib().mm_rows_scatter(sp, dp, rf, 5, _lib.ptr(slot), K, _lib.stream()))
+        if warm_up:
+            return tree.sync_n_data()
+        return None
+
+    def sample_indices(self, batch_size, uniforms=None):
+        """The stratified draw without the payload gather: (data slots [B] int64, node ids [B] int64, IS weights [B,1] f32)."""
+        data, node, w = self._draw(batch_size, uniforms)
+        return data, node, w
+
     def sample(self, batch_size, _chunk_size, uniforms=None):
         """7-tuple of the reference (buffer.py:81-86), all CUDA tensors; priority_idxs is an int64 tensor of NODE ids."""
+        data, node, w = self._draw(batch_size, uniforms)
+        return (self.states[data], self.actions[data], self.rewards[data], self.next_states[data], self.dones[data],
+                node, w)
+
+    def _draw(self, batch_size, uniforms=None):
         tree = self.sum_tree
         if self._sched is not None:
             self._sched.add_(self._sched_inc).clamp_(max=1.0)
@@ -343,11 +414,13 @@ class Prioritized_Experience_Replay:
         probs = prio / tree.total()
         w = torch.pow(self.capacity * probs, -beta)
         w = (w / w.max()).to(torch.float32).view(batch_size, 1)
-        return (self.states[data], self.actions[data], self.rewards[data], self.next_states[data], self.dones[data],
-                node, w)
+        return data, node, w
 
     def update(self, priority_idx, new_td_error):
-        self.sum_tree.update(priority_idx, self._get_priority(new_td_error))
+        if self.fast_tree:
+            self.sum_tree.set_leaves(priority_idx, self._get_priority(new_td_error))
+        else:
+            self.sum_tree.update(priority_idx, self._get_priority(new_td_error))
 
 
 class _GraphedIterations:
@@ -378,7 +451,8 @@ class _GraphedIterations:
             main.wait_stream(side)
             per.advance_host_schedule()
             done = 1
-            optimizer.zero_grad(set_to_none=True)
+            if not getattr(self, "fused", False):
+                optimizer.zero_grad(set_to_none=True)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self._static_loss = iteration(None)
@@ -398,8 +472,29 @@ class Target_Dqn(_GraphedIterations):
         self.chunk_size = args.chunk_size if args.use_recurrent else 1
         self.gamma, self.grad_clip_norm, self.device = args.gamma, args.grad_clip_norm, device
         self.use_graph = bool(getattr(args, "train_graph", False))
+        self.fused = bool(getattr(args, "fused", True))
+
+    def _iteration_fused(self, target_network, optimizer, u):
+        """One iteration on the fused kernels: target pass and behaviour pass (activations kept) read the sampled chunks
+        through their PER slots, the loss kernel emits dq, one backward kernel writes every weight gradient into ``p.grad``."""
+        per, beh, B, L = self.replay_buffer, self.behavior_network, self.batch_size, self.chunk_size
+        data, node, w = per.sample_indices(B, uniforms=u)
+        q_tgt = tf.qnet_seq(target_network, per.next_states, B, L, row_index=data, dones=per.dones, reset_on_done=True)
+        q_beh, save = tf.qnet_seq(beh, per.states, B, L, row_index=data, dones=per.dones, reset_on_done=True, save=True)
+        se, dq, td_last = tf.vdn_chunk_loss(q_beh, q_tgt, per.actions, per.rewards, per.dones, data, w.reshape(-1).contiguous(),
+                                            self.gamma)
+        tf.qnet_backward(beh, per.states, data, per.dones, save, dq, B, L)
+        torch.nn.utils.clip_grad_norm_(parameters=beh.parameters(), max_norm=self.grad_clip_norm, norm_type=2)
+        optimizer.step()
+        per.update(node, td_last)
+        return se.sum() / B
+
+    def _can_fuse(self, target_network):
+        return (self.fused and self.chunk_size > 1 and tf.qnet_supported(self.behavior_network) and tf.qnet_supported(target_network))
 
     def _iteration(self, target_network, optimizer, u):
+        if self._can_fuse(target_network):
+            return self._iteration_fused(target_network, optimizer, u)
         states, actions, rewards, next_states, dones, priority_idx, is_weight = \
             self.replay_buffer.sample(self.batch_size, self.chunk_size, uniforms=u)
         hidden = self.behavior_network.init_hidden(self.batch_size)
@@ -442,8 +537,29 @@ class Train_dqn(_GraphedIterations):
         self.chunk_size = args.chunk_size if args.use_recurrent else 1
         self.gamma, self.grad_clip_norm, self.device = args.gamma, args.grad_clip_norm, device
         self.use_graph = bool(getattr(args, "train_graph", False))
+        self.fused = bool(getattr(args, "fused", True))
+
+    def _iteration_fused(self, per, q_net, mix, tq_net, tmix, optimizer, u):
+        """qmix/_train.py:29-121 on the fused kernels: Q_Net target / behaviour passes, Mix_Net on both sides, loss, mixer BPTT
+        (emits dq), Q_Net BPTT; only the q-net gradients are clipped, as in the reference."""
+        B, L = self.batch_size, self.chunk_size
+        data, node, w = per.sample_indices(B, uniforms=u)
+        q_tgt = tf.qnet_seq(tq_net, per.next_states, B, L, row_index=data, dones=per.dones, reset_on_done=True)
+        qtot_tgt = tf.mix_seq(tmix, per.next_states, data, per.dones, q_tgt, None, B, L)
+        q_beh, save = tf.qnet_seq(q_net, per.states, B, L, row_index=data, dones=per.dones, reset_on_done=True, save=True)
+        qtot, msave = tf.mix_seq(mix, per.states, data, per.dones, q_beh, per.actions, B, L, save=True)
+        se, dqtot, td_last = tf.qmix_chunk_loss(qtot, qtot_tgt, per.rewards, per.dones, data, w.reshape(-1).contiguous(), self.gamma)
+        dq = tf.mix_backward(mix, per.states, data, per.dones, q_beh, per.actions, msave, dqtot, B, L)
+        tf.qnet_backward(q_net, per.states, data, per.dones, save, dq, B, L)
+        torch.nn.utils.clip_grad_norm_(parameters=q_net.parameters(), max_norm=self.grad_clip_norm, norm_type=2)
+        optimizer.step()
+        per.update(node, td_last)
+        return se.sum() / B
 
     def _iteration(self, Replay_buffer, behavior_q_net, behavior_mix_net, target_q_net, target_mix_net, optimizer, u):
+        if (self.fused and self.chunk_size > 1 and tf.qnet_supported(behavior_q_net) and tf.qnet_supported(target_q_net)
+                and tf.mix_supported(behavior_mix_net) and tf.mix_supported(target_mix_net)):
+            return self._iteration_fused(Replay_buffer, behavior_q_net, behavior_mix_net, target_q_net, target_mix_net, optimizer, u)
         states, actions, rewards, next_states, dones, priority_idx, w = Replay_buffer.sample(self.batch_size, self.chunk_size, uniforms=u)
         hidden, target_hidden = behavior_q_net.init_hidden(self.batch_size), target_q_net.init_hidden(self.batch_size)
         mix_hidden, target_mix_hidden = behavior_mix_net.init_hidden(self.batch_size), target_mix_net.init_hidden(self.batch_size)

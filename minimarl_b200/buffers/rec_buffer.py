@@ -218,12 +218,18 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
             vals = torch.as_tensor(host ** self.alpha, device=self.device).contiguous()
         idx = torch.as_tensor(np.asarray(idxes) if not torch.is_tensor(idxes) else idxes,
                               device=self.device).to(torch.int64).reshape(-1).contiguous()
-        st, mt = self._it_sums[p_id], self._it_mins[p_id]
-        _lib.check(_lib.lib().mm_segtree_set(_lib.ptr(st._value), _lib.ptr(mt._value), st._capacity, _lib.ptr(idx),
-                                             _lib.ptr(vals), 0.0, 0, idx.numel(), _lib.stream()))
-        # the reference's asserts and max tracking need the values on the host: one small sync
+        # the reference's asserts (rec_buffer.py:315-318) and max tracking need the values on the host: one small sync, BEFORE
+        # anything is written, so an out-of-range index can never reach the tree
         stats = torch.stack([pr.min(), pr.max(), idx.min().double(), idx.max().double()]).tolist()
         assert stats[0] > 0
         assert stats[2] >= 0
         assert stats[3] < len(self)
+        # PER samples with replacement: when an index repeats the reference's loop lets the LAST write win.  Every duplicate is
+        # given the value of its last occurrence, so the parallel write is deterministic.
+        order = torch.arange(idx.numel(), device=self.device)
+        last = torch.full((len(self),), -1, dtype=torch.int64, device=self.device).scatter_reduce_(0, idx, order, "amax")
+        vals = vals[last[idx]].contiguous()
+        st, mt = self._it_sums[p_id], self._it_mins[p_id]
+        _lib.check(_lib.lib().mm_segtree_set(_lib.ptr(st._value), _lib.ptr(mt._value), st._capacity, _lib.ptr(idx),
+                                             _lib.ptr(vals), 0.0, 0, idx.numel(), _lib.stream()))
         self.max_priorities[p_id] = max(self.max_priorities[p_id], stats[1])

@@ -6,30 +6,18 @@
 // redundantly in every lane of the env (the other agents' actions arrive by shuffle) than to
 // hand positions from lane to lane.
 #include "common.cuh"
+#include "switch_core.cuh"
 
 namespace {
+using sw::init_cells;
 
 constexpr int kThreads = 128;
-constexpr uint32_t kFreeCells = 0x63u | (0x7fu << 8) | (0x63u << 16);   // row 1 (corridor) + cols 0,1,5,6
-// agents 0/1 live in row 0, agents 2/3 in row 2; even agents start left (col 1) and must reach
-// col 6, odd agents start right (col 5) and must reach col 0
-__host__ __device__ constexpr uint32_t init_cell(int a) { return ((a & 2) ? 16u : 0u) + ((a & 1) ? 5u : 1u); }
-__host__ __device__ constexpr uint32_t goal_cell(int a) { return ((a & 2) ? 16u : 0u) + ((a & 1) ? 0u : 6u); }
-
-__device__ __forceinline__ uint32_t init_cells(int n_agents) {
-    uint32_t c = 0;
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-        if (a < n_agents) c |= init_cell(a) << (8 * a);
-    return c;
-}
-
 template <int A>
 __device__ __forceinline__ void write_obs(float* __restrict__ obs, int env, int agent, uint32_t cells,
                                           uint32_t step, const mm_switch_cfg& cfg) {
     const int d = 2 + (cfg.clock ? 1 : 0);
     // Python: step_count / max_steps in double, cast to float32 by the buffers
-    const float clk = (float)((double)step / (double)cfg.max_steps);
+    const float clk = sw::clock_value(step, cfg);
     if (!cfg.full_observable) {
         float* o = obs + ((size_t)env * A + agent) * d;
         const uint32_t cell = (cells >> (8 * agent)) & 0xffu;
@@ -92,7 +80,6 @@ switch_rollout_kernel(uint32_t* __restrict__ state, const int32_t* __restrict__ 
     uint32_t cells = state[env_c];
     uint32_t done = state[n + env_c];
     uint32_t step = state[2 * n + env_c];
-    const int group = lane & ~(A - 1);
     bool any_bad = false;
     int act_next = actions != nullptr ? actions[row] : 0;
     for (int t = 0; t < T; ++t) {
@@ -108,30 +95,8 @@ switch_rollout_kernel(uint32_t* __restrict__ state, const int32_t* __restrict__ 
             if (actions_out != nullptr && valid) actions_out[(size_t)t * rows + row] = my_act;
         }
         any_bad |= (unsigned)my_act > 4u;
-        step += 1;
-        float reward = cfg.step_cost;
-#pragma unroll
-        for (int a = 0; a < A; ++a) {
-            const int act = __shfl_sync(MM_FULL_MASK, my_act, group + a);
-            if ((done >> a) & 1u) continue;                      // finished agents no longer move
-            const uint32_t cell = (cells >> (8 * a)) & 0xffu;
-            const int r = cell >> 3, c = cell & 7;
-            const int nr = r + (act == 0) - (act == 2);
-            const int nc = c + (act == 3) - (act == 1);
-            uint32_t occupied = 0;
-#pragma unroll
-            for (int b = 0; b < A; ++b) occupied |= 1u << ((cells >> (8 * b)) & 0xffu);
-            const uint32_t target = (uint32_t)(nr * 8 + nc);
-            const bool vacant = ((unsigned)act < 4u) && ((unsigned)nr < 3u) && ((unsigned)nc < 7u) &&
-                                (((kFreeCells & ~occupied) >> target) & 1u);
-            const uint32_t now = vacant ? target : cell;
-            cells = (cells & ~(0xffu << (8 * a))) | (now << (8 * a));
-            if (now == goal_cell(a)) {
-                done |= 1u << a;
-                if (a == agent) reward = cfg.goal_reward;        // assignment, not +=, as in ma-gym
-            }
-        }
-        if ((int)step >= cfg.max_steps) done = (1u << A) - 1u;
+        float reward;
+        sw::transition<A>(cells, done, step, my_act, agent, lane, cfg, reward);
         if (valid) {
             if (rewards != nullptr) rewards[(size_t)t * rows + row] = reward;
             if (dones != nullptr) dones[(size_t)t * rows + row] = (uint8_t)((done >> agent) & 1u);

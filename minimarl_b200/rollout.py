@@ -163,6 +163,10 @@ class EpisodeCollector:
         else:
             eps = 0.0
         sl = slice(i0, i0 + N)
+        if not (explore or warmup):
+            # evaluation episodes are never committed: they go to scratch tensors, not into slots that may hold live
+            # training episodes (whose priorities stay in the tree)
+            return self._eval_rollout(eps, training_episode)
         onehot = pb.acts[:, sl]
         out = qmix_rollout(
             self.policy.q_network, env, T, eps, seed=self.seed, step_offset=self.total_env_steps,
@@ -187,3 +191,18 @@ class EpisodeCollector:
                 pb.commit(slots)
         # the reference logs the team return of the (single) env; here: mean over the N envs, a device scalar
         return {"average_episode_rewards": pb.rewards[:, sl, 0, 0].sum(0).mean()}
+
+    def _eval_rollout(self, eps, training_episode):
+        env, T, N = self.env, self.T, self.env.n_envs
+        pb = self.buffer.policy_buffers["policy_0"]
+        A, D, NA = pb.num_agents, pb.obs_dim, pb.act_dim
+        sc = getattr(self, "_scratch", None)
+        if sc is None:
+            z = dict(dtype=torch.float32, device=pb.obs.device)
+            sc = self._scratch = dict(obs=torch.zeros((T + 1, N, A, D), **z), act_onehot=torch.zeros((T, N, A, NA), **z),
+                                      rewards=torch.zeros((T, N, A), **z), dones=torch.zeros((T, N, A), **z),
+                                      dones_env=torch.zeros((T, N), **z))
+        qmix_rollout(self.policy.q_network, env, T, eps, seed=self.seed, step_offset=self.total_env_steps, **sc)
+        if training_episode:
+            self.total_env_steps += N * T
+        return {"average_episode_rewards": sc["rewards"][:, :, 0].sum(0).mean()}

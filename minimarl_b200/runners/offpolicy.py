@@ -49,8 +49,12 @@ class MAGYM_Runner:
         self.beta_anneal = DecayThenFlatSchedule(args.per_beta_start, 1.0, num_train_episodes, decay="linear")
         buf_args = (self.policy_info, self.policy_agents, self.buffer_size, self.episode_length, args.use_same_share_obs,
                     False, args.use_reward_normalization)
-        self.buffer = PrioritizedRecReplayBuffer(args.per_alpha, *buf_args, device=self.device) if self.use_per \
-            else RecReplayBuffer(*buf_args, device=self.device)
+        # The reference seeds leaves 0..n-1 instead of the slots just written (rec_buffer.py:265-268, quirk Q12).  With one env
+        # that only ever touches leaf 0; with N lockstep envs it would leave every slot >= N unsampled, so the runner seeds the
+        # written slots.  ``faithful_per_insert=True`` restores the reference's behaviour.
+        self.buffer = PrioritizedRecReplayBuffer(args.per_alpha, *buf_args, device=self.device,
+                                                 fix_insert_priority=not getattr(args, "faithful_per_insert", False)) \
+            if self.use_per else RecReplayBuffer(*buf_args, device=self.device)
         self._collector = EpisodeCollector(self.train_env, self.policies["policy_0"], self.buffer, self.episode_length,
                                            seed=getattr(args, "seed", 0))
         self.train_infos, self.env_infos = [], {}

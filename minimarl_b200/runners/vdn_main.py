@@ -9,11 +9,21 @@ target copy, with the reference's epsilon / alpha / beta schedules.
 
 ``run_vdn``: Checkers-v0 with full observations (D = 94), the vdn/_config.py default.
 ``run_qmix``: Switch2-v0 (D = 3), the qmix/_config.py default (qmix/_config.py:13-18).
+
+Default path (``args.fused``, on unless the shapes are outside the kernels): one ``mm_toplevel_rollout`` launch plays a whole
+episode of all envs (behaviour Q_Net, epsilon-greedy, env step), one ``mm_toplevel_qnet_seq`` launch runs the target network
+over the recorded next states, ``mm_toplevel_td`` sums ``cal_td_error`` per chunk, and the chunks of every env that was still
+alive at the chunk's first step go into the PER as one set (``mm_heaptree_add_set`` + ``mm_rows_scatter``).  Like the reference
+the run starts with an epsilon = 1 warm-up until the buffer holds ``buffer_limit`` chunks (vdn/main.py:80-125).  Differences
+from the one-env reference loop that lockstep batching forces, all documented in DESIGN.md: envs that finish early idle until
+the slowest env of the batch is done (their later chunks are not stored; a stored chunk may end in padding steps with
+done = 1, reward 0), and a chunk never straddles two episodes.
 """
 import time
 
 import torch
 
+from ..algorithms import toplevel_fused as tf
 from ..algorithms.toplevel import Mix_Net, Prioritized_Experience_Replay, Q_Net, Target_Dqn, Train_dqn, cal_td_error
 from ..envs.batched import BatchedCheckers, BatchedSwitch
 
@@ -88,11 +98,28 @@ class _ChunkGraph:
         return self.chunk, self.td_sum
 
 
+def _fused_episode(beh, tgt, env, per, args, epsilon, seed, step_offset, bufs):
+    """One episode of every env on the fused kernels; returns (score [N], env steps played)."""
+    L, T = args.chunk_size, (args.max_step // args.chunk_size) * args.chunk_size
+    out = tf.rollout_episode(beh, env, T, L, epsilon, seed=seed, step_offset=step_offset, out=bufs)
+    Cn, N = T // L, env.n_envs
+    q_tgt = tf.qnet_seq(tgt, out["next_states"], N, L, C_=Cn)                 # target state carried through the episode
+    td_sum, valid = tf.td_chunks(q_tgt, out["rewards"], out["dones"], out["behv"], out["alive"], args.gamma)
+    for c in range(Cn):                                                        # chunk order = the reference's add order
+        per.collect_samples_batch([out["states"][c], out["actions"][c], out["rewards"][c], out["next_states"][c],
+                                   out["dones"][c]], td_sum[c], warm_up=False, valid=valid[c])
+    return out, T * N
+
+
 def _run(args, env, episodes, mixer, log, timing):
     dev, n_envs = env.device, env.n_envs
     beh = Q_Net(env.observation_space, env.action_space, args).to(dev)
     tgt = Q_Net(env.observation_space, env.action_space, args).to(dev)
     tgt.load_state_dict(beh.state_dict())
+    fused = bool(getattr(args, "fused", True)) and tf.qnet_supported(beh) and env.n_agents == 2 and not (
+        isinstance(env, BatchedSwitch) and env.full_observable) and args.max_step >= args.chunk_size
+    if fused and not hasattr(args, "fast_tree"):
+        args.fast_tree = True                                   # set-semantics PER maintenance (heaptree_batch.cu)
     per = Prioritized_Experience_Replay(args, n_agents=env.n_agents, obs_dim=env.obs_dim, device=dev)
     use_graph = bool(getattr(args, "train_graph", False))            # capture one training iteration as a CUDA graph
     if mixer:
@@ -107,17 +134,34 @@ def _run(args, env, episodes, mixer, log, timing):
         trainer = Target_Dqn(per, beh, tgt, args, dev)
         train = lambda eps: trainer.train(target_network=tgt, optimizer=opt, epsilon=eps)
     L = args.chunk_size
-    graph = _ChunkGraph(beh, tgt, env, args).capture() if getattr(args, "rollout_graph", True) else None   # one-time capture
+    graph = None
+    if not fused and getattr(args, "rollout_graph", True):
+        graph = _ChunkGraph(beh, tgt, env, args).capture()                     # one-time capture
     history = []
     t_roll, t_train = [], []
     env_steps = 0
+    seed = int(getattr(args, "seed", 0))
+    bufs = None
+    played = 0                                                                 # episodes played so far: the Philox counter base
+    # ---- warm-up: epsilon = 1 until the buffer holds buffer_limit chunks (vdn/main.py:80-125) ---------------------------------
+    if fused and getattr(args, "warm_up", True):
+        while per.sum_tree.sync_n_data() < args.buffer_limit:
+            bufs, n = _fused_episode(beh, tgt, env, per, args, 1.0, seed, played * args.max_step, bufs)
+            played += 1
+            if timing is not None:
+                timing["warm_up_env_steps"] = timing.get("warm_up_env_steps", 0) + n
     for episode in range(episodes):
         epsilon = max(args.min_epsilon, args.max_epsilon - (args.max_epsilon - args.min_epsilon) *
                       (episode / args.epsilon_anneal_episode))
         if timing is not None:
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-        if graph is not None:
+        if fused:
+            bufs, n = _fused_episode(beh, tgt, env, per, args, epsilon, seed, played * args.max_step, bufs)
+            played += 1
+            env_steps += n
+            score = bufs["score"]
+        elif graph is not None:
             graph.begin_episode(env.reset(), epsilon)
             for _ in range(args.max_step // L):
                 chunk_tensors, td_sum = graph.run_chunk()
@@ -157,7 +201,8 @@ def _run(args, env, episodes, mixer, log, timing):
             torch.cuda.synchronize(dev)
             t1 = time.perf_counter()
             t_roll.append(t1 - t0)
-        loss = train(epsilon) if per.sum_tree.n_data >= args.batch_size else torch.tensor(float("nan"))
+        n_data = per.sum_tree.sync_n_data() if fused else per.sum_tree.n_data
+        loss = train(epsilon) if n_data >= args.batch_size else torch.tensor(float("nan"))
         if episode % args.update_target_interval == 0:
             tgt.load_state_dict(beh.state_dict())
             if mixer:
@@ -172,7 +217,7 @@ def _run(args, env, episodes, mixer, log, timing):
             log(rec)
     if timing is not None:
         timing.update(rollout_s=sum(t_roll), train_s=sum(t_train), rollout_s_per_episode=t_roll, train_s_per_episode=t_train,
-                      env_steps=env_steps, chunks_in_buffer=per.sum_tree.n_data)
+                      env_steps=env_steps, chunks_in_buffer=per.sum_tree.n_data, fused=fused)
     return history, beh
 
 
