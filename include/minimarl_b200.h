@@ -330,14 +330,22 @@ int mm_heaptree_add_batch(double* tree, int32_t capacity, int32_t n_data, const 
  *   add_set:    the valid items (valid == NULL: all) first fill the free slots in order, the rest replace the lowest-priority
  *               slots occupied before the batch (ties: lowest slot; r-th lowest -> r-th remaining item); items of one batch
  *               never evict each other, items beyond capacity are dropped.  slot_out[i] = data slot or -1.
- *               n_data_dev: device int32 fill count, updated.  Inner nodes are recomputed from the leaves.
- *               workspace: int32[k + capacity + 4].
+ *               n_data_dev: device int32 fill count, updated.  rebuild != 0: inner nodes are recomputed from the leaves
+ *               (the insert itself only reads leaves, so a run of inserts needs one mm_heaptree_rebuild at its end).
+ *               workspace: int32[k + 2 * capacity + 4].
  *   set_leaves: tree[node_idx[i]] = priority[i], the last i naming a leaf wins (the order of Replay_buffer.update calls in
  *               vdn/_train.py:96-99); node indices outside the leaf range are ignored; inner nodes recomputed.
  *               workspace: int32[capacity].
  *   rows_scatter: dst[t][slot[i]] = src[t][i] for n <= 8 row-major float tensors (row_floats[t] floats per row); slot -1 skips. */
 int mm_heaptree_add_set(double* tree, int32_t capacity, int32_t* n_data_dev, const double* priority, const uint8_t* valid,
-                        int32_t k, int64_t* slot_out, int32_t* workspace, void* stream);
+                        int32_t k, int64_t* slot_out, int32_t* workspace, int32_t rebuild, void* stream);
+int mm_heaptree_rebuild(double* tree, int32_t capacity, void* stream);
+/* One episode of N lockstep envs: C consecutive add_set calls (chunk c of every env, in the reference's add order) plus the
+ * payload scatter of each (src tensors chunk-major [C][N][row_floats]), one host call; inner nodes recomputed at the end.
+ * priority / valid / slot_out: [C][N]; workspace: int32[N + 2 * capacity + 4]. */
+int mm_chunk_per_insert_episode(double* tree, int32_t capacity, int32_t* n_data_dev, const double* priority, const uint8_t* valid,
+                                int32_t C, int32_t N, int64_t* slot_out, int32_t* workspace, const float* const* src_host,
+                                float* const* dst_host, const int32_t* row_floats_host, int32_t n_tensors, void* stream);
 int mm_heaptree_set_leaves(double* tree, int32_t capacity, const int64_t* node_idx, const double* priority, int32_t n,
                            int32_t* workspace, void* stream);
 int mm_rows_scatter(const float* const* src_host, float* const* dst_host, const int32_t* row_floats_host, int32_t n,

@@ -113,7 +113,9 @@ SIGNATURES = {
                                                   C.POINTER(CheckersCfg), _P]),
     "mm_qmix_rollout_tc": (C.c_int, [_P, _P, _P, _P, C.POINTER(RolloutIO), C.POINTER(CheckersCfg), C.POINTER(C.c_float),
                                      C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _P]),
-    "mm_heaptree_add_set": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P]),
+    "mm_heaptree_add_set": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, C.c_int32, _P]),
+    "mm_heaptree_rebuild": (C.c_int, [_P, C.c_int32, _P]),
+    "mm_chunk_per_insert_episode": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "mm_heaptree_set_leaves": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, _P, _P]),
     "mm_rows_scatter": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P]),
     "mm_toplevel_qnet_param_count": (C.c_int, [C.c_int32, C.c_int32]),

@@ -216,17 +216,20 @@ class SumTree:
         _lib.check(_lib.lib().mm_heaptree_set_leaves(_lib.ptr(self.priority_tree), self.capacity, _lib.ptr(idx), _lib.ptr(pr),
                                                      idx.numel(), _lib.ptr(self._ws), _lib.stream()))
 
-    def add_set(self, priority, valid=None):
+    def rebuild(self):
+        _lib.check(_lib.lib().mm_heaptree_rebuild(_lib.ptr(self.priority_tree), self.capacity, _lib.stream()))
+
+    def add_set(self, priority, valid=None, rebuild=True):
         """Batch insert with set semantics (``mm_heaptree_add_set``); returns the slot of every item (-1 = not stored).  The
         fill count lives on the device; ``sync_n_data`` refreshes the host copy."""
         k = priority.numel()
         if self._n_data_dev is None:
             self._n_data_dev = torch.tensor([self.n_data], dtype=torch.int32, device=self.device)
-        ws = torch.empty(k + self.capacity + 4, dtype=torch.int32, device=self.device)
+        ws = torch.empty(k + 2 * self.capacity + 4, dtype=torch.int32, device=self.device)
         slot = torch.empty(k, dtype=torch.int64, device=self.device)
         _lib.check(_lib.lib().mm_heaptree_add_set(_lib.ptr(self.priority_tree), self.capacity, _lib.ptr(self._n_data_dev),
                                                   _lib.ptr(priority), _lib.ptr(valid), k, _lib.ptr(slot), _lib.ptr(ws),
-                                                  _lib.stream()))
+                                                  int(bool(rebuild)), _lib.stream()))
         return slot
 
     def sync_n_data(self):
@@ -324,7 +327,7 @@ class Prioritized_Experience_Replay:
             tree.n_data += 1
         return tree.n_data if warm_up else None
 
-    def collect_samples_batch(self, samples, td_errors, warm_up, host_pow=False, valid=None):
+    def collect_samples_batch(self, samples, td_errors, warm_up, host_pow=False, valid=None, rebuild=True, priorities=None):
         """K consecutive ``collect_sample`` calls -- the chunks N lockstep envs finish at the same step, in env order
         (the reference's add order) -- without a Python loop: ``mm_heaptree_add_batch`` replays the K ``SumTree.add``s
         on the device (fill, then arg-min eviction where a later chunk may evict an earlier one of the same batch), the
@@ -333,13 +336,15 @@ class Prioritized_Experience_Replay:
         td_errors [K].  ``host_pow``: raise (td + eps) ** alpha with Python doubles like the reference (one D2H sync)
         instead of torch.pow on the device (<= 1 ulp from libm).
         ``fast_tree`` or ``valid`` (uint8 [K]: chunks of envs that had already finished are not stored): the batch goes in as a
-        SET (``mm_heaptree_add_set`` + one ``mm_rows_scatter``), see heaptree_batch.cu."""
+        SET (``mm_heaptree_add_set`` + one ``mm_rows_scatter``), see heaptree_batch.cu; ``rebuild=False`` defers the inner-node
+        recomputation (call ``sum_tree.rebuild()`` after the last insert of a run), ``priorities`` (float64 [K]) replaces
+        ``(td + eps) ** alpha`` when the caller raised a whole episode's TD sums at once."""
         tree = self.sum_tree
         s, a, r, s2, d = (torch.as_tensor(x, device=self.device, dtype=torch.float32) for x in samples)
         K = s.shape[0]
         td = torch.as_tensor(td_errors, device=self.device).reshape(K)
         if self.fast_tree or valid is not None:
-            return self._collect_set(s, a, r, s2, d, td, valid, warm_up)
+            return self._collect_set(s, a, r, s2, d, td, valid, warm_up, rebuild, priorities)
         if host_pow:
             prio = torch.tensor([(float(v) + self.eps) ** self.alpha for v in td.tolist()], dtype=torch.float64, device=self.device)
         else:
@@ -363,14 +368,18 @@ class Prioritized_Experience_Replay:
         tree.n_data = min(self.capacity, tree.n_data + K)
         return tree.n_data if warm_up else None
 
-    def _collect_set(self, s, a, r, s2, d, td, valid, warm_up):
+    def priorities_from_td(self, td):
+        """(td + eps) ** alpha in float64 on the device, alpha from the device schedule in graph mode."""
+        alpha = self._sched[0] if self._sched is not None else self.alpha
+        return torch.pow(td.to(torch.float64) + self.eps, alpha)
+
+    def _collect_set(self, s, a, r, s2, d, td, valid, warm_up, rebuild=True, priorities=None):
         tree = self.sum_tree
         K = s.shape[0]
-        alpha = self._sched[0] if self._sched is not None else self.alpha
-        prio = torch.pow(td.to(torch.float64) + self.eps, alpha).contiguous()
-        if valid is not None:
+        prio = (priorities if priorities is not None else self.priorities_from_td(td)).contiguous()
+        if valid is not None and (valid.dtype != torch.uint8 or not valid.is_contiguous()):
             valid = valid.to(device=self.device, dtype=torch.uint8).contiguous()
-        slot = tree.add_set(prio, valid)
+        slot = tree.add_set(prio, valid, rebuild=rebuild)
         src = [s.reshape(K, -1), a.reshape(K, -1), r.reshape(K, -1), s2.reshape(K, -1), d.reshape(K, -1)]
         dst = [self.states, self.actions, self.rewards, self.next_states, self.dones]
         src = [x if x.is_contiguous() else x.contiguous() for x in src]
@@ -381,6 +390,30 @@ class Prioritized_Experience_Replay:
         if warm_up:
             return tree.sync_n_data()
         return None
+
+    def collect_episode(self, chunks, td_sums, valid):
+        """All chunks of one lockstep episode: ``chunks`` = [states [C,N,L,A,D], actions [C,N,L,A], rewards [C,N,L,A], next_states,
+        dones [C,N,L]] (contiguous, chunk-major), ``td_sums`` / ``valid`` [C,N].  Equivalent to C ``collect_samples_batch`` calls
+        with set semantics (chunk order = the reference's add order), issued as one library call."""
+        tree = self.sum_tree
+        Cn, N = td_sums.shape
+        prio = self.priorities_from_td(td_sums).contiguous()
+        valid = valid.to(device=self.device, dtype=torch.uint8).contiguous()
+        if tree._n_data_dev is None:
+            tree._n_data_dev = torch.tensor([tree.n_data], dtype=torch.int32, device=self.device)
+        ws = torch.empty(N + 2 * self.capacity + 4, dtype=torch.int32, device=self.device)
+        slot = torch.empty((Cn, N), dtype=torch.int64, device=self.device)
+        dst = [self.states, self.actions, self.rewards, self.next_states, self.dones]
+        for x in chunks:
+            if not (x.is_cuda and x.is_contiguous() and x.dtype == torch.float32):
+                raise RuntimeError("collect_episode takes contiguous float32 CUDA tensors")
+        sp = (C.c_void_p * 5)(*[x.data_ptr() for x in chunks])
+        dp = (C.c_void_p * 5)(*[x.data_ptr() for x in dst])
+        rf = (C.c_int32 * 5)(*[x[0, 0].numel() for x in chunks])
+        _lib.check(_lib.lib().mm_chunk_per_insert_episode(
+            _lib.ptr(tree.priority_tree), self.capacity, _lib.ptr(tree._n_data_dev), _lib.ptr(prio), _lib.ptr(valid), Cn, N,
+            _lib.ptr(slot), _lib.ptr(ws), sp, dp, rf, 5, _lib.stream()))
+        return slot
 
     def sample_indices(self, batch_size, uniforms=None):
         """The stratified draw without the payload gather: (data slots [B] int64, node ids [B] int64, IS weights [B,1] f32)."""

@@ -28,11 +28,12 @@ struct SetHeader { int fill, evict, n_old, pad; };
 // one CTA: exclusive scan of the valid flags -> vrank, header, n_data update
 __global__ void __launch_bounds__(kScanThreads) set_scan_kernel(const uint8_t* __restrict__ valid, int k, int capacity,
                                                                  int* __restrict__ n_data, int* __restrict__ vrank,
-                                                                 SetHeader* __restrict__ hdr) {
+                                                                 SetHeader* __restrict__ hdr, int* __restrict__ rank) {
     __shared__ int warp_tot[32];
     __shared__ int carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) carry = 0;
+    for (int i = tid; i < capacity; i += kScanThreads) rank[i] = 0;
     __syncthreads();
     for (int base = 0; base < k; base += kScanThreads) {
         const int i = base + tid;
@@ -71,30 +72,34 @@ __global__ void __launch_bounds__(kScanThreads) set_scan_kernel(const uint8_t* _
     }
 }
 
-// rank of every old leaf among the old leaves by (priority, slot); the `evict` lowest publish their slot
+// rank of every old leaf among the old leaves by (priority, slot): block (x, y) counts, for 256 leaves, how many of the 1 024
+// leaves of slice y sort before each of them, and adds that to rank[]
 __global__ void __launch_bounds__(256) set_rank_kernel(const double* __restrict__ tree, int capacity,
-                                                       const SetHeader* __restrict__ hdr, int* __restrict__ evict_slot) {
+                                                       const SetHeader* __restrict__ hdr, int* __restrict__ rank) {
     __shared__ unsigned long long keys[1024];
-    const int n_old = hdr->n_old, evict = hdr->evict;
-    if (evict == 0) return;
+    const int n_old = hdr->n_old;
+    if (hdr->evict == 0) return;
+    const int base = blockIdx.y * 1024;
+    if (base >= n_old || blockIdx.x * blockDim.x >= n_old) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long* leaf = reinterpret_cast<const unsigned long long*>(tree + capacity - 1);
     // priorities are non-negative doubles: their bit patterns order like the values
     const unsigned long long mine = i < n_old ? leaf[i] : 0ull;
-    int rank = 0;
-    for (int base = 0; base < n_old; base += 1024) {
-        const int m = min(1024, n_old - base);
-        __syncthreads();
-        for (int t = threadIdx.x; t < m; t += blockDim.x) keys[t] = leaf[base + t];
-        __syncthreads();
-        if (i < n_old) {
-            for (int t = 0; t < m; ++t) {
-                const unsigned long long kt = keys[t];
-                rank += (kt < mine) || (kt == mine && base + t < i);
-            }
-        }
+    const int m = min(1024, n_old - base);
+    for (int t = threadIdx.x; t < m; t += blockDim.x) keys[t] = leaf[base + t];
+    __syncthreads();
+    if (i >= n_old) return;
+    int r = 0;
+#pragma unroll 4
+    for (int t = 0; t < m; ++t) {
+        const unsigned long long kt = keys[t];
+        r += (kt < mine) || (kt == mine && base + t < i);
     }
-    if (i < n_old && rank < evict) evict_slot[rank] = i;
+    if (r) atomicAdd(rank + i, r);
+}
+__global__ void set_publish_kernel(const SetHeader* __restrict__ hdr, const int* __restrict__ rank, int* __restrict__ evict_slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < hdr->n_old && rank[i] < hdr->evict) evict_slot[rank[i]] = i;
 }
 
 __global__ void set_assign_kernel(double* __restrict__ tree, int capacity, const SetHeader* __restrict__ hdr,
@@ -162,18 +167,27 @@ __global__ void __launch_bounds__(256) rows_scatter_kernel(const __grid_constant
 
 }  // namespace
 
-// workspace: int32[k + capacity + 4]
+// workspace: int32[k + 2 * capacity + 4]
 extern "C" int mm_heaptree_add_set(double* tree, int32_t capacity, int32_t* n_data_dev, const double* priority,
-                                   const uint8_t* valid, int32_t k, int64_t* slot_out, int32_t* workspace, void* stream) {
+                                   const uint8_t* valid, int32_t k, int64_t* slot_out, int32_t* workspace, int32_t rebuild,
+                                   void* stream) {
     if (!tree || !n_data_dev || !priority || !slot_out || !workspace || capacity <= 0 || k <= 0) return MM_ERR_BAD_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SetHeader* hdr = reinterpret_cast<SetHeader*>(workspace);
     int* vrank = workspace + 4;
     int* evict_slot = vrank + k;
-    set_scan_kernel<<<1, kScanThreads, 0, st>>>(valid, k, capacity, n_data_dev, vrank, hdr);
-    set_rank_kernel<<<(capacity + 255) / 256, 256, 0, st>>>(tree, capacity, hdr, evict_slot);
+    int* rank = evict_slot + capacity;
+    set_scan_kernel<<<1, kScanThreads, 0, st>>>(valid, k, capacity, n_data_dev, vrank, hdr, rank);
+    set_rank_kernel<<<dim3((capacity + 255) / 256, (capacity + 1023) / 1024), 256, 0, st>>>(tree, capacity, hdr, rank);
+    set_publish_kernel<<<(capacity + 255) / 256, 256, 0, st>>>(hdr, rank, evict_slot);
     set_assign_kernel<<<(k + 255) / 256, 256, 0, st>>>(tree, capacity, hdr, vrank, evict_slot, priority, k, slot_out);
-    rebuild_kernel<<<1, 1024, 0, st>>>(tree, capacity);
+    if (rebuild) rebuild_kernel<<<1, 1024, 0, st>>>(tree, capacity);
+    return mm::check_launch();
+}
+
+extern "C" int mm_heaptree_rebuild(double* tree, int32_t capacity, void* stream) {
+    if (!tree || capacity <= 0) return MM_ERR_BAD_ARG;
+    rebuild_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(tree, capacity);
     return mm::check_launch();
 }
 
@@ -200,5 +214,41 @@ extern "C" int mm_rows_scatter(const float* const* src_host, float* const* dst_h
     }
     a.slot = slot; a.k = k; a.n = n;
     rows_scatter_kernel<<<dim3(k, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return mm::check_launch();
+}
+
+// A whole episode of N lockstep envs: C consecutive mm_heaptree_add_set calls (chunk c of every env, c = 0..C-1, in the
+// order the reference adds them) and the payload scatter of each, enqueued from ONE host call; inner nodes recomputed once at
+// the end.  priority / valid / slot_out: [C][N]; src tensors are chunk-major [C][N][row_floats].  workspace: int32[N + 2 * capacity + 4].
+extern "C" int mm_chunk_per_insert_episode(double* tree, int32_t capacity, int32_t* n_data_dev, const double* priority,
+                                           const uint8_t* valid, int32_t C, int32_t N, int64_t* slot_out, int32_t* workspace,
+                                           const float* const* src_host, float* const* dst_host, const int32_t* row_floats_host,
+                                           int32_t n_tensors, void* stream) {
+    if (!tree || !n_data_dev || !priority || !slot_out || !workspace || capacity <= 0 || C <= 0 || N <= 0) return MM_ERR_BAD_ARG;
+    if (!src_host || !dst_host || !row_floats_host || n_tensors <= 0 || n_tensors > 8) return MM_ERR_BAD_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SetHeader* hdr = reinterpret_cast<SetHeader*>(workspace);
+    int* vrank = workspace + 4;
+    int* evict_slot = vrank + N;
+    int* rank = evict_slot + capacity;
+    ScatterArgs sc{};
+    for (int t = 0; t < n_tensors; ++t) {
+        if (!src_host[t] || !dst_host[t] || row_floats_host[t] <= 0) return MM_ERR_BAD_ARG;
+        sc.dst[t] = dst_host[t]; sc.row_floats[t] = row_floats_host[t];
+    }
+    sc.k = N; sc.n = n_tensors;
+    for (int c = 0; c < C; ++c) {
+        const double* pr = priority + (size_t)c * N;
+        const uint8_t* va = valid ? valid + (size_t)c * N : nullptr;
+        int64_t* so = slot_out + (size_t)c * N;
+        set_scan_kernel<<<1, kScanThreads, 0, st>>>(va, N, capacity, n_data_dev, vrank, hdr, rank);
+        set_rank_kernel<<<dim3((capacity + 255) / 256, (capacity + 1023) / 1024), 256, 0, st>>>(tree, capacity, hdr, rank);
+        set_publish_kernel<<<(capacity + 255) / 256, 256, 0, st>>>(hdr, rank, evict_slot);
+        set_assign_kernel<<<(N + 255) / 256, 256, 0, st>>>(tree, capacity, hdr, vrank, evict_slot, pr, N, so);
+        for (int t = 0; t < n_tensors; ++t) sc.src[t] = src_host[t] + (size_t)c * N * row_floats_host[t];
+        sc.slot = so;
+        rows_scatter_kernel<<<dim3(N, n_tensors), 256, 0, st>>>(sc);
+    }
+    rebuild_kernel<<<1, 1024, 0, st>>>(tree, capacity);
     return mm::check_launch();
 }

@@ -25,8 +25,10 @@
 namespace {
 
 constexpr int F1 = 64, F2 = 32, HH = 32, NAMAX = 8;
-constexpr int RT = 32;        // rows per agent block
-constexpr int BT = 128;       // threads per agent block
+constexpr int RT = 32;        // rows (envs) per CTA at most
+constexpr int RPT = 4;        // rows per warp in the forward kernels: a warp owns its rows through every layer and step
+constexpr int BT = 32 * (RT / RPT);   // threads per CTA at most (forward)
+constexpr int BTB = 128;      // threads per CTA of the backward kernel (8 rows per thread: its registers hold the gradients)
 constexpr int HS = 36;        // row stride of the hidden tiles (conflict-free float4 reads by row)
 constexpr int SV = 256;       // saved floats per (agent, step, row): x1 64 | x2 32 | r | z | n | gh_n | h (32 each)
 constexpr int kMaxD = 96;
@@ -38,185 +40,189 @@ struct QNetP {                // reference layout (nn.Linear / nn.GRUCell: weigh
 __host__ __device__ inline int pad4(int d) { return (d + 3) & ~3; }
 __host__ __device__ inline int pad8(int d) { return (d + 7) & ~7; }
 
-// floats of shared memory one agent block needs
-__host__ __device__ inline int block_smem_floats(int Dp, int n_x0) {
-    return Dp * F1 + F1 + F1 * F2 + F2 + HH * 6 * HH + 6 * HH + HH * NAMAX + NAMAX     // weights
-           + n_x0 * RT * Dp + RT * F1 + RT * F2 + 2 * RT * HS + RT * NAMAX;            // activations
-}
+// shared-memory floats: one agent's weights; one warp's activation tiles (one agent, n_x0 observation buffers)
+__host__ __device__ inline int weight_floats(int Dp) { return Dp * F1 + F1 + F1 * F2 + F2 + HH * 6 * HH + 6 * HH + HH * NAMAX + NAMAX; }
+__host__ __device__ inline int tile_floats(int Dp, int n_x0, int R = RPT) { return R * (n_x0 * Dp + F1 + F2 + 2 * HS + NAMAX); }
 
-struct Blk {                  // shared-memory views of one agent block
-    float *W1t, *b1, *W2t, *b2, *Wg, *bg, *Wot, *bo, *x0, *x1, *x2, *h, *q;
+// Weight matrices are stored as [k / 4][unit][4]: the four consecutive-k weights of one output unit are one 16-byte word,
+// lane = unit reads consecutive words (one conflict-free LDS.128 per unit and four k); the gate weights as
+// [k / 4][gate][unit][4] with gates 0..2 = W_ih (r, z, n), 3..5 = W_hh.
+struct Wts {
+    const float *W1q, *b1, *W2q, *b2, *Wgq, *bg, *Wot, *bo;
+};
+struct Tile {                 // activation tiles of RPT rows, private to one warp
+    float *x0, *x1, *x2, *h, *q;
 };
 
-__device__ __forceinline__ Blk carve(float* base, int Dp, int n_x0) {
-    Blk b;
-    float* p = base;
-    b.W1t = p; p += Dp * F1;
-    b.b1 = p; p += F1;
-    b.W2t = p; p += F1 * F2;
-    b.b2 = p; p += F2;
-    b.Wg = p; p += HH * 6 * HH;
-    b.bg = p; p += 6 * HH;
-    b.Wot = p; p += HH * NAMAX;
-    b.bo = p; p += NAMAX;
-    b.x0 = p; p += n_x0 * RT * Dp;
-    b.x1 = p; p += RT * F1;
-    b.x2 = p; p += RT * F2;
-    b.h = p; p += 2 * RT * HS;
-    b.q = p;
-    return b;
+__device__ __forceinline__ Wts carve_weights(float* p, int Dp) {
+    Wts w;
+    w.W1q = p; p += Dp * F1;
+    w.b1 = p; p += F1;
+    w.W2q = p; p += F1 * F2;
+    w.b2 = p; p += F2;
+    w.Wgq = p; p += HH * 6 * HH;
+    w.bg = p; p += 6 * HH;
+    w.Wot = p; p += HH * NAMAX;
+    w.bo = p;
+    return w;
+}
+__device__ __forceinline__ Tile carve_tile(float* p, int Dp, int n_x0, int R = RPT) {
+    Tile t;
+    t.x0 = p; p += R * n_x0 * Dp;
+    t.x1 = p; p += R * F1;
+    t.x2 = p; p += R * F2;
+    t.h = p; p += 2 * R * HS;
+    t.q = p;
+    return t;
 }
 
-__device__ __forceinline__ void bar_block(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(BT) : "memory"); }
-
-// stages one agent's weights (reference layout in global memory) into the transposed shared layout
-__device__ void stage_weights(const Blk& s, const QNetP& w, int D, int Dp, int NA, int bt) {
-    for (int i = bt; i < Dp * F1; i += BT) {
-        const int k = i / F1, n = i - k * F1;
-        s.W1t[i] = k < D ? w.w1[n * D + k] : 0.f;
+// stages one agent's weights (reference layout in global memory, read with unit stride) into the shared layout
+__device__ void stage_weights(float* base, const QNetP& w, int D, int Dp, int NA, int tid, int nthreads) {
+    float* W1q = base;
+    float* b1 = W1q + Dp * F1;
+    float* W2q = b1 + F1;
+    float* b2 = W2q + F1 * F2;
+    float* Wgq = b2 + F2;
+    float* bg = Wgq + HH * 6 * HH;
+    float* Wot = bg + 6 * HH;
+    float* bo = Wot + HH * NAMAX;
+    for (int i = tid; i < F1 * Dp; i += nthreads) {             // i = n * Dp + k
+        const int n = i / Dp, k = i - n * Dp;
+        W1q[((k >> 2) * F1 + n) * 4 + (k & 3)] = k < D ? w.w1[n * D + k] : 0.f;
     }
-    for (int i = bt; i < F1; i += BT) s.b1[i] = w.b1[i];
-    for (int i = bt; i < F1 * F2; i += BT) {
-        const int k = i / F2, n = i - k * F2;
-        s.W2t[i] = w.w2[n * F1 + k];
+    for (int i = tid; i < F1; i += nthreads) b1[i] = w.b1[i];
+    for (int i = tid; i < F2 * F1; i += nthreads) {             // i = n * 64 + k
+        const int n = i >> 6, k = i & 63;
+        W2q[((k >> 2) * F2 + n) * 4 + (k & 3)] = w.w2[i];
     }
-    for (int i = bt; i < F2; i += BT) s.b2[i] = w.b2[i];
-    for (int i = bt; i < HH * 6 * HH; i += BT) {                // Wg[k][gate][j]: gates 0..2 = W_ih (r, z, n), 3..5 = W_hh
-        const int k = i / (6 * HH), rem = i - k * 6 * HH, gate = rem / HH, j = rem - gate * HH;
-        s.Wg[i] = gate < 3 ? w.wih[(gate * HH + j) * F2 + k] : w.whh[((gate - 3) * HH + j) * HH + k];
+    for (int i = tid; i < F2; i += nthreads) b2[i] = w.b2[i];
+    for (int i = tid; i < 3 * HH * HH; i += nthreads) {         // i = (gate * 32 + j) * 32 + k
+        const int gj = i >> 5, k = i & 31, gate = gj >> 5, j = gj & 31;
+        Wgq[(((k >> 2) * 6 + gate) * HH + j) * 4 + (k & 3)] = w.wih[i];
+        Wgq[(((k >> 2) * 6 + gate + 3) * HH + j) * 4 + (k & 3)] = w.whh[i];
     }
-    for (int i = bt; i < 6 * HH; i += BT) s.bg[i] = i < 3 * HH ? w.bih[i] : w.bhh[i - 3 * HH];
-    for (int i = bt; i < HH * NAMAX; i += BT) {
+    for (int i = tid; i < 6 * HH; i += nthreads) bg[i] = i < 3 * HH ? w.bih[i] : w.bhh[i - 3 * HH];
+    for (int i = tid; i < HH * NAMAX; i += nthreads) {
         const int k = i / NAMAX, o = i - k * NAMAX;
-        s.Wot[i] = o < NA ? w.wo[o * HH + k] : 0.f;
+        Wot[i] = o < NA ? w.wo[o * HH + k] : 0.f;
     }
-    for (int i = bt; i < NAMAX; i += BT) s.bo[i] = i < NA ? w.bo[i] : 0.f;
+    for (int i = tid; i < NAMAX; i += nthreads) bo[i] = i < NA ? w.bo[i] : 0.f;
 }
 
 __device__ __forceinline__ float sigmoid_(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_(float x) { return 1.0f - 2.0f * __frcp_rn(1.0f + __expf(2.0f * x)); }
+__device__ __forceinline__ float dot4(const float4& x, const float4& w, float acc) {
+    acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc);
+    return fmaf(x.w, w.w, acc);
+}
 
-// One forward step of the agent block: x0 tile -> q tile; hidden state h[cur] -> h[cur ^ 1].
-// `sv` (SAVE): this tile's rows of the activation record of this step, row stride SV.
-// `keep_in`: per-row multiplier applied to the incoming hidden state (hidden reset after a terminal step), or null.
-template <bool SAVE>
-__device__ __forceinline__ void qnet_step(const Blk& s, const float* x0, int Dp, int cur, int bt, int bar_id, float* sv,
-                                          int n_valid) {
-    const int j = bt & 31, g = bt >> 5, r0 = g * 8;
-    // ---- fc1: [RT x Dp] x [Dp x 64] ------------------------------------------------------------------------------
+// One forward step of one warp's RPT rows of one agent: x0 tile -> q tile; hidden state h[cur] -> h[cur ^ 1].  Lane = output
+// unit.  Every layer reads only what this warp wrote, so the only synchronisation is __syncwarp: the warps of a CTA share
+// the weights and nothing else, and run through the time loop independently of each other.
+// `sv` (SAVE): this warp's rows of the activation record of this step, row stride SV; rows >= n_valid are not stored.
+template <bool SAVE, int R>
+__device__ __forceinline__ void qnet_step_warp(const Wts& w, const Tile& t, const float* x0, int Dp, int cur, int lane, float* sv,
+                                               int n_valid) {
+    const int j = lane;
+    // ---- fc1: [RPT x Dp] x [Dp x 64] -------------------------------------------------------------------------------
     {
-        float a0[8], a1[8];
-        const float c0 = s.b1[j], c1 = s.b1[j + 32];
+        float a0[R], a1[R];
+        const float c0 = w.b1[j], c1 = w.b1[j + 32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a0[i] = c0; a1[i] = c1; }
-        for (int k = 0; k < Dp; k += 4) {
-            const float* wk = s.W1t + k * F1 + j;
-            const float w00 = wk[0], w01 = wk[F1], w02 = wk[2 * F1], w03 = wk[3 * F1];
-            const float w10 = wk[32], w11 = wk[F1 + 32], w12 = wk[2 * F1 + 32], w13 = wk[3 * F1 + 32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 x = *reinterpret_cast<const float4*>(x0 + (r0 + i) * Dp + k);
-                a0[i] = fmaf(x.x, w00, a0[i]); a0[i] = fmaf(x.y, w01, a0[i]);
-                a0[i] = fmaf(x.z, w02, a0[i]); a0[i] = fmaf(x.w, w03, a0[i]);
-                a1[i] = fmaf(x.x, w10, a1[i]); a1[i] = fmaf(x.y, w11, a1[i]);
-                a1[i] = fmaf(x.z, w12, a1[i]); a1[i] = fmaf(x.w, w13, a1[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float v0 = fmaxf(a0[i], 0.f), v1 = fmaxf(a1[i], 0.f);
-            s.x1[(r0 + i) * F1 + j] = v0;
-            s.x1[(r0 + i) * F1 + j + 32] = v1;
-            if (SAVE && r0 + i < n_valid) { sv[(r0 + i) * SV + j] = v0; sv[(r0 + i) * SV + j + 32] = v1; }
-        }
-    }
-    bar_block(bar_id);
-    // ---- fc2: [RT x 64] x [64 x 32] -------------------------------------------------------------------------------
-    {
-        float a[8];
-        const float c = s.b2[j];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = c;
-#pragma unroll 4
-        for (int k = 0; k < F1; k += 4) {
-            const float* wk = s.W2t + k * F2 + j;
-            const float w0 = wk[0], w1 = wk[F2], w2 = wk[2 * F2], w3 = wk[3 * F2];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 x = *reinterpret_cast<const float4*>(s.x1 + (r0 + i) * F1 + k);
-                a[i] = fmaf(x.x, w0, a[i]); a[i] = fmaf(x.y, w1, a[i]);
-                a[i] = fmaf(x.z, w2, a[i]); a[i] = fmaf(x.w, w3, a[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float v = fmaxf(a[i], 0.f);
-            s.x2[(r0 + i) * F2 + j] = v;
-            if (SAVE && r0 + i < n_valid) sv[(r0 + i) * SV + 64 + j] = v;
-        }
-    }
-    bar_block(bar_id);
-    // ---- GRUCell: gi = W_ih x2 + b_ih, gh = W_hh h + b_hh; r, z, n; h' = (1 - z) n + z h ----------------------------
-    {
-        const float* hc = s.h + cur * RT * HS;
-        float* hn = s.h + (cur ^ 1) * RT * HS;
-        float ar[8], az[8], ai[8], ah[8];
-        const float cr = s.bg[j] + s.bg[3 * HH + j], cz = s.bg[HH + j] + s.bg[4 * HH + j];
-        const float ci = s.bg[2 * HH + j], ch = s.bg[5 * HH + j];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { ar[i] = cr; az[i] = cz; ai[i] = ci; ah[i] = ch; }
+        for (int i = 0; i < R; ++i) { a0[i] = c0; a1[i] = c1; }
+        const float4* wq = reinterpret_cast<const float4*>(w.W1q) + j;
 #pragma unroll 2
-        for (int k = 0; k < HH; k += 4) {
-            float wir[4], wiz[4], win[4], whr[4], whz[4], whn[4];
+        for (int k4 = 0; k4 < (Dp >> 2); ++k4) {
+            const float4 wa = wq[k4 * F1], wb = wq[k4 * F1 + 32];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float* wk = s.Wg + (k + u) * 6 * HH + j;
-                wir[u] = wk[0]; wiz[u] = wk[HH]; win[u] = wk[2 * HH];
-                whr[u] = wk[3 * HH]; whz[u] = wk[4 * HH]; whn[u] = wk[5 * HH];
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 x = *reinterpret_cast<const float4*>(s.x2 + (r0 + i) * F2 + k);
-                const float4 h = *reinterpret_cast<const float4*>(hc + (r0 + i) * HS + k);
-                const float xv[4] = {x.x, x.y, x.z, x.w}, hv[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    ar[i] = fmaf(xv[u], wir[u], ar[i]); ar[i] = fmaf(hv[u], whr[u], ar[i]);
-                    az[i] = fmaf(xv[u], wiz[u], az[i]); az[i] = fmaf(hv[u], whz[u], az[i]);
-                    ai[i] = fmaf(xv[u], win[u], ai[i]);
-                    ah[i] = fmaf(hv[u], whn[u], ah[i]);
-                }
+            for (int i = 0; i < R; ++i) {
+                const float4 x = *reinterpret_cast<const float4*>(x0 + i * Dp + 4 * k4);
+                a0[i] = dot4(x, wa, a0[i]);
+                a1[i] = dot4(x, wb, a1[i]);
             }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < R; ++i) {
+            const float v0 = fmaxf(a0[i], 0.f), v1 = fmaxf(a1[i], 0.f);
+            t.x1[i * F1 + j] = v0;
+            t.x1[i * F1 + j + 32] = v1;
+            if (SAVE && i < n_valid) { sv[i * SV + j] = v0; sv[i * SV + j + 32] = v1; }
+        }
+    }
+    __syncwarp();
+    // ---- fc2: [RPT x 64] x [64 x 32] --------------------------------------------------------------------------------
+    {
+        float a[R];
+        const float c = w.b2[j];
+#pragma unroll
+        for (int i = 0; i < R; ++i) a[i] = c;
+        const float4* wq = reinterpret_cast<const float4*>(w.W2q) + j;
+#pragma unroll 4
+        for (int k4 = 0; k4 < F1 / 4; ++k4) {
+            const float4 ww = wq[k4 * F2];
+#pragma unroll
+            for (int i = 0; i < R; ++i) a[i] = dot4(*reinterpret_cast<const float4*>(t.x1 + i * F1 + 4 * k4), ww, a[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const float v = fmaxf(a[i], 0.f);
+            t.x2[i * F2 + j] = v;
+            if (SAVE && i < n_valid) sv[i * SV + 64 + j] = v;
+        }
+    }
+    __syncwarp();
+    // ---- GRUCell: gi = W_ih x2 + b_ih, gh = W_hh h + b_hh; r, z, n; h' = (1 - z) n + z h ------------------------------
+    const float* hc = t.h + cur * R * HS;
+    float* hn = t.h + (cur ^ 1) * R * HS;
+    {
+        float ar[R], az[R], ai[R], ah[R];
+        const float cr = w.bg[j] + w.bg[3 * HH + j], cz = w.bg[HH + j] + w.bg[4 * HH + j];
+        const float ci = w.bg[2 * HH + j], ch = w.bg[5 * HH + j];
+#pragma unroll
+        for (int i = 0; i < R; ++i) { ar[i] = cr; az[i] = cz; ai[i] = ci; ah[i] = ch; }
+        const float4* wq = reinterpret_cast<const float4*>(w.Wgq) + j;
+#pragma unroll 2
+        for (int k4 = 0; k4 < HH / 4; ++k4) {
+            const float4 wir = wq[(k4 * 6 + 0) * HH], wiz = wq[(k4 * 6 + 1) * HH], win = wq[(k4 * 6 + 2) * HH];
+            const float4 whr = wq[(k4 * 6 + 3) * HH], whz = wq[(k4 * 6 + 4) * HH], whn = wq[(k4 * 6 + 5) * HH];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const float4 x = *reinterpret_cast<const float4*>(t.x2 + i * F2 + 4 * k4);
+                const float4 h = *reinterpret_cast<const float4*>(hc + i * HS + 4 * k4);
+                ar[i] = dot4(h, whr, dot4(x, wir, ar[i]));
+                az[i] = dot4(h, whz, dot4(x, wiz, az[i]));
+                ai[i] = dot4(x, win, ai[i]);
+                ah[i] = dot4(h, whn, ah[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
             const float r = sigmoid_(ar[i]), z = sigmoid_(az[i]);
             const float n = tanh_(fmaf(r, ah[i], ai[i]));
-            const float hp = hc[(r0 + i) * HS + j];
+            const float hp = hc[i * HS + j];
             const float hv = fmaf(z, hp - n, n);
-            hn[(r0 + i) * HS + j] = hv;
-            if (SAVE && r0 + i < n_valid) {
-                float* o = sv + (r0 + i) * SV + 96 + j;
+            hn[i * HS + j] = hv;
+            if (SAVE && i < n_valid) {
+                float* o = sv + i * SV + 96 + j;
                 o[0] = r; o[32] = z; o[64] = n; o[96] = ah[i]; o[128] = hv;
             }
         }
     }
-    bar_block(bar_id);
-    // ---- head: q[r][o] --------------------------------------------------------------------------------------------
+    __syncwarp();
+    // ---- head: lane = (row, output): RPT * NAMAX = 32 ----------------------------------------------------------------------
     {
-        const float* hn = s.h + (cur ^ 1) * RT * HS;
-        const int r = bt >> 2, oo = bt & 3;
-        float q0 = s.bo[oo], q1 = s.bo[oo + 4];
+        static_assert(R * NAMAX <= 32, "head mapping: one (row, output) per lane");
+        const int r = (lane >> 3) % R, o = lane & 7;               // lanes beyond R * NAMAX repeat rows (same values written)
+        float q = w.bo[o];
 #pragma unroll
         for (int k = 0; k < HH; k += 4) {
             const float4 h = *reinterpret_cast<const float4*>(hn + r * HS + k);
-            const float* wk = s.Wot + k * NAMAX + oo;
-            q0 = fmaf(h.x, wk[0], q0); q0 = fmaf(h.y, wk[NAMAX], q0); q0 = fmaf(h.z, wk[2 * NAMAX], q0); q0 = fmaf(h.w, wk[3 * NAMAX], q0);
-            q1 = fmaf(h.x, wk[4], q1); q1 = fmaf(h.y, wk[NAMAX + 4], q1); q1 = fmaf(h.z, wk[2 * NAMAX + 4], q1); q1 = fmaf(h.w, wk[3 * NAMAX + 4], q1);
+            const float* wk = w.Wot + k * NAMAX + o;
+            q = fmaf(h.x, wk[0], q); q = fmaf(h.y, wk[NAMAX], q); q = fmaf(h.z, wk[2 * NAMAX], q); q = fmaf(h.w, wk[3 * NAMAX], q);
         }
-        s.q[r * NAMAX + oo] = q0;
-        s.q[r * NAMAX + oo + 4] = q1;
+        t.q[r * NAMAX + o] = q;
     }
+    __syncwarp();
 }
 
 // ====================================================================================================================
@@ -246,24 +252,34 @@ template <int ENV> struct EnvCfg;
 template <> struct EnvCfg<ENV_CHECKERS> { using type = mm_checkers_cfg; };
 template <> struct EnvCfg<ENV_SWITCH> { using type = mm_switch_cfg; };
 
+// One warp = RE envs with BOTH agents: the warp runs agent 0's network on its RE rows, then agent 1's, then lanes
+// 0 .. 2 RE - 1 (lane = 2 env + agent) pick the actions and step the envs, and all lanes expand the next observations into
+// the warp's own operand tiles.  No block-level synchronisation inside the time loop.
+constexpr int RE = 2;         // envs per warp in the rollout kernel (the sequential env phase wants many warps per SM)
+constexpr int BTR = 512;      // its CTA size at most: 16 warps = 32 envs
+
 template <int ENV>
-__global__ void __launch_bounds__(2 * BT, 1)
+__global__ void __launch_bounds__(BTR, 1)
 toplevel_rollout_kernel(const __grid_constant__ RollArgs a, const __grid_constant__ typename EnvCfg<ENV>::type cfg) {
     extern __shared__ __align__(16) float smem[];
-    __shared__ uint32_t desc[RT][2][4];          // per (env, agent): what the observation is expanded from
-    const int tid = threadIdx.x, blk = tid >> 7, bt = tid & 127, lane = tid & 31, warp = tid >> 5;
+    __shared__ __align__(16) uint32_t desc_all[BTR / 32][RE][2][4];     // per (env, agent): what the observation is expanded from
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Dp = pad4(a.D);
-    const int per_block = block_smem_floats(Dp, 1);
-    const Blk s = carve(smem + blk * per_block, Dp, 1);
-    stage_weights(s, a.w[blk], a.D, Dp, a.NA, bt);
-    for (int i = bt; i < RT * Dp; i += BT) s.x0[i] = 0.f;
-    for (int i = bt; i < 2 * RT * HS; i += BT) s.h[i] = 0.f;
-    const int env0 = blockIdx.x * RT;
-    const int n_valid = min(RT, a.N - env0);
+    const int wf = weight_floats(Dp), tf_ = tile_floats(Dp, 1, RE);
+    stage_weights(smem, a.w[0], a.D, Dp, a.NA, tid, blockDim.x);
+    stage_weights(smem + wf, a.w[1], a.D, Dp, a.NA, tid, blockDim.x);
+    const Wts W0 = carve_weights(smem, Dp), W1 = carve_weights(smem + wf, Dp);
+    float* tiles = smem + 2 * wf + warp * 2 * tf_;
+    const Tile tl0 = carve_tile(tiles, Dp, 1, RE), tl1 = carve_tile(tiles + tf_, Dp, 1, RE);     // agent 1's tiles sit tf_ floats after agent 0's
+    for (int i = lane; i < 2 * tf_; i += 32) tiles[i] = 0.f;
+    uint32_t (*desc)[2][4] = desc_all[warp];
+    const int env0 = (blockIdx.x * (blockDim.x >> 5) + warp) * RE;
+    const int n_valid = max(0, min(RE, a.N - env0));
+    __syncthreads();
 
-    // env registers live in the first two warps: lane pair = the two agents of one env
-    const int el = tid >> 1, agent = tid & 1;
-    const bool env_lane = tid < 2 * RT;
+    // env registers: lane = 2 * env + agent for the first 2 * RPT lanes
+    const int el = (lane >> 1) & (RE - 1), agent = lane & 1;
+    const bool env_lane = lane < 2 * RE;
     ck::EnvRegs cs;
     ck::reset_regs(cs);
     uint32_t sw_cells = sw::init_cells(2), sw_done = 0, sw_step = 0;
@@ -275,21 +291,18 @@ toplevel_rollout_kernel(const __grid_constant__ RollArgs a, const __grid_constan
             const uint32_t mine = (cs.cells >> (8 * agent)) & 0xffu;
             const int r = mine >> 3, col = mine & 7;
             const uint64_t m = ck::neighbourhood_mask(cs.food, cs.cells, r, col);
-            desc[el][agent][0] = (uint32_t)m;
-            desc[el][agent][1] = (uint32_t)(m >> 32);
-            desc[el][agent][2] = __float_as_uint(c.pos_row[r]);
-            desc[el][agent][3] = __float_as_uint(c.pos_col[col]);
+            *reinterpret_cast<uint4*>(desc[el][agent]) =
+                make_uint4((uint32_t)m, (uint32_t)(m >> 32), __float_as_uint(c.pos_row[r]), __float_as_uint(c.pos_col[col]));
         } else {
             const mm_switch_cfg& c = cfg;
             const uint32_t cell = (sw_cells >> (8 * agent)) & 0xffu;
-            desc[el][agent][0] = __float_as_uint(c.pos_row[cell >> 3]);
-            desc[el][agent][1] = __float_as_uint(c.pos_col[cell & 7]);
-            desc[el][agent][2] = __float_as_uint(sw::clock_value(sw_step, c));
-            desc[el][agent][3] = 0;
+            *reinterpret_cast<uint4*>(desc[el][agent]) =
+                make_uint4(__float_as_uint(c.pos_row[cell >> 3]), __float_as_uint(c.pos_col[cell & 7]),
+                           __float_as_uint(sw::clock_value(sw_step, c)), 0u);
         }
     };
-    auto obs_value = [&](int row, int blk_agent, int d) -> float {
-        int src = blk_agent, dd = d;
+    auto obs_value = [&](int row, int tile_agent, int d) -> float {
+        int src = tile_agent, dd = d;
         if constexpr (ENV == ENV_CHECKERS) {
             if (a.full_obs) { src = d >= ck::kObs; dd = d - src * ck::kObs; }
             const uint32_t* q = desc[row][src];
@@ -300,38 +313,39 @@ toplevel_rollout_kernel(const __grid_constant__ RollArgs a, const __grid_constan
             return __uint_as_float(desc[row][src][dd]);
         }
     };
-    // expands the observation of every (row, agent) into the operand tiles and streams it to up to two global slots
+    // expands the observation of every (row, agent) of this warp into the operand tiles and streams it to up to two global slots
     auto expand = [&](float* g0, float* g1, int l0, int l1) {
 #pragma unroll 1
-        for (int rr = 0; rr < 8; ++rr) {
-            const int row = (warp & 3) * 8 + rr;
+        for (int ra = 0; ra < 2 * RE; ++ra) {
+            const int row = ra >> 1, ag = ra & 1;
             if (row >= n_valid) break;
             const long long e = env0 + row;
+            float* x0 = tl0.x0 + ag * tf_ + row * Dp;
             for (int d = lane; d < a.D; d += 32) {
-                const float v = obs_value(row, blk, d);
-                s.x0[row * Dp + d] = v;
-                if (g0) g0[((e * a.L + l0) * 2 + blk) * a.D + d] = v;
-                if (g1) g1[((e * a.L + l1) * 2 + blk) * a.D + d] = v;
+                const float v = obs_value(row, ag, d);
+                x0[d] = v;
+                if (g0) g0[((e * a.L + l0) * 2 + ag) * a.D + d] = v;
+                if (g1) g1[((e * a.L + l1) * 2 + ag) * a.D + d] = v;
             }
         }
     };
 
     if (env_lane) describe();
-    __syncthreads();
+    __syncwarp();
     expand(a.states, nullptr, 0, 0);
-    __syncthreads();
+    __syncwarp();
 
     int cur = 0;
     for (int t = 0; t < a.T; ++t) {
         const int c = t / a.L, l = t - c * a.L;
-        qnet_step<false>(s, s.x0, Dp, cur, bt, 1 + blk, nullptr, n_valid);
+        qnet_step_warp<false, RE>(W0, tl0, tl0.x0, Dp, cur, lane, nullptr, n_valid);
+        qnet_step_warp<false, RE>(W1, tl1, tl1.x0, Dp, cur, lane, nullptr, n_valid);
         cur ^= 1;
-        __syncthreads();
-        // ---- epsilon-greedy + env step (first two warps) -------------------------------------------------------------
-        if (warp < 2) {
+        // ---- epsilon-greedy + env step (lanes 0 .. 2 RPT - 1 hold the envs; every lane runs the shuffles) ------------------
+        {
             const int e = env0 + el;
-            const bool valid = el < n_valid;
-            const float* q = (agent ? s.q + per_block : s.q) + el * NAMAX;      // q tile of this lane's agent block
+            const bool valid = env_lane && el < n_valid;
+            const float* q = tl0.q + agent * tf_ + el * NAMAX;
             int act = 0;
             float best = q[0];
             for (int o = 1; o < a.NA; ++o)
@@ -371,16 +385,16 @@ toplevel_rollout_kernel(const __grid_constant__ RollArgs a, const __grid_constan
                     a.alive[(long long)t * a.N + e] = (uint8_t)was_alive;
                 }
             }
-            describe();
+            if (env_lane) describe();
         }
-        __syncthreads();
+        __syncwarp();
         {
             float* ns = a.next_states + (long long)c * a.N * a.L * 2 * a.D;
             const int t1 = t + 1, c1 = t1 / a.L, l1 = t1 - c1 * a.L;
             float* st = t1 < a.T ? a.states + (long long)c1 * a.N * a.L * 2 * a.D : nullptr;
             expand(ns, st, l, l1);
         }
-        __syncthreads();
+        __syncwarp();
     }
     if (env_lane && el < n_valid && agent == 0) {
         a.score[env0 + el] = score;
@@ -417,31 +431,36 @@ __device__ __forceinline__ void cp_async4(void* smem_ptr, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// grid (row tiles, agent); one warp = RPT rows of that agent, independent of the other warps after the weights are staged
 template <bool SAVE>
 __global__ void __launch_bounds__(BT, 2) qnet_seq_kernel(const __grid_constant__ SeqArgs a) {
     extern __shared__ __align__(16) float smem[];
-    __shared__ long long rows[RT];
-    const int bt = threadIdx.x, lane = bt & 31, warp = bt >> 5, agent = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, agent = blockIdx.y;
     const int Dp = pad4(a.D);
-    const Blk s = carve(smem, Dp, 2);
-    stage_weights(s, a.w[agent], a.D, Dp, a.NA, bt);
-    for (int i = bt; i < 2 * RT * Dp; i += BT) s.x0[i] = 0.f;
-    for (int i = bt; i < 2 * RT * HS; i += BT) s.h[i] = 0.f;
-    const int b0 = blockIdx.x * RT;
-    const int n_valid = min(RT, a.B - b0);
-    if (bt < RT) rows[bt] = bt < n_valid ? (a.row_index ? a.row_index[b0 + bt] : (long long)(b0 + bt)) : 0;
+    const int wf = weight_floats(Dp), tf_ = tile_floats(Dp, 2);
+    stage_weights(smem, a.w[agent], a.D, Dp, a.NA, tid, blockDim.x);
+    const Wts W = carve_weights(smem, Dp);
+    float* tiles = smem + wf + warp * tf_;
+    const Tile tl = carve_tile(tiles, Dp, 2);
+    for (int i = lane; i < tf_; i += 32) tiles[i] = 0.f;
+    const int b0 = (blockIdx.x * (blockDim.x >> 5) + warp) * RPT;
+    const int n_valid = max(0, min(RPT, a.B - b0));
+    long long rows[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) rows[i] = i < n_valid ? (a.row_index ? a.row_index[b0 + i] : (long long)(b0 + i)) : 0;
     __syncthreads();
+    if (n_valid == 0) return;
     const int T = a.C * a.L;
     auto fetch = [&](int t, int buf) {
         const int c = t / a.L, l = t - c * a.L;
         const float* base = a.obs + (long long)c * a.chunk_stride;
-        float* dst = s.x0 + buf * RT * Dp;
-#pragma unroll 1
-        for (int rr = 0; rr < 8; ++rr) {
-            const int row = warp * 8 + rr;
-            if (row >= n_valid) break;
-            const float* src = base + ((rows[row] * a.L + l) * 2 + agent) * a.D;
-            for (int d = lane; d < a.D; d += 32) cp_async4(dst + row * Dp + d, src + d);
+        float* dst = tl.x0 + buf * RPT * Dp;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            if (i < n_valid) {
+                const float* src = base + ((rows[i] * a.L + l) * 2 + agent) * a.D;
+                for (int d = lane; d < a.D; d += 32) cp_async4(dst + i * Dp + d, src + d);
+            }
         }
         cp_async_commit();
     };
@@ -450,29 +469,30 @@ __global__ void __launch_bounds__(BT, 2) qnet_seq_kernel(const __grid_constant__
     for (int t = 0; t < T; ++t) {
         const int c = t / a.L, l = t - c * a.L;
         cp_async_wait_all();
-        __syncthreads();
+        __syncwarp();
         if (t + 1 < T) fetch(t + 1, (t + 1) & 1);
         float* sv = SAVE ? a.save + (((long long)agent * T + t) * a.B + b0) * SV : nullptr;
-        qnet_step<SAVE>(s, s.x0 + (t & 1) * RT * Dp, Dp, cur, bt, 1, sv, n_valid);
+        qnet_step_warp<SAVE, RPT>(W, tl, tl.x0 + (t & 1) * RPT * Dp, Dp, cur, lane, sv, n_valid);
         cur ^= 1;
-        __syncthreads();
-        // q tile -> global; hidden reset where the recorded step was terminal
-        for (int i = bt; i < n_valid * a.NA; i += BT) {
-            const int row = i / a.NA, o = i - row * a.NA;
-            a.q_out[((((long long)c * a.B + b0 + row) * a.L + l) * 2 + agent) * a.NA + o] = s.q[row * NAMAX + o];
-        }
-        if (a.reset_on_done) {
-            float* hc = s.h + cur * RT * HS;
-            const int row = bt >> 2;
+        // q tile -> global (lane = (row, output)); hidden reset where the recorded step was terminal
+        {
+            const int row = lane >> 3, o = lane & 7;
             if (row < n_valid) {
-                const float d = a.dones[(long long)c * a.done_chunk_stride + rows[row] * a.L + l];
-                if (d != 0.f) {
-                    const float keep = 1.0f - d;
+                long long srow = rows[0];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) hc[row * HS + (bt & 3) * 8 + k] *= keep;
+                for (int i = 1; i < RPT; ++i) srow = row == i ? rows[i] : srow;
+                if (o < a.NA) a.q_out[((((long long)c * a.B + b0 + row) * a.L + l) * 2 + agent) * a.NA + o] = tl.q[row * NAMAX + o];
+                if (a.reset_on_done) {
+                    const float d = a.dones[(long long)c * a.done_chunk_stride + srow * a.L + l];
+                    if (d != 0.f) {
+                        float* hc = tl.h + cur * RPT * HS + row * HS + o * 4;
+                        const float keep = 1.0f - d;
+                        hc[0] *= keep; hc[1] *= keep; hc[2] *= keep; hc[3] *= keep;
+                    }
                 }
             }
         }
+        __syncwarp();
     }
 }
 
@@ -494,7 +514,7 @@ __host__ __device__ inline int param_count(int D, int NA) {
     return F1 * D + F1 + F2 * F1 + F2 + 3 * HH * F2 + 3 * HH * HH + 3 * HH + 3 * HH + NA * HH + NA;
 }
 
-__global__ void __launch_bounds__(BT, 2) qnet_bwd_kernel(const __grid_constant__ BwdArgs a) {
+__global__ void __launch_bounds__(BTB, 2) qnet_bwd_kernel(const __grid_constant__ BwdArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ long long rows[RT];
     const int bt = threadIdx.x, lane = bt & 31, warp = bt >> 5, agent = blockIdx.y;
@@ -516,11 +536,11 @@ __global__ void __launch_bounds__(BT, 2) qnet_bwd_kernel(const __grid_constant__
     float* DQ = A1 + RT * F1;               // [RT][NAMAX]
     float* HN = DQ + RT * NAMAX;            // [RT][HS]   output state of this step (head input)
     const QNetP& w = a.w[agent];
-    for (int i = bt; i < F2 * F1; i += BT) W2[i] = w.w2[i];
-    for (int i = bt; i < 3 * HH * F2; i += BT) { Wih[i] = w.wih[i]; Whh[i] = w.whh[i]; }
-    for (int i = bt; i < NAMAX * HH; i += BT) Wo[i] = i < a.NA * HH ? w.wo[i] : 0.f;
-    for (int i = bt; i < RT * (Dp + F1 + F2 + HS); i += BT) X0[i] = 0.f;       // X0, X1, X2, HP: rows past the batch stay zero
-    for (int i = bt; i < RT * HS; i += BT) HN[i] = 0.f;
+    for (int i = bt; i < F2 * F1; i += BTB) W2[i] = w.w2[i];
+    for (int i = bt; i < 3 * HH * F2; i += BTB) { Wih[i] = w.wih[i]; Whh[i] = w.whh[i]; }
+    for (int i = bt; i < NAMAX * HH; i += BTB) Wo[i] = i < a.NA * HH ? w.wo[i] : 0.f;
+    for (int i = bt; i < RT * (Dp + F1 + F2 + HS); i += BTB) X0[i] = 0.f;       // X0, X1, X2, HP: rows past the batch stay zero
+    for (int i = bt; i < RT * HS; i += BTB) HN[i] = 0.f;
     const int b0 = blockIdx.x * RT;
     const int n_valid = min(RT, a.B - b0);
     if (bt < RT) rows[bt] = bt < n_valid ? (a.row_index ? a.row_index[b0 + bt] : (long long)(b0 + bt)) : 0;
@@ -556,11 +576,11 @@ __global__ void __launch_bounds__(BT, 2) qnet_bwd_kernel(const __grid_constant__
         const float* sv = a.save + (((long long)agent * a.L + l) * a.B + b0) * SV;
         const float* svp = l > 0 ? a.save + (((long long)agent * a.L + l - 1) * a.B + b0) * SV : nullptr;
         // ---- tiles of this step -------------------------------------------------------------------------------------
-        for (int i = bt; i < n_valid * (F1 / 4); i += BT) {
+        for (int i = bt; i < n_valid * (F1 / 4); i += BTB) {
             const int row = i >> 4, q4 = i & 15;
             *reinterpret_cast<float4*>(X1 + row * F1 + 4 * q4) = *reinterpret_cast<const float4*>(sv + row * SV + 4 * q4);
         }
-        for (int i = bt; i < n_valid * (F2 / 4); i += BT) {
+        for (int i = bt; i < n_valid * (F2 / 4); i += BTB) {
             const int row = i >> 3, q4 = i & 7;
             *reinterpret_cast<float4*>(X2 + row * F2 + 4 * q4) = *reinterpret_cast<const float4*>(sv + row * SV + 64 + 4 * q4);
             *reinterpret_cast<float4*>(HN + row * HS + 4 * q4) = *reinterpret_cast<const float4*>(sv + row * SV + 224 + 4 * q4);
@@ -581,7 +601,7 @@ __global__ void __launch_bounds__(BT, 2) qnet_bwd_kernel(const __grid_constant__
             const float* src = a.obs + ((rows[row] * a.L + l) * 2 + agent) * a.D;
             for (int d = lane; d < a.D; d += 32) X0[row * Dp + d] = src[d];
         }
-        for (int i = bt; i < RT * NAMAX; i += BT) {
+        for (int i = bt; i < RT * NAMAX; i += BTB) {
             const int row = i >> 3, o = i & 7;
             DQ[i] = (row < n_valid && o < a.NA) ? a.dq[(((long long)(b0 + row) * a.L + l) * 2 + agent) * a.NA + o] : 0.f;
         }
@@ -846,6 +866,19 @@ __global__ void vdn_chunk_loss_kernel(const float* __restrict__ q_beh, const flo
     if (l == L - 1) td_last[b] = fabsf(diff);
 }
 
+// warps per CTA (RPT rows each): the full 8 when there is more than one wave of work, otherwise the smallest CTA that still
+// gives every SM slot one -- the kernels are sequential over time, so an idle SM is lost for the whole launch
+int warps_per_cta(int n_rows, int ctas_per_sm, int grid_y, int rows_per_warp = RPT, int max_warps = BT / 32) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int slots = sms * ctas_per_sm / grid_y;
+    if (slots < 1) slots = 1;
+    const int rows = (n_rows + slots - 1) / slots;
+    const int w = (rows + rows_per_warp - 1) / rows_per_warp;
+    return w < 1 ? 1 : (w > max_warps ? max_warps : w);
+}
+
 int check_dims(int D, int NA) {
     if (D < 1 || D > kMaxD || NA < 1 || NA > NAMAX) return MM_ERR_UNSUPPORTED;
     return MM_OK;
@@ -880,9 +913,10 @@ extern "C" int mm_toplevel_rollout(const float* const* params_host, int32_t env_
     a.N = N; a.T = T; a.L = L; a.D = D; a.NA = NA; a.eps = eps;
     a.seed = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)); a.step_offset = step_offset;
     const int Dp = pad4(D);
-    const size_t smem = (size_t)2 * block_smem_floats(Dp, 1) * sizeof(float);
+    const int warps = warps_per_cta(N, 1, 1, RE, BTR / 32);
+    const size_t smem = sizeof(float) * (size_t)(2 * weight_floats(Dp) + warps * 2 * tile_floats(Dp, 1, RE));
     if (smem > 227 * 1024) return MM_ERR_UNSUPPORTED;
-    const int grid = (N + RT - 1) / RT;
+    const int grid = (N + warps * RE - 1) / (warps * RE);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (env_kind == ENV_CHECKERS) {
@@ -891,13 +925,13 @@ extern "C" int mm_toplevel_rollout(const float* const* params_host, int32_t env_
         if (D != (a.full_obs ? 2 : 1) * MM_CHECKERS_OBS_DIM || cfg->auto_reset) return MM_ERR_UNSUPPORTED;
         e = cudaFuncSetAttribute(toplevel_rollout_kernel<ENV_CHECKERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
-        toplevel_rollout_kernel<ENV_CHECKERS><<<grid, 2 * BT, smem, st>>>(a, *cfg);
+        toplevel_rollout_kernel<ENV_CHECKERS><<<grid, 32 * warps, smem, st>>>(a, *cfg);
     } else if (env_kind == ENV_SWITCH) {
         const mm_switch_cfg* cfg = static_cast<const mm_switch_cfg*>(env_cfg_host);
         if (cfg->n_agents != 2 || cfg->full_observable || D != 2 + (cfg->clock ? 1 : 0)) return MM_ERR_UNSUPPORTED;
         e = cudaFuncSetAttribute(toplevel_rollout_kernel<ENV_SWITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
-        toplevel_rollout_kernel<ENV_SWITCH><<<grid, 2 * BT, smem, st>>>(a, *cfg);
+        toplevel_rollout_kernel<ENV_SWITCH><<<grid, 32 * warps, smem, st>>>(a, *cfg);
     } else {
         return MM_ERR_BAD_ARG;
     }
@@ -916,18 +950,21 @@ extern "C" int mm_toplevel_qnet_seq(const float* const* params_host, const float
     a.obs = obs; a.row_index = reinterpret_cast<const long long*>(row_index); a.chunk_stride = chunk_stride;
     a.dones = dones; a.done_chunk_stride = done_chunk_stride; a.reset_on_done = reset_on_done;
     a.q_out = q_out; a.save = save; a.B = B; a.L = L; a.C = C; a.D = D; a.NA = NA;
-    const size_t smem = (size_t)block_smem_floats(pad4(D), 2) * sizeof(float);
-    const dim3 grid((B + RT - 1) / RT, 2);
+    const int Dp = pad4(D);
+    const int per_sm = (sizeof(float) * (size_t)(weight_floats(Dp) + (BT / 32) * tile_floats(Dp, 2))) > 113 * 1024 ? 1 : 2;
+    const int warps = warps_per_cta(B, per_sm, 2);
+    const size_t smem = sizeof(float) * (size_t)(weight_floats(Dp) + warps * tile_floats(Dp, 2));
+    const dim3 grid((B + warps * RPT - 1) / (warps * RPT), 2);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (save) {
         e = cudaFuncSetAttribute(qnet_seq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
-        qnet_seq_kernel<true><<<grid, BT, smem, st>>>(a);
+        qnet_seq_kernel<true><<<grid, 32 * warps, smem, st>>>(a);
     } else {
         e = cudaFuncSetAttribute(qnet_seq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
-        qnet_seq_kernel<false><<<grid, BT, smem, st>>>(a);
+        qnet_seq_kernel<false><<<grid, 32 * warps, smem, st>>>(a);
     }
     return mm::check_launch();
 }
@@ -949,7 +986,7 @@ extern "C" int mm_toplevel_qnet_bwd(const float* const* params_host, float* cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaFuncSetAttribute(qnet_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
-    qnet_bwd_kernel<<<grid, BT, smem, st>>>(a);
+    qnet_bwd_kernel<<<grid, BTB, smem, st>>>(a);
     if (int rc = mm::check_launch()) return rc;
     ReduceArgs r{};
     r.partials = partials; r.n_tiles = grid.x; r.P = param_count(D, NA); r.D = D; r.NA = NA; r.accumulate = accumulate;

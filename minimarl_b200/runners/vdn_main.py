@@ -105,9 +105,8 @@ def _fused_episode(beh, tgt, env, per, args, epsilon, seed, step_offset, bufs):
     Cn, N = T // L, env.n_envs
     q_tgt = tf.qnet_seq(tgt, out["next_states"], N, L, C_=Cn)                 # target state carried through the episode
     td_sum, valid = tf.td_chunks(q_tgt, out["rewards"], out["dones"], out["behv"], out["alive"], args.gamma)
-    for c in range(Cn):                                                        # chunk order = the reference's add order
-        per.collect_samples_batch([out["states"][c], out["actions"][c], out["rewards"][c], out["next_states"][c],
-                                   out["dones"][c]], td_sum[c], warm_up=False, valid=valid[c])
+    # chunk c of every env goes in as one set, c = 0..C-1 (the reference's add order), all from one library call
+    per.collect_episode([out["states"], out["actions"], out["rewards"], out["next_states"], out["dones"]], td_sum, valid)
     return out, T * N
 
 
