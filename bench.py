@@ -14,8 +14,9 @@ Workloads (per GPU):
                            configuration the agent-steps/sec metric and its roofline are quoted on)
   qmix_rollout_4096x100    BASELINE.json configs[1]: 4 096 envs x T=100 (episode written to replay slots)
 
-Prints ONE JSON line (rank 0).  Besides the contract keys it carries: `roofline` / `roofline_gae` (CUDA-event kernel times
-inside the timed region against MEASURED_PEAKS.json), `e2e` (the same rollout for a caller holding HOST arrays:
+Prints ONE JSON line (rank 0).  Besides the contract keys it carries: `roofline` (CUDA-event kernel times inside the timed
+region against MEASURED_PEAKS.json; sub-objects `gae`, `learner`, `mappo_iteration`, `qmix_toplevel` hold the rooflines of the
+other kernels), a compact `summary` as the LAST key (QMIX train samples/sec, ms per update, MAPPO iteration split ...), `e2e` (the same rollout for a caller holding HOST arrays:
 BatchedCheckers.rollout_host, H2D / kernels / D2H pipelined in mm_checkers_rollout_host, wall clock), `cpu_baseline`,
 `clocks` (a separate NVML sampling process), and the sections `policy_rollout`, `learner` (QMIX train samples/sec),
 `mappo_iteration`, `env_switch2`, `qmix_toplevel` (skipped with --no-learner).  `--impl reference` times the CPU restatement
@@ -37,9 +38,13 @@ WORKLOADS = {
     "qmix_rollout_4096x100": dict(n_envs=4096, T=100, full_observable=False, max_steps=100),
 }
 AGENTS = 2
-# algorithmic bytes per env-step (D=47): actions 8 + state 40 r + 40 w + obs 376 + rew 8 + done 2
-ENV_STEP_BYTES = 474
+# algorithmic bytes per env-step (D=47): actions 8 + state 40 r + 40 w + obs 376 + rew 8 + done 2 = 474.
+# The T-step kernel keeps the env state in registers (24 B per env per LAUNCH), so the bytes it must move per env-step are
+# actions 8 + obs 376 + rewards 8 + dones 2 = 394: `roofline.frac` is quoted on those, the survey figure is reported beside it.
+ENV_STEP_BYTES_SURVEY = 474
+ENV_STEP_BYTES = 394
 GAE_BYTES_PER_ELEM = 16
+FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # fp32 FFMA peak of one B200 at clocks.max.sm
 METRIC = "agent-steps/sec batched env rollout"
 UNIT = "agent-steps/s"
 
@@ -50,6 +55,15 @@ def measured_peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
+
+
+def tf32_peak_tflops():
+    """Dense TF32 tensor peak = half the MEASURED sustained bf16 figure (MEASURED_PEAKS.json has no TF32 entry)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["bf16_tflops_sustained"]) / 2, "measured bf16 sustained / 2"
+    return 1400.0 / 2, "fallback bf16 sustained / 2"
 
 
 _SAMPLER_CHILD = r"""
@@ -278,7 +292,9 @@ def policy_rollout_section(dev, steps):
 def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
     """BASELINE configs[2] / [4]: one full MAPPO iteration -- fused policy + env rollout of n_envs x T steps into the device
     SharedReplayBuffer, bootstrap value + GAE, and R_MAPPO.train (ppo_epoch 15, one minibatch of all data chunks of
-    length 8, recurrent actor / critic of hidden size 32: the defaults of mappo/_config.py).  Runs on every rank (env
+    length 8, recurrent actor / critic of hidden size 32: the defaults of mappo/_config.py:204-336 -- lr 1e-4, value_loss_coef 0.5,
+    max_grad_norm 0.5, clip 0.2, entropy 0.01, huber 10 -- except data_chunk_length 8 instead of 5, which does not divide
+    T = 128: SURVEY.md 8a row a9).  Runs on every rank (env
     shard per GPU); the PPO update all-reduces its gradients over NCCL when world > 1."""
     import argparse as ap
     import torch
@@ -293,8 +309,8 @@ def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
         gain=0.01, use_conv1d=False, use_recurrent_policy=True, use_naive_recurrent_policy=False,
         use_policy_active_masks=True, use_value_active_masks=True, use_popart=False, use_valuenorm=True,
         use_huber_loss=True, use_max_grad_norm=True, use_clipped_value_loss=True, use_gae=True, ppo_epoch=15,
-        train_batch_size=1, data_chunk_length=8, clip_param=0.2, entropy_coef=0.01, value_loss_coef=1.0,
-        max_grad_norm=10.0, huber_delta=10.0, actor_lr=5e-4, critic_lr=5e-4, opti_eps=1e-5, weight_decay=0, gamma=0.99,
+        train_batch_size=1, data_chunk_length=8, clip_param=0.2, entropy_coef=0.01, value_loss_coef=0.5,
+        max_grad_norm=0.5, huber_delta=10.0, actor_lr=1e-4, critic_lr=1e-4, opti_eps=1e-5, weight_decay=0, gamma=0.99,
         gae_lambda=0.95, max_step=T, batch_size=n_envs, fused_precision="tf32", max_episodes=1000, use_eval=False,
         eval_interval=10, use_linear_lr_decay=False, seed=1)
     env = BatchedCheckers(n_envs, max_steps=100, auto_reset=True, device=dev)
@@ -331,6 +347,12 @@ def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
         "train_info": {k: float(v) for k, v in infos.items()},
         "peak_mem_GiB": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
     }
+    # useful math of the update: (17.7 + 17.4) kFLOP per row forward, x3 with the backward, all rows, all epochs
+    flops = n_envs * T * AGENTS * (17.7e3 + 17.4e3) * 3 * args.ppo_epoch
+    peak_tc, peak_src = tf32_peak_tflops()
+    out["roofline"] = {"bound": "tensor", "kernel": "ppo_trunk_kernel<fwd/bwd>", "achieved": flops / (ms[2] * 1e-3) / 1e12,
+                       "peak": peak_tc, "peak_source": peak_src, "unit": "TFLOP/s", "frac": flops / (ms[2] * 1e-3) / 1e12 / peak_tc,
+                       "useful_flop_per_update": flops}
     del r, env
     torch.cuda.empty_cache()
     return out
@@ -368,10 +390,11 @@ def switch_rollout_section(dev, steps=10):
 
 def qmix_toplevel_section(dev, episodes=3, n_envs=4096):
     """BASELINE configs[1]: the qmix/main.py loop on 4 096 lockstep Switch2-v0 envs (the qmix/_config.py default env) with
-    the chunk replay on the GPU: Q_Net.sample_action -> lockstep env kernel -> target Q_Net -> cal_td_error per step,
-    4 096 chunk inserts per 10 steps in one mm_heaptree_add_batch launch, then Train_dqn.train (update_iter 10, recurrent
-    Mix_Net on both sides).  qmix/_config.py defaults except buffer_limit (1 000 -> 8 192 chunks) and batch_size
-    (32 -> 4 096 chunks), scaled with the env count.  The per-agent networks are PyTorch modules (cuBLAS)."""
+    the chunk replay on the GPU, on the fused kernels (csrc/toplevel_qnet.cu, toplevel_mix.cu): mm_toplevel_rollout plays
+    the episode (behaviour Q_Net, one epsilon draw per env, Switch2 step), mm_toplevel_qnet_seq runs the target network,
+    mm_toplevel_td sums cal_td_error per chunk, the chunks of live envs enter the PER as sets, then Train_dqn.train
+    (update_iter 10, recurrent Mix_Net on both sides) as fused forward / BPTT kernels.  qmix/_config.py defaults except
+    buffer_limit (1 000 -> 8 192 chunks) and batch_size (32 -> 4 096 chunks), scaled with the env count."""
     import argparse as ap
     import torch
     from minimarl_b200.runners import run_qmix
@@ -389,14 +412,23 @@ def qmix_toplevel_section(dev, episodes=3, n_envs=4096):
     train_s = statistics.median(timing["train_s_per_episode"][1:])
     steps_per_episode = timing["env_steps"] / (episodes + 1) / n_envs
     samples = args.update_iter * batch * args.chunk_size
+    # useful math per agent-step (D = 3): behaviour + target Q_Net, 8 544 MACs each (fp32 FFMA kernels); per sample of the
+    # update: both agents, behaviour fwd + 2x bwd + target fwd, plus the recurrent mixer (~8.8 k MACs, same four passes)
+    roll_flops = steps_per_episode * n_envs * 2 * 2 * 2 * 8544
+    train_flops = samples * (2 * 4 * 2 * 8544 + 4 * 2 * 8800)
     return {"metric": "qmix/main.py loop, 4 096 lockstep Switch2-v0 envs, chunk replay on the GPU",
+            "fused": bool(timing.get("fused")),
+            "roofline": {"bound": "fp32 ffma", "peak": FFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "rollout_achieved": roll_flops / roll_s / 1e12, "rollout_frac": roll_flops / roll_s / 1e12 / FFMA_PEAK_TFLOPS,
+                         "train_achieved": train_flops / train_s / 1e12, "train_frac": train_flops / train_s / 1e12 / FFMA_PEAK_TFLOPS},
             "rollout_agent_steps_per_s": steps_per_episode * n_envs * 2 / roll_s,
             "rollout_ms_per_env_step_all_envs": roll_s * 1e3 / steps_per_episode,
             "train_samples_per_s": samples / train_s, "train_ms_per_call": train_s * 1e3,
             "first_episode_with_graph_capture_ms": {"rollout": timing["rollout_s_per_episode"][0] * 1e3,
                                                      "train": timing["train_s_per_episode"][0] * 1e3},
             "episodes": episodes, "chunk_inserts_per_episode": n_envs * args.max_step // args.chunk_size,
-            "cuda_graphs": "one graph per 10-step rollout chunk, one graph per training iteration",
+            "launches": "rollout: one launch per episode (policy + eps-greedy + env), one target pass, one PER insert call; "
+                        "training iteration replayed as a CUDA graph",
             "config": {"n_envs": n_envs, "env": "Switch2-v0", "buffer_limit_chunks": args.buffer_limit,
                        "batch_chunks": batch, "chunk_size": args.chunk_size, "update_iter": args.update_iter},
             "train_loss": history[-1]["train_loss"], "train_score": history[-1]["train_score"]}
@@ -503,7 +535,20 @@ def learner_section(dev, steps):
         "agentq_forward_fp32": {"ms": ms_agent, "TFLOPs": rows * 64000 / (ms_agent * 1e-3) / 1e12,
                                 "note": "fused FFMA kernel, the 1e-5 parity path"},
         "mixer_forward": {"ms": ms_mixer, "rows": T * B, "TFLOPs": T * B * 54528 / (ms_mixer * 1e-3) / 1e12},
+        "roofline": _learner_roofline(ms_update, rows, T * B, ms_gather, gather_bytes, peak),
     }
+
+
+def _learner_roofline(ms_update, agent_rows, mixer_rows, ms_gather, gather_bytes, hbm_peak):
+    """Useful math of one update: agent net 64 kFLOP per (row, step) x (live fwd + 2x bwd + target fwd), mixer
+    54.5 kFLOP per (t, b) x the same four passes; against the TF32 tensor peak.  HBM side: the replay gather."""
+    flops = agent_rows * 64000 * 4 + mixer_rows * 54528 * 4
+    peak_tc, peak_src = tf32_peak_tflops()
+    return {"bound": "tensor", "kernel": "train_policy_on_batch (all kernels of one update)", "achieved": flops / (ms_update * 1e-3) / 1e12,
+            "peak": peak_tc, "peak_source": peak_src, "unit": "TFLOP/s", "frac": flops / (ms_update * 1e-3) / 1e12 / peak_tc,
+            "useful_flop_per_update": flops,
+            "hbm_gather": {"achieved": gather_bytes / (ms_gather * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": gather_bytes / (ms_gather * 1e-3) / 1e9 / hbm_peak}}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -678,6 +723,7 @@ def run_ours(args, wl):
     if rank == 0:
         peak, peak_kind = measured_peaks()
         achieved = n * T * ENV_STEP_BYTES / (rollout_ms * 1e-3) / 1e9
+        achieved_survey = n * T * ENV_STEP_BYTES_SURVEY / (rollout_ms * 1e-3) / 1e9
         gae_achieved = n * T * A * (GAE_BYTES_PER_ELEM + 4) / (gae_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -700,10 +746,13 @@ def run_ours(args, wl):
                        "host_cores_local_to_gpu": numa},
             "roofline": {"bound": "hbm", "kernel": "checkers_rollout_kernel", "achieved": achieved, "peak": peak,
                          "peak_source": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": n * T * ENV_STEP_BYTES, "kernel_ms": rollout_ms},
-            "roofline_gae": {"bound": "hbm", "kernel": "gae_kernel", "achieved": gae_achieved, "peak": peak,
-                             "unit": "GB/s", "frac": gae_achieved / peak, "kernel_ms": gae_ms,
-                             "algorithmic_bytes_per_launch": n * T * A * (GAE_BYTES_PER_ELEM + 4)},
+                         "algorithmic_bytes_per_launch": n * T * ENV_STEP_BYTES, "kernel_ms": rollout_ms,
+                         "formula": "394 B per env-step (actions 8 + obs 376 + rewards 8 + dones 2; the env state stays in "
+                                    "registers for the T steps) x n_envs x T / kernel time / measured HBM copy peak",
+                         "frac_survey_474B": achieved_survey / peak,
+                         "gae": {"kernel": "gae_tile_kernel", "achieved": gae_achieved, "peak": peak, "unit": "GB/s",
+                                 "frac": gae_achieved / peak, "kernel_ms": gae_ms,
+                                 "algorithmic_bytes_per_launch": n * T * A * (GAE_BYTES_PER_ELEM + 4)}},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": "port", "sample": cpu_sample,
                              "host_cores": cores, "c_port_1core": cpu_c},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
@@ -718,20 +767,42 @@ def run_ours(args, wl):
             "clocks": clocks,
         }
         if not args.no_learner:
-            try:
-                line["policy_rollout"] = policy_rollout_section(dev, args.learner_steps)
-            except Exception as e:
-                line["policy_rollout"] = {"error": f"{type(e).__name__}: {e}"}
+            sections = {}
+            for name, fn in (("policy_rollout", lambda: policy_rollout_section(dev, args.learner_steps)),
+                             ("env_switch2", lambda: switch_rollout_section(dev)),
+                             ("qmix_toplevel", lambda: qmix_toplevel_section(dev))):
+                try:
+                    sections[name] = fn()
+                except Exception as e:
+                    sections[name] = {"error": f"{type(e).__name__}: {e}"}
+            line["policy_rollout"] = sections["policy_rollout"]
+            line["env_switch2"] = sections["env_switch2"]
             line["learner"] = learner
             line["mappo_iteration"] = mappo_it
-            try:
-                line["env_switch2"] = switch_rollout_section(dev)
-            except Exception as e:
-                line["env_switch2"] = {"error": f"{type(e).__name__}: {e}"}
-            try:
-                line["qmix_toplevel"] = qmix_toplevel_section(dev)
-            except Exception as e:
-                line["qmix_toplevel"] = {"error": f"{type(e).__name__}: {e}"}
+            line["qmix_toplevel"] = sections["qmix_toplevel"]
+            # The second half of the BASELINE metric and the other configs, compact, where the driver's record keeps them:
+            # inside `roofline` (kept whole) and as the LAST key of the line (the driver's stdout tail).
+            g = lambda d, *ks: (d or {}).get(ks[0]) if len(ks) == 1 else g((d or {}).get(ks[0]), *ks[1:])
+            summary = {
+                "qmix_train_samples_per_s": g(learner, "value"), "qmix_ms_per_update": g(learner, "ms_per_update"),
+                "qmix_update_tflops_frac_of_tf32_peak": g(learner, "roofline", "frac"),
+                "qmix_gather_frac_of_hbm": g(learner, "roofline", "hbm_gather", "frac"),
+                "mappo_iteration_ms": g(mappo_it, "ms_per_iteration"), "mappo_ms_rollout": g(mappo_it, "ms_rollout"),
+                "mappo_ms_ppo_update": g(mappo_it, "ms_ppo_update"), "mappo_agent_steps_per_s": g(mappo_it, "value"),
+                "mappo_update_tflops_frac_of_tf32_peak": g(mappo_it, "roofline", "frac"),
+                "toplevel_qmix_rollout_agent_steps_per_s": g(sections["qmix_toplevel"], "rollout_agent_steps_per_s"),
+                "toplevel_qmix_train_samples_per_s": g(sections["qmix_toplevel"], "train_samples_per_s"),
+                "toplevel_qmix_train_ms_per_call": g(sections["qmix_toplevel"], "train_ms_per_call"),
+                "policy_rollout_4096_agent_steps_per_s": g(sections["policy_rollout"], "n_envs_4096", "agent_steps_per_s"),
+                "env_frac_of_hbm_394B": achieved / peak, "gae_frac_of_hbm": gae_achieved / peak,
+                "e2e_agent_steps_per_s": e2e_value,
+            }
+            line["roofline"]["learner"] = g(learner, "roofline")
+            line["roofline"]["mappo_iteration"] = g(mappo_it, "roofline")
+            line["roofline"]["qmix_toplevel"] = g(sections["qmix_toplevel"], "roofline")
+            line["e2e"]["learner_ms_per_update"] = g(learner, "ms_per_update")
+            line["e2e"]["learner_samples_per_s"] = g(learner, "value")
+            line["summary"] = summary
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

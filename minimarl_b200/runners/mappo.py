@@ -112,12 +112,16 @@ class MAGYM_Runner:
         self.train_infos.append(infos)
         return infos
 
-    def run(self, episodes=None):
+    def run(self, episodes=None, sink=None):
+        """``sink``: a ``MetricSink``; gets ``train_infos`` (+ ``Test_Rewards``) per iteration like the reference's
+        ``wandb.log(train_infos)`` (mappo/runner/shared/magym_runner.py:100-105), device tensors copied in one go."""
         self.warmup()
         for episode in range(self.max_episodes if episodes is None else episodes):
             infos = self.run_episode(episode)
             if self.use_eval and episode % self.eval_interval == 0:
                 infos["Test_Rewards"] = self.eval()
+            if sink is not None:
+                sink.log(infos, step=episode)
         return self.train_infos
 
     @torch.no_grad()

@@ -121,7 +121,15 @@ class MAGYM_Runner:
         return self.eval_reward
 
     def log(self):
-        self.last_log = {"total_env_steps": self.total_env_steps, "episodes": self.num_episodes_collected,
-                         "average_episode_rewards": float(self.env_infos.get("average_episode_rewards", float("nan"))),
-                         **({k: float(v) for k, v in self.train_infos[-1].items()} if self.train_infos else {})}
+        """base_runner.py:308-331 (log_env / log_train): one record per call; with ``self.sink`` (a ``MetricSink``) it goes to
+        logging / wandb with ``step=total_env_steps`` and the tensors cross to the host in one copy."""
+        from ..utils.sinks import MetricSink
+        rec = {"total_env_steps": self.total_env_steps, "episodes": self.num_episodes_collected,
+               "average_episode_rewards": self.env_infos.get("average_episode_rewards", float("nan")),
+               **({"policy_0/" + k: v for k, v in self.train_infos[-1].items()} if self.train_infos else {})}
+        sink = getattr(self, "sink", None)
+        self.last_log = (sink.log(rec, step=self.total_env_steps, force=True) if sink is not None else None) or MetricSink.to_host(rec)
+        for k in list(self.last_log):                        # keep the un-prefixed spellings older callers read
+            if k.startswith("policy_0/"):
+                self.last_log[k[len("policy_0/"):]] = self.last_log[k]
         return self.last_log

@@ -26,6 +26,7 @@ import torch
 from ..algorithms import toplevel_fused as tf
 from ..algorithms.toplevel import Mix_Net, Prioritized_Experience_Replay, Q_Net, Target_Dqn, Train_dqn, cal_td_error
 from ..envs.batched import BatchedCheckers, BatchedSwitch
+from ..utils.sinks import MetricSink, test_line, vdn_line
 
 
 class _ChunkGraph:
@@ -110,7 +111,7 @@ def _fused_episode(beh, tgt, env, per, args, epsilon, seed, step_offset, bufs):
     return out, T * N
 
 
-def _run(args, env, episodes, mixer, log, timing):
+def _run(args, env, episodes, mixer, log, timing, sink=None, test=None):
     dev, n_envs = env.device, env.n_envs
     beh = Q_Net(env.observation_space, env.action_space, args).to(dev)
     tgt = Q_Net(env.observation_space, env.action_space, args).to(dev)
@@ -209,27 +210,45 @@ def _run(args, env, episodes, mixer, log, timing):
         if timing is not None:
             torch.cuda.synchronize(dev)
             t_train.append(time.perf_counter() - t1)
-        rec = {"episode": episode, "train_score": score.mean().item(), "train_loss": float(loss), "eps": epsilon,
+        # device values stay tensors; the sink (or the history below) brings them over in one copy
+        rec = {"episode": episode, "train_score": score.mean(), "train_loss": loss, "eps": epsilon,
                "alpha": per.alpha, "beta": per.beta}
+        if sink is not None:
+            sink.log(rec, step=episode, line=vdn_line(args.max_episodes))
+        rec = MetricSink.to_host(rec)
         history.append(rec)
         if log:
             log(rec)
+        if test is not None and (episode + 1) % args.test_interval == 0:           # vdn/main.py:185-190
+            t_score, t_loss = test.execute(beh, tgt)
+            history[-1].update({"test-score": t_score, "test-loss": t_loss})
+            if sink is not None:
+                sink.log({"test-score": t_score, "test-loss": t_loss}, step=episode, line=test_line, force=True)
     if timing is not None:
         timing.update(rollout_s=sum(t_roll), train_s=sum(t_train), rollout_s_per_episode=t_roll, train_s_per_episode=t_train,
                       env_steps=env_steps, chunks_in_buffer=per.sum_tree.n_data, fused=fused)
     return history, beh
 
 
-def run_vdn(args, n_envs, episodes, device="cuda", log=None, timing=None):
-    env = BatchedCheckers(n_envs, full_observable=True, max_steps=args.max_step, step_cost=args.step_cost,
-                          device=torch.device(device))
-    return _run(args, env, episodes, False, log, timing)
+def _test_module(args, env_factory, dev):
+    """``Test`` (vdn/_test.py) on its own lockstep boards when the config asks for periodic evaluation."""
+    if not getattr(args, "test_interval", 0) or not getattr(args, "test_episodes", 0):
+        return None
+    from ..algorithms.toplevel import Test
+    return Test(env_factory(int(args.test_episodes)), args, dev)
 
 
-def run_qmix(args, n_envs, episodes, device="cuda", log=None, timing=None, env_id="Switch2-v0"):
+def run_vdn(args, n_envs, episodes, device="cuda", log=None, timing=None, sink=None):
+    """vdn/main.py on ``n_envs`` lockstep boards.  ``sink``: a ``MetricSink`` (logging / wandb lines of vdn/main.py:180-196)."""
+    dev = torch.device(device)
+    make = lambda n: BatchedCheckers(n, full_observable=True, max_steps=args.max_step, step_cost=args.step_cost, device=dev)
+    return _run(args, make(n_envs), episodes, False, log, timing, sink, _test_module(args, make, dev))
+
+
+def run_qmix(args, n_envs, episodes, device="cuda", log=None, timing=None, env_id="Switch2-v0", sink=None):
     dev = torch.device(device)
     if env_id.startswith("Switch"):
-        env = BatchedSwitch(n_envs, n_agents=int(env_id[6]), max_steps=args.max_step, step_cost=args.step_cost, device=dev)
+        make = lambda n: BatchedSwitch(n, n_agents=int(env_id[6]), max_steps=args.max_step, step_cost=args.step_cost, device=dev)
     else:
-        env = BatchedCheckers(n_envs, full_observable=False, max_steps=args.max_step, step_cost=args.step_cost, device=dev)
-    return _run(args, env, episodes, True, log, timing)
+        make = lambda n: BatchedCheckers(n, full_observable=False, max_steps=args.max_step, step_cost=args.step_cost, device=dev)
+    return _run(args, make(n_envs), episodes, True, log, timing, sink, None)

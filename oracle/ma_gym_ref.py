@@ -19,7 +19,7 @@ This restatement follows the published algorithm of that version and is anchored
 * obs dims 47 / 94 from the author's notes (``정리:3-19``) and the prose spec
   ``default/vdn/explain.txt`` (3x8 grid, 2 position values + 3x3x5 neighbourhood);
 * the reward lattice and the termination rule recovered from 52k logged episode scores
-  (``vdn/logs/vdn-1710766189.log``) -- see ``tests/test_env_log_anchors.py``.
+  (``vdn/logs/vdn-1710766189.log``) -- see ``tests/test_oracle_env.py``.
 
 Everything is plain Python on lists, like the original, so float results are Python doubles
 (``round(x, 2)``, ``step_cost + 10``); callers cast to float32 exactly as the reference's

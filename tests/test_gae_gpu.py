@@ -63,3 +63,20 @@ def test_gae_full_size_linearity(cuda):
     lhs = run(r1 + r2, v1 + v2)
     rhs = run(r1, v1) + run(r2, v2)
     assert torch.allclose(lhs, rhs, atol=2e-4, rtol=1e-5)
+
+
+def test_gae_full_size_matches_oracle(cuda):
+    """BASELINE size (T = 128, 16 384 envs x 2 agents = 32 768 rows), ValueNorm denormalisation and advantages in the same
+    pass: bit-equal to the numpy oracle (pinned on tests/golden/gae.npz)."""
+    from minimarl_b200.ops import gae_returns
+    T, rows = 128, 32768
+    rewards, values, masks = _inputs(T, rows, 11)
+    denorm = (np.sqrt(np.float32(1.3)), np.float32(0.1))
+    ref = gae_ref.compute_returns(rewards, values, masks, 0.99, 0.95, True, denorm)
+    ref_adv = gae_ref.advantages(ref, values, denorm)
+    returns = torch.zeros((T + 1, rows), device=cuda)
+    adv = torch.zeros((T, rows), device=cuda)
+    gae_returns(torch.from_numpy(rewards).to(cuda), torch.from_numpy(values).to(cuda), torch.from_numpy(masks).to(cuda),
+                returns, 0.99, 0.95, use_gae=True, denorm=denorm, advantages=adv)
+    assert np.array_equal(returns[:-1].cpu().numpy(), ref[:-1])
+    assert np.array_equal(adv.cpu().numpy(), ref_adv)

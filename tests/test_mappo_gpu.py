@@ -94,6 +94,40 @@ def test_full_mappo_train_matches_reference(cuda):
             assert np.allclose(p.cpu().numpy(), g[prefix + name], atol=5e-4, rtol=1e-4), prefix + name
 
 
+def test_full_mappo_train_fused_tf32_matches_reference(cuda):
+    """R_MAPPO.train through the FUSED update (tcgen05 trunk forward / backward, loss kernels, chunks read in place; TF32
+    operands) against the reference-recorded run: train_info 5e-4 relative, parameters after the 4 Adam steps 2e-3 abs
+    (measured 6e-5 and 3e-4; lr = 5e-4-scale steps turn a sign flip of a ~0 gradient into a 2 lr difference)."""
+    from minimarl_b200.algorithms import R_MAPPO
+    from minimarl_b200.buffers import SharedReplayBuffer
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        g = _g()
+        args, policy = _policy(cuda, g, "tf32")
+        trainer = R_MAPPO(args, policy, device=cuda)
+        space = Box(np.zeros(47), np.ones(47))
+        buf = SharedReplayBuffer(args, 2, space, space, Discrete(5), device=cuda)
+        for k in ["obs", "share_obs", "rnn_states", "rnn_states_critic", "actions", "masks", "rewards", "value_preds",
+                  "action_log_probs", "active_masks"]:
+            getattr(buf, k).copy_(torch.from_numpy(g["buf_" + k]))
+        buf.compute_returns(g["next_value"], trainer.value_normalizer)
+        calls = []
+        fused = trainer._ppo_update_fused
+        trainer._ppo_update_fused = lambda *a, **k: (calls.append(1), fused(*a, **k))[1]
+        info = trainer.train(buf, perms=list(g["perms"]))
+        assert len(calls) == int(g["ppo_epoch"]) * int(g["train_batch_size"]), "the fused update did not run"
+        for k in ["value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio", "Sampling_Rewards"]:
+            want, got = float(g["info_" + k]), float(info[k])
+            assert abs(got - want) < 5e-4 * max(1.0, abs(want)), (k, got, want)
+        for prefix, module in [("actor_after.", policy.actor), ("critic_after.", policy.critic), ("vn_after.", trainer.value_normalizer)]:
+            for name, p in module.state_dict().items():
+                assert np.allclose(p.cpu().numpy(), g[prefix + name], atol=2e-3, rtol=1e-3), prefix + name
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def test_lockstep_mappo_rollout_and_update(cuda):
     """Runner-shaped loop on the device: collect (fused actor / critic step) -> env kernel writes the buffer slot
     in place -> insert -> compute_returns (GAE kernel) -> train.  Checks shapes, finiteness and that stepping

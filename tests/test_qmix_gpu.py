@@ -142,6 +142,47 @@ def test_full_qmix_update_matches_reference(cuda):
     trainer.prep_rollout(); trainer.prep_training()
 
 
+def test_full_qmix_update_tf32_matches_reference(cuda):
+    """The benchmarked learner precision: TF32 operands (tensor-core target / greedy / mixer passes, TF32 cuBLAS in the live
+    pass), fp32 accumulation.  Same fixture as the fp32 test; stated tolerances: loss 3e-3 rel, grad norm 2e-3 rel, Q_tot 2e-3,
+    priorities 2e-3 of the largest, every gradient tensor 1e-2 of its norm (measured: 6e-4, 3e-4, 3e-4, 4e-4, <= 2.6e-3)."""
+    from minimarl_b200.algorithms import QMix, QMixPolicy
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        g = _g()
+        args = _args(fused_precision="tf32")
+        T, B, A, D, nA = 12, 6, 2, 47, 5
+        pconf = {"cent_obs_dim": A * D, "cent_act_dim": A * nA, "obs_space": Box(np.zeros(D), np.ones(D)),
+                 "share_obs_space": Box(np.zeros(A * D), np.ones(A * D)), "act_space": Discrete(nA)}
+        policy = QMixPolicy(args, {"args": args, "device": cuda, "num_agents": A}, pconf)
+        trainer = QMix(args, A, B, {"policy_0": policy}, lambda a: "policy_0", device=cuda, episode_length=T)
+        _load(policy.q_network, g, "q.")
+        _load(trainer.target_policies["policy_0"].q_network, g, "tq.")
+        _load(trainer.mixer, g, "mix.")
+        _load(trainer.target_mixer, g, "tmix.")
+        batch = tuple({"policy_0": g[k]} for k in ["obs", "share_obs", "acts", "rewards", "dones", "dones_env"]) + \
+            ({"policy_0": None}, g["weights"], np.arange(B))
+        info, new_prio, _ = trainer.train_policy_on_batch(batch)
+        assert abs(info["loss"].item() - float(g["train_loss"])) < 3e-3 * abs(float(g["train_loss"]))
+        assert abs(float(info["grad_norm"]) - float(g["train_grad_norm"])) < 2e-3 * float(g["train_grad_norm"])
+        assert abs(info["Q_tot"].item() - float(g["train_Q_tot"])) < 2e-3
+        want = g["train_new_priorities"]
+        assert np.abs(new_prio.cpu().numpy() - want).max() < 2e-3 * np.abs(want).max()
+        names = [n for n, _ in policy.q_network.named_parameters()] + ["mix." + n for n, _ in trainer.mixer.named_parameters()]
+        checked = 0
+        for n, p in zip(names, trainer.parameters):
+            key = "grad." + n
+            if key in g.files:
+                err = np.linalg.norm(p.grad.cpu().numpy() - g[key]) / np.linalg.norm(g[key])
+                assert err < 1e-2, (n, err)
+                checked += 1
+        assert checked >= 30
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def test_q_select_and_td_kernels_against_torch(cuda):
     from minimarl_b200.ops import q_select, qmix_td_loss
     T, B, A, NA = 20, 37, 2, 5
