@@ -23,7 +23,7 @@ from ..nn.gru import GRU
 from ..nn.layernorm import LayerNorm
 from ..nn.ppo_trunk import ChunkRows, ppo_trunk, trunk_fits
 from ..ops.ppo_loss import ppo_actor_loss, ppo_value_loss
-from ..parallel import allreduce_mean_grads, allreduce_stats
+from ..parallel import GradBucket, allreduce_mean_grads, allreduce_stats
 
 
 def _shape(space):
@@ -391,6 +391,7 @@ class R_MAPPO:
             raise NotImplementedError("PopArt is outside the hot path")
         self.value_normalizer = ValueNorm(input_shape=1).to(self.device) if self._use_valuenorm else None
         self._fused_loss = bool(getattr(args, "fused_update", True)) and torch.device(device).type == "cuda"
+        self._buckets = {}
 
     def cal_value_loss(self, values, value_preds_batch, return_batch, active_masks_batch):
         if self._fused_loss and values.is_cuda:
@@ -443,22 +444,35 @@ class R_MAPPO:
         else:
             policy_action_loss = -torch.sum(torch.min(surr1, surr2), dim=-1, keepdim=True).mean()
         policy_loss = policy_action_loss
-        self.policy.actor_optimizer.zero_grad()
+        self._zero_grads(self.policy.actor, self.policy.actor_optimizer)
         if update_actor:
             (policy_loss - dist_entropy * self.entropy_coef).backward()
-        allreduce_mean_grads(list(self.policy.actor.parameters()))
+        allreduce_mean_grads(list(self.policy.actor.parameters()), bucket=self._buckets.get(id(self.policy.actor)))
         actor_grad_norm = nn.utils.clip_grad_norm_(self.policy.actor.parameters(), self.max_grad_norm) \
             if self._use_max_grad_norm else _grad_norm(self.policy.actor.parameters())
         self.policy.actor_optimizer.step()
 
         value_loss = self.cal_value_loss(values, value_preds_batch, return_batch, active_masks_batch)
-        self.policy.critic_optimizer.zero_grad()
+        self._zero_grads(self.policy.critic, self.policy.critic_optimizer)
         (value_loss * self.value_loss_coef).backward()
-        allreduce_mean_grads(list(self.policy.critic.parameters()))
+        allreduce_mean_grads(list(self.policy.critic.parameters()), bucket=self._buckets.get(id(self.policy.critic)))
         critic_grad_norm = nn.utils.clip_grad_norm_(self.policy.critic.parameters(), self.max_grad_norm) \
             if self._use_max_grad_norm else _grad_norm(self.policy.critic.parameters())
         self.policy.critic_optimizer.step()
         return value_loss, critic_grad_norm, policy_loss, dist_entropy, actor_grad_norm, imp_weights
+
+    def _zero_grads(self, module, optimizer):
+        """Multi-GPU: the module's gradients live in one flat ``GradBucket`` (``p.grad`` are views; backward and the fused
+        trunk op write straight into it, the exchange is one all-reduce on the flat buffer), zeroed here instead of
+        ``optimizer.zero_grad()`` so that the views survive.  Single GPU: plain ``zero_grad``."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            b = self._buckets.get(id(module))
+            if b is None or not b.attached():
+                b = self._buckets[id(module)] = GradBucket(list(module.parameters()))
+            b.zero()
+        else:
+            optimizer.zero_grad()
 
     def _ppo_update_fused(self, sample, update_actor=True):
         """Same update with the fused trunk op and the loss kernels: logits -> (policy loss, entropy, ratio) in one pass."""
@@ -470,10 +484,10 @@ class R_MAPPO:
         policy_loss, dist_entropy, ratio = ppo_actor_loss(
             logits, to(actions_batch), to(old_action_log_probs_batch), to(adv_targ),
             to(active_masks_batch) if self._use_policy_active_masks else None, self.clip_param)
-        self.policy.actor_optimizer.zero_grad()
+        self._zero_grads(self.policy.actor, self.policy.actor_optimizer)
         if update_actor:
             (policy_loss - dist_entropy * self.entropy_coef).backward()
-        allreduce_mean_grads(list(actor.parameters()))
+        allreduce_mean_grads(list(actor.parameters()), bucket=self._buckets.get(id(actor)))
         actor_grad_norm = nn.utils.clip_grad_norm_(actor.parameters(), self.max_grad_norm) \
             if self._use_max_grad_norm else _grad_norm(actor.parameters())
         self.policy.actor_optimizer.step()
@@ -484,9 +498,9 @@ class R_MAPPO:
             g = lambda x: x.gather() if isinstance(x, ChunkRows) else x
             values, _ = critic(g(share_obs_batch), g(rnn_states_critic_batch), g(masks_batch))
         value_loss = self.cal_value_loss(values, to(value_preds_batch), to(return_batch), to(active_masks_batch))
-        self.policy.critic_optimizer.zero_grad()
+        self._zero_grads(self.policy.critic, self.policy.critic_optimizer)
         (value_loss * self.value_loss_coef).backward()
-        allreduce_mean_grads(list(critic.parameters()))
+        allreduce_mean_grads(list(critic.parameters()), bucket=self._buckets.get(id(critic)))
         critic_grad_norm = nn.utils.clip_grad_norm_(critic.parameters(), self.max_grad_norm) \
             if self._use_max_grad_norm else _grad_norm(critic.parameters())
         self.policy.critic_optimizer.step()

@@ -23,7 +23,7 @@ import torch
 
 from ..nn import AgentQFunction, QMixer, VDNMixer
 from ..ops.td import q_select, qmix_td_loss
-from ..parallel import allreduce_mean_grads
+from ..parallel import GradBucket, allreduce_mean_grads
 
 
 def _space_dim(space):
@@ -176,7 +176,18 @@ class QMix:
 
     # -- gradient exchange (the only collective on this path) -------------------------------------
     def _allreduce_grads(self):
-        allreduce_mean_grads(self.parameters)
+        allreduce_mean_grads(self.parameters, bucket=getattr(self, "_bucket", None))
+
+    def _zero_grads(self):
+        """Multi-GPU: gradients of every parameter live in one flat ``GradBucket`` (views), see parallel.py."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            b = getattr(self, "_bucket", None)
+            if b is None or not b.attached():
+                b = self._bucket = GradBucket(self.parameters)
+            b.zero()
+        else:
+            self.optimizer.zero_grad()
 
     def train_policy_on_batch(self, batch, update_policy_id=None):
         obs_batch, cent_obs_batch, act_batch, rew_batch, dones_batch, dones_env_batch, avail_act_batch, \
@@ -233,7 +244,7 @@ class QMix:
                                                  self.args.per_nu, self.per_eps)
         new_priorities = prio if self.use_per else None
 
-        self.optimizer.zero_grad()
+        self._zero_grads()
         loss.backward()
         self._allreduce_grads()
         grad_norm = torch.nn.utils.clip_grad_norm_(self.parameters, self.args.max_grad_norm)

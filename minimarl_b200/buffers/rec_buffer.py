@@ -162,6 +162,9 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
         self._it_sums = {p_id: SumSegmentTree(it_capacity, device) for p_id in policy_info.keys()}
         self._it_mins = {p_id: MinSegmentTree(it_capacity, device) for p_id in policy_info.keys()}
         self.max_priorities = {p_id: 1.0 for p_id in policy_info.keys()}
+        # sharded replay (one shard per GPU): importance weights normalised with min p / sum p / len over ALL
+        # shards (parallel.per_global_weights) instead of this shard's tree alone
+        self.sharded = False
 
     def _seed_priorities(self, idx_range):
         n = len(idx_range)
@@ -202,6 +205,11 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
         _lib.check(_lib.lib().mm_per_sample(_lib.ptr(st._value), _lib.ptr(mt._value), st._capacity, len(self),
                                             _lib.ptr(uniforms), batch_size, float(beta), _lib.ptr(batch_inds),
                                             _lib.ptr(weights), _lib.stream()))
+        if self.sharded:
+            from ..parallel import per_global_weights
+            n = len(self)
+            leaves = st._value[st._capacity:st._capacity + n]
+            weights = per_global_weights(leaves[batch_inds], mt._value[st._capacity:st._capacity + n].min(), leaves.sum(), n, beta)
         return self._gather(batch_inds) + (weights, batch_inds)
 
     def update_priorities(self, idxes, priorities, p_id=None):

@@ -55,6 +55,9 @@ class MAGYM_Runner:
         self.buffer = PrioritizedRecReplayBuffer(args.per_alpha, *buf_args, device=self.device,
                                                  fix_insert_priority=not getattr(args, "faithful_per_insert", False)) \
             if self.use_per else RecReplayBuffer(*buf_args, device=self.device)
+        import torch.distributed as dist
+        if self.use_per and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.buffer.sharded = True                       # env / replay shard per GPU: global PER normaliser
         self._collector = EpisodeCollector(self.train_env, self.policies["policy_0"], self.buffer, self.episode_length,
                                            seed=getattr(args, "seed", 0))
         self.train_infos, self.env_infos = [], {}

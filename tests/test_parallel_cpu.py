@@ -7,7 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from minimarl_b200.parallel import allreduce_mean_grads, allreduce_stats, shard_range
+from minimarl_b200.parallel import (GradBucket, allreduce_mean_grads, allreduce_stats, per_global_weights,
+                                    shard_range)
 
 
 def test_shard_range_partitions_everything():
@@ -37,6 +38,30 @@ def _worker(rank, world, port, out):
     stats = allreduce_stats([float(rank + 1), 1.0])
     ok = torch.allclose(got, want, atol=1e-6) and unused.grad is None and nbytes == got.numel() * 4
     ok = ok and stats.tolist() == [3.0, 2.0]
+    # ---- flat bucket: p.grad are views, backward lands in the bucket, one collective, extras summed alongside --------
+    torch.manual_seed(0)
+    net2 = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    unused2 = torch.nn.Parameter(torch.ones(4))
+    bucket = GradBucket(list(net2.parameters()) + [unused2], n_extra=2)
+    bucket.zero()
+    net2(x).sum().backward()
+    ok = ok and bucket.attached()                               # autograd accumulated in place into the views
+    bucket.extra.copy_(torch.tensor([float(rank + 1), 1.0]))
+    nbytes2 = allreduce_mean_grads(bucket.params, bucket=bucket)
+    got2 = torch.cat([p.grad.reshape(-1) for p in net2.parameters()])
+    ok = ok and torch.allclose(got2, want, atol=1e-6) and bucket.extra.tolist() == [3.0, 2.0]
+    ok = ok and float(unused2.grad.abs().sum()) == 0.0 and nbytes2 == bucket.flat.numel() * 4
+    torch.optim.SGD(bucket.params, lr=0.1).zero_grad(set_to_none=True)          # views dropped -> falls back to packing
+    ok = ok and not bucket.attached()
+    # ---- sharded PER: weights under the global normaliser equal the single-process formula on the union ---------------
+    g = torch.Generator().manual_seed(5)
+    prios = torch.rand(10, dtype=torch.float64, generator=g) + 0.05             # 10 episodes, 6 on rank 0, 4 on rank 1
+    mine = prios[:6] if rank == 0 else prios[6:]
+    beta = 0.4
+    w = per_global_weights(mine[:3], mine.min(), mine.sum(), len(mine), beta)
+    p_min = prios.min() / prios.sum()
+    want_w = (mine[:3] / prios.sum() * 10) ** (-beta) / (p_min * 10) ** (-beta)
+    ok = ok and torch.allclose(w, want_w, rtol=1e-12)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
