@@ -10,9 +10,11 @@
 // 32 hidden columns of its row, the four parts of a row meet through shared memory for the LayerNorm statistics.
 //
 // Forward (training mode) also stores, per (step, row), the operands the weight gradients need: the normalised
-// observation x0 [48], the two MLP activations x1, x2 [32] and the masked input state hp [32].
-// Backward walks the steps in reverse; for each step it RE-COMPUTES the forward from obs[t] and hp[t] (three MMA
-// phases; cheaper than storing and re-reading every intermediate), then propagates
+// observation x0 [48], the NORMALISED (pre-affine) MLP activations xh1, xh2 [32] -- the host multiplies the matching
+// weight-gradient blocks by the LayerNorm gains -- the masked input state hp [32], and in the spare columns of the row
+// 1 / sigma of both LayerNorms and the two ReLU masks.
+// Backward walks the steps in reverse; for each step it reloads xh1 / xh2 / hp, RE-COMPUTES only the GRU cell (one MMA
+// phase: the gates from x2 = xh2 g2 + b2 and hp), then propagates
 //     d head -> LayerNorm -> GRU cell -> (dx2 = dGi Wih, dhp = dGh Whh on tcgen05) -> LayerNorm/ReLU -> (dx1 = dA2 W2)
 //     -> LayerNorm/ReLU
 // and emits the pre-activation gradients dA1, dA2 [32], dGi [96], dGh_n [32] per (step, row).  The weight gradients
@@ -68,7 +70,10 @@ __host__ __device__ inline Layout make_layout() {
     return L;
 }
 
-constexpr int XS = 152;   // row stride of the saved-operand matrix X: x0 [0,48) x1 [48,80) x2 [80,112) hp [112,144) 1 [144] 0 [145,152)
+// row stride of the saved-operand matrix X: x0 [0,48) xh1 [48,80) xh2 [80,112) hp [112,144) | 1 [144] 1/sigma1 [145] 1/sigma2 [146]
+// 0 [147] | per column part p: relu1 bits + 256 * relu2 bits as a float [148 + p].  Columns 145..151 are read by the backward
+// kernel only; the weight-gradient GEMM produces (ignored) output columns for them.
+constexpr int XS = 152;
 constexpr int GS = 192;   // row stride of the gradient matrix G: dA1 [0,32) dA2 [32,64) dGi [64,160) dGh_n [160,192)
 // per-CTA column-sum accumulators: S[o][j] = sum_r dout[r][o] * xhat3[r][j] (NOMAX x H), dbo (NOMAX), dgamma2 (H), dgamma1 (H)
 constexpr int kTmemS = 5;   // head outputs whose S rows are accumulated in TMEM (the rest, if any, by warp shuffles per step)
@@ -130,6 +135,15 @@ __device__ __forceinline__ void store8_kmajor(uint8_t* tile, int r, int k0, int 
         make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
     *reinterpret_cast<float4*>(tile + tc::kmajor_offset(r, k0 + 4, K)) =
         make_float4(to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7]));
+}
+__device__ __forceinline__ void store8_kmajor_raw(uint8_t* tile, int r, int k0, int K, const float (&v)[CPT]) {
+    *reinterpret_cast<float4*>(tile + tc::kmajor_offset(r, k0, K)) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(tile + tc::kmajor_offset(r, k0 + 4, K)) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void load8_kmajor(const uint8_t* tile, int r, int k0, int K, float (&v)[CPT]) {
+    const float4 q0 = *reinterpret_cast<const float4*>(tile + tc::kmajor_offset(r, k0, K));
+    const float4 q1 = *reinterpret_cast<const float4*>(tile + tc::kmajor_offset(r, k0 + 4, K));
+    v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
 }
 __device__ __forceinline__ void store8_global(float* dst, const float (&v)[CPT]) {
     mm::st_stream(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
@@ -201,9 +215,12 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
     uint8_t* sdG = sWhhT + 3 * H * H * 4;                 // [128 x 4H]: dr | dz | dn | dn*r ; dA2 re-uses its first 16 KB
     float* sAcc = reinterpret_cast<float*>(sdG + kRows * 4 * H * 4);       // [4 row quarters][ACC_N]
     float* sDout = sAcc + 4 * ACC_N;                                       // [128][NO] head gradients of the current step
+    float* sTail = sDout + kRows * NOMAX;                                  // [128][8] columns 144..151 of the step's X rows
     // regions that are idle while a step starts double as the raw observation tile (filled by cp.async one step ahead)
     // and, in the forward, as the head's partial sums
     float* sObs = reinterpret_cast<float*>(sX1);                           // [128][D]  (<= 24 KB, forward only)
+    uint8_t* sStage = tail;                               // [128 x H] un-rounded xh1 / xh2 on their way to X (forward only; aliases sW2T..)
+    float* sTailF = reinterpret_cast<float*>(sStage + kRows * H * 4);      // [128][8] columns 144..151 of the step's X rows (forward)
     float* sHead = reinterpret_cast<float*>(sX0);                          // [NOMAX][4][128]  (forward only)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -345,6 +362,15 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
         for (int i = n + tid; i < kRows * a.NO; i += kThreads) sDout[i] = 0.f;
     };
 
+    // columns 144..151 of the X rows of (tile, step t): LayerNorm scales and ReLU masks the forward left there
+    auto fetch_tail = [&](long long row0, int n_valid, int t) {
+        if (tid < 2 * kRows) {
+            const int r = tid >> 1, half = tid & 1;
+            const float* src = a.X + ((long long)t * a.R + row0 + min(r, n_valid - 1)) * XS + 144 + 4 * half;
+            cp_async16(sTail + r * 8 + 4 * half, src);
+        }
+    };
+
     for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const long long row0 = tile * kRows;
         const int n_valid = (int)min((long long)kRows, a.R - row0);
@@ -362,10 +388,12 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
             load8_global(a.obs_row ? a.h0 + sRowBase[row] * H + j0 : a.h0 + grow * H + j0, h);
             fetch_obs(row0, n_valid, 0);
         } else {
-            // backward: the normalised observations and the input state of a step come straight from X into the operand tiles
+            // backward: the normalised activations and the input state of a step come straight from X into the tiles
             const float* xrow = a.X + ((long long)(a.L - 1) * a.R + row0) * XS;
-            global_to_tile_async<K1>(sX0, xrow, XS, n_valid, tid);
+            global_to_tile_async<H>(sX0, xrow + 48, XS, n_valid, tid);
+            global_to_tile_async<H>(sX2, xrow + 80, XS, n_valid, tid);
             global_to_tile_async<H>(sHp, xrow + 112, XS, n_valid, tid);
+            fetch_tail(row0, n_valid, a.L - 1);
             fetch_dout(row0, n_valid, a.L - 1);
             cp_async_commit();
         }
@@ -378,7 +406,25 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
             // ---- F1. plain LayerNorm of the observation row -> X0 tile; masked input state -> Hp tile ----------------
             cp_async_wait_all();
             __syncthreads();
-            if (!BWD) {
+            float xh1[CPT], rstd1, xh2[CPT], rstd2;
+            uint32_t relu1 = 0, relu2 = 0;
+            float* const xtile = a.X ? a.X + ((long long)t * a.R + row0) * XS : nullptr;      // this tile's rows of X at step t
+            if (BWD) {
+                // backward: xh1 / xh2 / hp of this step are in the tiles, the LayerNorm scales and ReLU masks in the row's tail
+                load8_kmajor(sHp, row, j0, H, hp);
+                load8_kmajor(sX0, row, j0, H, xh1);
+                load8_kmajor(sX2, row, j0, H, xh2);
+                const float* tailp = sTail + row * 8;
+                rstd1 = tailp[1];
+                rstd2 = tailp[2];
+                const uint32_t bits = (uint32_t)tailp[4 + part];
+                relu1 = bits & 0xffu;
+                relu2 = bits >> 8;
+                float y[CPT];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) y[j] = fmaf(xh2[j], sP[L.ln2_w + j0 + j], sP[L.ln2_b + j0 + j]);
+                store8_kmajor(sX2, row, j0, H, y);              // in place: the operand of the gate MMAs
+            } else {
                 float x0[12];
                 const float* o = sObs + row * a.D;
                 float s = 0.f, q = 0.f;
@@ -407,81 +453,78 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) hp[j] = to_tf32(h[j] * mask);
                 store8_kmajor(sHp, row, j0, H, hp);
-            } else {
-                const float4 q0 = *reinterpret_cast<const float4*>(sHp + tc::kmajor_offset(row, j0, H));
-                const float4 q1 = *reinterpret_cast<const float4*>(sHp + tc::kmajor_offset(row, j0 + 4, H));
-                hp[0] = q0.x; hp[1] = q0.y; hp[2] = q0.z; hp[3] = q0.w; hp[4] = q1.x; hp[5] = q1.y; hp[6] = q1.z; hp[7] = q1.w;
-            }
-            PROF(0);
-            publish();
-            PROF(1);
-            if (tid == 0) {
+                PROF(0);
+                publish();
+                PROF(1);
+                if (tid == 0) {
 #pragma unroll
-                for (int kk = 0; kk < K1 / 8; ++kk) tc::mma_tf32(tmem, dX0 + 16 * kk, dW1 + 16 * kk, id32, kk > 0);
-                tc::mma_commit(&bar);
-            }
-            float* const xtile = a.X ? a.X + ((long long)t * a.R + row0) * XS : nullptr;      // this tile's rows of X at step t
-            if (!BWD && xtile) {
-                tile_to_global<K1>(sX0, xtile, XS, n_valid, tid);
-                tile_to_global<H>(sHp, xtile + 112, XS, n_valid, tid);
-            }
-            wait_mma();
-            PROF(2);
-            // ---- F2. fc1 epilogue ------------------------------------------------------------------------------------
-            float xh1[CPT], rstd1;
-            uint32_t relu1 = 0;
-            {
-                float v[CPT];
-                tc::tmem_ld8(lane_addr + j0, v);
-                float s = 0.f, q = 0.f;
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    v[j] += sP[L.b1 + j0 + j];
-                    if (v[j] > 0.f) relu1 |= 1u << j; else v[j] = 0.f;
-                    s += v[j]; q = fmaf(v[j], v[j], q);
+                    for (int kk = 0; kk < K1 / 8; ++kk) tc::mma_tf32(tmem, dX0 + 16 * kk, dW1 + 16 * kk, id32, kk > 0);
+                    tc::mma_commit(&bar);
                 }
-                float mean;
-                row_stats(s, q, mean, rstd1, H);
-                float y[CPT];
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    xh1[j] = (v[j] - mean) * rstd1;
-                    y[j] = fmaf(xh1[j], sP[L.ln1_w + j0 + j], sP[L.ln1_b + j0 + j]);
+                if (xtile) {
+                    tile_to_global<K1>(sX0, xtile, XS, n_valid, tid);
+                    tile_to_global<H>(sHp, xtile + 112, XS, n_valid, tid);
                 }
-                store8_kmajor(sX1, row, j0, H, y);
-            }
-            publish();
-            if (tid == 0) {
+                wait_mma();
+                PROF(2);
+                // ---- F2. fc1 epilogue --------------------------------------------------------------------------------
+                {
+                    float v[CPT];
+                    tc::tmem_ld8(lane_addr + j0, v);
+                    float s1 = 0.f, q1 = 0.f;
 #pragma unroll
-                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 32, dX1 + 16 * kk, dW2 + 16 * kk, id32, kk > 0);
-                tc::mma_commit(&bar);
-            }
-            if (!BWD && xtile) tile_to_global<H>(sX1, xtile + 48, XS, n_valid, tid);
-            PROF(3);
-            wait_mma();
-            PROF(4);
-            // ---- F3. fc2 epilogue ------------------------------------------------------------------------------------
-            float xh2[CPT], rstd2;
-            uint32_t relu2 = 0;
-            {
-                float v[CPT];
-                tc::tmem_ld8(lane_addr + 32 + j0, v);
-                float s = 0.f, q = 0.f;
+                    for (int j = 0; j < CPT; ++j) {
+                        v[j] += sP[L.b1 + j0 + j];
+                        if (v[j] > 0.f) relu1 |= 1u << j; else v[j] = 0.f;
+                        s1 += v[j]; q1 = fmaf(v[j], v[j], q1);
+                    }
+                    float mean1;
+                    row_stats(s1, q1, mean1, rstd1, H);
+                    float y[CPT];
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    v[j] += sP[L.b2 + j0 + j];
-                    if (v[j] > 0.f) relu2 |= 1u << j; else v[j] = 0.f;
-                    s += v[j]; q = fmaf(v[j], v[j], q);
+                    for (int j = 0; j < CPT; ++j) {
+                        xh1[j] = (v[j] - mean1) * rstd1;
+                        y[j] = fmaf(xh1[j], sP[L.ln1_w + j0 + j], sP[L.ln1_b + j0 + j]);
+                    }
+                    store8_kmajor(sX1, row, j0, H, y);
+                    if (xtile) store8_kmajor_raw(sStage, row, j0, H, xh1);
                 }
-                float mean;
-                row_stats(s, q, mean, rstd2, H);
-                float y[CPT];
+                publish();
+                if (tid == 0) {
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    xh2[j] = (v[j] - mean) * rstd2;
-                    y[j] = fmaf(xh2[j], sP[L.ln2_w + j0 + j], sP[L.ln2_b + j0 + j]);
+                    for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 32, dX1 + 16 * kk, dW2 + 16 * kk, id32, kk > 0);
+                    tc::mma_commit(&bar);
                 }
-                store8_kmajor(sX2, row, j0, H, y);
+                if (xtile) tile_to_global<H>(sStage, xtile + 48, XS, n_valid, tid);
+                PROF(3);
+                wait_mma();
+                PROF(4);
+                // ---- F3. fc2 epilogue --------------------------------------------------------------------------------
+                {
+                    float v[CPT];
+                    tc::tmem_ld8(lane_addr + 32 + j0, v);
+                    float s2 = 0.f, q2 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        v[j] += sP[L.b2 + j0 + j];
+                        if (v[j] > 0.f) relu2 |= 1u << j; else v[j] = 0.f;
+                        s2 += v[j]; q2 = fmaf(v[j], v[j], q2);
+                    }
+                    float mean2;
+                    row_stats(s2, q2, mean2, rstd2, H);
+                    float y[CPT];
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        xh2[j] = (v[j] - mean2) * rstd2;
+                        y[j] = fmaf(xh2[j], sP[L.ln2_w + j0 + j], sP[L.ln2_b + j0 + j]);
+                    }
+                    store8_kmajor(sX2, row, j0, H, y);
+                    if (xtile) {
+                        store8_kmajor_raw(sStage, row, j0, H, xh2);     // the xh1 copy out of sStage finished before the last barrier
+                        sTailF[row * 8 + part] = part == 0 ? 1.0f : part == 1 ? rstd1 : part == 2 ? rstd2 : 0.f;
+                        sTailF[row * 8 + 4 + part] = (float)(relu1 | (relu2 << 8));
+                    }
+                }
             }
             publish();
             if (tid == 0) {
@@ -495,7 +538,12 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 160, dHp + 16 * kk, dWhh_n + 16 * kk, id32, kk > 0);
                 tc::mma_commit(&bar);
             }
-            if (!BWD && xtile) tile_to_global<H>(sX2, xtile + 80, XS, n_valid, tid);
+            if (!BWD && xtile) {
+                tile_to_global<H>(sStage, xtile + 80, XS, n_valid, tid);
+                if (tid < 2 * kRows && (tid >> 1) < n_valid)
+                    mm::st_stream(reinterpret_cast<float4*>(xtile + (tid >> 1) * XS + 144 + 4 * (tid & 1)),
+                                  *reinterpret_cast<const float4*>(sTailF + (tid >> 1) * 8 + 4 * (tid & 1)));
+            }
             PROF(5);
             wait_mma();
             PROF(6);
@@ -503,9 +551,11 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
                 if (!BWD) {
                     fetch_obs(row0, n_valid, t + 1);     // the X1 / X2 tiles are consumed, the next observations land there
                 } else {
-                    const float* xrow = a.X + ((long long)(t - 1) * a.R + row0) * XS;   // X0 / Hp tiles are consumed as well
-                    global_to_tile_async<K1>(sX0, xrow, XS, n_valid, tid);
+                    const float* xrow = a.X + ((long long)(t - 1) * a.R + row0) * XS;   // every thread holds its xh1 / xh2 in registers
+                    global_to_tile_async<H>(sX0, xrow + 48, XS, n_valid, tid);
+                    global_to_tile_async<H>(sX2, xrow + 80, XS, n_valid, tid);
                     global_to_tile_async<H>(sHp, xrow + 112, XS, n_valid, tid);
+                    fetch_tail(row0, n_valid, t - 1);
                     cp_async_commit();
                 }
             }
@@ -564,19 +614,51 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) dy[j] = 0.f;
 #pragma unroll
-                for (int o = 0; o < NOMAX; ++o) {
+                for (int o = 0; o < NOMAX; ++o)
+                    if (o < a.NO) {
+#pragma unroll
+                        for (int j = 0; j < CPT; ++j) dy[j] = fmaf(dO[o], sP[L.wo + o * H + j0 + j], dy[j]);
+                    }
+                // S[o][:] += dout[o] * xhat3 for the first kTmemS outputs and dbo += dout: running sums in TMEM, the loads of a
+                // group in flight together (one wait per group instead of one per output)
+                {
+                    float t0[CPT], t1[CPT], t2[CPT];
+                    tc::tmem_ld8_issue(acc_addr + 0, t0);
+                    tc::tmem_ld8_issue(acc_addr + 8, t1);
+                    tc::tmem_ld8_issue(acc_addr + 16, t2);
+                    tc::tmem_ld_fence<CPT>(t0, t1, t2);
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        t0[j] = fmaf(dO[0], xh3[j], t0[j]); t1[j] = fmaf(dO[1], xh3[j], t1[j]); t2[j] = fmaf(dO[2], xh3[j], t2[j]);
+                    }
+                    tc::tmem_st8(acc_addr + 0, t0);
+                    tc::tmem_st8(acc_addr + 8, t1);
+                    tc::tmem_st8(acc_addr + 16, t2);
+                }
+                {
+                    float t3[CPT], t4[CPT], t5[CPT];
+                    tc::tmem_ld8_issue(acc_addr + 24, t3);
+                    tc::tmem_ld8_issue(acc_addr + 32, t4);
+                    tc::tmem_ld8_issue(acc_addr + 56, t5);
+                    tc::tmem_ld_fence<CPT>(t3, t4, t5);
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        t3[j] = fmaf(dO[3], xh3[j], t3[j]); t4[j] = fmaf(dO[4], xh3[j], t4[j]);
+                        if (part == 0) t5[j] += dO[j];
+                    }
+                    tc::tmem_st8(acc_addr + 24, t3);
+                    tc::tmem_st8(acc_addr + 32, t4);
+                    tc::tmem_st8(acc_addr + 56, t5);
+                }
+                static_assert(kTmemS == 5, "the grouped TMEM accumulation above covers outputs 0..4");
+#pragma unroll
+                for (int o = kTmemS; o < NOMAX; ++o)
                     if (o < a.NO) {
                         float p[CPT];
 #pragma unroll
-                        for (int j = 0; j < CPT; ++j) {
-                            dy[j] = fmaf(dO[o], sP[L.wo + o * H + j0 + j], dy[j]);
-                            p[j] = dO[o] * xh3[j];
-                        }
-                        if (o < kTmemS) tmem_accumulate(8 * o, p);
-                        else            colsum8(p, acc + ACC_S + o * H + j0, lane);
+                        for (int j = 0; j < CPT; ++j) p[j] = dO[o] * xh3[j];
+                        colsum8(p, acc + ACC_S + o * H + j0, lane);
                     }
-                }
-                if (part == 0) tmem_accumulate(56, dO);
             }
             PROF(13);
             // LayerNorm(h) backward
@@ -725,7 +807,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_trunk_kernel(const __grid_con
 size_t trunk_smem(bool bwd) {
     const Layout L = make_layout();
     size_t s = (size_t)4 * (H * K1 + H * H + 6 * H * H + kRows * K1 + 3 * kRows * H + 2 * kRows * 8 + (L.total - L.small)) + 256 + kRows * 8;
-    if (bwd) s += (size_t)4 * (H * H + 6 * H * H + kRows * 4 * H + 4 * ACC_N + kRows * NOMAX);
+    if (bwd) s += (size_t)4 * (H * H + 6 * H * H + kRows * 4 * H + 4 * ACC_N + 2 * kRows * NOMAX);
+    else     s += (size_t)4 * (kRows * H + kRows * 8);   // staging tile, row tails
     return s;
 }
 

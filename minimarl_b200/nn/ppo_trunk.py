@@ -3,8 +3,9 @@ over data chunks as ONE differentiable op (``mm_ppo_trunk_fwd`` / ``mm_ppo_trunk
 
 It computes what ``R_Actor.evaluate_actions`` / ``R_Critic.forward`` compute in the chunked (recurrent-generator)
 mode (mappo/algorithms/r_actor_critic.py:95-146,189-208; rnn.py:24-80): rows are data chunks, the carried state is
-multiplied by ``masks[t]`` before every step.  The forward stores the operands of the weight gradients, the backward
-kernel re-computes the forward per step, walks the chunk in reverse and returns the pre-activation gradients G; all
+multiplied by ``masks[t]`` before every step.  The forward stores the operands of the weight gradients (normalised
+activations, LayerNorm scales, ReLU masks), the backward kernel re-computes only the GRU cell per step, walks the chunk in
+reverse and returns the pre-activation gradients G; all
 weight and bias gradients are blocks of ONE large-K TF32 GEMM ``G^T X`` (X carries a ones column), the LayerNorm gain
 and head gradients come from column sums reduced inside the kernel.  ``LayerNorm(D)``'s affine is folded into the first Linear for the kernel and unfolded here.
 """
@@ -83,10 +84,9 @@ class _PPOTrunkFn(torch.autograd.Function):
         X = None
         if train:
             XS = dims()["XS"]
+            # columns 144..151 are written by the kernel: the ones column (bias gradients come out of the weight-gradient
+            # GEMM), 1 / sigma of the two LayerNorms and the ReLU masks for the backward kernel
             X = torch.empty((L * R, XS), **z)
-            tail = torch.zeros(XS - 144, **z)
-            tail[0] = 1.0
-            X[:, 144:] = tail                      # the ones column: bias gradients come out of the weight-gradient GEMM
         _lib.check(_lib.lib().mm_ppo_trunk_fwd(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(row_index), int(step_rows), _lib.ptr(h0),
                                                _lib.ptr(masks), _lib.ptr(out), None, _lib.ptr(X), L, R, D, NO, _lib.stream()))
         if train:
@@ -113,8 +113,11 @@ class _PPOTrunkFn(torch.autograd.Function):
         S = acc[d["S"]: d["S"] + NOMAX * H].view(NOMAX, H)[:NO]   # sum_r dout[r, o] * xhat3[r, j]
         dbo = acc[d["dbo"]: d["dbo"] + NO]
         gw1f, gb1f = W[0:32, 0:D], W[0:32, 144]                   # folded first Linear
-        gw2, gb2 = W[32:64, 48:80], W[32:64, 144]
-        gwih, gbih = W[64:160, 80:112], W[64:160, 144]
+        # X holds the NORMALISED activations xh1 / xh2 (x = xh * gain + offset is what the layer consumed):
+        #   dW = G^T x = (G^T xh) * gain + outer(db, offset)
+        gb2, gbih = W[32:64, 144], W[64:160, 144]
+        gw2 = W[32:64, 48:80] * p["ln1_w"] + torch.outer(gb2, p["ln1_b"])
+        gwih = W[64:160, 80:112] * p["ln2_w"] + torch.outer(gbih, p["ln2_b"])
         gwhh = torch.cat([W[64:128, 112:144], W[160:192, 112:144]], 0)
         gbhh = torch.cat([gbih[:2 * H], W[160:192, 144]])
         w1, wo = p["w1"], p["wo"]
