@@ -680,16 +680,28 @@ def run_ours(args, wl):
     host_acts = hb["act"].numpy()
     host_acts[...] = actions.cpu().numpy()
     e2e_steps = max(1, min(args.steps, 20))
-    for _ in range(3):
+    e2e_by_transport = {}
+    for transport in ("direct", "compact"):              # both paths timed; the public call (transport="auto") keeps the faster
+        for _ in range(3):
+            env.reset()
+            env.rollout_host(host_acts, transport=transport)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            env.reset()
+            o_h, r_h, d_h = env.rollout_host(host_acts, transport=transport)   # returns after the last output landed
+        e2e_by_transport[transport] = time.perf_counter() - t0
+    for _ in range(3):                                   # the call a user makes: auto picks per host / rank count
         env.reset()
         env.rollout_host(host_acts)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         env.reset()
-        o_h, r_h, d_h = env.rollout_host(host_acts)      # returns after the last D2H landed (stream synchronised)
+        o_h, r_h, d_h = env.rollout_host(host_acts)
     e2e_s = time.perf_counter() - t0
-    e2e_checksum = float(r_h.sum())                      # the host result is read
+    e2e_transport = hb["transport"]
+    e2e_checksum = float(r_h.sum()) + float(o_h[-1].sum())   # the host result is read
     # the one-env-step-per-call variant (step_host: H2D, kernel, D2H, sync every env step), for comparison
     sw_steps = min(T, 32)
     env.reset()
@@ -701,12 +713,13 @@ def run_ours(args, wl):
         env.step_host(host_acts[t])
     sw_s = time.perf_counter() - t1
     if world > 1:
-        t = torch.tensor([e2e_s, sw_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([e2e_s, sw_s, e2e_by_transport["direct"], e2e_by_transport["compact"]], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s, sw_s = float(t[0].item()), float(t[1].item())
+        e2e_by_transport = {"direct": float(t[2].item()), "compact": float(t[3].item())}
     e2e_value = n * A * T * e2e_steps * world / e2e_s
     e2e_stepwise = n * A * sw_steps * world / sw_s
-    h2d_step, d2h_step = env.rollout_host_bytes(T)
+    h2d_step, d2h_step = env.rollout_host_bytes(T, e2e_transport or "direct")
 
     learner = mappo_it = None
     if not args.no_learner:             # on every rank: the update all-reduces its gradients when world > 1
@@ -758,9 +771,13 @@ def run_ours(args, wl):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                     "steps": e2e_steps, "ms_per_step": e2e_s * 1e3 / e2e_steps,
                     "pcie_GBps": (h2d_step + d2h_step) * e2e_steps / e2e_s / 1e9, "result_checksum": e2e_checksum,
-                    "api": "BatchedCheckers.reset(); BatchedCheckers.rollout_host(numpy actions [T,N,A]) -> numpy obs / "
-                           "rewards / dones of all T steps (page-locked host arrays; mm_checkers_rollout_host pipelines "
-                           "H2D, kernel and D2H in chunks of 8 env steps); wall clock around the calls",
+                    "host_bytes_written_per_step": n * T * (A * D * 4 + A * 4 + A),
+                    "transport": e2e_transport,
+                    "by_transport": {k: n * A * T * e2e_steps * world / v for k, v in e2e_by_transport.items()},
+                    "api": "BatchedCheckers.reset(); BatchedCheckers.rollout_host(numpy actions [T,N,A]) -> numpy obs / rewards / "
+                           "dones of all T steps in page-locked host arrays; transport auto: direct = float32 observations over "
+                           "PCIe (mm_checkers_rollout_host), compact = one 64-bit word per agent-step over PCIe, expanded "
+                           "bit-identically by host threads (mm_checkers_rollout_host_compact); wall clock around the calls",
                     "stepwise_value": e2e_stepwise,
                     "stepwise_api": "BatchedCheckers.step_host: one env step per call, synchronised every step"},
             "gpu_launches": launches_per_step * args.steps,

@@ -104,6 +104,17 @@ int mm_checkers_rollout_host(uint32_t* state, const int32_t* actions_host, float
                              int32_t* bad_action_flag, int32_t T, int32_t chunk,
                              const mm_checkers_cfg* cfg_host, void* stream, void* copy_stream);
 
+/* The same host-array rollout with a compact device-to-host transport: the kernel emits one 64-bit word per agent-step
+ * (45 neighbourhood bits | row | col | reward kind | done: 8 B instead of 193 B over PCIe) and n_threads host threads
+ * (<= 0: one per CPU this process may run on, at most 32) expand the words into the same obs / rewards / dones arrays,
+ * bit-identical to mm_checkers_rollout_host, chunk by chunk while the device works on the next chunk.  Returns after every
+ * output landed (it synchronises copy_stream itself).  codes_host: page-locked uint64 [T][N][2]; codes_stage: device
+ * uint64 [2][chunk][N][2]; actions_stage: device int32 [2][chunk][N][2]. */
+int mm_checkers_rollout_host_compact(uint32_t* state, const int32_t* actions_host, float* obs_host, float* rewards_host,
+                                     uint8_t* dones_host, uint64_t* codes_host, int32_t* actions_stage, uint64_t* codes_stage,
+                                     int32_t* bad_action_flag, int32_t T, int32_t chunk, int32_t n_threads,
+                                     const mm_checkers_cfg* cfg_host, void* stream, void* copy_stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Switch{2,4}-v0 (ma-gym 0.0.14 `Switch`, un-vendored; qmix default env, qmix/_config.py:13-18,
  * qmix/main.py:66-71).  State planes: 0 = agent cells (8 bits per agent), 1 = per-agent done bits,

@@ -52,6 +52,7 @@ SIGNATURES = {
     "mm_checkers_rollout": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_uint64, C.c_uint64,
                                       C.POINTER(CheckersCfg), _P]),
     "mm_checkers_rollout_host": (C.c_int, [_P] * 10 + [C.c_int32, C.c_int32, C.POINTER(CheckersCfg), _P, _P]),
+    "mm_checkers_rollout_host_compact": (C.c_int, [_P] * 9 + [C.c_int32, C.c_int32, C.c_int32, C.POINTER(CheckersCfg), _P, _P]),
     "mm_switch_reset": (C.c_int, [_P, _P, _P, C.POINTER(SwitchCfg), _P]),
     "mm_switch_step": (C.c_int, [_P, _P, _P, _P, _P, _P, C.POINTER(SwitchCfg), _P]),
     "mm_switch_rollout": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_uint64, C.c_uint64,

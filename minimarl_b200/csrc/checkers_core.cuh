@@ -48,9 +48,10 @@ __device__ __forceinline__ uint64_t neighbourhood_mask(uint32_t food, uint32_t c
 }
 
 // One env.step for the (env, agent) of this lane.  All 32 lanes must call it.
+// reward_kind: 0 none, 1 lemon, 2 apple (index into cfg.reward[agent]), 3 = reward forced to 0 (episode already over)
 __device__ __forceinline__ void transition(EnvRegs& s, int act, int agent, int lane,
                                            const mm_checkers_cfg& cfg, float& reward, uint32_t& done,
-                                           bool& bad_action) {
+                                           bool& bad_action, int* reward_kind = nullptr) {
     const uint32_t latch = s.food & kDoneLatch;
     const uint32_t mine = (s.cells >> (8 * agent)) & 0xffu;
     const uint32_t other = (s.cells >> (8 * (agent ^ 1))) & 0xffu;
@@ -78,6 +79,7 @@ __device__ __forceinline__ void transition(EnvRegs& s, int act, int agent, int l
     const bool done_now = ((int)s.step >= cfg.max_steps) || ((food_new & kAppleCells) == 0u);
     // rewards are forced to 0 once the episode had already finished before this step
     reward = latch ? 0.0f : cfg.reward[agent][kind];
+    if (reward_kind) *reward_kind = latch ? 3 : kind;
     done = (latch || done_now) ? 1u : 0u;
     s.food = food_new | (done ? kDoneLatch : 0u);
 }

@@ -183,15 +183,21 @@ class BatchedCheckers(_BatchedBase):
                 rew=pin((T, n, a), torch.float32), done=pin((T, n, a), torch.uint8),
                 s_act=dev((2, chunk, n, a), torch.int32), s_obs=dev((2, chunk, n, a, d), torch.float32),
                 s_rew=dev((2, chunk, n, a), torch.float32), s_done=dev((2, chunk, n, a), torch.uint8),
-                copy_stream=torch.cuda.Stream(device=self.device))
+                codes=pin((T, n, a), torch.int64), s_codes=dev((2, chunk, n, a), torch.int64),
+                copy_stream=torch.cuda.Stream(device=self.device), transport=None, trial={})
         return self._hostT
 
-    def rollout_host(self, actions_np, chunk=8, want_obs=True):
+    def rollout_host(self, actions_np, chunk=8, want_obs=True, transport="auto", n_threads=0):
         """T lockstep steps for a caller holding HOST arrays (what the reference's runners hold):
         ``actions_np`` [T,N,A] ints -> numpy (obs [T,N,A,D], rewards [T,N,A], dones [T,N,A] bool), views of
         page-locked buffers that the next call overwrites.  H2D of the actions, the kernels and the D2H of the
-        outputs are pipelined chunk by chunk (``mm_checkers_rollout_host``); returns after the last copy landed.
-        Pass the ``host_buffers(T)["act"].numpy()`` array itself to skip the staging copy of the actions."""
+        outputs are pipelined chunk by chunk; returns after the last output landed.
+        Pass the ``host_buffers(T)["act"].numpy()`` array itself to skip the staging copy of the actions.
+
+        ``transport``: "direct" moves the float32 observations over PCIe as they are (``mm_checkers_rollout_host``);
+        "compact" moves one 64-bit word per agent-step and expands it on ``n_threads`` host threads into the same arrays,
+        bit-identical (``mm_checkers_rollout_host_compact``); "auto" times one call of each on this env / host and keeps the
+        faster (which one wins depends on how many ranks share the host's memory bandwidth)."""
         T = int(np.shape(actions_np)[0])
         h = self.host_buffers(T, chunk)
         act = h["act"].numpy()
@@ -199,6 +205,31 @@ class BatchedCheckers(_BatchedBase):
             act[...] = np.asarray(actions_np).reshape(T, self.n_envs, self.n_agents)
         cur = torch.cuda.current_stream(self.device)
         h["copy_stream"].wait_stream(cur)
+        if transport == "auto":
+            if not want_obs:
+                transport = "direct"                         # without the observations there is nothing to compress
+            elif h["transport"] is not None:
+                transport = h["transport"]
+            else:
+                transport = "direct" if "direct" not in h["trial"] else "compact"
+                import time
+                cur.synchronize()
+                t0 = time.perf_counter()
+                out = self.rollout_host(actions_np, chunk, want_obs, transport, n_threads)
+                h["trial"][transport] = time.perf_counter() - t0
+                if len(h["trial"]) == 2:
+                    h["transport"] = min(h["trial"], key=h["trial"].get)
+                return out
+        if transport == "compact":
+            _lib.check(_lib.lib().mm_checkers_rollout_host_compact(
+                _lib.ptr(self.state), h["act"].data_ptr(), h["obs"].data_ptr() if want_obs else None, h["rew"].data_ptr(),
+                h["done"].data_ptr(), h["codes"].data_ptr(), _lib.ptr(h["s_act"]), _lib.ptr(h["s_codes"]),
+                _lib.ptr(self.bad_action), T, int(chunk), int(n_threads), C.byref(self.cfg), cur.cuda_stream,
+                h["copy_stream"].cuda_stream))
+            cur.synchronize()
+            return (h["obs"].numpy() if want_obs else None), h["rew"].numpy(), h["done"].numpy().view(np.bool_)
+        if transport != "direct":
+            raise Exception(f"unknown transport {transport!r}")
         _lib.check(_lib.lib().mm_checkers_rollout_host(
             _lib.ptr(self.state), h["act"].data_ptr(), h["obs"].data_ptr() if want_obs else None,
             h["rew"].data_ptr(), h["done"].data_ptr(), _lib.ptr(h["s_act"]),
@@ -208,8 +239,10 @@ class BatchedCheckers(_BatchedBase):
         cur.synchronize()
         return (h["obs"].numpy() if want_obs else None), h["rew"].numpy(), h["done"].numpy().view(np.bool_)
 
-    def rollout_host_bytes(self, T):
+    def rollout_host_bytes(self, T, transport="direct"):
         """(H2D, D2H) bytes one ``rollout_host`` call of T steps moves over PCIe."""
+        if transport == "compact":
+            return T * self.h2d_bytes_per_step, T * self.n_envs * self.n_agents * 8
         return T * self.h2d_bytes_per_step, T * self.d2h_bytes_per_step
 
     # -- state decoding (tests, eval, render shims) -------------------------------------------------

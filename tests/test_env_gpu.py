@@ -315,8 +315,9 @@ def test_full_size_rollout_matches_oracle(cuda):
         assert np.array_equal(rew[t], r) and np.array_equal(done[t], d), t
 
 
+@pytest.mark.parametrize("transport", ["direct", "compact"])
 @pytest.mark.parametrize("T,chunk,full", [(1, 8, False), (5, 8, False), (8, 8, True), (37, 8, False), (48, 5, True)])
-def test_checkers_rollout_host_matches_oracle(cuda, T, chunk, full):
+def test_checkers_rollout_host_matches_oracle(cuda, T, chunk, full, transport):
     """Host-buffer rollout (mm_checkers_rollout_host: chunked H2D / kernel / D2H pipeline) vs the oracle, incl.
     ragged last chunks, a single chunk, and a second call that continues from the state the first one left."""
     from minimarl_b200 import BatchedCheckers
@@ -327,7 +328,7 @@ def test_checkers_rollout_host_matches_oracle(cuda, T, chunk, full):
     rng = np.random.default_rng(T * 100 + chunk)
     for call in range(2):
         acts = rng.integers(0, 5, size=(T, n, 2), dtype=np.int32)
-        obs, rew, done = env.rollout_host(acts, chunk=chunk)
+        obs, rew, done = env.rollout_host(acts, chunk=chunk, transport=transport, n_threads=3)
         for t in range(T):
             o, r, d = ref.step(acts[t])
             assert np.array_equal(obs[t], o), f"call {call}: obs differ at step {t}"
@@ -336,10 +337,27 @@ def test_checkers_rollout_host_matches_oracle(cuda, T, chunk, full):
     h = env.host_buffers(T, chunk)
     h["act"].numpy()[...] = rng.integers(0, 5, size=(T, n, 2), dtype=np.int32)
     acts = h["act"].numpy().copy()
-    obs, rew, done = env.rollout_host(h["act"].numpy(), chunk=chunk, want_obs=False)
+    obs, rew, done = env.rollout_host(h["act"].numpy(), chunk=chunk, want_obs=False, transport=transport)
     assert obs is None
     for t in range(T):
         _, r, d = ref.step(acts[t])
         assert np.array_equal(rew[t], r) and np.array_equal(done[t], d)
     pos, steps, _ = ref.export()
     assert np.array_equal(env.positions().cpu().numpy(), pos) and np.array_equal(env.step_count().cpu().numpy(), steps)
+
+
+def test_rollout_host_auto_transport_picks_one_and_stays_exact(cuda):
+    """transport="auto": one timed call of each path, then the faster one; every call returns the oracle's arrays."""
+    from minimarl_b200 import BatchedCheckers
+    n, T = 2048, 16
+    env = BatchedCheckers(n, max_steps=30, device=cuda, auto_reset=True)
+    ref = CheckersBatchRef(n, False, 30, -0.01, auto_reset=True)
+    env.reset(); ref.reset()
+    rng = np.random.default_rng(3)
+    for call in range(4):
+        acts = rng.integers(0, 5, size=(T, n, 2), dtype=np.int32)
+        obs, rew, done = env.rollout_host(acts)
+        for t in range(T):
+            o, r, d = ref.step(acts[t])
+            assert np.array_equal(obs[t], o) and np.array_equal(rew[t], r) and np.array_equal(done[t], d), (call, t)
+    assert env.host_buffers(T)["transport"] in ("direct", "compact")
