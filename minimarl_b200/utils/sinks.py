@@ -51,13 +51,13 @@ class MetricSink:
 
     @staticmethod
     def to_host(record):
-        """dict of floats / tensors -> dict of Python floats with ONE device-to-host copy for all tensor values."""
+        """dict of numbers / tensors -> the same dict with every tensor value as a Python float, ONE device-to-host copy for all."""
         keys = [k for k, v in record.items() if torch.is_tensor(v)]
         out = dict(record)
         if keys:
             flat = torch.stack([record[k].detach().reshape(()).to(torch.float64) for k in keys]).tolist()
             out.update(zip(keys, flat))
-        return {k: (float(v) if isinstance(v, (int, float)) and not isinstance(v, bool) else v) for k, v in out.items()}
+        return out
 
     def log(self, record, step=None, line=None, force=False):
         """Returns the host record when it was emitted, else None (thinned by ``every``; tensors stay on the device)."""

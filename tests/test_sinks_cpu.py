@@ -12,7 +12,7 @@ def test_to_host_and_reference_line_formats(caplog):
     rec = {"episode": 4, "train_score": torch.tensor(8.0), "train_loss": torch.tensor(1.25), "eps": 0.7998, "alpha": 0.6,
            "beta": torch.tensor(0.4, dtype=torch.float64)}
     host = MetricSink.to_host(rec)
-    assert host == {"episode": 4.0, "train_score": 8.0, "train_loss": 1.25, "eps": 0.7998, "alpha": 0.6, "beta": 0.4}
+    assert host == {"episode": 4, "train_score": 8.0, "train_loss": 1.25, "eps": 0.7998, "alpha": 0.6, "beta": 0.4}
     # the f-string of vdn/main.py:180
     episode, max_episodes, train_score, train_loss, epsilon, alpha, beta = 4, 30000, 8.0, 1.25, 0.7998, 0.6, 0.4
     want = (f"{(episode+1):<8}/{max_episodes:<10} episodes | train score: {train_score:<6.2f} | train loss: {train_loss:<7.2f} | "
