@@ -263,6 +263,12 @@ int mm_tc_raw_selftest(const float* imgA, const float* imgB, float* D, int32_t N
                        int32_t a_lbo, int32_t a_sbo, int32_t b_step, int32_t b_lbo, int32_t b_sbo, int32_t trans_a,
                        int32_t trans_b, void* stream);
 
+/* The same probe for kind::f16 (fp16 operands, fp32 accumulate): images are 64 KB of raw bytes, M = 64 or 128, trans_a /
+ * trans_b set the MN-major bits; D [128,N] is the dump of all 128 TMEM lanes (pre-filled with -12345). */
+int mm_tc_raw_f16_selftest(const void* imgA, const void* imgB, float* D, int32_t M, int32_t N, int32_t steps, int32_t a_step,
+                           int32_t a_lbo, int32_t a_sbo, int32_t b_step, int32_t b_lbo, int32_t b_sbo, int32_t trans_a,
+                           int32_t trans_b, void* stream);
+
 /* Lane probe: the same product with the instruction descriptor's M = 64 or 128 (A has M rows); every TMEM lane holds
  * -12345 before the MMA and D [128,N] is the dump of all 128 lanes afterwards: shows where a 64-row accumulator lives. */
 int mm_tc_lane_probe(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, void* stream);

@@ -108,6 +108,7 @@ SIGNATURES = {
     "mm_ppo_trunk_dims": (C.c_int, [_P]),
     "mm_tc_lane_probe": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "mm_tc_raw_selftest": (C.c_int, [_P, _P, _P] + [C.c_int32] * 10 + [_P]),
+    "mm_tc_raw_f16_selftest": (C.c_int, [_P, _P, _P] + [C.c_int32] * 11 + [_P]),
     "mm_mappo_rollout_param_count": (C.c_int, []),
     "mm_mappo_rollout_param_offsets": (C.c_int, [_P]),
     "mm_mappo_rollout_tc": (C.c_int, [_P] * 11 + [C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64,

@@ -34,13 +34,18 @@ def build(force=False, verbose=False):
     build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu")]
+    headers.append(os.path.join(HERE, "..", "include", "minimarl_b200.h"))
+    t_hdr = max(os.path.getmtime(h) for h in headers)
     for src in sources():
         obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), t_hdr):
+            continue                      # object newer than its source and every header: keep it
         cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode != 0:

@@ -43,6 +43,23 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint6
         : "memory");
 }
 
+// kind::f16 with fp16 operands (11-bit significand, the same as tf32), fp32 accumulate.  a_mn / b_mn select the MN-major
+// reading of an operand (bits 15 / 16): with 16-bit types the no-swizzle layout serves both majors -- a tile stored as
+// [rows][features] in 8 x 16-byte core matrices is K-major when the features are contracted and MN-major when the rows are.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool a_mn = false, bool b_mn = false) {
+    return (1u << 4)            // c_format = F32; a_format = b_format = 0 (F16)
+         | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16)
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

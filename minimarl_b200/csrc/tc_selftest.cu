@@ -165,7 +165,75 @@ tc_lane_probe_kernel(const float* __restrict__ A, const float* __restrict__ B, f
     if (warp == 0) tc::tmem_dealloc(tmem, ncols);
 }
 
+// Raw probe for kind::f16 (fp16 operands): 64 KB images, descriptor fields and the two major bits given by the caller; M = 64
+// or 128.  All 128 TMEM lanes x N columns are dumped.  tests/test_tc_gpu.py records with it that ONE [rows][features] tile in
+// the no-swizzle core-matrix layout is read K-major (features contracted) and MN-major (rows contracted) by swapping the
+// leading / stride byte offsets -- what ppo_trunk's in-kernel weight gradients rest on.
+__global__ void __launch_bounds__(128, 1)
+tc_raw_f16_selftest_kernel(const uint32_t* __restrict__ imgA, const uint32_t* __restrict__ imgB, float* __restrict__ D, int M,
+                           int N, int steps, int a_step, int a_lbo, int a_sbo, int b_step, int b_lbo, int b_sbo, int ta, int tb) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    uint32_t* sA = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* sB = sA + 16384;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t ncols = 32;
+    while ((int)ncols < N) ncols <<= 1;
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) tc::mbar_init(&bar, 1);
+    for (int i = tid; i < 16384; i += 128) { sA[i] = imgA[i]; sB[i] = imgB[i]; }
+    tc::fence_smem_to_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    float sentinel[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sentinel[j] = -12345.0f;
+    for (int c = 0; c < N; c += 8) tc::tmem_st8(lane_addr + c, sentinel);
+    tc::tmem_wait_st();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_f16(M, N, ta != 0, tb != 0);
+        for (int kk = 0; kk < steps; ++kk)
+            tc::mma_f16(tmem, tc::make_desc(tc::smem_u32(sA) + kk * a_step, a_lbo, a_sbo),
+                        tc::make_desc(tc::smem_u32(sB) + kk * b_step, b_lbo, b_sbo), idesc, kk > 0);
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    const int row = warp * 32 + lane;
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tc::tmem_ld16(lane_addr + c, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (c + j < N) D[row * N + c + j] = v[j];
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, ncols);
+}
+
 }  // namespace
+
+extern "C" int mm_tc_raw_f16_selftest(const void* imgA, const void* imgB, float* D, int32_t M, int32_t N, int32_t steps,
+                                      int32_t a_step, int32_t a_lbo, int32_t a_sbo, int32_t b_step, int32_t b_lbo, int32_t b_sbo,
+                                      int32_t trans_a, int32_t trans_b, void* stream) {
+    if (!imgA || !imgB || !D || (M != 64 && M != 128) || N < 16 || N > 256 || N % 16 || steps < 1 || steps > 16)
+        return MM_ERR_BAD_ARG;
+    const size_t smem = (size_t)2 * 65536;
+    cudaError_t e = cudaFuncSetAttribute(tc_raw_f16_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
+    tc_raw_f16_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint32_t*>(imgA), static_cast<const uint32_t*>(imgB), D, M, N, steps, a_step, a_lbo, a_sbo, b_step,
+        b_lbo, b_sbo, trans_a, trans_b);
+    return mm::check_launch();
+}
 
 extern "C" int mm_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, void* stream) {
     if (!A || !B || !D || N < 16 || N > 256 || N % 16 || K < 8 || K % 8 || K > 128) return MM_ERR_BAD_ARG;

@@ -46,3 +46,24 @@ def test_tcgen05_descriptor_strides_probe(cuda):
             rows = (D[:, 0] != 0).nonzero().flatten().tolist()
             # with SBO = 128 and LBO = 256 row m and row m + 16 (second k group of m) share a byte: both must light up
             assert m in rows and all((r - m) % 8 == 0 for r in rows), (lbo, sbo, m, k, rows)
+
+
+def test_tcgen05_f16_one_tile_both_majors(cuda):
+    """kind::f16: ONE [rows][features] fp16 tile in the no-swizzle core-matrix layout (8 x 16-byte core matrices, feature chunks
+    outermost) is a K-major operand when the features are contracted (LBO = chunk stride, SBO = 128) and an MN-major operand when
+    the rows are contracted (LBO = 128 between groups of 8 rows, SBO = chunk stride).  Exact on small integers."""
+    import numpy as np
+    from profiles.probe_f16_layouts import run, tile_image
+    rng = np.random.default_rng(1)
+    G = rng.integers(-4, 5, (128, 128)).astype(np.float32)
+    X = rng.integers(-4, 5, (128, 48)).astype(np.float32)
+    W = rng.integers(-4, 5, (96, 32)).astype(np.float32)
+    ig, chg = tile_image(G)
+    ix, chx = tile_image(X)
+    iw, chw = tile_image(W)
+    D = run(ig, ix, 128, 48, 8, (256, 128, chg), (256, 128, chx), 1, 1)              # G^T X over the 128 rows
+    assert np.array_equal(D, G.T @ X)
+    D = run(ig, iw, 128, 32, 6, (2 * chg, chg, 128), (256, 128, chw), 0, 1)          # G[:, :96] W with W stored [96][32]
+    assert np.array_equal(D, G[:, :96] @ W)
+    D = run(ix, iw, 128, 96, 2, (2 * chx, chx, 128), (2 * chw, chw, 128), 0, 0)      # X[:, :32] W^T
+    assert np.array_equal(D, X[:, :32] @ W.T)
