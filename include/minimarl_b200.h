@@ -516,6 +516,42 @@ int mm_ppo_trunk_bwd(const float* params, const int64_t* obs_row, int64_t obs_st
                      int32_t NO, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Second-generation fused trunk (csrc/ppo_trunk2.cu): the same function as mm_ppo_trunk_fwd / _bwd
+ * (R_Actor.evaluate_actions / R_Critic.forward in the chunked mode, mappo/algorithms/r_actor_critic.py:95-146,189-208,
+ * rnn.py:24-80; the update of mappo/algorithms/ramppo_network.py:103-209) with fp16 operands on tcgen05 (kind::f16, fp32
+ * accumulate), thread = row, several tiles in flight per SM and EVERY weight gradient contracted inside the backward kernel
+ * (G^T X as MN-major tcgen05.mma over the data path's own tiles, accumulated in TMEM) -- no X / G matrices, no GEMM afterwards.
+ *   mm_ppo_obs_table: LayerNorm (no affine) of observation rows, obs fp32 [rows, D] -> xhat fp16 [rows, 48] (zero padded);
+ *     once per update, shared by both networks and all epochs.
+ *   params: fp32 device buffer w1 [32][48] | w2 [32][32] | wih [96][32] | whh [96][32] | b1 [32] | b2 [32] | bih [96] | bhh [96] |
+ *     wo [8][32] | bo [8] with every LayerNorm affine folded into the Linear that follows it (W' = W diag(g), b' = b + W beta).
+ *   Chunks are addressed in place like recurrent_generator (shared_buffer.py:318-427): step t of chunk r is table row
+ *     first[r] + t * step_rows of xhat / masks; h0 is row first[r] of a [rows, 32] table.
+ *   fwd: out [L, R, NO]; saved != NULL (training): mm_ppo_trunk2_dims()[1] bytes per (128-row tile, step) of operand images
+ *     (normalised activations, masked input state, 1 / sigma and ReLU bits) for the backward.
+ *   bwd: dout [L, R, NO]; scale: device float, power of two applied to dout inside the kernel (fp16 range); acc
+ *     [n_acc_ctas >= mm_ppo_trunk2_bwd_ctas(R)][128][dims[2]]: per CTA the TMEM accumulators
+ *       columns [0, dims[3]):  lanes dr | dz | dn_i | dn_h (32 each)  x  xh2 [0,32) | hp [32,64) | 1 [64]
+ *       columns [dims[3], ..): lanes dA1 | dA2 | xh3 (32 each) | 1 [96]  x  x0 [0,48) | xh1 [48,80) | dout [80,88) | 1 [95]
+ *     i.e. scale * (gradients of the folded weights and biases); the caller sums over CTAs and unfolds the LayerNorm affines.
+ *   mm_ppo_trunk2_dims -> {parameter count, saved bytes per (tile, step), accumulator columns, columns of the first
+ *     accumulator, tile rows, 48, 8, 32};  mm_ppo_trunk2_set_slots: tiles in flight per SM (tuning; 0 = keep).
+ * ---------------------------------------------------------------------------------------------- */
+int mm_ppo_trunk2_dims(int32_t* dims8);
+int mm_ppo_trunk2_set_slots(int32_t fwd_slots, int32_t bwd_slots);
+int mm_ppo_trunk2_bwd_ctas(int64_t R);
+/* Debug: page-locked host int32[4]; a bounded wait inside the trunk kernels that times out writes {code, block, thread, 1} there
+ * before it traps (NULL = off). */
+int mm_ppo_trunk2_set_debug(void* host_mapped_int4);
+int mm_ppo_obs_table(const float* obs, void* xhat_f16, int64_t rows, int32_t D, void* stream);
+int mm_ppo_trunk2_fwd(const float* params, const void* xhat_f16, const int64_t* first, int64_t step_rows, const float* h0,
+                      const float* masks, float* out, float* h_final, void* saved, int32_t L, int64_t R, int32_t NO,
+                      void* stream);
+int mm_ppo_trunk2_bwd(const float* params, const void* xhat_f16, const int64_t* first, int64_t step_rows, const float* masks,
+                      const void* saved, const float* dout, const float* scale, float* acc, int32_t n_acc_ctas, int32_t L,
+                      int64_t R, int32_t NO, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * PPO losses of R_MAPPO.ppo_update / cal_value_loss (mappo/algorithms/ramppo_network.py:70-171), one pass each.
  * Rows R = minibatch entries; every per-row input is a float32 vector of length R (logits [R, NA], NA <= 8);
  * active == NULL means weight 1.

@@ -521,11 +521,12 @@ class R_MAPPO:
         advantages = ((advantages - mean_advantages) / (std_advantages + 1e-5)).to(torch.float32)
 
         train_info = dict(value_loss=0, policy_loss=0, dist_entropy=0, actor_grad_norm=0, critic_grad_norm=0, ratio=0)
+        tables = {}                    # normalised observation tables of this update (built on first use by the fused trunk)
         for epoch in range(self.ppo_epoch):
             perm = None if perms is None else perms[epoch]
             if self._use_recurrent_policy:
                 gen = buffer.recurrent_generator(advantages, self.train_batch_size, self.data_chunk_length, perm=perm,
-                                                 lazy_obs=self._fused_loss)
+                                                 lazy_obs=self._fused_loss, tables=tables)
             elif self._use_naive_recurrent:
                 gen = buffer.naive_recurrent_generator(advantages, self.train_batch_size, perm=perm)
             else:

@@ -140,7 +140,7 @@ class SharedReplayBuffer(object):
             yield (share_obs[ind], obs[ind], rnn_states[ind], rnn_states_critic[ind], actions[ind],
                    value_preds[ind], returns[ind], masks[ind], active_masks[ind], log_probs[ind], adv[ind], None)
 
-    def recurrent_generator(self, advantages, num_mini_batch, data_chunk_length, perm=None, lazy_obs=False):
+    def recurrent_generator(self, advantages, num_mini_batch, data_chunk_length, perm=None, lazy_obs=False, tables=None):
         """Chunks of L consecutive rows of the (env, agent, time)-major flattening, shuffled
         (shared_buffer.py:318-427).  Row f of that flattening is storage element [t, env, agent] with
         env = f // (A*T), agent = (f // T) % A, t = f % T, so the chunks are gathered straight from the
@@ -162,9 +162,10 @@ class SharedReplayBuffer(object):
                 # of a [T(+1), N, A, F] tensor, N * A rows per step) serves all eleven fields, nothing is gathered
                 from ..nn.ppo_trunk import ChunkRows
                 first = (t0 * N + env0) * A + agent0
-                rows = lambda x: ChunkRows(x.reshape(-1, x.shape[-1]), first, N * A, L)
+                rows = lambda x, key=None: ChunkRows(x.reshape(-1, x.shape[-1]), first, N * A, L, tables, key)
                 state = lambda x: ChunkRows(x.reshape(-1, *x.shape[3:]), first, N * A, 1)
-                yield (rows(self.share_obs), rows(self.obs), state(self.rnn_states), state(self.rnn_states_critic),
+                # ``tables`` (a dict owned by the caller, one per update) keeps the normalised fp16 observation tables
+                yield (rows(self.share_obs, "share_obs"), rows(self.obs, "obs"), state(self.rnn_states), state(self.rnn_states_critic),
                        rows(self.actions), rows(self.value_preds), rows(self.returns), rows(self.masks),
                        rows(self.active_masks), rows(self.action_log_probs), rows(adv), None)
                 continue
