@@ -522,7 +522,9 @@ int mm_ppo_trunk_bwd(const float* params, const int64_t* obs_row, int64_t obs_st
  * accumulate), thread = row, several tiles in flight per SM and EVERY weight gradient contracted inside the backward kernel
  * (G^T X as MN-major tcgen05.mma over the data path's own tiles, accumulated in TMEM) -- no X / G matrices, no GEMM afterwards.
  *   mm_ppo_obs_table: LayerNorm (no affine) of observation rows, obs fp32 [rows, D] -> xhat fp16 [rows, 48] (zero padded);
- *     once per update, shared by both networks and all epochs.
+ *     once per update, shared by both networks and all epochs.  masks != NULL (D < 48): masks[row] rides in column 47 (the
+ *     folded first Linear has a zero there) and the kernels, called with mask_in_table = 1, read it from the 32-byte sector
+ *     their observation gather fetches anyway instead of gathering 4 bytes per row and step from the mask table.
  *   params: fp32 device buffer w1 [32][48] | w2 [32][32] | wih [96][32] | whh [96][32] | b1 [32] | b2 [32] | bih [96] | bhh [96] |
  *     wo [8][32] | bo [8] with every LayerNorm affine folded into the Linear that follows it (W' = W diag(g), b' = b + W beta).
  *   Chunks are addressed in place like recurrent_generator (shared_buffer.py:318-427): step t of chunk r is table row
@@ -543,13 +545,24 @@ int mm_ppo_trunk2_bwd_ctas(int64_t R);
 /* Debug: page-locked host int32[4]; a bounded wait inside the trunk kernels that times out writes {code, block, thread, 1} there
  * before it traps (NULL = off). */
 int mm_ppo_trunk2_set_debug(void* host_mapped_int4);
-int mm_ppo_obs_table(const float* obs, void* xhat_f16, int64_t rows, int32_t D, void* stream);
+int mm_ppo_obs_table(const float* obs, const float* masks, void* xhat_f16, int64_t rows, int32_t D, void* stream);
+/* The algebra around the two kernels as one launch each.  params18: HOST array of the 18 device pointers ln0_w, ln0_b, w1 [32][D],
+ * b1, ln1_w, ln1_b, w2, b2, ln2_w, ln2_b, wih, whh, bih, bhh, ln3_w, ln3_b, wo [NO][32], bo (the module's own tensors).
+ *   pack: folds the LayerNorm affines -> packed kernel parameters (dims[0] floats).
+ *   unfold: sums acc over the CTAs, applies 1 / scale and unfolds the affines -> the 18 gradients back to back in grads
+ *     (offsets from mm_ppo_trunk2_grad_layout, 19 entries); red: scratch of 128 * dims[2] floats. */
+/* scale2 (device float[2]): [0] <- 2^floor(log2(64 / max |dout|)), the gradient scale mm_ppo_trunk2_bwd takes; [1] is scratch. */
+int mm_ppo_trunk2_scale(const float* dout, int64_t n, float* scale2, void* stream);
+int mm_ppo_trunk2_pack(const void* const* params18, float* packed, int32_t D, int32_t NO, void* stream);
+int mm_ppo_trunk2_grad_layout(int32_t D, int32_t NO, int32_t* offsets19);
+int mm_ppo_trunk2_unfold(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params18,
+                         float* grads, int32_t D, int32_t NO, void* stream);
 int mm_ppo_trunk2_fwd(const float* params, const void* xhat_f16, const int64_t* first, int64_t step_rows, const float* h0,
-                      const float* masks, float* out, float* h_final, void* saved, int32_t L, int64_t R, int32_t NO,
-                      void* stream);
+                      const float* masks, int32_t mask_in_table, float* out, float* h_final, void* saved, int32_t L, int64_t R,
+                      int32_t NO, void* stream);
 int mm_ppo_trunk2_bwd(const float* params, const void* xhat_f16, const int64_t* first, int64_t step_rows, const float* masks,
-                      const void* saved, const float* dout, const float* scale, float* acc, int32_t n_acc_ctas, int32_t L,
-                      int64_t R, int32_t NO, void* stream);
+                      int32_t mask_in_table, const void* saved, const float* dout, const float* scale, float* acc,
+                      int32_t n_acc_ctas, int32_t L, int64_t R, int32_t NO, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PPO losses of R_MAPPO.ppo_update / cal_value_loss (mappo/algorithms/ramppo_network.py:70-171), one pass each.

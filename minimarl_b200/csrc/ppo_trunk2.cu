@@ -129,6 +129,7 @@ struct Args {
     const float* scale;        // device float: power-of-two gradient scale                      (backward)
     float* acc;                // [grid][128][ACC_COLS]                                          (backward)
     int L, NO;
+    int mask_in_table;         // masks ride in column K1 - 1 of xhat (D < K1): no separate 4-byte gather per row and step
     long long R, n_tiles;
 };
 
@@ -322,7 +323,8 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_fwd_kernel(const 
                 }
             }
             for (int t = 0; t < a.L; ++t) {
-                const float mask = a.masks ? a.masks[my_first + (long long)t * a.step_rows] : 1.0f;
+                const float mask = a.mask_in_table ? __half2float(a.xhat[(my_first + (long long)t * a.step_rows) * K1 + K1 - 1])
+                                                     : a.masks ? a.masks[my_first + (long long)t * a.step_rows] : 1.0f;
                 // ---- S0: masked input state -> [xh2 | hp] tile (chunks 4..7); observations landed -> fc1 -------------------
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -657,7 +659,8 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_bwd_kernel(const 
             for (int j = 0; j < H; ++j) carry[j] = 0.f;
 
             for (int t = a.L - 1; t >= 0; --t) {
-                const float mask = a.masks ? a.masks[my_first + (long long)t * a.step_rows] : 1.0f;
+                const float mask = a.mask_in_table ? __half2float(a.xhat[(my_first + (long long)t * a.step_rows) * K1 + K1 - 1])
+                                                     : a.masks ? a.masks[my_first + (long long)t * a.step_rows] : 1.0f;
                 float dO[NOMAX];
                 {
                     const float* drow = a.dout + ((long long)t * a.R + grow) * a.NO;
@@ -885,8 +888,8 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_bwd_kernel(const 
 }
 
 // LayerNorm(D) without affine of every observation row, once per update: fp32 [rows][D] -> fp16 [rows][K1], zero padded
-__global__ void __launch_bounds__(256) obs_table_kernel(const float* __restrict__ obs, __half* __restrict__ out, long long rows,
-                                                        int D) {
+__global__ void __launch_bounds__(256) obs_table_kernel(const float* __restrict__ obs, const float* __restrict__ masks,
+                                                        __half* __restrict__ out, long long rows, int D) {
     const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
@@ -903,7 +906,185 @@ __global__ void __launch_bounds__(256) obs_table_kernel(const float* __restrict_
     const float rstd = rsqrtf(q / D + kEps);
     __half* dst = out + r * K1;
     dst[lane] = __float2half_rn(d0 * rstd);
-    if (lane + 32 < K1) dst[lane + 32] = __float2half_rn(d1 * rstd);
+    if (lane + 32 < K1) dst[lane + 32] = (masks && lane + 32 == K1 - 1) ? __float2half_rn(masks[r]) : __float2half_rn(d1 * rstd);
+}
+
+// ---- host-side algebra as two launches: folding the LayerNorm affines into the kernel parameters, and (after the backward)
+// summing the per-CTA accumulators and unfolding them into the gradients of the module's own parameters ----------------------
+// parameter tensors in the order of nn/ppo_trunk.py PARAM_ORDER
+enum { Q_LN0W, Q_LN0B, Q_W1, Q_B1, Q_LN1W, Q_LN1B, Q_W2, Q_B2, Q_LN2W, Q_LN2B, Q_WIH, Q_WHH, Q_BIH, Q_BHH, Q_LN3W, Q_LN3B, Q_WO, Q_BO, Q_N };
+struct ParamPtrs { const float* p[Q_N]; };
+
+__device__ __forceinline__ float dot_row(const float* w, const float* v, int n) {
+    float acc = 0.f;
+    for (int k = 0; k < n; ++k) acc = fmaf(w[k], v[k], acc);
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) trunk2_pack_kernel(const ParamPtrs q, float* __restrict__ out, int D, int NO) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= P_TOTAL) return;
+    float v;
+    if (i < P_W2) {
+        const int n = i / K1, k = i - n * K1;
+        v = k < D ? q.p[Q_W1][n * D + k] * q.p[Q_LN0W][k] : 0.f;
+    } else if (i < P_WIH) {
+        const int j = i - P_W2;
+        v = q.p[Q_W2][j] * q.p[Q_LN1W][j & (H - 1)];
+    } else if (i < P_WHH) {
+        const int j = i - P_WIH;
+        v = q.p[Q_WIH][j] * q.p[Q_LN2W][j & (H - 1)];
+    } else if (i < P_B1) {
+        v = q.p[Q_WHH][i - P_WHH];
+    } else if (i < P_B2) {
+        const int n = i - P_B1;
+        v = q.p[Q_B1][n] + dot_row(q.p[Q_W1] + n * D, q.p[Q_LN0B], D);
+    } else if (i < P_BIH) {
+        const int n = i - P_B2;
+        v = q.p[Q_B2][n] + dot_row(q.p[Q_W2] + n * H, q.p[Q_LN1B], H);
+    } else if (i < P_BHH) {
+        const int n = i - P_BIH;
+        v = q.p[Q_BIH][n] + dot_row(q.p[Q_WIH] + n * H, q.p[Q_LN2B], H);
+    } else if (i < P_WO) {
+        v = q.p[Q_BHH][i - P_BHH];
+    } else if (i < P_BO) {
+        const int j = i - P_WO, o = j / H;
+        v = o < NO ? q.p[Q_WO][j] * q.p[Q_LN3W][j & (H - 1)] : 0.f;
+    } else {
+        const int o = i - P_BO;
+        v = o < NO ? q.p[Q_BO][o] + dot_row(q.p[Q_WO] + o * H, q.p[Q_LN3B], H) : 0.f;
+    }
+    out[i] = v;
+}
+
+// gradient buffer: the eighteen tensors of PARAM_ORDER back to back (sizes depend on D and NO)
+struct GradLayout { int off[Q_N + 1]; };
+__host__ __device__ inline GradLayout grad_layout(int D, int NO) {
+    const int n[Q_N] = {D, D, H * D, H, H, H, H * H, H, H, H, 3 * H * H, 3 * H * H, 3 * H, 3 * H, H, H, NO * H, NO};
+    GradLayout g;
+    g.off[0] = 0;
+    for (int i = 0; i < Q_N; ++i) g.off[i + 1] = g.off[i] + n[i];
+    return g;
+}
+
+__device__ unsigned int g_unfold_ticket = 0;
+
+// grid x 256 threads: every CTA sums a slice of the [n_ctas][128][ACC_COLS] accumulators into `red`; the CTA that finishes
+// last (ticket counter) turns them into the parameter gradients (1 / scale applied, LayerNorm affines unfolded:
+// W' = W diag(g), b' = b + W beta  =>  dW = dW' diag(g) + db' beta^T, dg = sum_n dW'[n,:] W[n,:], dbeta = W^T db')
+__global__ void __launch_bounds__(256) trunk2_unfold_kernel(const float* __restrict__ acc, int n_ctas, const float* __restrict__ scale,
+                                                             float* __restrict__ red, const ParamPtrs q, float* __restrict__ grads,
+                                                             int D, int NO) {
+    __shared__ bool last;
+    const float inv = 1.0f / scale[0];
+    constexpr int kN = kRows * ACC_COLS;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < kN; i += gridDim.x * 256) {
+        float s0 = 0.f, s1 = 0.f;
+        int c = 0;
+        for (; c + 1 < n_ctas; c += 2) {
+            s0 += acc[(size_t)c * kN + i];
+            s1 += acc[(size_t)(c + 1) * kN + i];
+        }
+        if (c < n_ctas) s0 += acc[(size_t)c * kN + i];
+        red[i] = (s0 + s1) * inv;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&g_unfold_ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x == 0) g_unfold_ticket = 0;
+    const GradLayout L = grad_layout(D, NO);
+    const volatile float* r = red;
+    auto A = [&](int lane, int col) { return r[lane * ACC_COLS + col]; };
+    auto B = [&](int lane, int col) { return r[lane * ACC_COLS + ACC_A_COLS + col]; };
+    auto whh_lane = [](int g) { return g < 2 * H ? g : g + H; };      // dr | dz | (dn_i) | dn_h
+    const int tid = threadIdx.x;
+    // first Linear and LayerNorm(D)
+    for (int i = tid; i < H * D; i += 256) {
+        const int n = i / D, k = i - n * D;
+        grads[L.off[Q_W1] + i] = B(n, k) * q.p[Q_LN0W][k] + B(n, 95) * q.p[Q_LN0B][k];
+    }
+    for (int k = tid; k < D; k += 256) {
+        float gw = 0.f, gb = 0.f;
+        for (int n = 0; n < H; ++n) {
+            gw = fmaf(B(n, k), q.p[Q_W1][n * D + k], gw);
+            gb = fmaf(B(n, 95), q.p[Q_W1][n * D + k], gb);
+        }
+        grads[L.off[Q_LN0W] + k] = gw;
+        grads[L.off[Q_LN0B] + k] = gb;
+    }
+    // second Linear and LayerNorm 1
+    for (int i = tid; i < H * H; i += 256) {
+        const int n = i / H, k = i & (H - 1);
+        grads[L.off[Q_W2] + i] = B(H + n, 48 + k) * q.p[Q_LN1W][k] + B(H + n, 95) * q.p[Q_LN1B][k];
+    }
+    // GRU input weights and LayerNorm 2; hidden weights
+    for (int i = tid; i < 3 * H * H; i += 256) {
+        const int g = i / H, k = i & (H - 1);
+        grads[L.off[Q_WIH] + i] = A(g, k) * q.p[Q_LN2W][k] + A(g, 64) * q.p[Q_LN2B][k];
+        grads[L.off[Q_WHH] + i] = A(whh_lane(g), H + k);
+    }
+    for (int g = tid; g < 3 * H; g += 256) {
+        grads[L.off[Q_BIH] + g] = A(g, 64);
+        grads[L.off[Q_BHH] + g] = A(whh_lane(g), 64);
+    }
+    for (int k = tid; k < H; k += 256) {
+        grads[L.off[Q_B1] + k] = B(k, 95);
+        grads[L.off[Q_B2] + k] = B(H + k, 95);
+        float gw1 = 0.f, gb1 = 0.f, gw2 = 0.f, gb2 = 0.f, gw3 = 0.f, gb3 = 0.f;
+        for (int n = 0; n < H; ++n) {
+            gw1 = fmaf(B(H + n, 48 + k), q.p[Q_W2][n * H + k], gw1);
+            gb1 = fmaf(B(H + n, 95), q.p[Q_W2][n * H + k], gb1);
+        }
+        for (int g = 0; g < 3 * H; ++g) {
+            gw2 = fmaf(A(g, k), q.p[Q_WIH][g * H + k], gw2);
+            gb2 = fmaf(A(g, 64), q.p[Q_WIH][g * H + k], gb2);
+        }
+        for (int o = 0; o < NO; ++o) {
+            gw3 = fmaf(B(2 * H + k, 80 + o), q.p[Q_WO][o * H + k], gw3);
+            gb3 = fmaf(B(96, 80 + o), q.p[Q_WO][o * H + k], gb3);
+        }
+        grads[L.off[Q_LN1W] + k] = gw1; grads[L.off[Q_LN1B] + k] = gb1;
+        grads[L.off[Q_LN2W] + k] = gw2; grads[L.off[Q_LN2B] + k] = gb2;
+        grads[L.off[Q_LN3W] + k] = gw3; grads[L.off[Q_LN3B] + k] = gb3;
+    }
+    // head
+    for (int i = tid; i < NO * H; i += 256) {
+        const int o = i / H, k = i & (H - 1);
+        grads[L.off[Q_WO] + i] = B(2 * H + k, 80 + o) * q.p[Q_LN3W][k] + B(96, 80 + o) * q.p[Q_LN3B][k];
+    }
+    for (int o = tid; o < NO; o += 256) grads[L.off[Q_BO] + o] = B(96, 80 + o);
+}
+
+// power-of-two gradient scale from max |dout|: scale2[0] = 2^floor(log2(64 / max)), scale2[1] = bits of the maximum (zeroed by the
+// caller's memset); one pass over dout, the CTA that finishes last writes the scale
+__device__ unsigned int g_scale_ticket = 0;
+__global__ void __launch_bounds__(256) trunk2_scale_kernel(const float* __restrict__ dout, long long n, float* __restrict__ scale2) {
+    __shared__ bool last;
+    unsigned int m = 0;
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const float4 v = reinterpret_cast<const float4*>(dout)[i];
+        m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)), max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+    }
+    if (blockIdx.x == 0)
+        for (long long i = (n4 << 2) + threadIdx.x; i < n; i += 256) m = max(m, __float_as_uint(fabsf(dout[i])));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(MM_FULL_MASK, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(reinterpret_cast<unsigned int*>(scale2) + 1, m);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&g_scale_ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last || threadIdx.x) return;
+    __threadfence();
+    g_scale_ticket = 0;
+    const float amax = __uint_as_float(*(reinterpret_cast<volatile unsigned int*>(scale2) + 1));
+    int e = (amax > 0.f && amax < 3.0e38f) ? ilogbf(64.0f / fmaxf(amax, 1e-30f)) : 0;     // non-finite gradients stay non-finite
+    e = e < -60 ? -60 : e > 60 ? 60 : e;
+    scale2[0] = ldexpf(1.0f, e);
 }
 
 int n_sms() {
@@ -965,17 +1146,63 @@ extern "C" int mm_ppo_trunk2_bwd_ctas(int64_t R) {
     return (int)(want < n_sms() ? want : n_sms());
 }
 
-extern "C" int mm_ppo_obs_table(const float* obs, void* xhat, int64_t rows, int32_t D, void* stream) {
+// params18: HOST array of the 18 device pointers of nn/ppo_trunk.py PARAM_ORDER (ln0_w, ln0_b, w1, b1, ln1_w, ln1_b, w2, b2, ln2_w,
+// ln2_b, wih, whh, bih, bhh, ln3_w, ln3_b, wo, bo; w1 is [32][D], wo [NO][32]) -> packed kernel parameters (dims[0] floats)
+extern "C" int mm_ppo_trunk2_pack(const void* const* params18, float* packed, int32_t D, int32_t NO, void* stream) {
+    if (!params18 || !packed || D < 1 || D > K1 || NO < 1 || NO > NOMAX) return MM_ERR_BAD_ARG;
+    ParamPtrs q;
+    for (int i = 0; i < Q_N; ++i) {
+        if (!params18[i]) return MM_ERR_BAD_ARG;
+        q.p[i] = static_cast<const float*>(params18[i]);
+    }
+    trunk2_pack_kernel<<<(P_TOTAL + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, packed, D, NO);
+    return mm::check_launch();
+}
+
+// scale2: device float[2]; [0] receives the power of two that puts max |dout| at 64 (what mm_ppo_trunk2_bwd takes as `scale`)
+extern "C" int mm_ppo_trunk2_scale(const float* dout, int64_t n, float* scale2, void* stream) {
+    if (!dout || !scale2 || n <= 0 || !mm::aligned(dout, 16)) return MM_ERR_BAD_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(scale2, 0, 8, st);
+    if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
+    const long long want = (n / 4 + 255) / 256;
+    trunk2_scale_kernel<<<(unsigned)(want < 2 * n_sms() ? (want ? want : 1) : 2 * n_sms()), 256, 0, st>>>(dout, n, scale2);
+    return mm::check_launch();
+}
+
+// number of floats of the gradient buffer mm_ppo_trunk2_unfold fills, and the 19 offsets of its 18 tensors
+extern "C" int mm_ppo_trunk2_grad_layout(int32_t D, int32_t NO, int32_t* offsets19) {
+    if (!offsets19 || D < 1 || D > K1 || NO < 1 || NO > NOMAX) return MM_ERR_BAD_ARG;
+    const GradLayout g = grad_layout(D, NO);
+    for (int i = 0; i <= Q_N; ++i) offsets19[i] = g.off[i];
+    return MM_OK;
+}
+
+// acc [n_ctas][128][dims[2]] from mm_ppo_trunk2_bwd -> gradients of the module parameters (PARAM_ORDER, back to back in grads);
+// red: scratch of 128 * dims[2] floats
+extern "C" int mm_ppo_trunk2_unfold(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params18,
+                                    float* grads, int32_t D, int32_t NO, void* stream) {
+    if (!acc || !scale || !red || !params18 || !grads || n_ctas < 1 || D < 1 || D > K1 || NO < 1 || NO > NOMAX) return MM_ERR_BAD_ARG;
+    ParamPtrs q;
+    for (int i = 0; i < Q_N; ++i) {
+        if (!params18[i]) return MM_ERR_BAD_ARG;
+        q.p[i] = static_cast<const float*>(params18[i]);
+    }
+    trunk2_unfold_kernel<<<44, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, grads, D, NO);
+    return mm::check_launch();
+}
+
+extern "C" int mm_ppo_obs_table(const float* obs, const float* masks, void* xhat, int64_t rows, int32_t D, void* stream) {
     if (!obs || !xhat || rows <= 0 || D < 1 || D > K1) return MM_ERR_BAD_ARG;
-    if (!mm::aligned(xhat, 16)) return MM_ERR_BAD_ARG;
-    obs_table_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(obs, static_cast<__half*>(xhat),
+    if (!mm::aligned(xhat, 16) || (masks && D >= K1)) return MM_ERR_BAD_ARG;
+    obs_table_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(obs, masks, static_cast<__half*>(xhat),
                                                                                                   rows, D);
     return mm::check_launch();
 }
 
 extern "C" int mm_ppo_trunk2_fwd(const float* params, const void* xhat, const int64_t* first, int64_t step_rows, const float* h0,
-                                 const float* masks, float* out, float* h_final, void* saved, int32_t L, int64_t R, int32_t NO,
-                                 void* stream) {
+                                 const float* masks, int32_t mask_in_table, float* out, float* h_final, void* saved, int32_t L,
+                                 int64_t R, int32_t NO, void* stream) {
     if (!params || !xhat || !first || !h0 || !out || L <= 0 || R <= 0) return MM_ERR_BAD_ARG;
     if (NO < 1 || NO > NOMAX) return MM_ERR_UNSUPPORTED;
     if (!mm::aligned(xhat, 16) || !mm::aligned(h0, 16) || (saved && !mm::aligned(saved, 16)) ||
@@ -983,7 +1210,7 @@ extern "C" int mm_ppo_trunk2_fwd(const float* params, const void* xhat, const in
         return MM_ERR_BAD_ARG;
     Args a{};
     a.params = params; a.xhat = static_cast<const __half*>(xhat); a.first = reinterpret_cast<const long long*>(first);
-    a.step_rows = step_rows; a.h0 = h0; a.masks = masks; a.out = out; a.h_final = h_final;
+    a.step_rows = step_rows; a.h0 = h0; a.masks = masks; a.mask_in_table = mask_in_table; a.out = out; a.h_final = h_final;
     a.saved = static_cast<uint8_t*>(saved);
     a.L = L; a.NO = NO; a.R = R; a.n_tiles = (R + kRows - 1) / kRows;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -996,14 +1223,16 @@ extern "C" int mm_ppo_trunk2_fwd(const float* params, const void* xhat, const in
 }
 
 extern "C" int mm_ppo_trunk2_bwd(const float* params, const void* xhat, const int64_t* first, int64_t step_rows,
-                                 const float* masks, const void* saved, const float* dout, const float* scale, float* acc,
-                                 int32_t n_acc_ctas, int32_t L, int64_t R, int32_t NO, void* stream) {
+                                 const float* masks, int32_t mask_in_table, const void* saved, const float* dout,
+                                 const float* scale, float* acc, int32_t n_acc_ctas, int32_t L, int64_t R, int32_t NO,
+                                 void* stream) {
     if (!params || !xhat || !first || !saved || !dout || !scale || !acc || L <= 0 || R <= 0) return MM_ERR_BAD_ARG;
     if (NO < 1 || NO > NOMAX) return MM_ERR_UNSUPPORTED;
     if (!mm::aligned(xhat, 16) || !mm::aligned(saved, 16) || !mm::aligned(acc, 16)) return MM_ERR_BAD_ARG;
     Args a{};
     a.params = params; a.xhat = static_cast<const __half*>(xhat); a.first = reinterpret_cast<const long long*>(first);
-    a.step_rows = step_rows; a.masks = masks; a.saved = static_cast<uint8_t*>(const_cast<void*>(saved)); a.dout = dout;
+    a.step_rows = step_rows; a.masks = masks; a.mask_in_table = mask_in_table;
+    a.saved = static_cast<uint8_t*>(const_cast<void*>(saved)); a.dout = dout;
     a.scale = scale; a.acc = acc;
     a.L = L; a.NO = NO; a.R = R; a.n_tiles = (R + kRows - 1) / kRows;
     const int grid = mm_ppo_trunk2_bwd_ctas(R);

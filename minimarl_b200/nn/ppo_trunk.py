@@ -144,28 +144,45 @@ def dims2():
     return _DIMS2
 
 
-def obs_table(obs2d):
+def obs_table(obs2d, masks=None):
     """LayerNorm (no affine) of every observation row, fp16, zero padded to 48 columns: [rows, D] -> [rows, 48].  Computed once
-    per update; both networks and every epoch gather their chunk rows from it (mm_ppo_obs_table)."""
+    per update; both networks and every epoch gather their chunk rows from it (mm_ppo_obs_table).  With D < 48 the row's mask
+    rides in column 47 (``masks`` [rows]): the kernels then read it from the sector their gather fetches anyway."""
     obs2d = obs2d.contiguous()
     rows, D = obs2d.shape
+    if masks is not None and D >= K1:
+        masks = None
     out = torch.empty((rows, K1), dtype=torch.float16, device=obs2d.device)
-    _lib.check(_lib.lib().mm_ppo_obs_table(_lib.ptr(obs2d), _lib.ptr(out), rows, D, _lib.stream()))
+    _lib.check(_lib.lib().mm_ppo_obs_table(_lib.ptr(obs2d), _lib.ptr(masks), _lib.ptr(out), rows, D, _lib.stream()))
     return out
 
 
-def _pack2(p, D, NO):
-    """Kernel parameters with every LayerNorm affine folded into the Linear that follows it: W' = W diag(g), b' = b + W beta."""
-    dev = p["w1"].device
-    w1 = torch.zeros((H, K1), dtype=torch.float32, device=dev)
-    w1[:, :D] = p["w1"] * p["ln0_w"]
-    wo = torch.zeros((NOMAX, H), dtype=torch.float32, device=dev)
-    wo[:NO] = p["wo"] * p["ln3_w"]
-    bo = torch.zeros(NOMAX, dtype=torch.float32, device=dev)
-    bo[:NO] = p["bo"] + p["wo"] @ p["ln3_b"]
-    return torch.cat([w1.reshape(-1), (p["w2"] * p["ln1_w"]).reshape(-1), (p["wih"] * p["ln2_w"]).reshape(-1),
-                      p["whh"].reshape(-1), p["b1"] + p["w1"] @ p["ln0_b"], p["b2"] + p["w2"] @ p["ln1_b"],
-                      p["bih"] + p["wih"] @ p["ln2_b"], p["bhh"], wo.reshape(-1), bo])
+def _ptr_array(params):
+    """HOST array of the 18 device pointers (PARAM_ORDER) the pack / unfold launches take."""
+    arr = (C.c_void_p * len(PARAM_ORDER))()
+    for i, t in enumerate(params):
+        assert t.is_contiguous() and t.dtype == torch.float32
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _pack2(params, D, NO):
+    """Kernel parameters with every LayerNorm affine folded into the Linear that follows it (W' = W diag(g), b' = b + W beta):
+    one launch (mm_ppo_trunk2_pack)."""
+    out = torch.empty(dims2()["n_params"], dtype=torch.float32, device=params[0].device)
+    _lib.check(_lib.lib().mm_ppo_trunk2_pack(_ptr_array(params), _lib.ptr(out), D, NO, _lib.stream()))
+    return out
+
+
+_GRAD_LAYOUT = {}
+
+
+def _grad_layout(D, NO):
+    if (D, NO) not in _GRAD_LAYOUT:
+        o = (C.c_int32 * (len(PARAM_ORDER) + 1))()
+        _lib.check(_lib.lib().mm_ppo_trunk2_grad_layout(D, NO, o))
+        _GRAD_LAYOUT[(D, NO)] = list(o)
+    return _GRAD_LAYOUT[(D, NO)]
 
 
 class _PPOTrunkFn(torch.autograd.Function):
@@ -173,20 +190,22 @@ class _PPOTrunkFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xhat, h0, masks, first, step_rows, L, D, *params):
+        # masks None and D < 48: the masks ride in column 47 of xhat
         p = dict(zip(PARAM_ORDER, params))
         R, NO = first.numel(), p["wo"].shape[0]
         d = dims2()
-        with torch.no_grad():
-            packed = _pack2(p, D, NO)
-        assert packed.numel() == d["n_params"]
+        params = [t.detach().contiguous() for t in params]
+        packed = _pack2(params, D, NO)
         out = torch.empty((L, R, NO), dtype=torch.float32, device=xhat.device)
         train = any(ctx.needs_input_grad[7:])
         saved = None
         if train:
             n_tiles = (R + d["tile_rows"] - 1) // d["tile_rows"]
             saved = torch.empty(n_tiles * L * d["saved_bytes"], dtype=torch.uint8, device=xhat.device)
+        in_table = int(masks is None and D < K1)
         _lib.check(_lib.lib().mm_ppo_trunk2_fwd(_lib.ptr(packed), _lib.ptr(xhat), _lib.ptr(first), int(step_rows), _lib.ptr(h0),
-                                                _lib.ptr(masks), _lib.ptr(out), None, _lib.ptr(saved), L, R, NO, _lib.stream()))
+                                                _lib.ptr(masks), in_table, _lib.ptr(out), None, _lib.ptr(saved), L, R, NO,
+                                                _lib.stream()))
         if train:
             ctx.save_for_backward(packed, xhat, first, masks if masks is not None else packed.new_empty(0), saved, *params)
             ctx.dims = (L, R, D, NO, int(step_rows), masks is not None)
@@ -201,31 +220,22 @@ class _PPOTrunkFn(torch.autograd.Function):
         dout = dout.contiguous()
         # gradients travel as fp16 operands: a power-of-two scale puts max |dout| at 64 (fp16 overflows at 65 504, keeps 11 bits
         # down to 6e-5); the weight gradients come back multiplied by it
-        amax = dout.abs().amax().clamp_min(1e-30)
-        scale = torch.exp2(torch.floor(torch.log2(64.0 / amax))).clamp(2.0 ** -60, 2.0 ** 60)
+        scale = torch.empty(2, dtype=torch.float32, device=dout.device)
+        _lib.check(_lib.lib().mm_ppo_trunk2_scale(_lib.ptr(dout), dout.numel(), _lib.ptr(scale), _lib.stream()))
         n_ctas = _lib.lib().mm_ppo_trunk2_bwd_ctas(R)
         acc = torch.empty((n_ctas, d["tile_rows"], d["acc_cols"]), dtype=torch.float32, device=dout.device)
         _lib.check(_lib.lib().mm_ppo_trunk2_bwd(_lib.ptr(packed), _lib.ptr(xhat), _lib.ptr(first), step_rows,
-                                                _lib.ptr(masks if has_masks else None), _lib.ptr(saved), _lib.ptr(dout),
-                                                _lib.ptr(scale.reshape(1)), _lib.ptr(acc), n_ctas, L, R, NO, _lib.stream()))
-        acc = acc.sum(0) / scale
-        A, B = acc[:, :d["acc_a_cols"]], acc[:, d["acc_a_cols"]:]
-        # A: lanes dr | dz | dn_i | dn_h  x  columns xh2 [0,32) | hp [32,64) | 1 [64]
-        # B: lanes dA1 | dA2 | xh3 | 1 [96]  x  columns x0 [0,48) | xh1 [48,80) | dout [80,88) | 1 [95]
-        gwih, gbih = A[0:96, 0:32], A[0:96, 64]
-        gwhh = torch.cat([A[0:64, 32:64], A[96:128, 32:64]], 0)
-        gbhh = torch.cat([A[0:64, 64], A[96:128, 64]])
-        gw1, gb1 = B[0:32, 0:D], B[0:32, 95]
-        gw2, gb2 = B[32:64, 48:80], B[32:64, 95]
-        gwo, gbo = B[64:96, 80:80 + NO].t(), B[96, 80:80 + NO]
-        # unfold W' = W diag(g), b' = b + W beta:  dW = dW' diag(g) + outer(db', beta), dg = sum_n dW'[n, :] W[n, :], dbeta = W^T db'
-        unfold = lambda gw, gb, w, g, b: (gw * g + torch.outer(gb, b), (gw * w).sum(0), w.t() @ gb)
-        dw1, dg0, db0 = unfold(gw1, gb1, p["w1"], p["ln0_w"], p["ln0_b"])
-        dw2, dg1, db1 = unfold(gw2, gb2, p["w2"], p["ln1_w"], p["ln1_b"])
-        dwih, dg2, db2 = unfold(gwih, gbih, p["wih"], p["ln2_w"], p["ln2_b"])
-        dwo, dg3, db3 = unfold(gwo, gbo, p["wo"], p["ln3_w"], p["ln3_b"])
-        grads = dict(ln0_w=dg0, ln0_b=db0, w1=dw1, b1=gb1, ln1_w=dg1, ln1_b=db1, w2=dw2, b2=gb2, ln2_w=dg2, ln2_b=db2,
-                     wih=dwih, whh=gwhh, bih=gbih, bhh=gbhh, ln3_w=dg3, ln3_b=db3, wo=dwo, bo=gbo)
+                                                _lib.ptr(masks if has_masks else None), int(not has_masks and D < K1),
+                                                _lib.ptr(saved), _lib.ptr(dout),
+                                                _lib.ptr(scale), _lib.ptr(acc), n_ctas, L, R, NO, _lib.stream()))
+        # one launch: sum over the CTAs, 1 / scale, LayerNorm affines unfolded into the gradients of the module's own tensors
+        off = _grad_layout(D, NO)
+        flat = torch.empty(off[-1], dtype=torch.float32, device=dout.device)
+        red = torch.empty(d["tile_rows"] * d["acc_cols"], dtype=torch.float32, device=dout.device)
+        params = [p[k].detach().contiguous() for k in PARAM_ORDER]
+        _lib.check(_lib.lib().mm_ppo_trunk2_unfold(_lib.ptr(acc), n_ctas, _lib.ptr(scale), _lib.ptr(red),
+                                                   _ptr_array(params), _lib.ptr(flat), D, NO, _lib.stream()))
+        grads = {k: flat[off[i]: off[i + 1]].view_as(p[k]) for i, k in enumerate(PARAM_ORDER)}
         return (None,) * 7 + tuple(grads[k] if ctx.needs_input_grad[7 + i] else None for i, k in enumerate(PARAM_ORDER))
 
 
@@ -238,12 +248,13 @@ class ChunkRows:
         self.table, self.first, self.step_rows, self.L = table, first, int(step_rows), int(L)
         self.cache, self.key = cache, key
 
-    def xhat(self):
+    def xhat(self, masks=None):
+        """The normalised fp16 table of this storage, with ``masks`` [rows] embedded (kept in ``cache`` for the whole update)."""
         if self.cache is None:
-            return obs_table(self.table)
+            return obs_table(self.table, masks)
         t = self.cache.get(self.key)
         if t is None:
-            t = self.cache[self.key] = obs_table(self.table)
+            t = self.cache[self.key] = obs_table(self.table, masks)
         return t
 
     def size(self, dim):
@@ -274,9 +285,14 @@ def ppo_trunk(obs, h0, masks, params):
         if not isinstance(h0, ChunkRows):        # only the observations are addressed in place: gather would defeat it
             raise TypeError("with ChunkRows observations, h0 and masks must be ChunkRows of the same row map")
         assert h0.first is obs.first and masks.first is obs.first and masks.step_rows == obs.step_rows
-        return _PPOTrunkFn.apply(obs.xhat(), h0.table.contiguous(), masks.table.reshape(-1), obs.first.contiguous(),
-                                 obs.step_rows, obs.L, obs.table.shape[-1], *ps)
+        D = obs.table.shape[-1]
+        mt = masks.table.reshape(-1)
+        return _PPOTrunkFn.apply(obs.xhat(mt), h0.table.contiguous(), mt if D >= K1 else None, obs.first.contiguous(),
+                                 obs.step_rows, obs.L, D, *ps)
     L, R, D = obs.shape
     first = torch.arange(R, device=obs.device, dtype=torch.int64)
-    masks = masks.contiguous().reshape(-1) if masks is not None else None
-    return _PPOTrunkFn.apply(obs_table(obs.reshape(L * R, D)), h0.contiguous(), masks, first, R, L, D, *ps)
+    if masks is None:
+        masks = torch.ones((L, R), dtype=torch.float32, device=obs.device)
+    masks = masks.contiguous().reshape(-1)
+    return _PPOTrunkFn.apply(obs_table(obs.reshape(L * R, D), masks), h0.contiguous(), masks if D >= K1 else None, first, R, L, D,
+                             *ps)
