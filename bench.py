@@ -342,7 +342,8 @@ def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
         "ppo_update_samples_per_s": world * n_envs * T * AGENTS * args.ppo_epoch / (ms[2] * 1e-3),
         "config": {"n_envs_per_gpu": n_envs, "T": T, "agents": AGENTS, "ppo_epoch": args.ppo_epoch, "num_mini_batch": 1,
                    "data_chunk_length": 8, "hidden": 32, "fused_rollout": bool(r.fused_rollout),
-                   "fused_update": "tcgen05 trunk fwd/bwd + loss kernels", "precision": "tf32 operands, fp32 accumulate",
+                   "fused_update": "trunk2 fwd/bwd (tcgen05 kind::f16, weight gradients in the kernel) + loss kernels",
+                   "precision": "fp16 operands (11-bit significand, as tf32), fp32 accumulate",
                    "grad_allreduce": "NCCL, one flattened bucket per optimiser step" if world > 1 else None},
         "train_info": {k: float(v) for k, v in infos.items()},
         "peak_mem_GiB": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
@@ -350,9 +351,15 @@ def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
     # useful math of the update: (17.7 + 17.4) kFLOP per row forward, x3 with the backward, all rows, all epochs
     flops = n_envs * T * AGENTS * (17.7e3 + 17.4e3) * 3 * args.ppo_epoch
     peak_tc, peak_src = tf32_peak_tflops()
-    out["roofline"] = {"bound": "tensor", "kernel": "ppo_trunk_kernel<fwd/bwd>", "achieved": flops / (ms[2] * 1e-3) / 1e12,
+    peak_tc, peak_src = 2 * peak_tc, peak_src.replace(" / 2", "") + " (fp16 operands)"
+    # HBM side of the same kernels: per network pass the forward reads the fp16 observation rows (96 B) and writes the saved operand
+    # images (208 B) and the head outputs, the backward reads both again plus the head gradients
+    hbm_bytes = n_envs * T * AGENTS * (96 + 208 + 20 + 96 + 208 + 20) * 2 * args.ppo_epoch
+    out["roofline"] = {"bound": "tensor", "kernel": "trunk2_fwd_kernel / trunk2_bwd_kernel", "achieved": flops / (ms[2] * 1e-3) / 1e12,
                        "peak": peak_tc, "peak_source": peak_src, "unit": "TFLOP/s", "frac": flops / (ms[2] * 1e-3) / 1e12 / peak_tc,
-                       "useful_flop_per_update": flops}
+                       "useful_flop_per_update": flops, "hbm_GBs": hbm_bytes / (ms[2] * 1e-3) / 1e9,
+                       "hbm_frac": hbm_bytes / (ms[2] * 1e-3) / 1e9 / measured_peaks()[0],
+                       "what_bounds": "instruction issue of the per-row epilogues (ncu: issue slots 46 % / 35 % busy, tensor pipe 6 % / 12 %)"}
     del r, env
     torch.cuda.empty_cache()
     return out
@@ -806,7 +813,8 @@ def run_ours(args, wl):
                 "qmix_gather_frac_of_hbm": g(learner, "roofline", "hbm_gather", "frac"),
                 "mappo_iteration_ms": g(mappo_it, "ms_per_iteration"), "mappo_ms_rollout": g(mappo_it, "ms_rollout"),
                 "mappo_ms_ppo_update": g(mappo_it, "ms_ppo_update"), "mappo_agent_steps_per_s": g(mappo_it, "value"),
-                "mappo_update_tflops_frac_of_tf32_peak": g(mappo_it, "roofline", "frac"),
+                "mappo_update_tflops_frac_of_fp16_peak": g(mappo_it, "roofline", "frac"),
+                "mappo_update_frac_of_hbm": g(mappo_it, "roofline", "hbm_frac"),
                 "toplevel_qmix_rollout_agent_steps_per_s": g(sections["qmix_toplevel"], "rollout_agent_steps_per_s"),
                 "toplevel_qmix_train_samples_per_s": g(sections["qmix_toplevel"], "train_samples_per_s"),
                 "toplevel_qmix_train_ms_per_call": g(sections["qmix_toplevel"], "train_ms_per_call"),

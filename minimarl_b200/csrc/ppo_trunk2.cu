@@ -86,6 +86,82 @@ __device__ __forceinline__ void load_chunk(const uint8_t* tile, int chunk, int r
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
 
+// Row reductions as four independent chains: a 32-long dependent chain of FADD / FFMA is 128 cycles of pure latency for a warp
+// that has one or two neighbours on its scheduler, and nvcc does not reassociate floating-point sums.
+__device__ __forceinline__ float sum32(const float (&v)[H]) {
+    float s0 = v[0], s1 = v[1], s2 = v[2], s3 = v[3];
+#pragma unroll
+    for (int j = 4; j < H; j += 4) { s0 += v[j]; s1 += v[j + 1]; s2 += v[j + 2]; s3 += v[j + 3]; }
+    return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ float dot32(const float (&a)[H], const float (&b)[H]) {
+    float s0 = a[0] * b[0], s1 = a[1] * b[1], s2 = a[2] * b[2], s3 = a[3] * b[3];
+#pragma unroll
+    for (int j = 4; j < H; j += 4) {
+        s0 = fmaf(a[j], b[j], s0); s1 = fmaf(a[j + 1], b[j + 1], s1); s2 = fmaf(a[j + 2], b[j + 2], s2); s3 = fmaf(a[j + 3], b[j + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+// v -> (v - mean) * rstd in place, returns rstd (biased variance, eps inside the root: torch.nn.LayerNorm)
+__device__ __forceinline__ float normalise32(float (&v)[H]) {
+    const float mean = sum32(v) * (1.0f / H);
+#pragma unroll
+    for (int j = 0; j < H; ++j) v[j] -= mean;
+    const float rstd = rsqrtf(dot32(v, v) * (1.0f / H) + kEps);
+#pragma unroll
+    for (int j = 0; j < H; ++j) v[j] *= rstd;
+    return rstd;
+}
+// v -> LayerNorm(ReLU(v + b)) without affine; the bits of `relu` mark the positive pre-activations
+__device__ __forceinline__ float bias_relu_norm32(float (&v)[H], const float4* b4, uint32_t& relu) {
+    relu = 0;
+#pragma unroll
+    for (int j = 0; j < H / 4; ++j) {
+        const float4 b = b4[j];
+        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float x = v[4 * j + u] + bb[u];
+            const bool pos = x > 0.f;
+            relu |= (uint32_t)pos << (4 * j + u);
+            v[4 * j + u] = pos ? x : 0.f;
+        }
+    }
+    return normalise32(v);
+}
+// backward of y = normalise(a) followed by ReLU's mask: dx (gradient wrt y) -> gradient wrt the pre-activation, in place
+__device__ __forceinline__ void norm_relu_bwd32(float (&dx)[H], const float (&xh)[H], float rstd, uint32_t relu) {
+    const float sg = sum32(dx) * (1.0f / H), sq = dot32(dx, xh) * (1.0f / H);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const float v = rstd * (dx[j] - sg - xh[j] * sq);
+        dx[j] = (relu >> j & 1u) ? v : 0.f;
+    }
+}
+// head: out[o] = bo[o] + <xh3, wo[o]> for o < N (rows of wo past the real head width are zero), four chains per output
+template <int N>
+__device__ __forceinline__ void head32(const float (&xh3)[H], const float* sP, float* orow, int NO, bool valid) {
+    const float4* w4 = reinterpret_cast<const float4*>(sP + S_WO);
+    float acc[N][4];
+#pragma unroll
+    for (int o = 0; o < N; ++o) { acc[o][0] = sP[S_BO + o]; acc[o][1] = acc[o][2] = acc[o][3] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < H / 4; ++j)
+#pragma unroll
+        for (int o = 0; o < N; ++o) {
+            const float4 w = w4[o * (H / 4) + j];
+            acc[o][0] = fmaf(xh3[4 * j], w.x, acc[o][0]);
+            acc[o][1] = fmaf(xh3[4 * j + 1], w.y, acc[o][1]);
+            acc[o][2] = fmaf(xh3[4 * j + 2], w.z, acc[o][2]);
+            acc[o][3] = fmaf(xh3[4 * j + 3], w.w, acc[o][3]);
+        }
+    if (valid) {
+#pragma unroll
+        for (int o = 0; o < N; ++o)
+            if (o < NO) orow[o] = (acc[o][0] + acc[o][1]) + (acc[o][2] + acc[o][3]);
+    }
+}
+
 // weight [N][K] fp32 (device) -> fp16 tile, chunk-major with N rows: (k / 8) * N * 16 + n * 16 + (k % 8) * 2
 __device__ __forceinline__ void stage_weight(uint8_t* dst, const float* src, int N, int K, int tid, int nthreads) {
     for (int i = tid; i < N * K; i += nthreads) {
@@ -194,7 +270,6 @@ template <int NSLOT>
 __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_fwd_kernel(const __grid_constant__ Args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_ready[NSLOT], bar_done[NSLOT];
-    __shared__ int4 ist[NSLOT];                  // issuer state per slot: {ready parity, phase, events left}
     __shared__ uint32_t tmem_slot;
     constexpr int kThreads = (NSLOT + 1) * 128;
     constexpr uint32_t kTmemCols = NSLOT * 128 <= 128 ? 128 : NSLOT * 128 <= 256 ? 256 : 512;
@@ -223,51 +298,43 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_fwd_kernel(const 
     if (warp >= NSLOT * 4) {
         // ------------------------------------------------- MMA issuer ----------------------------------------------------
         reg_dec<kIssuerRegs>();
-        if (warp == NSLOT * 4 && lane == 0) {
+        // one issuer warp per slot (the warpgroup has four): it sleeps on its slot's "operands ready" barrier and answers with the
+        // phase's MMAs and a commit -- no accumulator is shared between slots in the forward, so no common instruction stream
+        const int s = warp - NSLOT * 4;
+        if (s < NSLOT && lane == 0) {
             const uint32_t w1 = tc::smem_u32(smem + F_W1), w2 = tc::smem_u32(smem + F_W2), wih = tc::smem_u32(smem + F_WIH),
                            whh = tc::smem_u32(smem + F_WHH);
             const uint32_t id32 = tc::make_idesc_f16(128, 32), id64 = tc::make_idesc_f16(128, 64);
-            // per-slot state (parity, phase, events left) lives in shared memory and the slot loop is not unrolled: descriptors
-            // are built when an event fires instead of being kept (and spilled) for every slot -- this warpgroup has 32 registers
-            int live = 0;
-            for (int s = 0; s < NSLOT; ++s) {
-                const int n = (int)tiles_of_slot(a.n_tiles, (long long)blockIdx.x * NSLOT + s, total_slots) * a.L * 3;
-                ist[s] = make_int4(0, 0, n, 0);
-                live += n > 0;
-            }
-            uint32_t spin = 0;
-            while (live) {
-#pragma unroll 1
-                for (int s = 0; s < NSLOT; ++s) {
-                    const int4 st = ist[s];
-                    if (st.z > 0 && tc::mbar_test(&bar_ready[s], (uint32_t)st.x)) {
-                        tc::fence_after_sync();
-                        const uint32_t base = tc::smem_u32(smem + F_SLOTS + s * FS_BYTES);
-                        const uint32_t x0 = base + FS_X0, xh1 = base + FS_SV + SV_XH1, xin = base + FS_SV + SV_IN;
-                        const uint32_t d = tmem + s * 128;
-                        if (st.y == 0) {                        // fc1: x0 [128 x 48] W1^T -> [0,32)
+            const uint32_t base = tc::smem_u32(smem + F_SLOTS + s * FS_BYTES);
+            const uint32_t x0 = base + FS_X0, xh1 = base + FS_SV + SV_XH1, xin = base + FS_SV + SV_IN;
+            const uint32_t d = tmem + s * 128;
+            const long long steps = tiles_of_slot(a.n_tiles, (long long)blockIdx.x * NSLOT + s, total_slots) * a.L;
+            uint32_t par = 0;
+            for (long long i = 0; i < steps; ++i) {
+                wait_bar(&bar_ready[s], par, 110 + s);              // fc1: x0 [128 x 48] W1^T -> [0,32)
+                par ^= 1;
+                tc::fence_after_sync();
 #pragma unroll
-                            for (int kk = 0; kk < 3; ++kk) tc::mma_f16(d, desc_k(x0, kk, CH), desc_k(w1, kk, H * 16), id32, kk > 0);
-                        } else if (st.y == 1) {                 // fc2: xh1 W2^T -> [32,64)
+                for (int kk = 0; kk < 3; ++kk) tc::mma_f16(d, desc_k(x0, kk, CH), desc_k(w1, kk, H * 16), id32, kk > 0);
+                tc::mma_commit(&bar_done[s]);
+                wait_bar(&bar_ready[s], par, 120 + s);              // fc2: xh1 W2^T -> [32,64)
+                par ^= 1;
+                tc::fence_after_sync();
 #pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) tc::mma_f16(d + 32, desc_k(xh1, kk, CH), desc_k(w2, kk, H * 16), id32, kk > 0);
-                        } else {                                // gates: r|z -> [64,128), i_n -> [0,32), h_n -> [32,64)
+                for (int kk = 0; kk < 2; ++kk) tc::mma_f16(d + 32, desc_k(xh1, kk, CH), desc_k(w2, kk, H * 16), id32, kk > 0);
+                tc::mma_commit(&bar_done[s]);
+                wait_bar(&bar_ready[s], par, 130 + s);              // gates: r|z -> [64,128), i_n -> [0,32), h_n -> [32,64)
+                par ^= 1;
+                tc::fence_after_sync();
 #pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) tc::mma_f16(d + 64, desc_k(xin, kk, CH), desc_k(wih, kk, 3 * H * 16), id64, kk > 0);
+                for (int kk = 0; kk < 2; ++kk) tc::mma_f16(d + 64, desc_k(xin, kk, CH), desc_k(wih, kk, 3 * H * 16), id64, kk > 0);
 #pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) tc::mma_f16(d + 64, desc_k(xin + 4 * CH, kk, CH), desc_k(whh, kk, 3 * H * 16), id64, true);
+                for (int kk = 0; kk < 2; ++kk) tc::mma_f16(d + 64, desc_k(xin + 4 * CH, kk, CH), desc_k(whh, kk, 3 * H * 16), id64, true);
 #pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) tc::mma_f16(d, desc_k(xin, kk, CH), desc_k(wih + 2 * H * 16, kk, 3 * H * 16), id32, kk > 0);
+                for (int kk = 0; kk < 2; ++kk) tc::mma_f16(d, desc_k(xin, kk, CH), desc_k(wih + 2 * H * 16, kk, 3 * H * 16), id32, kk > 0);
 #pragma unroll
-                            for (int kk = 0; kk < 2; ++kk) tc::mma_f16(d + 32, desc_k(xin + 4 * CH, kk, CH), desc_k(whh + 2 * H * 16, kk, 3 * H * 16), id32, kk > 0);
-                        }
-                        tc::mma_commit(&bar_done[s]);
-                        ist[s] = make_int4(st.x ^ 1, st.y == 2 ? 0 : st.y + 1, st.z - 1, 0);
-                        live -= st.z == 1;
-                        spin = 0;
-                    }
-                }
-                if (++spin > kSpinLimit) dbg_trap(999);
+                for (int kk = 0; kk < 2; ++kk) tc::mma_f16(d + 32, desc_k(xin + 4 * CH, kk, CH), desc_k(whh + 2 * H * 16, kk, 3 * H * 16), id32, kk > 0);
+                tc::mma_commit(&bar_done[s]);
             }
         }
     } else {
@@ -322,9 +389,14 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_fwd_kernel(const 
                     h[4 * j] = q.x; h[4 * j + 1] = q.y; h[4 * j + 2] = q.z; h[4 * j + 3] = q.w;
                 }
             }
+            auto load_mask = [&](int t) {
+                return a.mask_in_table ? __half2float(a.xhat[(my_first + (long long)t * a.step_rows) * K1 + K1 - 1])
+                                       : a.masks ? a.masks[my_first + (long long)t * a.step_rows] : 1.0f;
+            };
+            float mask_next = load_mask(0);
             for (int t = 0; t < a.L; ++t) {
-                const float mask = a.mask_in_table ? __half2float(a.xhat[(my_first + (long long)t * a.step_rows) * K1 + K1 - 1])
-                                                     : a.masks ? a.masks[my_first + (long long)t * a.step_rows] : 1.0f;
+                const float mask = mask_next;
+                if (t + 1 < a.L) mask_next = load_mask(t + 1);            // one step ahead: its latency hides behind this step
                 // ---- S0: masked input state -> [xh2 | hp] tile (chunks 4..7); observations landed -> fc1 -------------------
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -344,35 +416,12 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_fwd_kernel(const 
                 if (t + 1 < a.L) fetch_x0(t + 1);                         // fc1 has consumed the X0 tile
                 // ---- S1: fc1 epilogue: bias, ReLU, LayerNorm -> xh1 tile -> fc2 ------------------------------------------
                 float rstd1, rstd2;
-                uint32_t relu1 = 0, relu2 = 0;
+                uint32_t relu1, relu2;
                 {
                     float v[H];
                     tc::tmem_ld32_issue(tl, v);
                     tc::tmem_ld_fence<H>(v);
-                    float sum = 0.f;
-#pragma unroll
-                    for (int j = 0; j < H / 4; ++j) {
-                        const float4 b = sP4[S_B1 / 4 + j];
-                        const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float x = v[4 * j + u] + bb[u];
-                            const bool pos = x > 0.f;
-                            relu1 |= (uint32_t)pos << (4 * j + u);
-                            v[4 * j + u] = pos ? x : 0.f;
-                            sum += v[4 * j + u];
-                        }
-                    }
-                    const float mean = sum * (1.0f / H);
-                    float q = 0.f;
-#pragma unroll
-                    for (int j = 0; j < H; ++j) {
-                        v[j] -= mean;
-                        q = fmaf(v[j], v[j], q);
-                    }
-                    rstd1 = rsqrtf(q * (1.0f / H) + kEps);
-#pragma unroll
-                    for (int j = 0; j < H; ++j) v[j] *= rstd1;
+                    rstd1 = bias_relu_norm32(v, sP4 + S_B1 / 4, relu1);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) store_chunk(sXH1, c, row, v + 8 * c);
                 }
@@ -383,30 +432,7 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_fwd_kernel(const 
                     float v[H];
                     tc::tmem_ld32_issue(tl + 32, v);
                     tc::tmem_ld_fence<H>(v);
-                    float sum = 0.f;
-#pragma unroll
-                    for (int j = 0; j < H / 4; ++j) {
-                        const float4 b = sP4[S_B2 / 4 + j];
-                        const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float x = v[4 * j + u] + bb[u];
-                            const bool pos = x > 0.f;
-                            relu2 |= (uint32_t)pos << (4 * j + u);
-                            v[4 * j + u] = pos ? x : 0.f;
-                            sum += v[4 * j + u];
-                        }
-                    }
-                    const float mean = sum * (1.0f / H);
-                    float q = 0.f;
-#pragma unroll
-                    for (int j = 0; j < H; ++j) {
-                        v[j] -= mean;
-                        q = fmaf(v[j], v[j], q);
-                    }
-                    rstd2 = rsqrtf(q * (1.0f / H) + kEps);
-#pragma unroll
-                    for (int j = 0; j < H; ++j) v[j] *= rstd2;
+                    rstd2 = bias_relu_norm32(v, sP4 + S_B2 / 4, relu2);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) store_chunk(sIN, c, row, v + 8 * c);
                     sEX[row] = make_uint4(__float_as_uint(rstd1), __float_as_uint(rstd2), relu1, relu2);
@@ -440,31 +466,14 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_fwd_kernel(const 
                     }
                 }
                 {
-                    float sum = 0.f;
-#pragma unroll
-                    for (int j = 0; j < H; ++j) sum += h[j];
-                    const float mean = sum * (1.0f / H);
-                    float q = 0.f;
-#pragma unroll
-                    for (int j = 0; j < H; ++j) q = fmaf(h[j] - mean, h[j] - mean, q);
-                    const float rstd3 = rsqrtf(q * (1.0f / H) + kEps);
                     float xh3[H];
 #pragma unroll
-                    for (int j = 0; j < H; ++j) xh3[j] = (h[j] - mean) * rstd3;
+                    for (int j = 0; j < H; ++j) xh3[j] = h[j];
+                    normalise32(xh3);
                     float* orow = a.out + ((long long)t * a.R + grow) * a.NO;
-#pragma unroll 1
-                    for (int o = 0; o < a.NO; ++o) {
-                        float acc = sP[S_BO + o];
-#pragma unroll
-                        for (int j = 0; j < H / 4; ++j) {
-                            const float4 w = sP4[S_WO / 4 + o * (H / 4) + j];
-                            acc = fmaf(xh3[4 * j], w.x, acc);
-                            acc = fmaf(xh3[4 * j + 1], w.y, acc);
-                            acc = fmaf(xh3[4 * j + 2], w.z, acc);
-                            acc = fmaf(xh3[4 * j + 3], w.w, acc);
-                        }
-                        if (valid) orow[o] = acc;
-                    }
+                    if (a.NO == 1) head32<1>(xh3, sP, orow, a.NO, valid);
+                    else if (a.NO <= 5) head32<5>(xh3, sP, orow, a.NO, valid);
+                    else head32<NOMAX>(xh3, sP, orow, a.NO, valid);
                 }
                 if (a.saved) {                                          // the images were read before the next step rewrites them
                     if (row == 0) tc::bulk_wait_read_all();
@@ -658,14 +667,26 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_bwd_kernel(const 
 #pragma unroll
             for (int j = 0; j < H; ++j) carry[j] = 0.f;
 
-            for (int t = a.L - 1; t >= 0; --t) {
-                const float mask = a.mask_in_table ? __half2float(a.xhat[(my_first + (long long)t * a.step_rows) * K1 + K1 - 1])
-                                                     : a.masks ? a.masks[my_first + (long long)t * a.step_rows] : 1.0f;
-                float dO[NOMAX];
-                {
-                    const float* drow = a.dout + ((long long)t * a.R + grow) * a.NO;
+            auto load_mask = [&](int t) {
+                return a.mask_in_table ? __half2float(a.xhat[(my_first + (long long)t * a.step_rows) * K1 + K1 - 1])
+                                       : a.masks ? a.masks[my_first + (long long)t * a.step_rows] : 1.0f;
+            };
+            auto load_dout = [&](int t, float (&d)[NOMAX]) {
+                const float* drow = a.dout + ((long long)t * a.R + grow) * a.NO;
 #pragma unroll
-                    for (int o = 0; o < NOMAX; ++o) dO[o] = (valid && o < a.NO) ? drow[o] * gscale : 0.f;
+                for (int o = 0; o < NOMAX; ++o) d[o] = (valid && o < a.NO) ? drow[o] : 0.f;
+            };
+            float mask_next = load_mask(a.L - 1), dO_next[NOMAX];
+            load_dout(a.L - 1, dO_next);
+
+            for (int t = a.L - 1; t >= 0; --t) {
+                const float mask = mask_next;
+                float dO[NOMAX];
+#pragma unroll
+                for (int o = 0; o < NOMAX; ++o) dO[o] = dO_next[o] * gscale;
+                if (t > 0) {                                              // one step ahead: the latency hides behind this step
+                    mask_next = load_mask(t - 1);
+                    load_dout(t - 1, dO_next);
                 }
                 // ---- B0: the step's [xh2 | hp] tile has landed -> recompute the gate pre-activations ---------------------
                 wait_bar(&bar_in[s], in_par, 210 + s);
@@ -723,24 +744,9 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_bwd_kernel(const 
                         nh_[8 * c + j] = pack2(n, hnb);
                     }
                 }
-                float rstd3;
-                {
-                    float sum = 0.f;
+                const float rstd3 = normalise32(hrow);                    // hrow = xh3 from here on
 #pragma unroll
-                    for (int j = 0; j < H; ++j) sum += hrow[j];
-                    const float mean = sum * (1.0f / H);
-                    float q = 0.f;
-#pragma unroll
-                    for (int j = 0; j < H; ++j) {
-                        hrow[j] -= mean;
-                        q = fmaf(hrow[j], hrow[j], q);
-                    }
-                    rstd3 = rsqrtf(q * (1.0f / H) + kEps);
-#pragma unroll
-                    for (int j = 0; j < H; ++j) hrow[j] *= rstd3;          // hrow = xh3 from here on
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) store_chunk(sA2, 8 + c, row, hrow + 8 * c);
-                }
+                for (int c = 0; c < 4; ++c) store_chunk(sA2, 8 + c, row, hrow + 8 * c);
                 *reinterpret_cast<uint4*>(sDOUT + row * 16) =
                     make_uint4(pack2(dO[0], dO[1]), pack2(dO[2], dO[3]), pack2(dO[4], dO[5]), pack2(dO[6], dO[7]));
                 float g[H];                                               // d loss / d xh3 (the head's weights carry ln3's gain)
@@ -760,14 +766,7 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_bwd_kernel(const 
                     }
                 }
                 {
-                    float sg = 0.f, sq = 0.f;
-#pragma unroll
-                    for (int j = 0; j < H; ++j) {
-                        sg += g[j];
-                        sq = fmaf(g[j], hrow[j], sq);
-                    }
-                    sg *= (1.0f / H);
-                    sq *= (1.0f / H);
+                    const float sg = sum32(g) * (1.0f / H), sq = dot32(g, hrow) * (1.0f / H);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float dr[8], dz[8], dn[8], dnr[8], hp[8];
@@ -815,20 +814,7 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_bwd_kernel(const 
                         xh2[8 * c] = p0.x; xh2[8 * c + 1] = p0.y; xh2[8 * c + 2] = p1.x; xh2[8 * c + 3] = p1.y;
                         xh2[8 * c + 4] = p2.x; xh2[8 * c + 5] = p2.y; xh2[8 * c + 6] = p3.x; xh2[8 * c + 7] = p3.y;
                     }
-                    float sg = 0.f, sq = 0.f;
-#pragma unroll
-                    for (int j = 0; j < H; ++j) {
-                        sg += dx[j];
-                        sq = fmaf(dx[j], xh2[j], sq);
-                    }
-                    sg *= (1.0f / H);
-                    sq *= (1.0f / H);
-                    const float rstd2 = __uint_as_float(ex.y);
-#pragma unroll
-                    for (int j = 0; j < H; ++j) {
-                        const float v = rstd2 * (dx[j] - sg - xh2[j] * sq);
-                        dx[j] = (ex.w >> j & 1u) ? v : 0.f;
-                    }
+                    norm_relu_bwd32(dx, xh2, __uint_as_float(ex.y), ex.w);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) store_chunk(sA2, 4 + c, row, dx + 8 * c);
                 }
@@ -843,20 +829,7 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_bwd_kernel(const 
 #pragma unroll
                     for (int c = 0; c < 4; ++c) load_chunk(sXH1, c, row, xh1 + 8 * c);
                     tc::tmem_ld_fence<H>(dx);
-                    float sg = 0.f, sq = 0.f;
-#pragma unroll
-                    for (int j = 0; j < H; ++j) {
-                        sg += dx[j];
-                        sq = fmaf(dx[j], xh1[j], sq);
-                    }
-                    sg *= (1.0f / H);
-                    sq *= (1.0f / H);
-                    const float rstd1 = __uint_as_float(ex.x);
-#pragma unroll
-                    for (int j = 0; j < H; ++j) {
-                        const float v = rstd1 * (dx[j] - sg - xh1[j] * sq);
-                        dx[j] = (ex.z >> j & 1u) ? v : 0.f;
-                    }
+                    norm_relu_bwd32(dx, xh1, __uint_as_float(ex.x), ex.z);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) store_chunk(sA2, c, row, dx + 8 * c);
                 }
