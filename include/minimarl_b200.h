@@ -565,6 +565,33 @@ int mm_ppo_trunk2_bwd(const float* params, const void* xhat_f16, const int64_t* 
                       int32_t n_acc_ctas, int32_t L, int64_t R, int32_t NO, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Row-parallel half of the agent network's differentiated pass (csrc/agent_mlp.cu): what MLPBase / MLPLayer
+ * (offpolicy/utils/algorithm_utils/mlp.py:7-89) and the input projection of the GRU in RNNLayer (rnn.py:4-47) compute
+ * inside AgentQFunction.forward (offpolicy/algorithms/qmix/algorithm/agent_q_function.py:34-66) when
+ * QMix.train_policy_on_batch (offpolicy/algorithms/qmix/qmix.py:80-210) differentiates the live network, hidden size 64:
+ *   gi = Wih LN(ReLU(W2 LN(ReLU(W1 LN(obs) + b1)) + b2)) + bih          rows = (t, episode, agent) entries
+ * forward and backward as one tcgen05 kernel each (fp16 operands, fp32 accumulate), weight gradients inside the backward.
+ *   params: fp32 device buffer w1 [64][48] | w2 [64][64] | wih [192][64] | b1 [64] | b2 [64] | bih [192], LayerNorm affines folded
+ *     into the Linear that follows (W' = W diag(g), b' = b + W beta) by the caller.
+ *   fwd: obs [rows, D] (D <= 48) -> gi [rows, 192] (what mm_gru_seq_fwd takes); training: saved_rows [rows, dims[1]] (fp32
+ *     normalised activations, 1 / sigma, ReLU bits) and saved_x0 [tiles][dims[6]] fp16 (operand images of the normalised
+ *     observations); both NULL for inference.
+ *   bwd: dgi [rows, 192] (from mm_gru_seq_bwd), scale: device float, power of two applied to dgi (mm_ppo_trunk2_scale);
+ *     acc [n_acc_ctas >= mm_agent_mlp_bwd_ctas(rows)][128][dims[2]]: per CTA the TMEM accumulators, scale x
+ *       columns [0,192): lanes xh2 feature j (0..63), lane 64 = 1      x gi column      -> dWih'^T, dbih'
+ *       columns [192,256): lanes xh1 feature j, lane 64 = 1              x fc2 output    -> dW2'^T, db2'
+ *       columns [256,320): a 64-row accumulator (row r in lane 32 (r / 16) + r % 16): rows x0 feature k (0..47), row 48 = 1
+ *                                                                          x fc1 output    -> dW1'^T, db1'
+ *   mm_agent_mlp_dims -> {parameter count, saved floats per row, accumulator columns, tile rows, 48, 64, saved x0 halves per tile, 0}.
+ * ---------------------------------------------------------------------------------------------- */
+int mm_agent_mlp_dims(int32_t* dims8);
+int mm_agent_mlp_bwd_ctas(int64_t rows);
+int mm_agent_mlp_fwd(const float* params, const float* obs, float* gi, float* saved_rows, void* saved_x0, int64_t rows, int32_t D,
+                     void* stream);
+int mm_agent_mlp_bwd(const float* params, const float* saved_rows, const void* saved_x0, const float* dgi, const float* scale,
+                     float* acc, int32_t n_acc_ctas, int64_t rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * PPO losses of R_MAPPO.ppo_update / cal_value_loss (mappo/algorithms/ramppo_network.py:70-171), one pass each.
  * Rows R = minibatch entries; every per-row input is a float32 vector of length R (logits [R, NA], NA <= 8);
  * active == NULL means weight 1.

@@ -1,0 +1,138 @@
+"""Row-parallel half of the agent network's differentiated pass as ONE op (``mm_agent_mlp_fwd`` / ``_bwd``, tcgen05, fp16
+operands with fp32 accumulation): ``LayerNorm -> [Linear ReLU LayerNorm] x2 -> GRU input projection`` for hidden size 64.
+
+What ``MLPBase`` / ``MLPLayer`` (offpolicy/utils/algorithm_utils/mlp.py:7-89) and the input half of ``nn.GRU`` in ``RNNLayer``
+(rnn.py:4-47) compute when ``QMix.train_policy_on_batch`` (offpolicy/algorithms/qmix/qmix.py:80-210) differentiates the live
+network.  The op returns ``gi`` [rows, 192], which ``gru_from_gi`` feeds to the recurrence kernels of csrc/gru_tc.cu; the
+backward takes ``dgi`` and contracts every weight gradient inside the kernel (no cuBLAS, no LayerNorm / ReLU / bias launches).
+LayerNorm affines are folded into the Linear that follows for the kernel (W' = W diag(g), b' = b + W beta) and unfolded here.
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from ..ops.gram import colsum, gram
+
+H, K1 = 64, 48
+_DIMS = None
+_M64_LANES = [32 * (r // 16) + r % 16 for r in range(64)]      # where row r of a 64-row tcgen05 accumulator lives in TMEM
+
+
+def dims():
+    global _DIMS
+    if _DIMS is None:
+        d = (C.c_int32 * 8)()
+        _lib.check(_lib.lib().mm_agent_mlp_dims(d))
+        _DIMS = dict(zip("n_params saved_row_floats acc_cols tile_rows K1 H x0_halves_per_tile _".split(), list(d)))
+    return _DIMS
+
+
+def agent_mlp_fits(in_dim, hidden, layer_N=1):
+    return hidden == H and 1 <= in_dim <= K1 and layer_N == 1
+
+
+class _AgentMlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, obs, ln0_w, ln0_b, w1, b1, ln1_w, ln1_b, w2, b2, ln2_w, ln2_b, wih, bih):
+        rows, D = obs.shape
+        d = dims()
+        w1p = torch.zeros((H, K1), dtype=torch.float32, device=obs.device)
+        w1p[:, :D] = w1 * ln0_w
+        packed = torch.cat([w1p.reshape(-1), (w2 * ln1_w).reshape(-1), (wih * ln2_w).reshape(-1), b1 + w1 @ ln0_b,
+                            b2 + w2 @ ln1_b, bih + wih @ ln2_b])
+        gi = torch.empty((rows, 3 * H), dtype=torch.float32, device=obs.device)
+        train = any(ctx.needs_input_grad[1:])
+        saved_rows = saved_x0 = None
+        if train:
+            n_tiles = (rows + d["tile_rows"] - 1) // d["tile_rows"]
+            saved_rows = torch.empty((rows, d["saved_row_floats"]), dtype=torch.float32, device=obs.device)
+            saved_x0 = torch.empty((n_tiles, d["x0_halves_per_tile"]), dtype=torch.float16, device=obs.device)
+        _lib.check(_lib.lib().mm_agent_mlp_fwd(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(gi), _lib.ptr(saved_rows),
+                                               _lib.ptr(saved_x0), rows, D, _lib.stream()))
+        if train:
+            ctx.save_for_backward(packed, saved_rows, saved_x0, ln0_w, ln0_b, w1, ln1_w, ln1_b, w2, ln2_w, ln2_b, wih)
+            ctx.dims = (rows, D)
+        return gi
+
+    @staticmethod
+    def backward(ctx, dgi):
+        packed, saved_rows, saved_x0, ln0_w, ln0_b, w1, ln1_w, ln1_b, w2, ln2_w, ln2_b, wih = ctx.saved_tensors
+        rows, D = ctx.dims
+        d = dims()
+        dgi = dgi.contiguous()
+        lib = _lib.lib()
+        scale = torch.empty(2, dtype=torch.float32, device=dgi.device)
+        _lib.check(lib.mm_ppo_trunk2_scale(_lib.ptr(dgi), dgi.numel(), _lib.ptr(scale), _lib.stream()))
+        n_ctas = lib.mm_agent_mlp_bwd_ctas(rows)
+        acc = torch.empty((n_ctas, d["tile_rows"], d["acc_cols"]), dtype=torch.float32, device=dgi.device)
+        _lib.check(lib.mm_agent_mlp_bwd(_lib.ptr(packed), _lib.ptr(saved_rows), _lib.ptr(saved_x0), _lib.ptr(dgi), _lib.ptr(scale),
+                                        _lib.ptr(acc), n_ctas, rows, _lib.stream()))
+        A = acc.sum(0) / scale[0]
+        # columns [0,192): lanes xh2 feature | 1 [64] x gate; [192,256): lanes xh1 feature | 1 [64] x fc2 output;
+        # [256,320): 64-row accumulator, rows x0 feature | 1 [48] x fc1 output
+        gwih, gbih = A[:H, :3 * H].t(), A[H, :3 * H]
+        gw2, gb2 = A[:H, 3 * H:4 * H].t(), A[H, 3 * H:4 * H]
+        t3 = A[_M64_LANES, 4 * H:5 * H]
+        gw1, gb1 = t3[:D].t(), t3[K1]
+        # unfold W' = W diag(g), b' = b + W beta:  dW = dW' diag(g) + outer(db', beta), dg = sum_n dW'[n, :] W[n, :], dbeta = W^T db'
+        unfold = lambda gw, gb, w, g, b: (gw * g + torch.outer(gb, b), (gw * w).sum(0), w.t() @ gb)
+        dw1, dg0, db0 = unfold(gw1, gb1, w1, ln0_w, ln0_b)
+        dw2, dg1, db1 = unfold(gw2, gb2, w2, ln1_w, ln1_b)
+        dwih, dg2, db2 = unfold(gwih, gbih, wih, ln2_w, ln2_b)
+        return None, dg0, db0, dw1, gb1, dg1, db1, dw2, gb2, dg2, db2, dwih, gbih
+
+
+def agent_mlp_gi(obs2d, ln0, fc1, ln1, fc2, ln2, w_ih, b_ih):
+    """obs2d [rows, D]; ln*: (weight, bias) of the LayerNorms, fc*: (weight, bias) of the Linears -> gi [rows, 192]."""
+    return _AgentMlpFn.apply(obs2d.contiguous(), ln0[0], ln0[1], fc1[0], fc1[1], ln1[0], ln1[1], fc2[0], fc2[1], ln2[0], ln2[1],
+                             w_ih, b_ih)
+
+
+class _GruFromGiFn(torch.autograd.Function):
+    """The recurrence of ``nn.GRU`` on precomputed input projections (``mm_gru_seq_fwd`` / ``_bwd``): the op of nn/gru.py without
+    its row-parallel input half, which ``agent_mlp_gi`` has fused into the layers below."""
+
+    @staticmethod
+    def forward(ctx, gi, h0, w_hh, b_hh, T, R):
+        Hh = w_hh.shape[1]
+        z_ = dict(dtype=torch.float32, device=gi.device)
+        h_seq = torch.empty((T, R, Hh), **z_)
+        need = any(ctx.needs_input_grad)
+        saved = [torch.empty((T, R, Hh), **z_) for _ in range(4)] if need else [None] * 4
+        h0c = h0.contiguous() if h0 is not None else None
+        _lib.check(_lib.lib().mm_gru_seq_fwd(_lib.ptr(gi), _lib.ptr(h0c), _lib.ptr(w_hh.contiguous()), _lib.ptr(b_hh.contiguous()),
+                                             _lib.ptr(h_seq), *[_lib.ptr(s) for s in saved], T, R, Hh, _lib.stream()))
+        if need:
+            ctx.save_for_backward(h0c if h0c is not None else torch.empty(0, device=gi.device), w_hh, h_seq, *saved)
+            ctx.dims = (T, R, Hh, h0 is not None)
+        return h_seq
+
+    @staticmethod
+    def backward(ctx, dh_seq):
+        h0, w_hh, h_seq, r, z, n, ghn = ctx.saved_tensors
+        T, R, Hh, has_h0 = ctx.dims
+        z_ = dict(dtype=torch.float32, device=h_seq.device)
+        dgi = torch.empty((T * R, 3 * Hh), **z_)
+        dghn = torch.empty((T, R, Hh), **z_)
+        dh0 = torch.empty((R, Hh), **z_)
+        _lib.check(_lib.lib().mm_gru_seq_bwd(_lib.ptr(dh_seq.contiguous()), _lib.ptr(r), _lib.ptr(z), _lib.ptr(n), _lib.ptr(ghn),
+                                             _lib.ptr(h_seq), _lib.ptr(h0 if has_h0 else None), _lib.ptr(w_hh.contiguous()),
+                                             _lib.ptr(dgi), _lib.ptr(dghn), _lib.ptr(dh0), T, R, Hh, _lib.stream()))
+        h_prev = torch.empty((T, R, Hh), **z_)
+        if has_h0:
+            h_prev[0].copy_(h0)
+        else:
+            h_prev[0].zero_()
+        h_prev[1:].copy_(h_seq[:-1])
+        hp2 = h_prev.view(T * R, Hh)
+        dghn2 = dghn.view(T * R, Hh)
+        dw_hh_all = gram(dgi, hp2)                       # the n rows of this product are discarded: one pass over hp2
+        dw_hh = torch.cat((dw_hh_all[:2 * Hh], gram(dghn2, hp2)), dim=0)
+        db_hh = torch.cat((colsum(dgi[:, :2 * Hh].contiguous()), colsum(dghn2)))
+        return dgi, (dh0 if (has_h0 and ctx.needs_input_grad[1]) else None), dw_hh, db_hh, None, None
+
+
+def gru_from_gi(gi, h0, w_hh, b_hh, T, R):
+    """gi [T * R, 3H] (input projections incl. b_ih) -> h_seq [T, R, H]."""
+    return _GruFromGiFn.apply(gi, h0, w_hh, b_hh, T, R)

@@ -205,7 +205,25 @@ class RNNBase(MLPBase):
         self._recurrent_N = args.recurrent_N
         self.rnn = RNNLayer(self.hidden_size, self.hidden_size, self._recurrent_N, self._use_orthogonal)
 
+    def _fused_mlp_ok(self, x):
+        """The differentiated pass runs the row-parallel layers as the fused op (csrc/agent_mlp.cu): default network shape on
+        CUDA with TF32 matmuls allowed (the switch the fp32 parity path turns off), sequence input."""
+        from .agent_mlp import agent_mlp_fits
+        return (x.is_cuda and x.dim() == 3 and x.dtype == torch.float32 and torch.is_grad_enabled() and self._use_feature_normalization
+                and self._use_ReLU and self._recurrent_N == 1 and agent_mlp_fits(x.shape[-1], self.hidden_size, self._layer_N)
+                and torch.backends.cuda.matmul.allow_tf32 and torch.backends.cudnn.allow_tf32
+                and getattr(self, "fused_mlp", True))
+
     def forward(self, x, hxs):
+        if self._fused_mlp_ok(x):
+            from .agent_mlp import agent_mlp_gi, gru_from_gi
+            T, R, D = x.shape
+            wb = lambda m: (m.weight, m.bias)
+            g = self.rnn.rnn
+            gi = agent_mlp_gi(x.reshape(T * R, D), wb(self.feature_norm), wb(self.mlp.fc1[0]), wb(self.mlp.fc1[2]),
+                              wb(self.mlp.fc2[0][0]), wb(self.mlp.fc2[0][2]), g.weight_ih_l0, g.bias_ih_l0)
+            h_seq = gru_from_gi(gi, hxs[0] if hxs is not None else None, g.weight_hh_l0, g.bias_hh_l0, T, R)
+            return self.rnn.norm(h_seq), h_seq[-1]
         if self._use_feature_normalization:
             x = self.feature_norm(x)
         x = self.mlp(x)
