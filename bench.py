@@ -501,14 +501,8 @@ def learner_section(dev, steps):
     world = dist.get_world_size() if dist.is_initialized() else 1
     for _ in range(3):
         update()
-    if world > 1:
-        dist.barrier()
-    ms_update, info_ = timed(update, steps)
-    if world > 1:                       # weak scaling: every rank trains on its own batch, gradients all-reduced (NCCL)
-        t_ = torch.tensor([ms_update], device=dev, dtype=torch.float64)
-        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-        ms_update = float(t_.item())
-    # component timings (each in isolation, after the full updates)
+    ms_eager, _ = timed(update, max(3, steps // 4))          # launched from Python one kernel at a time (host-bound)
+    # component timings (each in isolation, after the eager updates and before the graph's private pool exists)
     ms_sample, sample = timed(lambda: buf.sample(B, beta=0.4, p_id="policy_0"), 5)
     ms_gather, _ = timed(lambda: buf._gather(sample[8]), 10)          # the gather launch alone (indices already drawn)
     stacked = torch.cat(list(sample[0]["policy_0"]), dim=-2)
@@ -520,6 +514,22 @@ def learner_section(dev, steps):
         ms_agent, _ = timed(lambda: agentq_forward(net.packed(), stacked, h0, D, 64, NA), 5)
         qs = torch.randn((T, B, A), device=dev)
         ms_mixer, _ = timed(lambda: trainer.target_mixer(qs, sample[1]["policy_0"][:-1]), 5)
+    graphed = None
+    if world == 1:
+        # the same update as ONE CUDA graph (algorithms.qmix.GraphedUpdate): ~230 launches take the host ~7 ms to issue, the
+        # device needs ~6; the multi-GPU leg keeps the eager loop (its NCCL all-reduce is not captured)
+        from minimarl_b200.algorithms.qmix import GraphedUpdate
+        graphed = GraphedUpdate(trainer, buf, B)
+        eager_update, update = update, (lambda: graphed(0.4))
+        for _ in range(3):
+            update()
+    if world > 1:
+        dist.barrier()
+    ms_update, info_ = timed(update, steps)
+    if world > 1:                       # weak scaling: every rank trains on its own batch, gradients all-reduced (NCCL)
+        t_ = torch.tensor([ms_update], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        ms_update = float(t_.item())
     rows = (T + 1) * A * B
     peak, _ = measured_peaks()
     gather_bytes = 2 * 81952 * B
@@ -527,8 +537,11 @@ def learner_section(dev, steps):
         "metric": "QMIX train samples/sec", "value": world * B * T / (ms_update * 1e-3), "unit": "samples/s",
         "n_gpus": world, "grad_allreduce": "NCCL all-reduce of one flattened fp32 bucket per update" if world > 1 else None,
         "config": {"buffer_episodes": S, "episode_length": T, "batch_episodes_per_gpu": B, "agents": A, "hidden": 64,
-                   "per": True, "double_q": True, "precision": "tf32 operands, fp32 accumulate (custom kernels and cuBLAS)"},
-        "ms_per_update": ms_update, "loss": float(info_["loss"]),
+                   "per": True, "double_q": True, "precision": "tf32 / fp16 operands (11-bit significand), fp32 accumulate (custom kernels; cuBLAS for the hypernetworks, "
+                                "the head and the recurrent weight gradients)"},
+        "ms_per_update": ms_update, "ms_per_update_eager_launches": ms_eager,
+        "launch_mode": "one CUDA graph per update (GraphedUpdate)" if graphed is not None else "eager launches",
+        "loss": float(info_["loss"]),
         "sample_gather": {"ms": ms_sample, "algorithmic_GBps": gather_bytes / (ms_sample * 1e-3) / 1e9,
                           "frac_of_measured_hbm": gather_bytes / (ms_sample * 1e-3) / 1e9 / peak,
                           "note": "PER draw (uniforms, mm_per_sample) + mm_replay_gather; 2 x 81 952 B per sampled episode"},

@@ -585,6 +585,14 @@ int mm_ppo_trunk2_bwd(const float* params, const void* xhat_f16, const int64_t* 
  *   mm_agent_mlp_dims -> {parameter count, saved floats per row, accumulator columns, tile rows, 48, 64, saved x0 halves per tile, 0}.
  * ---------------------------------------------------------------------------------------------- */
 int mm_agent_mlp_dims(int32_t* dims8);
+/* The algebra around the two kernels, one launch each.  params12: HOST array of the 12 device pointers ln0_w, ln0_b, w1 [64][D], b1,
+ * ln1_w, ln1_b, w2, b2, ln2_w, ln2_b, w_ih [192][64], b_ih (the module's own tensors).  pack folds the LayerNorm affines into the
+ * packed parameters; unfold sums acc over the CTAs, applies 1 / scale and writes the 12 gradients back to back into grads
+ * (offsets from mm_agent_mlp_grad_layout, 13 entries); red: scratch of 128 * dims[2] floats. */
+int mm_agent_mlp_pack(const void* const* params12, float* packed, int32_t D, void* stream);
+int mm_agent_mlp_grad_layout(int32_t D, int32_t* offsets13);
+int mm_agent_mlp_unfold(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params12, float* grads,
+                        int32_t D, void* stream);
 int mm_agent_mlp_bwd_ctas(int64_t rows);
 int mm_agent_mlp_fwd(const float* params, const float* obs, float* gi, float* saved_rows, void* saved_x0, int64_t rows, int32_t D,
                      void* stream);

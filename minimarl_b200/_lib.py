@@ -122,6 +122,9 @@ SIGNATURES = {
                                     C.c_int32, _P]),
     "mm_agent_mlp_dims": (C.c_int, [C.POINTER(C.c_int32)]),
     "mm_agent_mlp_bwd_ctas": (C.c_int, [C.c_int64]),
+    "mm_agent_mlp_pack": (C.c_int, [_P, _P, C.c_int32, _P]),
+    "mm_agent_mlp_grad_layout": (C.c_int, [C.c_int32, C.POINTER(C.c_int32)]),
+    "mm_agent_mlp_unfold": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P]),
     "mm_agent_mlp_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "mm_agent_mlp_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P]),
     "mm_tc_raw_f16_selftest": (C.c_int, [_P, _P, _P] + [C.c_int32] * 11 + [_P]),

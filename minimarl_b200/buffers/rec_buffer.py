@@ -162,6 +162,7 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
         self._it_sums = {p_id: SumSegmentTree(it_capacity, device) for p_id in policy_info.keys()}
         self._it_mins = {p_id: MinSegmentTree(it_capacity, device) for p_id in policy_info.keys()}
         self.max_priorities = {p_id: 1.0 for p_id in policy_info.keys()}
+        self._max_prio_dev = {}          # running maxima of un-validated updates (device scalars), folded in at the next insert
         # sharded replay (one shard per GPU): importance weights normalised with min p / sum p / len over ALL
         # shards (parallel.per_global_weights) instead of this shard's tree alone
         self.sharded = False
@@ -169,6 +170,8 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
     def _seed_priorities(self, idx_range):
         n = len(idx_range)
         for p_id in self.policy_info.keys():
+            if p_id in self._max_prio_dev:
+                self.max_priorities[p_id] = max(self.max_priorities[p_id], float(self._max_prio_dev[p_id]))
             v = self.max_priorities[p_id] ** self.alpha
             st, mt = self._it_sums[p_id], self._it_mins[p_id]
             if self.fix_insert_priority:
@@ -212,7 +215,7 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
             weights = per_global_weights(leaves[batch_inds], mt._value[st._capacity:st._capacity + n].min(), leaves.sum(), n, beta)
         return self._gather(batch_inds) + (weights, batch_inds)
 
-    def update_priorities(self, idxes, priorities, p_id=None):
+    def update_priorities(self, idxes, priorities, p_id=None, validate=True):
         """``priorities ** alpha`` goes into both trees in one launch.  Host (numpy) priorities -- what the
         reference's trainer hands over -- are raised to alpha on the host in float64 exactly as the reference
         does; device tensors are raised on the device (torch.pow, <= 1 ulp from libm)."""
@@ -226,12 +229,21 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
             vals = torch.as_tensor(host ** self.alpha, device=self.device).contiguous()
         idx = torch.as_tensor(np.asarray(idxes) if not torch.is_tensor(idxes) else idxes,
                               device=self.device).to(torch.int64).reshape(-1).contiguous()
-        # the reference's asserts (rec_buffer.py:315-318) and max tracking need the values on the host: one small sync, BEFORE
-        # anything is written, so an out-of-range index can never reach the tree
-        stats = torch.stack([pr.min(), pr.max(), idx.min().double(), idx.max().double()]).tolist()
-        assert stats[0] > 0
-        assert stats[2] >= 0
-        assert stats[3] < len(self)
+        if validate:
+            # the reference's asserts (rec_buffer.py:315-318) and max tracking need the values on the host: one small sync, BEFORE
+            # anything is written, so an out-of-range index can never reach the tree
+            stats = torch.stack([pr.min(), pr.max(), idx.min().double(), idx.max().double()]).tolist()
+            assert stats[0] > 0
+            assert stats[2] >= 0
+            assert stats[3] < len(self)
+        else:
+            # no host round trip (CUDA-graph replay, GraphedUpdate): indices are clamped instead of asserted, the running maximum
+            # stays on the device until the next insert reads it
+            idx = idx.clamp(0, len(self) - 1)
+            m = self._max_prio_dev.get(p_id)
+            if m is None:
+                m = self._max_prio_dev[p_id] = torch.zeros((), dtype=torch.float64, device=self.device)
+            m.copy_(torch.maximum(m, pr.max()))
         # PER samples with replacement: when an index repeats the reference's loop lets the LAST write win.  Every duplicate is
         # given the value of its last occurrence, so the parallel write is deterministic.
         order = torch.arange(idx.numel(), device=self.device)
@@ -240,4 +252,5 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
         st, mt = self._it_sums[p_id], self._it_mins[p_id]
         _lib.check(_lib.lib().mm_segtree_set(_lib.ptr(st._value), _lib.ptr(mt._value), st._capacity, _lib.ptr(idx),
                                              _lib.ptr(vals), 0.0, 0, idx.numel(), _lib.stream()))
-        self.max_priorities[p_id] = max(self.max_priorities[p_id], stats[1])
+        if validate:
+            self.max_priorities[p_id] = max(self.max_priorities[p_id], stats[1])

@@ -112,9 +112,26 @@ struct Args {
     const float* dgi;       // [rows][3H]                                         (backward)
     const float* scale;     // device float: power-of-two gradient scale          (backward)
     float* acc;             // [grid][128][ACC_COLS]                              (backward)
+    unsigned int* ticket;   // tile counter (zero at launch; the last CTA to leave resets it): tiles are handed out dynamically,
+                            // so a CTA that starts late because another kernel holds its SM does not stretch the launch
     int D;
     long long rows, n_tiles;
 };
+
+// next tile of this CTA, the same value in every thread (one atomic per tile; the barrier also separates the tiles)
+__device__ __forceinline__ long long next_tile(unsigned int* ticket, unsigned int* slot) {
+    __syncthreads();
+    if (threadIdx.x == 0) *slot = atomicAdd(ticket, 1u);
+    __syncthreads();
+    return (long long)*slot;
+}
+// the last CTA to run out of tiles puts the counter back to zero for the next launch
+__device__ __forceinline__ void retire(unsigned int* ticket, unsigned int n_tiles) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == n_tiles + 2u * gridDim.x - 1u) *ticket = 0u;
+    }
+}
 
 __device__ __forceinline__ void block_publish() {
     tc::fence_smem_to_async();
@@ -131,7 +148,7 @@ constexpr int F_W1 = 0, F_W2 = F_W1 + H * K1 * 2, F_WIH = F_W2 + H * H * 2, F_BI
 __global__ void __launch_bounds__(128, 2) agent_mlp_fwd_kernel(const __grid_constant__ Args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t tmem_slot;
+    __shared__ uint32_t tmem_slot, tile_slot;
     const int tid = threadIdx.x, warp = tid >> 5, row = tid;
     float* sB = reinterpret_cast<float*>(smem + F_BIAS);
     uint8_t* sX0 = smem + F_X0;
@@ -157,7 +174,7 @@ __global__ void __launch_bounds__(128, 2) agent_mlp_fwd_kernel(const __grid_cons
         tc::fence_after_sync();
     };
 
-    for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (long long tile = next_tile(a.ticket, &tile_slot); tile < a.n_tiles; tile = next_tile(a.ticket, &tile_slot)) {
         const long long row0 = tile * kRows;
         const bool valid = row0 + row < a.rows;
         const long long grow = valid ? row0 + row : a.rows - 1;          // rows past the end shadow the last row
@@ -261,6 +278,7 @@ __global__ void __launch_bounds__(128, 2) agent_mlp_fwd_kernel(const __grid_cons
         tc::fence_before_sync();                                         // orders this tile's TMEM reads before the next tile's MMAs
     }
     if (a.saved_x0 && tid == 0) tc::bulk_wait_all();
+    retire(a.ticket, (unsigned int)a.n_tiles);
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 256);
@@ -278,7 +296,7 @@ constexpr int T_WORK = 0, T_ACC_IH = 64, T_ACC_2 = T_ACC_IH + G3, T_ACC_1 = T_AC
 __global__ void __launch_bounds__(128, 1) agent_mlp_bwd_kernel(const __grid_constant__ Args a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar, bar_x0;
-    __shared__ uint32_t tmem_slot;
+    __shared__ uint32_t tmem_slot, tile_slot;
     const int tid = threadIdx.x, warp = tid >> 5, row = tid;
     uint8_t* sXH2 = smem + B_XH2;
     uint8_t* sXH1 = smem + B_XH1;
@@ -319,7 +337,7 @@ __global__ void __launch_bounds__(128, 1) agent_mlp_bwd_kernel(const __grid_cons
         tc::fence_after_sync();
     };
 
-    for (long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (long long tile = next_tile(a.ticket, &tile_slot); tile < a.n_tiles; tile = next_tile(a.ticket, &tile_slot)) {
         const long long row0 = tile * kRows;
         const int n_valid = (int)min((long long)kRows, a.rows - row0);
         const bool valid = row < n_valid;
@@ -426,6 +444,7 @@ __global__ void __launch_bounds__(128, 1) agent_mlp_bwd_kernel(const __grid_cons
         started = true;
         wait_mma();                                 // nothing of this tile is read by the tensor core any more
     }
+    retire(a.ticket, (unsigned int)a.n_tiles);
     // ---- the weight-gradient accumulators leave TMEM: [128 lanes][ACC_COLS] per CTA -----------------------------------------------
     tc::fence_before_sync();
     __syncthreads();
@@ -437,6 +456,10 @@ __global__ void __launch_bounds__(128, 1) agent_mlp_bwd_kernel(const __grid_cons
             float v[32];
             tc::tmem_ld32_issue(tl + T_ACC_IH + c, v);
             tc::tmem_ld_fence<32>(v);
+            if (!started) {                       // this CTA never received a tile: its accumulators were never written
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<float4*>(dst + c + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -445,6 +468,135 @@ __global__ void __launch_bounds__(128, 1) agent_mlp_bwd_kernel(const __grid_cons
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---- the algebra around the two kernels, one launch each: folding the LayerNorm affines into the packed parameters, and summing
+// the per-CTA accumulators + unfolding them into the gradients of the module's own tensors --------------------------------------
+enum { Q_LN0W, Q_LN0B, Q_W1, Q_B1, Q_LN1W, Q_LN1B, Q_W2, Q_B2, Q_LN2W, Q_LN2B, Q_WIH, Q_BIH, Q_N };
+struct ParamPtrs { const float* p[Q_N]; };
+
+__device__ __forceinline__ float dot_row(const float* w, const float* v, int n) {
+    float acc = 0.f;
+    for (int k = 0; k < n; ++k) acc = fmaf(w[k], v[k], acc);
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) agent_mlp_pack_kernel(const ParamPtrs q, float* __restrict__ out, int D) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= P_TOTAL) return;
+    float v;
+    if (i < P_W2) {
+        const int n = i / K1, k = i - n * K1;
+        v = k < D ? q.p[Q_W1][n * D + k] * q.p[Q_LN0W][k] : 0.f;
+    } else if (i < P_WIH) {
+        const int j = i - P_W2;
+        v = q.p[Q_W2][j] * q.p[Q_LN1W][j & (H - 1)];
+    } else if (i < P_B1) {
+        const int j = i - P_WIH;
+        v = q.p[Q_WIH][j] * q.p[Q_LN2W][j & (H - 1)];
+    } else if (i < P_B2) {
+        const int n = i - P_B1;
+        v = q.p[Q_B1][n] + dot_row(q.p[Q_W1] + n * D, q.p[Q_LN0B], D);
+    } else if (i < P_BIH) {
+        const int n = i - P_B2;
+        v = q.p[Q_B2][n] + dot_row(q.p[Q_W2] + n * H, q.p[Q_LN1B], H);
+    } else {
+        const int n = i - P_BIH;
+        v = q.p[Q_BIH][n] + dot_row(q.p[Q_WIH] + n * H, q.p[Q_LN2B], H);
+    }
+    out[i] = v;
+}
+
+struct GradLayout { int off[Q_N + 1]; };
+__host__ __device__ inline GradLayout grad_layout(int D) {
+    const int n[Q_N] = {D, D, H * D, H, H, H, H * H, H, H, H, G3 * H, G3};
+    GradLayout g;
+    g.off[0] = 0;
+    for (int i = 0; i < Q_N; ++i) g.off[i + 1] = g.off[i] + n[i];
+    return g;
+}
+
+__device__ unsigned int g_unfold_ticket = 0;
+
+// every CTA sums a slice of the [n_ctas][128][ACC_COLS] accumulators into `red`; the last one turns them into gradients:
+// W' = W diag(g), b' = b + W beta  =>  dW = dW' diag(g) + db' beta^T, dg = sum_n dW'[n,:] W[n,:], dbeta = W^T db'
+__global__ void __launch_bounds__(256) agent_mlp_unfold_kernel(const float* __restrict__ acc, int n_ctas, const float* __restrict__ scale,
+                                                                float* __restrict__ red, const ParamPtrs q, float* __restrict__ grads,
+                                                                int D) {
+    __shared__ bool last;
+    const float inv = 1.0f / scale[0];
+    constexpr int kN = kRows * ACC_COLS;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < kN; i += gridDim.x * 256) {
+        float s0 = 0.f, s1 = 0.f;
+        int c = 0;
+        for (; c + 1 < n_ctas; c += 2) {
+            s0 += acc[(size_t)c * kN + i];
+            s1 += acc[(size_t)(c + 1) * kN + i];
+        }
+        if (c < n_ctas) s0 += acc[(size_t)c * kN + i];
+        red[i] = (s0 + s1) * inv;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&g_unfold_ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x == 0) g_unfold_ticket = 0;
+    const GradLayout L = grad_layout(D);
+    const volatile float* r = red;
+    // T1: lanes xh2 feature | 1 [64] x gate column;  T2: lanes xh1 feature | 1 [64] x fc2 output;  T3: 64-row accumulator (row r in
+    // lane 32 (r / 16) + r % 16): rows x0 feature | 1 [48] x fc1 output
+    auto T1 = [&](int lane, int col) { return r[lane * ACC_COLS + col]; };
+    auto T2 = [&](int lane, int col) { return r[lane * ACC_COLS + G3 + col]; };
+    auto T3 = [&](int rr, int col) { return r[(32 * (rr >> 4) + (rr & 15)) * ACC_COLS + G3 + H + col]; };
+    const int tid = threadIdx.x;
+    for (int i = tid; i < H * D; i += 256) {
+        const int n = i / D, k = i - n * D;
+        grads[L.off[Q_W1] + i] = T3(k, n) * q.p[Q_LN0W][k] + T3(K1, n) * q.p[Q_LN0B][k];
+    }
+    for (int k = tid; k < D; k += 256) {
+        float gw = 0.f, gb = 0.f;
+        for (int n = 0; n < H; ++n) {
+            gw = fmaf(T3(k, n), q.p[Q_W1][n * D + k], gw);
+            gb = fmaf(T3(K1, n), q.p[Q_W1][n * D + k], gb);
+        }
+        grads[L.off[Q_LN0W] + k] = gw;
+        grads[L.off[Q_LN0B] + k] = gb;
+    }
+    for (int i = tid; i < H * H; i += 256) {
+        const int n = i / H, k = i & (H - 1);
+        grads[L.off[Q_W2] + i] = T2(k, n) * q.p[Q_LN1W][k] + T2(H, n) * q.p[Q_LN1B][k];
+    }
+    for (int i = tid; i < G3 * H; i += 256) {
+        const int g = i / H, k = i & (H - 1);
+        grads[L.off[Q_WIH] + i] = T1(k, g) * q.p[Q_LN2W][k] + T1(H, g) * q.p[Q_LN2B][k];
+    }
+    for (int g = tid; g < G3; g += 256) grads[L.off[Q_BIH] + g] = T1(H, g);
+    for (int k = tid; k < H; k += 256) {
+        grads[L.off[Q_B1] + k] = T3(K1, k);
+        grads[L.off[Q_B2] + k] = T2(H, k);
+        float gw1 = 0.f, gb1 = 0.f, gw2 = 0.f, gb2 = 0.f;
+        for (int n = 0; n < H; ++n) {
+            gw1 = fmaf(T2(k, n), q.p[Q_W2][n * H + k], gw1);
+            gb1 = fmaf(T2(H, n), q.p[Q_W2][n * H + k], gb1);
+        }
+        for (int g = 0; g < G3; ++g) {
+            gw2 = fmaf(T1(k, g), q.p[Q_WIH][g * H + k], gw2);
+            gb2 = fmaf(T1(H, g), q.p[Q_WIH][g * H + k], gb2);
+        }
+        grads[L.off[Q_LN1W] + k] = gw1; grads[L.off[Q_LN1B] + k] = gb1;
+        grads[L.off[Q_LN2W] + k] = gw2; grads[L.off[Q_LN2B] + k] = gb2;
+    }
+}
+
+__device__ unsigned int g_ticket_fwd = 0, g_ticket_bwd = 0;
+
+unsigned int* ticket_ptr(bool bwd) {
+    void* p = nullptr;
+    if (bwd) cudaGetSymbolAddress(&p, g_ticket_bwd);
+    else     cudaGetSymbolAddress(&p, g_ticket_fwd);
+    return static_cast<unsigned int*>(p);
 }
 
 int n_sms() {
@@ -464,6 +616,38 @@ extern "C" int mm_agent_mlp_dims(int32_t* d) {
     return MM_OK;
 }
 
+static bool take_ptrs(const void* const* params12, ParamPtrs& q) {
+    if (!params12) return false;
+    for (int i = 0; i < Q_N; ++i) {
+        if (!params12[i]) return false;
+        q.p[i] = static_cast<const float*>(params12[i]);
+    }
+    return true;
+}
+
+// params12: HOST array of the 12 device pointers ln0_w, ln0_b, w1 [64][D], b1, ln1_w, ln1_b, w2, b2, ln2_w, ln2_b, w_ih [192][64], b_ih
+extern "C" int mm_agent_mlp_pack(const void* const* params12, float* packed, int32_t D, void* stream) {
+    ParamPtrs q;
+    if (!take_ptrs(params12, q) || !packed || D < 1 || D > K1) return MM_ERR_BAD_ARG;
+    agent_mlp_pack_kernel<<<(P_TOTAL + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, packed, D);
+    return mm::check_launch();
+}
+
+extern "C" int mm_agent_mlp_grad_layout(int32_t D, int32_t* offsets13) {
+    if (!offsets13 || D < 1 || D > K1) return MM_ERR_BAD_ARG;
+    const GradLayout g = grad_layout(D);
+    for (int i = 0; i <= Q_N; ++i) offsets13[i] = g.off[i];
+    return MM_OK;
+}
+
+extern "C" int mm_agent_mlp_unfold(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params12,
+                                   float* grads, int32_t D, void* stream) {
+    ParamPtrs q;
+    if (!take_ptrs(params12, q) || !acc || !scale || !red || !grads || n_ctas < 1 || D < 1 || D > K1) return MM_ERR_BAD_ARG;
+    agent_mlp_unfold_kernel<<<80, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, grads, D);
+    return mm::check_launch();
+}
+
 extern "C" int mm_agent_mlp_bwd_ctas(int64_t rows) {
     const long long tiles = (rows + kRows - 1) / kRows;
     return (int)(tiles < n_sms() ? tiles : n_sms());
@@ -478,6 +662,7 @@ extern "C" int mm_agent_mlp_fwd(const float* params, const float* obs, float* gi
     Args a{};
     a.params = params; a.obs = obs; a.gi = gi; a.saved_rows = saved_rows; a.saved_x0 = static_cast<__half*>(saved_x0);
     a.D = D; a.rows = rows; a.n_tiles = (rows + kRows - 1) / kRows;
+    a.ticket = ticket_ptr(false);
     cudaError_t e = cudaFuncSetAttribute(agent_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_BYTES);
     if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
     const long long want = a.n_tiles, cap = 2LL * n_sms();
@@ -493,6 +678,7 @@ extern "C" int mm_agent_mlp_bwd(const float* params, const float* saved_rows, co
     a.params = params; a.saved_rows = const_cast<float*>(saved_rows);
     a.saved_x0 = static_cast<__half*>(const_cast<void*>(saved_x0)); a.dgi = dgi; a.scale = scale; a.acc = acc;
     a.rows = rows; a.n_tiles = (rows + kRows - 1) / kRows;
+    a.ticket = ticket_ptr(true);
     const int grid = mm_agent_mlp_bwd_ctas(rows);
     if (n_acc_ctas < grid) return MM_ERR_BAD_ARG;
     cudaError_t e = cudaFuncSetAttribute(agent_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_BYTES);

@@ -16,7 +16,6 @@ from ..ops.gram import colsum, gram
 
 H, K1 = 64, 48
 _DIMS = None
-_M64_LANES = [32 * (r // 16) + r % 16 for r in range(64)]      # where row r of a 64-row tcgen05 accumulator lives in TMEM
 
 
 def dims():
@@ -32,15 +31,33 @@ def agent_mlp_fits(in_dim, hidden, layer_N=1):
     return hidden == H and 1 <= in_dim <= K1 and layer_N == 1
 
 
+_GRAD_LAYOUT = {}
+
+
+def _grad_layout(D):
+    if D not in _GRAD_LAYOUT:
+        o = (C.c_int32 * 13)()
+        _lib.check(_lib.lib().mm_agent_mlp_grad_layout(D, o))
+        _GRAD_LAYOUT[D] = list(o)
+    return _GRAD_LAYOUT[D]
+
+
+def _ptr_array(params):
+    arr = (C.c_void_p * len(params))()
+    for i, t in enumerate(params):
+        assert t.is_contiguous() and t.dtype == torch.float32
+        arr[i] = t.data_ptr()
+    return arr
+
+
 class _AgentMlpFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, obs, ln0_w, ln0_b, w1, b1, ln1_w, ln1_b, w2, b2, ln2_w, ln2_b, wih, bih):
+    def forward(ctx, obs, *params):                 # params: ln0_w, ln0_b, w1, b1, ln1_w, ln1_b, w2, b2, ln2_w, ln2_b, wih, bih
         rows, D = obs.shape
         d = dims()
-        w1p = torch.zeros((H, K1), dtype=torch.float32, device=obs.device)
-        w1p[:, :D] = w1 * ln0_w
-        packed = torch.cat([w1p.reshape(-1), (w2 * ln1_w).reshape(-1), (wih * ln2_w).reshape(-1), b1 + w1 @ ln0_b,
-                            b2 + w2 @ ln1_b, bih + wih @ ln2_b])
+        params = [t.detach().contiguous() for t in params]
+        packed = torch.empty(d["n_params"], dtype=torch.float32, device=obs.device)
+        _lib.check(_lib.lib().mm_agent_mlp_pack(_ptr_array(params), _lib.ptr(packed), D, _lib.stream()))
         gi = torch.empty((rows, 3 * H), dtype=torch.float32, device=obs.device)
         train = any(ctx.needs_input_grad[1:])
         saved_rows = saved_x0 = None
@@ -51,13 +68,14 @@ class _AgentMlpFn(torch.autograd.Function):
         _lib.check(_lib.lib().mm_agent_mlp_fwd(_lib.ptr(packed), _lib.ptr(obs), _lib.ptr(gi), _lib.ptr(saved_rows),
                                                _lib.ptr(saved_x0), rows, D, _lib.stream()))
         if train:
-            ctx.save_for_backward(packed, saved_rows, saved_x0, ln0_w, ln0_b, w1, ln1_w, ln1_b, w2, ln2_w, ln2_b, wih)
+            ctx.save_for_backward(packed, saved_rows, saved_x0, *params)
             ctx.dims = (rows, D)
         return gi
 
     @staticmethod
     def backward(ctx, dgi):
-        packed, saved_rows, saved_x0, ln0_w, ln0_b, w1, ln1_w, ln1_b, w2, ln2_w, ln2_b, wih = ctx.saved_tensors
+        packed, saved_rows, saved_x0 = ctx.saved_tensors[:3]
+        params = list(ctx.saved_tensors[3:])
         rows, D = ctx.dims
         d = dims()
         dgi = dgi.contiguous()
@@ -68,19 +86,14 @@ class _AgentMlpFn(torch.autograd.Function):
         acc = torch.empty((n_ctas, d["tile_rows"], d["acc_cols"]), dtype=torch.float32, device=dgi.device)
         _lib.check(lib.mm_agent_mlp_bwd(_lib.ptr(packed), _lib.ptr(saved_rows), _lib.ptr(saved_x0), _lib.ptr(dgi), _lib.ptr(scale),
                                         _lib.ptr(acc), n_ctas, rows, _lib.stream()))
-        A = acc.sum(0) / scale[0]
-        # columns [0,192): lanes xh2 feature | 1 [64] x gate; [192,256): lanes xh1 feature | 1 [64] x fc2 output;
-        # [256,320): 64-row accumulator, rows x0 feature | 1 [48] x fc1 output
-        gwih, gbih = A[:H, :3 * H].t(), A[H, :3 * H]
-        gw2, gb2 = A[:H, 3 * H:4 * H].t(), A[H, 3 * H:4 * H]
-        t3 = A[_M64_LANES, 4 * H:5 * H]
-        gw1, gb1 = t3[:D].t(), t3[K1]
-        # unfold W' = W diag(g), b' = b + W beta:  dW = dW' diag(g) + outer(db', beta), dg = sum_n dW'[n, :] W[n, :], dbeta = W^T db'
-        unfold = lambda gw, gb, w, g, b: (gw * g + torch.outer(gb, b), (gw * w).sum(0), w.t() @ gb)
-        dw1, dg0, db0 = unfold(gw1, gb1, w1, ln0_w, ln0_b)
-        dw2, dg1, db1 = unfold(gw2, gb2, w2, ln1_w, ln1_b)
-        dwih, dg2, db2 = unfold(gwih, gbih, wih, ln2_w, ln2_b)
-        return None, dg0, db0, dw1, gb1, dg1, db1, dw2, gb2, dg2, db2, dwih, gbih
+        # one launch: sum over the CTAs, 1 / scale, LayerNorm affines unfolded into the gradients of the module's own tensors
+        off = _grad_layout(D)
+        flat = torch.empty(off[-1], dtype=torch.float32, device=dgi.device)
+        red = torch.empty(d["tile_rows"] * d["acc_cols"], dtype=torch.float32, device=dgi.device)
+        _lib.check(lib.mm_agent_mlp_unfold(_lib.ptr(acc), n_ctas, _lib.ptr(scale), _lib.ptr(red), _ptr_array(params), _lib.ptr(flat),
+                                           D, _lib.stream()))
+        return (None,) + tuple(flat[off[i]: off[i + 1]].view_as(params[i]) if ctx.needs_input_grad[1 + i] else None
+                               for i in range(len(params)))
 
 
 def agent_mlp_gi(obs2d, ln0, fc1, ln1, fc2, ln2, w_ih, b_ih):

@@ -221,3 +221,61 @@ def test_q_select_and_td_kernels_against_torch(cuda):
     td = err.abs().detach()
     assert torch.allclose(prio, (0.1 * td.mean(0) + 0.9 * td.max(0)[0]).flatten() + 1e-6, rtol=1e-5)
     assert abs(qmean.item() - (q2.detach() * (1 - bad)).mean().item()) < 1e-6
+
+
+def test_graphed_update_replays_the_eager_update(cuda):
+    """GraphedUpdate (PER draw + gather, train_policy_on_batch on both streams, priority write-back, soft target update captured
+    as ONE CUDA graph) against the same four updates launched eagerly: same PER draws, so the same batches -- parameters after four
+    Adam steps within 2e-3 of their norm (TF32-class kernels with atomics in the reductions: not bit-identical), priority trees
+    within 1e-3 of the total mass."""
+    import copy
+    from minimarl_b200.algorithms import QMix, QMixPolicy
+    from minimarl_b200.algorithms.qmix import GraphedUpdate
+    from minimarl_b200.buffers import PrioritizedRecReplayBuffer
+    flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        T, A, D, NA, S, B = 10, 2, 47, 5, 96, 32
+        args = _args(fused_precision="tf32", episode_length=T, batch_size=B)
+        info = {"policy_0": {"obs_space": Box(np.zeros(D), np.ones(D)), "share_obs_space": Box(np.zeros(A * D), np.ones(A * D)),
+                             "act_space": Discrete(NA)}}
+        pconf = {"cent_obs_dim": A * D, "cent_act_dim": A * NA, "obs_space": info["policy_0"]["obs_space"],
+                 "share_obs_space": info["policy_0"]["share_obs_space"], "act_space": info["policy_0"]["act_space"]}
+        results = []
+        for graphed in (False, True):
+            torch.manual_seed(7)
+            buf = PrioritizedRecReplayBuffer(0.6, info, {"policy_0": [0, 1]}, S, T, True, False, device=cuda)
+            pb = buf.policy_buffers["policy_0"]
+            g = torch.Generator(device=cuda).manual_seed(3)
+            pb.obs.copy_(torch.rand(pb.obs.shape, device=cuda, generator=g))
+            pb.share_obs.copy_(pb.obs.reshape(T + 1, S, A * D))
+            pb.acts.copy_(torch.nn.functional.one_hot(torch.randint(0, NA, (T, S, A), device=cuda, generator=g), NA).float())
+            pb.rewards.copy_(torch.randn(pb.rewards.shape, device=cuda, generator=g))
+            pb.dones.zero_(); pb.dones_env.zero_(); pb.dones_env[-1] = 1
+            pb.filled_i, pb.current_i = S, 0
+            buf.update_priorities(torch.arange(S, device=cuda), torch.rand(S, device=cuda, generator=g) * 0.99 + 0.01, "policy_0")
+            buf.seed(11)
+            policy = QMixPolicy(args, {"args": args, "device": cuda, "num_agents": A}, pconf)
+            trainer = QMix(args, A, B, {"policy_0": policy}, lambda a: "policy_0", device=cuda, episode_length=T)
+            losses = []
+            if graphed:
+                gu = GraphedUpdate(trainer, buf, B)
+                for _ in range(4):
+                    losses.append(float(gu(0.4)["loss"]))
+            else:
+                for _ in range(4):
+                    u = torch.rand(B, dtype=torch.float64, device=cuda, generator=buf._gen)
+                    sample = buf.sample(B, beta=0.4, p_id="policy_0", uniforms=u)
+                    info_, prio, idx = trainer.train_policy_on_batch(sample)
+                    buf.update_priorities(idx, prio, "policy_0")
+                    trainer.soft_target_updates()
+                    losses.append(float(info_["loss"]))
+            results.append((losses, [p.detach().clone() for p in trainer.parameters],
+                            buf._it_sums["policy_0"]._value.clone()))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = flags
+    (la, pa, ta), (lb, pb_, tb) = results
+    assert np.allclose(la, lb, rtol=2e-3), (la, lb)
+    for x, y in zip(pa, pb_):
+        assert float((x - y).norm()) <= 2e-3 * float(y.norm()) + 1e-6
+    assert float((ta - tb).abs().max()) <= 1e-3 * float(tb[1])
