@@ -142,7 +142,7 @@ class _GruFromGiFn(torch.autograd.Function):
         dghn2 = dghn.view(T * R, Hh)
         dw_hh_all = gram(dgi, hp2)                       # the n rows of this product are discarded: one pass over hp2
         dw_hh = torch.cat((dw_hh_all[:2 * Hh], gram(dghn2, hp2)), dim=0)
-        db_hh = torch.cat((colsum(dgi[:, :2 * Hh].contiguous()), colsum(dghn2)))
+        db_hh = torch.cat((colsum(dgi)[:2 * Hh], colsum(dghn2)))          # b_hh's r and z gradients are b_ih's
         return dgi, (dh0 if (has_h0 and ctx.needs_input_grad[1]) else None), dw_hh, db_hh, None, None
 
 
