@@ -237,6 +237,25 @@ int mm_qmixer_tc_param_offsets(int32_t SD, int32_t A, int32_t* offsets_host);
 int mm_qmixer_tc_forward(const float* params, const float* agent_q, const float* states, float* q_tot,
                          int64_t M, int32_t SD, int32_t A, void* stream);
 
+/* The differentiated (live) mixer of QMix.train_policy_on_batch (offpolicy/algorithms/qmix/qmix.py:150-208 through
+ * q_mixer.py:68-94): forward = mm_qmixer_tc_forward on a buffer packed by mm_qmixer_tc_pack straight from the module tensors;
+ * backward = mm_qmixer_bwd, ONE kernel that recomputes the activations of a 128-row tile and contracts every weight gradient on
+ * tcgen05 (csrc/mixer_bwd.cu), followed by mm_qmixer_bwd_unfold (sum over CTAs, scale removed, the 14 gradient tensors back to
+ * back in module order; offsets from mm_qmixer_bwd_grad_layout).
+ *   params14: HOST array of the 14 device pointers in QMixer.parameters() order (hyper_w1.0.weight, .bias, hyper_w1.2.*,
+ *             hyper_w2.0.*, hyper_w2.2.*, hyper_b1.*, hyper_b2.0.*, hyper_b2.2.*), weights [out][in] fp32
+ *   agent_q [M][2], states [M][SD] (SD even, <= 94), dout [M] = dL/dQ_tot, scale = mm_ppo_trunk2_scale(dout); dq [M][2]
+ *   acc [n_acc_ctas >= mm_qmixer_bwd_ctas(M)][128][dims[0]], vec [n_acc_ctas][dims[1]]: per-CTA accumulators (scratch)
+ *   mm_qmixer_bwd_dims -> {accumulator columns, vector floats, tile rows, gradient floats}. */
+int mm_qmixer_tc_pack(const void* const* params14, float* packed, int32_t SD, int32_t n_agents, void* stream);
+int mm_qmixer_bwd_dims(int32_t SD, int32_t* dims4);
+int mm_qmixer_bwd_ctas(int64_t M);
+int mm_qmixer_bwd_grad_layout(int32_t SD, int32_t* offsets15);
+int mm_qmixer_bwd(const void* const* params14, const float* agent_q, const float* states, const float* dout, const float* scale,
+                  float* dq, float* acc, float* vec, int32_t n_acc_ctas, int64_t M, int32_t SD, int32_t n_agents, void* stream);
+int mm_qmixer_bwd_unfold(const float* acc, const float* vec, int32_t n_ctas, const float* scale, float* grads, int32_t SD,
+                         void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Tail of QMix.train_policy_on_batch (offpolicy/algorithms/qmix/qmix.py:134-191).
  * mm_q_select: rows r = a*B + b.  q_all / target_q_all [T+1,R,NA], acts [T,R,NA] (one-hot rows; arg-max
@@ -630,6 +649,20 @@ int mm_ppo_value_loss_bwd(const float* values, const float* value_preds, const f
 /* Column sums of a row-major float32 matrix x [rows, C] (C <= 256) accumulated into out [C] (caller zeroes): the bias
  * gradients of the learner's Linear / GRU layers (what autograd computes with dY.sum(0)). */
 int mm_colsum(const float* x, float* out, int64_t rows, int32_t C, void* stream);
+
+/* Gradient-norm clipping + Adam on one flat fp32 parameter buffer (csrc/optim.cu): what the learners run after each backward
+ * pass -- torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam.step()
+ * (offpolicy/algorithms/qmix/qmix.py:200-208, mappo/algorithms/ramppo_network.py:181-209, vdn/_train.py:96-100) -- as two
+ * launches.  params / grads / exp_avg / exp_avg_sq [n] (device); step: device float, advanced by one inside the call (Adam's
+ * bias-correction exponent); scratch: mm_clip_adam_scratch_doubles() doubles; norm_out (optional): the total gradient 2-norm
+ * before clipping (what clip_grad_norm_ returns).  max_norm <= 0: no clipping.  clip_n <= n: the norm is taken over, and the
+ * coefficient applied to, the first clip_n elements only (qmix/_train.py:113-115 clips the q-network but steps the mixer too).  Update rule and operation order of
+ * torch.optim.Adam (no amsgrad / maximize): g' = g * min(1, max_norm / (norm + 1e-6)) (+ weight_decay * p),
+ * m += (g' - m)(1 - beta1), v = beta2 v + (1 - beta2) g'^2, p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps). */
+int mm_clip_adam_scratch_doubles(void);
+int mm_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step, double* scratch,
+                      float* norm_out, int64_t n, int64_t clip_n, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, float max_norm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ from ..nn.gru import GRU
 from ..nn.layernorm import LayerNorm
 from ..nn.ppo_trunk import ChunkRows, ppo_trunk, trunk_fits
 from ..ops.ppo_loss import ppo_actor_loss, ppo_value_loss
+from ..optim import FlatAdam, clip_and_step, make_adam
 from ..parallel import GradBucket, allreduce_mean_grads, allreduce_stats
 
 
@@ -333,10 +334,11 @@ class R_MAPPOPolicy:
         self.obs_space, self.share_obs_space, self.act_space = obs_space, cent_obs_space, act_space
         self.actor = R_Actor(args, obs_space, act_space, device)
         self.critic = R_Critic(args, cent_obs_space, device)
-        self.actor_optimizer = torch.optim.Adam(self.actor.parameters(), lr=self.actor_lr, eps=self.opti_eps,
-                                                weight_decay=self.weight_decay)
-        self.critic_optimizer = torch.optim.Adam(self.critic.parameters(), lr=self.critic_lr, eps=self.opti_eps,
-                                                 weight_decay=self.weight_decay)
+        # FlatAdam on the GPU (optim.py: clip + Adam as two launches on flat buffers), torch.optim.Adam for host parameters
+        self.actor_optimizer = make_adam(self.actor.parameters(), lr=self.actor_lr, eps=self.opti_eps,
+                                         weight_decay=self.weight_decay)
+        self.critic_optimizer = make_adam(self.critic.parameters(), lr=self.critic_lr, eps=self.opti_eps,
+                                          weight_decay=self.weight_decay)
 
     def lr_decay(self, episode, episodes):
         for opt, lr0 in ((self.actor_optimizer, self.actor_lr), (self.critic_optimizer, self.critic_lr)):
@@ -448,17 +450,15 @@ class R_MAPPO:
         if update_actor:
             (policy_loss - dist_entropy * self.entropy_coef).backward()
         allreduce_mean_grads(list(self.policy.actor.parameters()), bucket=self._buckets.get(id(self.policy.actor)))
-        actor_grad_norm = nn.utils.clip_grad_norm_(self.policy.actor.parameters(), self.max_grad_norm) \
-            if self._use_max_grad_norm else _grad_norm(self.policy.actor.parameters())
-        self.policy.actor_optimizer.step()
+        actor_grad_norm = clip_and_step(self.policy.actor_optimizer, list(self.policy.actor.parameters()),
+                                         self.max_grad_norm if self._use_max_grad_norm else 0.0)
 
         value_loss = self.cal_value_loss(values, value_preds_batch, return_batch, active_masks_batch)
         self._zero_grads(self.policy.critic, self.policy.critic_optimizer)
         (value_loss * self.value_loss_coef).backward()
         allreduce_mean_grads(list(self.policy.critic.parameters()), bucket=self._buckets.get(id(self.policy.critic)))
-        critic_grad_norm = nn.utils.clip_grad_norm_(self.policy.critic.parameters(), self.max_grad_norm) \
-            if self._use_max_grad_norm else _grad_norm(self.policy.critic.parameters())
-        self.policy.critic_optimizer.step()
+        critic_grad_norm = clip_and_step(self.policy.critic_optimizer, list(self.policy.critic.parameters()),
+                                         self.max_grad_norm if self._use_max_grad_norm else 0.0)
         return value_loss, critic_grad_norm, policy_loss, dist_entropy, actor_grad_norm, imp_weights
 
     def _zero_grads(self, module, optimizer):
@@ -466,7 +466,10 @@ class R_MAPPO:
         trunk op write straight into it, the exchange is one all-reduce on the flat buffer), zeroed here instead of
         ``optimizer.zero_grad()`` so that the views survive.  Single GPU: plain ``zero_grad``."""
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if isinstance(optimizer, FlatAdam):
+            self._buckets[id(module)] = optimizer.bucket
+            optimizer.zero_grad()
+        elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             b = self._buckets.get(id(module))
             if b is None or not b.attached():
                 b = self._buckets[id(module)] = GradBucket(list(module.parameters()))
@@ -488,9 +491,8 @@ class R_MAPPO:
         if update_actor:
             (policy_loss - dist_entropy * self.entropy_coef).backward()
         allreduce_mean_grads(list(actor.parameters()), bucket=self._buckets.get(id(actor)))
-        actor_grad_norm = nn.utils.clip_grad_norm_(actor.parameters(), self.max_grad_norm) \
-            if self._use_max_grad_norm else _grad_norm(actor.parameters())
-        self.policy.actor_optimizer.step()
+        actor_grad_norm = clip_and_step(self.policy.actor_optimizer, list(actor.parameters()),
+                                         self.max_grad_norm if self._use_max_grad_norm else 0.0)
 
         if critic._chunk_fusable(to(share_obs_batch), to(rnn_states_critic_batch)):
             values = critic._fused_chunks(to(share_obs_batch), to(rnn_states_critic_batch), to(masks_batch))
@@ -501,9 +503,8 @@ class R_MAPPO:
         self._zero_grads(self.policy.critic, self.policy.critic_optimizer)
         (value_loss * self.value_loss_coef).backward()
         allreduce_mean_grads(list(critic.parameters()), bucket=self._buckets.get(id(critic)))
-        critic_grad_norm = nn.utils.clip_grad_norm_(critic.parameters(), self.max_grad_norm) \
-            if self._use_max_grad_norm else _grad_norm(critic.parameters())
-        self.policy.critic_optimizer.step()
+        critic_grad_norm = clip_and_step(self.policy.critic_optimizer, list(critic.parameters()),
+                                         self.max_grad_norm if self._use_max_grad_norm else 0.0)
         return value_loss, critic_grad_norm, policy_loss, dist_entropy, actor_grad_norm, ratio
 
     def train(self, buffer, update_actor=True, perms=None):
@@ -553,7 +554,3 @@ class R_MAPPO:
     def prep_rollout(self):
         self.policy.actor.eval()
         self.policy.critic.eval()
-
-
-def _grad_norm(params):
-    return torch.sqrt(sum((p.grad.norm() ** 2 for p in params if p.grad is not None)))

@@ -23,6 +23,7 @@ import torch
 
 from ..nn import AgentQFunction, QMixer, VDNMixer
 from ..ops.td import q_select, qmix_td_loss
+from ..optim import FlatAdam, clip_and_step, make_adam
 from ..parallel import GradBucket, allreduce_mean_grads
 
 
@@ -169,9 +170,11 @@ class QMix:
         for policy in policies.values():
             self.parameters += policy.parameters()
         self.parameters += self.mixer.parameters()
-        # capturable: the step counter lives on the device, so a whole update can be replayed as a CUDA graph (GraphedUpdate)
-        self.optimizer = torch.optim.Adam(params=self.parameters, lr=self.lr, eps=self.opti_eps,
-                                          capturable=self.device.type == "cuda")
+        # FlatAdam (optim.py): parameters and gradients live in flat buffers, clip + Adam are two launches, the step counter
+        # lives on the device, so a whole update can be replayed as a CUDA graph (GraphedUpdate)
+        self.optimizer = make_adam(self.parameters, lr=self.lr, eps=self.opti_eps)
+        if isinstance(self.optimizer, FlatAdam):
+            self._bucket = self.optimizer.bucket
         self.batch_size = batch_size
         self.overlap_target = True
         self._side_stream = torch.cuda.Stream(device=self.device)
@@ -183,7 +186,9 @@ class QMix:
     def _zero_grads(self):
         """Multi-GPU: gradients of every parameter live in one flat ``GradBucket`` (views), see parallel.py."""
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if isinstance(self.optimizer, FlatAdam):
+            self.optimizer.zero_grad()
+        elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             b = getattr(self, "_bucket", None)
             if b is None or not b.attached():
                 b = self._bucket = GradBucket(self.parameters)
@@ -252,8 +257,7 @@ class QMix:
         self._zero_grads()
         loss.backward()
         self._allreduce_grads()
-        grad_norm = torch.nn.utils.clip_grad_norm_(self.parameters, self.args.max_grad_norm)
-        self.optimizer.step()
+        grad_norm = clip_and_step(self.optimizer, self.parameters, self.args.max_grad_norm)
         train_info = {"loss": loss.detach(), "grad_norm": grad_norm, "Q_tot": q_tot_mean}
         return train_info, new_priorities, idxes
 

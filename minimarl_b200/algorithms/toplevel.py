@@ -27,6 +27,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
+from ..optim import clip_and_step
 from . import toplevel_fused as tf
 
 
@@ -517,8 +518,7 @@ class Target_Dqn(_GraphedIterations):
         se, dq, td_last = tf.vdn_chunk_loss(q_beh, q_tgt, per.actions, per.rewards, per.dones, data, w.reshape(-1).contiguous(),
                                             self.gamma)
         tf.qnet_backward(beh, per.states, data, per.dones, save, dq, B, L)
-        torch.nn.utils.clip_grad_norm_(parameters=beh.parameters(), max_norm=self.grad_clip_norm, norm_type=2)
-        optimizer.step()
+        clip_and_step(optimizer, beh.parameters(), self.grad_clip_norm)
         per.update(node, td_last)
         return se.sum() / B
 
@@ -584,8 +584,7 @@ class Train_dqn(_GraphedIterations):
         se, dqtot, td_last = tf.qmix_chunk_loss(qtot, qtot_tgt, per.rewards, per.dones, data, w.reshape(-1).contiguous(), self.gamma)
         dq = tf.mix_backward(mix, per.states, data, per.dones, q_beh, per.actions, msave, dqtot, B, L)
         tf.qnet_backward(q_net, per.states, data, per.dones, save, dq, B, L)
-        torch.nn.utils.clip_grad_norm_(parameters=q_net.parameters(), max_norm=self.grad_clip_norm, norm_type=2)
-        optimizer.step()
+        clip_and_step(optimizer, q_net.parameters(), self.grad_clip_norm, prefix=True)
         per.update(node, td_last)
         return se.sum() / B
 

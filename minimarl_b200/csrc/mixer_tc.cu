@@ -192,7 +192,47 @@ qmixer_tc_kernel(const float* __restrict__ params, const float* __restrict__ age
     if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+// module tensors (QMixer.parameters() order: hyper_w1.0, hyper_w1.2, hyper_w2.0, hyper_w2.2, hyper_b1, hyper_b2.0, hyper_b2.2; weight
+// then bias) -> the packed buffer above, one launch (the live mixer repacks after every optimiser step)
+struct ModulePtrs { const float* p[14]; };
+__global__ void __launch_bounds__(256) qmixer_tc_pack_kernel(const ModulePtrs q, float* __restrict__ out, int SD) {
+    const Layout L = make_layout();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= L.total) return;
+    float v = 0.f;
+    if (i < L.w1b) {
+        const int n = i / K1, k = i - n * K1;
+        if (k < SD) {
+            if (n < HH) v = q.p[0][n * SD + k];
+            else if (n < 2 * HH) v = q.p[4][(n - HH) * SD + k];
+            else if (n < 3 * HH) v = q.p[10][(n - 2 * HH) * SD + k];
+            else v = q.p[8][(n - 3 * HH) * SD + k];
+        }
+    } else if (i < L.w2b) v = q.p[2][i - L.w1b];
+    else if (i < L.bcat) v = q.p[6][i - L.w2b];
+    else if (i < L.b1b) {
+        const int n = i - L.bcat;
+        v = n < HH ? q.p[1][n] : n < 2 * HH ? q.p[5][n - HH] : n < 3 * HH ? q.p[11][n - 2 * HH] : q.p[9][n - 3 * HH];
+    } else if (i < L.b2b) v = q.p[3][i - L.b1b];
+    else if (i < L.wb2) v = q.p[7][i - L.b2b];
+    else if (i < L.bb2) v = q.p[12][i - L.wb2];
+    else if (i == L.bb2) v = q.p[13][0];
+    out[i] = v;
+}
+
 }  // namespace
+
+extern "C" int mm_qmixer_tc_pack(const void* const* params14, float* packed, int32_t SD, int32_t n_agents, void* stream) {
+    if (!params14 || !packed) return MM_ERR_BAD_ARG;
+    if (SD <= 0 || SD > K1 || (SD & 1) || n_agents != A) return MM_ERR_UNSUPPORTED;
+    ModulePtrs q;
+    for (int i = 0; i < 14; ++i) {
+        if (!params14[i]) return MM_ERR_BAD_ARG;
+        q.p[i] = static_cast<const float*>(params14[i]);
+    }
+    qmixer_tc_pack_kernel<<<(make_layout().total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, packed, SD);
+    return mm::check_launch();
+}
 
 extern "C" int mm_qmixer_tc_param_count(int32_t SD, int32_t n_agents) {
     if (SD <= 0 || SD > K1 || (SD & 1) || n_agents != A) return MM_ERR_UNSUPPORTED;

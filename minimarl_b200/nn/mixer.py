@@ -106,6 +106,68 @@ class _MixingFn(torch.autograd.Function):
         return dq, dw1, db1, dw2, db2
 
 
+def _ptr_array(params):
+    arr = (C.c_void_p * len(params))()
+    for i, t in enumerate(params):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise RuntimeError("minimarl_b200 fused mixer takes contiguous float32 CUDA parameters (no CPU fallback)")
+        arr[i] = t.data_ptr()
+    return arr
+
+
+_BWD_DIMS = {}
+
+
+def _bwd_dims(SD):
+    if SD not in _BWD_DIMS:
+        d, off = (C.c_int32 * 4)(), (C.c_int32 * 15)()
+        _lib.check(_lib.lib().mm_qmixer_bwd_dims(SD, d))
+        _lib.check(_lib.lib().mm_qmixer_bwd_grad_layout(SD, off))
+        _BWD_DIMS[SD] = (list(d), list(off))
+    return _BWD_DIMS[SD]
+
+
+class _QMixerLiveFn(torch.autograd.Function):
+    """The differentiated mixer as two kernels: forward = ``mm_qmixer_tc_forward`` (nothing saved but the inputs), backward =
+    ``mm_qmixer_bwd`` (recomputes a 128-row tile's activations, dq and every weight gradient on tcgen05) + ``_unfold``.
+    params: the 14 tensors of ``QMixer.parameters()`` (hypernet_layers == 2) in module order."""
+
+    @staticmethod
+    def forward(ctx, q, states, *params):
+        M, A = q.shape
+        SD = states.shape[1]
+        lib = _lib.lib()
+        q, states = q.contiguous(), states.contiguous()
+        params = [t.detach().contiguous() for t in params]
+        packed = torch.empty(lib.mm_qmixer_tc_param_count(SD, A), dtype=torch.float32, device=q.device)
+        _lib.check(lib.mm_qmixer_tc_pack(_ptr_array(params), _lib.ptr(packed), SD, A, _lib.stream()))
+        out = torch.empty(M, dtype=torch.float32, device=q.device)
+        _lib.check(lib.mm_qmixer_tc_forward(_lib.ptr(packed), _lib.ptr(q), _lib.ptr(states), _lib.ptr(out), M, SD, A, _lib.stream()))
+        ctx.save_for_backward(q, states, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, states = ctx.saved_tensors[:2]
+        params = list(ctx.saved_tensors[2:])
+        M, A = q.shape
+        SD = states.shape[1]
+        lib = _lib.lib()
+        (acc_cols, vec_n, tile_rows, n_grads), off = _bwd_dims(SD)
+        dout = dout.contiguous()
+        z = dict(dtype=torch.float32, device=q.device)
+        scale = torch.empty(2, **z)
+        _lib.check(lib.mm_ppo_trunk2_scale(_lib.ptr(dout), M, _lib.ptr(scale), _lib.stream()))
+        n_ctas = lib.mm_qmixer_bwd_ctas(M)
+        acc, vec = torch.empty((n_ctas, tile_rows, acc_cols), **z), torch.empty((n_ctas, vec_n), **z)
+        dq, grads = torch.empty_like(q), torch.empty(n_grads, **z)
+        _lib.check(lib.mm_qmixer_bwd(_ptr_array(params), _lib.ptr(q), _lib.ptr(states), _lib.ptr(dout), _lib.ptr(scale), _lib.ptr(dq),
+                                     _lib.ptr(acc), _lib.ptr(vec), n_ctas, M, SD, A, _lib.stream()))
+        _lib.check(lib.mm_qmixer_bwd_unfold(_lib.ptr(acc), _lib.ptr(vec), n_ctas, _lib.ptr(scale), _lib.ptr(grads), SD, _lib.stream()))
+        return (dq if ctx.needs_input_grad[0] else None, None) + tuple(
+            grads[off[i]:off[i + 1]].view_as(params[i]) if ctx.needs_input_grad[2 + i] else None for i in range(len(params)))
+
+
 def _init(m, use_orthogonal):
     (nn.init.orthogonal_ if use_orthogonal else nn.init.xavier_uniform_)(m.weight.data, gain=1)
     nn.init.constant_(m.bias.data, 0)
@@ -174,6 +236,12 @@ class QMixer(nn.Module):
                                                         s.shape[0], self.cent_obs_dim, self.num_agents, _lib.stream()))
             return out.view(-1, batch_size, 1, 1)
         states = states.view(-1, batch_size, self.cent_obs_dim).float()
+        if (states.is_cuda and self.fusable and self.tc_ok and self.precision == "tf32" and self.cent_obs_dim <= 94
+                and torch.backends.cuda.matmul.allow_tf32):
+            # differentiated pass on the tensor cores: forward kernel + ONE backward kernel with the weight gradients inside
+            out = _QMixerLiveFn.apply(agent_q_inps.reshape(-1, self.num_agents), states.reshape(-1, self.cent_obs_dim),
+                                      *self.parameters())
+            return out.view(-1, batch_size, 1, 1)
         if states.is_cuda and self.hidden_layer_dim == 32 and self.num_mixer_q_inps in (2, 4):
             # differentiated pass: hypernetworks through cuBLAS, the per-row mixing through one custom kernel
             s2 = states.reshape(-1, self.cent_obs_dim)

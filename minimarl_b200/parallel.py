@@ -28,20 +28,28 @@ class GradBucket:
     never receive a gradient (the reference's unused ``fc_h`` duplicates, quirk Q6) still own a zero slice, on every rank alike.
     """
 
-    def __init__(self, params, n_extra=0):
+    def __init__(self, params, n_extra=0, align=1):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("GradBucket needs at least one parameter")
-        dev, n = self.params[0].device, sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.offsets, n = [], 0                   # ``align`` (floats): start of every slice; the gaps stay zero
+        for p in self.params:
+            self.offsets.append(n)
+            n += -(-p.numel() // align) * align
         self.n_grad, self.n_extra = n, int(n_extra)
         self.flat = torch.zeros(n + self.n_extra, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
+        self.reattach(zero=False)
+
+    def reattach(self, zero=True):
+        """(Re)install the views; existing gradients are copied in unless ``zero``."""
+        if zero:
+            self.flat.zero_()
+        for p, off in zip(self.params, self.offsets):
             view = self.flat[off:off + p.numel()].view_as(p)
-            if p.grad is not None:
+            if p.grad is not None and not zero and p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)
             p.grad = view
-            off += p.numel()
 
     @property
     def grads(self):
@@ -53,12 +61,8 @@ class GradBucket:
 
     def attached(self):
         """False once something replaced a ``p.grad`` (e.g. ``zero_grad(set_to_none=True)``)."""
-        off = 0
-        for p in self.params:
-            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + 4 * off:
-                return False
-            off += p.numel()
-        return True
+        base = self.flat.data_ptr()
+        return all(p.grad is not None and p.grad.data_ptr() == base + 4 * off for p, off in zip(self.params, self.offsets))
 
     def zero(self):
         self.flat.zero_()

@@ -26,6 +26,7 @@ import torch
 from ..algorithms import toplevel_fused as tf
 from ..algorithms.toplevel import Mix_Net, Prioritized_Experience_Replay, Q_Net, Target_Dqn, Train_dqn, cal_td_error
 from ..envs.batched import BatchedCheckers, BatchedSwitch
+from ..optim import make_adam
 from ..utils.sinks import MetricSink, test_line, vdn_line
 
 
@@ -111,6 +112,13 @@ def _fused_episode(beh, tgt, env, per, args, epsilon, seed, step_offset, bufs):
     return out, T * N
 
 
+def _adam(params, lr, fused, capturable):
+    """vdn/main.py:97 / qmix/main.py: ``optim.Adam(params, lr)``; on the fused path the flat two-launch optimiser (optim.py)."""
+    if fused:
+        return make_adam(params, lr=lr, eps=1e-8)
+    return torch.optim.Adam(params, lr=lr, capturable=capturable)
+
+
 def _run(args, env, episodes, mixer, log, timing, sink=None, test=None):
     dev, n_envs = env.device, env.n_envs
     beh = Q_Net(env.observation_space, env.action_space, args).to(dev)
@@ -125,12 +133,12 @@ def _run(args, env, episodes, mixer, log, timing, sink=None, test=None):
     if mixer:
         mix, tmix = Mix_Net(env.observation_space, args).to(dev), Mix_Net(env.observation_space, args).to(dev)
         tmix.load_state_dict(mix.state_dict())
-        opt = torch.optim.Adam([{"params": beh.parameters()}, {"params": mix.parameters()}], lr=args.lr, capturable=use_graph)
+        opt = _adam(list(beh.parameters()) + list(mix.parameters()), args.lr, fused, use_graph)
         trainer = Train_dqn(args, dev)
         train = lambda eps: trainer.train(per, beh, mix, tgt, tmix, opt, eps)
     else:
         mix = tmix = None
-        opt = torch.optim.Adam(beh.parameters(), lr=args.lr, capturable=use_graph)
+        opt = _adam(list(beh.parameters()), args.lr, fused, use_graph)
         trainer = Target_Dqn(per, beh, tgt, args, dev)
         train = lambda eps: trainer.train(target_network=tgt, optimizer=opt, epsilon=eps)
     L = args.chunk_size

@@ -75,7 +75,7 @@ def test_fused_chunk_pass_matches_eager_actor_and_critic(cuda, L, N):
         assert float((lp_f.detach().cpu() - lp_r.detach()).abs().max()) < 1e-2 and abs(float(ent_f.detach()) - float(ent_r.detach())) < 1e-3
         for (k, pr), pf in zip(ref.named_parameters(), fused.parameters()):
             if pr.grad is None:                      # mlp.fc_h: the template layer the reference clones and never calls
-                assert pf.grad is None, k
+                assert pf.grad is None or not pf.grad.any(), k     # (a zero slice of FlatAdam's bucket)
                 continue
             assert _rel(pf.grad.cpu(), pr.grad) < _grad_tol(k), (k, _rel(pf.grad.cpu(), pr.grad))
         # critic

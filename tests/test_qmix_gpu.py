@@ -134,7 +134,7 @@ def test_full_qmix_update_matches_reference(cuda):
             assert np.allclose(p.grad.cpu().numpy(), g[key], rtol=1e-3, atol=2e-5), n
             checked += 1
         else:
-            assert p.grad is None, n                                   # the unused fc_h duplicate
+            assert p.grad is None or not p.grad.any(), n               # the unused fc_h duplicate (a zero slice of FlatAdam's bucket)
     assert checked >= 30
     assert any((a - b).abs().max().item() > 0 for a, b in zip(before, trainer.parameters))
     trainer.soft_target_updates()
@@ -279,3 +279,56 @@ def test_graphed_update_replays_the_eager_update(cuda):
     for x, y in zip(pa, pb_):
         assert float((x - y).norm()) <= 2e-3 * float(y.norm()) + 1e-6
     assert float((ta - tb).abs().max()) <= 1e-3 * float(tb[1])
+
+
+def _mixer_f64(P, q, sd):
+    """q_mixer.py:68-94 in float64; also returns every pre-activation that sits under a ReLU / abs kink."""
+    M, SD = sd.shape
+    lin = lambda x, n: x @ P[n + ".weight"].t() + P[n + ".bias"]
+    h1a, h2a, hba = lin(sd, "hyper_w1.0"), lin(sd, "hyper_w2.0"), lin(sd, "hyper_b2.0")
+    w1raw, w2raw = lin(torch.relu(h1a), "hyper_w1.2"), lin(torch.relu(h2a), "hyper_w2.2")
+    b1 = lin(sd, "hyper_b1").view(M, 1, 32)
+    b2 = lin(torch.relu(hba), "hyper_b2.2").view(M, 1, 1)
+    pre = torch.matmul(q.view(M, 1, 2), w1raw.abs().view(M, 2, 32)) + b1
+    out = (torch.matmul(torch.nn.functional.elu(pre), w2raw.abs().view(M, 32, 1)) + b2).reshape(-1)
+    return out, torch.cat([h1a, h2a, hba, w1raw, w2raw], dim=1)
+
+
+@pytest.mark.parametrize("M,SD", [(1, 94), (300, 94), (128 * 150 + 77, 94), (4099, 46)])
+def test_live_mixer_kernels_match_float64(cuda, M, SD):
+    """The differentiated mixer (forward kernel + mm_qmixer_bwd with the weight gradients inside) against the same function in
+    float64 on the CPU (q_mixer.py:68-94 under autograd).  Operands carry an 11-bit significand (TF32 forward, fp16 tiles in the
+    backward): Q_tot to 2e-3 of its scale, dq and every parameter gradient to 4e-3 relative (Frobenius).  The gradient of
+    ReLU / abs jumps at 0, so any rounding of the forward picks a side there: the rows are drawn so that no pre-activation lies
+    within 2e-3 of a kink (rounding moves them by ~3e-4); the statistical effect of the kinks at full size is covered by the
+    update-level TF32 test above."""
+    from minimarl_b200.nn import QMixer
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.manual_seed(M + SD)
+    mixer = QMixer(_args(fused_precision="tf32"), 2, SD, cuda)
+    with torch.no_grad():
+        for p in mixer.parameters():
+            p.add_(torch.randn_like(p) * 0.05)                            # biases are initialised to zero
+    ref = {k: v.detach().double().cpu() for k, v in mixer.state_dict().items()}
+    q, s = torch.randn(6 * M + 64, 1, 2) * 3, torch.rand(6 * M + 64, 1, SD)
+    with torch.no_grad():
+        _, kinks = _mixer_f64(ref, q.double(), s.double().reshape(-1, SD))
+    keep = (kinks.abs().min(dim=1).values > 2e-3).nonzero().reshape(-1)[:M]
+    assert keep.numel() == M
+    q, s = q[keep].contiguous(), s[keep].contiguous()
+    w = torch.randn(M) * 1e-4                                             # loss-mean sized upstream gradients
+    q_m = q.to(cuda).requires_grad_(True)
+    out = mixer(q_m, s.to(cuda))
+    (out.reshape(-1) * w.to(cuda)).sum().backward()
+
+    P = {k: v.clone().requires_grad_(True) for k, v in ref.items()}
+    q_r = q.double().requires_grad_(True)
+    out_r, _ = _mixer_f64(P, q_r, s.double().reshape(M, SD))
+    (out_r * w.double()).sum().backward()
+
+    scale = out_r.detach().abs().max().item()
+    assert (out.detach().reshape(-1).cpu().double() - out_r.detach()).abs().max().item() < 2e-3 * max(scale, 1.0)
+    rel = lambda a, b: ((a.double().cpu() - b).norm() / b.norm().clamp(min=1e-30)).item()
+    assert rel(q_m.grad.reshape(M, 2), q_r.grad.reshape(M, 2)) < 4e-3
+    for name, p in mixer.named_parameters():
+        assert p.grad is not None and rel(p.grad, P[name].grad) < 4e-3, (name, rel(p.grad, P[name].grad))

@@ -257,7 +257,9 @@ def test_fused_training_iteration_matches_module_iteration(cuda, mixer):
     torch.backends.cuda.matmul.allow_tf32 = False
     D = 3 if mixer else 94
     results = []
-    for fused in (False, True):
+    from minimarl_b200.optim import FlatAdam
+    for fused, flat in ((False, False), (True, False), (True, True)):       # flat: FlatAdam (clip + Adam as two launches)
+        adam = FlatAdam if flat else torch.optim.Adam
         args = _args(fused=fused, batch_size=64)
         per = _filled_per(cuda, args, D, 200)
         beh, tgt = _qnet(cuda, D, args, seed=1), _qnet(cuda, D, args, seed=2)
@@ -266,20 +268,21 @@ def test_fused_training_iteration_matches_module_iteration(cuda, mixer):
             torch.manual_seed(3)
             mix = Mix_Net(beh.observation_space, args).to(cuda)
             tmix = Mix_Net(beh.observation_space, args).to(cuda)
-            opt = torch.optim.Adam(list(beh.parameters()) + list(mix.parameters()), lr=1e-3)
+            opt = adam(list(beh.parameters()) + list(mix.parameters()), lr=1e-3)
             loss = Train_dqn(args, cuda).train(per, beh, mix, tgt, tmix, opt, 0.5, uniforms=u)
             weights = [p.detach().clone() for p in list(beh.parameters()) + list(mix.parameters())]
         else:
-            opt = torch.optim.Adam(beh.parameters(), lr=1e-3)
+            opt = adam(list(beh.parameters()), lr=1e-3)
             loss = Target_Dqn(per, beh, tgt, args, cuda).train(target_network=tgt, optimizer=opt, epsilon=0.5, uniforms=u)
             weights = [p.detach().clone() for p in beh.parameters()]
         results.append((float(loss), per.sum_tree.priority_tree.clone(), weights))
-    (l0, t0, w0), (l1, t1, w1) = results
-    assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
-    assert torch.allclose(t0, t1, rtol=1e-4, atol=1e-9)
-    for a, b in zip(w0, w1):
-        # one Adam step moves every weight by ~lr; a sign flip of a ~0 gradient would show as 2e-3
-        assert (a - b).abs().max().item() < 2e-5, (a - b).abs().max().item()
+    l0, t0, w0 = results[0]
+    for l1, t1, w1 in results[1:]:
+        assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
+        assert torch.allclose(t0, t1, rtol=1e-4, atol=1e-9)
+        for a, b in zip(w0, w1):
+            # one Adam step moves every weight by ~lr; a sign flip of a ~0 gradient would show as 2e-3
+            assert (a - b).abs().max().item() < 2e-5, (a - b).abs().max().item()
 
 
 def test_add_set_and_set_leaves_contract(cuda):
