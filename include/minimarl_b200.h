@@ -656,13 +656,14 @@ int mm_colsum(const float* x, float* out, int64_t rows, int32_t C, void* stream)
  * launches.  params / grads / exp_avg / exp_avg_sq [n] (device); step: device float, advanced by one inside the call (Adam's
  * bias-correction exponent); scratch: mm_clip_adam_scratch_doubles() doubles; norm_out (optional): the total gradient 2-norm
  * before clipping (what clip_grad_norm_ returns).  max_norm <= 0: no clipping.  clip_n <= n: the norm is taken over, and the
- * coefficient applied to, the first clip_n elements only (qmix/_train.py:113-115 clips the q-network but steps the mixer too).  Update rule and operation order of
+ * coefficient applied to, the first clip_n elements only (qmix/_train.py:113-115 clips the q-network but steps the mixer too).
+ * lr_dev (optional, device float) overrides lr: a captured CUDA graph then follows a learning-rate schedule.  Update rule and operation order of
  * torch.optim.Adam (no amsgrad / maximize): g' = g * min(1, max_norm / (norm + 1e-6)) (+ weight_decay * p),
  * m += (g' - m)(1 - beta1), v = beta2 v + (1 - beta2) g'^2, p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps). */
 int mm_clip_adam_scratch_doubles(void);
 int mm_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step, double* scratch,
-                      float* norm_out, int64_t n, int64_t clip_n, float lr, float beta1, float beta2, float eps,
-                      float weight_decay, float max_norm, void* stream);
+                      float* norm_out, int64_t n, int64_t clip_n, float lr, const float* lr_dev, float beta1, float beta2,
+                      float eps, float weight_decay, float max_norm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -100,7 +100,7 @@ SIGNATURES = {
     "mm_qmixer_bwd_unfold": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int32, _P]),
     "mm_colsum": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P]),
     "mm_clip_adam_scratch_doubles": (C.c_int, []),
-    "mm_clip_adam_step": (C.c_int, [_P] * 7 + [C.c_int64, C.c_int64] + [C.c_float] * 6 + [_P]),
+    "mm_clip_adam_step": (C.c_int, [_P] * 7 + [C.c_int64, C.c_int64, C.c_float, _P] + [C.c_float] * 5 + [_P]),
     "mm_ppo_actor_loss_fwd": (C.c_int, [_P] * 6 + [C.c_int64, C.c_int32, C.c_float, _P, _P, C.c_int64, C.c_int64, _P]),
     "mm_ppo_actor_loss_bwd": (C.c_int, [_P] * 7 + [C.c_int64, C.c_int32, C.c_float, _P, C.c_int64, C.c_int64, _P]),
     "mm_ppo_value_loss_fwd": (C.c_int, [_P] * 5 + [C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_int32, _P, _P, C.c_int64,

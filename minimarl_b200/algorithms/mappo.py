@@ -394,6 +394,9 @@ class R_MAPPO:
         self.value_normalizer = ValueNorm(input_shape=1).to(self.device) if self._use_valuenorm else None
         self._fused_loss = bool(getattr(args, "fused_update", True)) and torch.device(device).type == "cuda"
         self._buckets = {}
+        # one PPO epoch (row map, both networks' fused passes, losses, backward, clip + Adam: ~70 launches) replayed as a CUDA graph
+        self._train_graph = bool(getattr(args, "train_graph", True)) and self._fused_loss
+        self._graph_state = None
 
     def cal_value_loss(self, values, value_preds_batch, return_batch, active_masks_batch):
         if self._fused_loss and values.is_cuda:
@@ -521,6 +524,8 @@ class R_MAPPO:
         std_advantages = torch.sqrt((stats[1] / stats[2] - mean_advantages ** 2).clamp(min=0))
         advantages = ((advantages - mean_advantages) / (std_advantages + 1e-5)).to(torch.float32)
 
+        if self._graphable(buffer, perms):
+            return self._train_graphed(buffer, advantages, update_actor)
         train_info = dict(value_loss=0, policy_loss=0, dist_entropy=0, actor_grad_norm=0, critic_grad_norm=0, ratio=0)
         tables = {}                    # normalised observation tables of this update (built on first use by the fused trunk)
         for epoch in range(self.ppo_epoch):
@@ -544,6 +549,72 @@ class R_MAPPO:
         num_updates = self.ppo_epoch * self.train_batch_size
         for k in train_info.keys():
             train_info[k] /= num_updates
+        train_info["Sampling_Rewards"] = buffer.rewards.sum()
+        return train_info
+
+    # -- the PPO epochs as a replayed CUDA graph -----------------------------------------------------------------------------
+    def _graphable(self, buffer, perms):
+        """The launch-bound epoch loop (2 200 launches per update at the bench size, ~50 ms of host enqueue) is replayed from a
+        graph when everything it touches is static storage: single GPU, the fused chunk path for both networks, FlatAdam, the
+        device permutation, no caller-supplied permutations."""
+        import torch.distributed as dist
+        if not (self._train_graph and perms is None and self._use_recurrent_policy and torch.is_tensor(buffer.obs) and buffer.obs.is_cuda):
+            return False
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return False
+        T, L = buffer.rewards.shape[0], self.data_chunk_length
+        pol = self.policy
+        fits = lambda net, x: hasattr(net, "_chunk_fusable") and net._fusable and net._precision == "tf32" and \
+            trunk_fits(x.shape[-1], net.hidden_size, net._n_out) and getattr(net, "_fused_update", True) and L > 1
+        return (T % L == 0 and torch.backends.cuda.matmul.allow_tf32 and fits(pol.actor, buffer.obs) and fits(pol.critic, buffer.share_obs)
+                and isinstance(pol.actor_optimizer, FlatAdam) and isinstance(pol.critic_optimizer, FlatAdam))
+
+    def _epoch(self, buffer, st, update_actor):
+        gen = buffer.recurrent_generator(st["adv"], self.train_batch_size, self.data_chunk_length, perm=st["perm"], lazy_obs=True,
+                                         tables=st["tables"])
+        for sample in gen:
+            value_loss, critic_grad_norm, policy_loss, dist_entropy, actor_grad_norm, ratio = self.ppo_update(sample, update_actor)
+            st["acc"] += torch.stack([value_loss.detach(), policy_loss.detach(), dist_entropy.detach(), actor_grad_norm.reshape(()),
+                                      critic_grad_norm.reshape(()), ratio.detach().mean()])
+
+    def _train_graphed(self, buffer, advantages, update_actor):
+        from ..nn.ppo_trunk import obs_table
+        T, N, A = buffer.rewards.shape[0:3]
+        dev = buffer.obs.device
+        key = (buffer.obs.data_ptr(), buffer.share_obs.data_ptr(), tuple(buffer.obs.shape), tuple(buffer.share_obs.shape),
+               bool(update_actor), self.ppo_epoch, self.train_batch_size, self.data_chunk_length)
+        st = self._graph_state
+        fresh = st is None or st["key"] != key
+        if fresh:
+            st = self._graph_state = dict(key=key, adv=torch.empty_like(advantages), tables={}, graph=None,
+                                          perm=torch.empty(N * T * A // self.data_chunk_length, dtype=torch.int64, device=dev),
+                                          acc=torch.zeros(6, dtype=torch.float32, device=dev))
+        st["adv"].copy_(advantages)
+        st["acc"].zero_()
+        masks = buffer.masks.reshape(-1)
+        for k, src in (("obs", buffer.obs), ("share_obs", buffer.share_obs)):       # this update's normalised fp16 tables, in place
+            if k in st["tables"]:
+                obs_table(src.reshape(-1, src.shape[-1]), masks, out=st["tables"][k])
+        for opt in (self.policy.actor_optimizer, self.policy.critic_optimizer):
+            opt.sync_lr()
+        for epoch in range(self.ppo_epoch):
+            st["perm"].copy_(torch.randperm(st["perm"].numel(), device=dev))
+            if st["graph"] is not None:
+                st["graph"].replay()
+                continue
+            # first epoch with this buffer: a real epoch on a side stream (builds the tables, warms the allocator), then the capture
+            main, side = torch.cuda.current_stream(dev), torch.cuda.Stream(device=dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._epoch(buffer, st, update_actor)
+            main.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._epoch(buffer, st, update_actor)
+            st["graph"] = graph
+        vals = st["acc"] / (self.ppo_epoch * self.train_batch_size)
+        train_info = dict(zip(("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio"), vals.unbind(0)))
         train_info["Sampling_Rewards"] = buffer.rewards.sum()
         return train_info
 

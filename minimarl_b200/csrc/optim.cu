@@ -39,6 +39,7 @@ struct AdamArgs {
     float* v;
     const float* step;
     const double* partial;
+    const float* lr_dev;
     float* norm_out;
     long long n, clip_n;
     int n_partial;
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(kThreads) clip_adam_kernel(AdamArgs a) {
     const float t = *a.step;
     const float bc1 = 1.f - powf(a.beta1, t);
     const float bc2_sqrt = sqrtf(1.f - powf(a.beta2, t));
-    const float step_size = a.lr / bc1;
+    const float step_size = (a.lr_dev ? *a.lr_dev : a.lr) / bc1;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.n; i += (long long)gridDim.x * kThreads) {
         float p = a.p[i];
         float g = a.g[i];
@@ -84,15 +85,15 @@ __global__ void __launch_bounds__(kThreads) clip_adam_kernel(AdamArgs a) {
 extern "C" int mm_clip_adam_scratch_doubles(void) { return kMaxCtas; }
 
 extern "C" int mm_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step,
-                                 double* scratch, float* norm_out, int64_t n, int64_t clip_n, float lr, float beta1, float beta2,
-                                 float eps, float weight_decay, float max_norm, void* stream) {
+                                 double* scratch, float* norm_out, int64_t n, int64_t clip_n, float lr, const float* lr_dev,
+                                 float beta1, float beta2, float eps, float weight_decay, float max_norm, void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !step || !scratch || n <= 0 || clip_n < 0 || clip_n > n)
         return MM_ERR_BAD_ARG;
     auto st = static_cast<cudaStream_t>(stream);
     long long ctas = (n + kThreads * 4 - 1) / (kThreads * 4);
     if (ctas > kMaxCtas) ctas = kMaxCtas;
     gradnorm_partial_kernel<<<(unsigned)ctas, kThreads, 0, st>>>(grads, clip_n, scratch, step);
-    AdamArgs a{params, grads, exp_avg, exp_avg_sq, step, scratch, norm_out, n, clip_n, (int)ctas,
+    AdamArgs a{params, grads, exp_avg, exp_avg_sq, step, scratch, lr_dev, norm_out, n, clip_n, (int)ctas,
                lr, beta1, beta2, eps, weight_decay, max_norm};
     clip_adam_kernel<<<(unsigned)ctas, kThreads, 0, st>>>(a);
     return mm::check_launch();

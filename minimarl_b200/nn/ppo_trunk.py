@@ -144,7 +144,7 @@ def dims2():
     return _DIMS2
 
 
-def obs_table(obs2d, masks=None):
+def obs_table(obs2d, masks=None, out=None):
     """LayerNorm (no affine) of every observation row, fp16, zero padded to 48 columns: [rows, D] -> [rows, 48].  Computed once
     per update; both networks and every epoch gather their chunk rows from it (mm_ppo_obs_table).  With D < 48 the row's mask
     rides in column 47 (``masks`` [rows]): the kernels then read it from the sector their gather fetches anyway."""
@@ -152,7 +152,9 @@ def obs_table(obs2d, masks=None):
     rows, D = obs2d.shape
     if masks is not None and D >= K1:
         masks = None
-    out = torch.empty((rows, K1), dtype=torch.float16, device=obs2d.device)
+    if out is None:
+        out = torch.empty((rows, K1), dtype=torch.float16, device=obs2d.device)
+    assert out.shape == (rows, K1) and out.dtype == torch.float16 and out.is_contiguous()
     _lib.check(_lib.lib().mm_ppo_obs_table(_lib.ptr(obs2d), _lib.ptr(masks), _lib.ptr(out), rows, D, _lib.stream()))
     return out
 

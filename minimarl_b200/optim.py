@@ -35,6 +35,7 @@ class FlatAdam(torch.optim.Optimizer):
         self._step = torch.zeros((), dtype=torch.float32, device=dev)
         self._scratch = torch.zeros(lib().mm_clip_adam_scratch_doubles(), dtype=torch.float64, device=dev)
         self._norm = torch.zeros((), dtype=torch.float32, device=dev)
+        self._lr, self._lr_host = torch.full((), float(lr), dtype=torch.float32, device=dev), float(lr)
         with torch.no_grad():
             for p, off in zip(ps, self.bucket.offsets):
                 view = self.flat_params[off:off + p.numel()].view_as(p)
@@ -54,6 +55,14 @@ class FlatAdam(torch.optim.Optimizer):
         else:
             self.bucket.zero()
 
+    def sync_lr(self):
+        """The kernel reads the learning rate from a device scalar (so that a captured graph follows ``lr_decay``): refreshed
+        here when ``param_groups[0]["lr"]`` changed.  Call it before replaying a graph that contains ``clip_and_step``."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_host:
+            self._lr.fill_(lr)
+            self._lr_host = lr
+
     @torch.no_grad()
     def clip_and_step(self, max_norm=0.0, clip_params=None):
         """``clip_grad_norm_(clip_params or all, max_norm)`` (``max_norm`` <= 0 / None: no clipping) + ``Adam.step()``.
@@ -72,9 +81,10 @@ class FlatAdam(torch.optim.Optimizer):
             raise RuntimeError("FlatAdam: a parameter's storage was replaced (p.data = ...); copy into it in place instead")
         g = self.param_groups[0]
         b1, b2 = g["betas"]
+        self.sync_lr()
         check(lib().mm_clip_adam_step(ptr(self.flat_params), ptr(self.bucket.flat), ptr(self.exp_avg), ptr(self.exp_avg_sq),
                                       ptr(self._step), ptr(self._scratch), ptr(self._norm), self.bucket.n_grad, clip_n, float(g["lr"]),
-                                      float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
+                                      ptr(self._lr), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
                                       float(max_norm) if max_norm else 0.0, stream()))
         return self._norm
 

@@ -167,3 +167,49 @@ def test_lockstep_mappo_rollout_and_update(cuda):
     assert all(torch.isfinite(torch.as_tensor(v)).all() for v in info.values())
     assert (buf.masks[1:] == 0).any()            # some episodes ended (max_steps = 12) and were auto-reset
     buf.after_update()
+
+
+def test_graphed_ppo_epochs_equal_the_eager_loop(cuda):
+    """R_MAPPO.train with the epoch replayed as a CUDA graph (the default on one GPU) against the same loop issued launch by
+    launch (train_graph=False): same device permutations, same kernels, so parameters, ValueNorm state and the reported
+    statistics agree after two updates (the second one is all replays) up to the summation order of the dynamically scheduled
+    weight-gradient tiles (2e-5 on parameters that moved by ~3e-3, 1e-3 relative on the statistics) -- including a
+    learning-rate change between them, which the graph follows through FlatAdam's device-side lr."""
+    from minimarl_b200.algorithms import R_MAPPO, R_MAPPOPolicy
+    from minimarl_b200.buffers import SharedReplayBuffer
+    g = _g()
+    N, T = 64, 16
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        results = []
+        for graph in (False, True):
+            args = _args(g, "tf32", max_step=T, batch_size=N, ppo_epoch=3, train_batch_size=1, data_chunk_length=8, train_graph=graph)
+            space = Box(np.zeros(47), np.ones(47))
+            torch.manual_seed(11)
+            policy = R_MAPPOPolicy(args, space, space, Discrete(5), device=cuda)
+            trainer = R_MAPPO(args, policy, device=cuda)
+            buf = SharedReplayBuffer(args, 2, space, space, Discrete(5), device=cuda)
+            infos = []
+            for it in range(2):
+                gen = torch.Generator(device=cuda).manual_seed(100 + it)
+                r = lambda x: torch.rand(x.shape, device=cuda, generator=gen)
+                buf.obs.copy_(r(buf.obs)); buf.share_obs.copy_(buf.obs)
+                buf.rnn_states.copy_(r(buf.rnn_states) - 0.5); buf.rnn_states_critic.copy_(r(buf.rnn_states_critic) - 0.5)
+                buf.actions.copy_((r(buf.actions) * 5).floor().clamp(max=4)); buf.action_log_probs.copy_(-1.6 + 0.1 * r(buf.action_log_probs))
+                buf.value_preds.copy_(r(buf.value_preds)); buf.rewards.copy_(r(buf.rewards) - 0.3)
+                buf.masks.copy_((r(buf.masks) > 0.1).float()); buf.active_masks.fill_(1.0)
+                buf.compute_returns(buf.value_preds[-1].clone(), trainer.value_normalizer)
+                policy.lr_decay(it, 4)
+                trainer.prep_training()
+                info = trainer.train(buf)
+                infos.append({k: float(v) for k, v in info.items()})
+            assert (trainer._graph_state is not None) == graph
+            params = [p.detach().clone() for p in list(policy.actor.parameters()) + list(policy.critic.parameters())]
+            results.append((infos, params, trainer.value_normalizer.running_mean.detach().clone()))
+        (i0, p0, v0), (i1, p1, v1) = results
+        for a, b in zip(i0, i1):
+            assert all(abs(a[k] - b[k]) <= 1e-3 * max(abs(a[k]), 1e-3) for k in a), (a, b)
+        assert all((a - b).abs().max().item() < 2e-5 for a, b in zip(p0, p1)) and torch.allclose(v0, v1, rtol=1e-5)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
