@@ -314,6 +314,7 @@ def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
         gae_lambda=0.95, max_step=T, batch_size=n_envs, fused_precision="tf32", max_episodes=1000, use_eval=False,
         eval_interval=10, use_linear_lr_decay=False, seed=1)
     env = BatchedCheckers(n_envs, max_steps=100, auto_reset=True, device=dev)
+    torch.manual_seed(args.seed)                            # every rank starts from the same parameters (mappo/main.py seeds likewise)
     r = MappoRunner({"args": args, "train_env": env, "eval_env": env, "num_agents": AGENTS, "device": dev})
     r.warmup()
     r.run_episode(0)                                        # warm-up iteration (allocations, cuBLAS heuristics)
@@ -360,6 +361,8 @@ def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
                        "useful_flop_per_update": flops, "hbm_GBs": hbm_bytes / (ms[2] * 1e-3) / 1e9,
                        "hbm_frac": hbm_bytes / (ms[2] * 1e-3) / 1e9 / measured_peaks()[0],
                        "what_bounds": "instruction issue of the per-row epilogues (ncu: issue slots 46 % / 35 % busy, tensor pipe 6 % / 12 %)"}
+    out["ranks_in_sync"] = _ranks_in_sync(list(r.policy.actor.parameters()) + list(r.policy.critic.parameters()))
+    out["launch_mode"] = "PPO epoch replayed as a CUDA graph" if r.trainer._graph_state is not None else "eager launches"
     del r, env
     torch.cuda.empty_cache()
     return out
@@ -477,6 +480,7 @@ def learner_section(dev, steps):
     buf.update_priorities(torch.arange(S, device=dev), torch.rand(S, device=dev, generator=g) * 0.99 + 0.01, "policy_0")
     pconf = {"cent_obs_dim": A * D, "cent_act_dim": A * NA, "obs_space": info["policy_0"]["obs_space"],
              "share_obs_space": info["policy_0"]["share_obs_space"], "act_space": info["policy_0"]["act_space"]}
+    torch.manual_seed(args.seed)                            # every rank starts from the same parameters
     policy = QMixPolicy(args, {"args": args, "device": dev, "num_agents": A}, pconf)
     trainer = QMix(args, A, B, {"policy_0": policy}, lambda a: "policy_0", device=dev, episode_length=T)
 
@@ -515,9 +519,9 @@ def learner_section(dev, steps):
         qs = torch.randn((T, B, A), device=dev)
         ms_mixer, _ = timed(lambda: trainer.target_mixer(qs, sample[1]["policy_0"][:-1]), 5)
     graphed = None
-    if world == 1:
-        # the same update as ONE CUDA graph (algorithms.qmix.GraphedUpdate): ~230 launches take the host ~7 ms to issue, the
-        # device needs ~6; the multi-GPU leg keeps the eager loop (its NCCL all-reduce is not captured)
+    if True:
+        # the same update as ONE CUDA graph (algorithms.qmix.GraphedUpdate): ~170 launches take the host ~6 ms to issue, the
+        # device needs < 5; with several GPUs the NCCL gradient all-reduce is captured with the rest (one graph per rank)
         from minimarl_b200.algorithms.qmix import GraphedUpdate
         graphed = GraphedUpdate(trainer, buf, B)
         eager_update, update = update, (lambda: graphed(0.4))
@@ -541,6 +545,7 @@ def learner_section(dev, steps):
                                 "the head and the recurrent weight gradients)"},
         "ms_per_update": ms_update, "ms_per_update_eager_launches": ms_eager,
         "launch_mode": "one CUDA graph per update (GraphedUpdate)" if graphed is not None else "eager launches",
+        "ranks_in_sync": _ranks_in_sync(trainer.parameters),
         "loss": float(info_["loss"]),
         "sample_gather": {"ms": ms_sample, "algorithmic_GBps": gather_bytes / (ms_sample * 1e-3) / 1e9,
                           "frac_of_measured_hbm": gather_bytes / (ms_sample * 1e-3) / 1e9 / peak,
@@ -557,6 +562,20 @@ def learner_section(dev, steps):
         "mixer_forward": {"ms": ms_mixer, "rows": T * B, "TFLOPs": T * B * 54528 / (ms_mixer * 1e-3) / 1e12},
         "roofline": _learner_roofline(ms_update, rows, T * B, ms_gather, gather_bytes, peak),
     }
+
+
+def _ranks_in_sync(params):
+    """Multi-GPU: the learners start from the same seed and average their gradients, so the parameters must stay bit-identical
+    on every rank (also through the captured NCCL all-reduce of the graph replays).  None on one GPU."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return None
+    flat = torch.cat([p.detach().reshape(-1).double() for p in params])
+    mine = torch.stack([flat.sum(), flat.abs().sum(), (flat * flat).sum()])
+    every = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(every, mine)
+    return bool(all(torch.equal(e, every[0]) for e in every) and torch.isfinite(mine).all())
 
 
 def _learner_roofline(ms_update, agent_rows, mixer_rows, ms_gather, gather_bytes, hbm_peak):

@@ -76,7 +76,7 @@ class ValueNorm(nn.Module):
         if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
             # sharded batch: global moments = all-reduced sums / all-reduced count
             packed = torch.cat([batch_mean.reshape(-1) * n, batch_sq_mean.reshape(-1) * n,
-                                torch.tensor([n], device=batch_mean.device)]).double()
+                                torch.full((1,), n, device=batch_mean.device)]).double()      # (no host tensor: graph-capturable)
             packed = allreduce_stats(packed)
             k = batch_mean.numel()
             batch_mean = (packed[:k] / packed[-1]).to(batch_mean.dtype).reshape(batch_mean.shape)
@@ -555,12 +555,10 @@ class R_MAPPO:
     # -- the PPO epochs as a replayed CUDA graph -----------------------------------------------------------------------------
     def _graphable(self, buffer, perms):
         """The launch-bound epoch loop (2 200 launches per update at the bench size, ~50 ms of host enqueue) is replayed from a
-        graph when everything it touches is static storage: single GPU, the fused chunk path for both networks, FlatAdam, the
-        device permutation, no caller-supplied permutations."""
-        import torch.distributed as dist
+        graph when everything it touches is static storage: the fused chunk path for both networks, FlatAdam, the device
+        permutation, no caller-supplied permutations.  With several GPUs the gradient / ValueNorm all-reduces (NCCL) are captured
+        with the rest: every rank replays its own graph in lockstep."""
         if not (self._train_graph and perms is None and self._use_recurrent_policy and torch.is_tensor(buffer.obs) and buffer.obs.is_cuda):
-            return False
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             return False
         T, L = buffer.rewards.shape[0], self.data_chunk_length
         pol = self.policy
@@ -610,7 +608,7 @@ class R_MAPPO:
             main.wait_stream(side)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):      # NCCL's watchdog thread may query events meanwhile
                 self._epoch(buffer, st, update_actor)
             st["graph"] = graph
         vals = st["acc"] / (self.ppo_epoch * self.train_batch_size)

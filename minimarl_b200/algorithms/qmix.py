@@ -323,7 +323,9 @@ class GraphedUpdate:
             self.trainer.optimizer.zero_grad(set_to_none=True)
             torch.cuda.synchronize()
             self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
+            # thread_local: with several GPUs NCCL's watchdog thread queries events while this thread captures (the gradient
+            # all-reduce is captured with the rest: one graph per rank, replayed in lockstep)
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
                 self._info = self._step(beta)
             self._key = key
             return info
