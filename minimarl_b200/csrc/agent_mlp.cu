@@ -140,10 +140,30 @@ __device__ __forceinline__ void block_publish() {
     tc::fence_after_sync();
 }
 
+// Thread = row makes every per-thread global access of a warp touch 32 different 128-byte lines (16 bytes of each): the L1 / LSU
+// transaction rate, not HBM, then bounds the kernel (ncu: lg_throttle, long_scoreboard).  Rows therefore travel through a
+// warp-private staging slab [32 rows][32 floats] (row stride 36 floats: conflict-free for 16-byte accesses both ways): the
+// global side of a slab is 8 instructions of 4 rows x 128 contiguous bytes each.
+constexpr int SLAB_STRIDE = 36, SLAB_FLOATS = 32 * SLAB_STRIDE;
+// v: 32 consecutive columns of this lane's row  ->  global rows gdst + r * row_stride (r < n_rows), 32 floats each
+__device__ __forceinline__ void slab_store(float* slab, const float* v, float* gdst, long long row_stride, int n_rows, int lane) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(slab + lane * SLAB_STRIDE + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int rr = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + rr;
+        if (r < n_rows) mm::st_stream(reinterpret_cast<float4*>(gdst + r * row_stride + c4), *reinterpret_cast<const float4*>(slab + r * SLAB_STRIDE + c4));
+    }
+    __syncwarp();
+}
 // ======================================================= forward ==========================================================
 // shared memory: W1 | W2 | Wih | biases | X0 tile (6 chunks) | XH1 tile (8) | XH2 tile (8)
 constexpr int F_W1 = 0, F_W2 = F_W1 + H * K1 * 2, F_WIH = F_W2 + H * H * 2, F_BIAS = F_WIH + G3 * H * 2,
-              F_X0 = F_BIAS + (2 * H + G3) * 4, F_XH1 = F_X0 + 6 * CH, F_XH2 = F_XH1 + 8 * CH, F_BYTES = F_XH2 + 8 * CH;
+              F_X0 = F_BIAS + (2 * H + G3) * 4, F_XH1 = F_X0 + 6 * CH, F_XH2 = F_XH1 + 8 * CH, F_SLAB = F_XH2 + 8 * CH,
+              F_BYTES = F_SLAB + 4 * SLAB_FLOATS * 4;
 
 __global__ void __launch_bounds__(128, 2) agent_mlp_fwd_kernel(const __grid_constant__ Args a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -154,6 +174,8 @@ __global__ void __launch_bounds__(128, 2) agent_mlp_fwd_kernel(const __grid_cons
     uint8_t* sX0 = smem + F_X0;
     uint8_t* sXH1 = smem + F_XH1;
     uint8_t* sXH2 = smem + F_XH2;
+    float* slab = reinterpret_cast<float*>(smem + F_SLAB) + warp * SLAB_FLOATS;
+    const int lane = tid & 31;
 
     stage_weight(smem + F_W1, a.params + P_W1, H, K1, tid, 128);
     stage_weight(smem + F_W2, a.params + P_W2, H, H, tid, 128);
@@ -178,6 +200,8 @@ __global__ void __launch_bounds__(128, 2) agent_mlp_fwd_kernel(const __grid_cons
         const long long row0 = tile * kRows;
         const bool valid = row0 + row < a.rows;
         const long long grow = valid ? row0 + row : a.rows - 1;          // rows past the end shadow the last row
+        const long long wrow0 = row0 + 32 * warp;                         // first row of this warp's slab
+        const int wn = (int)max(0LL, min(32LL, a.rows - wrow0));          // valid rows in it
         // ---- LayerNorm(D) of the observation row (no affine) -> X0 tile ----------------------------------------------------
         {
             float x[K1];
@@ -216,10 +240,10 @@ __global__ void __launch_bounds__(128, 2) agent_mlp_fwd_kernel(const __grid_cons
             rstd1 = bias_relu_norm(v, sB, relu1);
 #pragma unroll
             for (int c = 0; c < H / 8; ++c) store_chunk(sXH1, c, row, v + 8 * c);
-            if (srow && valid) {
-#pragma unroll
-                for (int j = 0; j < H / 4; ++j)
-                    mm::st_stream(reinterpret_cast<float4*>(srow) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            if (a.saved_rows) {
+                float* g0 = a.saved_rows + wrow0 * SV_ROW_FLOATS;
+                slab_store(slab, v, g0, SV_ROW_FLOATS, wn, lane);
+                slab_store(slab, v + 32, g0 + 32, SV_ROW_FLOATS, wn, lane);
             }
         }
         block_publish();
@@ -238,10 +262,12 @@ __global__ void __launch_bounds__(128, 2) agent_mlp_fwd_kernel(const __grid_cons
             rstd2 = bias_relu_norm(v, sB + H, relu2);
 #pragma unroll
             for (int c = 0; c < H / 8; ++c) store_chunk(sXH2, c, row, v + 8 * c);
+            if (a.saved_rows) {
+                float* g0 = a.saved_rows + wrow0 * SV_ROW_FLOATS + H;
+                slab_store(slab, v, g0, SV_ROW_FLOATS, wn, lane);
+                slab_store(slab, v + 32, g0 + 32, SV_ROW_FLOATS, wn, lane);
+            }
             if (srow && valid) {
-#pragma unroll
-                for (int j = 0; j < H / 4; ++j)
-                    mm::st_stream(reinterpret_cast<float4*>(srow + H) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                 mm::st_stream(reinterpret_cast<float4*>(srow + 2 * H),
                               make_float4(rstd1, rstd2, __uint_as_float(relu1[0]), __uint_as_float(relu1[1])));
                 mm::st_stream(reinterpret_cast<float4*>(srow + 2 * H) + 1,
@@ -258,21 +284,19 @@ __global__ void __launch_bounds__(128, 2) agent_mlp_fwd_kernel(const __grid_cons
         wait_mma();
         // ---- input projection of the GRU: + bias, rows out --------------------------------------------------------------------
         {
-            float* out = a.gi + grow * G3;
+            float* out = a.gi + wrow0 * G3;
 #pragma unroll 1
             for (int c = 0; c < G3 / 32; ++c) {
                 float v[32];
                 tc::tmem_ld32_issue(tl + 32 * c, v);
                 tc::tmem_ld_fence<32>(v);
                 const float4* b4 = reinterpret_cast<const float4*>(sB + 2 * H + 32 * c);
-                if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b = b4[j];
-                        mm::st_stream(reinterpret_cast<float4*>(out + 32 * c) + j,
-                                      make_float4(v[4 * j] + b.x, v[4 * j + 1] + b.y, v[4 * j + 2] + b.z, v[4 * j + 3] + b.w));
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const float4 b = b4[j];
+                    v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                 }
+                slab_store(slab, v, out + 32 * c, G3, wn, lane);
             }
         }
         tc::fence_before_sync();                                         // orders this tile's TMEM reads before the next tile's MMAs
@@ -351,17 +375,26 @@ __global__ void __launch_bounds__(128, 1) agent_mlp_bwd_kernel(const __grid_cons
         {
             const float4* src = reinterpret_cast<const float4*>(a.dgi + row0 * G3);
             const int n_pieces = n_valid * (G3 / 4);
-#pragma unroll 4
-            for (int i = 0; i < kRows * (G3 / 4) / 128; ++i) {
-                const int idx = i * 128 + tid, r = idx / (G3 / 4), p = idx - r * (G3 / 4);      // row r, features 4p .. 4p + 3
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (idx < n_pieces) v = src[idx];
-                *reinterpret_cast<uint2*>(sG + (p >> 1) * CHP + r * 16 + (p & 1) * 8) =
-                    make_uint2(pack2(v.x * gscale, v.y * gscale), pack2(v.z * gscale, v.w * gscale));
+#pragma unroll 1
+            for (int i0 = 0; i0 < kRows * (G3 / 4) / 128; i0 += 16) {          // 16 loads in flight per thread, then their 16 stores
+                float4 v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int idx = (i0 + u) * 128 + tid;
+                    v[u] = idx < n_pieces ? __ldcs(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int idx = (i0 + u) * 128 + tid, r = idx / (G3 / 4), p = idx - r * (G3 / 4);   // row r, features 4p .. 4p + 3
+                    *reinterpret_cast<uint2*>(sG + (p >> 1) * CHP + r * 16 + (p & 1) * 8) =
+                        make_uint2(pack2(v[u].x * gscale, v[u].y * gscale), pack2(v[u].z * gscale, v[u].w * gscale));
+                }
             }
         }
         // ---- this thread's saved rows: xh2 -> operand tile (and kept for the LayerNorm backward) ----------------------------
         const float* srow = a.saved_rows + grow * SV_ROW_FLOATS;
+        // (per-thread row reads: 34 independent 16-byte loads in flight; staging them through shared memory like the forward's
+        // stores serialises four load -> store -> read round trips and was measured slower, 0.49 vs 0.41 ms)
         float xh[H];
 #pragma unroll
         for (int j = 0; j < H / 4; ++j) {
