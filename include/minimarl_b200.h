@@ -474,6 +474,12 @@ int mm_gru_seq_fwd(const float* gi, const float* h0, const float* w_hh, const fl
 int mm_gru_seq_bwd(const float* dh_seq, const float* r, const float* z, const float* n, const float* ghn,
                    const float* h_seq, const float* h0, const float* w_hh, float* dgi, float* dghn, float* dh0,
                    int32_t T, int64_t R, int32_t H, void* stream);
+/* The same with the fp16 consumers' gradient scale as a by-product: scale2 (device float[2]) receives max |dgi| in [1] and the
+ * power of two mm_ppo_trunk2_scale(dgi) would compute in [0] -- the backward tracks the maximum while it writes dgi, so
+ * mm_agent_mlp_bwd / mm_gru_wgrad need no pass of their own over the 3H-wide gradient. */
+int mm_gru_seq_bwd_scaled(const float* dh_seq, const float* r, const float* z, const float* n, const float* ghn,
+                          const float* h_seq, const float* h0, const float* w_hh, float* dgi, float* dghn, float* dh0,
+                          float* scale2, int32_t T, int64_t R, int32_t H, void* stream);
 
 /* The mixing step of QMixer.forward after the hypernetworks (q_mixer.py:80-93), forward and backward, for the
  * differentiated pass:  out[m] = elu(q[m,:] @ w1[m,:,:] + b1[m,:]) . w2[m,:] + b2[m]
@@ -664,6 +670,25 @@ int mm_clip_adam_scratch_doubles(void);
 int mm_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step, double* scratch,
                       float* norm_out, int64_t n, int64_t clip_n, float lr, const float* lr_dev, float beta1, float beta2,
                       float eps, float weight_decay, float max_norm, void* stream);
+
+/* LayerNorm(H) + the Q head Linear(H, NA) of the recurrent agent network on the GRU outputs, one kernel per direction
+ * (csrc/ln_head.cu; rnn.py:18,45 and act.py as agent_q_function.py:60-66 applies them, differentiated by qmix.py:196).
+ * H in {32, 64}, NA <= 8.  h [M, H], q [M, NA]; mean / rstd [M] are written by the forward and read by the backward.
+ * Backward: dh [M, H]; dwq [NA, H], dbq [NA], dln_w [H], dln_b [H] are ACCUMULATED into (the caller zeroes them). */
+int mm_ln_head_fwd(const float* h, const float* ln_w, const float* ln_b, const float* wq, const float* bq, float* q, float* mean,
+                   float* rstd, int64_t M, int32_t H, int32_t NA, void* stream);
+int mm_ln_head_bwd(const float* dq, const float* h, const float* mean, const float* rstd, const float* ln_w, const float* ln_b,
+                   const float* wq, float* dh, float* dwq, float* dbq, float* dln_w, float* dln_b, int64_t M, int32_t H,
+                   int32_t NA, void* stream);
+
+/* Recurrent weight gradients of the GRU on tcgen05 (csrc/gru_wgrad.cu): dw_hh [3H, H] = [dgi_r | dgi_z | dgh_n]^T h_prev and
+ * db_hh [3H] = the column sums, contracted over all T * R rows -- the weight_hh_l0 / bias_hh_l0 gradients of nn.GRU in RNNLayer
+ * (rnn.py:4-47) under qmix.py:196's backward.  dgi [T R, 3H] and dghn [T R, H] from mm_gru_seq_bwd, h_seq [T R, H] from
+ * mm_gru_seq_fwd (h_prev of step t is h_seq[t - 1], of step 0 h0 or zero), scale = mm_ppo_trunk2_scale(dgi) (device), acc: scratch
+ * of n_acc_ctas >= mm_gru_wgrad_ctas(T R) x 128 x 3H floats.  H = 64. */
+int mm_gru_wgrad_ctas(int64_t rows);
+int mm_gru_wgrad(const float* dgi, const float* dghn, const float* h_seq, const float* h0, const float* scale, float* acc,
+                 int32_t n_acc_ctas, float* dw_hh, float* db_hh, int32_t T, int64_t R, int32_t H, void* stream);
 
 #ifdef __cplusplus
 }

@@ -226,6 +226,7 @@ struct GruBwdArgs {
     float *dgi, *dghn, *dh0;                                    // [T,R,3H]; [T,R,H]; [R,H]
     int T;
     long long R;
+    float* scale2;                                              // optional: scale2[1] <- max |dgi| as float bits (atomicMax)
 };
 
 // ---- 64-row backward with coalesced tile loads --------------------------------------------------------------------------
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_bwd_tile_kernel(const GruBwdA
     float dh_rec[CPH];
 #pragma unroll
     for (int j = 0; j < CPH; ++j) dh_rec[j] = 0.f;
+    float amax = 0.f;                                           // max |dgi| seen by this thread (for the fp16 consumers' scale)
 
     for (int t = a.T - 1; t >= 0; --t) {
         float dh[CPH], rr[CPH], zz[CPH], nn[CPH], gn[CPH], hp[CPH];
@@ -317,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_bwd_tile_kernel(const GruBwdA
             d_r[j] = an * gn[j] * rr[j] * (1.0f - rr[j]);
             d_z[j] = g * (hp[j] - nn[j]) * zz[j] * (1.0f - zz[j]);
             dh_rec[j] = g * zz[j];                                   // direct path; the W_hh path is added after the MMA
+            amax = fmaxf(amax, fmaxf(fabsf(d_n[j]), fmaxf(fabsf(d_r[j]), fabsf(d_z[j]))));
         }
         const long long o = ((long long)t * a.R + row0 + row) * H + cc;
         float* dgi = a.dgi + ((long long)t * a.R + row0 + row) * K3 + cc;
@@ -357,9 +360,23 @@ __global__ void __launch_bounds__(kThreads, 1) gru_bwd_tile_kernel(const GruBwdA
         tc::fence_before_sync();          // the next step's MMA overwrites this accumulator: order the loads before it
     }
     if (a.dh0 != nullptr) st_row<CPH>(a.dh0 + (row0 + row) * H + cc, dh_rec, valid);
+    if (a.scale2 != nullptr) {
+        unsigned int m = valid ? __float_as_uint(amax) : 0u;        // non-negative floats order like their bit patterns
+#pragma unroll
+        for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(MM_FULL_MASK, m, o));
+        if (lane == 0 && m) atomicMax(reinterpret_cast<unsigned int*>(a.scale2) + 1, m);
+    }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, kCols);
+}
+
+// scale2[0] = the power of two that puts max |dgi| (scale2[1]) at 64..128: what mm_ppo_trunk2_scale computes in a pass of its own
+__global__ void gru_scale_finish_kernel(float* __restrict__ scale2) {
+    const float amax = scale2[1];
+    int e = (amax > 0.f && amax < 3.0e38f) ? ilogbf(64.0f / fmaxf(amax, 1e-30f)) : 0;     // non-finite gradients stay non-finite
+    e = e < -60 ? -60 : e > 60 ? 60 : e;
+    scale2[0] = ldexpf(1.0f, e);
 }
 
 template <int H>
@@ -394,15 +411,29 @@ extern "C" int mm_gru_seq_fwd(const float* gi, const float* h0, const float* w_h
     return H == 64 ? launch_fwd_tile<64>(a, st) : launch_fwd_tile<32>(a, st);
 }
 
-extern "C" int mm_gru_seq_bwd(const float* dh_seq, const float* r, const float* z, const float* n, const float* ghn,
-                              const float* h_seq, const float* h0, const float* w_hh, float* dgi, float* dghn,
-                              float* dh0, int32_t T, int64_t R, int32_t H, void* stream) {
+// scale2 (optional, device float[2]): [1] <- max |dgi|, [0] <- the power-of-two scale mm_ppo_trunk2_scale(dgi) would return
+extern "C" int mm_gru_seq_bwd_scaled(const float* dh_seq, const float* r, const float* z, const float* n, const float* ghn,
+                                     const float* h_seq, const float* h0, const float* w_hh, float* dgi, float* dghn,
+                                     float* dh0, float* scale2, int32_t T, int64_t R, int32_t H, void* stream) {
     if (!dh_seq || !r || !z || !n || !ghn || !h_seq || !w_hh || !dgi || !dghn || T <= 0 || R <= 0) return MM_ERR_BAD_ARG;
     if (H != 32 && H != 64) return MM_ERR_UNSUPPORTED;
     if (!aligned16(dh_seq) || !aligned16(r) || !aligned16(z) || !aligned16(n) || !aligned16(ghn) || !aligned16(h_seq) ||
         !aligned16(h0) || !aligned16(dgi) || !aligned16(dghn) || !aligned16(dh0))
         return MM_ERR_BAD_ARG;
-    GruBwdArgs a{dh_seq, r, z, n, ghn, h_seq, h0, w_hh, dgi, dghn, dh0, T, R};
+    GruBwdArgs a{dh_seq, r, z, n, ghn, h_seq, h0, w_hh, dgi, dghn, dh0, T, R, scale2};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return H == 64 ? launch_bwd_tile<64>(a, st) : launch_bwd_tile<32>(a, st);
+    if (scale2) {
+        cudaError_t e = cudaMemsetAsync(scale2, 0, 8, st);
+        if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
+    }
+    const int rc = H == 64 ? launch_bwd_tile<64>(a, st) : launch_bwd_tile<32>(a, st);
+    if (rc != MM_OK || !scale2) return rc;
+    gru_scale_finish_kernel<<<1, 1, 0, st>>>(scale2);
+    return mm::check_launch();
+}
+
+extern "C" int mm_gru_seq_bwd(const float* dh_seq, const float* r, const float* z, const float* n, const float* ghn,
+                              const float* h_seq, const float* h0, const float* w_hh, float* dgi, float* dghn,
+                              float* dh0, int32_t T, int64_t R, int32_t H, void* stream) {
+    return mm_gru_seq_bwd_scaled(dh_seq, r, z, n, ghn, h_seq, h0, w_hh, dgi, dghn, dh0, nullptr, T, R, H, stream);
 }

@@ -16,6 +16,7 @@ from ..ops.gram import colsum, gram
 
 H, K1 = 64, 48
 _DIMS = None
+_SCALES = {}          # (data_ptr, numel) of a dgi tensor -> its power-of-two gradient scale, from the GRU backward to agent_mlp's
 
 
 def dims():
@@ -80,8 +81,10 @@ class _AgentMlpFn(torch.autograd.Function):
         d = dims()
         dgi = dgi.contiguous()
         lib = _lib.lib()
-        scale = torch.empty(2, dtype=torch.float32, device=dgi.device)
-        _lib.check(lib.mm_ppo_trunk2_scale(_lib.ptr(dgi), dgi.numel(), _lib.ptr(scale), _lib.stream()))
+        scale = _SCALES.pop((dgi.data_ptr(), dgi.numel()), None)          # left by the GRU backward that produced this dgi
+        if scale is None:
+            scale = torch.empty(2, dtype=torch.float32, device=dgi.device)
+            _lib.check(lib.mm_ppo_trunk2_scale(_lib.ptr(dgi), dgi.numel(), _lib.ptr(scale), _lib.stream()))
         n_ctas = lib.mm_agent_mlp_bwd_ctas(rows)
         acc = torch.empty((n_ctas, d["tile_rows"], d["acc_cols"]), dtype=torch.float32, device=dgi.device)
         _lib.check(lib.mm_agent_mlp_bwd(_lib.ptr(packed), _lib.ptr(saved_rows), _lib.ptr(saved_x0), _lib.ptr(dgi), _lib.ptr(scale),
@@ -129,9 +132,21 @@ class _GruFromGiFn(torch.autograd.Function):
         dgi = torch.empty((T * R, 3 * Hh), **z_)
         dghn = torch.empty((T, R, Hh), **z_)
         dh0 = torch.empty((R, Hh), **z_)
-        _lib.check(_lib.lib().mm_gru_seq_bwd(_lib.ptr(dh_seq.contiguous()), _lib.ptr(r), _lib.ptr(z), _lib.ptr(n), _lib.ptr(ghn),
-                                             _lib.ptr(h_seq), _lib.ptr(h0 if has_h0 else None), _lib.ptr(w_hh.contiguous()),
-                                             _lib.ptr(dgi), _lib.ptr(dghn), _lib.ptr(dh0), T, R, Hh, _lib.stream()))
+        scale = torch.empty(2, **z_)                     # [0]: power-of-two scale of dgi for the fp16 consumers, [1]: max |dgi|
+        _lib.check(_lib.lib().mm_gru_seq_bwd_scaled(_lib.ptr(dh_seq.contiguous()), _lib.ptr(r), _lib.ptr(z), _lib.ptr(n), _lib.ptr(ghn),
+                                                    _lib.ptr(h_seq), _lib.ptr(h0 if has_h0 else None), _lib.ptr(w_hh.contiguous()),
+                                                    _lib.ptr(dgi), _lib.ptr(dghn), _lib.ptr(dh0), _lib.ptr(scale), T, R, Hh,
+                                                    _lib.stream()))
+        _SCALES[(dgi.data_ptr(), dgi.numel())] = scale  # agent_mlp's backward receives this dgi next
+        lib = _lib.lib()
+        if Hh == H:
+            # dW_hh / db_hh on tcgen05 straight from dgi, dgh_n and the (shifted) h_seq: no h_prev copy, no cuBLAS, no column sums
+            n_ctas = lib.mm_gru_wgrad_ctas(T * R)
+            acc = torch.empty((n_ctas, 128, 3 * Hh), **z_)
+            dw_hh, db_hh = torch.empty((3 * Hh, Hh), **z_), torch.empty(3 * Hh, **z_)
+            _lib.check(lib.mm_gru_wgrad(_lib.ptr(dgi), _lib.ptr(dghn), _lib.ptr(h_seq), _lib.ptr(h0 if has_h0 else None), _lib.ptr(scale),
+                                        _lib.ptr(acc), n_ctas, _lib.ptr(dw_hh), _lib.ptr(db_hh), T, R, Hh, _lib.stream()))
+            return dgi, (dh0 if (has_h0 and ctx.needs_input_grad[1]) else None), dw_hh, db_hh, None, None
         h_prev = torch.empty((T, R, Hh), **z_)
         if has_h0:
             h_prev[0].copy_(h0)
@@ -149,3 +164,45 @@ class _GruFromGiFn(torch.autograd.Function):
 def gru_from_gi(gi, h0, w_hh, b_hh, T, R):
     """gi [T * R, 3H] (input projections incl. b_ih) -> h_seq [T, R, H]."""
     return _GruFromGiFn.apply(gi, h0, w_hh, b_hh, T, R)
+
+
+class _LnHeadFn(torch.autograd.Function):
+    """``Linear(H, NA)(LayerNorm(H)(h))`` on the GRU outputs (mm_ln_head_fwd / _bwd): the NA = 5 head is a bandwidth problem, one
+    pass over the rows per direction instead of LayerNorm kernels + three padded cuBLAS GEMMs + a bias column sum."""
+
+    @staticmethod
+    def forward(ctx, h, ln_w, ln_b, wq, bq):
+        M, Hh = h.shape
+        NA = wq.shape[0]
+        h = h.contiguous()
+        ps = [t.detach().contiguous() for t in (ln_w, ln_b, wq, bq)]
+        z = dict(dtype=torch.float32, device=h.device)
+        q, mean, rstd = torch.empty((M, NA), **z), torch.empty(M, **z), torch.empty(M, **z)
+        _lib.check(_lib.lib().mm_ln_head_fwd(_lib.ptr(h), *[_lib.ptr(t) for t in ps], _lib.ptr(q), _lib.ptr(mean), _lib.ptr(rstd),
+                                             M, Hh, NA, _lib.stream()))
+        ctx.save_for_backward(h, mean, rstd, *ps)
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        h, mean, rstd, ln_w, ln_b, wq, bq = ctx.saved_tensors
+        M, Hh = h.shape
+        NA = wq.shape[0]
+        z = dict(dtype=torch.float32, device=h.device)
+        dh = torch.empty_like(h)
+        flat = torch.zeros(NA * Hh + NA + 2 * Hh, **z)                    # dwq | dbq | dln_w | dln_b, accumulated by the kernel
+        dwq, dbq, dg, db = flat[:NA * Hh].view(NA, Hh), flat[NA * Hh:NA * Hh + NA], flat[NA * Hh + NA:NA * Hh + NA + Hh], flat[NA * Hh + NA + Hh:]
+        _lib.check(_lib.lib().mm_ln_head_bwd(_lib.ptr(dq.contiguous()), _lib.ptr(h), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(ln_w),
+                                             _lib.ptr(ln_b), _lib.ptr(wq), _lib.ptr(dh), _lib.ptr(flat), _lib.ptr(flat[NA * Hh:]),
+                                             _lib.ptr(flat[NA * Hh + NA:]), _lib.ptr(flat[NA * Hh + NA + Hh:]), M, Hh, NA, _lib.stream()))
+        return dh, dg, db, dwq, dbq
+
+
+def ln_head_fits(hidden, n_out):
+    return hidden in (32, 64) and 1 <= n_out <= 8 and (hidden * n_out) % 4 == 0
+
+
+def ln_head(h, ln_w, ln_b, wq, bq):
+    """h [..., H] -> Linear(H, NA)(LayerNorm(H)(h)) [..., NA]."""
+    out = _LnHeadFn.apply(h.reshape(-1, h.shape[-1]), ln_w, ln_b, wq, bq)
+    return out.view(*h.shape[:-1], wq.shape[0])

@@ -214,15 +214,19 @@ class RNNBase(MLPBase):
                 and torch.backends.cuda.matmul.allow_tf32 and torch.backends.cudnn.allow_tf32
                 and getattr(self, "fused_mlp", True))
 
+    def hidden_seq(self, x, hxs):
+        """The fused differentiated pass up to the GRU outputs (before ``rnn.norm``): h_seq [T, R, H]."""
+        from .agent_mlp import agent_mlp_gi, gru_from_gi
+        T, R, D = x.shape
+        wb = lambda m: (m.weight, m.bias)
+        g = self.rnn.rnn
+        gi = agent_mlp_gi(x.reshape(T * R, D), wb(self.feature_norm), wb(self.mlp.fc1[0]), wb(self.mlp.fc1[2]),
+                          wb(self.mlp.fc2[0][0]), wb(self.mlp.fc2[0][2]), g.weight_ih_l0, g.bias_ih_l0)
+        return gru_from_gi(gi, hxs[0] if hxs is not None else None, g.weight_hh_l0, g.bias_hh_l0, T, R)
+
     def forward(self, x, hxs):
         if self._fused_mlp_ok(x):
-            from .agent_mlp import agent_mlp_gi, gru_from_gi
-            T, R, D = x.shape
-            wb = lambda m: (m.weight, m.bias)
-            g = self.rnn.rnn
-            gi = agent_mlp_gi(x.reshape(T * R, D), wb(self.feature_norm), wb(self.mlp.fc1[0]), wb(self.mlp.fc1[2]),
-                              wb(self.mlp.fc2[0][0]), wb(self.mlp.fc2[0][2]), g.weight_ih_l0, g.bias_ih_l0)
-            h_seq = gru_from_gi(gi, hxs[0] if hxs is not None else None, g.weight_hh_l0, g.bias_hh_l0, T, R)
+            h_seq = self.hidden_seq(x, hxs)
             return self.rnn.norm(h_seq), h_seq[-1]
         if self._use_feature_normalization:
             x = self.feature_norm(x)
@@ -299,5 +303,11 @@ class AgentQFunction(nn.Module):
             obs = obs[None]
         if rnn_states.dim() == 2:
             rnn_states = rnn_states[None]
+        from .agent_mlp import ln_head, ln_head_fits
+        if not no_sequence and self.rnn._fused_mlp_ok(obs) and ln_head_fits(self.hidden_size, self.act_dim):
+            # fused differentiated pass: row-parallel trunk, recurrence, then LayerNorm + head as one op
+            h_seq = self.rnn.hidden_seq(obs, rnn_states.contiguous())
+            norm, head = self.rnn.rnn.norm, self.q.action_out
+            return ln_head(h_seq, norm.weight, norm.bias, head.weight, head.bias), h_seq[-1]
         rnn_outs, h_final = self.rnn(obs, rnn_states.contiguous())
         return self.q(rnn_outs, no_sequence), h_final

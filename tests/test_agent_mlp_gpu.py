@@ -91,3 +91,27 @@ def test_agent_network_live_pass_uses_the_fused_op_and_matches_eager(cuda):
     for n in ga:
         rel = float((ga[n] - gb[n]).norm() / (gb[n].norm() + 1e-30))
         assert rel < 5e-2, (n, rel)
+
+
+@pytest.mark.parametrize("M,H,NA", [(1, 64, 5), (77, 64, 5), (8 * 1184 * 8 + 13, 64, 5), (333, 32, 5), (100, 64, 8), (50, 64, 3)])
+def test_ln_head_matches_float64(cuda, M, H, NA):
+    """mm_ln_head_fwd / _bwd (LayerNorm + the Q head, fp32 arithmetic) against the same two layers in float64: outputs 2e-6 of
+    their scale, dh and the four parameter gradients 1e-5 relative (fp32 sums over the rows, atomics across CTAs)."""
+    from minimarl_b200.nn.agent_mlp import ln_head
+    torch.manual_seed(M + NA)
+    h = torch.randn(M, H) * 2 + 0.3
+    ps = [1 + 0.2 * torch.randn(H), 0.2 * torch.randn(H), torch.randn(NA, H) / 8, 0.1 * torch.randn(NA)]
+    dq = torch.randn(M, NA) * (torch.rand(M, NA) < 0.3)                     # mostly one action per row carries a gradient
+    hm = h.to(cuda).requires_grad_(True)
+    pm = [p.to(cuda).requires_grad_(True) for p in ps]
+    q = ln_head(hm, *pm)
+    q.backward(dq.to(cuda))
+    hr = h.double().requires_grad_(True)
+    pr = [p.double().requires_grad_(True) for p in ps]
+    qr = torch.nn.functional.linear(torch.nn.functional.layer_norm(hr, (H,), pr[0], pr[1], 1e-5), pr[2], pr[3])
+    qr.backward(dq.double())
+    assert (q.detach().cpu().double() - qr.detach()).abs().max().item() < 2e-6 * max(1.0, qr.detach().abs().max().item())
+    rel = lambda a, b: ((a.detach().cpu().double() - b).norm() / b.norm().clamp(min=1e-30)).item()
+    assert rel(hm.grad, hr.grad) < 1e-5
+    for a, b in zip(pm, pr):
+        assert rel(a.grad, b.grad) < 1e-5, rel(a.grad, b.grad)
