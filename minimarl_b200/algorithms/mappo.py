@@ -595,13 +595,27 @@ class R_MAPPO:
                 obs_table(src.reshape(-1, src.shape[-1]), masks, out=st["tables"][k])
         for opt in (self.policy.actor_optimizer, self.policy.critic_optimizer):
             opt.sync_lr()
+        # the epochs' permutations (same generator calls in the same order as the eager loop) are drawn on a second stream while
+        # the previous epochs replay: the radix sorts behind randperm are ~1.1 ms per update that nothing waits for any more
+        main = torch.cuda.current_stream(dev)
+        if "perm_stream" not in st:
+            st["perm_stream"] = torch.cuda.Stream(device=dev)
+            st["perms"] = torch.empty((self.ppo_epoch, st["perm"].numel()), dtype=torch.int64, device=dev)
+            st["perm_events"] = [torch.cuda.Event() for _ in range(self.ppo_epoch)]
+        ps = st["perm_stream"]
+        ps.wait_stream(main)                              # the previous update's reads of ``perms`` are enqueued on main
+        with torch.cuda.stream(ps):
+            for epoch in range(self.ppo_epoch):
+                st["perms"][epoch].copy_(torch.randperm(st["perm"].numel(), device=dev))
+                st["perm_events"][epoch].record(ps)
         for epoch in range(self.ppo_epoch):
-            st["perm"].copy_(torch.randperm(st["perm"].numel(), device=dev))
+            main.wait_event(st["perm_events"][epoch])
+            st["perm"].copy_(st["perms"][epoch])
             if st["graph"] is not None:
                 st["graph"].replay()
                 continue
             # first epoch with this buffer: a real epoch on a side stream (builds the tables, warms the allocator), then the capture
-            main, side = torch.cuda.current_stream(dev), torch.cuda.Stream(device=dev)
+            side = torch.cuda.Stream(device=dev)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 self._epoch(buffer, st, update_actor)

@@ -560,14 +560,21 @@ __global__ void __launch_bounds__(256) agent_mlp_unfold_kernel(const float* __re
     const float inv = 1.0f / scale[0];
     constexpr int kN = kRows * ACC_COLS;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < kN; i += gridDim.x * 256) {
-        float s0 = 0.f, s1 = 0.f;
+        // 16 independent loads in flight: with two the 148 round trips to L2 / HBM were the whole cost of this kernel
+        float s[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s[u] = 0.f;
         int c = 0;
-        for (; c + 1 < n_ctas; c += 2) {
-            s0 += acc[(size_t)c * kN + i];
-            s1 += acc[(size_t)(c + 1) * kN + i];
+        for (; c + 15 < n_ctas; c += 16) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) s[u] += __ldcs(acc + (size_t)(c + u) * kN + i);
         }
-        if (c < n_ctas) s0 += acc[(size_t)c * kN + i];
-        red[i] = (s0 + s1) * inv;
+        for (; c < n_ctas; ++c) s[0] += __ldcs(acc + (size_t)c * kN + i);
+#pragma unroll
+        for (int u = 8; u > 0; u >>= 1)
+#pragma unroll
+            for (int v = 0; v < u; ++v) s[v] += s[v + u];
+        red[i] = s[0] * inv;
     }
     __threadfence();
     __syncthreads();
@@ -677,7 +684,7 @@ extern "C" int mm_agent_mlp_unfold(const float* acc, int32_t n_ctas, const float
                                    float* grads, int32_t D, void* stream) {
     ParamPtrs q;
     if (!take_ptrs(params12, q) || !acc || !scale || !red || !grads || n_ctas < 1 || D < 1 || D > K1) return MM_ERR_BAD_ARG;
-    agent_mlp_unfold_kernel<<<80, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, grads, D);
+    agent_mlp_unfold_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, grads, D);
     return mm::check_launch();
 }
 

@@ -863,23 +863,37 @@ __global__ void __launch_bounds__((NSLOT + 1) * 128, 1) trunk2_bwd_kernel(const 
 // LayerNorm(D) without affine of every observation row, once per update: fp32 [rows][D] -> fp16 [rows][K1], zero padded
 __global__ void __launch_bounds__(256) obs_table_kernel(const float* __restrict__ obs, const float* __restrict__ masks,
                                                         __half* __restrict__ out, long long rows, int D) {
-    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    constexpr int RPW = 4;                               // rows per warp: eight loads in flight per lane instead of two
+    const long long r0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW;
     const int lane = threadIdx.x & 31;
-    if (r >= rows) return;
-    const float* src = obs + r * D;
-    const float x0 = lane < D ? src[lane] : 0.f, x1 = lane + 32 < D ? src[lane + 32] : 0.f;
-    float s = x0 + x1;
+    if (r0 >= rows) return;
+    float x0[RPW], x1[RPW], mk[RPW];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(MM_FULL_MASK, s, o);
-    const float mean = s / D;
-    const float d0 = lane < D ? x0 - mean : 0.f, d1 = lane + 32 < D ? x1 - mean : 0.f;
-    float q = d0 * d0 + d1 * d1;
+    for (int u = 0; u < RPW; ++u) {
+        const long long r = min(r0 + u, rows - 1);
+        const float* src = obs + r * D;
+        x0[u] = lane < D ? __ldcs(src + lane) : 0.f;
+        x1[u] = lane + 32 < D ? __ldcs(src + lane + 32) : 0.f;
+        mk[u] = (masks && lane == K1 - 1 - 32) ? masks[r] : 0.f;
+    }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(MM_FULL_MASK, q, o);
-    const float rstd = rsqrtf(q / D + kEps);
-    __half* dst = out + r * K1;
-    dst[lane] = __float2half_rn(d0 * rstd);
-    if (lane + 32 < K1) dst[lane + 32] = (masks && lane + 32 == K1 - 1) ? __float2half_rn(masks[r]) : __float2half_rn(d1 * rstd);
+    for (int u = 0; u < RPW; ++u) {
+        const long long r = r0 + u;
+        float s = x0[u] + x1[u];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(MM_FULL_MASK, s, o);
+        const float mean = s / D;
+        const float d0 = lane < D ? x0[u] - mean : 0.f, d1 = lane + 32 < D ? x1[u] - mean : 0.f;
+        float q = d0 * d0 + d1 * d1;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(MM_FULL_MASK, q, o);
+        const float rstd = rsqrtf(q / D + kEps);
+        if (r < rows) {
+            __half* dst = out + r * K1;
+            dst[lane] = __float2half_rn(d0 * rstd);
+            if (lane + 32 < K1) dst[lane + 32] = (masks && lane + 32 == K1 - 1) ? __float2half_rn(mk[u]) : __float2half_rn(d1 * rstd);
+        }
+    }
 }
 
 // ---- host-side algebra as two launches: folding the LayerNorm affines into the kernel parameters, and (after the backward)
@@ -952,14 +966,21 @@ __global__ void __launch_bounds__(256) trunk2_unfold_kernel(const float* __restr
     const float inv = 1.0f / scale[0];
     constexpr int kN = kRows * ACC_COLS;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < kN; i += gridDim.x * 256) {
-        float s0 = 0.f, s1 = 0.f;
+        // 16 independent loads in flight: with two the 148 round trips to L2 / HBM were the whole cost of this kernel
+        float s[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s[u] = 0.f;
         int c = 0;
-        for (; c + 1 < n_ctas; c += 2) {
-            s0 += acc[(size_t)c * kN + i];
-            s1 += acc[(size_t)(c + 1) * kN + i];
+        for (; c + 15 < n_ctas; c += 16) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) s[u] += __ldcs(acc + (size_t)(c + u) * kN + i);
         }
-        if (c < n_ctas) s0 += acc[(size_t)c * kN + i];
-        red[i] = (s0 + s1) * inv;
+        for (; c < n_ctas; ++c) s[0] += __ldcs(acc + (size_t)c * kN + i);
+#pragma unroll
+        for (int u = 8; u > 0; u >>= 1)
+#pragma unroll
+            for (int v = 0; v < u; ++v) s[v] += s[v + u];
+        red[i] = s[0] * inv;
     }
     __threadfence();
     __syncthreads();
@@ -1161,14 +1182,14 @@ extern "C" int mm_ppo_trunk2_unfold(const float* acc, int32_t n_ctas, const floa
         if (!params18[i]) return MM_ERR_BAD_ARG;
         q.p[i] = static_cast<const float*>(params18[i]);
     }
-    trunk2_unfold_kernel<<<44, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, grads, D, NO);
+    trunk2_unfold_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, grads, D, NO);
     return mm::check_launch();
 }
 
 extern "C" int mm_ppo_obs_table(const float* obs, const float* masks, void* xhat, int64_t rows, int32_t D, void* stream) {
     if (!obs || !xhat || rows <= 0 || D < 1 || D > K1) return MM_ERR_BAD_ARG;
     if (!mm::aligned(xhat, 16) || (masks && D >= K1)) return MM_ERR_BAD_ARG;
-    obs_table_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(obs, masks, static_cast<__half*>(xhat),
+    obs_table_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(obs, masks, static_cast<__half*>(xhat),
                                                                                                   rows, D);
     return mm::check_launch();
 }
