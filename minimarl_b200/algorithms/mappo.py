@@ -613,6 +613,8 @@ class R_MAPPO:
             st["perm"].copy_(st["perms"][epoch])
             if st["graph"] is not None:
                 st["graph"].replay()
+                for opt in (self.policy.actor_optimizer, self.policy.critic_optimizer):
+                    opt.bump_versions()                  # a replay runs no Python; the rollout's packed parameters key on versions
                 continue
             # first epoch with this buffer: a real epoch on a side stream (builds the tables, warms the allocator), then the capture
             side = torch.cuda.Stream(device=dev)

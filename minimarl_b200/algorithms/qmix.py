@@ -330,6 +330,11 @@ class GraphedUpdate:
             self._key = key
             return info
         self._graph.replay()
+        # a replay runs no Python: bump the version counters the packed-parameter caches of the rollout kernels key on
+        tr = self.trainer
+        moved = list(tr.parameters) + [p for pid in tr.policy_ids for p in tr.target_policies[pid].parameters()] + \
+            list(tr.target_mixer.parameters())
+        torch.autograd.graph.increment_version(moved)
         return self._info
 
 

@@ -86,7 +86,14 @@ class FlatAdam(torch.optim.Optimizer):
                                       ptr(self._step), ptr(self._scratch), ptr(self._norm), self.bucket.n_grad, clip_n, float(g["lr"]),
                                       ptr(self._lr), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
                                       float(max_norm) if max_norm else 0.0, stream()))
+        self.bump_versions()
         return self._norm
+
+    def bump_versions(self):
+        """The kernel writes the parameters through raw pointers: tell autograd's version counters, which the packed-parameter
+        caches of the rollout / target kernels key on (``p._version``).  A host-side operation -- callers that REPLAY a captured
+        step (no Python runs then) call it after the replay."""
+        torch.autograd.graph.increment_version(self.bucket.params)
 
     def step(self, closure=None):
         loss = None

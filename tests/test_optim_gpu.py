@@ -61,8 +61,10 @@ def test_flat_adam_views_state_and_replaced_grads(cuda):
     for p in mine:
         assert torch.equal(p.grad, 2 * p.detach())
     before = [p.detach().clone() for p in mine]
+    versions = [p._version for p in mine]
     mine[0].grad = torch.ones_like(mine[0])                          # replaced: not a view any more
     opt.clip_and_step(1.0)
+    assert all(p._version > v for p, v in zip(mine, versions))       # caches keyed on p._version see the raw-pointer update
     assert opt.bucket.attached() and all(not torch.equal(b, p.detach()) for b, p in zip(before, mine))
     sd = opt.state_dict()
     clone = [torch.nn.Parameter(p.detach().clone()) for p in mine]

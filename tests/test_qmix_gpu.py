@@ -270,6 +270,13 @@ def test_graphed_update_replays_the_eager_update(cuda):
                     buf.update_priorities(idx, prio, "policy_0")
                     trainer.soft_target_updates()
                     losses.append(float(info_["loss"]))
+            # the rollout / target kernels read PACKED copies of the parameters, cached on the tensors' version counters: the
+            # optimiser kernel writes through raw pointers and a graph replay runs no Python, so both must bump them
+            from minimarl_b200.nn.agent_q import pack_agentq_tc
+            for net in (policy.q_network, trainer.target_policies["policy_0"].q_network):
+                assert net.tc_ok
+                fresh = pack_agentq_tc(net.state_dict(), net.input_dim, net.hidden_size, net.act_dim, cuda)
+                assert torch.equal(net.packed_tc(), fresh), "stale packed parameters"
             results.append((losses, [p.detach().clone() for p in trainer.parameters],
                             buf._it_sums["policy_0"]._value.clone()))
     finally:
