@@ -541,8 +541,8 @@ def learner_section(dev, steps):
         "metric": "QMIX train samples/sec", "value": world * B * T / (ms_update * 1e-3), "unit": "samples/s",
         "n_gpus": world, "grad_allreduce": "NCCL all-reduce of one flattened fp32 bucket per update" if world > 1 else None,
         "config": {"buffer_episodes": S, "episode_length": T, "batch_episodes_per_gpu": B, "agents": A, "hidden": 64,
-                   "per": True, "double_q": True, "precision": "tf32 / fp16 operands (11-bit significand), fp32 accumulate (custom kernels; cuBLAS for the hypernetworks, "
-                                "the head and the recurrent weight gradients)"},
+                   "per": True, "double_q": True, "precision": "tf32 / fp16 operands (11-bit significand), fp32 accumulate; every kernel of the update is this repo's "
+                                "(no cuBLAS / cutlass launch)"},
         "ms_per_update": ms_update, "ms_per_update_eager_launches": ms_eager,
         "launch_mode": "one CUDA graph per update (GraphedUpdate)" if graphed is not None else "eager launches",
         "ranks_in_sync": _ranks_in_sync(trainer.parameters),
