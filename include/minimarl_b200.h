@@ -582,6 +582,10 @@ int mm_ppo_trunk2_pack(const void* const* params18, float* packed, int32_t D, in
 int mm_ppo_trunk2_grad_layout(int32_t D, int32_t NO, int32_t* offsets19);
 int mm_ppo_trunk2_unfold(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params18,
                          float* grads, int32_t D, int32_t NO, void* stream);
+/* The same with every gradient ADDED to its own destination tensor (grads18: HOST array of the 18 device pointers, in the order of
+ * params18): the parameters' .grad storage -- what autograd's AccumulateGrad would do one launch per tensor later. */
+int mm_ppo_trunk2_unfold_into(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params18,
+                              void* const* grads18, int32_t D, int32_t NO, void* stream);
 int mm_ppo_trunk2_fwd(const float* params, const void* xhat_f16, const int64_t* first, int64_t step_rows, const float* h0,
                       const float* masks, int32_t mask_in_table, float* out, float* h_final, void* saved, int32_t L, int64_t R,
                       int32_t NO, void* stream);

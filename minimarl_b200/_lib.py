@@ -129,6 +129,7 @@ SIGNATURES = {
     "mm_ppo_trunk2_pack": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
     "mm_ppo_trunk2_grad_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "mm_ppo_trunk2_unfold": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "mm_ppo_trunk2_unfold_into": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
     "mm_ppo_obs_table": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
     "mm_ppo_trunk2_fwd": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int64, C.c_int32, _P]),
     "mm_ppo_trunk2_bwd": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64,

@@ -21,7 +21,7 @@ import torch.nn as nn
 from ..nn.agent_q import MLPBase, _init_linear, _tc_fits, agentq_forward, pack_agentq, pack_agentq_tc
 from ..nn.gru import GRU
 from ..nn.layernorm import LayerNorm
-from ..nn.ppo_trunk import ChunkRows, ppo_trunk, trunk_fits
+from ..nn.ppo_trunk import ChunkRows, direct_param_grads, ppo_trunk, trunk_fits
 from ..ops.ppo_loss import ppo_actor_loss, ppo_value_loss
 from ..optim import FlatAdam, clip_and_step, make_adam
 from ..parallel import GradBucket, allreduce_mean_grads, allreduce_stats
@@ -492,7 +492,8 @@ class R_MAPPO:
             to(active_masks_batch) if self._use_policy_active_masks else None, self.clip_param)
         self._zero_grads(self.policy.actor, self.policy.actor_optimizer)
         if update_actor:
-            (policy_loss - dist_entropy * self.entropy_coef).backward()
+            with direct_param_grads():                   # the trunk op adds its 18 gradients into the bucket views itself
+                (policy_loss - dist_entropy * self.entropy_coef).backward()
         allreduce_mean_grads(list(actor.parameters()), bucket=self._buckets.get(id(actor)))
         actor_grad_norm = clip_and_step(self.policy.actor_optimizer, list(actor.parameters()),
                                          self.max_grad_norm if self._use_max_grad_norm else 0.0)
@@ -504,7 +505,8 @@ class R_MAPPO:
             values, _ = critic(g(share_obs_batch), g(rnn_states_critic_batch), g(masks_batch))
         value_loss = self.cal_value_loss(values, to(value_preds_batch), to(return_batch), to(active_masks_batch))
         self._zero_grads(self.policy.critic, self.policy.critic_optimizer)
-        (value_loss * self.value_loss_coef).backward()
+        with direct_param_grads():
+            (value_loss * self.value_loss_coef).backward()
         allreduce_mean_grads(list(critic.parameters()), bucket=self._buckets.get(id(critic)))
         critic_grad_norm = clip_and_step(self.policy.critic_optimizer, list(critic.parameters()),
                                          self.max_grad_norm if self._use_max_grad_norm else 0.0)

@@ -959,8 +959,10 @@ __device__ unsigned int g_unfold_ticket = 0;
 // grid x 256 threads: every CTA sums a slice of the [n_ctas][128][ACC_COLS] accumulators into `red`; the CTA that finishes
 // last (ticket counter) turns them into the parameter gradients (1 / scale applied, LayerNorm affines unfolded:
 // W' = W diag(g), b' = b + W beta  =>  dW = dW' diag(g) + db' beta^T, dg = sum_n dW'[n,:] W[n,:], dbeta = W^T db')
+struct GradPtrs { float* p[Q_N]; };
+
 __global__ void __launch_bounds__(256) trunk2_unfold_kernel(const float* __restrict__ acc, int n_ctas, const float* __restrict__ scale,
-                                                             float* __restrict__ red, const ParamPtrs q, float* __restrict__ grads,
+                                                             float* __restrict__ red, const ParamPtrs q, const GradPtrs gp, int accumulate,
                                                              int D, int NO) {
     __shared__ bool last;
     const float inv = 1.0f / scale[0];
@@ -989,8 +991,10 @@ __global__ void __launch_bounds__(256) trunk2_unfold_kernel(const float* __restr
     if (!last) return;
     __threadfence();
     if (threadIdx.x == 0) g_unfold_ticket = 0;
-    const GradLayout L = grad_layout(D, NO);
     const volatile float* r = red;
+    // one destination tensor per parameter: a flat scratch buffer, or the parameters' own .grad storage (then += : the values are
+    // ADDED to what is there, which is what autograd's AccumulateGrad would do with them one launch per tensor later)
+    auto put = [&](int t, int i, float v) { gp.p[t][i] = accumulate ? gp.p[t][i] + v : v; };
     auto A = [&](int lane, int col) { return r[lane * ACC_COLS + col]; };
     auto B = [&](int lane, int col) { return r[lane * ACC_COLS + ACC_A_COLS + col]; };
     auto whh_lane = [](int g) { return g < 2 * H ? g : g + H; };      // dr | dz | (dn_i) | dn_h
@@ -998,7 +1002,7 @@ __global__ void __launch_bounds__(256) trunk2_unfold_kernel(const float* __restr
     // first Linear and LayerNorm(D)
     for (int i = tid; i < H * D; i += 256) {
         const int n = i / D, k = i - n * D;
-        grads[L.off[Q_W1] + i] = B(n, k) * q.p[Q_LN0W][k] + B(n, 95) * q.p[Q_LN0B][k];
+        put(Q_W1, i, B(n, k) * q.p[Q_LN0W][k] + B(n, 95) * q.p[Q_LN0B][k]);
     }
     for (int k = tid; k < D; k += 256) {
         float gw = 0.f, gb = 0.f;
@@ -1006,27 +1010,27 @@ __global__ void __launch_bounds__(256) trunk2_unfold_kernel(const float* __restr
             gw = fmaf(B(n, k), q.p[Q_W1][n * D + k], gw);
             gb = fmaf(B(n, 95), q.p[Q_W1][n * D + k], gb);
         }
-        grads[L.off[Q_LN0W] + k] = gw;
-        grads[L.off[Q_LN0B] + k] = gb;
+        put(Q_LN0W, k, gw);
+        put(Q_LN0B, k, gb);
     }
     // second Linear and LayerNorm 1
     for (int i = tid; i < H * H; i += 256) {
         const int n = i / H, k = i & (H - 1);
-        grads[L.off[Q_W2] + i] = B(H + n, 48 + k) * q.p[Q_LN1W][k] + B(H + n, 95) * q.p[Q_LN1B][k];
+        put(Q_W2, i, B(H + n, 48 + k) * q.p[Q_LN1W][k] + B(H + n, 95) * q.p[Q_LN1B][k]);
     }
     // GRU input weights and LayerNorm 2; hidden weights
     for (int i = tid; i < 3 * H * H; i += 256) {
         const int g = i / H, k = i & (H - 1);
-        grads[L.off[Q_WIH] + i] = A(g, k) * q.p[Q_LN2W][k] + A(g, 64) * q.p[Q_LN2B][k];
-        grads[L.off[Q_WHH] + i] = A(whh_lane(g), H + k);
+        put(Q_WIH, i, A(g, k) * q.p[Q_LN2W][k] + A(g, 64) * q.p[Q_LN2B][k]);
+        put(Q_WHH, i, A(whh_lane(g), H + k));
     }
     for (int g = tid; g < 3 * H; g += 256) {
-        grads[L.off[Q_BIH] + g] = A(g, 64);
-        grads[L.off[Q_BHH] + g] = A(whh_lane(g), 64);
+        put(Q_BIH, g, A(g, 64));
+        put(Q_BHH, g, A(whh_lane(g), 64));
     }
     for (int k = tid; k < H; k += 256) {
-        grads[L.off[Q_B1] + k] = B(k, 95);
-        grads[L.off[Q_B2] + k] = B(H + k, 95);
+        put(Q_B1, k, B(k, 95));
+        put(Q_B2, k, B(H + k, 95));
         float gw1 = 0.f, gb1 = 0.f, gw2 = 0.f, gb2 = 0.f, gw3 = 0.f, gb3 = 0.f;
         for (int n = 0; n < H; ++n) {
             gw1 = fmaf(B(H + n, 48 + k), q.p[Q_W2][n * H + k], gw1);
@@ -1040,16 +1044,16 @@ __global__ void __launch_bounds__(256) trunk2_unfold_kernel(const float* __restr
             gw3 = fmaf(B(2 * H + k, 80 + o), q.p[Q_WO][o * H + k], gw3);
             gb3 = fmaf(B(96, 80 + o), q.p[Q_WO][o * H + k], gb3);
         }
-        grads[L.off[Q_LN1W] + k] = gw1; grads[L.off[Q_LN1B] + k] = gb1;
-        grads[L.off[Q_LN2W] + k] = gw2; grads[L.off[Q_LN2B] + k] = gb2;
-        grads[L.off[Q_LN3W] + k] = gw3; grads[L.off[Q_LN3B] + k] = gb3;
+        put(Q_LN1W, k, gw1); put(Q_LN1B, k, gb1);
+        put(Q_LN2W, k, gw2); put(Q_LN2B, k, gb2);
+        put(Q_LN3W, k, gw3); put(Q_LN3B, k, gb3);
     }
     // head
     for (int i = tid; i < NO * H; i += 256) {
         const int o = i / H, k = i & (H - 1);
-        grads[L.off[Q_WO] + i] = B(2 * H + k, 80 + o) * q.p[Q_LN3W][k] + B(96, 80 + o) * q.p[Q_LN3B][k];
+        put(Q_WO, i, B(2 * H + k, 80 + o) * q.p[Q_LN3W][k] + B(96, 80 + o) * q.p[Q_LN3B][k]);
     }
-    for (int o = tid; o < NO; o += 256) grads[L.off[Q_BO] + o] = B(96, 80 + o);
+    for (int o = tid; o < NO; o += 256) put(Q_BO, o, B(96, 80 + o));
 }
 
 // power-of-two gradient scale from max |dout|: scale2[0] = 2^floor(log2(64 / max)), scale2[1] = bits of the maximum (zeroed by the
@@ -1174,16 +1178,35 @@ extern "C" int mm_ppo_trunk2_grad_layout(int32_t D, int32_t NO, int32_t* offsets
 
 // acc [n_ctas][128][dims[2]] from mm_ppo_trunk2_bwd -> gradients of the module parameters (PARAM_ORDER, back to back in grads);
 // red: scratch of 128 * dims[2] floats
-extern "C" int mm_ppo_trunk2_unfold(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params18,
-                                    float* grads, int32_t D, int32_t NO, void* stream) {
-    if (!acc || !scale || !red || !params18 || !grads || n_ctas < 1 || D < 1 || D > K1 || NO < 1 || NO > NOMAX) return MM_ERR_BAD_ARG;
+static int unfold_launch(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params18,
+                         const GradPtrs& gp, int accumulate, int32_t D, int32_t NO, void* stream) {
+    if (!acc || !scale || !red || !params18 || n_ctas < 1 || D < 1 || D > K1 || NO < 1 || NO > NOMAX) return MM_ERR_BAD_ARG;
     ParamPtrs q;
     for (int i = 0; i < Q_N; ++i) {
-        if (!params18[i]) return MM_ERR_BAD_ARG;
+        if (!params18[i] || !gp.p[i]) return MM_ERR_BAD_ARG;
         q.p[i] = static_cast<const float*>(params18[i]);
     }
-    trunk2_unfold_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, grads, D, NO);
+    trunk2_unfold_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, gp, accumulate, D, NO);
     return mm::check_launch();
+}
+
+extern "C" int mm_ppo_trunk2_unfold(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params18,
+                                    float* grads, int32_t D, int32_t NO, void* stream) {
+    if (!grads || D < 1 || D > K1 || NO < 1 || NO > NOMAX) return MM_ERR_BAD_ARG;
+    const GradLayout g = grad_layout(D, NO);
+    GradPtrs gp;
+    for (int i = 0; i < Q_N; ++i) gp.p[i] = grads + g.off[i];
+    return unfold_launch(acc, n_ctas, scale, red, params18, gp, 0, D, NO, stream);
+}
+
+// the same, every gradient ADDED to its own destination tensor (grads18: HOST array of 18 device pointers, PARAM_ORDER): the
+// parameters' .grad storage, so that no per-tensor accumulation launch follows
+extern "C" int mm_ppo_trunk2_unfold_into(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params18,
+                                         void* const* grads18, int32_t D, int32_t NO, void* stream) {
+    if (!grads18) return MM_ERR_BAD_ARG;
+    GradPtrs gp;
+    for (int i = 0; i < Q_N; ++i) gp.p[i] = static_cast<float*>(grads18[i]);
+    return unfold_launch(acc, n_ctas, scale, red, params18, gp, 1, D, NO, stream);
 }
 
 extern "C" int mm_ppo_obs_table(const float* obs, const float* masks, void* xhat, int64_t rows, int32_t D, void* stream) {

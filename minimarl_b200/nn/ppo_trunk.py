@@ -187,6 +187,30 @@ def _grad_layout(D, NO):
     return _GRAD_LAYOUT[(D, NO)]
 
 
+class direct_param_grads:
+    """``with direct_param_grads(): loss.backward()`` -- the fused ops add their weight gradients straight into the parameters'
+    existing ``.grad`` tensors (the views of a ``GradBucket``) from the kernel that produces them and hand autograd ``None``: one
+    launch instead of one accumulation launch per parameter tensor (18 per network pass, 540 per MAPPO update).  Only valid for
+    a plain ``backward()`` into ``.grad`` (not ``torch.autograd.grad``), hence opt-in by the trainer."""
+    active = False
+
+    def __enter__(self):
+        self._prev, direct_param_grads.active = direct_param_grads.active, True
+
+    def __exit__(self, *exc):
+        direct_param_grads.active = self._prev
+
+
+def _grad_targets(param_objs):
+    """The ``.grad`` tensors of the parameters when all of them can take a direct write, else None."""
+    if not direct_param_grads.active:
+        return None
+    gs = [p.grad for p in param_objs]
+    if all(g is not None and g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() for g in gs):
+        return gs
+    return None
+
+
 class _PPOTrunkFn(torch.autograd.Function):
     """mm_ppo_trunk2_fwd / mm_ppo_trunk2_bwd: fp16 operands on tcgen05, thread = row, weight gradients inside the backward."""
 
@@ -211,6 +235,7 @@ class _PPOTrunkFn(torch.autograd.Function):
         if train:
             ctx.save_for_backward(packed, xhat, first, masks if masks is not None else packed.new_empty(0), saved, *params)
             ctx.dims = (L, R, D, NO, int(step_rows), masks is not None)
+            ctx.param_objs = list(p.values())            # the Parameters themselves (their .grad may take the gradients directly)
         return out
 
     @staticmethod
@@ -232,9 +257,15 @@ class _PPOTrunkFn(torch.autograd.Function):
                                                 _lib.ptr(scale), _lib.ptr(acc), n_ctas, L, R, NO, _lib.stream()))
         # one launch: sum over the CTAs, 1 / scale, LayerNorm affines unfolded into the gradients of the module's own tensors
         off = _grad_layout(D, NO)
-        flat = torch.empty(off[-1], dtype=torch.float32, device=dout.device)
         red = torch.empty(d["tile_rows"] * d["acc_cols"], dtype=torch.float32, device=dout.device)
         params = [p[k].detach().contiguous() for k in PARAM_ORDER]
+        targets = _grad_targets(ctx.param_objs) if all(ctx.needs_input_grad[7:]) else None
+        if targets is not None:
+            gptrs = (C.c_void_p * len(PARAM_ORDER))(*[g.data_ptr() for g in targets])
+            _lib.check(_lib.lib().mm_ppo_trunk2_unfold_into(_lib.ptr(acc), n_ctas, _lib.ptr(scale), _lib.ptr(red), _ptr_array(params),
+                                                            gptrs, D, NO, _lib.stream()))
+            return (None,) * (7 + len(PARAM_ORDER))
+        flat = torch.empty(off[-1], dtype=torch.float32, device=dout.device)
         _lib.check(_lib.lib().mm_ppo_trunk2_unfold(_lib.ptr(acc), n_ctas, _lib.ptr(scale), _lib.ptr(red),
                                                    _ptr_array(params), _lib.ptr(flat), D, NO, _lib.stream()))
         grads = {k: flat[off[i]: off[i + 1]].view_as(p[k]) for i, k in enumerate(PARAM_ORDER)}
