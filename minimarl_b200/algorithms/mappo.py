@@ -22,7 +22,7 @@ from ..nn.agent_q import MLPBase, _init_linear, _tc_fits, agentq_forward, pack_a
 from ..nn.gru import GRU
 from ..nn.layernorm import LayerNorm
 from ..nn.ppo_trunk import ChunkRows, direct_param_grads, ppo_trunk, trunk_fits
-from ..ops.ppo_loss import ppo_actor_loss, ppo_value_loss
+from ..ops.ppo_loss import ppo_actor_loss, ppo_value_loss, refresh_packs
 from ..optim import FlatAdam, clip_and_step, make_adam
 from ..parallel import GradBucket, allreduce_mean_grads, allreduce_stats
 
@@ -595,6 +595,7 @@ class R_MAPPO:
         for k, src in (("obs", buffer.obs), ("share_obs", buffer.share_obs)):       # this update's normalised fp16 tables, in place
             if k in st["tables"]:
                 obs_table(src.reshape(-1, src.shape[-1]), masks, out=st["tables"][k])
+        refresh_packs(st["tables"])                       # the interleaved loss-input tables (ops/ppo_loss.py), in place
         for opt in (self.policy.actor_optimizer, self.policy.critic_optimizer):
             opt.sync_lr()
         # the epochs' permutations (same generator calls in the same order as the eager loop) are drawn on a second stream while

@@ -9,16 +9,51 @@ import torch
 from .. import _lib
 
 
-def _rows(xs, R):
+def _rows(xs, R, pack_key=None):
     """Per-row inputs: dense [R] vectors, or tables addressed like recurrent_generator's chunks (``ChunkRows`` objects, all
-    sharing one row map).  -> (list of float32 tensors, first, step_rows, n_chunks)."""
+    sharing one row map).  -> (device pointers (int / None), tensors to keep alive, first, step_rows, n_chunks).
+
+    Chunk-addressed tables are read by random 4-byte gathers -- one 32-byte DRAM sector per input and row, which is what bounds
+    the loss kernels.  With a per-update cache (``ChunkRows.cache``) the inputs are interleaved ONCE per update into a [rows, 4]
+    table (kept under ``pack_key``, with its sources under ``pack_key + ":src"`` so that a captured update can refresh it in
+    place): a row's inputs then share one sector, and the kernels' row map ``first[c] + l * step`` runs on 4 x first / 4 x step."""
     lazy = [x for x in xs if x is not None and hasattr(x, "first")]
     if not lazy:
-        return [None if x is None else x.reshape(R).to(torch.float32).contiguous() for x in xs], None, 0, 0
+        ts = [None if x is None else x.reshape(R).to(torch.float32).contiguous() for x in xs]
+        return [_lib.ptr(t) for t in ts], ts, None, 0, 0
     ref = lazy[0]
     assert len(lazy) == sum(x is not None for x in xs) and all(x.first is ref.first and x.step_rows == ref.step_rows for x in lazy)
     assert ref.L * ref.first.numel() == R
-    return [None if x is None else x.table.reshape(-1) for x in xs], ref.first, ref.step_rows, ref.first.numel()
+    cache = getattr(ref, "cache", None)
+    if cache is None or pack_key is None or len(lazy) > 4:
+        ts = [None if x is None else x.table.reshape(-1) for x in xs]
+        return [_lib.ptr(t) for t in ts], ts, ref.first, ref.step_rows, ref.first.numel()
+    pack = cache.get(pack_key)
+    if pack is None:
+        srcs = [x.table.reshape(-1) for x in lazy]
+        n = min(t.numel() for t in srcs)                 # [T] and [T + 1]-step tensors share the (t, env, agent) row index
+        pack = torch.zeros((n, 4), dtype=torch.float32, device=srcs[0].device)
+        for j, t in enumerate(srcs):
+            pack[:, j].copy_(t[:n])
+        cache[pack_key], cache[pack_key + ":src"] = pack, srcs
+    first4 = getattr(ref.first, "_mm_x4", None)
+    if first4 is None:
+        first4 = ref.first * 4
+        ref.first._mm_x4 = first4
+    base, ptrs, j = pack.data_ptr(), [], 0
+    for x in xs:
+        ptrs.append(None if x is None else base + 4 * j)
+        j += x is not None
+    return ptrs, [pack], first4, 4 * ref.step_rows, ref.first.numel()
+
+
+def refresh_packs(cache):
+    """Re-interleave the [rows, 4] loss-input tables of ``_rows`` in place from their (static) sources: a captured update."""
+    for k, srcs in list(cache.items()):
+        if k.endswith(":src"):
+            pack = cache[k[:-4]]
+            for j, t in enumerate(srcs):
+                pack[:, j].copy_(t[:pack.shape[0]])
 
 
 class _ActorLoss(torch.autograd.Function):
@@ -26,15 +61,13 @@ class _ActorLoss(torch.autograd.Function):
     def forward(ctx, logits, actions, old_logp, adv, active, clip):
         R, NA = logits.shape
         logits = logits.contiguous()
-        (actions, old_logp, adv, active), first, step, n_chunks = _rows((actions, old_logp, adv, active), R)
+        ptrs, keep, first, step, n_chunks = _rows((actions, old_logp, adv, active), R, "actor_loss_pack")
         sums = torch.zeros(4, dtype=torch.float64, device=logits.device)
-        _lib.check(_lib.lib().mm_ppo_actor_loss_fwd(_lib.ptr(logits), _lib.ptr(actions), _lib.ptr(old_logp), _lib.ptr(adv),
-                                                    _lib.ptr(active), None, R, NA, float(clip), _lib.ptr(sums), _lib.ptr(first),
-                                                    step, n_chunks, _lib.stream()))
+        _lib.check(_lib.lib().mm_ppo_actor_loss_fwd(_lib.ptr(logits), *ptrs, None, R, NA, float(clip), _lib.ptr(sums),
+                                                    _lib.ptr(first), step, n_chunks, _lib.stream()))
         empty = logits.new_empty(0)
-        ctx.save_for_backward(logits, actions, old_logp, adv, active if active is not None else empty, sums,
-                              first if first is not None else empty)
-        ctx.clip, ctx.has_active, ctx.map = float(clip), active is not None, (first is not None, step, n_chunks)
+        ctx.save_for_backward(logits, sums, first if first is not None else empty, *[t for t in keep if t is not None])
+        ctx.clip, ctx.ptrs, ctx.map = float(clip), ptrs, (first is not None, step, n_chunks)
         policy_loss = (-sums[0] / sums[3]).to(torch.float32)
         entropy = (sums[1] / sums[3]).to(torch.float32)
         ratio = (sums[2] / R).to(torch.float32)
@@ -43,13 +76,12 @@ class _ActorLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_pl, g_ent, _g_ratio):
-        logits, actions, old_logp, adv, active, sums, first = ctx.saved_tensors
+        logits, sums, first = ctx.saved_tensors[:3]          # (the per-row inputs stay alive in saved_tensors[3:]; ctx.ptrs address them)
         R, NA = logits.shape
         inv = (1.0 / sums[3]).to(torch.float32)
         g = torch.stack([-g_pl.to(torch.float32) * inv, g_ent.to(torch.float32) * inv]).contiguous()
         dlogits = torch.empty_like(logits)
-        _lib.check(_lib.lib().mm_ppo_actor_loss_bwd(_lib.ptr(logits), _lib.ptr(actions), _lib.ptr(old_logp), _lib.ptr(adv),
-                                                    _lib.ptr(active if ctx.has_active else None), _lib.ptr(g), _lib.ptr(dlogits),
+        _lib.check(_lib.lib().mm_ppo_actor_loss_bwd(_lib.ptr(logits), *ctx.ptrs, _lib.ptr(g), _lib.ptr(dlogits),
                                                     R, NA, ctx.clip, _lib.ptr(first if ctx.map[0] else None), ctx.map[1],
                                                     ctx.map[2], _lib.stream()))
         return dlogits, None, None, None, None, None
@@ -65,28 +97,26 @@ class _ValueLoss(torch.autograd.Function):
     def forward(ctx, values, value_preds, returns, active, norm, clip, delta, use_huber, use_clipped):
         R = values.numel()
         v = values.reshape(R).to(torch.float32).contiguous()
-        (vp, ret, active), first, step, n_chunks = _rows((value_preds, returns, active), R)
+        ptrs, keep, first, step, n_chunks = _rows((value_preds, returns, active), R, "value_loss_pack")
         sums = torch.zeros(2, dtype=torch.float64, device=values.device)
         cfg = (float(clip), float(delta), int(bool(use_huber)), int(bool(use_clipped)))
-        _lib.check(_lib.lib().mm_ppo_value_loss_fwd(_lib.ptr(v), _lib.ptr(vp), _lib.ptr(ret), _lib.ptr(active), _lib.ptr(norm),
-                                                    R, *cfg, _lib.ptr(sums), _lib.ptr(first), step, n_chunks, _lib.stream()))
+        _lib.check(_lib.lib().mm_ppo_value_loss_fwd(_lib.ptr(v), *ptrs, _lib.ptr(norm), R, *cfg, _lib.ptr(sums), _lib.ptr(first), step,
+                                                    n_chunks, _lib.stream()))
         empty = values.new_empty(0)
-        ctx.save_for_backward(v, vp, ret, active if active is not None else empty, norm if norm is not None else empty, sums,
-                              first if first is not None else empty)
-        ctx.cfg, ctx.has, ctx.map = cfg, (active is not None, norm is not None), (first is not None, step, n_chunks)
+        ctx.save_for_backward(v, norm if norm is not None else empty, sums, first if first is not None else empty,
+                              *[t for t in keep if t is not None])
+        ctx.cfg, ctx.ptrs, ctx.has_norm, ctx.map = cfg, ptrs, norm is not None, (first is not None, step, n_chunks)
         ctx.shape = values.shape
         return (sums[0] / sums[1]).to(torch.float32)
 
     @staticmethod
     def backward(ctx, g_loss):
-        v, vp, ret, active, norm, sums, first = ctx.saved_tensors
+        v, norm, sums, first = ctx.saved_tensors[:4]
         g = (g_loss.to(torch.float32) / sums[1].to(torch.float32)).reshape(1).contiguous()
         dv = torch.empty_like(v)
-        _lib.check(_lib.lib().mm_ppo_value_loss_bwd(_lib.ptr(v), _lib.ptr(vp), _lib.ptr(ret),
-                                                    _lib.ptr(active if ctx.has[0] else None),
-                                                    _lib.ptr(norm if ctx.has[1] else None), _lib.ptr(g), _lib.ptr(dv), v.numel(),
-                                                    *ctx.cfg, _lib.ptr(first if ctx.map[0] else None), ctx.map[1], ctx.map[2],
-                                                    _lib.stream()))
+        _lib.check(_lib.lib().mm_ppo_value_loss_bwd(_lib.ptr(v), *ctx.ptrs, _lib.ptr(norm if ctx.has_norm else None), _lib.ptr(g),
+                                                    _lib.ptr(dv), v.numel(), *ctx.cfg, _lib.ptr(first if ctx.map[0] else None),
+                                                    ctx.map[1], ctx.map[2], _lib.stream()))
         return dv.view(ctx.shape), None, None, None, None, None, None, None, None
 
 
