@@ -278,6 +278,14 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
             for (int kk = 0; kk < K1 / 8; ++kk)
                 tc::mma_tf32(tmem, dA1 + 16 * kk, dW1 + 16 * kk, idesc_h, kk > 0);
             tc::mma_commit(&bar);
+            // the hidden-state halves of the gates only need h_{t-1}: issued now, behind fc1 and outside its commit, they run under
+            // the fc1 / fc2 epilogues instead of in front of the gate phase (columns [H, 4H) are not touched until then)
+#pragma unroll
+            for (int kk = 0; kk < H / 8; ++kk)
+                tc::mma_tf32(tmem + H, dHid + 16 * kk, dWhh_rz + 16 * kk, idesc_2h, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < H / 8; ++kk)
+                tc::mma_tf32(tmem + 3 * H, dHid + 16 * kk, dWhh_n + 16 * kk, idesc_h, kk > 0);
         }
         wait_mma();
 
@@ -306,17 +314,11 @@ agentq_tc_kernel(const float* __restrict__ params, const float* __restrict__ obs
         publish();
         if (tid == 0) {
 #pragma unroll
-            for (int kk = 0; kk < H / 8; ++kk)         // r | z : x part, then h part accumulated on top
-                tc::mma_tf32(tmem + H, dA + 16 * kk, dWih_rz + 16 * kk, idesc_2h, kk > 0);
+            for (int kk = 0; kk < H / 8; ++kk)         // r | z : x part on top of the h part issued at the start of the step
+                tc::mma_tf32(tmem + H, dA + 16 * kk, dWih_rz + 16 * kk, idesc_2h, true);
 #pragma unroll
-            for (int kk = 0; kk < H / 8; ++kk)
-                tc::mma_tf32(tmem + H, dHid + 16 * kk, dWhh_rz + 16 * kk, idesc_2h, true);
-#pragma unroll
-            for (int kk = 0; kk < H / 8; ++kk)         // i_n
+            for (int kk = 0; kk < H / 8; ++kk)         // i_n  (h_n: issued at the start of the step)
                 tc::mma_tf32(tmem, dA + 16 * kk, dWih_n + 16 * kk, idesc_h, kk > 0);
-#pragma unroll
-            for (int kk = 0; kk < H / 8; ++kk)         // h_n
-                tc::mma_tf32(tmem + 3 * H, dHid + 16 * kk, dWhh_n + 16 * kk, idesc_h, kk > 0);
             tc::mma_commit(&bar);
         }
         wait_mma();

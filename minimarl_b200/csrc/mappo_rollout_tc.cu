@@ -264,6 +264,15 @@ __global__ void __launch_bounds__(kThreads, 1) mappo_rollout_kernel(const __grid
 #pragma unroll
             for (int kk = 0; kk < K1 / 8; ++kk) tc::mma_tf32(tmem, dX + 16 * kk, dW1 + 16 * kk, id64, kk > 0);
             tc::mma_commit(&bar);
+            // the hidden-state halves of both nets' gates only need h_{t-1}: issued now, outside fc1's commit, they run under the
+            // fc1 / fc2 epilogues (columns [64, 320) are not touched until the gate phase)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+#pragma unroll
+                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 64 + 64 * k, dHd[k] + 16 * kk, dWhh_rz[k] + 16 * kk, id64, kk > 0);
+#pragma unroll
+                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 256 + 32 * k, dHd[k] + 16 * kk, dWhh_n[k] + 16 * kk, id32, kk > 0);
+            }
         }
         wait_mma();
         // ---- B. fc1 epilogue -> sA[net] ----------------------------------------------------------------------------
@@ -293,13 +302,9 @@ __global__ void __launch_bounds__(kThreads, 1) mappo_rollout_kernel(const __grid
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
 #pragma unroll
-                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 64 + 64 * k, dA[k] + 16 * kk, dWih_rz[k] + 16 * kk, id64, kk > 0);
-#pragma unroll
-                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 64 + 64 * k, dHd[k] + 16 * kk, dWhh_rz[k] + 16 * kk, id64, true);
+                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 64 + 64 * k, dA[k] + 16 * kk, dWih_rz[k] + 16 * kk, id64, true);
 #pragma unroll
                 for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 192 + 32 * k, dA[k] + 16 * kk, dWih_n[k] + 16 * kk, id32, kk > 0);
-#pragma unroll
-                for (int kk = 0; kk < H / 8; ++kk) tc::mma_tf32(tmem + 256 + 32 * k, dHd[k] + 16 * kk, dWhh_n[k] + 16 * kk, id32, kk > 0);
             }
             tc::mma_commit(&bar);
         }
