@@ -354,6 +354,12 @@ class Prioritized_Experience_Replay:
         rc = _lib.lib().mm_heaptree_add_batch(_lib.ptr(tree.priority_tree), self.capacity, tree.n_data, _lib.ptr(prio.contiguous()),
                                               K, _lib.ptr(slot), _lib.stream())
         if rc == -3:                                      # arg-min tree larger than shared memory: one by one
+            if not getattr(self, "_warned_big_tree", False):
+                import warnings
+                warnings.warn(f"mm_heaptree_add_batch: a tree of {self.capacity} slots does not fit in shared memory (limit ~14 000); "
+                              "the reference-order batch insert falls back to one add per chunk (bit-identical, ~0.2 ms each) -- "
+                              "fast_tree=True (set-semantics insert, heaptree_batch.cu) has no such limit", stacklevel=2)
+                self._warned_big_tree = True
             for i in range(K):
                 self.collect_sample([s[i], a[i], r[i], s2[i], d[i]], float(td[i]), warm_up)
             return tree.n_data if warm_up else None
