@@ -187,6 +187,10 @@ int mm_segtree_find_prefixsum(const double* sum_tree, int32_t capacity, const do
 int mm_per_sample(const double* sum_tree, const double* min_tree, int32_t capacity, int32_t len,
                   const double* uniforms, int32_t n, double beta, int64_t* idx_out, double* weights_out,
                   void* stream);
+/* The same with beta read from device memory when the kernel runs: a captured (CUDA graph) update follows the PER beta schedule
+ * (offpolicy/runner/shared/base_runner.py: beta_anneal) without being re-captured. */
+int mm_per_sample_dev(const double* sum_tree, const double* min_tree, int32_t capacity, int32_t len, const double* uniforms,
+                      int32_t n, const double* beta_dev, int64_t* idx_out, double* weights_out, void* stream);
 
 /* RecPolicyBuffer.sample_inds (rec_buffer.py:192-240): gather B episodes idx[b] out of the time-major
  * storage obs [T+1,S,A,D], share_obs [T+1,S,SD], acts [T,S,A,NA], rewards/dones [T,S,A,1],

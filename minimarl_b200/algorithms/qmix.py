@@ -295,22 +295,26 @@ class GraphedUpdate:
     buffer.update_priorities) is unchanged in content; what is dropped is the host-side assert of update_priorities (indices are
     clamped on the device instead) and the host copy of the running maximum priority (kept on the device, read at the next
     insert).  The uniforms of the PER draw are generated outside the graph from the buffer's own generator.  The graph is
-    re-captured when the number of stored episodes or beta changes."""
+    re-captured when the number of stored episodes changes (beta is a device scalar)."""
 
     def __init__(self, trainer, buffer, batch_size, p_id="policy_0"):
         self.trainer, self.buffer, self.batch_size, self.p_id = trainer, buffer, int(batch_size), p_id
         self._graph, self._key, self._info = None, None, None
         self._uniforms = torch.empty(self.batch_size, dtype=torch.float64, device=buffer.device)
+        self._beta = torch.zeros((), dtype=torch.float64, device=buffer.device)    # read by the sampling kernel at replay time
 
     def _step(self, beta):
-        sample = self.buffer.sample(self.batch_size, beta=beta, p_id=self.p_id, uniforms=self._uniforms)
+        sample = self.buffer.sample(self.batch_size, beta=beta, p_id=self.p_id, uniforms=self._uniforms, beta_dev=self._beta)
         info, prio, idx = self.trainer.train_policy_on_batch(sample)
         self.buffer.update_priorities(idx, prio, self.p_id, validate=False)
         self.trainer.soft_target_updates()
         return info
 
     def __call__(self, beta):
-        key = (len(self.buffer), float(beta))
+        # beta travels through a device scalar (the annealing schedule does not force a re-capture); the sharded PER normaliser
+        # of a multi-GPU run still takes it on the host
+        key = (len(self.buffer), float(beta) if getattr(self.buffer, "sharded", False) else None)
+        self._beta.fill_(float(beta))
         self._uniforms.copy_(torch.rand(self.batch_size, dtype=torch.float64, device=self.buffer.device, generator=self.buffer._gen))
         if self._graph is None or key != self._key:
             # a real update on a side stream doubles as the warm-up a capture needs (cuBLAS workspaces, lazy kernel loading)

@@ -192,11 +192,12 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
         self.policy_buffers[p_id].commit(idx_range)
         self._seed_priorities(idx_range)
 
-    def sample(self, batch_size, beta=0, p_id=None, uniforms=None):
+    def sample(self, batch_size, beta=0, p_id=None, uniforms=None, beta_dev=None):
         """Returns the reference's 9-tuple; ``weights`` (float64) and ``batch_inds`` (int64) are CUDA tensors.
-        ``uniforms`` (optional, float64 in [0,1)) replaces the internal draw, for reproducible tests."""
+        ``uniforms`` (optional, float64 in [0,1)) replaces the internal draw, for reproducible tests.  ``beta_dev`` (optional,
+        0-dim float64 CUDA tensor) is read by the kernel instead of ``beta``: a captured update follows the beta schedule."""
         assert len(self) > batch_size, "Cannot sample with no completed episodes in the buffer!"
-        assert beta > 0
+        assert beta > 0 or beta_dev is not None
         if uniforms is None:
             uniforms = torch.rand(batch_size, dtype=torch.float64, device=self.device, generator=self._gen)
         else:
@@ -205,9 +206,14 @@ class PrioritizedRecReplayBuffer(RecReplayBuffer):
         st, mt = self._it_sums[p_id], self._it_mins[p_id]
         batch_inds = torch.empty(batch_size, dtype=torch.int64, device=self.device)
         weights = torch.empty(batch_size, dtype=torch.float64, device=self.device)
-        _lib.check(_lib.lib().mm_per_sample(_lib.ptr(st._value), _lib.ptr(mt._value), st._capacity, len(self),
-                                            _lib.ptr(uniforms), batch_size, float(beta), _lib.ptr(batch_inds),
-                                            _lib.ptr(weights), _lib.stream()))
+        if beta_dev is not None and not self.sharded:
+            _lib.check(_lib.lib().mm_per_sample_dev(_lib.ptr(st._value), _lib.ptr(mt._value), st._capacity, len(self),
+                                                    _lib.ptr(uniforms), batch_size, _lib.ptr(beta_dev), _lib.ptr(batch_inds),
+                                                    _lib.ptr(weights), _lib.stream()))
+        else:
+            _lib.check(_lib.lib().mm_per_sample(_lib.ptr(st._value), _lib.ptr(mt._value), st._capacity, len(self),
+                                                _lib.ptr(uniforms), batch_size, float(beta), _lib.ptr(batch_inds),
+                                                _lib.ptr(weights), _lib.stream()))
         if self.sharded:
             from ..parallel import per_global_weights
             n = len(self)

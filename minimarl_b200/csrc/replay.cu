@@ -78,8 +78,9 @@ __global__ void segtree_find_kernel(const double* __restrict__ tree, int capacit
 // PrioritizedRecReplayBuffer.sample: mass = u * sum(0, len-1), tree descent, importance weights.
 __global__ void per_sample_kernel(const double* __restrict__ sum_tree, const double* __restrict__ min_tree,
                                   int capacity, int len, const double* __restrict__ u, int n, double beta,
-                                  int64_t* __restrict__ idx_out, double* __restrict__ w_out) {
+                                  const double* __restrict__ beta_dev, int64_t* __restrict__ idx_out, double* __restrict__ w_out) {
     __shared__ double s_total, s_whole, s_max_w;
+    if (beta_dev) beta = *beta_dev;                      // a captured update follows the annealing schedule through this scalar
     if (threadIdx.x == 0) {
         // `sum(0, len(self) - 1)`: end is exclusive and the caller already subtracted one (kept as is)
         s_total = range_reduce<false>(sum_tree, 0, len - 2, 1, 0, capacity - 1);
@@ -252,7 +253,19 @@ extern "C" int mm_per_sample(const double* sum_tree, const double* min_tree, int
     if (capacity <= 0 || len < 2 || len > capacity || n <= 0 || !(beta > 0)) return MM_ERR_BAD_ARG;
     const int blocks = (n + 255) / 256 < 148 ? (n + 255) / 256 : 148;
     per_sample_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(sum_tree, min_tree, capacity, len,
-                                                                            uniforms, n, beta, idx_out, weights_out);
+                                                                            uniforms, n, beta, nullptr, idx_out, weights_out);
+    return mm::check_launch();
+}
+
+// the same with beta read from device memory at run time (a CUDA-graph replay of the update follows the beta schedule)
+extern "C" int mm_per_sample_dev(const double* sum_tree, const double* min_tree, int32_t capacity, int32_t len,
+                                 const double* uniforms, int32_t n, const double* beta_dev, int64_t* idx_out, double* weights_out,
+                                 void* stream) {
+    if (!sum_tree || !min_tree || !uniforms || !beta_dev || !idx_out || !weights_out) return MM_ERR_BAD_ARG;
+    if (capacity <= 0 || len < 2 || len > capacity || n <= 0) return MM_ERR_BAD_ARG;
+    const int blocks = (n + 255) / 256 < 148 ? (n + 255) / 256 : 148;
+    per_sample_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(sum_tree, min_tree, capacity, len,
+                                                                            uniforms, n, 0.0, beta_dev, idx_out, weights_out);
     return mm::check_launch();
 }
 

@@ -96,9 +96,27 @@ class MAGYM_Runner:
             rewards.append(self.collect_rollout(explore=True, training_episode=False, warmup=True)["average_episode_rewards"])
         self.warmup_reward = torch.stack(rewards).mean()
 
+    def _graphed_update(self):
+        """The whole update (PER draw, gather, train_policy_on_batch, priority write-back, soft target update) as one CUDA graph
+        replay (algorithms.qmix.GraphedUpdate) once the buffer is full -- its length is part of the captured sampling kernel --
+        for the configuration the reference defaults to: one policy, PER, soft target updates."""
+        if not (getattr(self.args, "train_graph", True) and self.use_per and self.use_soft_update and len(self.policy_ids) == 1
+                and torch.device(self.device).type == "cuda" and hasattr(self.trainer, "train_policy_on_batch")
+                and len(self.buffer) == self.buffer.policy_buffers[self.policy_ids[0]].buffer_size):
+            return None
+        g = getattr(self, "_graphed", None)
+        if g is None:
+            from ..algorithms.qmix import GraphedUpdate
+            g = self._graphed = GraphedUpdate(self.trainer, self.buffer, self.batch_size, self.policy_ids[0])
+        return g
+
     def batch_train_q(self):
         self.trainer.prep_training()
         self.train_infos = []
+        graphed = self._graphed_update()
+        if graphed is not None:
+            self.train_infos.append(graphed(self.beta_anneal.eval(self.total_train_steps)))
+            return
         for p_id in self.policy_ids:
             if self.use_per:
                 beta = self.beta_anneal.eval(self.total_train_steps)
