@@ -259,6 +259,8 @@ int mm_qmixer_bwd(const void* const* params14, const float* agent_q, const float
                   float* dq, float* acc, float* vec, int32_t n_acc_ctas, int64_t M, int32_t SD, int32_t n_agents, void* stream);
 int mm_qmixer_bwd_unfold(const float* acc, const float* vec, int32_t n_ctas, const float* scale, float* grads, int32_t SD,
                          void* stream);
+int mm_qmixer_bwd_unfold_into(const float* acc, const float* vec, int32_t n_ctas, const float* scale, void* const* grads14,
+                              int32_t SD, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Tail of QMix.train_policy_on_batch (offpolicy/algorithms/qmix/qmix.py:134-191).
@@ -626,6 +628,10 @@ int mm_agent_mlp_pack(const void* const* params12, float* packed, int32_t D, voi
 int mm_agent_mlp_grad_layout(int32_t D, int32_t* offsets13);
 int mm_agent_mlp_unfold(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params12, float* grads,
                         int32_t D, void* stream);
+/* ..._into: every gradient ADDED to its own destination tensor (HOST array of device pointers, same order as the parameters):
+ * the parameters' .grad storage, so that autograd's per-tensor accumulation launches disappear (nn/_direct.py). */
+int mm_agent_mlp_unfold_into(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params12,
+                             void* const* grads12, int32_t D, void* stream);
 int mm_agent_mlp_bwd_ctas(int64_t rows);
 int mm_agent_mlp_fwd(const float* params, const float* obs, float* gi, float* saved_rows, void* saved_x0, int64_t rows, int32_t D,
                      void* stream);
@@ -693,10 +699,10 @@ int mm_ln_head_bwd(const float* dq, const float* h, const float* mean, const flo
  * db_hh [3H] = the column sums, contracted over all T * R rows -- the weight_hh_l0 / bias_hh_l0 gradients of nn.GRU in RNNLayer
  * (rnn.py:4-47) under qmix.py:196's backward.  dgi [T R, 3H] and dghn [T R, H] from mm_gru_seq_bwd, h_seq [T R, H] from
  * mm_gru_seq_fwd (h_prev of step t is h_seq[t - 1], of step 0 h0 or zero), scale = mm_ppo_trunk2_scale(dgi) (device), acc: scratch
- * of n_acc_ctas >= mm_gru_wgrad_ctas(T R) x 128 x 3H floats.  H = 64. */
+ * of n_acc_ctas >= mm_gru_wgrad_ctas(T R) x 128 x 3H floats; accumulate != 0 adds to dw_hh / db_hh instead of writing.  H = 64. */
 int mm_gru_wgrad_ctas(int64_t rows);
 int mm_gru_wgrad(const float* dgi, const float* dghn, const float* h_seq, const float* h0, const float* scale, float* acc,
-                 int32_t n_acc_ctas, float* dw_hh, float* db_hh, int32_t T, int64_t R, int32_t H, void* stream);
+                 int32_t n_acc_ctas, float* dw_hh, float* db_hh, int32_t accumulate, int32_t T, int64_t R, int32_t H, void* stream);
 
 #ifdef __cplusplus
 }

@@ -100,10 +100,11 @@ SIGNATURES = {
     "mm_qmixer_bwd_grad_layout": (C.c_int, [C.c_int32, C.POINTER(C.c_int32)]),
     "mm_qmixer_bwd": (C.c_int, [_P] * 8 + [C.c_int32, C.c_int64, C.c_int32, C.c_int32, _P]),
     "mm_qmixer_bwd_unfold": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int32, _P]),
+    "mm_qmixer_bwd_unfold_into": (C.c_int, [_P, _P, C.c_int32, _P, _P, C.c_int32, _P]),
     "mm_ln_head_fwd": (C.c_int, [_P] * 8 + [C.c_int64, C.c_int32, C.c_int32, _P]),
     "mm_ln_head_bwd": (C.c_int, [_P] * 12 + [C.c_int64, C.c_int32, C.c_int32, _P]),
     "mm_gru_wgrad_ctas": (C.c_int, [C.c_int64]),
-    "mm_gru_wgrad": (C.c_int, [_P] * 6 + [C.c_int32, _P, _P, C.c_int32, C.c_int64, C.c_int32, _P]),
+    "mm_gru_wgrad": (C.c_int, [_P] * 6 + [C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P]),
     "mm_colsum": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P]),
     "mm_clip_adam_scratch_doubles": (C.c_int, []),
     "mm_clip_adam_step": (C.c_int, [_P] * 7 + [C.c_int64, C.c_int64, C.c_float, _P] + [C.c_float] * 5 + [_P]),
@@ -140,6 +141,7 @@ SIGNATURES = {
     "mm_agent_mlp_pack": (C.c_int, [_P, _P, C.c_int32, _P]),
     "mm_agent_mlp_grad_layout": (C.c_int, [C.c_int32, C.POINTER(C.c_int32)]),
     "mm_agent_mlp_unfold": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P]),
+    "mm_agent_mlp_unfold_into": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P]),
     "mm_agent_mlp_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "mm_agent_mlp_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, _P]),
     "mm_tc_raw_f16_selftest": (C.c_int, [_P, _P, _P] + [C.c_int32] * 11 + [_P]),

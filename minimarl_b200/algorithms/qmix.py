@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from ..nn import AgentQFunction, QMixer, VDNMixer
+from ..nn._direct import direct_param_grads
 from ..ops.td import q_select, qmix_td_loss
 from ..optim import FlatAdam, clip_and_step, make_adam
 from ..parallel import GradBucket, allreduce_mean_grads
@@ -255,7 +256,8 @@ class QMix:
         new_priorities = prio if self.use_per else None
 
         self._zero_grads()
-        loss.backward()
+        with direct_param_grads():                       # the fused ops add their weight gradients into the bucket views themselves
+            loss.backward()
         self._allreduce_grads()
         grad_norm = clip_and_step(self.optimizer, self.parameters, self.args.max_grad_norm)
         train_info = {"loss": loss.detach(), "grad_norm": grad_norm, "Q_tot": q_tot_mean}

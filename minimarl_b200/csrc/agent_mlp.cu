@@ -553,8 +553,10 @@ __device__ unsigned int g_unfold_ticket = 0;
 
 // every CTA sums a slice of the [n_ctas][128][ACC_COLS] accumulators into `red`; the last one turns them into gradients:
 // W' = W diag(g), b' = b + W beta  =>  dW = dW' diag(g) + db' beta^T, dg = sum_n dW'[n,:] W[n,:], dbeta = W^T db'
+struct GradPtrs { float* p[Q_N]; };
+
 __global__ void __launch_bounds__(256) agent_mlp_unfold_kernel(const float* __restrict__ acc, int n_ctas, const float* __restrict__ scale,
-                                                                float* __restrict__ red, const ParamPtrs q, float* __restrict__ grads,
+                                                                float* __restrict__ red, const ParamPtrs q, const GradPtrs gp, int accumulate,
                                                                 int D) {
     __shared__ bool last;
     const float inv = 1.0f / scale[0];
@@ -583,8 +585,9 @@ __global__ void __launch_bounds__(256) agent_mlp_unfold_kernel(const float* __re
     if (!last) return;
     __threadfence();
     if (threadIdx.x == 0) g_unfold_ticket = 0;
-    const GradLayout L = grad_layout(D);
     const volatile float* r = red;
+    // one destination per parameter tensor: a flat scratch buffer (=) or the parameters' own .grad storage (+=)
+    auto put = [&](int t, int i, float v) { gp.p[t][i] = accumulate ? gp.p[t][i] + v : v; };
     // T1: lanes xh2 feature | 1 [64] x gate column;  T2: lanes xh1 feature | 1 [64] x fc2 output;  T3: 64-row accumulator (row r in
     // lane 32 (r / 16) + r % 16): rows x0 feature | 1 [48] x fc1 output
     auto T1 = [&](int lane, int col) { return r[lane * ACC_COLS + col]; };
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(256) agent_mlp_unfold_kernel(const float* __re
     const int tid = threadIdx.x;
     for (int i = tid; i < H * D; i += 256) {
         const int n = i / D, k = i - n * D;
-        grads[L.off[Q_W1] + i] = T3(k, n) * q.p[Q_LN0W][k] + T3(K1, n) * q.p[Q_LN0B][k];
+        put(Q_W1, i, T3(k, n) * q.p[Q_LN0W][k] + T3(K1, n) * q.p[Q_LN0B][k]);
     }
     for (int k = tid; k < D; k += 256) {
         float gw = 0.f, gb = 0.f;
@@ -601,21 +604,21 @@ __global__ void __launch_bounds__(256) agent_mlp_unfold_kernel(const float* __re
             gw = fmaf(T3(k, n), q.p[Q_W1][n * D + k], gw);
             gb = fmaf(T3(K1, n), q.p[Q_W1][n * D + k], gb);
         }
-        grads[L.off[Q_LN0W] + k] = gw;
-        grads[L.off[Q_LN0B] + k] = gb;
+        put(Q_LN0W, k, gw);
+        put(Q_LN0B, k, gb);
     }
     for (int i = tid; i < H * H; i += 256) {
         const int n = i / H, k = i & (H - 1);
-        grads[L.off[Q_W2] + i] = T2(k, n) * q.p[Q_LN1W][k] + T2(H, n) * q.p[Q_LN1B][k];
+        put(Q_W2, i, T2(k, n) * q.p[Q_LN1W][k] + T2(H, n) * q.p[Q_LN1B][k]);
     }
     for (int i = tid; i < G3 * H; i += 256) {
         const int g = i / H, k = i & (H - 1);
-        grads[L.off[Q_WIH] + i] = T1(k, g) * q.p[Q_LN2W][k] + T1(H, g) * q.p[Q_LN2B][k];
+        put(Q_WIH, i, T1(k, g) * q.p[Q_LN2W][k] + T1(H, g) * q.p[Q_LN2B][k]);
     }
-    for (int g = tid; g < G3; g += 256) grads[L.off[Q_BIH] + g] = T1(H, g);
+    for (int g = tid; g < G3; g += 256) put(Q_BIH, g, T1(H, g));
     for (int k = tid; k < H; k += 256) {
-        grads[L.off[Q_B1] + k] = T3(K1, k);
-        grads[L.off[Q_B2] + k] = T2(H, k);
+        put(Q_B1, k, T3(K1, k));
+        put(Q_B2, k, T2(H, k));
         float gw1 = 0.f, gb1 = 0.f, gw2 = 0.f, gb2 = 0.f;
         for (int n = 0; n < H; ++n) {
             gw1 = fmaf(T2(k, n), q.p[Q_W2][n * H + k], gw1);
@@ -625,8 +628,8 @@ __global__ void __launch_bounds__(256) agent_mlp_unfold_kernel(const float* __re
             gw2 = fmaf(T1(k, g), q.p[Q_WIH][g * H + k], gw2);
             gb2 = fmaf(T1(H, g), q.p[Q_WIH][g * H + k], gb2);
         }
-        grads[L.off[Q_LN1W] + k] = gw1; grads[L.off[Q_LN1B] + k] = gb1;
-        grads[L.off[Q_LN2W] + k] = gw2; grads[L.off[Q_LN2B] + k] = gb2;
+        put(Q_LN1W, k, gw1); put(Q_LN1B, k, gb1);
+        put(Q_LN2W, k, gw2); put(Q_LN2B, k, gb2);
     }
 }
 
@@ -680,12 +683,32 @@ extern "C" int mm_agent_mlp_grad_layout(int32_t D, int32_t* offsets13) {
     return MM_OK;
 }
 
+static int unfold_launch(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params12,
+                         const GradPtrs& gp, int accumulate, int32_t D, void* stream) {
+    ParamPtrs q;
+    if (!take_ptrs(params12, q) || !acc || !scale || !red || n_ctas < 1 || D < 1 || D > K1) return MM_ERR_BAD_ARG;
+    for (int i = 0; i < Q_N; ++i)
+        if (!gp.p[i]) return MM_ERR_BAD_ARG;
+    agent_mlp_unfold_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, gp, accumulate, D);
+    return mm::check_launch();
+}
+
 extern "C" int mm_agent_mlp_unfold(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params12,
                                    float* grads, int32_t D, void* stream) {
-    ParamPtrs q;
-    if (!take_ptrs(params12, q) || !acc || !scale || !red || !grads || n_ctas < 1 || D < 1 || D > K1) return MM_ERR_BAD_ARG;
-    agent_mlp_unfold_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, grads, D);
-    return mm::check_launch();
+    if (!grads || D < 1 || D > K1) return MM_ERR_BAD_ARG;
+    const GradLayout L = grad_layout(D);
+    GradPtrs gp;
+    for (int i = 0; i < Q_N; ++i) gp.p[i] = grads + L.off[i];
+    return unfold_launch(acc, n_ctas, scale, red, params12, gp, 0, D, stream);
+}
+
+// the same, every gradient ADDED to its own destination tensor (grads12: HOST array of 12 device pointers, order of params12)
+extern "C" int mm_agent_mlp_unfold_into(const float* acc, int32_t n_ctas, const float* scale, float* red, const void* const* params12,
+                                        void* const* grads12, int32_t D, void* stream) {
+    if (!grads12) return MM_ERR_BAD_ARG;
+    GradPtrs gp;
+    for (int i = 0; i < Q_N; ++i) gp.p[i] = static_cast<float*>(grads12[i]);
+    return unfold_launch(acc, n_ctas, scale, red, params12, gp, 1, D, stream);
 }
 
 extern "C" int mm_agent_mlp_bwd_ctas(int64_t rows) {

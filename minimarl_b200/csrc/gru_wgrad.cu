@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) gru_wgrad_kernel(const __grid_con
 
 // one thread per gradient element: dw_hh [3H][H] then db_hh [3H]
 __global__ void __launch_bounds__(256) gru_wgrad_unfold_kernel(const float* __restrict__ acc, int n_ctas, const float* __restrict__ scale,
-                                                                float* __restrict__ dw_hh, float* __restrict__ db_hh) {
+                                                                float* __restrict__ dw_hh, float* __restrict__ db_hh, int accumulate) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= G3 * H + G3) return;
     int lane, col;
@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(256) gru_wgrad_unfold_kernel(const float* __re
     }
     if (c < n_ctas) s0 += p[c * stride];
     const float v = (s0 + s1) / scale[0];
-    if (i < G3 * H) dw_hh[i] = v;
-    else            db_hh[col] = v;
+    float* dst = i < G3 * H ? dw_hh + i : db_hh + col;
+    *dst = accumulate ? *dst + v : v;
 }
 
 int n_sms() {
@@ -184,8 +184,10 @@ extern "C" int mm_gru_wgrad_ctas(int64_t rows) {
 }
 
 // acc: scratch [n_acc_ctas >= mm_gru_wgrad_ctas(T R)][128][3H] floats.  scale: device float (mm_ppo_trunk2_scale of dgi).
+// accumulate != 0: the gradients are ADDED to dw_hh / db_hh (the parameters' .grad storage) instead of written.
 extern "C" int mm_gru_wgrad(const float* dgi, const float* dghn, const float* h_seq, const float* h0, const float* scale, float* acc,
-                            int32_t n_acc_ctas, float* dw_hh, float* db_hh, int32_t T, int64_t R, int32_t Hh, void* stream) {
+                            int32_t n_acc_ctas, float* dw_hh, float* db_hh, int32_t accumulate, int32_t T, int64_t R, int32_t Hh,
+                            void* stream) {
     if (!dgi || !dghn || !h_seq || !scale || !acc || !dw_hh || !db_hh || T <= 0 || R <= 0) return MM_ERR_BAD_ARG;
     if (Hh != H) return MM_ERR_UNSUPPORTED;
     if (!mm::aligned(dgi, 16) || !mm::aligned(dghn, 16) || !mm::aligned(h_seq, 16) || (h0 && !mm::aligned(h0, 16)) || !mm::aligned(acc, 16))
@@ -197,6 +199,6 @@ extern "C" int mm_gru_wgrad(const float* dgi, const float* dghn, const float* h_
     cudaError_t e = cudaFuncSetAttribute(gru_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_BYTES);
     if (e != cudaSuccess) { mm::set_last_error(e); return MM_ERR_LAUNCH; }
     gru_wgrad_kernel<<<grid, kThreads, S_BYTES, st>>>(a);
-    gru_wgrad_unfold_kernel<<<(G3 * H + G3 + 255) / 256, 256, 0, st>>>(acc, grid, scale, dw_hh, db_hh);
+    gru_wgrad_unfold_kernel<<<(G3 * H + G3 + 255) / 256, 256, 0, st>>>(acc, grid, scale, dw_hh, db_hh, accumulate);
     return mm::check_launch();
 }

@@ -381,8 +381,10 @@ __host__ __device__ inline GradLayout grad_layout(int SD) {
 }
 
 // one thread per gradient element: sum of its accumulator slot over the CTAs, scale removed
+struct GradPtrs { float* p[P_N]; };
+
 __global__ void __launch_bounds__(256) qmixer_bwd_unfold_kernel(const float* __restrict__ acc, const float* __restrict__ vec, int n_ctas,
-                                                                 const float* __restrict__ scale, float* __restrict__ grads, int SD) {
+                                                                 const float* __restrict__ scale, const GradPtrs gp, int accumulate, int SD) {
     const GradLayout L = grad_layout(SD);
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= L.off[P_N]) return;
@@ -419,7 +421,8 @@ __global__ void __launch_bounds__(256) qmixer_bwd_unfold_kernel(const float* __r
     } else {
         for (int c = 0; c < n_ctas; ++c) s0 += vec[(size_t)c * VEC + vi];
     }
-    grads[i] = (s0 + s1) / (scale[0] * kScaleMul);
+    const float v = (s0 + s1) / (scale[0] * kScaleMul);
+    gp.p[t][j] = accumulate ? gp.p[t][j] + v : v;
 }
 
 int n_sms() {
@@ -480,7 +483,24 @@ extern "C" int mm_qmixer_bwd_unfold(const float* acc, const float* vec, int32_t 
                                     void* stream) {
     if (!acc || !vec || !scale || !grads || n_ctas < 1) return MM_ERR_BAD_ARG;
     if (SD < 2 || SD > SDMAX || (SD & 1)) return MM_ERR_UNSUPPORTED;
-    const int total = grad_layout(SD).off[P_N];
-    qmixer_bwd_unfold_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, vec, n_ctas, scale, grads, SD);
+    const GradLayout L = grad_layout(SD);
+    GradPtrs gp;
+    for (int i = 0; i < P_N; ++i) gp.p[i] = grads + L.off[i];
+    qmixer_bwd_unfold_kernel<<<(L.off[P_N] + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, vec, n_ctas, scale, gp, 0, SD);
+    return mm::check_launch();
+}
+
+// the same, every gradient ADDED to its own destination tensor (grads14: HOST array of 14 device pointers, module order)
+extern "C" int mm_qmixer_bwd_unfold_into(const float* acc, const float* vec, int32_t n_ctas, const float* scale, void* const* grads14,
+                                         int32_t SD, void* stream) {
+    if (!acc || !vec || !scale || !grads14 || n_ctas < 1) return MM_ERR_BAD_ARG;
+    if (SD < 2 || SD > SDMAX || (SD & 1)) return MM_ERR_UNSUPPORTED;
+    GradPtrs gp;
+    for (int i = 0; i < P_N; ++i) {
+        if (!grads14[i]) return MM_ERR_BAD_ARG;
+        gp.p[i] = static_cast<float*>(grads14[i]);
+    }
+    qmixer_bwd_unfold_kernel<<<(grad_layout(SD).off[P_N] + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, vec, n_ctas, scale,
+                                                                                                                    gp, 1, SD);
     return mm::check_launch();
 }

@@ -13,6 +13,7 @@ import torch
 
 from .. import _lib
 from ..ops.gram import colsum, gram
+from ._direct import grad_targets
 
 H, K1 = 64, 48
 _DIMS = None
@@ -56,6 +57,7 @@ class _AgentMlpFn(torch.autograd.Function):
     def forward(ctx, obs, *params):                 # params: ln0_w, ln0_b, w1, b1, ln1_w, ln1_b, w2, b2, ln2_w, ln2_b, wih, bih
         rows, D = obs.shape
         d = dims()
+        param_objs = list(params)                      # the Parameters themselves (their .grad may take the gradients directly)
         params = [t.detach().contiguous() for t in params]
         packed = torch.empty(d["n_params"], dtype=torch.float32, device=obs.device)
         _lib.check(_lib.lib().mm_agent_mlp_pack(_ptr_array(params), _lib.ptr(packed), D, _lib.stream()))
@@ -71,6 +73,7 @@ class _AgentMlpFn(torch.autograd.Function):
         if train:
             ctx.save_for_backward(packed, saved_rows, saved_x0, *params)
             ctx.dims = (rows, D)
+            ctx.param_objs = param_objs
         return gi
 
     @staticmethod
@@ -91,8 +94,14 @@ class _AgentMlpFn(torch.autograd.Function):
                                         _lib.ptr(acc), n_ctas, rows, _lib.stream()))
         # one launch: sum over the CTAs, 1 / scale, LayerNorm affines unfolded into the gradients of the module's own tensors
         off = _grad_layout(D)
-        flat = torch.empty(off[-1], dtype=torch.float32, device=dgi.device)
         red = torch.empty(d["tile_rows"] * d["acc_cols"], dtype=torch.float32, device=dgi.device)
+        targets = grad_targets(ctx.param_objs, ctx.needs_input_grad[1:])
+        if targets is not None:
+            gptrs = (C.c_void_p * len(targets))(*[g.data_ptr() for g in targets])
+            _lib.check(lib.mm_agent_mlp_unfold_into(_lib.ptr(acc), n_ctas, _lib.ptr(scale), _lib.ptr(red), _ptr_array(params), gptrs, D,
+                                                    _lib.stream()))
+            return (None,) * (1 + len(params))
+        flat = torch.empty(off[-1], dtype=torch.float32, device=dgi.device)
         _lib.check(lib.mm_agent_mlp_unfold(_lib.ptr(acc), n_ctas, _lib.ptr(scale), _lib.ptr(red), _ptr_array(params), _lib.ptr(flat),
                                            D, _lib.stream()))
         return (None,) + tuple(flat[off[i]: off[i + 1]].view_as(params[i]) if ctx.needs_input_grad[1 + i] else None
@@ -122,6 +131,7 @@ class _GruFromGiFn(torch.autograd.Function):
         if need:
             ctx.save_for_backward(h0c if h0c is not None else torch.empty(0, device=gi.device), w_hh, h_seq, *saved)
             ctx.dims = (T, R, Hh, h0 is not None)
+            ctx.param_objs = [w_hh, b_hh]
         return h_seq
 
     @staticmethod
@@ -143,9 +153,13 @@ class _GruFromGiFn(torch.autograd.Function):
             # dW_hh / db_hh on tcgen05 straight from dgi, dgh_n and the (shifted) h_seq: no h_prev copy, no cuBLAS, no column sums
             n_ctas = lib.mm_gru_wgrad_ctas(T * R)
             acc = torch.empty((n_ctas, 128, 3 * Hh), **z_)
-            dw_hh, db_hh = torch.empty((3 * Hh, Hh), **z_), torch.empty(3 * Hh, **z_)
+            targets = grad_targets(ctx.param_objs, ctx.needs_input_grad[2:4])
+            dw_hh, db_hh = targets if targets is not None else (torch.empty((3 * Hh, Hh), **z_), torch.empty(3 * Hh, **z_))
             _lib.check(lib.mm_gru_wgrad(_lib.ptr(dgi), _lib.ptr(dghn), _lib.ptr(h_seq), _lib.ptr(h0 if has_h0 else None), _lib.ptr(scale),
-                                        _lib.ptr(acc), n_ctas, _lib.ptr(dw_hh), _lib.ptr(db_hh), T, R, Hh, _lib.stream()))
+                                        _lib.ptr(acc), n_ctas, _lib.ptr(dw_hh), _lib.ptr(db_hh), int(targets is not None), T, R, Hh,
+                                        _lib.stream()))
+            if targets is not None:
+                dw_hh = db_hh = None                     # already added to the parameters' .grad
             return dgi, (dh0 if (has_h0 and ctx.needs_input_grad[1]) else None), dw_hh, db_hh, None, None
         h_prev = torch.empty((T, R, Hh), **z_)
         if has_h0:
@@ -181,6 +195,7 @@ class _LnHeadFn(torch.autograd.Function):
         _lib.check(_lib.lib().mm_ln_head_fwd(_lib.ptr(h), *[_lib.ptr(t) for t in ps], _lib.ptr(q), _lib.ptr(mean), _lib.ptr(rstd),
                                              M, Hh, NA, _lib.stream()))
         ctx.save_for_backward(h, mean, rstd, *ps)
+        ctx.param_objs = [ln_w, ln_b, wq, bq]
         return q
 
     @staticmethod
@@ -190,6 +205,13 @@ class _LnHeadFn(torch.autograd.Function):
         NA = wq.shape[0]
         z = dict(dtype=torch.float32, device=h.device)
         dh = torch.empty_like(h)
+        targets = grad_targets(ctx.param_objs, ctx.needs_input_grad[1:])
+        if targets is not None:                          # the kernel accumulates: straight into the parameters' .grad
+            g_lnw, g_lnb, g_wq, g_bq = targets
+            _lib.check(_lib.lib().mm_ln_head_bwd(_lib.ptr(dq.contiguous()), _lib.ptr(h), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(ln_w),
+                                                 _lib.ptr(ln_b), _lib.ptr(wq), _lib.ptr(dh), _lib.ptr(g_wq), _lib.ptr(g_bq),
+                                                 _lib.ptr(g_lnw), _lib.ptr(g_lnb), M, Hh, NA, _lib.stream()))
+            return dh, None, None, None, None
         flat = torch.zeros(NA * Hh + NA + 2 * Hh, **z)                    # dwq | dbq | dln_w | dln_b, accumulated by the kernel
         dwq, dbq, dg, db = flat[:NA * Hh].view(NA, Hh), flat[NA * Hh:NA * Hh + NA], flat[NA * Hh + NA:NA * Hh + NA + Hh], flat[NA * Hh + NA + Hh:]
         _lib.check(_lib.lib().mm_ln_head_bwd(_lib.ptr(dq.contiguous()), _lib.ptr(h), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(ln_w),

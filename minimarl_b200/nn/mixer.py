@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
+from ._direct import grad_targets
 from .linear import Linear
 
 _NAMES = ["wcat", "bcat", "w1b", "b1b", "w2b", "b2b", "wb2", "bb2"]
@@ -138,6 +139,7 @@ class _QMixerLiveFn(torch.autograd.Function):
         SD = states.shape[1]
         lib = _lib.lib()
         q, states = q.contiguous(), states.contiguous()
+        ctx.param_objs = list(params)                   # the Parameters themselves (their .grad may take the gradients directly)
         params = [t.detach().contiguous() for t in params]
         packed = torch.empty(lib.mm_qmixer_tc_param_count(SD, A), dtype=torch.float32, device=q.device)
         _lib.check(lib.mm_qmixer_tc_pack(_ptr_array(params), _lib.ptr(packed), SD, A, _lib.stream()))
@@ -160,9 +162,15 @@ class _QMixerLiveFn(torch.autograd.Function):
         _lib.check(lib.mm_ppo_trunk2_scale(_lib.ptr(dout), M, _lib.ptr(scale), _lib.stream()))
         n_ctas = lib.mm_qmixer_bwd_ctas(M)
         acc, vec = torch.empty((n_ctas, tile_rows, acc_cols), **z), torch.empty((n_ctas, vec_n), **z)
-        dq, grads = torch.empty_like(q), torch.empty(n_grads, **z)
+        dq = torch.empty_like(q)
         _lib.check(lib.mm_qmixer_bwd(_ptr_array(params), _lib.ptr(q), _lib.ptr(states), _lib.ptr(dout), _lib.ptr(scale), _lib.ptr(dq),
                                      _lib.ptr(acc), _lib.ptr(vec), n_ctas, M, SD, A, _lib.stream()))
+        targets = grad_targets(ctx.param_objs, ctx.needs_input_grad[2:])
+        if targets is not None:
+            gptrs = (C.c_void_p * len(targets))(*[g.data_ptr() for g in targets])
+            _lib.check(lib.mm_qmixer_bwd_unfold_into(_lib.ptr(acc), _lib.ptr(vec), n_ctas, _lib.ptr(scale), gptrs, SD, _lib.stream()))
+            return (dq if ctx.needs_input_grad[0] else None, None) + (None,) * len(params)
+        grads = torch.empty(n_grads, **z)
         _lib.check(lib.mm_qmixer_bwd_unfold(_lib.ptr(acc), _lib.ptr(vec), n_ctas, _lib.ptr(scale), _lib.ptr(grads), SD, _lib.stream()))
         return (dq if ctx.needs_input_grad[0] else None, None) + tuple(
             grads[off[i]:off[i + 1]].view_as(params[i]) if ctx.needs_input_grad[2 + i] else None for i in range(len(params)))

@@ -16,6 +16,7 @@ import torch
 
 from .. import _lib
 from ..ops.gram import gram
+from ._direct import direct_param_grads, grad_targets  # noqa: F401  (re-exported)
 
 _OFF = None
 _NAMES = "w1 w2 wih whh small b1 ln1_w ln1_b b2 ln2_w ln2_b bih bhh ln3_w ln3_b wo bo total".split()
@@ -187,30 +188,6 @@ def _grad_layout(D, NO):
     return _GRAD_LAYOUT[(D, NO)]
 
 
-class direct_param_grads:
-    """``with direct_param_grads(): loss.backward()`` -- the fused ops add their weight gradients straight into the parameters'
-    existing ``.grad`` tensors (the views of a ``GradBucket``) from the kernel that produces them and hand autograd ``None``: one
-    launch instead of one accumulation launch per parameter tensor (18 per network pass, 540 per MAPPO update).  Only valid for
-    a plain ``backward()`` into ``.grad`` (not ``torch.autograd.grad``), hence opt-in by the trainer."""
-    active = False
-
-    def __enter__(self):
-        self._prev, direct_param_grads.active = direct_param_grads.active, True
-
-    def __exit__(self, *exc):
-        direct_param_grads.active = self._prev
-
-
-def _grad_targets(param_objs):
-    """The ``.grad`` tensors of the parameters when all of them can take a direct write, else None."""
-    if not direct_param_grads.active:
-        return None
-    gs = [p.grad for p in param_objs]
-    if all(g is not None and g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() for g in gs):
-        return gs
-    return None
-
-
 class _PPOTrunkFn(torch.autograd.Function):
     """mm_ppo_trunk2_fwd / mm_ppo_trunk2_bwd: fp16 operands on tcgen05, thread = row, weight gradients inside the backward."""
 
@@ -259,7 +236,7 @@ class _PPOTrunkFn(torch.autograd.Function):
         off = _grad_layout(D, NO)
         red = torch.empty(d["tile_rows"] * d["acc_cols"], dtype=torch.float32, device=dout.device)
         params = [p[k].detach().contiguous() for k in PARAM_ORDER]
-        targets = _grad_targets(ctx.param_objs) if all(ctx.needs_input_grad[7:]) else None
+        targets = grad_targets(ctx.param_objs, ctx.needs_input_grad[7:])
         if targets is not None:
             gptrs = (C.c_void_p * len(PARAM_ORDER))(*[g.data_ptr() for g in targets])
             _lib.check(_lib.lib().mm_ppo_trunk2_unfold_into(_lib.ptr(acc), n_ctas, _lib.ptr(scale), _lib.ptr(red), _ptr_array(params),
