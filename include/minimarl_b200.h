@@ -201,6 +201,12 @@ int mm_replay_gather(const float* obs, const float* share_obs, const float* acts
                      float* out_share_obs, float* out_acts, float* out_rewards, float* out_dones,
                      float* out_dones_env, int32_t T, int32_t S, int32_t B, int32_t A, int32_t D, int32_t SD,
                      int32_t NA, void* stream);
+/* The same with out_obs [T+1, A, B, D] and out_acts [T, A, B, NA] (rewards / dones stay agent-major): the (t, a * B + b) row order
+ * QMix.train_policy_on_batch stacks the agents into (qmix.py:96-100) -- permuted views of these are the reference's [A, T, B, d]. */
+int mm_replay_gather_stacked(const float* obs, const float* share_obs, const float* acts, const float* rewards, const float* dones,
+                             const float* dones_env, const int64_t* idx, float* out_obs, float* out_share_obs, float* out_acts,
+                             float* out_rewards, float* out_dones, float* out_dones_env, int32_t T, int32_t S, int32_t B,
+                             int32_t A, int32_t D, int32_t SD, int32_t NA, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Recurrent agent network forward, fused over the whole sequence:

@@ -65,6 +65,7 @@ SIGNATURES = {
     "mm_per_sample": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_double, _P, _P, _P]),
     "mm_per_sample_dev": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, _P]),
     "mm_replay_gather": (C.c_int, [_P] * 13 + [C.c_int32] * 7 + [_P]),
+    "mm_replay_gather_stacked": (C.c_int, [_P] * 13 + [C.c_int32] * 7 + [_P]),
     "mm_agentq_param_count": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "mm_agentq_param_offsets": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "mm_agentq_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_int32, C.c_int32,

@@ -209,8 +209,9 @@ class QMix:
         acts = _t(act_batch[p_id], dev)                              # [A, T, B, NA]
         A, T1, B = pol_obs.shape[0], pol_obs.shape[1], pol_obs.shape[2]
         T = T1 - 1
-        stacked_obs = torch.cat(list(pol_obs), dim=-2)               # [T+1, A*B, D], rows r = a*B + b
-        stacked_acts = torch.cat(list(acts), dim=-2)                 # [T, A*B, NA]
+        # rows r = a*B + b (torch.cat(list(x), dim=-2) in the reference); a view when the replay gathered in that order
+        stacked_obs = pol_obs.permute(1, 0, 2, 3).reshape(T1, A * B, -1)      # [T+1, A*B, D]
+        stacked_acts = acts.permute(1, 0, 2, 3).reshape(T, A * B, -1)         # [T, A*B, NA]
         total = A * B
         prev_acts = None
         if self.args.prev_act_inp:

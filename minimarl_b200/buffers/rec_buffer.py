@@ -97,18 +97,20 @@ class RecPolicyBuffer:
             if not torch.is_tensor(sample_inds) else sample_inds.to(device=self.device, dtype=torch.int64).contiguous()
         B, T, A = idx.numel(), self.episode_length, self.num_agents
         z = dict(dtype=torch.float32, device=self.device)
-        obs = torch.empty((A, T + 1, B, self.obs_dim), **z)
+        # obs / acts are STORED [T(+1), A, B, d] -- the (t, a * B + b) row order the learner stacks the agents into, so its
+        # torch.cat over the agents is a view -- and returned as the reference's [A, T(+1), B, d] through a permuted view
+        obs = torch.empty((T + 1, A, B, self.obs_dim), **z)
         share_obs = torch.empty((T + 1, B, self.share_obs_dim), **z)
-        acts = torch.empty((A, T, B, self.act_dim), **z)
+        acts = torch.empty((T, A, B, self.act_dim), **z)
         rewards = torch.empty((A, T, B, 1), **z)
         dones = torch.empty((A, T, B, 1), **z)
         dones_env = torch.empty((T, B, 1), **z)
         p = _lib.ptr
-        _lib.check(_lib.lib().mm_replay_gather(
+        _lib.check(_lib.lib().mm_replay_gather_stacked(
             p(self.obs), p(self.share_obs), p(self.acts), p(self.rewards), p(self.dones), p(self.dones_env),
             p(idx), p(obs), p(share_obs), p(acts), p(rewards), p(dones), p(dones_env),
             T, self.buffer_size, B, A, self.obs_dim, self.share_obs_dim, self.act_dim, _lib.stream()))
-        return obs, share_obs, acts, rewards, dones, dones_env, None
+        return obs.permute(1, 0, 2, 3), share_obs, acts.permute(1, 0, 2, 3), rewards, dones, dones_env, None
 
 
 class RecReplayBuffer:

@@ -107,6 +107,7 @@ struct GatherParams {
     float *o_obs, *o_share_obs, *o_acts, *o_rewards, *o_dones, *o_dones_env;
     const int64_t* idx;
     int T, S, B, A, D, SD, NA;
+    int stacked;   // 0: obs / acts agent-major [A, T(+1), B, d] (the reference's _cast); 1: [T(+1), A, B, d] = the learner's stacked rows
 };
 
 // Loads are issued in batches of 4 per lane BEFORE the dependent stores (read-only path, so the compiler
@@ -129,13 +130,13 @@ __device__ __forceinline__ void copy_run(const float* __restrict__ from, int n, 
     }
 }
 
-// src [TT, S, A, d] at (t, s, :, :) -> dst [A, TT, B, d] at (:, t, b, :)
+// src [TT, S, A, d] at (t, s, :, :) -> dst [A, TT, B, d] at (:, t, b, :), or (stacked) dst [TT, A, B, d] at (t, :, b, :)
 __device__ __forceinline__ void copy_agent_major(const float* __restrict__ src, float* __restrict__ dst,
                                                  int t, int b, int64_t s, int S, int B, int A, int d, int TT,
-                                                 int lane) {
+                                                 int lane, bool stacked = false) {
     const float* from = src + ((int64_t)t * S + s) * A * d;
-    const int64_t agent_stride = (int64_t)TT * B * d;
-    float* to = dst + ((int64_t)t * B + b) * d;
+    const int64_t agent_stride = stacked ? (int64_t)B * d : (int64_t)TT * B * d;
+    float* to = dst + (stacked ? ((int64_t)t * A * B + b) : ((int64_t)t * B + b)) * d;
     copy_run(from, A * d, to, [=](int k) { const int a = k / d; return (int64_t)a * agent_stride + (k - a * d); }, lane);
 }
 
@@ -145,11 +146,11 @@ __global__ void __launch_bounds__(256) replay_gather_kernel(const GatherParams p
     if (w >= (int64_t)(p.T + 1) * p.B) return;
     const int t = (int)(w / p.B), b = (int)(w - (int64_t)t * p.B);
     const int64_t s = p.idx[b];
-    copy_agent_major(p.obs, p.o_obs, t, b, s, p.S, p.B, p.A, p.D, p.T + 1, lane);
+    copy_agent_major(p.obs, p.o_obs, t, b, s, p.S, p.B, p.A, p.D, p.T + 1, lane, p.stacked != 0);
     copy_run(p.share_obs + ((int64_t)t * p.S + s) * p.SD, p.SD, p.o_share_obs + ((int64_t)t * p.B + b) * p.SD,
              [](int k) { return (int64_t)k; }, lane);
     if (t < p.T) {
-        copy_agent_major(p.acts, p.o_acts, t, b, s, p.S, p.B, p.A, p.NA, p.T, lane);
+        copy_agent_major(p.acts, p.o_acts, t, b, s, p.S, p.B, p.A, p.NA, p.T, lane, p.stacked != 0);
         copy_agent_major(p.rewards, p.o_rewards, t, b, s, p.S, p.B, p.A, 1, p.T, lane);
         copy_agent_major(p.dones, p.o_dones, t, b, s, p.S, p.B, p.A, 1, p.T, lane);
         if (lane == 0) p.o_dones_env[(int64_t)t * p.B + b] = __ldg(p.dones_env + (int64_t)t * p.S + s);
@@ -191,8 +192,8 @@ __global__ void __launch_bounds__(256) replay_gather_fast_kernel(const GatherPar
         if (lane < 2) { rw = __ldg(p.rewards + src_tb * 2 + lane); dn = __ldg(p.dones + src_tb * 2 + lane); }
         if (lane == 0) de = __ldg(p.dones_env + src_tb);
     }
-    const int64_t agent_stride_obs = (int64_t)T1 * p.B * D;
-    float* dobs = p.o_obs + dst_tb * D;
+    const int64_t agent_stride_obs = p.stacked ? (int64_t)p.B * D : (int64_t)T1 * p.B * D;
+    float* dobs = p.o_obs + (p.stacked ? (int64_t)t * 2 * p.B + b : dst_tb) * D;
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -210,7 +211,8 @@ __global__ void __launch_bounds__(256) replay_gather_fast_kernel(const GatherPar
         const int64_t agent_stride = (int64_t)p.T * p.B;
         if (lane < 2 * NA) {
             const int a = lane >= NA ? 1 : 0;
-            p.o_acts[(a * agent_stride + dst_tb) * NA + (lane - a * NA)] = ac;
+            const int64_t row = p.stacked ? ((int64_t)t * 2 + a) * p.B + b : a * agent_stride + dst_tb;
+            p.o_acts[row * NA + (lane - a * NA)] = ac;
         }
         if (lane < 2) {
             p.o_rewards[lane * agent_stride + dst_tb] = rw;
@@ -269,17 +271,17 @@ extern "C" int mm_per_sample_dev(const double* sum_tree, const double* min_tree,
     return mm::check_launch();
 }
 
-extern "C" int mm_replay_gather(const float* obs, const float* share_obs, const float* acts,
-                                const float* rewards, const float* dones, const float* dones_env,
-                                const int64_t* idx, float* out_obs, float* out_share_obs, float* out_acts,
-                                float* out_rewards, float* out_dones, float* out_dones_env, int32_t T,
-                                int32_t S, int32_t B, int32_t A, int32_t D, int32_t SD, int32_t NA,
-                                void* stream) {
+static int gather_launch(const float* obs, const float* share_obs, const float* acts,
+                         const float* rewards, const float* dones, const float* dones_env,
+                         const int64_t* idx, float* out_obs, float* out_share_obs, float* out_acts,
+                         float* out_rewards, float* out_dones, float* out_dones_env, int32_t T,
+                         int32_t S, int32_t B, int32_t A, int32_t D, int32_t SD, int32_t NA, int stacked,
+                         void* stream) {
     if (!obs || !share_obs || !acts || !rewards || !dones || !dones_env || !idx) return MM_ERR_BAD_ARG;
     if (!out_obs || !out_share_obs || !out_acts || !out_rewards || !out_dones || !out_dones_env) return MM_ERR_BAD_ARG;
     if (T <= 0 || S <= 0 || B <= 0 || A <= 0 || D <= 0 || SD <= 0 || NA <= 0) return MM_ERR_BAD_ARG;
     GatherParams p{obs, share_obs, acts, rewards, dones, dones_env, out_obs, out_share_obs, out_acts,
-                   out_rewards, out_dones, out_dones_env, idx, T, S, B, A, D, SD, NA};
+                   out_rewards, out_dones, out_dones_env, idx, T, S, B, A, D, SD, NA, stacked};
     const int64_t warps = (int64_t)(T + 1) * B;
     const int64_t blocks = (warps * 32 + 255) / 256;
     if (A == 2 && D <= 64 && SD <= 96 && NA <= 16)
@@ -287,4 +289,26 @@ extern "C" int mm_replay_gather(const float* obs, const float* share_obs, const 
     else
         replay_gather_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     return mm::check_launch();
+}
+
+extern "C" int mm_replay_gather(const float* obs, const float* share_obs, const float* acts,
+                                const float* rewards, const float* dones, const float* dones_env,
+                                const int64_t* idx, float* out_obs, float* out_share_obs, float* out_acts,
+                                float* out_rewards, float* out_dones, float* out_dones_env, int32_t T,
+                                int32_t S, int32_t B, int32_t A, int32_t D, int32_t SD, int32_t NA,
+                                void* stream) {
+    return gather_launch(obs, share_obs, acts, rewards, dones, dones_env, idx, out_obs, out_share_obs, out_acts, out_rewards,
+                         out_dones, out_dones_env, T, S, B, A, D, SD, NA, 0, stream);
+}
+
+// the same with out_obs [T+1, A, B, D] and out_acts [T, A, B, NA]: the row order (t, a * B + b) the learner stacks the agents
+// into (qmix.py:96-100), so that torch.cat over the agents becomes a view
+extern "C" int mm_replay_gather_stacked(const float* obs, const float* share_obs, const float* acts,
+                                        const float* rewards, const float* dones, const float* dones_env,
+                                        const int64_t* idx, float* out_obs, float* out_share_obs, float* out_acts,
+                                        float* out_rewards, float* out_dones, float* out_dones_env, int32_t T,
+                                        int32_t S, int32_t B, int32_t A, int32_t D, int32_t SD, int32_t NA,
+                                        void* stream) {
+    return gather_launch(obs, share_obs, acts, rewards, dones, dones_env, idx, out_obs, out_share_obs, out_acts, out_rewards,
+                         out_dones, out_dones_env, T, S, B, A, D, SD, NA, 1, stream);
 }

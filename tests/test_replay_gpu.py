@@ -117,3 +117,33 @@ def test_uniform_buffer_and_gather_roundtrip(cuda):
     assert torch.equal(dones_env, pb.dones_env)
     s = buf.sample(16)
     assert s[0]["policy_0"].shape == (A, T + 1, 16, D) and s[7] is None and s[8] is None
+
+
+def test_gather_layouts_agree(cuda):
+    """mm_replay_gather (agent-major [A, T, B, d], the reference's `_cast`) and mm_replay_gather_stacked ([T, A, B, d], what
+    the buffer stores so that the learner's torch.cat over the agents is a view) hold the same values, for the fast (A = 2) and the
+    generic (A = 3) kernel; the stacked rows are the reference's cat order r = a * B + b."""
+    from minimarl_b200 import _lib
+    for A, D, SD, NA in ((2, 47, 94, 5), (3, 10, 30, 4)):
+        T, S, B = 6, 40, 17
+        g = torch.Generator(device=cuda).manual_seed(A)
+        r = lambda *s: torch.rand(*s, device=cuda, generator=g)
+        obs, share, acts = r(T + 1, S, A, D), r(T + 1, S, SD), r(T, S, A, NA)
+        rew, dn, de = r(T, S, A, 1), r(T, S, A, 1), r(T, S, 1)
+        idx = torch.randint(0, S, (B,), device=cuda, generator=g)
+        outs = []
+        for name in ("mm_replay_gather", "mm_replay_gather_stacked"):
+            st = name.endswith("stacked")
+            o_obs = torch.empty((T + 1, A, B, D) if st else (A, T + 1, B, D), device=cuda)
+            o_acts = torch.empty((T, A, B, NA) if st else (A, T, B, NA), device=cuda)
+            o_sh, o_rw, o_dn, o_de = torch.empty(T + 1, B, SD, device=cuda), torch.empty(A, T, B, 1, device=cuda), \
+                torch.empty(A, T, B, 1, device=cuda), torch.empty(T, B, 1, device=cuda)
+            p = _lib.ptr
+            _lib.check(getattr(_lib.lib(), name)(p(obs), p(share), p(acts), p(rew), p(dn), p(de), p(idx), p(o_obs), p(o_sh), p(o_acts),
+                                                 p(o_rw), p(o_dn), p(o_de), T, S, B, A, D, SD, NA, _lib.stream()))
+            outs.append((o_obs.permute(1, 0, 2, 3) if st else o_obs, o_acts.permute(1, 0, 2, 3) if st else o_acts, o_sh, o_rw, o_dn, o_de))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+        assert torch.equal(outs[0][0], obs[:, idx].permute(2, 0, 1, 3))              # [A, T+1, B, D]
+        stacked = outs[1][0].permute(1, 0, 2, 3).reshape(T + 1, A * B, D)
+        assert stacked.data_ptr() == outs[1][0].data_ptr() and torch.equal(stacked, torch.cat(list(outs[0][0]), dim=-2))
