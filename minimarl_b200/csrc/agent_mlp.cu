@@ -549,20 +549,18 @@ __host__ __device__ inline GradLayout grad_layout(int D) {
     return g;
 }
 
-__device__ unsigned int g_unfold_ticket = 0;
 
 // every CTA sums a slice of the [n_ctas][128][ACC_COLS] accumulators into `red`; the last one turns them into gradients:
 // W' = W diag(g), b' = b + W beta  =>  dW = dW' diag(g) + db' beta^T, dg = sum_n dW'[n,:] W[n,:], dbeta = W^T db'
 struct GradPtrs { float* p[Q_N]; };
 
-__global__ void __launch_bounds__(256) agent_mlp_unfold_kernel(const float* __restrict__ acc, int n_ctas, const float* __restrict__ scale,
-                                                                float* __restrict__ red, const ParamPtrs q, const GradPtrs gp, int accumulate,
-                                                                int D) {
-    __shared__ bool last;
+// Two launches: (1) every thread sums one accumulator slot over the CTAs (16 loads in flight); (2) one thread per GRADIENT ELEMENT
+// turns the sums into the module's gradients.  (One kernel whose last CTA did step 2 alone spent 120 of its 140 us there.)
+__global__ void __launch_bounds__(256) agent_mlp_reduce_kernel(const float* __restrict__ acc, int n_ctas, const float* __restrict__ scale,
+                                                                float* __restrict__ red) {
     const float inv = 1.0f / scale[0];
     constexpr int kN = kRows * ACC_COLS;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < kN; i += gridDim.x * 256) {
-        // 16 independent loads in flight: with two the 148 round trips to L2 / HBM were the whole cost of this kernel
         float s[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) s[u] = 0.f;
@@ -578,59 +576,39 @@ __global__ void __launch_bounds__(256) agent_mlp_unfold_kernel(const float* __re
             for (int v = 0; v < u; ++v) s[v] += s[v + u];
         red[i] = s[0] * inv;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(&g_unfold_ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    if (threadIdx.x == 0) g_unfold_ticket = 0;
-    const volatile float* r = red;
-    // one destination per parameter tensor: a flat scratch buffer (=) or the parameters' own .grad storage (+=)
-    auto put = [&](int t, int i, float v) { gp.p[t][i] = accumulate ? gp.p[t][i] + v : v; };
+}
+
+// W' = W diag(g), b' = b + W beta  =>  dW = dW' diag(g) + db' beta^T, dg = sum_n dW'[n,:] W[n,:], dbeta = W^T db'
+__global__ void __launch_bounds__(256) agent_mlp_unfold_kernel(const float* __restrict__ r, const ParamPtrs q, const GradPtrs gp,
+                                                                int accumulate, int D) {
+    const GradLayout L = grad_layout(D);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= L.off[Q_N]) return;
+    int t = 0;
+    while (i >= L.off[t + 1]) ++t;
+    const int j = i - L.off[t];
     // T1: lanes xh2 feature | 1 [64] x gate column;  T2: lanes xh1 feature | 1 [64] x fc2 output;  T3: 64-row accumulator (row r in
     // lane 32 (r / 16) + r % 16): rows x0 feature | 1 [48] x fc1 output
     auto T1 = [&](int lane, int col) { return r[lane * ACC_COLS + col]; };
     auto T2 = [&](int lane, int col) { return r[lane * ACC_COLS + G3 + col]; };
     auto T3 = [&](int rr, int col) { return r[(32 * (rr >> 4) + (rr & 15)) * ACC_COLS + G3 + H + col]; };
-    const int tid = threadIdx.x;
-    for (int i = tid; i < H * D; i += 256) {
-        const int n = i / D, k = i - n * D;
-        put(Q_W1, i, T3(k, n) * q.p[Q_LN0W][k] + T3(K1, n) * q.p[Q_LN0B][k]);
+    float v = 0.f;
+    switch (t) {
+        case Q_W1: { const int n = j / D, k = j - n * D; v = T3(k, n) * q.p[Q_LN0W][k] + T3(K1, n) * q.p[Q_LN0B][k]; break; }
+        case Q_LN0W: for (int n = 0; n < H; ++n) v = fmaf(T3(j, n), q.p[Q_W1][n * D + j], v); break;
+        case Q_LN0B: for (int n = 0; n < H; ++n) v = fmaf(T3(K1, n), q.p[Q_W1][n * D + j], v); break;
+        case Q_B1: v = T3(K1, j); break;
+        case Q_W2: { const int n = j / H, k = j & (H - 1); v = T2(k, n) * q.p[Q_LN1W][k] + T2(H, n) * q.p[Q_LN1B][k]; break; }
+        case Q_B2: v = T2(H, j); break;
+        case Q_LN1W: for (int n = 0; n < H; ++n) v = fmaf(T2(j, n), q.p[Q_W2][n * H + j], v); break;
+        case Q_LN1B: for (int n = 0; n < H; ++n) v = fmaf(T2(H, n), q.p[Q_W2][n * H + j], v); break;
+        case Q_WIH: { const int g = j / H, k = j & (H - 1); v = T1(k, g) * q.p[Q_LN2W][k] + T1(H, g) * q.p[Q_LN2B][k]; break; }
+        case Q_BIH: v = T1(H, j); break;
+        case Q_LN2W: for (int g = 0; g < G3; ++g) v = fmaf(T1(j, g), q.p[Q_WIH][g * H + j], v); break;
+        default: for (int g = 0; g < G3; ++g) v = fmaf(T1(H, g), q.p[Q_WIH][g * H + j], v); break;      // Q_LN2B
     }
-    for (int k = tid; k < D; k += 256) {
-        float gw = 0.f, gb = 0.f;
-        for (int n = 0; n < H; ++n) {
-            gw = fmaf(T3(k, n), q.p[Q_W1][n * D + k], gw);
-            gb = fmaf(T3(K1, n), q.p[Q_W1][n * D + k], gb);
-        }
-        put(Q_LN0W, k, gw);
-        put(Q_LN0B, k, gb);
-    }
-    for (int i = tid; i < H * H; i += 256) {
-        const int n = i / H, k = i & (H - 1);
-        put(Q_W2, i, T2(k, n) * q.p[Q_LN1W][k] + T2(H, n) * q.p[Q_LN1B][k]);
-    }
-    for (int i = tid; i < G3 * H; i += 256) {
-        const int g = i / H, k = i & (H - 1);
-        put(Q_WIH, i, T1(k, g) * q.p[Q_LN2W][k] + T1(H, g) * q.p[Q_LN2B][k]);
-    }
-    for (int g = tid; g < G3; g += 256) put(Q_BIH, g, T1(H, g));
-    for (int k = tid; k < H; k += 256) {
-        put(Q_B1, k, T3(K1, k));
-        put(Q_B2, k, T2(H, k));
-        float gw1 = 0.f, gb1 = 0.f, gw2 = 0.f, gb2 = 0.f;
-        for (int n = 0; n < H; ++n) {
-            gw1 = fmaf(T2(k, n), q.p[Q_W2][n * H + k], gw1);
-            gb1 = fmaf(T2(H, n), q.p[Q_W2][n * H + k], gb1);
-        }
-        for (int g = 0; g < G3; ++g) {
-            gw2 = fmaf(T1(k, g), q.p[Q_WIH][g * H + k], gw2);
-            gb2 = fmaf(T1(H, g), q.p[Q_WIH][g * H + k], gb2);
-        }
-        put(Q_LN1W, k, gw1); put(Q_LN1B, k, gb1);
-        put(Q_LN2W, k, gw2); put(Q_LN2B, k, gb2);
-    }
+    // one destination per parameter tensor: a flat scratch buffer (=) or the parameters' own .grad storage (+=)
+    gp.p[t][j] = accumulate ? gp.p[t][j] + v : v;
 }
 
 __device__ unsigned int g_ticket_fwd = 0, g_ticket_bwd = 0;
@@ -689,7 +667,9 @@ static int unfold_launch(const float* acc, int32_t n_ctas, const float* scale, f
     if (!take_ptrs(params12, q) || !acc || !scale || !red || n_ctas < 1 || D < 1 || D > K1) return MM_ERR_BAD_ARG;
     for (int i = 0; i < Q_N; ++i)
         if (!gp.p[i]) return MM_ERR_BAD_ARG;
-    agent_mlp_unfold_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, gp, accumulate, D);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    agent_mlp_reduce_kernel<<<(kRows * ACC_COLS + 255) / 256, 256, 0, st>>>(acc, n_ctas, scale, red);
+    agent_mlp_unfold_kernel<<<(grad_layout(D).off[Q_N] + 255) / 256, 256, 0, st>>>(red, q, gp, accumulate, D);
     return mm::check_launch();
 }
 

@@ -954,21 +954,19 @@ __host__ __device__ inline GradLayout grad_layout(int D, int NO) {
     return g;
 }
 
-__device__ unsigned int g_unfold_ticket = 0;
 
 // grid x 256 threads: every CTA sums a slice of the [n_ctas][128][ACC_COLS] accumulators into `red`; the CTA that finishes
 // last (ticket counter) turns them into the parameter gradients (1 / scale applied, LayerNorm affines unfolded:
 // W' = W diag(g), b' = b + W beta  =>  dW = dW' diag(g) + db' beta^T, dg = sum_n dW'[n,:] W[n,:], dbeta = W^T db')
 struct GradPtrs { float* p[Q_N]; };
 
-__global__ void __launch_bounds__(256) trunk2_unfold_kernel(const float* __restrict__ acc, int n_ctas, const float* __restrict__ scale,
-                                                             float* __restrict__ red, const ParamPtrs q, const GradPtrs gp, int accumulate,
-                                                             int D, int NO) {
-    __shared__ bool last;
+// Two launches: (1) every thread sums one accumulator slot over the CTAs (16 loads in flight); (2) one thread per GRADIENT ELEMENT
+// turns the sums into the module's gradients (a single kernel whose last CTA did step 2 alone spent most of its 40 us there).
+__global__ void __launch_bounds__(256) trunk2_reduce_kernel(const float* __restrict__ acc, int n_ctas, const float* __restrict__ scale,
+                                                             float* __restrict__ red) {
     const float inv = 1.0f / scale[0];
     constexpr int kN = kRows * ACC_COLS;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < kN; i += gridDim.x * 256) {
-        // 16 independent loads in flight: with two the 148 round trips to L2 / HBM were the whole cost of this kernel
         float s[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) s[u] = 0.f;
@@ -984,76 +982,43 @@ __global__ void __launch_bounds__(256) trunk2_unfold_kernel(const float* __restr
             for (int v = 0; v < u; ++v) s[v] += s[v + u];
         red[i] = s[0] * inv;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(&g_unfold_ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    if (threadIdx.x == 0) g_unfold_ticket = 0;
-    const volatile float* r = red;
-    // one destination tensor per parameter: a flat scratch buffer, or the parameters' own .grad storage (then += : the values are
-    // ADDED to what is there, which is what autograd's AccumulateGrad would do with them one launch per tensor later)
-    auto put = [&](int t, int i, float v) { gp.p[t][i] = accumulate ? gp.p[t][i] + v : v; };
+}
+
+__global__ void __launch_bounds__(256) trunk2_unfold_kernel(const float* __restrict__ r, const ParamPtrs q, const GradPtrs gp,
+                                                             int accumulate, int D, int NO) {
+    const GradLayout L = grad_layout(D, NO);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= L.off[Q_N]) return;
+    int t = 0;
+    while (i >= L.off[t + 1]) ++t;
+    const int j = i - L.off[t];
     auto A = [&](int lane, int col) { return r[lane * ACC_COLS + col]; };
     auto B = [&](int lane, int col) { return r[lane * ACC_COLS + ACC_A_COLS + col]; };
     auto whh_lane = [](int g) { return g < 2 * H ? g : g + H; };      // dr | dz | (dn_i) | dn_h
-    const int tid = threadIdx.x;
-    // first Linear and LayerNorm(D)
-    for (int i = tid; i < H * D; i += 256) {
-        const int n = i / D, k = i - n * D;
-        put(Q_W1, i, B(n, k) * q.p[Q_LN0W][k] + B(n, 95) * q.p[Q_LN0B][k]);
+    float v = 0.f;
+    switch (t) {
+        case Q_W1: { const int n = j / D, k = j - n * D; v = B(n, k) * q.p[Q_LN0W][k] + B(n, 95) * q.p[Q_LN0B][k]; break; }
+        case Q_LN0W: for (int n = 0; n < H; ++n) v = fmaf(B(n, j), q.p[Q_W1][n * D + j], v); break;
+        case Q_LN0B: for (int n = 0; n < H; ++n) v = fmaf(B(n, 95), q.p[Q_W1][n * D + j], v); break;
+        case Q_B1: v = B(j, 95); break;
+        case Q_W2: { const int n = j / H, k = j & (H - 1); v = B(H + n, 48 + k) * q.p[Q_LN1W][k] + B(H + n, 95) * q.p[Q_LN1B][k]; break; }
+        case Q_B2: v = B(H + j, 95); break;
+        case Q_LN1W: for (int n = 0; n < H; ++n) v = fmaf(B(H + n, 48 + j), q.p[Q_W2][n * H + j], v); break;
+        case Q_LN1B: for (int n = 0; n < H; ++n) v = fmaf(B(H + n, 95), q.p[Q_W2][n * H + j], v); break;
+        case Q_WIH: { const int g = j / H, k = j & (H - 1); v = A(g, k) * q.p[Q_LN2W][k] + A(g, 64) * q.p[Q_LN2B][k]; break; }
+        case Q_WHH: { const int g = j / H, k = j & (H - 1); v = A(whh_lane(g), H + k); break; }
+        case Q_BIH: v = A(j, 64); break;
+        case Q_BHH: v = A(whh_lane(j), 64); break;
+        case Q_LN2W: for (int g = 0; g < 3 * H; ++g) v = fmaf(A(g, j), q.p[Q_WIH][g * H + j], v); break;
+        case Q_LN2B: for (int g = 0; g < 3 * H; ++g) v = fmaf(A(g, 64), q.p[Q_WIH][g * H + j], v); break;
+        case Q_LN3W: for (int o = 0; o < NO; ++o) v = fmaf(B(2 * H + j, 80 + o), q.p[Q_WO][o * H + j], v); break;
+        case Q_LN3B: for (int o = 0; o < NO; ++o) v = fmaf(B(96, 80 + o), q.p[Q_WO][o * H + j], v); break;
+        case Q_WO: { const int o = j / H, k = j & (H - 1); v = B(2 * H + k, 80 + o) * q.p[Q_LN3W][k] + B(96, 80 + o) * q.p[Q_LN3B][k]; break; }
+        default: v = B(96, 80 + j); break;                                                                // Q_BO
     }
-    for (int k = tid; k < D; k += 256) {
-        float gw = 0.f, gb = 0.f;
-        for (int n = 0; n < H; ++n) {
-            gw = fmaf(B(n, k), q.p[Q_W1][n * D + k], gw);
-            gb = fmaf(B(n, 95), q.p[Q_W1][n * D + k], gb);
-        }
-        put(Q_LN0W, k, gw);
-        put(Q_LN0B, k, gb);
-    }
-    // second Linear and LayerNorm 1
-    for (int i = tid; i < H * H; i += 256) {
-        const int n = i / H, k = i & (H - 1);
-        put(Q_W2, i, B(H + n, 48 + k) * q.p[Q_LN1W][k] + B(H + n, 95) * q.p[Q_LN1B][k]);
-    }
-    // GRU input weights and LayerNorm 2; hidden weights
-    for (int i = tid; i < 3 * H * H; i += 256) {
-        const int g = i / H, k = i & (H - 1);
-        put(Q_WIH, i, A(g, k) * q.p[Q_LN2W][k] + A(g, 64) * q.p[Q_LN2B][k]);
-        put(Q_WHH, i, A(whh_lane(g), H + k));
-    }
-    for (int g = tid; g < 3 * H; g += 256) {
-        put(Q_BIH, g, A(g, 64));
-        put(Q_BHH, g, A(whh_lane(g), 64));
-    }
-    for (int k = tid; k < H; k += 256) {
-        put(Q_B1, k, B(k, 95));
-        put(Q_B2, k, B(H + k, 95));
-        float gw1 = 0.f, gb1 = 0.f, gw2 = 0.f, gb2 = 0.f, gw3 = 0.f, gb3 = 0.f;
-        for (int n = 0; n < H; ++n) {
-            gw1 = fmaf(B(H + n, 48 + k), q.p[Q_W2][n * H + k], gw1);
-            gb1 = fmaf(B(H + n, 95), q.p[Q_W2][n * H + k], gb1);
-        }
-        for (int g = 0; g < 3 * H; ++g) {
-            gw2 = fmaf(A(g, k), q.p[Q_WIH][g * H + k], gw2);
-            gb2 = fmaf(A(g, 64), q.p[Q_WIH][g * H + k], gb2);
-        }
-        for (int o = 0; o < NO; ++o) {
-            gw3 = fmaf(B(2 * H + k, 80 + o), q.p[Q_WO][o * H + k], gw3);
-            gb3 = fmaf(B(96, 80 + o), q.p[Q_WO][o * H + k], gb3);
-        }
-        put(Q_LN1W, k, gw1); put(Q_LN1B, k, gb1);
-        put(Q_LN2W, k, gw2); put(Q_LN2B, k, gb2);
-        put(Q_LN3W, k, gw3); put(Q_LN3B, k, gb3);
-    }
-    // head
-    for (int i = tid; i < NO * H; i += 256) {
-        const int o = i / H, k = i & (H - 1);
-        put(Q_WO, i, B(2 * H + k, 80 + o) * q.p[Q_LN3W][k] + B(96, 80 + o) * q.p[Q_LN3B][k]);
-    }
-    for (int o = tid; o < NO; o += 256) put(Q_BO, o, B(96, 80 + o));
+    // one destination tensor per parameter: a flat scratch buffer (=), or the parameters' own .grad storage (+=: what autograd's
+    // AccumulateGrad would do with the values one launch per tensor later)
+    gp.p[t][j] = accumulate ? gp.p[t][j] + v : v;
 }
 
 // power-of-two gradient scale from max |dout|: scale2[0] = 2^floor(log2(64 / max)), scale2[1] = bits of the maximum (zeroed by the
@@ -1186,7 +1151,9 @@ static int unfold_launch(const float* acc, int32_t n_ctas, const float* scale, f
         if (!params18[i] || !gp.p[i]) return MM_ERR_BAD_ARG;
         q.p[i] = static_cast<const float*>(params18[i]);
     }
-    trunk2_unfold_kernel<<<148, 256, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_ctas, scale, red, q, gp, accumulate, D, NO);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    trunk2_reduce_kernel<<<(kRows * ACC_COLS + 255) / 256, 256, 0, st>>>(acc, n_ctas, scale, red);
+    trunk2_unfold_kernel<<<(grad_layout(D, NO).off[Q_N] + 255) / 256, 256, 0, st>>>(red, q, gp, accumulate, D, NO);
     return mm::check_launch();
 }
 
