@@ -157,14 +157,20 @@ __global__ void __launch_bounds__(256) gru_wgrad_unfold_kernel(const float* __re
     else            { col = i - G3 * H; lane = H; }
     const float* p = acc + (size_t)lane * G3 + col;
     const size_t stride = (size_t)kRows * G3;
-    float s0 = 0.f, s1 = 0.f;
+    float s[16];                                         // 16 independent loads in flight
+#pragma unroll
+    for (int u = 0; u < 16; ++u) s[u] = 0.f;
     int c = 0;
-    for (; c + 1 < n_ctas; c += 2) {
-        s0 += p[c * stride];
-        s1 += p[(c + 1) * stride];
+    for (; c + 15 < n_ctas; c += 16) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s[u] += p[(c + u) * stride];
     }
-    if (c < n_ctas) s0 += p[c * stride];
-    const float v = (s0 + s1) / scale[0];
+    for (; c < n_ctas; ++c) s[0] += p[c * stride];
+#pragma unroll
+    for (int u = 8; u > 0; u >>= 1)
+#pragma unroll
+        for (int w = 0; w < u; ++w) s[w] += s[w + u];
+    const float v = s[0] / scale[0];
     float* dst = i < G3 * H ? dw_hh + i : db_hh + col;
     *dst = accumulate ? *dst + v : v;
 }

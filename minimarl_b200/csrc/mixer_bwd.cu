@@ -408,20 +408,23 @@ __global__ void __launch_bounds__(256) qmixer_bwd_unfold_kernel(const float* __r
         case P_WB2: vi = AE + E + j; break;
         default:    vi = AE + E + HH; break;
     }
-    float s0 = 0.f, s1 = 0.f;
-    if (lane >= 0) {
-        const float* p = acc + (size_t)lane * ACC_COLS + col;
-        const size_t stride = (size_t)kRows * ACC_COLS;
-        int c = 0;
-        for (; c + 1 < n_ctas; c += 2) {
-            s0 += p[c * stride];
-            s1 += p[(c + 1) * stride];
-        }
-        if (c < n_ctas) s0 += p[c * stride];
-    } else {
-        for (int c = 0; c < n_ctas; ++c) s0 += vec[(size_t)c * VEC + vi];
+    // 16 independent loads in flight (the sum over the CTAs is a chain of L2 round trips otherwise)
+    const float* p = lane >= 0 ? acc + (size_t)lane * ACC_COLS + col : vec + vi;
+    const size_t stride = lane >= 0 ? (size_t)kRows * ACC_COLS : (size_t)VEC;
+    float s[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) s[u] = 0.f;
+    int c = 0;
+    for (; c + 15 < n_ctas; c += 16) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s[u] += p[(c + u) * stride];
     }
-    const float v = (s0 + s1) / (scale[0] * kScaleMul);
+    for (; c < n_ctas; ++c) s[0] += p[c * stride];
+#pragma unroll
+    for (int u = 8; u > 0; u >>= 1)
+#pragma unroll
+        for (int w = 0; w < u; ++w) s[w] += s[w + u];
+    const float v = s[0] / (scale[0] * kScaleMul);
     gp.p[t][j] = accumulate ? gp.p[t][j] + v : v;
 }
 

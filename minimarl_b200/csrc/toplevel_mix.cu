@@ -552,6 +552,7 @@ __global__ void mix_grad_reduce_kernel(const __grid_constant__ MixReduceArgs a) 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.P) return;
     float sum = 0.f;
+#pragma unroll 16                                     // same summation order, 16 loads in flight instead of 4
     for (int t = 0; t < a.n_tiles; ++t) sum += a.partials[(long long)t * a.P + i];
     int off = i;
 #pragma unroll

@@ -786,6 +786,7 @@ __global__ void qnet_grad_reduce_kernel(const __grid_constant__ ReduceArgs a) {
     if (i >= a.P) return;
     const float* p = a.partials + (long long)agent * a.n_tiles * a.P + i;
     float sum = 0.f;
+#pragma unroll 16                                     // same summation order, 16 loads in flight instead of 4
     for (int t = 0; t < a.n_tiles; ++t) sum += p[(long long)t * a.P];
     const int sizes[10] = {F1 * a.D, F1, F2 * F1, F2, 3 * HH * F2, 3 * HH * HH, 3 * HH, 3 * HH, a.NA * HH, a.NA};
     // QNetP order is w1 b1 w2 b2 wih whh bih bhh wo bo: the same as the partial layout
