@@ -322,11 +322,11 @@ def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    infos = None
+    infos, host_train = None, 0.0
     for k in range(steps):
         ev[k][0].record(); r.rollout()
         ev[k][1].record(); r.compute()
-        ev[k][2].record(); infos = r.train()
+        ev[k][2].record(); t_h = time.perf_counter(); infos = r.train(); host_train += time.perf_counter() - t_h
         ev[k][3].record()
     torch.cuda.synchronize()
     ms = [sum(e[i].elapsed_time(e[i + 1]) for e in ev) / steps for i in range(3)]
@@ -363,6 +363,13 @@ def mappo_iteration_section(dev, steps, n_envs=16384, T=128):
                        "what_bounds": "instruction issue of the per-row epilogues (ncu: issue slots 46 % / 35 % busy, tensor pipe 6 % / 12 %)"}
     out["ranks_in_sync"] = _ranks_in_sync(list(r.policy.actor.parameters()) + list(r.policy.critic.parameters()))
     out["launch_mode"] = "PPO epoch replayed as a CUDA graph" if r.trainer._graph_state is not None else "eager launches"
+    out["ms_ppo_update_host_enqueue"] = 1e3 * host_train / steps        # time R_MAPPO.train() keeps the host (no sync inside)
+    if world > 1:                                           # per rank: device time of the update, host time of the call
+        mine = torch.tensor([ms[2], 1e3 * host_train / steps], device=dev, dtype=torch.float64)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        out["ms_ppo_update_per_rank"] = [round(float(e[0]), 2) for e in every]
+        out["ms_ppo_update_host_enqueue_per_rank"] = [round(float(e[1]), 2) for e in every]
     del r, env
     torch.cuda.empty_cache()
     return out
