@@ -774,10 +774,17 @@ def run_ours(args, wl):
         except Exception as e:          # the headline line must survive a learner failure; report it
             learner = {"error": f"{type(e).__name__}: {e}"}
         torch.cuda.empty_cache()
+        s2 = ClockSampler(local) if rank == 0 else None      # clocks / throttle reasons while the tensor-core-heavy update runs
+        if s2:
+            s2.mark_begin()
         try:
             mappo_it = mappo_iteration_section(dev, max(2, args.learner_steps // 2))
         except Exception as e:
             mappo_it = {"error": f"{type(e).__name__}: {e}"}
+        if s2:
+            s2.mark_end()
+            c2 = s2.stop()
+            mappo_it["clocks"] = {k: c2[k] for k in ("sm_mhz", "sm_mhz_min_timed_region", "sm_max_mhz", "reasons", "samples_in_timed_region")}
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
