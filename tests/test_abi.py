@@ -46,6 +46,15 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu():
     cfg.n_envs, cfg.max_steps = 0, 100
     assert lib.mm_checkers_reset(None, None, None, ctypes.byref(cfg), None) == -1
     assert lib.mm_gae_returns(None, None, None, None, None, 0, 0, 0.99, 0.95, 1, 0, 1.0, 0.0, None) == -1
+    # the entry points added in round 2 validate before they launch as well (NULL pointers, unsupported shapes)
+    assert lib.mm_clip_adam_step(None, None, None, None, None, None, None, 10, 10, 1e-3, None, 0.9, 0.999, 1e-8, 0.0, 1.0, None) == -1
+    assert lib.mm_qmixer_bwd(None, None, None, None, None, None, None, None, 1, 128, 94, 2, None) == -1
+    assert lib.mm_qmixer_bwd_dims(95, (ctypes.c_int32 * 4)()) == -3            # odd state width: unsupported
+    assert lib.mm_ln_head_fwd(None, None, None, None, None, None, None, None, 10, 64, 5, None) == -1
+    assert lib.mm_gru_wgrad(None, None, None, None, None, None, 1, None, None, 0, 4, 8, 64, None) == -1
+    assert lib.mm_per_sample_dev(None, None, 8, 4, None, 2, None, None, None, None) == -1
+    assert lib.mm_replay_gather_stacked(*([None] * 13), 1, 1, 1, 2, 4, 8, 2, None) == -1
+    assert lib.mm_gru_wgrad_ctas(128 * 1000) >= 1 and lib.mm_qmixer_bwd_ctas(1) == 1
     with pytest.raises(RuntimeError, match="bad argument"):
         L.check(-1)
 
