@@ -49,3 +49,34 @@ def test_inference_path_saves_nothing(cuda):
     with torch.no_grad():
         out, hn = g(torch.randn(5, 64, 64, device=cuda))
     assert out.shape == (5, 64, 64) and hn.shape == (1, 64, 64) and not out.requires_grad
+
+
+@pytest.mark.parametrize("T,R,with_h0,accumulate", [(1, 5, True, False), (3, 77, True, True), (4, 200, False, False), (7, 128 * 160 + 9, True, False)])
+def test_gru_wgrad_matches_float64(cuda, T, R, with_h0, accumulate):
+    """mm_gru_wgrad (dW_hh / db_hh from dgi, dgh_n and the shifted h_seq on tcgen05, fp16 tiles with a power-of-two gradient
+    scale) against the float64 contraction: 2e-3 relative (Frobenius) -- 11-bit operands, fp32 accumulation over T * R rows;
+    ragged tiles, tiles straddling the first step, zero / given initial state, write and accumulate modes."""
+    from minimarl_b200 import _lib
+    H = 64
+    g = torch.Generator().manual_seed(T * 1000 + R)
+    dgi = torch.randn(T * R, 3 * H, generator=g) * 3e-4
+    dghn = torch.randn(T * R, H, generator=g) * 3e-4
+    h_seq = torch.tanh(torch.randn(T * R, H, generator=g))
+    h0 = torch.tanh(torch.randn(R, H, generator=g)) if with_h0 else None
+    hp = torch.cat([h0 if with_h0 else torch.zeros(R, H), h_seq[:-R]]).double()
+    G = torch.cat([dgi[:, :2 * H], dghn], dim=1).double()
+    dw_ref, db_ref = G.t() @ hp, G.sum(0)
+    lib = _lib.lib()
+    d = lambda x: x.to(cuda).contiguous()
+    dgi_d, dghn_d, h_d, h0_d = d(dgi), d(dghn), d(h_seq), (d(h0) if with_h0 else None)
+    scale = torch.empty(2, device=cuda)
+    _lib.check(lib.mm_ppo_trunk2_scale(_lib.ptr(dgi_d), dgi_d.numel(), _lib.ptr(scale), _lib.stream()))
+    n_ctas = lib.mm_gru_wgrad_ctas(T * R)
+    acc = torch.empty((n_ctas, 128, 3 * H), device=cuda)
+    base_w, base_b = torch.randn(3 * H, H, generator=g) * 1e-3, torch.randn(3 * H, generator=g) * 1e-3
+    dw, db = (d(base_w), d(base_b)) if accumulate else (torch.empty(3 * H, H, device=cuda), torch.empty(3 * H, device=cuda))
+    _lib.check(lib.mm_gru_wgrad(_lib.ptr(dgi_d), _lib.ptr(dghn_d), _lib.ptr(h_d), _lib.ptr(h0_d), _lib.ptr(scale), _lib.ptr(acc), n_ctas,
+                                _lib.ptr(dw), _lib.ptr(db), int(accumulate), T, R, H, _lib.stream()))
+    if accumulate:
+        dw_ref, db_ref = dw_ref + base_w.double(), db_ref + base_b.double()
+    assert _rel(dw.cpu().double(), dw_ref) < 2e-3 and _rel(db.cpu().double(), db_ref) < 2e-3
